@@ -1,0 +1,250 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes bindings of the two CPU oracles (see ``oracle/__init__.py``)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_LIB = os.path.join(_HERE, "libgcoracle.so")
+REF_LIB = os.path.join(_HERE, "_ref", "libgcref.so")
+REFERENCE_ROOT = "/root/reference"
+
+MAX_VERTICES = 40000
+MAX_INDICES = 60000
+MESH_TYPES = 5
+MAX_BLOCKS = 256
+
+
+def build(with_ref: bool | None = None) -> None:
+    """Compile libgcoracle.so, and _ref/libgcref.so when the reference tree is present."""
+    subprocess.check_call(["make", "-C", _HERE, "libgcoracle.so"], stdout=subprocess.DEVNULL)
+    if with_ref is None:
+        with_ref = os.path.isdir(os.path.join(REFERENCE_ROOT, "Code"))
+    if with_ref:
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+class BlockInfo(ctypes.Structure):
+    _fields_ = [("textures", ctypes.c_uint8 * 6), ("mesh_type", ctypes.c_uint8), ("cull", ctypes.c_uint8),
+                ("alpha", ctypes.c_uint8), ("invisible", ctypes.c_uint8), ("opaque", ctypes.c_uint8),
+                ("reserved", ctypes.c_uint8)]
+
+
+class _OrWorld(ctypes.Structure):
+    _fields_ = [("size_x", ctypes.c_int), ("size_z", ctypes.c_int),
+                ("blocks", ctypes.c_void_p), ("sun", ctypes.c_void_p), ("light", ctypes.c_void_p),
+                ("surface", ctypes.c_void_p), ("table", BlockInfo * MAX_BLOCKS),
+                ("table_count", ctypes.c_int), ("kill_zone_id", ctypes.c_int)]
+
+
+class _OrMesh(ctypes.Structure):
+    _fields_ = [("vertices", ctypes.c_uint8 * (MAX_VERTICES * 12)),
+                ("indices", (ctypes.c_uint16 * MAX_INDICES) * MESH_TYPES),
+                ("vert_count", ctypes.c_int32), ("index_count", ctypes.c_int32 * MESH_TYPES),
+                ("index_allocated", ctypes.c_int32 * MESH_TYPES), ("overflow", ctypes.c_int32)]
+
+
+class Mesh:
+    """One chunk's mesh as plain numpy: ``vertices`` (n,12) u8, ``indices[t]`` u16, ``overflow``."""
+
+    def __init__(self, vertices, indices, overflow=False, allocated=None):
+        self.vertices = vertices
+        self.indices = indices
+        self.overflow = bool(overflow)
+        self.allocated = allocated
+
+    @property
+    def vert_count(self):
+        return len(self.vertices)
+
+    @property
+    def quads(self):
+        return len(self.vertices) // 4
+
+    def same_as(self, other) -> bool:
+        return (self.vertices.shape == other.vertices.shape and np.array_equal(self.vertices, other.vertices)
+                and all(np.array_equal(a, b) for a, b in zip(self.indices, other.indices)))
+
+
+def fnv1a64(data: bytes | np.ndarray) -> str:
+    L = oracle_lib()
+    b = np.ascontiguousarray(data).view(np.uint8).reshape(-1) if isinstance(data, np.ndarray) else np.frombuffer(data, np.uint8)
+    return "%016x" % L.gcor_fnv1a64(b.ctypes.data_as(ctypes.c_void_p), b.size, 0)
+
+
+_olib = None
+_rlib = None
+
+
+def oracle_lib() -> ctypes.CDLL:
+    global _olib
+    if _olib is None:
+        if not os.path.exists(ORACLE_LIB):
+            build(with_ref=False)
+        L = ctypes.CDLL(ORACLE_LIB)
+        L.gcor_world_init.argtypes = [ctypes.POINTER(_OrWorld), ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4
+        L.gcor_build_chunk.argtypes = [ctypes.POINTER(_OrWorld)] + [ctypes.c_int] * 3 + [ctypes.POINTER(_OrMesh)]
+        L.gcor_chunk_overflowed.argtypes = [ctypes.POINTER(_OrWorld)] + [ctypes.c_int] * 7
+        L.gcor_bench_build.argtypes = [ctypes.POINTER(_OrWorld), ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
+        L.gcor_bench_build.restype = ctypes.c_double
+        L.gcor_fnv1a64.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
+        L.gcor_fnv1a64.restype = ctypes.c_uint64
+        L.gcor_default_block_table.argtypes = [ctypes.POINTER(BlockInfo), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+        _olib = L
+    return _olib
+
+
+def ref_lib() -> ctypes.CDLL:
+    global _rlib
+    if _rlib is None:
+        L = ctypes.CDLL(REF_LIB)
+        L.gcref_world_create.restype = ctypes.c_void_p
+        L.gcref_world_create.argtypes = [ctypes.c_int] * 4
+        L.gcref_world_destroy.argtypes = [ctypes.c_void_p]
+        L.gcref_block_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.gcref_block_light_steps.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.gcref_set_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
+        L.gcref_get_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
+        L.gcref_set_surface.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.gcref_get_surface.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.gcref_generate_flat.argtypes = [ctypes.c_void_p]
+        L.gcref_compute_surface.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.gcref_compute_surface_all.argtypes = [ctypes.c_void_p]
+        L.gcref_light_all.argtypes = [ctypes.c_void_p]
+        L.gcref_build_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
+        L.gcref_chunk_overflowed.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 7
+        L.gcref_bench_build.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
+        L.gcref_bench_build.restype = ctypes.c_double
+        _rlib = L
+    return _rlib
+
+
+def default_block_table():
+    """(table: list[BlockInfo] of 24, kill_zone_id) as restated in gc_mesh_cpu.c from Code/Block.cpp:139-276."""
+    arr = (BlockInfo * MAX_BLOCKS)()
+    n = ctypes.c_int(0)
+    kz = ctypes.c_int(0)
+    oracle_lib().gcor_default_block_table(arr, ctypes.byref(n), ctypes.byref(kz))
+    return arr, n.value, kz.value
+
+
+class OracleWorld:
+    """The restated oracle over a HostWorld's arrays (borrowed, not copied)."""
+
+    def __init__(self, host):
+        self.host = host
+        self._w = _OrWorld()
+        oracle_lib().gcor_world_init(ctypes.byref(self._w), host.size_x, host.size_z, host.blocks.ctypes.data,
+                                     host.sun.ctypes.data, host.light.ctypes.data, host.surface.ctypes.data)
+        self._m = _OrMesh()
+
+    def set_block_table(self, infos, kill_zone_id=20):
+        for i, b in enumerate(infos):
+            self._w.table[i] = b
+        self._w.table_count = len(infos)
+        self._w.kill_zone_id = kill_zone_id
+
+    def build_chunk(self, cx, cy, cz) -> Mesh:
+        m = self._m
+        oracle_lib().gcor_build_chunk(ctypes.byref(self._w), int(cx), int(cy), int(cz), ctypes.byref(m))
+        n = m.vert_count
+        verts = np.frombuffer(m.vertices, np.uint8, n * 12).reshape(n, 12).copy()
+        idx = [np.frombuffer(m.indices[t], np.uint16, m.index_count[t]).copy() for t in range(MESH_TYPES)]
+        return Mesh(verts, idx, m.overflow, [int(a) for a in m.index_allocated])
+
+    def chunk_overflowed(self, cx, cy, cz, x, y, z, total_vertices) -> bool:
+        return bool(oracle_lib().gcor_chunk_overflowed(ctypes.byref(self._w), cx, cy, cz, x, y, z, total_vertices))
+
+    def bench(self, coords: np.ndarray, threads: int):
+        coords = np.ascontiguousarray(coords, np.int32)
+        q = ctypes.c_int64(0)
+        sec = oracle_lib().gcor_bench_build(ctypes.byref(self._w), coords.ctypes.data, len(coords), threads, ctypes.byref(q))
+        return sec, q.value
+
+
+class RefWorld:
+    """The reference's own mesher (compiled verbatim) over a copy of a HostWorld (must be square)."""
+
+    def __init__(self, host=None, size=None, seed=1337):
+        self.L = ref_lib()
+        if host is not None:
+            assert host.size_x == host.size_z, "the reference window is square (World::size)"
+            size = host.size_x
+        self.size = size
+        self.h = ctypes.c_void_p(self.L.gcref_world_create(size, seed, 2**31 - 1, 2**31 - 1 - 64))
+        if host is not None:
+            self.upload(host)
+
+    def close(self):
+        if self.h:
+            self.L.gcref_world_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, host, light=True):
+        for cz in range(self.size):
+            for cx in range(self.size):
+                for cy in range(4):
+                    s = host.slot(cx, cy, cz)
+                    self.L.gcref_set_chunk(self.h, cx, cy, cz, host.blocks[s].ctypes.data,
+                                           host.sun[s].ctypes.data if light else None,
+                                           host.light[s].ctypes.data if light else None)
+                self.L.gcref_set_surface(self.h, cx, cz, host.surface[host.column(cx, cz)].ctypes.data)
+
+    def download(self, host):
+        for cz in range(self.size):
+            for cx in range(self.size):
+                for cy in range(4):
+                    s = host.slot(cx, cy, cz)
+                    self.L.gcref_get_chunk(self.h, cx, cy, cz, host.blocks[s].ctypes.data, host.sun[s].ctypes.data, host.light[s].ctypes.data)
+                self.L.gcref_get_surface(self.h, cx, cz, host.surface[host.column(cx, cz)].ctypes.data)
+
+    def generate_flat(self):
+        self.L.gcref_generate_flat(self.h)
+
+    def compute_surface(self):
+        self.L.gcref_compute_surface_all(self.h)
+
+    def compute_light(self):
+        self.L.gcref_light_all(self.h)
+
+    def block_table(self):
+        out = np.zeros(24 * 12, np.int32)
+        self.L.gcref_block_table(self.h, out.ctypes.data)
+        return out.reshape(24, 12)
+
+    def light_steps(self):
+        out = np.zeros(24, np.int32)
+        self.L.gcref_block_light_steps(self.h, out.ctypes.data)
+        return out
+
+    def build_chunk(self, cx, cy, cz) -> Mesh:
+        verts = np.zeros(MAX_VERTICES * 12, np.uint8)
+        idx = [np.zeros(MAX_INDICES, np.uint16) for _ in range(MESH_TYPES)]
+        idxp = (ctypes.c_void_p * MESH_TYPES)(*[a.ctypes.data for a in idx])
+        counts = np.zeros(11, np.int32)
+        self.L.gcref_build_chunk(self.h, int(cx), int(cy), int(cz), verts.ctypes.data, idxp, counts.ctypes.data)
+        n = int(counts[0])
+        return Mesh(verts[: n * 12].reshape(n, 12).copy(), [idx[t][: counts[1 + t]].copy() for t in range(MESH_TYPES)],
+                    False, [int(a) for a in counts[6:11]])
+
+    def chunk_overflowed(self, cx, cy, cz, x, y, z, total_vertices) -> bool:
+        return bool(self.L.gcref_chunk_overflowed(self.h, cx, cy, cz, x, y, z, total_vertices))
+
+    def bench(self, coords: np.ndarray, threads: int):
+        coords = np.ascontiguousarray(coords, np.int32)
+        q = ctypes.c_int64(0)
+        sec = self.L.gcref_bench_build(self.h, coords.ctypes.data, len(coords), threads, ctypes.byref(q))
+        return sec, q.value

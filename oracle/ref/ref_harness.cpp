@@ -1,0 +1,345 @@
+// TEST INFRASTRUCTURE ONLY — the "gold" oracle: the reference's own mesher, compiled verbatim.
+//
+// This translation unit #includes the reference's hot-path headers and sources where they
+// lie under /root/reference/Code (never copied into this repository) in the order of the
+// reference's unity build (Code/Main.cpp:92-143), minus the Win32/GL/imgui/audio bodies,
+// behind the stand-ins in shim_platform.h / shim_glm.h.  It then exposes a small C ABI so
+// tests (ctypes) and bench.py's `--impl reference` / `cpu_baseline` legs can drive
+//     generate (flat only) -> ComputeSurface -> SetLightNodes -> BuildChunkAsync
+// exactly as the reference does.  Built by oracle/Makefile into oracle/_ref/libgcref.so.
+// Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load it.
+
+#include "shim_platform.h"
+
+// Stand-ins for headers whose bodies need Win32 / imgui (Code/Main.cpp:92-100).
+#define DEBUG_SERVICES 0
+#define TIMED_FUNCTION
+#define BEGIN_BLOCK(ID)
+#define END_BLOCK(ID)
+#define DRAW_CHUNK_OUTLINE(chunk)
+#define TRACK_MESH
+#define RESET_TRACKED_MESHES
+
+#include "Utils.h"
+
+template <typename T>
+struct ObjectPool
+{
+    T* Get() { return new T(); }
+    void Return(T* item) { delete item; }
+};
+
+#include "Containers.h"
+#include "Random.h"
+
+struct UI { int unused; };
+struct AudioEngine { int unused; };
+
+#include "AssetBuilder.h"
+#include "Assets.h"
+#include "Input.h"
+#include "Mesh.h"
+#include "Block.h"
+#include "Particles.h"
+#include "Environment.h"
+#include "Generation.h"
+#include "World.h"
+#include "WorldIO.h"
+#include "Renderer.h"
+#include "Lighting.h"
+#include "WorldRender.h"
+#include "Simulation.h"
+#include "Async.h"
+#include "Commands.h"
+#include "GameState.h"
+
+// Link-time stubs for symbols the kept sources name but the mesher never reaches.
+static Sound GetSound(GameState*, SoundID) { return Sound{}; }
+static void PlaySound(Sound) {}
+static void IgnoreCollideFunc(GameState*, World*, vec3&, vec3, Block) {}
+static void BounceCollideFunc(GameState*, World*, vec3&, vec3, Block) {}
+static void DefaultCollideFunc(GameState*, World*, vec3&, vec3, Block) {}
+static void OverTimeDamageCollideFunc(GameState*, World*, vec3&, vec3, Block) {}
+static void KillCollideFunc(GameState*, World*, vec3&, vec3, Block) {}
+static bool OverlapsBlock(Player*, int, int, int) { return false; }
+static void QueueAsync(GameState*, AsyncFunc, World*, void*, AsyncCallback) {}
+static FrustumVisibility TestFrustum(Camera*, vec3, vec3) { return FRUSTUM_VISIBLE; }
+static bool LoadGroupFromDisk(World*, ChunkGroup*) { return false; }
+static void SaveGroup(GameState*, World*, void*) {}
+static void DeleteRegions(World*) {}
+static bool LoadWorldFileData(GameState*, World*) { return false; }
+static void RemoveFromRegion(World*, ChunkGroup*) {}
+static void SpawnPlayer(GameState*, World*, Player*, Rectf) {}
+static void TeleportPlayer(GameState*, WorldLocation) {}
+static void CreateBiomes(GameState*, World*) {}
+static void ResetEnvironment(GameState*, World*) {}
+static void SaveWorld(GameState*, World*) {}
+static void GenerateDungeonTerrain(World*, ChunkGroup*) {}
+static void MoveCamera(Camera*, vec3) {}
+static void UpdateCameraVectors(Camera*) {}
+static void UpdateViewMatrix(Camera*) {}
+static void GetCameraPlanes(Camera*) {}
+static void DeleteDirectory(char*) {}
+
+#include "Mesh.cpp"
+#include "Block.cpp"
+#include "World.cpp"
+#include "Lighting.cpp"
+#include "WorldRender.cpp"
+#include "Generation.cpp"
+
+#include <chrono>
+#include <thread>
+
+// ---------------------------------------------------------------------------------------
+// C ABI of the gold oracle.
+// ---------------------------------------------------------------------------------------
+struct GcRefWorld
+{
+    GameState* state;
+    World* world;
+    int size;
+};
+
+static ChunkGroup* RefGroup(GcRefWorld* w, int cx, int cz) { return w->world->groups[cz * w->size + cx]; }
+
+static void RefCopyOut(MeshData* md, uint8_t* verts, uint16_t* const* idx, int32_t* counts)
+{
+    counts[0] = md->vertCount;
+    if (verts) memcpy(verts, md->vertices, (size_t)md->vertCount * sizeof(VertexInfo));
+    for (int t = 0; t < MESH_TYPE_COUNT; t++)
+    {
+        MeshIndexData* d = md->indices[t];
+        counts[1 + t] = d ? d->count : 0;
+        // counts[6 + t]: was the index array allocated at all (WorldRender.cpp:454-459)?
+        counts[6 + t] = d ? 1 : 0;
+        if (d && idx && idx[t]) memcpy(idx[t], d->data, (size_t)d->count * sizeof(uint16_t));
+    }
+}
+
+static void RefResetMeshData(MeshData* md)
+{
+    md->vertCount = 0;
+    for (int t = 0; t < MESH_TYPE_COUNT; t++)
+    {
+        if (md->indices[t]) { delete md->indices[t]; md->indices[t] = nullptr; }
+    }
+}
+
+extern "C" {
+
+int gcref_sizeof(int what)
+{
+    switch (what)
+    {
+        case 0: return (int)sizeof(VertexInfo);
+        case 1: return (int)sizeof(MeshData);
+        case 2: return (int)sizeof(MeshIndexData);
+        case 3: return (int)sizeof(Chunk);
+        case 4: return (int)sizeof(ChunkGroup);
+        case 5: return (int)sizeof(BlockData);
+        case 6: return (int)offsetof(VertexInfo, pos);
+        case 7: return (int)offsetof(VertexInfo, uv);
+        case 8: return (int)offsetof(VertexInfo, color);
+        case 9: return (int)offsetof(VertexInfo, alpha);
+        case 10: return (int)offsetof(VertexInfo, reserved);
+        case 11: return MAX_VERTICES;
+        case 12: return MAX_INDICES;
+        case 13: return BLOCK_COUNT;
+    }
+    return -1;
+}
+
+// Column window like World::groups (World.cpp:153-160): size x size columns, all present.
+GcRefWorld* gcref_world_create(int size, int seed, int radius, int falloffRadius)
+{
+    GcRefWorld* w = new GcRefWorld;
+    w->state = new GameState();
+    w->world = new World();
+    w->size = size;
+    World* world = w->world;
+    world->size = size;
+    world->loadRange = size / 2;
+    world->totalGroups = size * size;
+    world->groups = (ChunkGroup**)calloc((size_t)world->totalGroups, sizeof(ChunkGroup*));
+    world->properties.seed = seed;
+    world->properties.radius = radius;
+    world->properties.biome = BIOME_FLAT;
+    world->falloffRadius = falloffRadius;
+    CreateBlockData(w->state, world->blockData);
+
+    for (int cz = 0; cz < size; cz++)
+    {
+        for (int cx = 0; cx < size; cx++)
+        {
+            // As CreateChunkGroup (World.cpp:624-643) without the async load.
+            ChunkGroup* group = (ChunkGroup*)calloc(1, sizeof(ChunkGroup));
+            group->pos = ivec3(cx, 0, cz);
+            group->active = true;
+            for (int i = 0; i < WORLD_CHUNK_HEIGHT; i++)
+            {
+                Chunk* chunk = group->chunks + i;
+                chunk->lcPos = ivec3(cx, i, cz);
+                chunk->lwPos = LChunkToLWorldP(chunk->lcPos);
+                chunk->group = group;
+            }
+            group->state = GROUP_LOADED;
+            world->groups[cz * size + cx] = group;
+        }
+    }
+    return w;
+}
+
+void gcref_world_destroy(GcRefWorld* w)
+{
+    for (int i = 0; i < w->world->totalGroups; i++) free(w->world->groups[i]);
+    free(w->world->groups);
+    delete w->world;
+    delete w->state;
+    delete w;
+}
+
+// Dump the fields of World::blockData the mesher reads (Block.cpp:5-68).
+// out[b*12 + 0..5] textures, 6 meshType, 7 cull, 8 alpha, 9 invisible, 10 opaque, 11 lightEmitted
+void gcref_block_table(GcRefWorld* w, int32_t* out)
+{
+    for (int b = 0; b < BLOCK_COUNT; b++)
+    {
+        BlockData& d = w->world->blockData[b];
+        for (int f = 0; f < 6; f++) out[b * 12 + f] = d.textures[f];
+        out[b * 12 + 6] = (int)d.meshType;
+        out[b * 12 + 7] = d.cull;
+        out[b * 12 + 8] = d.alpha;
+        out[b * 12 + 9] = d.invisible ? 1 : 0;
+        out[b * 12 + 10] = IsOpaque(w->world, (Block)b) ? 1 : 0;
+        out[b * 12 + 11] = d.lightEmitted;
+    }
+}
+
+void gcref_block_light_steps(GcRefWorld* w, int32_t* out)
+{
+    for (int b = 0; b < BLOCK_COUNT; b++) out[b] = w->world->blockData[b].lightStep;
+}
+
+void gcref_set_chunk(GcRefWorld* w, int cx, int cy, int cz, const uint16_t* blocks, const uint8_t* sun, const uint8_t* light)
+{
+    Chunk* c = RefGroup(w, cx, cz)->chunks + cy;
+    if (blocks) memcpy(c->blocks, blocks, sizeof(c->blocks));
+    if (sun) memcpy(c->sunlight, sun, sizeof(c->sunlight));
+    if (light) memcpy(c->blockLight, light, sizeof(c->blockLight));
+}
+
+void gcref_get_chunk(GcRefWorld* w, int cx, int cy, int cz, uint16_t* blocks, uint8_t* sun, uint8_t* light)
+{
+    Chunk* c = RefGroup(w, cx, cz)->chunks + cy;
+    if (blocks) memcpy(blocks, c->blocks, sizeof(c->blocks));
+    if (sun) memcpy(sun, c->sunlight, sizeof(c->sunlight));
+    if (light) memcpy(light, c->blockLight, sizeof(c->blockLight));
+}
+
+void gcref_set_surface(GcRefWorld* w, int cx, int cz, const uint8_t* surface) { memcpy(RefGroup(w, cx, cz)->surface, surface, CHUNK_SIZE_2); }
+void gcref_get_surface(GcRefWorld* w, int cx, int cz, uint8_t* surface) { memcpy(surface, RefGroup(w, cx, cz)->surface, CHUNK_SIZE_2); }
+
+// GenerateFlatTerrain (Generation.cpp:772-836) on every column; no noise involved when radius is huge.
+void gcref_generate_flat(GcRefWorld* w)
+{
+    for (int i = 0; i < w->world->totalGroups; i++) GenerateFlatTerrain(w->world, w->world->groups[i]);
+}
+
+// ComputeSurface (Lighting.cpp:19-26) on one column / all columns.
+void gcref_compute_surface(GcRefWorld* w, int cx, int cz)
+{
+    ChunkGroup* g = RefGroup(w, cx, cz);
+    memset(g->surface, 0, sizeof(g->surface));
+    ComputeSurface(g);
+}
+
+void gcref_compute_surface_all(GcRefWorld* w)
+{
+    for (int cz = 0; cz < w->size; cz++) for (int cx = 0; cx < w->size; cx++) gcref_compute_surface(w, cx, cz);
+}
+
+// SetLightNodes (Lighting.cpp:247-281) for all non-edge columns, z-major then x (a fixed order;
+// the reference's order is thread-timing dependent, WorldRender.cpp:255-260).
+void gcref_light_all(GcRefWorld* w)
+{
+    for (int cz = 1; cz < w->size - 1; cz++)
+    {
+        for (int cx = 1; cx < w->size - 1; cx++)
+        {
+            ChunkGroup* g = RefGroup(w, cx, cz);
+            Queue<ivec3> sunNodes(MAX_LIGHT_NODES);
+            Queue<ivec3> lightNodes(MAX_LIGHT_NODES);
+            SetLightNodes(w->world, g, sunNodes, lightNodes);
+            g->state = GROUP_PREPROCESSED;
+        }
+    }
+}
+
+// BuildChunkAsync (WorldRender.cpp:6-27) on one chunk with a fresh MeshData.
+// verts: >= 40000*12 bytes (or null), idx[t]: >= 60000 u16 each (or null),
+// counts[11]: vertCount, count[5], allocated[5].  Returns chunk->totalVertices.
+int gcref_build_chunk(GcRefWorld* w, int cx, int cy, int cz, uint8_t* verts, uint16_t* const* idx, int32_t* counts)
+{
+    Chunk* chunk = RefGroup(w, cx, cz)->chunks + cy;
+    MeshData* md = new MeshData();
+    md->vertCount = 0;
+    chunk->meshData = md;
+    BuildChunkAsync(w->state, w->world, chunk);
+    RefCopyOut(md, verts, idx, counts);
+    RefResetMeshData(md);
+    delete md;
+    chunk->meshData = nullptr;
+    return chunk->totalVertices;
+}
+
+// ChunkOverflowed (WorldRender.cpp:412-439).
+int gcref_chunk_overflowed(GcRefWorld* w, int cx, int cy, int cz, int x, int y, int z, int totalVertices)
+{
+    Chunk* chunk = RefGroup(w, cx, cz)->chunks + cy;
+    chunk->totalVertices = totalVertices;
+    return ChunkOverflowed(w->world, chunk, x, y, z) ? 1 : 0;
+}
+
+// Multi-threaded mesh-build timing: the reference's one-chunk-per-job queue (Async.cpp:5-35) restated as
+// an atomic counter; each worker owns a private MeshData (the pool hands one per job, WorldRender.cpp:61-67).
+// coords: n x (cx,cy,cz).  Returns seconds; *quadsOut = total quads.
+double gcref_bench_build(GcRefWorld* w, const int32_t* coords, int n, int threads, int64_t* quadsOut)
+{
+    std::atomic<int> next(0);
+    std::atomic<int64_t> quads(0);
+    std::vector<MeshData*> mds((size_t)threads);
+    for (int t = 0; t < threads; t++) { mds[t] = new MeshData(); }
+
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+    {
+        pool.emplace_back([&, t]()
+        {
+            MeshData* md = mds[t];
+            int64_t local = 0;
+            for (;;)
+            {
+                int i = next.fetch_add(1);
+                if (i >= n) break;
+                Chunk* chunk = RefGroup(w, coords[i * 3 + 0], coords[i * 3 + 2])->chunks + coords[i * 3 + 1];
+                md->vertCount = 0;
+                chunk->meshData = md;
+                BuildChunkAsync(w->state, w->world, chunk);
+                local += md->vertCount / 4;
+                RefResetMeshData(md);
+                chunk->meshData = nullptr;
+            }
+            quads += local;
+        });
+    }
+    for (auto& th : pool) th.join();
+    auto t1 = std::chrono::steady_clock::now();
+
+    for (int t = 0; t < threads; t++) delete mds[t];
+    if (quadsOut) *quadsOut = quads.load();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
