@@ -1,0 +1,549 @@
+// gcmesh — C ABI (include/gcmesh.h) over the sm_100a kernels.  C-style C++ host code: contexts, the device
+// world (the window of columns), batch arenas, tensor-map encoding, submission and result hand-off.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "gcmesh_kernel.cuh"
+
+using namespace gc;
+
+namespace
+{
+thread_local std::string g_error;
+
+int fail(int status, const char* what, const char* detail = nullptr)
+{
+    g_error = what;
+    if (detail) { g_error += ": "; g_error += detail; }
+    return status;
+}
+
+#define GC_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) return fail(GC_ERR_CUDA, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// The reference's 24 block types (Code/Block.cpp:139-276; texture layers Code/Assets.h:7-34).
+void solid(GcBlockInfo* b, int top, int bottom, int side)
+{
+    memset(b, 0, sizeof(*b));
+    b->textures[0] = (uint8_t)top; b->textures[1] = (uint8_t)bottom;
+    b->textures[2] = b->textures[3] = b->textures[4] = b->textures[5] = (uint8_t)side;
+    b->alpha = 255; b->opaque = 1;                      // CreateDefaultBlock, Block.cpp:128-137
+}
+
+void reference_block_table(GcBlockInfo* t)
+{
+    solid(&t[0], 0, 0, 0); t[0].invisible = 1; t[0].cull = GC_CULL_INVISIBLE; t[0].opaque = 0;      // AIR
+    solid(&t[1], 8, 6, 9);                                                                          // GRASS
+    solid(&t[2], 6, 6, 6);                                                                          // DIRT
+    solid(&t[3], 48, 48, 48);                                                                       // STONE
+    solid(&t[4], 5, 5, 5);                                                                          // CRATE
+    solid(&t[5], 44, 44, 44);                                                                       // SAND
+    solid(&t[6], 49, 49, 49);                                                                       // STONE_BRICK
+    solid(&t[7], 42, 42, 42);                                                                       // METAL_CRATE
+    solid(&t[8], 51, 51, 51); t[8].mesh_type = GC_MESH_FLUID; t[8].cull = GC_CULL_FLUID; t[8].alpha = 127; t[8].opaque = 0;   // WATER
+    solid(&t[9], 60, 60, 59);                                                                       // WOOD
+    solid(&t[10], 21, 21, 21);                                                                      // LEAVES
+    solid(&t[11], 3, 3, 3);                                                                         // CLAY
+    solid(&t[12], 46, 6, 47);                                                                       // SNOW
+    solid(&t[13], 10, 10, 10); t[13].mesh_type = GC_MESH_TRANSPARENT; t[13].cull = GC_CULL_TRANSPARENT; t[13].alpha = 190; t[13].opaque = 0;  // ICE
+    solid(&t[14], 12, 12, 12); t[14].opaque = 0;                                                    // LANTERN
+    solid(&t[15], 50, 50, 50);                                                                      // TRAMPOLINE
+    solid(&t[16], 2, 0, 1);                                                                         // CACTUS
+    solid(&t[17], 22, 22, 22); t[17].mesh_type = GC_MESH_MAGMA; t[17].opaque = 0;                   // MAGMA
+    solid(&t[18], 4, 4, 4);                                                                         // COOLED_MAGMA
+    solid(&t[19], 43, 43, 43);                                                                      // OBSIDIAN
+    solid(&t[20], 0, 0, 0); t[20].invisible = 1; t[20].cull = GC_CULL_INVISIBLE; t[20].opaque = 0;  // KILL_ZONE
+    solid(&t[21], 13, 13, 13); t[21].mesh_type = GC_MESH_FLUID; t[21].cull = GC_CULL_FLUID; t[21].alpha = 127; t[21].opaque = 0;  // LAVA
+    solid(&t[22], 7, 7, 7); t[22].mesh_type = GC_MESH_CUTOUT; t[22].cull = GC_CULL_CUTOUT; t[22].opaque = 0;                      // GLASS
+    solid(&t[23], 45, 45, 45);                                                                      // SHOCKER
+}
+}  // namespace
+
+struct GcContext
+{
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int num_sms;
+    EncodeTiledFn encode;
+    DeviceTables* d_tables;
+    int use_tma;
+};
+
+struct GcWorld
+{
+    GcContext* ctx;
+    int size_x, size_z;
+    size_t n_cols, n_slots;
+    uint16_t* d_blocks;
+    uint8_t* d_sun;
+    uint8_t* d_light;
+    uint8_t* d_surface;
+    MeshTensorMaps maps;
+};
+
+struct GcBatch
+{
+    GcContext* ctx;
+    int max_chunks;
+    uint64_t max_quads;
+    GcChunkCoord* d_coords;
+    GcChunkOut* d_out;
+    uint8_t* d_vertices;
+    uint16_t* d_indices;
+    unsigned long long* d_cursor;   // [0] quad cursor
+    int32_t* d_counters;            // [0] work counter, [1] error flag
+    GcChunkOut* h_out;              // pinned
+    GcChunkCoord* h_coords;         // pinned staging for coords
+    unsigned long long* h_cursor;   // pinned
+    int32_t* h_counters;            // pinned
+    int n;
+    int state;                      // 0 idle, 1 submitted, 2 waited
+    int launches;
+    cudaEvent_t ev_start, ev_stop, ev_done;
+};
+
+static int encode_map(GcContext* ctx, CUtensorMap* map, CUtensorMapDataType type, int elem_bytes, void* base, size_t n_slots, int box_y)
+{
+    // (x = 32, y = 64, z = 32, slot) over one brick arena; the reference's brick index x + 32*(y + 64*z) (World.cpp:278-281)
+    cuuint64_t dims[4] = { 32, 64, 32, (cuuint64_t)n_slots };
+    cuuint64_t strides[3] = { (cuuint64_t)(32 * elem_bytes), (cuuint64_t)(32 * 64 * elem_bytes), (cuuint64_t)(GC_CHUNK_SIZE_3 * elem_bytes) };
+    cuuint32_t box[4] = { 32, (cuuint32_t)box_y, 1, 1 };
+    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = ctx->encode(map, type, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+    {
+        char buf[64];
+        snprintf(buf, sizeof(buf), "CUresult %d", (int)r);
+        return fail(GC_ERR_CUDA, "cuTensorMapEncodeTiled", buf);
+    }
+    return GC_OK;
+}
+
+static int upload_tables(GcContext* ctx, const GcBlockInfo* table, int n, int kill_zone_id)
+{
+    DeviceTables* h = new (std::nothrow) DeviceTables;
+    if (!h) return fail(GC_ERR_ARG, "out of host memory");
+    for (int i = 0; i < 256; i++)
+    {
+        // ids beyond the table read as AIR (the reference asserts block < BLOCK_COUNT, World.cpp:294)
+        const GcBlockInfo& b = table[i < n ? i : 0];
+        const int emits = (i != 0) && (i < n) && !b.invisible;   // BuildChunkAsync skips AIR and invisible, WorldRender.cpp:19-22
+        const uint32_t c = class_byte(b.cull, b.opaque, b.mesh_type, emits);
+        h->cls8[i] = (uint8_t)c;
+        h->lut[i] = spread_class(c);
+        h->mat[i].lo = (uint32_t)b.textures[0] | ((uint32_t)b.textures[1] << 8) | ((uint32_t)b.textures[2] << 16) | ((uint32_t)b.textures[3] << 24);
+        h->mat[i].hi = (uint32_t)b.textures[4] | ((uint32_t)b.textures[5] << 8) | ((uint32_t)b.alpha << 16);
+    }
+    h->kill_zone = kill_zone_id;
+    cudaError_t e = cudaMemcpyAsync(ctx->d_tables, h, sizeof(DeviceTables), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    delete h;
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "upload block table", cudaGetErrorString(e));
+    return GC_OK;
+}
+
+extern "C" {
+
+const char* gcmesh_version(void) { return "gcmesh 0.1 (sm_100a)"; }
+const char* gcmesh_last_error(void) { return g_error.c_str(); }
+
+int gcmesh_default_block_table(GcBlockInfo* table, int* n, int* kill_zone_id)
+{
+    if (!table) return fail(GC_ERR_ARG, "table is null");
+    reference_block_table(table);
+    if (n) *n = 24;                    // BLOCK_COUNT, Block.h:36
+    if (kill_zone_id) *kill_zone_id = 20;  // BLOCK_KILL_ZONE, Block.h:32
+    return GC_OK;
+}
+
+int gcmesh_create(int device, void* stream, GcContext** out)
+{
+    if (!out) return fail(GC_ERR_ARG, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(GC_ERR_CUDA, "no usable CUDA device (gcmesh has no CPU fallback)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(GC_ERR_ARG, "device index out of range");
+    GC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(GC_ERR_CUDA, "gcmesh kernels are built for sm_100a only", prop.name);
+
+    GcContext* ctx = new (std::nothrow) GcContext();
+    if (!ctx) return fail(GC_ERR_ARG, "out of host memory");
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->own_stream = stream == nullptr;
+    ctx->stream = (cudaStream_t)stream;
+    const char* env = getenv("GCMESH_NO_TMA");
+    ctx->use_tma = (env && env[0] == '1') ? 0 : 1;
+    if (ctx->own_stream) { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); if (e != cudaSuccess) { delete ctx; return fail(GC_ERR_CUDA, "cudaStreamCreate", cudaGetErrorString(e)); } }
+
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) { delete ctx; return fail(GC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found"); }
+    ctx->encode = (EncodeTiledFn)fn;
+
+    e = cudaMalloc(&ctx->d_tables, sizeof(DeviceTables));
+    if (e != cudaSuccess) { delete ctx; return fail(GC_ERR_CUDA, "cudaMalloc tables", cudaGetErrorString(e)); }
+    GcBlockInfo table[24];
+    reference_block_table(table);
+    int st = upload_tables(ctx, table, 24, 20);
+    if (st != GC_OK) { cudaFree(ctx->d_tables); delete ctx; return st; }
+    *out = ctx;
+    return GC_OK;
+}
+
+int gcmesh_destroy(GcContext* ctx)
+{
+    if (!ctx) return GC_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_tables);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GC_OK;
+}
+
+int gcmesh_set_stream(GcContext* ctx, void* stream)
+{
+    if (!ctx) return fail(GC_ERR_ARG, "ctx is null");
+    if (ctx->own_stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    ctx->stream = (cudaStream_t)stream;
+    return GC_OK;
+}
+
+int gcmesh_set_block_table(GcContext* ctx, const GcBlockInfo* table, int n, int kill_zone_id)
+{
+    if (!ctx || !table) return fail(GC_ERR_ARG, "null argument");
+    if (n < 1 || n > GC_MAX_BLOCK_TYPES) return fail(GC_ERR_ARG, "table size must be 1..256");
+    if (kill_zone_id < 0 || kill_zone_id >= n) return fail(GC_ERR_ARG, "kill_zone_id outside the table");
+    for (int i = 0; i < n; i++)
+    {
+        if (table[i].cull > GC_CULL_INVISIBLE) return fail(GC_ERR_ARG, "cull must be 0..4 (CullValue, Block.h:40-47)");
+        if (table[i].mesh_type >= GC_MESH_TYPE_COUNT) return fail(GC_ERR_ARG, "mesh_type must be 0..4 (BlockMeshType, Mesh.h:8-16)");
+    }
+    GC_CUDA(cudaSetDevice(ctx->device));
+    return upload_tables(ctx, table, n, kill_zone_id);
+}
+
+int gcmesh_synchronize(GcContext* ctx)
+{
+    if (!ctx) return fail(GC_ERR_ARG, "ctx is null");
+    GC_CUDA(cudaSetDevice(ctx->device));
+    GC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int gcmesh_world_create(GcContext* ctx, int size_x, int size_z, GcWorld** out)
+{
+    if (!ctx || !out) return fail(GC_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (size_x < 3 || size_z < 3) return fail(GC_ERR_ARG, "a window needs at least 3x3 columns (edge columns are halo only)");
+    GC_CUDA(cudaSetDevice(ctx->device));
+    GcWorld* w = new (std::nothrow) GcWorld();
+    if (!w) return fail(GC_ERR_ARG, "out of host memory");
+    w->ctx = ctx; w->size_x = size_x; w->size_z = size_z;
+    w->n_cols = (size_t)size_x * size_z;
+    w->n_slots = w->n_cols * GC_WORLD_CHUNK_HEIGHT;
+    cudaError_t e = cudaMalloc(&w->d_blocks, w->n_slots * GC_CHUNK_SIZE_3 * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_sun, w->n_slots * GC_CHUNK_SIZE_3);
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_light, w->n_slots * GC_CHUNK_SIZE_3);
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_surface, w->n_cols * GC_CHUNK_SIZE_2);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w->d_blocks, 0, w->n_slots * GC_CHUNK_SIZE_3 * 2, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w->d_sun, 0, w->n_slots * GC_CHUNK_SIZE_3, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w->d_light, 0, w->n_slots * GC_CHUNK_SIZE_3, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w->d_surface, 0, w->n_cols * GC_CHUNK_SIZE_2, ctx->stream);
+    if (e != cudaSuccess) { gcmesh_world_destroy(w); return fail(GC_ERR_CUDA, "world allocation", cudaGetErrorString(e)); }
+    int st = GC_OK;
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_slab, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots, 64);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_row, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots, 1);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots, 64);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_row, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots, 1);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.light_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_light, w->n_slots, 64);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.light_row, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_light, w->n_slots, 1);
+    if (st != GC_OK) { gcmesh_world_destroy(w); return st; }
+    *out = w;
+    return GC_OK;
+}
+
+int gcmesh_world_destroy(GcWorld* w)
+{
+    if (!w) return GC_OK;
+    cudaSetDevice(w->ctx->device);
+    cudaStreamSynchronize(w->ctx->stream);
+    cudaFree(w->d_blocks); cudaFree(w->d_sun); cudaFree(w->d_light); cudaFree(w->d_surface);
+    delete w;
+    return GC_OK;
+}
+
+static bool column_ok(const GcWorld* w, int cx, int cz) { return cx >= 0 && cx < w->size_x && cz >= 0 && cz < w->size_z; }
+
+int gcmesh_world_upload_chunk(GcWorld* w, int cx, int cy, int cz, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    if (!column_ok(w, cx, cz) || cy < 0 || cy >= GC_WORLD_CHUNK_HEIGHT) return fail(GC_ERR_ARG, "chunk position outside the window");
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    const size_t slot = ((size_t)cz * w->size_x + cx) * GC_WORLD_CHUNK_HEIGHT + cy;
+    if (blocks) GC_CUDA(cudaMemcpyAsync(w->d_blocks + slot * GC_CHUNK_SIZE_3, blocks, GC_CHUNK_SIZE_3 * 2, cudaMemcpyHostToDevice, w->ctx->stream));
+    if (sunlight) GC_CUDA(cudaMemcpyAsync(w->d_sun + slot * GC_CHUNK_SIZE_3, sunlight, GC_CHUNK_SIZE_3, cudaMemcpyHostToDevice, w->ctx->stream));
+    if (block_light) GC_CUDA(cudaMemcpyAsync(w->d_light + slot * GC_CHUNK_SIZE_3, block_light, GC_CHUNK_SIZE_3, cudaMemcpyHostToDevice, w->ctx->stream));
+    return GC_OK;
+}
+
+int gcmesh_world_upload_surface(GcWorld* w, int cx, int cz, const uint8_t* surface)
+{
+    if (!w || !surface) return fail(GC_ERR_ARG, "null argument");
+    if (!column_ok(w, cx, cz)) return fail(GC_ERR_ARG, "column outside the window");
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    GC_CUDA(cudaMemcpyAsync(w->d_surface + ((size_t)cz * w->size_x + cx) * GC_CHUNK_SIZE_2, surface, GC_CHUNK_SIZE_2, cudaMemcpyHostToDevice, w->ctx->stream));
+    return GC_OK;
+}
+
+int gcmesh_world_upload_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    if (cz0 < 0 || cz1 > w->size_z || cz0 >= cz1) return fail(GC_ERR_ARG, "row range outside the window");
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    const size_t s0 = (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT * GC_CHUNK_SIZE_3;
+    const size_t ns = (size_t)(cz1 - cz0) * w->size_x * GC_WORLD_CHUNK_HEIGHT * GC_CHUNK_SIZE_3;
+    if (blocks) GC_CUDA(cudaMemcpyAsync(w->d_blocks + s0, blocks + s0, ns * 2, cudaMemcpyHostToDevice, w->ctx->stream));
+    if (sunlight) GC_CUDA(cudaMemcpyAsync(w->d_sun + s0, sunlight + s0, ns, cudaMemcpyHostToDevice, w->ctx->stream));
+    if (block_light) GC_CUDA(cudaMemcpyAsync(w->d_light + s0, block_light + s0, ns, cudaMemcpyHostToDevice, w->ctx->stream));
+    if (surface)
+    {
+        const size_t c0 = (size_t)cz0 * w->size_x * GC_CHUNK_SIZE_2, nc = (size_t)(cz1 - cz0) * w->size_x * GC_CHUNK_SIZE_2;
+        GC_CUDA(cudaMemcpyAsync(w->d_surface + c0, surface + c0, nc, cudaMemcpyHostToDevice, w->ctx->stream));
+    }
+    return GC_OK;
+}
+
+int gcmesh_world_upload_all(GcWorld* w, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    return gcmesh_world_upload_rows(w, 0, w->size_z, blocks, sunlight, block_light, surface);
+}
+
+int gcmesh_world_device_ptrs(GcWorld* w, void** blocks, void** sunlight, void** block_light, void** surface)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    if (blocks) *blocks = w->d_blocks;
+    if (sunlight) *sunlight = w->d_sun;
+    if (block_light) *block_light = w->d_light;
+    if (surface) *surface = w->d_surface;
+    return GC_OK;
+}
+
+size_t gcmesh_world_halo_bytes(const GcWorld* w) { return w ? halo_bytes(w->size_x) : 0; }
+
+int gcmesh_world_pack_halo(GcWorld* w, int cz, int z, void* device_buf)
+{
+    if (!w || !device_buf) return fail(GC_ERR_ARG, "null argument");
+    if (cz < 0 || cz >= w->size_z || z < 0 || z >= GC_CHUNK_SIZE_H) return fail(GC_ERR_ARG, "row / plane outside the window");
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    GC_CUDA(launch_halo_copy(w->d_blocks, w->d_sun, w->d_light, w->d_surface, w->size_x, cz, z, (uint8_t*)device_buf, false, w->ctx->stream));
+    return GC_OK;
+}
+
+int gcmesh_world_unpack_halo(GcWorld* w, int cz, int z, const void* device_buf)
+{
+    if (!w || !device_buf) return fail(GC_ERR_ARG, "null argument");
+    if (cz < 0 || cz >= w->size_z || z < 0 || z >= GC_CHUNK_SIZE_H) return fail(GC_ERR_ARG, "row / plane outside the window");
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    GC_CUDA(launch_halo_copy(w->d_blocks, w->d_sun, w->d_light, w->d_surface, w->size_x, cz, z, (uint8_t*)device_buf, true, w->ctx->stream));
+    return GC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBatch** out)
+{
+    if (!ctx || !out) return fail(GC_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (max_chunks < 1) return fail(GC_ERR_ARG, "max_chunks must be positive");
+    if (max_quads < 1) max_quads = 1;
+    if (max_quads > 0xFFFFFFFFull) return fail(GC_ERR_ARG, "max_quads must fit 32 bits (GcChunkOut::quad_base)");
+    GC_CUDA(cudaSetDevice(ctx->device));
+    GcBatch* b = new (std::nothrow) GcBatch();
+    if (!b) return fail(GC_ERR_ARG, "out of host memory");
+    b->ctx = ctx; b->max_chunks = max_chunks; b->max_quads = max_quads;
+    cudaError_t e = cudaMalloc(&b->d_coords, sizeof(GcChunkCoord) * (size_t)max_chunks);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_out, sizeof(GcChunkOut) * (size_t)max_chunks);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_vertices, (size_t)max_quads * 48);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_indices, (size_t)max_quads * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_cursor, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_counters, sizeof(int32_t) * 2);
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_out, sizeof(GcChunkOut) * (size_t)max_chunks);
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_coords, sizeof(GcChunkCoord) * (size_t)max_chunks);
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_cursor, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_counters, sizeof(int32_t) * 2);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_stop);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) { gcmesh_batch_destroy(b); return fail(GC_ERR_CUDA, "batch allocation", cudaGetErrorString(e)); }
+    *out = b;
+    return GC_OK;
+}
+
+int gcmesh_batch_destroy(GcBatch* b)
+{
+    if (!b) return GC_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->d_coords); cudaFree(b->d_out); cudaFree(b->d_vertices); cudaFree(b->d_indices); cudaFree(b->d_cursor); cudaFree(b->d_counters);
+    if (b->h_out) cudaFreeHost(b->h_out);
+    if (b->h_coords) cudaFreeHost(b->h_coords);
+    if (b->h_cursor) cudaFreeHost(b->h_cursor);
+    if (b->h_counters) cudaFreeHost(b->h_counters);
+    if (b->ev_start) cudaEventDestroy(b->ev_start);
+    if (b->ev_stop) cudaEventDestroy(b->ev_stop);
+    if (b->ev_done) cudaEventDestroy(b->ev_done);
+    delete b;
+    return GC_OK;
+}
+
+int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
+{
+    if (!w || !b || (!coords && n > 0)) return fail(GC_ERR_ARG, "null argument");
+    if (w->ctx != b->ctx) return fail(GC_ERR_ARG, "world and batch belong to different contexts");
+    if (n < 0) return fail(GC_ERR_ARG, "negative chunk count");
+    if (n > b->max_chunks) return fail(GC_ERR_CAPACITY, "batch created for fewer chunks");
+    for (int i = 0; i < n; i++)
+    {
+        const GcChunkCoord c = coords[i];
+        // edge columns are inputs only (WorldRender.cpp:235); chunk rows are 0..3 (World.h:21)
+        if (c.cx < 1 || c.cx > w->size_x - 2 || c.cz < 1 || c.cz > w->size_z - 2 || c.cy < 0 || c.cy >= GC_WORLD_CHUNK_HEIGHT)
+            return fail(GC_ERR_ARG, "chunk on the window edge or outside the window");
+    }
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    if (b->state == 1) GC_CUDA(cudaEventSynchronize(b->ev_done));
+    b->n = n;
+    b->launches = 0;
+    memcpy(b->h_coords, coords, sizeof(GcChunkCoord) * (size_t)n);
+    cudaStream_t s = ctx->stream;
+    GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, s));
+    GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), s));
+    GC_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t) * 2, s));
+    GC_CUDA(cudaEventRecord(b->ev_start, s));
+    if (n > 0)
+    {
+        MeshParams p;
+        p.blocks = w->d_blocks; p.sun = w->d_sun; p.light = w->d_light; p.surface = w->d_surface;
+        p.size_x = w->size_x; p.size_z = w->size_z;
+        p.coords = b->d_coords; p.n_chunks = n; p.out = b->d_out;
+        p.vertex_arena = b->d_vertices; p.index_arena = b->d_indices; p.max_quads = b->max_quads;
+        p.quad_cursor = b->d_cursor; p.work_counter = b->d_counters; p.tables = ctx->d_tables;
+        p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma;
+        const int grid = n < ctx->num_sms ? n : ctx->num_sms;
+        GC_CUDA(launch_mesh(p, w->maps, grid, s));
+        b->launches = 1;
+    }
+    GC_CUDA(cudaEventRecord(b->ev_stop, s));
+    GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    GC_CUDA(cudaMemcpyAsync(b->h_counters, b->d_counters, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, s));
+    GC_CUDA(cudaEventRecord(b->ev_done, s));
+    b->state = 1;
+    return GC_OK;
+}
+
+int gcmesh_wait(GcBatch* b)
+{
+    if (!b) return fail(GC_ERR_ARG, "batch is null");
+    if (b->state == 0) return fail(GC_ERR_STATE, "nothing submitted");
+    GC_CUDA(cudaSetDevice(b->ctx->device));
+    GC_CUDA(cudaEventSynchronize(b->ev_done));
+    b->state = 2;
+    if (b->h_counters[1] != 0) return fail(GC_ERR_CUDA, "mesh kernel watchdog fired (mbarrier wait did not complete)");
+    return GC_OK;
+}
+
+int gcmesh_batch_results(GcBatch* b, const GcChunkOut** out, int* n, uint64_t* total_quads)
+{
+    if (!b) return fail(GC_ERR_ARG, "batch is null");
+    if (b->state != 2) return fail(GC_ERR_STATE, "call gcmesh_wait first");
+    if (out) *out = b->h_out;
+    if (n) *n = b->n;
+    if (total_quads) *total_quads = *b->h_cursor < b->max_quads ? *b->h_cursor : b->max_quads;
+    return GC_OK;
+}
+
+int gcmesh_batch_download(GcBatch* b, void* vertices, void* indices)
+{
+    if (!b) return fail(GC_ERR_ARG, "batch is null");
+    if (b->state != 2) return fail(GC_ERR_STATE, "call gcmesh_wait first");
+    GC_CUDA(cudaSetDevice(b->ctx->device));
+    const uint64_t q = *b->h_cursor < b->max_quads ? *b->h_cursor : b->max_quads;
+    if (q == 0) return GC_OK;
+    if (vertices) GC_CUDA(cudaMemcpyAsync(vertices, b->d_vertices, (size_t)q * 48, cudaMemcpyDeviceToHost, b->ctx->stream));
+    if (indices) GC_CUDA(cudaMemcpyAsync(indices, b->d_indices, (size_t)q * 12, cudaMemcpyDeviceToHost, b->ctx->stream));
+    GC_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return GC_OK;
+}
+
+int gcmesh_batch_fill_meshdata(GcBatch* b, int i, GcMeshData* out)
+{
+    if (!b || !out) return fail(GC_ERR_ARG, "null argument");
+    if (b->state != 2) return fail(GC_ERR_STATE, "call gcmesh_wait first");
+    if (i < 0 || i >= b->n) return fail(GC_ERR_ARG, "chunk index outside the batch");
+    GC_CUDA(cudaSetDevice(b->ctx->device));
+    const GcChunkOut& c = b->h_out[i];
+    out->vert_count = (int32_t)c.vert_count;
+    for (int t = 0; t < GC_MESH_TYPE_COUNT; t++) out->index_count[t] = (int32_t)c.index_count[t];
+    if (c.vert_count == 0) return GC_OK;
+    cudaStream_t s = b->ctx->stream;
+    GC_CUDA(cudaMemcpyAsync(out->vertices, b->d_vertices + (size_t)c.quad_base * 48, (size_t)c.vert_count * 12, cudaMemcpyDeviceToHost, s));
+    for (int t = 0; t < GC_MESH_TYPE_COUNT; t++)
+        if (c.index_count[t])
+            GC_CUDA(cudaMemcpyAsync(out->indices[t], b->d_indices + (size_t)c.quad_base * 6 + c.index_offset[t], (size_t)c.index_count[t] * 2, cudaMemcpyDeviceToHost, s));
+    GC_CUDA(cudaStreamSynchronize(s));
+    return GC_OK;
+}
+
+int gcmesh_batch_device_ptrs(GcBatch* b, void** vertices, void** indices, void** chunk_out)
+{
+    if (!b) return fail(GC_ERR_ARG, "batch is null");
+    if (vertices) *vertices = b->d_vertices;
+    if (indices) *indices = b->d_indices;
+    if (chunk_out) *chunk_out = b->d_out;
+    return GC_OK;
+}
+
+int gcmesh_batch_elapsed_ms(GcBatch* b, float* ms)
+{
+    if (!b || !ms) return fail(GC_ERR_ARG, "null argument");
+    if (b->state != 2) return fail(GC_ERR_STATE, "call gcmesh_wait first");
+    GC_CUDA(cudaEventElapsedTime(ms, b->ev_start, b->ev_stop));
+    return GC_OK;
+}
+
+int gcmesh_batch_launches(GcBatch* b) { return b ? b->launches : 0; }
+
+int gcmesh_kernel_info(int* regs, int* smem_bytes, int* threads)
+{
+    int r = 0, ss = 0, md = 0;
+    cudaError_t e = mesh_kernel_attributes(&r, &ss, &md);
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "cudaFuncGetAttributes", cudaGetErrorString(e));
+    if (regs) *regs = r;
+    if (smem_bytes) *smem_bytes = (int)mesh_smem_bytes();
+    if (threads) *threads = kMeshThreads;
+    return GC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// gcmesh kernels (sm_100a): declarations shared by the kernel TU and the C-ABI TU.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gcmesh.h"
+#include "mesh_core.cuh"
+
+namespace gc
+{
+// Device-side block tables, built by gcmesh_set_block_table.
+struct DeviceTables
+{
+    LutEntry lut[256];   // class bits spread for the bit-plane accumulation
+    MatEntry mat[256];   // texture layers + alpha
+    uint8_t cls8[256];   // class byte
+    int32_t kill_zone;
+};
+
+struct MeshParams
+{
+    const uint16_t* blocks;
+    const uint8_t* sun;
+    const uint8_t* light;
+    const uint8_t* surface;
+    int32_t size_x, size_z;
+    const GcChunkCoord* coords;
+    int32_t n_chunks;
+    GcChunkOut* out;
+    uint8_t* vertex_arena;
+    uint16_t* index_arena;
+    unsigned long long max_quads;
+    unsigned long long* quad_cursor;   // arena reservation cursor (quads)
+    int32_t* work_counter;             // dynamic chunk scheduler
+    const DeviceTables* tables;
+    int32_t* error_flag;               // set by the mbarrier watchdog
+    int32_t use_tma;                   // 0: the producer warp stages slabs with plain loads (debug aid)
+};
+
+// Six tensor maps over the three brick arenas viewed as (x=32, y=64, z=32, slot):
+// a "slab" box (32,64,1,1) and a "row" box (32,1,1,1) for each of blocks / sunlight / blockLight.
+struct MeshTensorMaps
+{
+    CUtensorMap blocks_slab, blocks_row, sun_slab, sun_row, light_slab, light_row;
+};
+
+constexpr int kMeshThreads = 640;
+size_t mesh_smem_bytes();
+cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int grid, cudaStream_t stream);
+cudaError_t mesh_kernel_attributes(int* regs, int* static_smem, int* max_dyn_smem);
+
+// Slab-halo pack / unpack (multi-GPU): see gcmesh_world_pack_halo in gcmesh.h.
+cudaError_t launch_halo_copy(const uint16_t* blocks, const uint8_t* sun, const uint8_t* light, const uint8_t* surface,
+                             int size_x, int cz, int z, uint8_t* buf, bool unpack, cudaStream_t stream);
+size_t halo_bytes(int size_x);
+}  // namespace gc

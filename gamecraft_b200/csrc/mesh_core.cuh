@@ -1,0 +1,378 @@
+// gcmesh core: the per-lane building blocks of the chunk-mesh kernel.
+//
+// Everything here is a small __host__ __device__ function over plain pointers, so the SAME code runs
+//   * inside the sm_100a kernel (gcmesh_kernel.cu), on shared-memory tiles, and
+//   * inside tests/emu (a sequential host walk over the same phases) where it is checked bit-for-bit
+//     against the CPU oracle before any GPU time is spent.
+// The kernel adds only the orchestration: TMA staging, mbarriers, warp roles, scans, arena reservation.
+//
+// On-chip form of one chunk + 1-voxel halo (tile cell (x,ty,tz), x in -1..32, ty in -1..64, tz in -1..32):
+//   row index      hr(ty,tz) = (ty+1)*34 + (tz+1)                      2244 rows, z fastest
+//   planes[k][hr]  uint32, bit x = class bit k of cell (x,ty,tz), x in 0..31
+//                  k: 0..3 = cull >= 1..4 (thermometer code of CullValue, Block.h:40-47)
+//                     4    = opaque (Block.cpp:65-68)
+//                     5..7 = mesh type bits (Mesh.h:8-16); 7 (all ones) = never emits (AIR / invisible)
+//   hx[hr]         uint16: low byte = the 8 class bits of cell x = -1, high byte = of cell x = 32
+//   lt[hr*40+4+x]  uint8: (sun << 4) | blockLight with GetSunlight's rules applied (Lighting.cpp:69-79);
+//                  0x00 below the world, 0xFF above it (GetFinalLight, WorldRender.cpp:316-319)
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GC_HD __host__ __device__ __forceinline__
+#else
+#define GC_HD static inline
+#endif
+
+namespace gc
+{
+constexpr int kTX = 32, kTY = 64, kTZ = 32;
+constexpr int kRowsY = kTY + 2, kRowsZ = kTZ + 2;
+constexpr int kHaloRows = kRowsY * kRowsZ;   // 2244
+constexpr int kCenterRows = kTY * kTZ;       // 2048
+constexpr int kLtStride = 40;
+constexpr int kLtBytes = kHaloRows * kLtStride;
+constexpr int kPlanes = 8;
+constexpr int kMaxQuads = 10000;             // MAX_VERTICES / 4, Mesh.h:5
+constexpr int kMeshTypes = 5;
+constexpr int kNoEmitType = 7;
+
+enum { P_G1 = 0, P_G2 = 1, P_G3 = 2, P_G4 = 3, P_OPAQUE = 4, P_M0 = 5, P_M1 = 6, P_M2 = 7 };
+
+GC_HD int hrow(int ty, int tz) { return (ty + 1) * kRowsZ + (tz + 1); }
+
+// ---- small portable intrinsics ----
+GC_HD int popc(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+GC_HD int lowbit(uint32_t v)  // index of lowest set bit, v != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+// per byte: a >= b ? 0xFF : 0x00
+GC_HD uint32_t cmpge4(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vcmpgeu4(a, b);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++)
+        if (((a >> (8 * i)) & 255u) >= ((b >> (8 * i)) & 255u)) r |= 255u << (8 * i);
+    return r;
+#endif
+}
+// per byte max
+GC_HD uint32_t max4(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vmaxu4(a, b);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++)
+    {
+        uint32_t x = (a >> (8 * i)) & 255u, y = (b >> (8 * i)) & 255u;
+        r |= (x > y ? x : y) << (8 * i);
+    }
+    return r;
+#endif
+}
+
+// ---- block table in kernel form ----
+struct LutEntry { uint32_t lo, hi; };  // class bit k at bit position 8k (lo: k 0..3, hi: k 4..7)
+
+// class byte of one block type: the 8 class bits packed (see file header)
+GC_HD uint32_t class_byte(int cull, int opaque, int mesh_type, int emits)
+{
+    uint32_t c = 0;
+    for (int k = 1; k <= 4; k++)
+        if (cull >= k) c |= 1u << (k - 1);
+    if (opaque) c |= 1u << P_OPAQUE;
+    c |= (uint32_t)(emits ? mesh_type : kNoEmitType) << P_M0;
+    return c;
+}
+GC_HD LutEntry spread_class(uint32_t cls)
+{
+    LutEntry e;
+    e.lo = (cls & 1u) | ((cls & 2u) << 7) | ((cls & 4u) << 14) | ((cls & 8u) << 21);
+    uint32_t h = cls >> 4;
+    e.hi = (h & 1u) | ((h & 2u) << 7) | ((h & 4u) << 14) | ((h & 8u) << 21);
+    return e;
+}
+
+// =====================================================================================================
+// Phase 1: raw voxels -> on-chip form
+// =====================================================================================================
+
+// Eight consecutive voxels (x = 8o .. 8o+7) of one row -> one byte of each class plane.
+// ids: 4 words holding 8 uint16 block ids.  planes_b = (uint8_t*)planes.
+GC_HD void p1_class_octet(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, const LutEntry* lut, uint8_t* planes_b, int hr, int o)
+{
+    uint32_t lo, hi;
+    const bool uniform = (w0 == w1) && (w2 == w3) && (w0 == w2) && ((w0 >> 16) == (w0 & 0xFFFFu));
+    if (uniform)
+    {
+        LutEntry e = lut[w0 & 255u];
+        lo = e.lo * 255u;
+        hi = e.hi * 255u;
+    }
+    else
+    {
+        const uint32_t w[4] = { w0, w1, w2, w3 };
+        lo = 0; hi = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            LutEntry a = lut[w[i] & 255u];
+            LutEntry b = lut[(w[i] >> 16) & 255u];
+            lo += (a.lo << (2 * i)) + (b.lo << (2 * i + 1));
+            hi += (a.hi << (2 * i)) + (b.hi << (2 * i + 1));
+        }
+    }
+    uint8_t* p = planes_b + hr * 4 + o;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        p[(k * kHaloRows) * 4] = (uint8_t)(lo >> (8 * k));
+        p[((k + 4) * kHaloRows) * 4] = (uint8_t)(hi >> (8 * k));
+    }
+}
+
+// A whole row whose cells all have the same class byte (rows outside the world: KILL_ZONE below, AIR above,
+// GetBlockSafe World.cpp:422-428).
+GC_HD void p1_class_const_octet(uint32_t cls, uint8_t* planes_b, int hr, int o)
+{
+    uint8_t* p = planes_b + hr * 4 + o;
+#pragma unroll
+    for (int k = 0; k < 8; k++) p[(k * kHaloRows) * 4] = ((cls >> k) & 1u) ? 0xFF : 0x00;
+}
+
+// Four voxels of light: sun/bl/surf hold 4 bytes each (x ascending from the low byte); wy = world y of the row.
+//   sun' = wy >= surface ? 15 : max(sun, 1)      GetSunlight, Lighting.cpp:69-79 (MAX_LIGHT / MIN_LIGHT, Lighting.h:5-6)
+//   out  = sun' << 4 | blockLight
+GC_HD uint32_t p1_light4(uint32_t sun, uint32_t bl, uint32_t surf, int wy)
+{
+    uint32_t above = cmpge4((uint32_t)wy * 0x01010101u, surf);
+    uint32_t s = max4(sun & 0x0F0F0F0Fu, 0x01010101u);
+    s = (above & 0x0F0F0F0Fu) | (~above & s);
+    return (s << 4) | (bl & 0x0F0F0F0Fu);
+}
+
+// One cell of the x = -1 / x = 32 halo columns.  side 0: x = -1, side 1: x = 32.
+GC_HD void p1_xhalo_cell(uint32_t cls, uint32_t light_byte, uint8_t* hx_b, uint8_t* lt, int hr, int side)
+{
+    hx_b[hr * 2 + side] = (uint8_t)cls;
+    lt[hr * kLtStride + (side ? 36 : 3)] = (uint8_t)light_byte;
+}
+
+GC_HD uint32_t light_byte_of(uint32_t sun, uint32_t bl, uint32_t surf, int wy)
+{
+    uint32_t s = sun & 15u;
+    if (s == 0) s = 1;
+    if ((uint32_t)wy >= surf) s = 15;
+    return (s << 4) | (bl & 15u);
+}
+
+// =====================================================================================================
+// Phase 2: face masks of one centre row
+// =====================================================================================================
+struct RowFaces
+{
+    uint32_t f[6];        // up(+y), down(-y), front(+z), back(-z), right(+x), left(-x): BuildBlock's order, WorldRender.cpp:468-556
+    uint32_t m0, m1, m2;  // mesh-type bit planes of the row
+};
+
+// drawn iff emits(v) && cull(v) < cull(n)   (CanDrawFace, WorldRender.cpp:387-391; "n != v" is implied by the
+// strict inequality because cull is a function of the block id).  With the thermometer code g_k = cull >= k:
+// cull(v) < cull(n)  <=>  OR_k (~g_k(v) & g_k(n)).
+GC_HD uint32_t lt_mask(const uint32_t g[4], uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3)
+{
+    return (~g[0] & n0) | (~g[1] & n1) | (~g[2] & n2) | (~g[3] & n3);
+}
+
+GC_HD void p2_row_faces(const uint32_t* planes, const uint16_t* hx, int ty, int tz, RowFaces& r)
+{
+    const int hr = hrow(ty, tz);
+    uint32_t g[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) g[k] = planes[k * kHaloRows + hr];
+    r.m0 = planes[P_M0 * kHaloRows + hr];
+    r.m1 = planes[P_M1 * kHaloRows + hr];
+    r.m2 = planes[P_M2 * kHaloRows + hr];
+    const uint32_t vis = ~(r.m0 & r.m1 & r.m2);
+    const uint32_t h = hx[hr];
+
+    const int up = hr + kRowsZ, dn = hr - kRowsZ, fr = hr + 1, bk = hr - 1;
+    r.f[0] = vis & lt_mask(g, planes[up], planes[kHaloRows + up], planes[2 * kHaloRows + up], planes[3 * kHaloRows + up]);
+    r.f[1] = vis & lt_mask(g, planes[dn], planes[kHaloRows + dn], planes[2 * kHaloRows + dn], planes[3 * kHaloRows + dn]);
+    r.f[2] = vis & lt_mask(g, planes[fr], planes[kHaloRows + fr], planes[2 * kHaloRows + fr], planes[3 * kHaloRows + fr]);
+    r.f[3] = vis & lt_mask(g, planes[bk], planes[kHaloRows + bk], planes[2 * kHaloRows + bk], planes[3 * kHaloRows + bk]);
+    // +x neighbour of voxel x is voxel x+1 (bit x+1), voxel 31's is the x = 32 halo cell (hx high byte)
+    r.f[4] = vis & lt_mask(g, (g[0] >> 1) | (((h >> 8) & 1u) << 31), (g[1] >> 1) | (((h >> 9) & 1u) << 31),
+                           (g[2] >> 1) | (((h >> 10) & 1u) << 31), (g[3] >> 1) | (((h >> 11) & 1u) << 31));
+    r.f[5] = vis & lt_mask(g, (g[0] << 1) | (h & 1u), (g[1] << 1) | ((h >> 1) & 1u),
+                           (g[2] << 1) | ((h >> 2) & 1u), (g[3] << 1) | ((h >> 3) & 1u));
+}
+
+// total quads of the row and, packed 4 x 8 bit, the quads of mesh types 1..4 (type 0 = total - sum)
+GC_HD void p2_row_counts(const RowFaces& r, int& total, uint32_t& typ4)
+{
+    total = popc(r.f[0]) + popc(r.f[1]) + popc(r.f[2]) + popc(r.f[3]) + popc(r.f[4]) + popc(r.f[5]);
+    typ4 = 0;
+    const uint32_t any = r.f[0] | r.f[1] | r.f[2] | r.f[3] | r.f[4] | r.f[5];
+    if (any & (r.m0 | r.m1 | r.m2))
+    {
+        const uint32_t t1 = r.m0 & ~r.m1 & ~r.m2, t2 = ~r.m0 & r.m1 & ~r.m2, t3 = r.m0 & r.m1 & ~r.m2, t4 = ~r.m0 & ~r.m1 & r.m2;
+        int c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+#pragma unroll
+        for (int d = 0; d < 6; d++)
+        {
+            c1 += popc(r.f[d] & t1); c2 += popc(r.f[d] & t2); c3 += popc(r.f[d] & t3); c4 += popc(r.f[d] & t4);
+        }
+        typ4 = (uint32_t)c1 | ((uint32_t)c2 << 8) | ((uint32_t)c3 << 16) | ((uint32_t)c4 << 24);
+    }
+}
+
+// =====================================================================================================
+// Phase 3a: one row -> quad list entries (in emission order) + its index-stream words
+// =====================================================================================================
+// list entry: bits 0..2 face, 3..7 x, 8..12 tz, 13..18 ty
+GC_HD uint32_t quad_entry(int ty, int tz, int x, int d) { return (uint32_t)d | ((uint32_t)x << 3) | ((uint32_t)tz << 8) | ((uint32_t)ty << 13); }
+
+// rank0: chunk-relative rank of the row's first quad; trank[t]: rank of the row's first quad within mesh type t;
+// list_base: rank of list[0]; idx_words: the chunk's index segment as uint32 (3 words per quad);
+// type_off[t]: quads before mesh type t's stream inside the segment.
+// SetIndices (Mesh.cpp:32-50): o+2, o+1, o, o+3, o+2, o with o = (uint16)vertCount = 4*rank.
+GC_HD void p3a_row(const RowFaces& r, int ty, int tz, uint32_t rank0, const uint32_t trank0[kMeshTypes], uint32_t list_base,
+                   uint32_t* list, uint32_t* idx_words, const uint32_t type_off[kMeshTypes])
+{
+    uint32_t any = r.f[0] | r.f[1] | r.f[2] | r.f[3] | r.f[4] | r.f[5];
+    uint32_t rank = rank0;
+    uint32_t tr[kMeshTypes];
+#pragma unroll
+    for (int t = 0; t < kMeshTypes; t++) tr[t] = trank0[t] + type_off[t];
+    while (any)
+    {
+        const int x = lowbit(any);
+        any &= any - 1;
+        const uint32_t t = ((r.m0 >> x) & 1u) | (((r.m1 >> x) & 1u) << 1) | (((r.m2 >> x) & 1u) << 2);
+        // select this voxel's running stream position without dynamic register indexing
+        uint32_t pos = tr[0];
+        pos = t == 1 ? tr[1] : pos; pos = t == 2 ? tr[2] : pos; pos = t == 3 ? tr[3] : pos; pos = t == 4 ? tr[4] : pos;
+        uint32_t n = 0;
+#pragma unroll
+        for (int d = 0; d < 6; d++)
+        {
+            if ((r.f[d] >> x) & 1u)
+            {
+                list[rank - list_base] = quad_entry(ty, tz, x, d);
+                const uint32_t o = (rank * 4u) & 0xFFFFu;
+                uint32_t* w = idx_words + (size_t)(pos + n) * 3;
+                w[0] = ((o + 2u) & 0xFFFFu) | (((o + 1u) & 0xFFFFu) << 16);
+                w[1] = o | (((o + 3u) & 0xFFFFu) << 16);
+                w[2] = ((o + 2u) & 0xFFFFu) | (o << 16);
+                rank++; n++;
+            }
+        }
+        tr[0] += t == 0 ? n : 0; tr[1] += t == 1 ? n : 0; tr[2] += t == 2 ? n : 0; tr[3] += t == 3 ? n : 0; tr[4] += t == 4 ? n : 0;
+    }
+}
+
+// =====================================================================================================
+// Phase 3b: one quad -> 4 vertices (48 bytes)
+// =====================================================================================================
+// Per face: the cell in front (a), the two in-plane axes (u, v) as (lt byte stride, row stride, x stride),
+// and the four corners (BuildBlock's vertex order) as bits.  Packed so one table word serves a lane.
+struct FaceDesc
+{
+    int8_t nx, ny, nz;       // outward normal
+    int8_t ux, uy, uz;       // first in-plane axis
+    int8_t vx, vy, vz;       // second in-plane axis
+    uint8_t corners[4];      // per vertex: bit0 = +x corner, bit1 = +y, bit2 = +z   (WorldRender.cpp:475-553)
+};
+
+// up, down, front, back, right, left.  In-plane axes as VertexLight picks them (WorldRender.cpp:333-355):
+// AXIS_Y -> (x, z); AXIS_Z -> (x, y); AXIS_X -> (y, z).
+#define GC_FACE_TABLE { \
+    { 0, 1, 0,  1, 0, 0,  0, 0, 1,  { 3, 7, 6, 2 } }, \
+    { 0,-1, 0,  1, 0, 0,  0, 0, 1,  { 0, 4, 5, 1 } }, \
+    { 0, 0, 1,  1, 0, 0,  0, 1, 0,  { 4, 6, 7, 5 } }, \
+    { 0, 0,-1,  1, 0, 0,  0, 1, 0,  { 1, 3, 2, 0 } }, \
+    { 1, 0, 0,  0, 1, 0,  0, 0, 1,  { 5, 7, 3, 1 } }, \
+    {-1, 0, 0,  0, 1, 0,  0, 0, 1,  { 0, 2, 6, 4 } } }
+
+// material word of a block type: bytes 0..5 texture layer per face, byte 6 alpha
+struct MatEntry { uint32_t lo, hi; };
+
+// light byte -> packed (blockLight | sun << 16)
+GC_HD uint32_t unpack_light(uint32_t b) { return (b & 15u) | ((b >> 4) << 16); }
+
+// opaque bit of cell (x, row hr), x in -1..32
+GC_HD uint32_t opaque_at(const uint32_t* plane_o, const uint16_t* hx, int hr, int x)
+{
+    const uint32_t h = hx[hr];
+    const uint64_t w = ((uint64_t)plane_o[hr] << 1) | ((h >> P_OPAQUE) & 1u) | ((uint64_t)((h >> (8 + P_OPAQUE)) & 1u) << 33);
+    return (uint32_t)(w >> (x + 1)) & 1u;
+}
+
+// VertexLight (WorldRender.cpp:329-383) on packed sums: fields are 17*nibble sums, so
+//   4 samples: (17*S) >> 2          3 samples: (17*S)/3 = 5*S + floor(2*S/3), floor(n/3) = (n*171) >> 9 for n < 512
+GC_HD uint32_t corner_color(uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool open)
+{
+    if (open) return (((a + b + c + d) * 17u) >> 2) & 0x00FF00FFu;
+    const uint32_t s = a + b + c;
+    return s * 5u + (((s * 2u * 171u) >> 9) & 0x001F001Fu);
+}
+
+// out: 12 words = 4 vertices x 12 bytes {pos u8x3, uv u8x3, color u8x4 (L,L,L,S), alpha, 0}  (VertexInfo, Mesh.h:37-44)
+GC_HD void p3b_quad(uint32_t entry, const FaceDesc& f, const uint8_t* lt, const uint32_t* plane_o, const uint16_t* hx,
+                    MatEntry mat, uint32_t out[12])
+{
+    const int d = entry & 7, x = (entry >> 3) & 31, tz = (entry >> 8) & 31, ty = (entry >> 13) & 63;
+    const int ax = x + f.nx, ay = ty + f.ny, az = tz + f.nz;
+    const int hr_a = hrow(ay, az);
+    const int hr_u = f.uy * kRowsZ + f.uz, hr_v = f.vy * kRowsZ + f.vz;      // row strides of the in-plane axes
+    const int lt_a = hr_a * kLtStride + 4 + ax;
+    const int lt_u = hr_u * kLtStride + f.ux, lt_v = hr_v * kLtStride + f.vx;  // lt byte strides
+
+    // 3x3 light neighbourhood in the layer in front of the face; L[i][j] at a + (i-1)*u + (j-1)*v
+    uint32_t L[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) L[i][j] = unpack_light(lt[lt_a + (i - 1) * lt_u + (j - 1) * lt_v]);
+    // opacity of the four edge cells (only b and c are ever tested, WorldRender.cpp:361-362)
+    const uint32_t o_um = opaque_at(plane_o, hx, hr_a - hr_u, ax - f.ux), o_up = opaque_at(plane_o, hx, hr_a + hr_u, ax + f.ux);
+    const uint32_t o_vm = opaque_at(plane_o, hx, hr_a - hr_v, ax - f.vx), o_vp = opaque_at(plane_o, hx, hr_a + hr_v, ax + f.vx);
+
+    const uint32_t tex = (d < 4 ? (mat.lo >> (8 * d)) : (mat.hi >> (8 * (d - 4)))) & 255u;
+    const uint32_t alpha = (mat.hi >> 16) & 255u;
+
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        const uint32_t c = f.corners[k];
+        const int cxb = c & 1, cyb = (c >> 1) & 1, czb = (c >> 2) & 1;
+        // corner sign along u / v: the corner bit of the axis u (v) points along
+        const int su = f.ux ? cxb : (f.uy ? cyb : czb);
+        const int sv = f.vx ? cxb : (f.vy ? cyb : czb);
+        const uint32_t ob = su ? o_up : o_um, oc = sv ? o_vp : o_vm;
+        const uint32_t col = corner_color(L[1][1], L[su * 2][1], L[1][sv * 2], L[su * 2][sv * 2], !(ob & oc));
+        const uint32_t l = col & 255u, s = (col >> 16) & 255u;
+        const uint32_t u = (k >> 1) & 1u, v = (k == 0 || k == 3) ? 1u : 0u;   // uv: (0,1) (0,0) (1,0) (1,1)
+        out[3 * k + 0] = (uint32_t)(x + cxb) | ((uint32_t)(ty + cyb) << 8) | ((uint32_t)(tz + czb) << 16) | (u << 24);
+        out[3 * k + 1] = v | (tex << 8) | (l << 16) | (l << 24);
+        out[3 * k + 2] = l | (s << 8) | (alpha << 16);
+    }
+}
+
+}  // namespace gc

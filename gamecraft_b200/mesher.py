@@ -1,0 +1,337 @@
+"""Host-side mirror of the reference's mesh-build call sites over ``libgcmesh.so`` (ctypes; no torch types).
+
+Reference call sites mirrored (Code/WorldRender.cpp):
+  * ``BuildChunk(state, world, chunk)``  (:69-78)  -> :func:`build_chunk`
+  * ``RebuildChunks(state, world)``      (:80-91)  -> :func:`rebuild_chunks`  (one batched GPU submission)
+  * ``chunk->meshData`` (Code/Mesh.h:46-52)         -> :class:`ChunkMesh`
+The CUDA library is mandatory: importing works anywhere, but creating a :class:`Context` without a usable
+B200 raises :class:`GcMeshError` — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libgcmesh.so")
+
+CHUNK_VOXELS = 65536
+MESH_TYPES = 5
+MAX_QUADS = 10000
+MESH_OPAQUE, MESH_CUTOUT, MESH_TRANSPARENT, MESH_FLUID, MESH_MAGMA = range(5)
+CHUNK_OVERFLOW = 1
+CHUNK_NO_SPACE = 2
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+SOURCES = ["gcmesh_kernel.cu", "gcmesh_api.cu"]
+HEADERS = ["gcmesh_kernel.cuh", "mesh_core.cuh", os.path.join("..", "..", "include", "gcmesh.h")]
+
+
+class GcMeshError(RuntimeError):
+    pass
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libgcmesh.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB_PATH, "-lcudart"]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB_PATH
+
+
+class BlockInfo(ctypes.Structure):
+    """GcBlockInfo: the fields of the reference's BlockData the mesher reads (Code/Block.h:85-100)."""
+    _fields_ = [("textures", ctypes.c_uint8 * 6), ("mesh_type", ctypes.c_uint8), ("cull", ctypes.c_uint8),
+                ("alpha", ctypes.c_uint8), ("invisible", ctypes.c_uint8), ("opaque", ctypes.c_uint8),
+                ("reserved", ctypes.c_uint8)]
+
+
+class ChunkOut(ctypes.Structure):
+    """GcChunkOut."""
+    _fields_ = [("quad_base", ctypes.c_uint32), ("vert_count", ctypes.c_uint32),
+                ("index_count", ctypes.c_uint32 * MESH_TYPES), ("index_offset", ctypes.c_uint32 * MESH_TYPES),
+                ("quads", ctypes.c_uint32), ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 2)]
+
+
+CHUNK_OUT_DTYPE = np.dtype([("quad_base", "<u4"), ("vert_count", "<u4"), ("index_count", "<u4", (5,)),
+                            ("index_offset", "<u4", (5,)), ("quads", "<u4"), ("flags", "<u4"), ("reserved", "<u4", (2,))])
+assert CHUNK_OUT_DTYPE.itemsize == ctypes.sizeof(ChunkOut) == 64
+
+EXPORTS = [
+    "gcmesh_version", "gcmesh_last_error", "gcmesh_create", "gcmesh_destroy", "gcmesh_set_stream",
+    "gcmesh_set_block_table", "gcmesh_default_block_table", "gcmesh_synchronize",
+    "gcmesh_world_create", "gcmesh_world_destroy", "gcmesh_world_upload_chunk", "gcmesh_world_upload_surface",
+    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
+    "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
+    "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_wait", "gcmesh_batch_results",
+    "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
+    "gcmesh_batch_launches", "gcmesh_kernel_info",
+]
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libgcmesh.so (building it if the sources are newer).  Fails loudly when it cannot be loaded."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        L.gcmesh_version.restype = ctypes.c_char_p
+        L.gcmesh_last_error.restype = ctypes.c_char_p
+        L.gcmesh_create.argtypes = [ci, vp, ctypes.POINTER(vp)]
+        L.gcmesh_destroy.argtypes = [vp]
+        L.gcmesh_set_stream.argtypes = [vp, vp]
+        L.gcmesh_set_block_table.argtypes = [vp, ctypes.POINTER(BlockInfo), ci, ci]
+        L.gcmesh_default_block_table.argtypes = [ctypes.POINTER(BlockInfo), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.gcmesh_synchronize.argtypes = [vp]
+        L.gcmesh_world_create.argtypes = [vp, ci, ci, ctypes.POINTER(vp)]
+        L.gcmesh_world_destroy.argtypes = [vp]
+        L.gcmesh_world_upload_chunk.argtypes = [vp, ci, ci, ci, vp, vp, vp]
+        L.gcmesh_world_upload_surface.argtypes = [vp, ci, ci, vp]
+        L.gcmesh_world_upload_all.argtypes = [vp, vp, vp, vp, vp]
+        L.gcmesh_world_upload_rows.argtypes = [vp, ci, ci, vp, vp, vp, vp]
+        L.gcmesh_world_device_ptrs.argtypes = [vp] + [ctypes.POINTER(vp)] * 4
+        L.gcmesh_world_halo_bytes.argtypes = [vp]
+        L.gcmesh_world_halo_bytes.restype = ctypes.c_size_t
+        L.gcmesh_world_pack_halo.argtypes = [vp, ci, ci, vp]
+        L.gcmesh_world_unpack_halo.argtypes = [vp, ci, ci, vp]
+        L.gcmesh_batch_create.argtypes = [vp, ci, ctypes.c_uint64, ctypes.POINTER(vp)]
+        L.gcmesh_batch_destroy.argtypes = [vp]
+        L.gcmesh_submit.argtypes = [vp, vp, vp, ci]
+        L.gcmesh_wait.argtypes = [vp]
+        L.gcmesh_batch_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_uint64)]
+        L.gcmesh_batch_download.argtypes = [vp, vp, vp]
+        L.gcmesh_batch_fill_meshdata.argtypes = [vp, ci, vp]
+        L.gcmesh_batch_device_ptrs.argtypes = [vp] + [ctypes.POINTER(vp)] * 3
+        L.gcmesh_batch_elapsed_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+        L.gcmesh_batch_launches.argtypes = [vp]
+        L.gcmesh_kernel_info.argtypes = [ctypes.POINTER(ci)] * 3
+        _lib = L
+    return _lib
+
+
+def _check(status: int, what: str) -> None:
+    if status != 0:
+        raise GcMeshError("%s failed (%d): %s" % (what, status, lib().gcmesh_last_error().decode()))
+
+
+def _ptr(a) -> ctypes.c_void_p:
+    if a is None:
+        return ctypes.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return ctypes.c_void_p(a.ctypes.data)
+    return ctypes.c_void_p(int(a))
+
+
+def default_block_table():
+    """The reference's 24 block types (Code/Block.cpp:139-276) as (list[BlockInfo], kill_zone_id)."""
+    arr = (BlockInfo * 256)()
+    n, kz = ctypes.c_int(0), ctypes.c_int(0)
+    _check(lib().gcmesh_default_block_table(arr, ctypes.byref(n), ctypes.byref(kz)), "gcmesh_default_block_table")
+    return [arr[i] for i in range(n.value)], kz.value
+
+
+class Context:
+    """One GPU + one stream (``GameState``'s role for this path).  ``stream`` is a raw ``cudaStream_t`` value."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.h = ctypes.c_void_p()
+        _check(lib().gcmesh_create(int(device), ctypes.c_void_p(stream or 0), ctypes.byref(self.h)), "gcmesh_create")
+        self.device = device
+
+    def set_block_table(self, infos, kill_zone_id: int = 20) -> None:
+        arr = (BlockInfo * len(infos))(*infos)
+        _check(lib().gcmesh_set_block_table(self.h, arr, len(infos), kill_zone_id), "gcmesh_set_block_table")
+
+    def set_stream(self, stream: int) -> None:
+        _check(lib().gcmesh_set_stream(self.h, ctypes.c_void_p(stream)), "gcmesh_set_stream")
+
+    def synchronize(self) -> None:
+        _check(lib().gcmesh_synchronize(self.h), "gcmesh_synchronize")
+
+    def kernel_info(self):
+        r, s, t = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        _check(lib().gcmesh_kernel_info(ctypes.byref(r), ctypes.byref(s), ctypes.byref(t)), "gcmesh_kernel_info")
+        return {"registers": r.value, "smem_bytes": s.value, "threads": t.value}
+
+    def close(self) -> None:
+        if self.h:
+            lib().gcmesh_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class World:
+    """Device mirror of the reference's window of columns (``World::groups``, Code/World.h:131)."""
+
+    def __init__(self, ctx: Context, size_x: int, size_z: int):
+        self.ctx, self.size_x, self.size_z = ctx, int(size_x), int(size_z)
+        self.h = ctypes.c_void_p()
+        _check(lib().gcmesh_world_create(ctx.h, self.size_x, self.size_z, ctypes.byref(self.h)), "gcmesh_world_create")
+
+    def upload(self, host) -> "World":
+        """All columns of a HostWorld-shaped object (``blocks``/``sun``/``light``/``surface`` arrays)."""
+        assert host.size_x == self.size_x and host.size_z == self.size_z
+        _check(lib().gcmesh_world_upload_all(self.h, _ptr(host.blocks), _ptr(host.sun), _ptr(host.light), _ptr(host.surface)),
+               "gcmesh_world_upload_all")
+        return self
+
+    def upload_rows(self, host, cz0: int, cz1: int) -> "World":
+        _check(lib().gcmesh_world_upload_rows(self.h, cz0, cz1, _ptr(host.blocks), _ptr(host.sun), _ptr(host.light), _ptr(host.surface)),
+               "gcmesh_world_upload_rows")
+        return self
+
+    def upload_chunk(self, cx, cy, cz, blocks=None, sunlight=None, block_light=None) -> None:
+        _check(lib().gcmesh_world_upload_chunk(self.h, cx, cy, cz, _ptr(blocks), _ptr(sunlight), _ptr(block_light)), "gcmesh_world_upload_chunk")
+
+    def upload_surface(self, cx, cz, surface) -> None:
+        _check(lib().gcmesh_world_upload_surface(self.h, cx, cz, _ptr(surface)), "gcmesh_world_upload_surface")
+
+    def device_ptrs(self):
+        p = [ctypes.c_void_p() for _ in range(4)]
+        _check(lib().gcmesh_world_device_ptrs(self.h, *[ctypes.byref(x) for x in p]), "gcmesh_world_device_ptrs")
+        return tuple(x.value for x in p)
+
+    def halo_bytes(self) -> int:
+        return int(lib().gcmesh_world_halo_bytes(self.h))
+
+    def pack_halo(self, cz: int, z: int, device_buf: int) -> None:
+        _check(lib().gcmesh_world_pack_halo(self.h, cz, z, ctypes.c_void_p(device_buf)), "gcmesh_world_pack_halo")
+
+    def unpack_halo(self, cz: int, z: int, device_buf: int) -> None:
+        _check(lib().gcmesh_world_unpack_halo(self.h, cz, z, ctypes.c_void_p(device_buf)), "gcmesh_world_unpack_halo")
+
+    def close(self) -> None:
+        if self.h:
+            lib().gcmesh_world_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ChunkMesh:
+    """What BuildChunkAsync leaves in ``chunk->meshData`` (Code/Mesh.h:46-52): (n,12) u8 vertices + 5 u16 index arrays."""
+
+    def __init__(self, vertices, indices, flags=0, quads=0):
+        self.vertices, self.indices, self.flags, self.quads = vertices, indices, int(flags), int(quads)
+
+    @property
+    def vert_count(self) -> int:
+        return len(self.vertices)
+
+    @property
+    def overflow(self) -> bool:
+        return bool(self.flags & CHUNK_OVERFLOW)
+
+
+class Batch:
+    """Output arenas + descriptors of one batched submission (the reference's ``vector<Chunk*>`` job)."""
+
+    def __init__(self, ctx: Context, max_chunks: int, max_quads: int):
+        self.ctx, self.max_chunks, self.max_quads = ctx, int(max_chunks), int(max_quads)
+        self.h = ctypes.c_void_p()
+        _check(lib().gcmesh_batch_create(ctx.h, self.max_chunks, self.max_quads, ctypes.byref(self.h)), "gcmesh_batch_create")
+        self._coords = None
+
+    def submit(self, world: World, coords) -> "Batch":
+        self._coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)
+        _check(lib().gcmesh_submit(world.h, self.h, _ptr(self._coords), len(self._coords)), "gcmesh_submit")
+        return self
+
+    def wait(self) -> "Batch":
+        _check(lib().gcmesh_wait(self.h), "gcmesh_wait")
+        return self
+
+    def results(self):
+        """(descriptors as a structured numpy array view, total_quads)."""
+        p, n, q = ctypes.c_void_p(), ctypes.c_int(0), ctypes.c_uint64(0)
+        _check(lib().gcmesh_batch_results(self.h, ctypes.byref(p), ctypes.byref(n), ctypes.byref(q)), "gcmesh_batch_results")
+        if n.value == 0:
+            return np.zeros(0, CHUNK_OUT_DTYPE), 0
+        buf = (ctypes.c_uint8 * (n.value * 64)).from_address(p.value)
+        return np.frombuffer(buf, CHUNK_OUT_DTYPE, n.value), int(q.value)
+
+    def download(self, vertices=None, indices=None):
+        """Copy the used arena prefix to host arrays: (total_quads*4, 12) u8 and (total_quads*6,) u16."""
+        _, q = self.results()
+        if vertices is None:
+            vertices = np.empty((q * 4, 12), np.uint8)
+        if indices is None:
+            indices = np.empty(q * 6, np.uint16)
+        _check(lib().gcmesh_batch_download(self.h, _ptr(vertices), _ptr(indices)), "gcmesh_batch_download")
+        return vertices, indices
+
+    def meshes(self):
+        """One :class:`ChunkMesh` per submitted chunk, in submit order."""
+        desc, q = self.results()
+        verts, idx = self.download()
+        out = []
+        for d in desc:
+            qb, nv = int(d["quad_base"]), int(d["vert_count"])
+            v = verts[qb * 4: qb * 4 + nv]
+            ii = [idx[qb * 6 + int(d["index_offset"][t]): qb * 6 + int(d["index_offset"][t]) + int(d["index_count"][t])] for t in range(MESH_TYPES)]
+            out.append(ChunkMesh(v, ii, d["flags"], d["quads"]))
+        return out
+
+    def device_ptrs(self):
+        p = [ctypes.c_void_p() for _ in range(3)]
+        _check(lib().gcmesh_batch_device_ptrs(self.h, *[ctypes.byref(x) for x in p]), "gcmesh_batch_device_ptrs")
+        return tuple(x.value for x in p)
+
+    def elapsed_ms(self) -> float:
+        ms = ctypes.c_float(0)
+        _check(lib().gcmesh_batch_elapsed_ms(self.h, ctypes.byref(ms)), "gcmesh_batch_elapsed_ms")
+        return float(ms.value)
+
+    def launches(self) -> int:
+        return int(lib().gcmesh_batch_launches(self.h))
+
+    def close(self) -> None:
+        if self.h:
+            lib().gcmesh_batch_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def rebuild_chunks(world: World, coords, batch: Batch | None = None):
+    """``RebuildChunks`` (Code/WorldRender.cpp:80-91): mesh a list of chunks in ONE submission; returns ChunkMesh list."""
+    coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)
+    own = batch is None
+    if own:
+        batch = Batch(world.ctx, max(1, len(coords)), max(1, len(coords)) * MAX_QUADS)
+    try:
+        return batch.submit(world, coords).wait().meshes()
+    finally:
+        if own:
+            batch.close()
+
+
+def build_chunk(world: World, cx: int, cy: int, cz: int) -> ChunkMesh:
+    """``BuildChunk`` (Code/WorldRender.cpp:69-78) for one chunk."""
+    return rebuild_chunks(world, [(cx, cy, cz)])[0]

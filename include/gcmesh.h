@@ -1,0 +1,166 @@
+/*
+ * gcmesh — B200-native chunk mesher for Gamecraft: C ABI of libgcmesh.so.
+ *
+ * Drop-in boundary for ONE path of the reference: the per-chunk mesh build that the reference runs as
+ * work-queue jobs,
+ *     QueueAsync(state, BuildChunkAsync,    world, chunk,  OnChunkBuilt)      Code/WorldRender.cpp:69-78
+ *     QueueAsync(state, RebuildChunksAsync, world, &list,  OnChunksRebuilt)   Code/WorldRender.cpp:80-91
+ * (job type AsyncFunc, Code/Async.h:5-6).  Here the same work is ONE batched GPU submission:
+ * chunk block / light arrays in, per chunk one 12-byte vertex stream + five uint16 index streams out,
+ * byte-identical to BuildChunkAsync (Code/WorldRender.cpp:6-27) -> BuildBlock (:445-560).
+ *
+ * Plain C, plain pointers and sizes; no torch / CUDA types in any signature (streams travel as void*).
+ * There is no CPU fallback: every entry point that needs the GPU fails with GC_ERR_CUDA when none is usable.
+ * All functions return 0 (GC_OK) or a negative GcStatus; gcmesh_last_error() explains the last failure.
+ */
+#ifndef GCMESH_H
+#define GCMESH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- geometry and caps: mirrored from the reference ---- */
+#define GC_CHUNK_SIZE_H 32          /* Code/World.h:6  CHUNK_SIZE_H */
+#define GC_CHUNK_SIZE_V 64          /* Code/World.h:7  CHUNK_SIZE_V */
+#define GC_CHUNK_SIZE_3 65536       /* Code/World.h:16 CHUNK_SIZE_3 */
+#define GC_CHUNK_SIZE_2 1024        /* Code/World.h:17 CHUNK_SIZE_2 */
+#define GC_WORLD_CHUNK_HEIGHT 4     /* Code/World.h:21 */
+#define GC_WORLD_BLOCK_HEIGHT 256   /* Code/World.h:22 */
+#define GC_MAX_VERTICES 40000       /* Code/Mesh.h:5 */
+#define GC_MAX_INDICES 60000        /* Code/Mesh.h:6 */
+#define GC_MAX_QUADS 10000          /* MAX_VERTICES / 4 == MAX_INDICES / 6 */
+#define GC_VERTEX_BYTES 12          /* sizeof(VertexInfo), Code/Mesh.h:37-44 */
+#define GC_MAX_BLOCK_TYPES 256
+
+/* BlockMeshType, Code/Mesh.h:8-16 */
+enum { GC_MESH_OPAQUE = 0, GC_MESH_CUTOUT = 1, GC_MESH_TRANSPARENT = 2, GC_MESH_FLUID = 3, GC_MESH_MAGMA = 4, GC_MESH_TYPE_COUNT = 5 };
+/* CullValue, Code/Block.h:40-47 */
+enum { GC_CULL_OPAQUE = 0, GC_CULL_CUTOUT = 1, GC_CULL_TRANSPARENT = 2, GC_CULL_FLUID = 3, GC_CULL_INVISIBLE = 4 };
+
+typedef enum GcStatus
+{
+    GC_OK = 0,
+    GC_ERR_ARG = -1,        /* null pointer, out-of-range coordinate, edge chunk, bad table ... */
+    GC_ERR_CUDA = -2,       /* a CUDA runtime / driver call failed (including: no usable GPU) */
+    GC_ERR_CAPACITY = -3,   /* batch holds more chunks than it was created for */
+    GC_ERR_STATE = -4       /* results requested before gcmesh_wait / submit */
+} GcStatus;
+
+/* The fields of the reference's BlockData that the mesher reads (Code/Block.h:85-100; accessors Block.cpp:5-68). */
+typedef struct GcBlockInfo
+{
+    uint8_t textures[6]; /* texture-array layer per face: top, bottom, front, back, right, left (Block.h:49-57) */
+    uint8_t mesh_type;   /* GC_MESH_*: which index stream the block's quads go to (Block.cpp:25-28) */
+    uint8_t cull;        /* GC_CULL_* 0..4: a face is drawn iff cull(block) < cull(neighbour) (WorldRender.cpp:387-391) */
+    uint8_t alpha;       /* vertex alpha (Block.cpp:50-53) */
+    uint8_t invisible;   /* never emits quads (Block.cpp:20-23) */
+    uint8_t opaque;      /* lightStep == INT_MAX (Block.cpp:65-68): darkens the 3-sample corner average */
+    uint8_t reserved;
+} GcBlockInfo;
+
+/* Chunk position in the window: lcPos of the reference's Chunk (Code/World.h:71). */
+typedef struct GcChunkCoord { int32_t cx, cy, cz; } GcChunkCoord;
+
+/* Per-chunk result flags. */
+#define GC_CHUNK_OVERFLOW 1u   /* more than GC_MAX_QUADS quads: the reference asserts (WorldRender.cpp:558); nothing is emitted */
+#define GC_CHUNK_NO_SPACE 2u   /* the batch arena was too small for this chunk; nothing is emitted */
+
+/*
+ * Per-chunk result: the counters of the reference's MeshData / MeshIndexData (Code/Mesh.h:31-52) plus where the
+ * chunk's streams live in the batch arenas.  Vertices of chunk i: vertex arena bytes
+ * [quad_base*48, quad_base*48 + vert_count*12).  Index stream t: index arena uint16 elements
+ * [quad_base*6 + index_offset[t], ... + index_count[t]).
+ */
+typedef struct GcChunkOut
+{
+    uint32_t quad_base;
+    uint32_t vert_count;                         /* == chunk->totalVertices (WorldRender.cpp:559) unless flags != 0 */
+    uint32_t index_count[GC_MESH_TYPE_COUNT];    /* MeshIndexData::count per mesh type */
+    uint32_t index_offset[GC_MESH_TYPE_COUNT];   /* uint16 elements from the chunk's index segment start */
+    uint32_t quads;                              /* quads the chunk has (also when flags != 0) */
+    uint32_t flags;
+    uint32_t reserved[2];
+} GcChunkOut;
+
+/* The reference's MeshData (Code/Mesh.h:46-52) flattened: what BuildChunkAsync leaves in chunk->meshData. */
+typedef struct GcMeshData
+{
+    uint8_t vertices[GC_MAX_VERTICES * GC_VERTEX_BYTES];
+    uint16_t indices[GC_MESH_TYPE_COUNT][GC_MAX_INDICES];
+    int32_t index_count[GC_MESH_TYPE_COUNT];
+    int32_t vert_count;
+} GcMeshData;
+
+typedef struct GcContext GcContext;
+typedef struct GcWorld GcWorld;
+typedef struct GcBatch GcBatch;
+
+/* ---- context ---- */
+const char* gcmesh_version(void);
+const char* gcmesh_last_error(void);
+/* Binds to CUDA device `device`; work runs on `stream` (a cudaStream_t passed as void*; NULL = a private stream). */
+int gcmesh_create(int device, void* stream, GcContext** out);
+int gcmesh_destroy(GcContext* ctx);
+int gcmesh_set_stream(GcContext* ctx, void* stream);
+/* World::blockData (Code/World.h:166) as the mesher needs it.  n <= GC_MAX_BLOCK_TYPES; id 0 must be AIR
+ * (BuildChunkAsync skips it by id, WorldRender.cpp:19); kill_zone_id is what a cell below the world reads as
+ * (GetBlockSafe, World.cpp:422-428).  A context starts with the reference's 24-entry table (Block.cpp:139-276). */
+int gcmesh_set_block_table(GcContext* ctx, const GcBlockInfo* table, int n, int kill_zone_id);
+int gcmesh_default_block_table(GcBlockInfo* table, int* n, int* kill_zone_id);
+int gcmesh_synchronize(GcContext* ctx);
+
+/* ---- device world: the window of columns, World::groups (Code/World.h:131, World.cpp:153-160) ---- */
+/* size_x * size_z columns of 4 chunk bricks + a 32x32 surface map each, zero-initialised (all AIR, no light).
+ * slot(cx,cy,cz) = (cz*size_x + cx)*4 + cy; brick layout as the reference: x + 32*(y + 64*z) (World.cpp:278-281). */
+int gcmesh_world_create(GcContext* ctx, int size_x, int size_z, GcWorld** out);
+int gcmesh_world_destroy(GcWorld* world);
+/* Host -> device copy of one chunk's arrays (Chunk::blocks / sunlight / blockLight, World.h:74-78); NULL skips an array.
+ * Asynchronous on the context stream; the host arrays must stay valid until gcmesh_synchronize / gcmesh_wait. */
+int gcmesh_world_upload_chunk(GcWorld* world, int cx, int cy, int cz, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light);
+/* ChunkGroup::surface (World.h:94). */
+int gcmesh_world_upload_surface(GcWorld* world, int cx, int cz, const uint8_t* surface);
+/* Whole window at once from brick-major host arrays (nslots*65536 elements each, surface ncols*1024). */
+int gcmesh_world_upload_all(GcWorld* world, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface);
+/* Rows [cz0, cz1) of columns only (a z-slab of the window), same host layout as upload_all (pointers to the full arrays). */
+int gcmesh_world_upload_rows(GcWorld* world, int cz0, int cz1, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface);
+/* Raw device pointers of the four arenas, for device-resident producers (and for NCCL halo exchange). */
+int gcmesh_world_device_ptrs(GcWorld* world, void** blocks, void** sunlight, void** block_light, void** surface);
+/* Slab halo (multi-GPU): the z-boundary plane of one row of columns — for every column cx and chunk cy the
+ * 32x64 voxels at z = `z` of blocks (4096 B) + sunlight (2048 B) + blockLight (2048 B), then the surface row
+ * (32 B) per column.  pack gathers row `cz`, plane `z` into `device_buf`; unpack scatters it into row `cz`. */
+size_t gcmesh_world_halo_bytes(const GcWorld* world);
+int gcmesh_world_pack_halo(GcWorld* world, int cz, int z, void* device_buf);
+int gcmesh_world_unpack_halo(GcWorld* world, int cz, int z, const void* device_buf);
+
+/* ---- batches: one GPU submission = the reference's vector<Chunk*> job (WorldRender.cpp:29-37) ---- */
+/* Arenas for up to max_chunks chunks and max_quads quads in total (48 B of vertices + 12 B of indices per quad). */
+int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBatch** out);
+int gcmesh_batch_destroy(GcBatch* batch);
+/* Mesh `n` chunks of `world`.  Chunks on the window edge are rejected (the reference never meshes them,
+ * WorldRender.cpp:235).  Asynchronous; inputs must not change until gcmesh_wait (the reference's gating rule,
+ * WorldRender.cpp:265-277). `coords` is copied. */
+int gcmesh_submit(GcWorld* world, GcBatch* batch, const GcChunkCoord* coords, int n);
+int gcmesh_wait(GcBatch* batch);
+/* After gcmesh_wait: per-chunk descriptors (host memory owned by the batch, n entries, submit order). */
+int gcmesh_batch_results(GcBatch* batch, const GcChunkOut** out, int* n, uint64_t* total_quads);
+/* After gcmesh_wait: copy the used arena prefix to host memory (total_quads*48 and total_quads*12 bytes). */
+int gcmesh_batch_download(GcBatch* batch, void* vertices, void* indices);
+/* After gcmesh_wait: chunk i as the reference's MeshData. */
+int gcmesh_batch_fill_meshdata(GcBatch* batch, int i, GcMeshData* out);
+int gcmesh_batch_device_ptrs(GcBatch* batch, void** vertices, void** indices, void** chunk_out);
+/* Milliseconds the last submission's kernels took on the device (CUDA events on the context stream). */
+int gcmesh_batch_elapsed_ms(GcBatch* batch, float* ms);
+/* Number of kernel launches the last submission made. */
+int gcmesh_batch_launches(GcBatch* batch);
+
+/* Registers per thread, dynamic shared memory and block size of the mesh kernel (for reports). */
+int gcmesh_kernel_info(int* regs, int* smem_bytes, int* threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCMESH_H */

@@ -1,0 +1,155 @@
+// TEST INFRASTRUCTURE — sequential host walk over the kernel's phases.
+//
+// Runs the exact per-lane functions of gamecraft_b200/csrc/mesh_core.cuh (compiled for the host) in the
+// order the sm_100a kernel runs them, on ordinary memory instead of shared memory.  This checks the
+// bit-level logic (class planes, light packing, face masks, ranks, vertex packing) against the CPU oracle
+// on the build box, where there is no GPU.  It is NOT a fallback: nothing in the product links it.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../gamecraft_b200/csrc/mesh_core.cuh"
+#include "../../include/gcmesh.h"
+
+using namespace gc;
+
+namespace
+{
+struct EmuWorld
+{
+    int size_x, size_z;
+    const uint16_t* blocks;
+    const uint8_t* sun;
+    const uint8_t* light;
+    const uint8_t* surface;
+};
+
+const FaceDesc kFaces[6] = GC_FACE_TABLE;
+}
+
+extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks, const uint8_t* sun, const uint8_t* light,
+                                 const uint8_t* surface, const GcBlockInfo* table, int ntab, int kill_zone,
+                                 int cx, int cy, int cz, uint8_t* verts_out, uint16_t* idx_out, GcChunkOut* out)
+{
+    EmuWorld w = { size_x, size_z, blocks, sun, light, surface };
+    std::vector<LutEntry> lut(256);
+    std::vector<uint8_t> cls8(256);
+    std::vector<MatEntry> mat(256);
+    for (int i = 0; i < 256; i++)
+    {
+        const GcBlockInfo& b = table[i < ntab ? i : 0];
+        int emits = (i != 0) && !b.invisible && i < ntab;
+        uint32_t c = class_byte(b.cull, b.opaque, b.mesh_type, emits);
+        cls8[i] = (uint8_t)c;
+        lut[i] = spread_class(c);
+        mat[i].lo = b.textures[0] | (b.textures[1] << 8) | (b.textures[2] << 16) | ((uint32_t)b.textures[3] << 24);
+        mat[i].hi = b.textures[4] | (b.textures[5] << 8) | (b.alpha << 16);
+    }
+
+    std::vector<uint32_t> planes((size_t)kPlanes * kHaloRows, 0xDEADBEEFu);
+    std::vector<uint8_t> lt(kLtBytes, 0xAB);
+    std::vector<uint16_t> hx(kHaloRows, 0xFFFF);
+    uint8_t* planes_b = (uint8_t*)planes.data();
+    uint8_t* hx_b = (uint8_t*)hx.data();
+
+    // ---- phase 1 ----
+    for (int tz = -1; tz <= kTZ; tz++)
+    {
+        int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
+        int zz = tz & 31;
+        for (int ty = -1; ty <= kTY; ty++)
+        {
+            int wy = cy * 64 + ty;
+            int hr = hrow(ty, tz);
+            if (wy < 0 || wy >= 256)
+            {
+                uint32_t c = wy < 0 ? cls8[kill_zone] : cls8[0];
+                uint32_t lb = wy < 0 ? 0x00 : 0xFF;
+                for (int o = 0; o < 4; o++) p1_class_const_octet(c, planes_b, hr, o);
+                for (int x = 0; x < 32; x++) lt[hr * kLtStride + 4 + x] = (uint8_t)lb;
+                p1_xhalo_cell(c, lb, hx_b, lt.data(), hr, 0);
+                p1_xhalo_cell(c, lb, hx_b, lt.data(), hr, 1);
+                continue;
+            }
+            int ncy = wy >> 6, yy = wy & 63;
+            for (int dcx = -1; dcx <= 1; dcx++)
+            {
+                int64_t col = (int64_t)(cz + dcz) * w.size_x + (cx + dcx);
+                int64_t base = (col * 4 + ncy) * 65536 + 32 * (yy + 64 * zz);
+                const uint8_t* srow = w.surface + col * 1024 + zz * 32;
+                if (dcx == 0)
+                {
+                    const uint32_t* bw = (const uint32_t*)(w.blocks + base);
+                    for (int o = 0; o < 4; o++) p1_class_octet(bw[4 * o], bw[4 * o + 1], bw[4 * o + 2], bw[4 * o + 3], lut.data(), planes_b, hr, o);
+                    const uint32_t* sw = (const uint32_t*)(w.sun + base);
+                    const uint32_t* lw = (const uint32_t*)(w.light + base);
+                    const uint32_t* fw = (const uint32_t*)srow;
+                    for (int q = 0; q < 8; q++)
+                    {
+                        uint32_t v = p1_light4(sw[q], lw[q], fw[q], wy);
+                        memcpy(&lt[hr * kLtStride + 4 + 4 * q], &v, 4);
+                    }
+                }
+                else
+                {
+                    int xx = dcx < 0 ? 31 : 0;
+                    uint32_t id = w.blocks[base + xx] & 255u;
+                    uint32_t lb = light_byte_of(w.sun[base + xx], w.light[base + xx], srow[xx], wy);
+                    p1_xhalo_cell(cls8[id], lb, hx_b, lt.data(), hr, dcx < 0 ? 0 : 1);
+                }
+            }
+        }
+    }
+
+    // ---- phase 2 ----
+    std::vector<uint8_t> rowCnt(kCenterRows);
+    std::vector<uint32_t> rowTyp(kCenterRows);
+    uint32_t total = 0, ttot[kMeshTypes] = { 0, 0, 0, 0, 0 };
+    for (int R = 0; R < kCenterRows; R++)
+    {
+        RowFaces rf;
+        p2_row_faces(planes.data(), hx.data(), R >> 5, R & 31, rf);
+        int c; uint32_t t4;
+        p2_row_counts(rf, c, t4);
+        rowCnt[R] = (uint8_t)c; rowTyp[R] = t4;
+        total += c;
+        for (int t = 1; t < kMeshTypes; t++) ttot[t] += (t4 >> (8 * (t - 1))) & 255u;
+    }
+    ttot[0] = total - ttot[1] - ttot[2] - ttot[3] - ttot[4];
+
+    memset(out, 0, sizeof(*out));
+    out->quads = total;
+    if (total > (uint32_t)kMaxQuads) { out->flags = GC_CHUNK_OVERFLOW; return 0; }
+    out->vert_count = total * 4;
+    uint32_t type_off[kMeshTypes];
+    uint32_t acc = 0;
+    for (int t = 0; t < kMeshTypes; t++) { type_off[t] = acc; out->index_offset[t] = acc * 6; out->index_count[t] = ttot[t] * 6; acc += ttot[t]; }
+
+    // ---- phase 3a ----
+    std::vector<uint32_t> list(total + 1);
+    uint32_t rank = 0, trank[kMeshTypes] = { 0, 0, 0, 0, 0 };
+    for (int R = 0; R < kCenterRows; R++)
+    {
+        RowFaces rf;
+        p2_row_faces(planes.data(), hx.data(), R >> 5, R & 31, rf);
+        p3a_row(rf, R >> 5, R & 31, rank, trank, 0, list.data(), (uint32_t*)idx_out, type_off);
+        uint32_t t4 = rowTyp[R], c = rowCnt[R], nz = 0;
+        for (int t = 1; t < kMeshTypes; t++) { uint32_t k = (t4 >> (8 * (t - 1))) & 255u; trank[t] += k; nz += k; }
+        trank[0] += c - nz;
+        rank += c;
+    }
+
+    // ---- phase 3b ----
+    const uint16_t* cb = w.blocks + (((int64_t)cz * w.size_x + cx) * 4 + cy) * 65536;
+    for (uint32_t i = 0; i < total; i++)
+    {
+        uint32_t e = list[i];
+        int x = (e >> 3) & 31, tz = (e >> 8) & 31, ty = (e >> 13) & 63;
+        uint32_t id = cb[x + 32 * (ty + 64 * tz)] & 255u;
+        uint32_t v[12];
+        p3b_quad(e, kFaces[e & 7], lt.data(), planes.data() + P_OPAQUE * kHaloRows, hx.data(), mat[id], v);
+        memcpy(verts_out + (size_t)i * 48, v, 48);
+    }
+    return 0;
+}
