@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — chunks meshed/s of the B200 chunk mesher (and the reference CPU mesher beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload forest4096|...]
+
+One JSON line on stdout (rank 0).  A *step* is one pass of the hot path over one batch: every chunk of the
+workload is meshed once (all vertex + index streams written).  N = 1 workload: BASELINE.json configs[1], 4096
+seeded forest chunks (36x36-column window, inner 32x32 columns x 4 meshed).  N > 1: weak scaling — every rank
+owns a z-slab of 32 rows of columns (4096 chunks) of one 36 x (32N+4) world and exchanges the boundary voxel
+planes with its slab neighbours over NCCL send/recv inside the timed step.
+
+  value          whole-job chunks/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e            same metric through the host-facing C ABI: H2D of the window from pinned host memory + mesh + D2H of
+                 descriptors and the vertex/index streams, all inside the timed region
+  roofline       algorithmic bytes (262 424 + 60*quads per chunk) / mean kernel duration vs measured HBM peak
+  cpu_baseline   the reference's own mesher (oracle/_ref, compiled verbatim) — or its plain-C port — on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+ALG_BYTES_PER_CHUNK = 262144 + 256 + 24   # three arrays once + surface/4 + counters
+ALG_BYTES_PER_QUAD = 60                   # 4 x 12 B vertices + 6 x 2 B indices
+FALLBACK_HBM_GBS = 6650.0                 # B200_PROFILING.md fallback
+
+WORKLOADS = {
+    # name: (kind, meshed columns x, meshed rows z per rank, seed, radius)
+    "forest4096": ("forest", 32, 32, 1337, None),
+    "forest1024": ("forest", 16, 16, 1337, None),
+    "islands4096": ("islands", 32, 32, 4242, 512),
+    "checker1024": ("checker", 16, 16, 99, None),
+    "noise1024": ("noise", 16, 16, 77, None),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="forest4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_world(workload: str, rank: int, world_size: int):
+    """The rank's window: meshed rows + 2 margin rows/columns each side (one halo ring for the mesher, one more so
+    the halo ring's light is final, WorldRender.cpp:255-277).  Noise is sampled in world space, so overlapping rows
+    of neighbouring ranks hold identical voxels."""
+    from gamecraft_b200.worldgen import HostWorld, INT_MAX
+
+    kind, mx, mz, seed, radius = WORKLOADS[workload]
+    size_x, size_z = mx + 4, mz + 4
+    origin = (-(size_x // 2), rank * mz - (world_size * mz + 4) // 2)
+    t0 = time.time()
+    host = HostWorld(size_x, size_z, origin=origin)
+    host.build(kind, seed, radius=radius if radius else INT_MAX)
+    coords = host.interior_chunks(2)
+    return host, coords, time.time() - t0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def dram_traffic_per_launch(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the mesh kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+def cpu_reference_run(host, coords, seconds: float, threads: int | None = None):
+    """Times the reference CPU mesher on the host cores: oracle/_ref (the reference compiled verbatim) when that
+    library travelled with the repo, else the plain-C port.  Returns the cpu_baseline object."""
+    from oracle import binding as ob
+
+    threads = threads or os.cpu_count() or 1
+    if ob.have_ref() and host.size_x == host.size_z:
+        impl, kind = ob.RefWorld(host), "reference"
+    else:
+        impl, kind = ob.OracleWorld(host), "port"
+    n = len(coords)
+    sec, quads = impl.bench(coords, threads)                    # warm-up pass (page-in, allocator)
+    reps, total, total_q = 0, 0.0, 0
+    while total < seconds and reps < 50:
+        sec, quads = impl.bench(coords, threads)
+        total += sec; total_q += quads; reps += 1
+    one_n = max(1, min(n, int(n * 2.0 / max(total / reps * threads, 1e-6)) if reps else n))
+    sec1, _ = impl.bench(coords[:one_n], 1)                      # single-thread figure on a bounded prefix
+    return {
+        "value": n * reps / total, "unit": "chunks/s", "cores": threads, "kind": kind,
+        "sample": "%d x the full %d-chunk list, %d threads pulling chunks from one atomic counter (Async.cpp job queue shape)" % (reps, n, threads),
+        "quads_per_s": total_q / total, "one_thread_chunks_per_s": one_n / sec1,
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    host, coords, gen_s = make_world(args.workload, 0, 1)
+    threads = os.cpu_count() or 1
+    from oracle import binding as ob
+
+    impl, kind = (ob.RefWorld(host), "reference") if (ob.have_ref() and host.size_x == host.size_z) else (ob.OracleWorld(host), "port")
+    n = len(coords)
+    for _ in range(args.warmup):
+        impl.bench(coords, threads)
+    t, q = 0.0, 0
+    for _ in range(args.steps):
+        sec, quads = impl.bench(coords, threads)
+        t += sec; q += quads
+    value = n * args.steps / t
+    line = {
+        "impl": "reference", "metric": "chunks_meshed_per_s", "value": value, "unit": "chunks/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args.workload, 1, host, coords),
+        "quads_per_s": q / t,
+        "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": kind,
+                         "sample": "every step = the full %d-chunk list on %d host threads" % (n, threads)},
+        "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(workload, n_gpus, host, coords):
+    kind, mx, mz, seed, radius = WORKLOADS[workload]
+    return {
+        "workload": workload, "world": kind, "seed": seed, "chunks_per_gpu": int(len(coords)),
+        "window_columns_per_gpu": [host.size_x, host.size_z], "chunk_voxels": "32x64x32",
+        "parallelism": "z-slab per GPU, NCCL send/recv of boundary voxel planes" if n_gpus > 1 else "single GPU",
+        "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" % (len(coords) * 262144 / 1e6),
+    }
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from gamecraft_b200 import mesher
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size != args.gpus and world_size > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world_size))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the mesher has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    host, coords, gen_s = make_world(args.workload, rank, world_size)
+    n = len(coords)
+
+    stream = torch.cuda.current_stream()
+    ctx = mesher.Context(local_rank, stream.cuda_stream)
+    world = mesher.World(ctx, host.size_x, host.size_z)
+
+    # pinned host copies: the e2e leg uploads from these every step
+    pin = [torch.from_numpy(a).pin_memory() for a in (host.blocks, host.sun, host.light, host.surface)]
+
+    class Pinned:
+        size_x, size_z = host.size_x, host.size_z
+        blocks, sun, light, surface = [t.numpy() for t in pin]
+
+    world.upload(Pinned)
+    ctx.synchronize()
+
+    # size the arenas from a first pass
+    probe = mesher.Batch(ctx, n, n * mesher.MAX_QUADS // 8 + 1)
+    probe.submit(world, coords).wait()
+    desc, _ = probe.results()
+    total_quads = int(desc["quads"].sum())
+    if (desc["flags"] != 0).any():
+        probe.close()
+        probe = mesher.Batch(ctx, n, total_quads + 1)
+        probe.submit(world, coords).wait()
+        desc, _ = probe.results()
+    flags_bad = int((desc["flags"] != 0).sum())
+    probe.close()
+    batch = mesher.Batch(ctx, n, total_quads + 1)
+
+    # ---- slab halo exchange (N > 1): boundary voxel planes to / from the z-neighbours ----
+    halo = None
+    if world_size > 1:
+        hb = world.halo_bytes()
+        halo = {k: torch.empty(hb, dtype=torch.uint8, device="cuda") for k in ("send_up", "send_down", "recv_up", "recv_down")}
+        top_row, bottom_row = host.size_z - 3, 2          # last / first meshed row of columns
+
+    def exchange():
+        ops = []
+        if rank + 1 < world_size:
+            world.pack_halo(top_row, 31, halo["send_up"].data_ptr())
+            ops += [dist.P2POp(dist.isend, halo["send_up"], rank + 1), dist.P2POp(dist.irecv, halo["recv_up"], rank + 1)]
+        if rank > 0:
+            world.pack_halo(bottom_row, 0, halo["send_down"].data_ptr())
+            ops += [dist.P2POp(dist.isend, halo["send_down"], rank - 1), dist.P2POp(dist.irecv, halo["recv_down"], rank - 1)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        if rank + 1 < world_size:
+            world.unpack_halo(top_row + 1, 0, halo["recv_up"].data_ptr())
+        if rank > 0:
+            world.unpack_halo(bottom_row - 1, 31, halo["recv_down"].data_ptr())
+
+    def step():
+        launches = 0
+        if world_size > 1:
+            exchange()
+            launches += 2 * ((rank + 1 < world_size) + (rank > 0))
+        batch.submit(world, coords)
+        return launches + 1
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(max(args.warmup, 3)):
+        step()
+    batch.wait()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    barrier()
+    ev0.record()
+    launches = 0
+    for _ in range(args.steps):
+        launches += step()
+    ev1.record()
+    batch.wait()
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    # mean duration of the mesh kernel alone (the library's own events bracket exactly the launch)
+    for _ in range(min(args.steps, 10)):
+        batch.submit(world, coords).wait()
+        kernel_ms.append(batch.elapsed_ms())
+    clocks = sampler.stop()
+    desc, tq = batch.results()
+    assert int(desc["quads"].sum()) == total_quads
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    cq = torch.tensor([float(n), float(total_quads)], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cq, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    all_chunks, all_quads = float(cq[0].item()), float(cq[1].item())
+    ms_per_step = total_ms / args.steps
+    value = all_chunks / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-facing C ABI: pinned H2D + mesh + D2H of all results ----
+    e2e = None
+    if not args.no_e2e:
+        h_verts = torch.empty((total_quads * 4 + 4, 12), dtype=torch.uint8).pin_memory().numpy()
+        h_idx = torch.empty(total_quads * 6 + 6, dtype=torch.uint16).pin_memory().numpy()
+        h2d = sum(a.nbytes for a in (Pinned.blocks, Pinned.sun, Pinned.light, Pinned.surface))
+        d2h = n * 64 + total_quads * 60
+
+        def e2e_step():
+            world.upload(Pinned)
+            if world_size > 1:
+                exchange()
+            batch.submit(world, coords).wait()
+            batch.download(h_verts, h_idx)
+
+        ksteps = max(1, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / ksteps
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world_size > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": all_chunks / float(te.item()), "unit": "chunks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * float(te.item()), "steps": ksteps}
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        kms = float(np.mean(kernel_ms))
+        alg_bytes = n * ALG_BYTES_PER_CHUNK + total_quads * ALG_BYTES_PER_QUAD
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        line = {
+            "metric": "chunks_meshed_per_s", "value": value, "unit": "chunks/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args.workload, args.gpus, host, coords),
+            "quads_per_s": all_quads / (ms_per_step * 1e-3), "quads_per_chunk": total_quads / n, "chunks_flagged": flags_bad,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": dram_traffic_per_launch(args.workload), "peak_source": peak_src,
+                         "kernel": "gc_mesh_kernel", "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "gpu_launches": launches, "clocks": clocks, "kernel_info": ctx.kernel_info(), "worldgen_s": gen_s,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline and world_size == 1:
+            line["cpu_baseline"] = cpu_reference_run(host, coords, args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+
+    batch.close(); world.close(); ctx.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,253 @@
+"""Parity proper: the CUDA path, called through the C ABI (libgcmesh.so), against the oracle and the golden vectors."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import gcutil as util
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = util.load_golden()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gamecraft_b200 import mesher
+
+    c = mesher.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_meshes(ctx, host, coords, max_quads=None):
+    from gamecraft_b200 import mesher
+
+    world = mesher.World(ctx, host.size_x, host.size_z).upload(host)
+    batch = mesher.Batch(ctx, max(1, len(coords)), max_quads or max(1, len(coords)) * mesher.MAX_QUADS)
+    batch.submit(world, coords).wait()
+    out = batch.meshes()
+    desc, q = batch.results()
+    desc = desc.copy()
+    batch.close(); world.close()
+    return out, desc, q
+
+
+@pytest.mark.parametrize("key", sorted(GOLDEN))
+def test_gpu_matches_golden_and_oracle(ctx, key):
+    entry = GOLDEN[key]
+    w = util.golden_world(entry)
+    assert util.input_digest(w) == entry["inputs"]
+    coords = w.interior_chunks(1)
+    meshes, desc, q = gpu_meshes(ctx, w, coords)
+    o = ob.OracleWorld(w)
+    assert q == sum(v[0] for v in entry["chunks"].values()) // 4
+    for (cx, cy, cz), m in zip(coords, meshes):
+        assert util.mesh_signature(m) == entry["chunks"]["%d,%d,%d" % (cx, cy, cz)], "%s %s" % (key, (cx, cy, cz))
+        util.assert_same_mesh(m, o.build_chunk(cx, cy, cz), "%s %s" % (key, (cx, cy, cz)))
+
+
+@pytest.mark.parametrize("kind,size,seed", [("mixed", 6, 31), ("islands", 6, 12), ("noise", 4, 8), ("forest", 9, 2)])
+def test_gpu_matches_oracle_other_seeds(ctx, kind, size, seed):
+    kw = dict(radius=110, falloff=60) if kind in ("mixed", "islands") else {}
+    w = util.HostWorld(size, size + 1, origin=(-3, -3) if kw else (0, 0)).build(kind, seed, **kw)   # non-square window
+    coords = w.interior_chunks(1)
+    meshes, desc, q = gpu_meshes(ctx, w, coords)
+    o = ob.OracleWorld(w)
+    for (cx, cy, cz), m in zip(coords, meshes):
+        util.assert_same_mesh(m, o.build_chunk(cx, cy, cz), "%s %s" % (kind, (cx, cy, cz)))
+
+
+def test_gpu_empty_and_ragged_batches(ctx):
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(4, 4).build("mixed", 3, radius=100, falloff=60)
+    world = mesher.World(ctx, 4, 4).upload(w)
+    batch = mesher.Batch(ctx, 8, 80000)
+    batch.submit(world, np.zeros((0, 3), np.int32)).wait()          # empty submission
+    desc, q = batch.results()
+    assert len(desc) == 0 and q == 0 and batch.launches() == 0
+    o = ob.OracleWorld(w)
+    coords = np.array([(1, 0, 1), (2, 3, 2), (1, 0, 1), (2, 0, 1), (1, 0, 1)], np.int32)   # duplicates, odd count
+    for m, c in zip(batch.submit(world, coords).wait().meshes(), coords):
+        util.assert_same_mesh(m, o.build_chunk(*c), str(c))
+    m = mesher.build_chunk(world, 2, 1, 2)                             # the single-chunk call site
+    util.assert_same_mesh(m, o.build_chunk(2, 1, 2))
+    batch.close(); world.close()
+
+
+def test_gpu_all_air_world(ctx):
+    w = util.empty_world(3)
+    meshes, desc, q = gpu_meshes(ctx, w, w.interior_chunks(1))
+    assert q == 0 and all(m.vert_count == 0 for m in meshes) and not desc["flags"].any()
+
+
+def test_gpu_cap_edges_and_overflow_flag(ctx):
+    from gamecraft_b200 import mesher
+
+    w = util.cap_edge_world(pairs=1, singles=1665)                     # exactly 10 000 quads
+    meshes, desc, q = gpu_meshes(ctx, w, [(1, 1, 1)])
+    assert desc["flags"][0] == 0 and meshes[0].vert_count == 40000
+    util.assert_same_mesh(meshes[0], ob.OracleWorld(w).build_chunk(1, 1, 1))
+    w = util.cap_edge_world(pairs=2, singles=1664)                     # 10 004 quads
+    meshes, desc, q = gpu_meshes(ctx, w, [(1, 1, 1), (1, 0, 1)])
+    assert desc["flags"][0] == mesher.CHUNK_OVERFLOW and desc["quads"][0] == 10004 and meshes[0].vert_count == 0
+    assert desc["flags"][1] == 0
+    w = util.HostWorld(3, 3).build("stress", 1)                         # 196 608 quads per chunk
+    meshes, desc, q = gpu_meshes(ctx, w, w.interior_chunks(1), max_quads=1000)
+    assert (desc["flags"] == mesher.CHUNK_OVERFLOW).all() and (desc["quads"] == 196608).all() and q == 0
+
+
+def test_gpu_arena_too_small_is_flagged_not_overrun(ctx):
+    from gamecraft_b200 import mesher
+
+    w = util.golden_world(GOLDEN["checker5"])
+    coords = w.interior_chunks(1)
+    meshes, desc, q = gpu_meshes(ctx, w, coords, max_quads=3 * 9216 + 5)
+    ok = desc["flags"] == 0
+    assert ok.sum() >= 3 and (desc["flags"][~ok] == mesher.CHUNK_NO_SPACE).all() and (~ok).sum() > 0
+    o = ob.OracleWorld(w)
+    for c, m, f in zip(coords, meshes, ok):
+        if f:
+            util.assert_same_mesh(m, o.build_chunk(*c))
+        else:
+            assert m.vert_count == 0
+
+
+def test_gpu_custom_block_table(ctx):
+    from gamecraft_b200 import mesher
+
+    infos, kz = util.custom_table()
+    w = util.HostWorld(3, 3)
+    rng = np.random.default_rng(5)
+    w.blocks[:] = rng.integers(0, len(infos), w.blocks.shape, dtype=np.uint16) * (rng.random(w.blocks.shape) < 0.02)
+    w.sun[:] = rng.integers(0, 16, w.sun.shape, dtype=np.uint8)
+    w.light[:] = rng.integers(0, 16, w.light.shape, dtype=np.uint8)
+    w.compute_surface(threads=1)
+    o = ob.OracleWorld(w)
+    o.set_block_table(infos, kz)
+    c2 = mesher.Context(0)
+    c2.set_block_table([mesher.BlockInfo.from_buffer_copy(bytes(b)) for b in infos], kz)
+    meshes, desc, q = gpu_meshes(c2, w, w.interior_chunks(1))
+    for cy, m in enumerate(meshes):
+        want = o.build_chunk(1, cy, 1)
+        if want.overflow:
+            assert desc["flags"][cy] & mesher.CHUNK_OVERFLOW
+        else:
+            util.assert_same_mesh(m, want, "cy=%d" % cy)
+    c2.close()
+
+
+def test_gpu_argument_errors(ctx):
+    from gamecraft_b200 import mesher
+
+    world = mesher.World(ctx, 4, 4)
+    batch = mesher.Batch(ctx, 2, 100)
+    with pytest.raises(mesher.GcMeshError):
+        batch.submit(world, [(0, 0, 1)])           # edge column (WorldRender.cpp:235)
+    with pytest.raises(mesher.GcMeshError):
+        batch.submit(world, [(1, 4, 1)])           # chunk row outside 0..3
+    with pytest.raises(mesher.GcMeshError):
+        batch.submit(world, [(1, 0, 1)] * 3)       # more chunks than the batch holds
+    with pytest.raises(mesher.GcMeshError):
+        mesher.Batch(ctx, 2, 100).results()        # nothing submitted
+    batch.close(); world.close()
+
+
+def test_gpu_per_chunk_upload_and_fill_meshdata(ctx):
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(3, 3).build("mixed", 9, radius=100, falloff=60)
+    world = mesher.World(ctx, 3, 3)
+    for cz in range(3):
+        for cx in range(3):
+            for cy in range(4):
+                s = w.slot(cx, cy, cz)
+                world.upload_chunk(cx, cy, cz, w.blocks[s], w.sun[s], w.light[s])
+            world.upload_surface(cx, cz, w.surface[w.column(cx, cz)])
+    batch = mesher.Batch(ctx, 4, 40000)
+    batch.submit(world, [(1, cy, 1) for cy in range(4)]).wait()
+
+    class MeshData(ctypes.Structure):
+        _fields_ = [("vertices", ctypes.c_uint8 * 480000), ("indices", (ctypes.c_uint16 * 60000) * 5),
+                    ("index_count", ctypes.c_int32 * 5), ("vert_count", ctypes.c_int32)]
+
+    md = MeshData()
+    o = ob.OracleWorld(w)
+    for cy in range(4):
+        assert mesher.lib().gcmesh_batch_fill_meshdata(batch.h, cy, ctypes.byref(md)) == 0
+        want = o.build_chunk(1, cy, 1)
+        assert md.vert_count == want.vert_count
+        assert np.array_equal(np.frombuffer(md.vertices, np.uint8, md.vert_count * 12).reshape(-1, 12), want.vertices)
+        for t in range(5):
+            assert md.index_count[t] == len(want.indices[t])
+            assert np.array_equal(np.frombuffer(md.indices[t], np.uint16, md.index_count[t]), want.indices[t])
+    batch.close(); world.close()
+
+
+def test_gpu_halo_pack_unpack_kernels_match_host_layout(ctx):
+    import torch
+
+    from gamecraft_b200 import mesher, slab
+
+    w = util.HostWorld(5, 4).build("noise", 6)
+    world = mesher.World(ctx, 5, 4).upload(w)
+    buf = torch.zeros(world.halo_bytes(), dtype=torch.uint8, device="cuda")
+    assert world.halo_bytes() == slab.halo_bytes(5)
+    world.pack_halo(2, 31, buf.data_ptr())
+    ctx.synchronize()
+    assert np.array_equal(buf.cpu().numpy(), slab.pack_halo_host(w, 2, 31))
+    world.unpack_halo(0, 0, buf.data_ptr())            # scatter into another row / plane, then read it back packed
+    out = torch.zeros_like(buf)
+    world.pack_halo(0, 0, out.data_ptr())
+    ctx.synchronize()
+    assert torch.equal(out, buf)
+    world.close()
+
+
+def test_gpu_full_size_properties(ctx):
+    """BASELINE config 2 at full size (4096 forest chunks): size-independent properties + a sampled byte comparison."""
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(36, 36, origin=(-18, -18)).build("forest", 1337)
+    coords = w.interior_chunks(2)
+    assert len(coords) == 4096
+    world = mesher.World(ctx, 36, 36).upload(w)
+    batch = mesher.Batch(ctx, 4096, 4096 * 2500)
+    batch.submit(world, coords).wait()
+    desc, q = batch.results()
+    desc = desc.copy()
+    verts, idx = batch.download()
+    assert not desc["flags"].any() and int(desc["quads"].sum()) == q and q > 0
+    # segments tile the arena exactly once
+    order = np.argsort(desc["quad_base"], kind="stable")
+    nz = order[desc["quads"][order] > 0]
+    ends = desc["quad_base"][nz] + desc["quads"][nz]
+    assert desc["quad_base"][nz][0] == 0 and np.array_equal(desc["quad_base"][nz][1:], ends[:-1]) and ends[-1] == q
+    # every chunk: the five index streams reference each quad exactly once with SetIndices' pattern (Mesh.cpp:41-47)
+    pat = np.array([2, 1, 0, 3, 2, 0], np.int64)
+    for d in desc[::7]:
+        nq = int(d["quads"])
+        if nq == 0:
+            continue
+        seg = idx[int(d["quad_base"]) * 6: int(d["quad_base"]) * 6 + nq * 6].astype(np.int64).reshape(nq, 6)
+        o = seg[:, 2]
+        assert np.array_equal(seg, o[:, None] + pat[None, :]) and np.array_equal(np.sort(o), np.arange(nq) * 4)
+        assert int(d["index_count"].sum()) == nq * 6 and int(d["vert_count"]) == nq * 4
+    # determinism: a second submission gives identical bytes per chunk
+    batch.submit(world, coords).wait()
+    desc2, _ = batch.results()
+    verts2, idx2 = batch.download()
+    for i in range(0, 4096, 97):
+        a, b = desc[i], desc2[i]
+        assert a["quads"] == b["quads"]
+        n = int(a["quads"])
+        assert np.array_equal(verts[int(a["quad_base"]) * 4: int(a["quad_base"]) * 4 + n * 4], verts2[int(b["quad_base"]) * 4: int(b["quad_base"]) * 4 + n * 4])
+    # sampled byte comparison with the oracle
+    o = ob.OracleWorld(w)
+    meshes = batch.meshes()
+    rng = np.random.default_rng(0)
+    for i in rng.choice(4096, 96, replace=False):
+        util.assert_same_mesh(meshes[i], o.build_chunk(*coords[i]), str(coords[i]))
+    batch.close(); world.close()
