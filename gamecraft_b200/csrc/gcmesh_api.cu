@@ -114,15 +114,31 @@ struct GcBatch
     cudaEvent_t ev_start, ev_stop, ev_done;
 };
 
-static int encode_map(GcContext* ctx, CUtensorMap* map, CUtensorMapDataType type, int elem_bytes, void* base, size_t n_slots, int box_y)
+static int encode_map(GcContext* ctx, CUtensorMap* map, CUtensorMapDataType type, int elem_bytes, void* base, size_t n_slots, bool slab)
 {
-    // (x = 32, y = 64, z = 32, slot) over one brick arena; the reference's brick index x + 32*(y + 64*z) (World.cpp:278-281)
-    cuuint64_t dims[4] = { 32, 64, 32, (cuuint64_t)n_slots };
-    cuuint64_t strides[3] = { (cuuint64_t)(32 * elem_bytes), (cuuint64_t)(32 * 64 * elem_bytes), (cuuint64_t)(GC_CHUNK_SIZE_3 * elem_bytes) };
-    cuuint32_t box[4] = { 32, (cuuint32_t)box_y, 1, 1 };
-    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    // One brick arena viewed as a 4-D tensor (the reference's brick index is x + 32*(y + 64*z), World.cpp:278-281):
+    //   row  map: (x = 32, y = 64, z = 32, slot), box (32, 1, 1, 1)  — one x-row (the y halo rows of a slab)
+    //   slab map: (x*y8 = 256, y/8 = 8, z = 32, slot), box (256, 8, 1, 1) — one whole z-slab; x and 8 y-rows are
+    //             contiguous, so the same 2048 voxels are described as 8 long rows instead of 64 short ones and
+    //             the TMA unit issues 8 requests of 512 B / 256 B instead of 64 of 64 B / 32 B
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4], estr[4] = { 1, 1, 1, 1 };
+    if (slab)
+    {
+        dims[0] = 256; dims[1] = 8; dims[2] = 32; dims[3] = (cuuint64_t)n_slots;
+        strides[0] = (cuuint64_t)(256 * elem_bytes);
+        box[0] = 256; box[1] = 8; box[2] = 1; box[3] = 1;
+    }
+    else
+    {
+        dims[0] = 32; dims[1] = 64; dims[2] = 32; dims[3] = (cuuint64_t)n_slots;
+        strides[0] = (cuuint64_t)(32 * elem_bytes);
+        box[0] = 32; box[1] = 1; box[2] = 1; box[3] = 1;
+    }
+    strides[1] = (cuuint64_t)(32 * 64 * elem_bytes);
+    strides[2] = (cuuint64_t)(GC_CHUNK_SIZE_3 * elem_bytes);
     CUresult r = ctx->encode(map, type, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
     {
         char buf[64];
@@ -272,12 +288,12 @@ int gcmesh_world_create(GcContext* ctx, int size_x, int size_z, GcWorld** out)
     if (e == cudaSuccess) e = cudaMemsetAsync(w->d_surface, 0, w->n_cols * GC_CHUNK_SIZE_2, ctx->stream);
     if (e != cudaSuccess) { gcmesh_world_destroy(w); return fail(GC_ERR_CUDA, "world allocation", cudaGetErrorString(e)); }
     int st = GC_OK;
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_slab, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots, 64);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_row, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots, 1);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots, 64);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_row, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots, 1);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.light_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_light, w->n_slots, 64);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.light_row, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_light, w->n_slots, 1);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_slab, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots, true);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_row, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots, false);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots, true);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_row, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots, false);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.light_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_light, w->n_slots, true);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.light_row, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_light, w->n_slots, false);
     if (st != GC_OK) { gcmesh_world_destroy(w); return st; }
     *out = w;
     return GC_OK;

@@ -3,9 +3,10 @@
 // One persistent CTA per SM; each CTA pulls chunks from a work counter and, per chunk:
 //   P0  neighbour columns' surface window -> shared memory
 //   P1  34 z-slabs (32x64 voxels + 2 halo rows, three arrays) are staged by TMA tensor-map box loads
-//       (cp.async.bulk.tensor.4d, 4-stage mbarrier ring, issued by one elected lane) and converted by
-//       role-specialised warps into the resident on-chip form (class bit planes + packed light tile);
-//       five free-running warps gather the x = -1 / x = 32 halo columns
+//       (cp.async.bulk.tensor.4d, 6-stage mbarrier ring, issued by one elected lane) and converted by
+//       role-specialised warps into the resident on-chip form (class bit planes + packed light tile)
+//   P1x the x = -1 / x = 32 halo cells that some face or light footprint will actually read (rows next to an
+//       emitting boundary voxel) are gathered from the neighbour columns; air chunks gather nothing
 //   P2  face masks per row (bitwise, 32 voxels per op), per-row counts, per-layer warp reductions, scan,
 //       ONE atomicAdd reserves the chunk's contiguous segment in the batch arenas
 //   P3  per batch of layers: (a) rows -> ordered quad list + index words, (b) one thread per quad ->
@@ -21,11 +22,13 @@ namespace
 {
 constexpr int NT = kMeshThreads;          // 20 warps
 constexpr int kWarps = NT / 32;
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 constexpr int kSlabs = kRowsZ;            // 34 z-slabs per chunk: tz = -1 .. 32
-constexpr int kClassWarps = 9, kLightWarps = 5, kHaloWarps = 5;
+constexpr int kClassWarps = 9, kLightWarps = 9;
 constexpr int kConsumerWarps = kClassWarps + kLightWarps;  // warps that wait on the TMA ring
-static_assert(1 + kClassWarps + kLightWarps + kHaloWarps == kWarps, "warp roles");
+static_assert(1 + kClassWarps + kLightWarps <= kWarps, "warp roles");
+constexpr int kHaloTasks = kHaloRows * 2;
+constexpr int kHaloPerThread = (kHaloTasks + NT - 1) / NT;
 
 // ---- one staging slot: a z-slab of the three arrays, each TMA destination 128-byte aligned ----
 constexpr int kStBlocks = 0;                       // [64][32] u16
@@ -40,18 +43,18 @@ constexpr int kStLightHi = kStLightLo + 128;
 constexpr int kStageBytes = kStLightHi + 128;      // 8960
 static_assert(kStageBytes % 128 == 0, "stage alignment");
 constexpr int kListCap = kStages * kStageBytes / 4;  // the quad list reuses the staging ring in P3
-static_assert(kListCap >= 32 * 6 * 32, "one layer (<= 6144 quads) must fit the list");
+static_assert(kListCap >= kMaxQuads, "a whole chunk's quads must fit the list");
 
 // ---- shared-memory carve-up (dynamic, 1024-aligned base) ----
 constexpr int kOffStages = 0;
-constexpr int kOffPlanes = kOffStages + kStages * kStageBytes;            // 35840
+constexpr int kOffPlanes = kOffStages + kStages * kStageBytes;            // 53760
 constexpr int kOffLt = kOffPlanes + kPlanes * kHaloRows * 4;              // +71808
 constexpr int kOffHx = kOffLt + kLtBytes;                                 // +89760
-constexpr int kOffRowCnt = kOffHx + ((kHaloRows * 2 + 15) & ~15);
-constexpr int kOffRowTyp = kOffRowCnt + kCenterRows;
-constexpr int kOffSurf = kOffRowTyp + kCenterRows * 4;                    // [34][32] centre-x rows
-constexpr int kOffSurfX = kOffSurf + kRowsZ * 32;                         // [2][48] x = -1 / x = 32 columns (unused by v1 gathers)
-constexpr int kOffLut = kOffSurfX + 96;
+constexpr int kOffBv = kOffHx + ((kHaloRows * 2 + 15) & ~15);             // [2][2256]: emitting voxel at x = 0 / x = 31 of the row
+constexpr int kBvStride = (kHaloRows + 15) & ~15;
+constexpr int kOffSurf = kOffBv + 2 * kBvStride;                          // [34][32] centre-x surface rows
+constexpr int kOffSurfMax = kOffSurf + kRowsZ * 32;                       // [34][4] max surface per 8-voxel octet
+constexpr int kOffLut = kOffSurfMax + ((kRowsZ * 4 + 15) & ~15);
 constexpr int kOffMat = kOffLut + 256 * 8;
 constexpr int kOffCls = kOffMat + 256 * 8;
 constexpr int kOffLayerCnt = kOffCls + 256;                               // u32[64]
@@ -61,11 +64,11 @@ constexpr int kOffLayerBase = kOffLayerTypB + 256;                        // u32
 constexpr int kOffLayerTypBaseA = kOffLayerBase + 272;
 constexpr int kOffLayerTypBaseB = kOffLayerTypBaseA + 256;
 constexpr int kOffFaces = kOffLayerTypBaseB + 256;                        // FaceDesc[6], 16 B each
-constexpr int kOffBars = kOffFaces + 128;                                 // full[4], empty[4]
-constexpr int kOffCtx = kOffBars + 64;
-constexpr int kSmemBytes = kOffCtx + 128;
-static_assert(kOffPlanes % 16 == 0 && kOffLt % 16 == 0 && kOffHx % 16 == 0 && kOffRowTyp % 16 == 0 && kOffSurf % 16 == 0, "align");
-static_assert(kOffLut % 8 == 0 && kOffMat % 8 == 0 && kOffBars % 8 == 0 && kOffLayerCnt % 4 == 0, "align");
+constexpr int kOffBars = kOffFaces + 96;                                  // full[6], empty[6]
+constexpr int kOffCtx = kOffBars + 2 * kStages * 8;
+constexpr int kSmemBytes = kOffCtx + 64;
+static_assert(kOffPlanes % 16 == 0 && kOffLt % 16 == 0 && kOffHx % 16 == 0 && kOffBv % 16 == 0 && kOffSurf % 16 == 0, "align");
+static_assert(kOffLut % 8 == 0 && kOffMat % 8 == 0 && kOffBars % 8 == 0 && kOffLayerCnt % 4 == 0 && kOffCtx % 4 == 0, "align");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 struct alignas(16) FaceDesc16 { FaceDesc f; uint8_t pad[3]; };
@@ -101,10 +104,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware instead of spinning
         : "memory");
     return ok != 0;
 }
@@ -114,7 +117,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity))
     {
-        if (++spins > (1u << 24))
+        if (++spins > (1u << 22))
         {
             if (error_flag) atomicExch(error_flag, 1);
             __trap();
@@ -166,9 +169,9 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     uint8_t* s_lt = smem + kOffLt;
     uint16_t* s_hx = reinterpret_cast<uint16_t*>(smem + kOffHx);
     uint8_t* s_hx_b = smem + kOffHx;
-    uint8_t* s_rowcnt = smem + kOffRowCnt;
-    uint32_t* s_rowtyp = reinterpret_cast<uint32_t*>(smem + kOffRowTyp);
+    uint8_t* s_bv = smem + kOffBv;
     uint8_t* s_surf = smem + kOffSurf;
+    uint8_t* s_surfmax = smem + kOffSurfMax;
     LutEntry* s_lut = reinterpret_cast<LutEntry*>(smem + kOffLut);
     MatEntry* s_mat = reinterpret_cast<MatEntry*>(smem + kOffMat);
     uint8_t* s_cls = smem + kOffCls;
@@ -235,14 +238,18 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         const int cx = s_ctx->cx, cy = s_ctx->cy, cz = s_ctx->cz;
         const int lwy = cy * kTY;
 
-        // centre-x surface rows of the three columns (cz-1, cz, cz+1): s_surf[(tz+1)*32 + x]
-        for (int i = tid; i < kRowsZ * 8; i += NT)
+        // centre-x surface rows of the three columns (cz-1, cz, cz+1): s_surf[(tz+1)*32 + x], and their per-octet maxima
+        if (tid < kRowsZ * 4)
         {
-            const int r = i >> 3, q = i & 7;
+            const int r = tid >> 2, q = tid & 3;
             const int tz = r - 1;
             const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
             const size_t col = (size_t)(cz + dcz) * p.size_x + cx;
-            reinterpret_cast<uint32_t*>(s_surf)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.surface + col * 1024 + (tz & 31) * 32) + q);
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p.surface + col * 1024 + (tz & 31) * 32) + q);
+            reinterpret_cast<uint2*>(s_surf)[tid] = v;
+            const uint32_t m = max4(v.x, v.y);
+            const uint32_t m2 = max4(m, m >> 16);
+            s_surfmax[tid] = (uint8_t)max4(m2, m2 >> 8);
         }
         __syncthreads();
 
@@ -324,12 +331,13 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         }
         else if (warp <= kClassWarps)
         {
-            // ---- class warps: block ids -> 8 class bit planes ----
+            // ---- class warps: block ids -> 8 class bit planes (+ "boundary voxel emits" flags for P1x) ----
             const int task = (warp - 1) * 32 + lane;          // (row, octet)
             const bool active = task < kRowsY * 4;
             const int ty = (task >> 2) - 1, o = task & 3;
             const int wy = lwy + ty;
             const int row_off = ty < 0 ? kStBlocksLo : (ty >= kTY ? kStBlocksHi : kStBlocks + ty * 64);
+            const bool centre_y = ty >= 0 && ty < kTY;
             for (int s = 0; s < kSlabs; s++)
             {
                 const uint32_t g = slab_seq + s;
@@ -338,27 +346,31 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 if (active)
                 {
                     const int hr = hrow(ty, s - 1);
+                    uint32_t vis = 0;
                     if (wy < 0) p1_class_const_octet(kill_cls, s_planes_b, hr, o);
                     else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_class_const_octet(air_cls, s_planes_b, hr, o);
                     else
                     {
                         const uint4 v = *reinterpret_cast<const uint4*>(s_stage + stage * kStageBytes + row_off + o * 16);
-                        p1_class_octet(v.x, v.y, v.z, v.w, s_lut, s_planes_b, hr, o);
+                        vis = p1_class_octet(v.x, v.y, v.z, v.w, s_lut, s_planes_b, hr, o);
                     }
+                    const bool centre = centre_y && s >= 1 && s <= kTZ;
+                    if (o == 0) s_bv[hr] = centre ? (uint8_t)(vis & 1u) : (uint8_t)0;
+                    if (o == 3) s_bv[kBvStride + hr] = centre ? (uint8_t)(vis >> 7) : (uint8_t)0;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&s_bars[kStages + stage]));
             }
         }
-        else if (warp <= kClassWarps + kLightWarps)
+        else if (warp <= kConsumerWarps)
         {
             // ---- light warps: sunlight + blockLight + surface -> packed light tile ----
-            const int task = (warp - 1 - kClassWarps) * 32 + lane;   // (row, half)
-            const bool active = task < kRowsY * 2;
-            const int ty = (task >> 1) - 1, h = task & 1;
+            const int task = (warp - 1 - kClassWarps) * 32 + lane;   // (row, octet)
+            const bool active = task < kRowsY * 4;
+            const int ty = (task >> 2) - 1, o = task & 3;
             const int wy = lwy + ty;
-            const int sun_off = (ty < 0 ? kStSunLo : (ty >= kTY ? kStSunHi : kStSun + ty * 32)) + h * 16;
-            const int light_off = (ty < 0 ? kStLightLo : (ty >= kTY ? kStLightHi : kStLight + ty * 32)) + h * 16;
+            const int sun_off = (ty < 0 ? kStSunLo : (ty >= kTY ? kStSunHi : kStSun + ty * 32)) + o * 8;
+            const int light_off = (ty < 0 ? kStLightLo : (ty >= kTY ? kStLightHi : kStLight + ty * 32)) + o * 8;
             for (int s = 0; s < kSlabs; s++)
             {
                 const uint32_t g = slab_seq + s;
@@ -366,73 +378,75 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 mbar_wait(smem_u32(&s_bars[stage]), (g / kStages) & 1, p.error_flag);
                 if (active)
                 {
-                    uint32_t* dst = reinterpret_cast<uint32_t*>(s_lt + hrow(ty, s - 1) * kLtStride + 4 + h * 16);
-                    if (wy < 0) { dst[0] = 0u; dst[1] = 0u; dst[2] = 0u; dst[3] = 0u; }
-                    else if (wy >= GC_WORLD_BLOCK_HEIGHT) { dst[0] = ~0u; dst[1] = ~0u; dst[2] = ~0u; dst[3] = ~0u; }
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(s_lt + hrow(ty, s - 1) * kLtStride + 4 + o * 8);
+                    if (wy < 0) { dst[0] = 0u; dst[1] = 0u; }
+                    else if (wy >= GC_WORLD_BLOCK_HEIGHT) { dst[0] = ~0u; dst[1] = ~0u; }
                     else
                     {
                         const uint8_t* st = s_stage + stage * kStageBytes;
-                        const uint4 sn = *reinterpret_cast<const uint4*>(st + sun_off);
-                        const uint4 bl = *reinterpret_cast<const uint4*>(st + light_off);
-                        const uint4 sf = *reinterpret_cast<const uint4*>(s_surf + s * 32 + h * 16);
-                        dst[0] = p1_light4(sn.x, bl.x, sf.x, wy);
-                        dst[1] = p1_light4(sn.y, bl.y, sf.y, wy);
-                        dst[2] = p1_light4(sn.z, bl.z, sf.z, wy);
-                        dst[3] = p1_light4(sn.w, bl.w, sf.w, wy);
+                        const uint2 bl = *reinterpret_cast<const uint2*>(st + light_off);
+                        if (wy >= (int)s_surfmax[s * 4 + o])
+                        {
+                            dst[0] = p1_light4_above(bl.x);
+                            dst[1] = p1_light4_above(bl.y);
+                        }
+                        else
+                        {
+                            const uint2 sn = *reinterpret_cast<const uint2*>(st + sun_off);
+                            const uint2 sf = *reinterpret_cast<const uint2*>(s_surf + s * 32 + o * 8);
+                            dst[0] = p1_light4(sn.x, bl.x, sf.x, wy);
+                            dst[1] = p1_light4(sn.y, bl.y, sf.y, wy);
+                        }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&s_bars[kStages + stage]));
             }
         }
-        else
+        slab_seq += kSlabs;
+        __syncthreads();
+
+        // ================= P1x: the x-halo cells that will be read =================
         {
-            // ---- halo warps: the x = -1 / x = 32 columns, gathered straight from global memory ----
-            const int task = (warp - 1 - kConsumerWarps) * 32 + lane;   // (row, side)
-            const bool active = task < kRowsY * 2;
-            const int ty = (task >> 1) - 1, side = task & 1;
-            const int wy = lwy + ty;
-            const bool in_world = wy >= 0 && wy < GC_WORLD_BLOCK_HEIGHT;
-            const int xx = side ? 0 : 31;
-            constexpr int kBatch = 6;
-            if (active)
+            uint32_t id[kHaloPerThread], sn[kHaloPerThread], bl[kHaloPerThread], sf[kHaloPerThread];
+            uint32_t need = 0;
+#pragma unroll
+            for (int k = 0; k < kHaloPerThread; k++)
             {
-                for (int s0 = 0; s0 < kSlabs; s0 += kBatch)
+                const int task = tid + k * NT;
+                if (task < kHaloTasks)
                 {
-                    uint32_t id[kBatch], sn[kBatch], bl[kBatch], sf[kBatch];
-#pragma unroll
-                    for (int b = 0; b < kBatch; b++)
+                    const int hr = task >> 1, side = task & 1;
+                    const int ty = hr / kRowsZ - 1, tz = hr % kRowsZ - 1;
+                    const int wy = lwy + ty;
+                    if (wy >= 0 && wy < GC_WORLD_BLOCK_HEIGHT && xhalo_needed(s_bv + side * kBvStride, hr))
                     {
-                        const int s = s0 + b;
-                        if (s < kSlabs && in_world)
-                        {
-                            const int tz = s - 1;
-                            const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
-                            const int zz = tz & 31;
-                            const size_t col = (size_t)(cz + dcz) * p.size_x + (cx + (side ? 1 : -1));
-                            const size_t vox = (col * 4 + (wy >> 6)) * GC_CHUNK_SIZE_3 + xx + 32 * ((wy & 63) + 64 * zz);
-                            id[b] = __ldg(p.blocks + vox);
-                            sn[b] = __ldg(p.sun + vox);
-                            bl[b] = __ldg(p.light + vox);
-                            sf[b] = __ldg(p.surface + col * 1024 + zz * 32 + xx);
-                        }
-                    }
-#pragma unroll
-                    for (int b = 0; b < kBatch; b++)
-                    {
-                        const int s = s0 + b;
-                        if (s < kSlabs)
-                        {
-                            const int hr = hrow(ty, s - 1);
-                            if (wy < 0) p1_xhalo_cell(kill_cls, 0x00u, s_hx_b, s_lt, hr, side);
-                            else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_xhalo_cell(air_cls, 0xFFu, s_hx_b, s_lt, hr, side);
-                            else p1_xhalo_cell(s_cls[id[b] & 255u], light_byte_of(sn[b], bl[b], sf[b], wy), s_hx_b, s_lt, hr, side);
-                        }
+                        need |= 1u << k;
+                        const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
+                        const int zz = tz & 31, xx = side ? 0 : 31;
+                        const size_t col = (size_t)(cz + dcz) * p.size_x + (cx + (side ? 1 : -1));
+                        const size_t vox = (col * 4 + (wy >> 6)) * GC_CHUNK_SIZE_3 + xx + 32 * ((wy & 63) + 64 * zz);
+                        id[k] = __ldg(p.blocks + vox);
+                        sn[k] = __ldg(p.sun + vox);
+                        bl[k] = __ldg(p.light + vox);
+                        sf[k] = __ldg(p.surface + col * 1024 + zz * 32 + xx);
                     }
                 }
             }
+#pragma unroll
+            for (int k = 0; k < kHaloPerThread; k++)
+            {
+                const int task = tid + k * NT;
+                if (task < kHaloTasks)
+                {
+                    const int hr = task >> 1, side = task & 1;
+                    const int wy = lwy + hr / kRowsZ - 1;
+                    if (wy < 0) p1_xhalo_cell(kill_cls, 0x00u, s_hx_b, s_lt, hr, side);
+                    else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_xhalo_cell(air_cls, 0xFFu, s_hx_b, s_lt, hr, side);
+                    else if ((need >> k) & 1u) p1_xhalo_cell(s_cls[id[k] & 255u], light_byte_of(sn[k], bl[k], sf[k], wy), s_hx_b, s_lt, hr, side);
+                }
+            }
         }
-        slab_seq += kSlabs;
         __syncthreads();
 
         // ================= P2: face masks, counts, scan, reservation =================
@@ -442,9 +456,6 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             p2_row_faces(s_planes, s_hx, layer, lane, rf);
             int c; uint32_t t4;
             p2_row_counts(rf, c, t4);
-            const int R = layer * 32 + lane;
-            s_rowcnt[R] = (uint8_t)c;
-            s_rowtyp[R] = t4;
             uint32_t ta = (t4 & 255u) | (((t4 >> 8) & 255u) << 16);
             uint32_t tb = ((t4 >> 16) & 255u) | ((t4 >> 24) << 16);
             uint32_t cc = (uint32_t)c;
@@ -519,7 +530,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         // ================= P3: emission =================
         if (s_ctx->emit)
         {
-            const uint32_t quad_base = s_ctx->quad_base;
+            const uint32_t quad_base = s_ctx->quad_base, total = s_ctx->total;
             uint32_t type_off[kMeshTypes];
 #pragma unroll
             for (int t = 0; t < kMeshTypes; t++) type_off[t] = s_ctx->type_off[t];
@@ -527,55 +538,42 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             uint4* vtx = reinterpret_cast<uint4*>(p.vertex_arena) + (size_t)quad_base * 3;
             const uint16_t* chunk_blocks = p.blocks + ((size_t)(cz * p.size_x + cx) * 4 + cy) * GC_CHUNK_SIZE_3;
 
-            int l0 = 0;
-            while (l0 < kTY)
+            // ---- 3a: rows -> ordered quad list (whole chunk fits the staging ring) + index words ----
+            for (int layer = warp; layer < kTY; layer += kWarps)
             {
-                // batch of layers whose quads fit the list
-                const uint32_t base0 = s_layer_base[l0];
-                int l1 = l0 + 1;
-                while (l1 < kTY && s_layer_base[l1 + 1] - base0 <= (uint32_t)kListCap) l1++;
-                const uint32_t nb = s_layer_base[l1] - base0;
-                if (nb > 0)
+                if (s_layer_base[layer + 1] == s_layer_base[layer]) continue;   // warp-uniform
+                RowFaces rf;
+                p2_row_faces(s_planes, s_hx, layer, lane, rf);
+                int ci; uint32_t t4;
+                p2_row_counts(rf, ci, t4);
+                const uint32_t c = (uint32_t)ci;
+                const uint32_t ta = (t4 & 255u) | (((t4 >> 8) & 255u) << 16);
+                const uint32_t tb = ((t4 >> 16) & 255u) | ((t4 >> 24) << 16);
+                const uint32_t ce = warp_incl_scan(c, lane) - c;
+                const uint32_t ae = warp_incl_scan(ta, lane) - ta + s_layer_typbase_a[layer];
+                const uint32_t be = warp_incl_scan(tb, lane) - tb + s_layer_typbase_b[layer];
+                if (c)
                 {
-                    // ---- 3a: rows -> ordered list + index words ----
-                    for (int layer = l0 + warp; layer < l1; layer += kWarps)
-                    {
-                        if (s_layer_base[layer + 1] == s_layer_base[layer]) continue;   // warp-uniform
-                        const int R = layer * 32 + lane;
-                        const uint32_t c = s_rowcnt[R], t4 = s_rowtyp[R];
-                        uint32_t ta = (t4 & 255u) | (((t4 >> 8) & 255u) << 16);
-                        uint32_t tb = ((t4 >> 16) & 255u) | ((t4 >> 24) << 16);
-                        const uint32_t ce = warp_incl_scan(c, lane) - c;
-                        const uint32_t ae = warp_incl_scan(ta, lane) - ta + s_layer_typbase_a[layer];
-                        const uint32_t be = warp_incl_scan(tb, lane) - tb + s_layer_typbase_b[layer];
-                        if (c)
-                        {
-                            RowFaces rf;
-                            p2_row_faces(s_planes, s_hx, layer, lane, rf);
-                            uint32_t trank[kMeshTypes];
-                            const uint32_t rank0 = s_layer_base[layer] + ce;
-                            trank[1] = ae & 0xFFFFu; trank[2] = ae >> 16; trank[3] = be & 0xFFFFu; trank[4] = be >> 16;
-                            trank[0] = rank0 - trank[1] - trank[2] - trank[3] - trank[4];
-                            p3a_row(rf, layer, lane, rank0, trank, base0, s_list, idx_words, type_off);
-                        }
-                    }
-                    __syncthreads();
-                    // ---- 3b: one thread per quad ----
-                    for (uint32_t i = tid; i < nb; i += NT)
-                    {
-                        const uint32_t e = s_list[i];
-                        const int x = (e >> 3) & 31, tz = (e >> 8) & 31, ty = (e >> 13) & 63;
-                        const uint32_t id = __ldg(chunk_blocks + x + 32 * (ty + 64 * tz)) & 255u;
-                        uint32_t v[12];
-                        p3b_quad(e, s_faces[e & 7].f, s_lt, s_planes + P_OPAQUE * kHaloRows, s_hx, s_mat[id], v);
-                        uint4* dst = vtx + (size_t)(base0 + i) * 3;
-                        dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
-                        dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
-                        dst[2] = make_uint4(v[8], v[9], v[10], v[11]);
-                    }
-                    __syncthreads();
+                    uint32_t trank[kMeshTypes];
+                    const uint32_t rank0 = s_layer_base[layer] + ce;
+                    trank[1] = ae & 0xFFFFu; trank[2] = ae >> 16; trank[3] = be & 0xFFFFu; trank[4] = be >> 16;
+                    trank[0] = rank0 - trank[1] - trank[2] - trank[3] - trank[4];
+                    p3a_row(rf, layer, lane, rank0, trank, 0u, s_list, idx_words, type_off);
                 }
-                l0 = l1;
+            }
+            __syncthreads();
+            // ---- 3b: one thread per quad ----
+            for (uint32_t i = tid; i < total; i += NT)
+            {
+                const uint32_t e = s_list[i];
+                const int x = (e >> 3) & 31, tz = (e >> 8) & 31, ty = (e >> 13) & 63;
+                const uint32_t id = __ldg(chunk_blocks + x + 32 * (ty + 64 * tz)) & 255u;
+                uint32_t v[12];
+                p3b_quad(e, s_faces[e & 7].f, s_lt, s_planes + P_OPAQUE * kHaloRows, s_hx, s_mat[id], v);
+                uint4* dst = vtx + (size_t)i * 3;
+                dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                dst[2] = make_uint4(v[8], v[9], v[10], v[11]);
             }
         }
         // the staging ring was used as the quad list by the generic proxy: order it before the next TMA writes

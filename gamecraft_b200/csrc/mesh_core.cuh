@@ -115,7 +115,8 @@ GC_HD LutEntry spread_class(uint32_t cls)
 
 // Eight consecutive voxels (x = 8o .. 8o+7) of one row -> one byte of each class plane.
 // ids: 4 words holding 8 uint16 block ids.  planes_b = (uint8_t*)planes.
-GC_HD void p1_class_octet(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, const LutEntry* lut, uint8_t* planes_b, int hr, int o)
+// Returns the octet's 8-bit mask of emitting voxels (mesh type != 7).
+GC_HD uint32_t p1_class_octet(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, const LutEntry* lut, uint8_t* planes_b, int hr, int o)
 {
     uint32_t lo, hi;
     const bool uniform = (w0 == w1) && (w2 == w3) && (w0 == w2) && ((w0 >> 16) == (w0 & 0xFFFFu));
@@ -145,6 +146,7 @@ GC_HD void p1_class_octet(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, co
         p[(k * kHaloRows) * 4] = (uint8_t)(lo >> (8 * k));
         p[((k + 4) * kHaloRows) * 4] = (uint8_t)(hi >> (8 * k));
     }
+    return ~((hi >> 8) & (hi >> 16) & (hi >> 24)) & 255u;
 }
 
 // A whole row whose cells all have the same class byte (rows outside the world: KILL_ZONE below, AIR above,
@@ -159,19 +161,47 @@ GC_HD void p1_class_const_octet(uint32_t cls, uint8_t* planes_b, int hr, int o)
 // Four voxels of light: sun/bl/surf hold 4 bytes each (x ascending from the low byte); wy = world y of the row.
 //   sun' = wy >= surface ? 15 : max(sun, 1)      GetSunlight, Lighting.cpp:69-79 (MAX_LIGHT / MIN_LIGHT, Lighting.h:5-6)
 //   out  = sun' << 4 | blockLight
+// Plain 32-bit ops only (byte lanes never carry into each other):
+//   max(s,1), s <= 15:  nz = ((s + 15) >> 4) & 1;  s | (nz ^ 1)
+//   wy >= surf, 8 bit:  7-bit compare by borrow-free subtraction ((wy7 | 0x80) - surf7 keeps bit 7 iff wy7 >= surf7),
+//                       then the top bits: ge = top(wy) ? (ge7 | ~top(surf)) : (ge7 & ~top(surf))
 GC_HD uint32_t p1_light4(uint32_t sun, uint32_t bl, uint32_t surf, int wy)
 {
-    uint32_t above = cmpge4((uint32_t)wy * 0x01010101u, surf);
-    uint32_t s = max4(sun & 0x0F0F0F0Fu, 0x01010101u);
-    s = (above & 0x0F0F0F0Fu) | (~above & s);
+    const uint32_t a7 = ((uint32_t)(wy & 0x7F) * 0x01010101u) | 0x80808080u;
+    const uint32_t hi = (wy & 0x80) ? 0xFFFFFFFFu : 0u;
+    const uint32_t t = a7 - (surf & 0x7F7F7F7Fu);
+    const uint32_t ge = (t & ~surf) | (hi & (t | ~surf));
+    const uint32_t above15 = ((ge >> 7) & 0x01010101u) * 15u;
+    uint32_t s = sun & 0x0F0F0F0Fu;
+    const uint32_t nz = ((s + 0x0F0F0F0Fu) >> 4) & 0x01010101u;
+    s |= (nz ^ 0x01010101u) | above15;
     return (s << 4) | (bl & 0x0F0F0F0Fu);
 }
+
+// Same for cells known to lie at or above their column's surface (sun reads 15 whatever is stored).
+GC_HD uint32_t p1_light4_above(uint32_t bl) { return 0xF0F0F0F0u | (bl & 0x0F0F0F0Fu); }
 
 // One cell of the x = -1 / x = 32 halo columns.  side 0: x = -1, side 1: x = 32.
 GC_HD void p1_xhalo_cell(uint32_t cls, uint32_t light_byte, uint8_t* hx_b, uint8_t* lt, int hr, int side)
 {
     hx_b[hr * 2 + side] = (uint8_t)cls;
     lt[hr * kLtStride + (side ? 36 : 3)] = (uint8_t)light_byte;
+}
+
+// Is halo cell (side, row hr) ever read?  Only by faces / light footprints of an emitting voxel at x = 0 (side 0) or
+// x = 31 (side 1) in one of the 3x3 rows around it.  bv[hr] = that voxel emits (0 for rows outside the chunk).
+GC_HD uint32_t xhalo_needed(const uint8_t* bv, int hr)
+{
+    uint32_t n = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dz = -1; dz <= 1; dz++)
+        {
+            const int r = hr + dy * kRowsZ + dz;
+            if (r >= 0 && r < kHaloRows) n |= bv[r];
+        }
+    return n;
 }
 
 GC_HD uint32_t light_byte_of(uint32_t sun, uint32_t bl, uint32_t surf, int wy)

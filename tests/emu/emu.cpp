@@ -53,11 +53,14 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
     uint8_t* planes_b = (uint8_t*)planes.data();
     uint8_t* hx_b = (uint8_t*)hx.data();
 
-    // ---- phase 1 ----
+    // ---- phase 1: centre-x columns of every row (class planes + light), like the kernel's class / light warps ----
+    std::vector<uint8_t> bv(2 * kHaloRows, 0);   // [side][hr]: emitting voxel at x = 0 / x = 31 (centre rows only)
     for (int tz = -1; tz <= kTZ; tz++)
     {
         int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
         int zz = tz & 31;
+        int64_t col = (int64_t)(cz + dcz) * w.size_x + cx;
+        const uint8_t* srow = w.surface + col * 1024 + zz * 32;
         for (int ty = -1; ty <= kTY; ty++)
         {
             int wy = cy * 64 + ty;
@@ -68,37 +71,47 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
                 uint32_t lb = wy < 0 ? 0x00 : 0xFF;
                 for (int o = 0; o < 4; o++) p1_class_const_octet(c, planes_b, hr, o);
                 for (int x = 0; x < 32; x++) lt[hr * kLtStride + 4 + x] = (uint8_t)lb;
-                p1_xhalo_cell(c, lb, hx_b, lt.data(), hr, 0);
-                p1_xhalo_cell(c, lb, hx_b, lt.data(), hr, 1);
                 continue;
             }
-            int ncy = wy >> 6, yy = wy & 63;
-            for (int dcx = -1; dcx <= 1; dcx++)
+            int64_t base = (col * 4 + (wy >> 6)) * 65536 + 32 * ((wy & 63) + 64 * zz);
+            const uint32_t* bw = (const uint32_t*)(w.blocks + base);
+            const bool centre = ty >= 0 && ty < kTY && tz >= 0 && tz < kTZ;
+            for (int o = 0; o < 4; o++)
             {
-                int64_t col = (int64_t)(cz + dcz) * w.size_x + (cx + dcx);
-                int64_t base = (col * 4 + ncy) * 65536 + 32 * (yy + 64 * zz);
-                const uint8_t* srow = w.surface + col * 1024 + zz * 32;
-                if (dcx == 0)
-                {
-                    const uint32_t* bw = (const uint32_t*)(w.blocks + base);
-                    for (int o = 0; o < 4; o++) p1_class_octet(bw[4 * o], bw[4 * o + 1], bw[4 * o + 2], bw[4 * o + 3], lut.data(), planes_b, hr, o);
-                    const uint32_t* sw = (const uint32_t*)(w.sun + base);
-                    const uint32_t* lw = (const uint32_t*)(w.light + base);
-                    const uint32_t* fw = (const uint32_t*)srow;
-                    for (int q = 0; q < 8; q++)
-                    {
-                        uint32_t v = p1_light4(sw[q], lw[q], fw[q], wy);
-                        memcpy(&lt[hr * kLtStride + 4 + 4 * q], &v, 4);
-                    }
-                }
-                else
-                {
-                    int xx = dcx < 0 ? 31 : 0;
-                    uint32_t id = w.blocks[base + xx] & 255u;
-                    uint32_t lb = light_byte_of(w.sun[base + xx], w.light[base + xx], srow[xx], wy);
-                    p1_xhalo_cell(cls8[id], lb, hx_b, lt.data(), hr, dcx < 0 ? 0 : 1);
-                }
+                uint32_t vis = p1_class_octet(bw[4 * o], bw[4 * o + 1], bw[4 * o + 2], bw[4 * o + 3], lut.data(), planes_b, hr, o);
+                if (o == 0) bv[hr] = centre ? (vis & 1u) : 0;
+                if (o == 3) bv[kHaloRows + hr] = centre ? (vis >> 7) : 0;
             }
+            const uint32_t* sw = (const uint32_t*)(w.sun + base);
+            const uint32_t* lw = (const uint32_t*)(w.light + base);
+            const uint32_t* fw = (const uint32_t*)srow;
+            for (int q = 0; q < 8; q++)
+            {
+                // the kernel takes the "all above the surface" shortcut per octet; both forms must agree
+                int smax = 0;
+                for (int x = (q / 2) * 8; x < (q / 2) * 8 + 8; x++) smax = srow[x] > smax ? srow[x] : smax;
+                uint32_t v = wy >= smax ? p1_light4_above(lw[q]) : p1_light4(sw[q], lw[q], fw[q], wy);
+                if (v != p1_light4(sw[q], lw[q], fw[q], wy)) return -7;
+                memcpy(&lt[hr * kLtStride + 4 + 4 * q], &v, 4);
+            }
+        }
+    }
+    // ---- phase 1x: only the x-halo cells something will read; the others stay poisoned (0xFFFF / 0xAB) ----
+    for (int hr = 0; hr < kHaloRows; hr++)
+    {
+        int ty = hr / kRowsZ - 1, tz = hr % kRowsZ - 1;
+        int wy = cy * 64 + ty;
+        for (int side = 0; side < 2; side++)
+        {
+            if (wy < 0) { p1_xhalo_cell(cls8[kill_zone], 0x00, hx_b, lt.data(), hr, side); continue; }
+            if (wy >= 256) { p1_xhalo_cell(cls8[0], 0xFF, hx_b, lt.data(), hr, side); continue; }
+            if (!xhalo_needed(bv.data() + side * kHaloRows, hr)) continue;
+            int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
+            int zz = tz & 31, xx = side ? 0 : 31;
+            int64_t col = (int64_t)(cz + dcz) * w.size_x + (cx + (side ? 1 : -1));
+            int64_t vox = (col * 4 + (wy >> 6)) * 65536 + xx + 32 * ((wy & 63) + 64 * zz);
+            uint32_t lb = light_byte_of(w.sun[vox], w.light[vox], w.surface[col * 1024 + zz * 32 + xx], wy);
+            p1_xhalo_cell(cls8[w.blocks[vox] & 255u], lb, hx_b, lt.data(), hr, side);
         }
     }
 
