@@ -104,6 +104,8 @@ struct GcBatch
     uint16_t* d_indices;
     unsigned long long* d_cursor;   // [0] quad cursor
     int32_t* d_counters;            // [0] work counter, [1] error flag
+    unsigned long long* d_prof;     // 16 cycle counters when GCMESH_PROFILE=1
+    unsigned long long h_prof[16];
     GcChunkOut* h_out;              // pinned
     GcChunkCoord* h_coords;         // pinned staging for coords
     unsigned long long* h_cursor;   // pinned
@@ -404,6 +406,7 @@ int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBa
     if (e == cudaSuccess) e = cudaMalloc(&b->d_indices, (size_t)max_quads * 12);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_cursor, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_counters, sizeof(int32_t) * 2);
+    if (e == cudaSuccess && getenv("GCMESH_PROFILE")) e = cudaMalloc(&b->d_prof, sizeof(unsigned long long) * 16);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_out, sizeof(GcChunkOut) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_coords, sizeof(GcChunkCoord) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_cursor, sizeof(unsigned long long));
@@ -421,7 +424,7 @@ int gcmesh_batch_destroy(GcBatch* b)
     if (!b) return GC_OK;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    cudaFree(b->d_coords); cudaFree(b->d_out); cudaFree(b->d_vertices); cudaFree(b->d_indices); cudaFree(b->d_cursor); cudaFree(b->d_counters);
+    cudaFree(b->d_coords); cudaFree(b->d_out); cudaFree(b->d_vertices); cudaFree(b->d_indices); cudaFree(b->d_cursor); cudaFree(b->d_counters); cudaFree(b->d_prof);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_coords) cudaFreeHost(b->h_coords);
     if (b->h_cursor) cudaFreeHost(b->h_cursor);
@@ -465,7 +468,8 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
         p.coords = b->d_coords; p.n_chunks = n; p.out = b->d_out;
         p.vertex_arena = b->d_vertices; p.index_arena = b->d_indices; p.max_quads = b->max_quads;
         p.quad_cursor = b->d_cursor; p.work_counter = b->d_counters; p.tables = ctx->d_tables;
-        p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma;
+        p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma; p.prof = b->d_prof;
+        if (b->d_prof) GC_CUDA(cudaMemsetAsync(b->d_prof, 0, sizeof(unsigned long long) * 16, s));
         const int grid = n < ctx->num_sms ? n : ctx->num_sms;
         GC_CUDA(launch_mesh(p, w->maps, grid, s));
         b->launches = 1;
@@ -474,6 +478,7 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
     GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaMemcpyAsync(b->h_counters, b->d_counters, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, s));
+    if (b->d_prof) GC_CUDA(cudaMemcpyAsync(b->h_prof, b->d_prof, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaEventRecord(b->ev_done, s));
     b->state = 1;
     return GC_OK;
@@ -550,6 +555,15 @@ int gcmesh_batch_elapsed_ms(GcBatch* b, float* ms)
 }
 
 int gcmesh_batch_launches(GcBatch* b) { return b ? b->launches : 0; }
+
+// Development aid (GCMESH_PROFILE=1): the 16 in-kernel cycle counters of the last submission.
+int gcmesh_batch_profile(GcBatch* b, unsigned long long* out16)
+{
+    if (!b || !out16) return fail(GC_ERR_ARG, "null argument");
+    if (!b->d_prof) return fail(GC_ERR_STATE, "profiling is off (set GCMESH_PROFILE=1 before creating the batch)");
+    memcpy(out16, b->h_prof, sizeof(b->h_prof));
+    return GC_OK;
+}
 
 int gcmesh_kernel_info(int* regs, int* smem_bytes, int* threads)
 {

@@ -24,9 +24,14 @@ constexpr int NT = kMeshThreads;          // 20 warps
 constexpr int kWarps = NT / 32;
 constexpr int kStages = 6;
 constexpr int kSlabs = kRowsZ;            // 34 z-slabs per chunk: tz = -1 .. 32
-constexpr int kClassWarps = 9, kLightWarps = 9;
-constexpr int kConsumerWarps = kClassWarps + kLightWarps;  // warps that wait on the TMA ring
-static_assert(1 + kClassWarps + kLightWarps <= kWarps, "warp roles");
+// P1 consumers: kTeams teams of kTeamWarps warps (half class, half light).  A team owns every kTeams-th slab, so
+// several slabs are being converted at once and each lane carries a few independent tasks (ILP) — one warp per
+// task per slab left the SM waiting on its own ALU latency.
+constexpr int kTeams = 3, kTeamWarps = 6, kTeamRoleLanes = (kTeamWarps / 2) * 32;
+constexpr int kConsumerWarps = kTeams * kTeamWarps;
+constexpr int kTasksPerSlab = kRowsY * 4;                  // (row, octet) for class and again for light
+constexpr int kTasksPerLane = (kTasksPerSlab + kTeamRoleLanes - 1) / kTeamRoleLanes;
+static_assert(1 + kConsumerWarps <= kWarps, "warp roles");
 constexpr int kHaloTasks = kHaloRows * 2;
 constexpr int kHaloPerThread = (kHaloTasks + NT - 1) / NT;
 
@@ -78,6 +83,8 @@ struct ChunkCtx
 {
     int32_t chunk;        // index into coords, or -1 when the work is exhausted
     int32_t cx, cy, cz;
+    int32_t any_emit;     // some voxel of the chunk emits quads (else P1x / P2 / P3 are skipped)
+    int32_t any_bv;       // some emitting voxel sits at x = 0 or x = 31 (else no x-halo cell is ever read)
     int32_t emit;         // P3 runs
     uint32_t quad_base;   // arena segment (quads)
     uint32_t total;
@@ -155,6 +162,11 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
+#define GC_PROF_MARK(slot)                                                            \
+    do {                                                                              \
+        if (p.prof && tid == 0) { const long long t_ = clock64(); atomicAdd(p.prof + (slot), (unsigned long long)(t_ - prof_t)); prof_t = t_; } \
+    } while (0)
+
 // =====================================================================================================
 __global__ void __launch_bounds__(NT, 1)
 gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
@@ -202,7 +214,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         for (int i = 0; i < kStages; i++)
         {
             mbar_init(smem_u32(&s_bars[i]), 1);                         // full: the producer's expect_tx arrive
-            mbar_init(smem_u32(&s_bars[kStages + i]), kConsumerWarps);  // empty: one arrive per consumer warp
+            mbar_init(smem_u32(&s_bars[kStages + i]), kTeamWarps);      // empty: one arrive per warp of the owning team
         }
         fence_barrier_init();
         if (p.use_tma)
@@ -217,6 +229,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     __syncthreads();
 
     uint32_t slab_seq = 0;  // slabs staged so far by this CTA (ring position / parity source)
+    long long prof_t = clock64();
 
     for (;;)
     {
@@ -226,6 +239,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             int c = atomicAdd(p.work_counter, 1);
             if (c >= p.n_chunks) c = -1;
             s_ctx->chunk = c;
+            s_ctx->any_emit = 0; s_ctx->any_bv = 0;
             if (c >= 0)
             {
                 GcChunkCoord cc = p.coords[c];
@@ -253,6 +267,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         }
         __syncthreads();
 
+        GC_PROF_MARK(0);
         // ================= P1: stage + convert =================
         if (warp == 0)
         {
@@ -270,7 +285,12 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 const bool has_lo = lwy > 0, has_hi = lwy + kTY < GC_WORLD_BLOCK_HEIGHT;
                 uint8_t* st = s_stage + stage * kStageBytes;
 
-                if (g >= kStages) mbar_wait(empty, ((g / kStages) + 1) & 1, p.error_flag);
+                if (g >= kStages)
+                {
+                    const long long w0 = p.prof ? clock64() : 0;
+                    mbar_wait(empty, ((g / kStages) + 1) & 1, p.error_flag);
+                    if (p.prof && lane == 0) atomicAdd(p.prof + 8, (unsigned long long)(clock64() - w0));
+                }
 
                 if (p.use_tma)
                 {
@@ -329,73 +349,85 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 }
             }
         }
-        else if (warp <= kClassWarps)
-        {
-            // ---- class warps: block ids -> 8 class bit planes (+ "boundary voxel emits" flags for P1x) ----
-            const int task = (warp - 1) * 32 + lane;          // (row, octet)
-            const bool active = task < kRowsY * 4;
-            const int ty = (task >> 2) - 1, o = task & 3;
-            const int wy = lwy + ty;
-            const int row_off = ty < 0 ? kStBlocksLo : (ty >= kTY ? kStBlocksHi : kStBlocks + ty * 64);
-            const bool centre_y = ty >= 0 && ty < kTY;
-            for (int s = 0; s < kSlabs; s++)
-            {
-                const uint32_t g = slab_seq + s;
-                const int stage = g % kStages;
-                mbar_wait(smem_u32(&s_bars[stage]), (g / kStages) & 1, p.error_flag);
-                if (active)
-                {
-                    const int hr = hrow(ty, s - 1);
-                    uint32_t vis = 0;
-                    if (wy < 0) p1_class_const_octet(kill_cls, s_planes_b, hr, o);
-                    else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_class_const_octet(air_cls, s_planes_b, hr, o);
-                    else
-                    {
-                        const uint4 v = *reinterpret_cast<const uint4*>(s_stage + stage * kStageBytes + row_off + o * 16);
-                        vis = p1_class_octet(v.x, v.y, v.z, v.w, s_lut, s_planes_b, hr, o);
-                    }
-                    const bool centre = centre_y && s >= 1 && s <= kTZ;
-                    if (o == 0) s_bv[hr] = centre ? (uint8_t)(vis & 1u) : (uint8_t)0;
-                    if (o == 3) s_bv[kBvStride + hr] = centre ? (uint8_t)(vis >> 7) : (uint8_t)0;
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&s_bars[kStages + stage]));
-            }
-        }
         else if (warp <= kConsumerWarps)
         {
-            // ---- light warps: sunlight + blockLight + surface -> packed light tile ----
-            const int task = (warp - 1 - kClassWarps) * 32 + lane;   // (row, octet)
-            const bool active = task < kRowsY * 4;
-            const int ty = (task >> 2) - 1, o = task & 3;
-            const int wy = lwy + ty;
-            const int sun_off = (ty < 0 ? kStSunLo : (ty >= kTY ? kStSunHi : kStSun + ty * 32)) + o * 8;
-            const int light_off = (ty < 0 ? kStLightLo : (ty >= kTY ? kStLightHi : kStLight + ty * 32)) + o * 8;
-            for (int s = 0; s < kSlabs; s++)
+            const int cw = warp - 1;
+            const int team = cw / kTeamWarps, wt = cw % kTeamWarps;
+            const bool is_class = wt < kTeamWarps / 2;
+            const int l96 = (wt % (kTeamWarps / 2)) * 32 + lane;       // lane index within the team's class / light half
+            for (int s = team; s < kSlabs; s += kTeams)
             {
                 const uint32_t g = slab_seq + s;
                 const int stage = g % kStages;
-                mbar_wait(smem_u32(&s_bars[stage]), (g / kStages) & 1, p.error_flag);
-                if (active)
                 {
-                    uint32_t* dst = reinterpret_cast<uint32_t*>(s_lt + hrow(ty, s - 1) * kLtStride + 4 + o * 8);
-                    if (wy < 0) { dst[0] = 0u; dst[1] = 0u; }
-                    else if (wy >= GC_WORLD_BLOCK_HEIGHT) { dst[0] = ~0u; dst[1] = ~0u; }
-                    else
+                    const long long w0 = p.prof ? clock64() : 0;
+                    mbar_wait(smem_u32(&s_bars[stage]), (g / kStages) & 1, p.error_flag);
+                    if (p.prof && lane == 0 && cw == 0) atomicAdd(p.prof + 9, (unsigned long long)(clock64() - w0));
+                    if (p.prof && lane == 0 && cw == kTeamWarps / 2) atomicAdd(p.prof + 10, (unsigned long long)(clock64() - w0));
+                }
+                const uint8_t* st = s_stage + stage * kStageBytes;
+                const bool centre_z = s >= 1 && s <= kTZ;
+                if (is_class)
+                {
+                    // ---- block ids -> 8 class bit planes (+ "boundary voxel emits" flags for P1x) ----
+#pragma unroll
+                    for (int k = 0; k < kTasksPerLane; k++)
                     {
-                        const uint8_t* st = s_stage + stage * kStageBytes;
-                        const uint2 bl = *reinterpret_cast<const uint2*>(st + light_off);
-                        if (wy >= (int)s_surfmax[s * 4 + o])
+                        const int task = l96 + k * kTeamRoleLanes;        // (row, octet)
+                        if (task < kTasksPerSlab)
                         {
-                            dst[0] = p1_light4_above(bl.x);
-                            dst[1] = p1_light4_above(bl.y);
+                            const int ty = (task >> 2) - 1, o = task & 3;
+                            const int wy = lwy + ty;
+                            const int hr = hrow(ty, s - 1);
+                            uint32_t vis = 0;
+                            if (wy < 0) p1_class_const_octet(kill_cls, s_planes_b, hr, o);
+                            else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_class_const_octet(air_cls, s_planes_b, hr, o);
+                            else
+                            {
+                                const int row_off = ty < 0 ? kStBlocksLo : (ty >= kTY ? kStBlocksHi : kStBlocks + ty * 64);
+                                const uint4 v = *reinterpret_cast<const uint4*>(st + row_off + o * 16);
+                                vis = p1_class_octet(v.x, v.y, v.z, v.w, s_lut, s_planes_b, hr, o);
+                            }
+                            if (!(centre_z && ty >= 0 && ty < kTY)) vis = 0;
+                            if (o == 0) s_bv[hr] = (uint8_t)(vis & 1u);
+                            if (o == 3) s_bv[kBvStride + hr] = (uint8_t)(vis >> 7);
+                            if (vis) s_ctx->any_emit = 1;
+                            if ((o == 0 && (vis & 1u)) || (o == 3 && (vis >> 7))) s_ctx->any_bv = 1;
                         }
-                        else
+                    }
+                }
+                else
+                {
+                    // ---- sunlight + blockLight + surface -> packed light tile ----
+#pragma unroll
+                    for (int k = 0; k < kTasksPerLane; k++)
+                    {
+                        const int task = l96 + k * kTeamRoleLanes;        // (row, octet)
+                        if (task < kTasksPerSlab)
                         {
-                            const uint2 sn = *reinterpret_cast<const uint2*>(st + sun_off);
-                            const uint2 sf = *reinterpret_cast<const uint2*>(s_surf + s * 32 + o * 8);
-                            dst[0] = p1_light4(sn.x, bl.x, sf.x, wy);
-                            dst[1] = p1_light4(sn.y, bl.y, sf.y, wy);
+                            const int ty = (task >> 2) - 1, o = task & 3;
+                            const int wy = lwy + ty;
+                            uint32_t* dst = reinterpret_cast<uint32_t*>(s_lt + hrow(ty, s - 1) * kLtStride + 4 + o * 8);
+                            if (wy < 0) { dst[0] = 0u; dst[1] = 0u; }
+                            else if (wy >= GC_WORLD_BLOCK_HEIGHT) { dst[0] = ~0u; dst[1] = ~0u; }
+                            else
+                            {
+                                const int sun_off = (ty < 0 ? kStSunLo : (ty >= kTY ? kStSunHi : kStSun + ty * 32)) + o * 8;
+                                const int light_off = (ty < 0 ? kStLightLo : (ty >= kTY ? kStLightHi : kStLight + ty * 32)) + o * 8;
+                                const uint2 bl = *reinterpret_cast<const uint2*>(st + light_off);
+                                if (wy >= (int)s_surfmax[s * 4 + o])
+                                {
+                                    dst[0] = p1_light4_above(bl.x);
+                                    dst[1] = p1_light4_above(bl.y);
+                                }
+                                else
+                                {
+                                    const uint2 sn = *reinterpret_cast<const uint2*>(st + sun_off);
+                                    const uint2 sf = *reinterpret_cast<const uint2*>(s_surf + s * 32 + o * 8);
+                                    dst[0] = p1_light4(sn.x, bl.x, sf.x, wy);
+                                    dst[1] = p1_light4(sn.y, bl.y, sf.y, wy);
+                                }
+                            }
                         }
                     }
                 }
@@ -405,8 +437,11 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         }
         slab_seq += kSlabs;
         __syncthreads();
+        GC_PROF_MARK(1);
 
         // ================= P1x: the x-halo cells that will be read =================
+        const bool any_emit = s_ctx->any_emit != 0, any_bv = s_ctx->any_bv != 0;
+        if (any_emit)
         {
             uint32_t id[kHaloPerThread], sn[kHaloPerThread], bl[kHaloPerThread], sf[kHaloPerThread];
             uint32_t need = 0;
@@ -419,7 +454,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                     const int hr = task >> 1, side = task & 1;
                     const int ty = hr / kRowsZ - 1, tz = hr % kRowsZ - 1;
                     const int wy = lwy + ty;
-                    if (wy >= 0 && wy < GC_WORLD_BLOCK_HEIGHT && xhalo_needed(s_bv + side * kBvStride, hr))
+                    if (any_bv && wy >= 0 && wy < GC_WORLD_BLOCK_HEIGHT && xhalo_needed(s_bv + side * kBvStride, hr))
                     {
                         need |= 1u << k;
                         const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
@@ -449,7 +484,22 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         }
         __syncthreads();
 
+        GC_PROF_MARK(2);
         // ================= P2: face masks, counts, scan, reservation =================
+        if (!any_emit)
+        {
+            // nothing in the chunk can emit (all AIR / invisible): empty result, no scan, no emission
+            if (tid == 0)
+            {
+                GcChunkOut o;
+                o.quad_base = 0; o.vert_count = 0; o.quads = 0; o.flags = 0; o.reserved[0] = 0; o.reserved[1] = 0;
+                for (int t = 0; t < kMeshTypes; t++) { o.index_count[t] = 0; o.index_offset[t] = 0; }
+                p.out[chunk] = o;
+            }
+            __syncthreads();   // s_ctx is rewritten by thread 0 at the top of the loop
+            GC_PROF_MARK(3);
+            continue;
+        }
         for (int layer = warp; layer < kTY; layer += kWarps)
         {
             RowFaces rf;
@@ -527,6 +577,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         }
         __syncthreads();
 
+        GC_PROF_MARK(3);
         // ================= P3: emission =================
         if (s_ctx->emit)
         {
@@ -562,6 +613,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 }
             }
             __syncthreads();
+            GC_PROF_MARK(4);
             // ---- 3b: one thread per quad ----
             for (uint32_t i = tid; i < total; i += NT)
             {
@@ -579,6 +631,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         // the staging ring was used as the quad list by the generic proxy: order it before the next TMA writes
         fence_proxy_async();
         __syncthreads();
+        GC_PROF_MARK(5);
     }
 }
 

@@ -37,6 +37,7 @@ struct MeshParams
     const DeviceTables* tables;
     int32_t* error_flag;               // set by the mbarrier watchdog
     int32_t use_tma;                   // 0: the producer warp stages slabs with plain loads (debug aid)
+    unsigned long long* prof;          // optional: 16 cycle counters (phase / wait attribution), null = off
 };
 
 // Six tensor maps over the three brick arenas viewed as (x=32, y=64, z=32, slot):

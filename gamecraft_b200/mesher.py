@@ -73,7 +73,7 @@ EXPORTS = [
     "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
     "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_wait", "gcmesh_batch_results",
     "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
-    "gcmesh_batch_launches", "gcmesh_kernel_info",
+    "gcmesh_batch_launches", "gcmesh_kernel_info", "gcmesh_batch_profile",
 ]
 
 _lib = None
@@ -117,6 +117,7 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_batch_elapsed_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
         L.gcmesh_batch_launches.argtypes = [vp]
         L.gcmesh_kernel_info.argtypes = [ctypes.POINTER(ci)] * 3
+        L.gcmesh_batch_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
         _lib = L
     return _lib
 
@@ -303,6 +304,11 @@ class Batch:
         ms = ctypes.c_float(0)
         _check(lib().gcmesh_batch_elapsed_ms(self.h, ctypes.byref(ms)), "gcmesh_batch_elapsed_ms")
         return float(ms.value)
+
+    def profile(self):
+        out = (ctypes.c_uint64 * 16)()
+        _check(lib().gcmesh_batch_profile(self.h, out), "gcmesh_batch_profile")
+        return [int(v) for v in out]
 
     def launches(self) -> int:
         return int(lib().gcmesh_batch_launches(self.h))
