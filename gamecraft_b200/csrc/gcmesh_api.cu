@@ -105,7 +105,7 @@ struct GcBatch
     unsigned long long* d_cursor;   // [0] quad cursor
     int32_t* d_counters;            // [0] work counter, [1] error flag
     unsigned long long* d_prof;     // 16 cycle counters when GCMESH_PROFILE=1
-    unsigned long long h_prof[16];
+    unsigned long long h_prof[512];
     GcChunkOut* h_out;              // pinned
     GcChunkCoord* h_coords;         // pinned staging for coords
     unsigned long long* h_cursor;   // pinned
@@ -116,29 +116,15 @@ struct GcBatch
     cudaEvent_t ev_start, ev_stop, ev_done;
 };
 
-static int encode_map(GcContext* ctx, CUtensorMap* map, CUtensorMapDataType type, int elem_bytes, void* base, size_t n_slots, bool slab)
+static int encode_map(GcContext* ctx, CUtensorMap* map, CUtensorMapDataType type, int elem_bytes, void* base, size_t n_slots)
 {
-    // One brick arena viewed as a 4-D tensor (the reference's brick index is x + 32*(y + 64*z), World.cpp:278-281):
-    //   row  map: (x = 32, y = 64, z = 32, slot), box (32, 1, 1, 1)  — one x-row (the y halo rows of a slab)
-    //   slab map: (x*y8 = 256, y/8 = 8, z = 32, slot), box (256, 8, 1, 1) — one whole z-slab; x and 8 y-rows are
-    //             contiguous, so the same 2048 voxels are described as 8 long rows instead of 64 short ones and
-    //             the TMA unit issues 8 requests of 512 B / 256 B instead of 64 of 64 B / 32 B
-    cuuint64_t dims[4], strides[3];
-    cuuint32_t box[4], estr[4] = { 1, 1, 1, 1 };
-    if (slab)
-    {
-        dims[0] = 256; dims[1] = 8; dims[2] = 32; dims[3] = (cuuint64_t)n_slots;
-        strides[0] = (cuuint64_t)(256 * elem_bytes);
-        box[0] = 256; box[1] = 8; box[2] = 1; box[3] = 1;
-    }
-    else
-    {
-        dims[0] = 32; dims[1] = 64; dims[2] = 32; dims[3] = (cuuint64_t)n_slots;
-        strides[0] = (cuuint64_t)(32 * elem_bytes);
-        box[0] = 32; box[1] = 1; box[2] = 1; box[3] = 1;
-    }
-    strides[1] = (cuuint64_t)(32 * 64 * elem_bytes);
-    strides[2] = (cuuint64_t)(GC_CHUNK_SIZE_3 * elem_bytes);
+    // One brick arena viewed as a 4-D tensor.  The reference's brick index is x + 32*(y + 64*z) (World.cpp:278-281), so
+    // a z-slab (32 x 64 voxels) is contiguous; described as (x*y8 = 256, y/8 = 8, z = 32, slot) with box (256, 8, 1, 1)
+    // one TMA op moves a whole slab as 8 rows of 512 B / 256 B (64 rows of 64 B / 32 B made the TMA unit issue 8x
+    // more, smaller requests).
+    cuuint64_t dims[4] = { 256, 8, 32, (cuuint64_t)n_slots };
+    cuuint64_t strides[3] = { (cuuint64_t)(256 * elem_bytes), (cuuint64_t)(32 * 64 * elem_bytes), (cuuint64_t)(GC_CHUNK_SIZE_3 * elem_bytes) };
+    cuuint32_t box[4] = { 256, 8, 1, 1 }, estr[4] = { 1, 1, 1, 1 };
     CUresult r = ctx->encode(map, type, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -209,6 +195,9 @@ int gcmesh_create(int device, void* stream, GcContext** out)
     ctx->stream = (cudaStream_t)stream;
     const char* env = getenv("GCMESH_NO_TMA");
     ctx->use_tma = (env && env[0] == '1') ? 0 : 1;
+    const char* bulk = getenv("GCMESH_BULK");
+    if (ctx->use_tma && bulk && bulk[0] == '1') ctx->use_tma = 2;
+    if (ctx->use_tma && bulk && bulk[0] == '3') ctx->use_tma = 3;   // timing experiment only (wrong results)   // contiguous slabs by cp.async.bulk instead of tensor-map boxes
     if (ctx->own_stream) { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); if (e != cudaSuccess) { delete ctx; return fail(GC_ERR_CUDA, "cudaStreamCreate", cudaGetErrorString(e)); } }
 
     void* fn = nullptr;
@@ -290,12 +279,9 @@ int gcmesh_world_create(GcContext* ctx, int size_x, int size_z, GcWorld** out)
     if (e == cudaSuccess) e = cudaMemsetAsync(w->d_surface, 0, w->n_cols * GC_CHUNK_SIZE_2, ctx->stream);
     if (e != cudaSuccess) { gcmesh_world_destroy(w); return fail(GC_ERR_CUDA, "world allocation", cudaGetErrorString(e)); }
     int st = GC_OK;
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_slab, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots, true);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_row, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots, false);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots, true);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_row, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots, false);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.light_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_light, w->n_slots, true);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.light_row, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_light, w->n_slots, false);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_slab, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots);
+    if (st == GC_OK) st = encode_map(ctx, &w->maps.light_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_light, w->n_slots);
     if (st != GC_OK) { gcmesh_world_destroy(w); return st; }
     *out = w;
     return GC_OK;
@@ -406,7 +392,7 @@ int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBa
     if (e == cudaSuccess) e = cudaMalloc(&b->d_indices, (size_t)max_quads * 12);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_cursor, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_counters, sizeof(int32_t) * 2);
-    if (e == cudaSuccess && getenv("GCMESH_PROFILE")) e = cudaMalloc(&b->d_prof, sizeof(unsigned long long) * 16);
+    if (e == cudaSuccess && getenv("GCMESH_PROFILE")) e = cudaMalloc(&b->d_prof, sizeof(unsigned long long) * 512);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_out, sizeof(GcChunkOut) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_coords, sizeof(GcChunkCoord) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_cursor, sizeof(unsigned long long));
@@ -469,7 +455,7 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
         p.vertex_arena = b->d_vertices; p.index_arena = b->d_indices; p.max_quads = b->max_quads;
         p.quad_cursor = b->d_cursor; p.work_counter = b->d_counters; p.tables = ctx->d_tables;
         p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma; p.prof = b->d_prof;
-        if (b->d_prof) GC_CUDA(cudaMemsetAsync(b->d_prof, 0, sizeof(unsigned long long) * 16, s));
+        if (b->d_prof) GC_CUDA(cudaMemsetAsync(b->d_prof, 0, sizeof(unsigned long long) * 512, s));
         const int grid = n < ctx->num_sms ? n : ctx->num_sms;
         GC_CUDA(launch_mesh(p, w->maps, grid, s));
         b->launches = 1;
@@ -478,7 +464,7 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
     GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaMemcpyAsync(b->h_counters, b->d_counters, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, s));
-    if (b->d_prof) GC_CUDA(cudaMemcpyAsync(b->h_prof, b->d_prof, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, s));
+    if (b->d_prof) GC_CUDA(cudaMemcpyAsync(b->h_prof, b->d_prof, sizeof(unsigned long long) * 512, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaEventRecord(b->ev_done, s));
     b->state = 1;
     return GC_OK;
@@ -556,12 +542,12 @@ int gcmesh_batch_elapsed_ms(GcBatch* b, float* ms)
 
 int gcmesh_batch_launches(GcBatch* b) { return b ? b->launches : 0; }
 
-// Development aid (GCMESH_PROFILE=1): the 16 in-kernel cycle counters of the last submission.
-int gcmesh_batch_profile(GcBatch* b, unsigned long long* out16)
+// Development aid (GCMESH_PROFILE=1): the 512 in-kernel cycle counters of the last submission.
+int gcmesh_batch_profile(GcBatch* b, unsigned long long* out512)
 {
-    if (!b || !out16) return fail(GC_ERR_ARG, "null argument");
+    if (!b || !out512) return fail(GC_ERR_ARG, "null argument");
     if (!b->d_prof) return fail(GC_ERR_STATE, "profiling is off (set GCMESH_PROFILE=1 before creating the batch)");
-    memcpy(out16, b->h_prof, sizeof(b->h_prof));
+    memcpy(out512, b->h_prof, sizeof(b->h_prof));
     return GC_OK;
 }
 

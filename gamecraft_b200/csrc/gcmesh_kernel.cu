@@ -22,39 +22,33 @@ namespace
 {
 constexpr int NT = kMeshThreads;          // 20 warps
 constexpr int kWarps = NT / 32;
-constexpr int kStages = 6;
 constexpr int kSlabs = kRowsZ;            // 34 z-slabs per chunk: tz = -1 .. 32
-// P1 consumers: kTeams teams of kTeamWarps warps (half class, half light).  A team owns every kTeams-th slab, so
-// several slabs are being converted at once and each lane carries a few independent tasks (ILP) — one warp per
-// task per slab left the SM waiting on its own ALU latency.
-constexpr int kTeams = 3, kTeamWarps = 6, kTeamRoleLanes = (kTeamWarps / 2) * 32;
-constexpr int kConsumerWarps = kTeams * kTeamWarps;
-constexpr int kTasksPerSlab = kRowsY * 4;                  // (row, octet) for class and again for light
-constexpr int kTasksPerLane = (kTasksPerSlab + kTeamRoleLanes - 1) / kTeamRoleLanes;
-static_assert(1 + kConsumerWarps <= kWarps, "warp roles");
+// P1: kTeams teams of 4 warps (2 class + 2 light, one lane per voxel row).  Team t converts slabs t, t+4, ... and
+// stages them itself through its own two-slot ring: after a slab is converted the team syncs on a named barrier and
+// one of its lanes issues the TMA loads of the slab after next into the slot just freed.  (A separate producer warp
+// cost ~700 cycles per slab — try_wait ~140, arrive.expect_tx + UTMALDG ~360, measured — and paced the whole phase.)
+constexpr int kTeams = 4, kTeamWarps = 4, kTeamStages = 2;
+constexpr int kStages = kTeams * kTeamStages;              // 8
+constexpr int kSlabWarps = kTeams * kTeamWarps;            // warps 0 .. 15
+constexpr int kHaloWarp = kSlabWarps;                      // warp 16: the y-halo rows (ty = -1, 64), straight from global memory
+static_assert(kHaloWarp < kWarps, "warp roles");
+constexpr int kYHaloTasks = 2 * kRowsZ;                    // 2 faces x 34 rows
 constexpr int kHaloTasks = kHaloRows * 2;
 constexpr int kHaloPerThread = (kHaloTasks + NT - 1) / NT;
 
-// ---- one staging slot: a z-slab of the three arrays, each TMA destination 128-byte aligned ----
+// ---- one staging slot: a z-slab of the three arrays (TMA destinations 128-byte aligned) ----
 constexpr int kStBlocks = 0;                       // [64][32] u16
-constexpr int kStBlocksLo = 4096;                  // row ty = -1 (64 B used)
-constexpr int kStBlocksHi = 4096 + 128;            // row ty = 64
-constexpr int kStSun = 4096 + 256;                 // [64][32] u8
-constexpr int kStSunLo = kStSun + 2048;
-constexpr int kStSunHi = kStSunLo + 128;
-constexpr int kStLight = kStSunHi + 128;           // 6656
-constexpr int kStLightLo = kStLight + 2048;
-constexpr int kStLightHi = kStLightLo + 128;
-constexpr int kStageBytes = kStLightHi + 128;      // 8960
-static_assert(kStageBytes % 128 == 0, "stage alignment");
+constexpr int kStSun = 4096;                       // [64][32] u8
+constexpr int kStLight = 6144;
+constexpr int kStageBytes = 8192;
 constexpr int kListCap = kStages * kStageBytes / 4;  // the quad list reuses the staging ring in P3
 static_assert(kListCap >= kMaxQuads, "a whole chunk's quads must fit the list");
 
 // ---- shared-memory carve-up (dynamic, 1024-aligned base) ----
 constexpr int kOffStages = 0;
-constexpr int kOffPlanes = kOffStages + kStages * kStageBytes;            // 53760
-constexpr int kOffLt = kOffPlanes + kPlanes * kHaloRows * 4;              // +71808
-constexpr int kOffHx = kOffLt + kLtBytes;                                 // +89760
+constexpr int kOffPlanes = kOffStages + kStages * kStageBytes;            // 65536
+constexpr int kOffLt = kOffPlanes + kPlanes * kHaloRows * 4;              // centre bytes, then the x-halo bytes
+constexpr int kOffHx = kOffLt + ((kLtBytes + kLtxBytes + 15) & ~15);
 constexpr int kOffBv = kOffHx + ((kHaloRows * 2 + 15) & ~15);             // [2][2256]: emitting voxel at x = 0 / x = 31 of the row
 constexpr int kBvStride = (kHaloRows + 15) & ~15;
 constexpr int kOffSurf = kOffBv + 2 * kBvStride;                          // [34][32] centre-x surface rows
@@ -69,10 +63,10 @@ constexpr int kOffLayerBase = kOffLayerTypB + 256;                        // u32
 constexpr int kOffLayerTypBaseA = kOffLayerBase + 272;
 constexpr int kOffLayerTypBaseB = kOffLayerTypBaseA + 256;
 constexpr int kOffFaces = kOffLayerTypBaseB + 256;                        // FaceDesc[6], 16 B each
-constexpr int kOffBars = kOffFaces + 96;                                  // full[6], empty[6]
-constexpr int kOffCtx = kOffBars + 2 * kStages * 8;
+constexpr int kOffBars = kOffFaces + 96;                                  // full[8]
+constexpr int kOffCtx = kOffBars + kStages * 8;
 constexpr int kSmemBytes = kOffCtx + 64;
-static_assert(kOffPlanes % 16 == 0 && kOffLt % 16 == 0 && kOffHx % 16 == 0 && kOffBv % 16 == 0 && kOffSurf % 16 == 0, "align");
+static_assert(kOffPlanes % 128 == 0 && kOffLt % 16 == 0 && kOffHx % 16 == 0 && kOffBv % 16 == 0 && kOffSurf % 16 == 0, "align");
 static_assert(kOffLut % 8 == 0 && kOffMat % 8 == 0 && kOffBars % 8 == 0 && kOffLayerCnt % 4 == 0 && kOffCtx % 4 == 0, "align");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -111,23 +105,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware instead of spinning
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (and raises the error flag) instead of hanging the GPU.
+// Bounded wait: a protocol bug raises the error flag and traps after ~4 s of wall time instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* error_flag)
 {
+    if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while (!mbar_try_wait(bar, parity))
     {
-        if (++spins > (1u << 22))
+        if ((++spins & 0xFFFu) == 0)
         {
-            if (error_flag) atomicExch(error_flag, 1);
-            __trap();
+            const unsigned long long t = global_timer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull)
+            {
+                if (error_flag) atomicExch(error_flag, 1);
+                __trap();
+            }
         }
     }
 }
@@ -137,6 +144,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
+}
+// TMA bulk copy (no tensor map): `bytes` contiguous bytes global -> shared, completion on an mbarrier
+__device__ __forceinline__ void tma_load_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async()
 {
@@ -211,24 +229,20 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     }
     if (tid == 0)
     {
-        for (int i = 0; i < kStages; i++)
-        {
-            mbar_init(smem_u32(&s_bars[i]), 1);                         // full: the producer's expect_tx arrive
-            mbar_init(smem_u32(&s_bars[kStages + i]), kTeamWarps);      // empty: one arrive per warp of the owning team
-        }
+        for (int i = 0; i < kStages; i++) mbar_init(smem_u32(&s_bars[i]), 1);   // full: the issuing lane's expect_tx arrive
         fence_barrier_init();
         if (p.use_tma)
         {
-            prefetch_tensormap(&maps.blocks_slab); prefetch_tensormap(&maps.blocks_row);
-            prefetch_tensormap(&maps.sun_slab); prefetch_tensormap(&maps.sun_row);
-            prefetch_tensormap(&maps.light_slab); prefetch_tensormap(&maps.light_row);
+            prefetch_tensormap(&maps.blocks_slab);
+            prefetch_tensormap(&maps.sun_slab);
+            prefetch_tensormap(&maps.light_slab);
         }
     }
     const int kill_cls = p.tables->cls8[p.tables->kill_zone & 255];
     const int air_cls = p.tables->cls8[0];
     __syncthreads();
 
-    uint32_t slab_seq = 0;  // slabs staged so far by this CTA (ring position / parity source)
+    uint32_t team_seq = 0;  // slabs this warp's team has staged so far (ring slot / parity source)
     long long prof_t = clock64();
 
     for (;;)
@@ -269,173 +283,185 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
 
         GC_PROF_MARK(0);
         // ================= P1: stage + convert =================
-        if (warp == 0)
+        const bool has_lo = lwy > 0, has_hi = lwy + kTY < GC_WORLD_BLOCK_HEIGHT;
+        const long long p1_t0 = p.prof ? clock64() : 0;
+        const int col0 = cz * p.size_x + cx;
+        if (warp < kSlabWarps)
         {
-            // ---- producer ----
-            for (int s = 0; s < kSlabs; s++)
+            // ---- slab teams: one lane per voxel row (ty = 0..63); the team stages its own slabs ----
+            const int team = warp / kTeamWarps, wt = warp % kTeamWarps;
+            const bool is_class = wt < 2;
+            const int ty = (wt & 1) * 32 + lane;
+            const int wy = lwy + ty;
+            const int rot4 = (lane >> 1) & 3, rot2 = (lane >> 2) & 1;   // shared-memory read rotations (bank-conflict free)
+            const int n_mine = (kSlabs - team + kTeams - 1) / kTeams;  // slabs team, team + 4, ...
+
+            // stage slab number k of this team (s = team + 4k) into the team's ring slot for sequence number `seq`
+            auto issue = [&](int k, uint32_t seq)
             {
-                const uint32_t g = slab_seq + s;
-                const int stage = g % kStages;
-                const uint32_t full = smem_u32(&s_bars[stage]), empty = smem_u32(&s_bars[kStages + stage]);
+                const int s = team + k * kTeams;
+                const int stage = team * kTeamStages + (int)(seq % kTeamStages);
                 const int tz = s - 1;
                 const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
                 const int zz = tz & 31;
-                const int col = (cz + dcz) * p.size_x + cx;
-                const int slot = col * 4 + cy;
-                const bool has_lo = lwy > 0, has_hi = lwy + kTY < GC_WORLD_BLOCK_HEIGHT;
+                const int slot = (col0 + dcz * p.size_x) * 4 + cy;
+                const uint32_t full = smem_u32(&s_bars[stage]);
+                const uint32_t d = smem_u32(s_stage + stage * kStageBytes);
+                fence_proxy_async();   // the slot was read (and, as the quad list, written) by the generic proxy
+                mbar_expect_tx(full, 8192u);
+                tma_load_4d(d + kStBlocks, &maps.blocks_slab, 0, 0, zz, slot, full);
+                tma_load_4d(d + kStSun, &maps.sun_slab, 0, 0, zz, slot, full);
+                tma_load_4d(d + kStLight, &maps.light_slab, 0, 0, zz, slot, full);
+                if (p.prof && blockIdx.x == 0) p.prof[64 + s] = (unsigned long long)(clock64() - p1_t0);
+            };
+            auto stage_plain = [&](int k, uint32_t seq)   // debug staging path (GCMESH_NO_TMA=1): the whole warp copies
+            {
+                const int s = team + k * kTeams;
+                const int stage = team * kTeamStages + (int)(seq % kTeamStages);
+                const int tz = s - 1;
+                const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
+                const int slot = (col0 + dcz * p.size_x) * 4 + cy;
+                const size_t vox = (size_t)slot * GC_CHUNK_SIZE_3 + (size_t)(tz & 31) * 2048;
                 uint8_t* st = s_stage + stage * kStageBytes;
+                for (int i = lane; i < 256; i += 32) reinterpret_cast<uint4*>(st + kStBlocks)[i] = reinterpret_cast<const uint4*>(p.blocks + vox)[i];
+                for (int i = lane; i < 128; i += 32)
+                {
+                    reinterpret_cast<uint4*>(st + kStSun)[i] = reinterpret_cast<const uint4*>(p.sun + vox)[i];
+                    reinterpret_cast<uint4*>(st + kStLight)[i] = reinterpret_cast<const uint4*>(p.light + vox)[i];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s_bars[stage]));
+            };
 
-                if (g >= kStages)
+            // prologue: the first kTeamStages slabs (all slots are free: the previous chunk ended with a CTA-wide sync)
+            if (wt == 0)
+            {
+                for (int k = 0; k < kTeamStages && k < n_mine; k++)
+                {
+                    if (p.use_tma) { if (lane == 0) issue(k, team_seq + k); }
+                    else stage_plain(k, team_seq + k);
+                }
+            }
+            for (int k = 0; k < n_mine; k++)
+            {
+                const int s = team + k * kTeams;
+                const uint32_t seq = team_seq + k;
+                const int stage = team * kTeamStages + (int)(seq % kTeamStages);
                 {
                     const long long w0 = p.prof ? clock64() : 0;
-                    mbar_wait(empty, ((g / kStages) + 1) & 1, p.error_flag);
-                    if (p.prof && lane == 0) atomicAdd(p.prof + 8, (unsigned long long)(clock64() - w0));
+                    mbar_wait(smem_u32(&s_bars[stage]), (seq / kTeamStages) & 1, p.error_flag);
+                    if (p.prof && lane == 0 && warp == 0) atomicAdd(p.prof + 9, (unsigned long long)(clock64() - w0));
+                    if (p.prof && lane == 0 && warp == 2) atomicAdd(p.prof + 10, (unsigned long long)(clock64() - w0));
+                    if (p.prof && lane == 0 && warp == 0 && k == 0) atomicAdd(p.prof + 11, (unsigned long long)(clock64() - p1_t0));
+                    if (p.prof && lane == 0 && wt == 0 && blockIdx.x == 0) p.prof[128 + s] = (unsigned long long)(clock64() - p1_t0);
                 }
-
-                if (p.use_tma)
+                const long long c0 = p.prof ? clock64() : 0;
+                const uint8_t* st = s_stage + stage * kStageBytes;
+                const int hr = hrow(ty, s - 1);
+                if (is_class)
                 {
-                    if (lane == 0)
+                    Ids8 q[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
                     {
-                        const uint32_t bytes = 8192u + (has_lo ? 128u : 0u) + (has_hi ? 128u : 0u);
-                        mbar_expect_tx(full, bytes);
-                        const uint32_t d = smem_u32(st);
-                        tma_load_4d(d + kStBlocks, &maps.blocks_slab, 0, 0, zz, slot, full);
-                        tma_load_4d(d + kStSun, &maps.sun_slab, 0, 0, zz, slot, full);
-                        tma_load_4d(d + kStLight, &maps.light_slab, 0, 0, zz, slot, full);
-                        if (has_lo)
-                        {
-                            tma_load_4d(d + kStBlocksLo, &maps.blocks_row, 0, 63, zz, slot - 1, full);
-                            tma_load_4d(d + kStSunLo, &maps.sun_row, 0, 63, zz, slot - 1, full);
-                            tma_load_4d(d + kStLightLo, &maps.light_row, 0, 63, zz, slot - 1, full);
-                        }
-                        if (has_hi)
-                        {
-                            tma_load_4d(d + kStBlocksHi, &maps.blocks_row, 0, 0, zz, slot + 1, full);
-                            tma_load_4d(d + kStSunHi, &maps.sun_row, 0, 0, zz, slot + 1, full);
-                            tma_load_4d(d + kStLightHi, &maps.light_row, 0, 0, zz, slot + 1, full);
-                        }
+                        const uint4 v = *reinterpret_cast<const uint4*>(st + kStBlocks + ty * 64 + ((j + rot4) & 3) * 16);
+                        q[j].x = v.x; q[j].y = v.y; q[j].z = v.z; q[j].w = v.w;
                     }
+                    uint32_t out[8];
+                    p1_class_row(q, s_lut, out);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                    {
+                        out[j] = rotl_bytes(out[j], rot4);
+                        s_planes[j * kHaloRows + hr] = out[j];
+                    }
+                    const uint32_t vis = (s >= 1 && s <= kTZ) ? row_emit_mask(out) : 0u;
+                    s_bv[hr] = (uint8_t)(vis & 1u);
+                    s_bv[kBvStride + hr] = (uint8_t)(vis >> 31);
+                    if (vis) s_ctx->any_emit = 1;
+                    if (vis & 0x80000001u) s_ctx->any_bv = 1;
                 }
                 else
                 {
-                    // debug staging path: the producer warp copies the slab with plain 16-byte loads
-                    const size_t vox = (size_t)slot * GC_CHUNK_SIZE_3 + (size_t)zz * 2048;
+                    const uint32_t smax = *reinterpret_cast<const uint32_t*>(s_surfmax + s * 4);
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+                    {
+                        const int h = j ^ rot2;
+                        const uint4 sn = *reinterpret_cast<const uint4*>(st + kStSun + ty * 32 + h * 16);
+                        const uint4 bl = *reinterpret_cast<const uint4*>(st + kStLight + ty * 32 + h * 16);
+                        const uint4 sf = *reinterpret_cast<const uint4*>(s_surf + s * 32 + h * 16);
+                        const Words4 o = p1_light_half(Words4{ sn.x, sn.y, sn.z, sn.w }, Words4{ bl.x, bl.y, bl.z, bl.w },
+                                                       Words4{ sf.x, sf.y, sf.z, sf.w }, wy,
+                                                       wy >= (int)((smax >> (16 * h)) & 255u), wy >= (int)((smax >> (16 * h + 8)) & 255u));
+                        *reinterpret_cast<uint4*>(s_lt + hr * kLtStride + h * 16) = make_uint4(o.x, o.y, o.z, o.w);
+                    }
+                }
+                if (p.prof && lane == 0 && warp == 0) { atomicAdd(p.prof + 12, (unsigned long long)(clock64() - c0)); atomicAdd(p.prof + 13, 1ull); }
+                if (p.prof && lane == 0 && warp == 2) atomicAdd(p.prof + 14, (unsigned long long)(clock64() - c0));
+                if (p.prof && lane == 0 && wt == 0 && blockIdx.x == 0) p.prof[192 + s] = (unsigned long long)(clock64() - p1_t0);
+                // refill: once all four warps are done with the slot, one of them stages the slab after next into it
+                if (k + kTeamStages < n_mine)
+                {
+                    named_bar_sync(1 + team, kTeamWarps * 32);
+                    if (wt == (k & 3))
+                    {
+                        if (p.use_tma) { if (lane == 0) issue(k + kTeamStages, seq + kTeamStages); }
+                        else stage_plain(k + kTeamStages, seq + kTeamStages);
+                    }
+                }
+            }
+            team_seq += n_mine;
+        }
+        else if (warp == kHaloWarp)
+        {
+            // ---- y-halo rows: ty = -1 (face 0) and ty = 64 (face 1), tz = -1 .. 32, read straight from the neighbour chunks ----
+            for (int t = lane; t < kYHaloTasks; t += 32)
+            {
+                const int face = t / kRowsZ, tz = t % kRowsZ - 1;
+                const int ty = face ? kTY : -1;
+                const int wy = lwy + ty;
+                const int hr = hrow(ty, tz);
+                uint32_t out[8];
+                uint4 l0, l1;
+                if (!(face ? has_hi : has_lo))
+                {
+                    p1_class_row_const(face ? air_cls : kill_cls, out);
+                    const uint32_t c = face ? ~0u : 0u;
+                    l0 = make_uint4(c, c, c, c); l1 = l0;
+                }
+                else
+                {
+                    const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
+                    const int slot = (col0 + dcz * p.size_x) * 4 + cy + (face ? 1 : -1);
+                    const size_t vox = (size_t)slot * GC_CHUNK_SIZE_3 + 32 * ((face ? 0 : 63) + 64 * (tz & 31));
                     const uint4* gb = reinterpret_cast<const uint4*>(p.blocks + vox);
                     const uint4* gs = reinterpret_cast<const uint4*>(p.sun + vox);
                     const uint4* gl = reinterpret_cast<const uint4*>(p.light + vox);
-                    for (int i = lane; i < 256; i += 32) reinterpret_cast<uint4*>(st + kStBlocks)[i] = gb[i];
-                    for (int i = lane; i < 128; i += 32)
+                    Ids8 q[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
                     {
-                        reinterpret_cast<uint4*>(st + kStSun)[i] = gs[i];
-                        reinterpret_cast<uint4*>(st + kStLight)[i] = gl[i];
+                        const uint4 v = __ldg(gb + j);
+                        q[j].x = v.x; q[j].y = v.y; q[j].z = v.z; q[j].w = v.w;
                     }
-                    if (has_lo && lane < 8)
-                    {
-                        const size_t v = (size_t)(slot - 1) * GC_CHUNK_SIZE_3 + (size_t)zz * 2048 + 63 * 32;
-                        if (lane < 4) reinterpret_cast<uint4*>(st + kStBlocksLo)[lane] = reinterpret_cast<const uint4*>(p.blocks + v)[lane];
-                        else if (lane < 6) reinterpret_cast<uint4*>(st + kStSunLo)[lane - 4] = reinterpret_cast<const uint4*>(p.sun + v)[lane - 4];
-                        else reinterpret_cast<uint4*>(st + kStLightLo)[lane - 6] = reinterpret_cast<const uint4*>(p.light + v)[lane - 6];
-                    }
-                    if (has_hi && lane >= 8 && lane < 16)
-                    {
-                        const int l = lane - 8;
-                        const size_t v = (size_t)(slot + 1) * GC_CHUNK_SIZE_3 + (size_t)zz * 2048;
-                        if (l < 4) reinterpret_cast<uint4*>(st + kStBlocksHi)[l] = reinterpret_cast<const uint4*>(p.blocks + v)[l];
-                        else if (l < 6) reinterpret_cast<uint4*>(st + kStSunHi)[l - 4] = reinterpret_cast<const uint4*>(p.sun + v)[l - 4];
-                        else reinterpret_cast<uint4*>(st + kStLightHi)[l - 6] = reinterpret_cast<const uint4*>(p.light + v)[l - 6];
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(full);
+                    const uint4 sn0 = __ldg(gs), sn1 = __ldg(gs + 1), bl0 = __ldg(gl), bl1 = __ldg(gl + 1);
+                    p1_class_row(q, s_lut, out);
+                    const uint4 sf0 = *reinterpret_cast<const uint4*>(s_surf + (tz + 1) * 32), sf1 = *reinterpret_cast<const uint4*>(s_surf + (tz + 1) * 32 + 16);
+                    const Words4 a = p1_light_half(Words4{ sn0.x, sn0.y, sn0.z, sn0.w }, Words4{ bl0.x, bl0.y, bl0.z, bl0.w },
+                                                   Words4{ sf0.x, sf0.y, sf0.z, sf0.w }, wy, false, false);
+                    const Words4 b2 = p1_light_half(Words4{ sn1.x, sn1.y, sn1.z, sn1.w }, Words4{ bl1.x, bl1.y, bl1.z, bl1.w },
+                                                    Words4{ sf1.x, sf1.y, sf1.z, sf1.w }, wy, false, false);
+                    l0 = make_uint4(a.x, a.y, a.z, a.w); l1 = make_uint4(b2.x, b2.y, b2.z, b2.w);
                 }
+#pragma unroll
+                for (int j = 0; j < 8; j++) s_planes[j * kHaloRows + hr] = out[j];
+                s_bv[hr] = 0;
+                s_bv[kBvStride + hr] = 0;
+                *reinterpret_cast<uint4*>(s_lt + hr * kLtStride) = l0;
+                *reinterpret_cast<uint4*>(s_lt + hr * kLtStride + 16) = l1;
             }
         }
-        else if (warp <= kConsumerWarps)
-        {
-            const int cw = warp - 1;
-            const int team = cw / kTeamWarps, wt = cw % kTeamWarps;
-            const bool is_class = wt < kTeamWarps / 2;
-            const int l96 = (wt % (kTeamWarps / 2)) * 32 + lane;       // lane index within the team's class / light half
-            for (int s = team; s < kSlabs; s += kTeams)
-            {
-                const uint32_t g = slab_seq + s;
-                const int stage = g % kStages;
-                {
-                    const long long w0 = p.prof ? clock64() : 0;
-                    mbar_wait(smem_u32(&s_bars[stage]), (g / kStages) & 1, p.error_flag);
-                    if (p.prof && lane == 0 && cw == 0) atomicAdd(p.prof + 9, (unsigned long long)(clock64() - w0));
-                    if (p.prof && lane == 0 && cw == kTeamWarps / 2) atomicAdd(p.prof + 10, (unsigned long long)(clock64() - w0));
-                }
-                const uint8_t* st = s_stage + stage * kStageBytes;
-                const bool centre_z = s >= 1 && s <= kTZ;
-                if (is_class)
-                {
-                    // ---- block ids -> 8 class bit planes (+ "boundary voxel emits" flags for P1x) ----
-#pragma unroll
-                    for (int k = 0; k < kTasksPerLane; k++)
-                    {
-                        const int task = l96 + k * kTeamRoleLanes;        // (row, octet)
-                        if (task < kTasksPerSlab)
-                        {
-                            const int ty = (task >> 2) - 1, o = task & 3;
-                            const int wy = lwy + ty;
-                            const int hr = hrow(ty, s - 1);
-                            uint32_t vis = 0;
-                            if (wy < 0) p1_class_const_octet(kill_cls, s_planes_b, hr, o);
-                            else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_class_const_octet(air_cls, s_planes_b, hr, o);
-                            else
-                            {
-                                const int row_off = ty < 0 ? kStBlocksLo : (ty >= kTY ? kStBlocksHi : kStBlocks + ty * 64);
-                                const uint4 v = *reinterpret_cast<const uint4*>(st + row_off + o * 16);
-                                vis = p1_class_octet(v.x, v.y, v.z, v.w, s_lut, s_planes_b, hr, o);
-                            }
-                            if (!(centre_z && ty >= 0 && ty < kTY)) vis = 0;
-                            if (o == 0) s_bv[hr] = (uint8_t)(vis & 1u);
-                            if (o == 3) s_bv[kBvStride + hr] = (uint8_t)(vis >> 7);
-                            if (vis) s_ctx->any_emit = 1;
-                            if ((o == 0 && (vis & 1u)) || (o == 3 && (vis >> 7))) s_ctx->any_bv = 1;
-                        }
-                    }
-                }
-                else
-                {
-                    // ---- sunlight + blockLight + surface -> packed light tile ----
-#pragma unroll
-                    for (int k = 0; k < kTasksPerLane; k++)
-                    {
-                        const int task = l96 + k * kTeamRoleLanes;        // (row, octet)
-                        if (task < kTasksPerSlab)
-                        {
-                            const int ty = (task >> 2) - 1, o = task & 3;
-                            const int wy = lwy + ty;
-                            uint32_t* dst = reinterpret_cast<uint32_t*>(s_lt + hrow(ty, s - 1) * kLtStride + 4 + o * 8);
-                            if (wy < 0) { dst[0] = 0u; dst[1] = 0u; }
-                            else if (wy >= GC_WORLD_BLOCK_HEIGHT) { dst[0] = ~0u; dst[1] = ~0u; }
-                            else
-                            {
-                                const int sun_off = (ty < 0 ? kStSunLo : (ty >= kTY ? kStSunHi : kStSun + ty * 32)) + o * 8;
-                                const int light_off = (ty < 0 ? kStLightLo : (ty >= kTY ? kStLightHi : kStLight + ty * 32)) + o * 8;
-                                const uint2 bl = *reinterpret_cast<const uint2*>(st + light_off);
-                                if (wy >= (int)s_surfmax[s * 4 + o])
-                                {
-                                    dst[0] = p1_light4_above(bl.x);
-                                    dst[1] = p1_light4_above(bl.y);
-                                }
-                                else
-                                {
-                                    const uint2 sn = *reinterpret_cast<const uint2*>(st + sun_off);
-                                    const uint2 sf = *reinterpret_cast<const uint2*>(s_surf + s * 32 + o * 8);
-                                    dst[0] = p1_light4(sn.x, bl.x, sf.x, wy);
-                                    dst[1] = p1_light4(sn.y, bl.y, sf.y, wy);
-                                }
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&s_bars[kStages + stage]));
-            }
-        }
-        slab_seq += kSlabs;
         __syncthreads();
         GC_PROF_MARK(1);
 

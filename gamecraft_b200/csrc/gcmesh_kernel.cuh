@@ -37,14 +37,14 @@ struct MeshParams
     const DeviceTables* tables;
     int32_t* error_flag;               // set by the mbarrier watchdog
     int32_t use_tma;                   // 0: the producer warp stages slabs with plain loads (debug aid)
-    unsigned long long* prof;          // optional: 16 cycle counters (phase / wait attribution), null = off
+    unsigned long long* prof;          // optional: 512 cycle counters (phase / wait attribution), null = off
 };
 
-// Six tensor maps over the three brick arenas viewed as (x=32, y=64, z=32, slot):
-// a "slab" box (32,64,1,1) and a "row" box (32,1,1,1) for each of blocks / sunlight / blockLight.
+// Three tensor maps, one per brick arena (blocks / sunlight / blockLight), each viewing the arena as
+// (256, 8, z = 32, slot) so that one box (256, 8, 1, 1) is one whole z-slab of a brick (32 x 64 voxels).
 struct MeshTensorMaps
 {
-    CUtensorMap blocks_slab, blocks_row, sun_slab, sun_row, light_slab, light_row;
+    CUtensorMap blocks_slab, sun_slab, light_slab;
 };
 
 constexpr int kMeshThreads = 640;

@@ -13,8 +13,9 @@
 //                     4    = opaque (Block.cpp:65-68)
 //                     5..7 = mesh type bits (Mesh.h:8-16); 7 (all ones) = never emits (AIR / invisible)
 //   hx[hr]         uint16: low byte = the 8 class bits of cell x = -1, high byte = of cell x = 32
-//   lt[hr*40+4+x]  uint8: (sun << 4) | blockLight with GetSunlight's rules applied (Lighting.cpp:69-79);
+//   lt[hr*32+x]    uint8, x in 0..31: (sun << 4) | blockLight with GetSunlight's rules applied (Lighting.cpp:69-79);
 //                  0x00 below the world, 0xFF above it (GetFinalLight, WorldRender.cpp:316-319)
+//   lt[kLtBytes + hr*2 + side]  the same byte for the x = -1 (side 0) / x = 32 (side 1) halo cells
 #pragma once
 
 #include <stdint.h>
@@ -31,8 +32,9 @@ constexpr int kTX = 32, kTY = 64, kTZ = 32;
 constexpr int kRowsY = kTY + 2, kRowsZ = kTZ + 2;
 constexpr int kHaloRows = kRowsY * kRowsZ;   // 2244
 constexpr int kCenterRows = kTY * kTZ;       // 2048
-constexpr int kLtStride = 40;
-constexpr int kLtBytes = kHaloRows * kLtStride;
+constexpr int kLtStride = 32;
+constexpr int kLtBytes = kHaloRows * kLtStride;  // centre-x bytes; the x-halo bytes follow
+constexpr int kLtxBytes = kHaloRows * 2;
 constexpr int kPlanes = 8;
 constexpr int kMaxQuads = 10000;             // MAX_VERTICES / 4, Mesh.h:5
 constexpr int kMeshTypes = 5;
@@ -87,6 +89,32 @@ GC_HD uint32_t max4(uint32_t a, uint32_t b)
 #endif
 }
 
+// PRMT: result byte i = byte (sel nibble i) of the 8-byte pool {a bytes 0..3, b bytes 4..7}
+GC_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t pool = (uint64_t)a | ((uint64_t)b << 32);
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * i)) & 7))) & 255u) << (8 * i);
+    return r;
+#endif
+}
+// 4x4 byte transpose: out[j] byte i = in[i] byte j
+GC_HD void transpose4x4(const uint32_t in[4], uint32_t out[4])
+{
+    const uint32_t t0 = byte_perm(in[0], in[1], 0x5140), t1 = byte_perm(in[2], in[3], 0x5140);
+    const uint32_t t2 = byte_perm(in[0], in[1], 0x7362), t3 = byte_perm(in[2], in[3], 0x7362);
+    out[0] = byte_perm(t0, t1, 0x5410); out[1] = byte_perm(t0, t1, 0x7632);
+    out[2] = byte_perm(t2, t3, 0x5410); out[3] = byte_perm(t2, t3, 0x7632);
+}
+GC_HD uint32_t rotl_bytes(uint32_t v, int r)   // rotate left by r bytes, r in 0..3
+{
+    const int sh = (r & 3) * 8;
+    return sh ? ((v << sh) | (v >> (32 - sh))) : v;
+}
+
 // ---- block table in kernel form ----
 struct LutEntry { uint32_t lo, hi; };  // class bit k at bit position 8k (lo: k 0..3, hi: k 4..7)
 
@@ -113,50 +141,45 @@ GC_HD LutEntry spread_class(uint32_t cls)
 // Phase 1: raw voxels -> on-chip form
 // =====================================================================================================
 
-// Eight consecutive voxels (x = 8o .. 8o+7) of one row -> one byte of each class plane.
-// ids: 4 words holding 8 uint16 block ids.  planes_b = (uint8_t*)planes.
-// Returns the octet's 8-bit mask of emitting voxels (mesh type != 7).
-GC_HD uint32_t p1_class_octet(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, const LutEntry* lut, uint8_t* planes_b, int hr, int o)
+// Eight consecutive voxels -> their 8 class bits, one byte per plane: lo = planes 0..3, hi = planes 4..7
+// (byte k bit i = class bit k of voxel i).  w0..w3 hold the 8 uint16 block ids.
+GC_HD void p1_class_octet(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, const LutEntry* lut, uint32_t& lo, uint32_t& hi)
 {
-    uint32_t lo, hi;
     const bool uniform = (w0 == w1) && (w2 == w3) && (w0 == w2) && ((w0 >> 16) == (w0 & 0xFFFFu));
     if (uniform)
     {
-        LutEntry e = lut[w0 & 255u];
+        const LutEntry e = lut[w0 & 255u];
         lo = e.lo * 255u;
         hi = e.hi * 255u;
     }
     else
     {
-        const uint32_t w[4] = { w0, w1, w2, w3 };
-        lo = 0; hi = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-        {
-            LutEntry a = lut[w[i] & 255u];
-            LutEntry b = lut[(w[i] >> 16) & 255u];
-            lo += (a.lo << (2 * i)) + (b.lo << (2 * i + 1));
-            hi += (a.hi << (2 * i)) + (b.hi << (2 * i + 1));
-        }
+        const LutEntry a0 = lut[w0 & 255u], b0 = lut[(w0 >> 16) & 255u], a1 = lut[w1 & 255u], b1 = lut[(w1 >> 16) & 255u];
+        const LutEntry a2 = lut[w2 & 255u], b2 = lut[(w2 >> 16) & 255u], a3 = lut[w3 & 255u], b3 = lut[(w3 >> 16) & 255u];
+        lo = a0.lo + (b0.lo << 1) + (a1.lo << 2) + (b1.lo << 3) + (a2.lo << 4) + (b2.lo << 5) + (a3.lo << 6) + (b3.lo << 7);
+        hi = a0.hi + (b0.hi << 1) + (a1.hi << 2) + (b1.hi << 3) + (a2.hi << 4) + (b2.hi << 5) + (a3.hi << 6) + (b3.hi << 7);
     }
-    uint8_t* p = planes_b + hr * 4 + o;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-    {
-        p[(k * kHaloRows) * 4] = (uint8_t)(lo >> (8 * k));
-        p[((k + 4) * kHaloRows) * 4] = (uint8_t)(hi >> (8 * k));
-    }
-    return ~((hi >> 8) & (hi >> 16) & (hi >> 24)) & 255u;
 }
 
-// A whole row whose cells all have the same class byte (rows outside the world: KILL_ZONE below, AIR above,
-// GetBlockSafe World.cpp:422-428).
-GC_HD void p1_class_const_octet(uint32_t cls, uint8_t* planes_b, int hr, int o)
+// One row of 32 voxels -> the row's word of each of the 8 class planes.  q[k] = octet k (x = 8k .. 8k+7) as 8 uint16.
+// The caller may pass the octets rotated (q[k] = octet (k + r) & 3, to read shared memory without bank conflicts)
+// and undo it with rotl_bytes(out[j], r).
+struct Ids8 { uint32_t x, y, z, w; };
+GC_HD void p1_class_row(const Ids8 q[4], const LutEntry* lut, uint32_t out[8])
 {
-    uint8_t* p = planes_b + hr * 4 + o;
+    uint32_t lo[4], hi[4];
 #pragma unroll
-    for (int k = 0; k < 8; k++) p[(k * kHaloRows) * 4] = ((cls >> k) & 1u) ? 0xFF : 0x00;
+    for (int k = 0; k < 4; k++) p1_class_octet(q[k].x, q[k].y, q[k].z, q[k].w, lut, lo[k], hi[k]);
+    transpose4x4(lo, out);
+    transpose4x4(hi, out + 4);
 }
+GC_HD void p1_class_row_const(uint32_t cls, uint32_t out[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[k] = ((cls >> k) & 1u) ? 0xFFFFFFFFu : 0u;
+}
+// emitting voxels of a row (mesh type != 7) from its type planes
+GC_HD uint32_t row_emit_mask(const uint32_t out[8]) { return ~(out[P_M0] & out[P_M1] & out[P_M2]); }
 
 // Four voxels of light: sun/bl/surf hold 4 bytes each (x ascending from the low byte); wy = world y of the row.
 //   sun' = wy >= surface ? 15 : max(sun, 1)      GetSunlight, Lighting.cpp:69-79 (MAX_LIGHT / MIN_LIGHT, Lighting.h:5-6)
@@ -181,11 +204,24 @@ GC_HD uint32_t p1_light4(uint32_t sun, uint32_t bl, uint32_t surf, int wy)
 // Same for cells known to lie at or above their column's surface (sun reads 15 whatever is stored).
 GC_HD uint32_t p1_light4_above(uint32_t bl) { return 0xF0F0F0F0u | (bl & 0x0F0F0F0Fu); }
 
+// Half a row (16 voxels = 4 words).  above_lo / above_hi: the first / second octet lies wholly at or above the surface
+// (wy >= max surface of the octet), so its stored sunlight is never read.
+struct Words4 { uint32_t x, y, z, w; };
+GC_HD Words4 p1_light_half(const Words4& sun, const Words4& bl, const Words4& surf, int wy, bool above_lo, bool above_hi)
+{
+    Words4 o;
+    if (above_lo) { o.x = p1_light4_above(bl.x); o.y = p1_light4_above(bl.y); }
+    else { o.x = p1_light4(sun.x, bl.x, surf.x, wy); o.y = p1_light4(sun.y, bl.y, surf.y, wy); }
+    if (above_hi) { o.z = p1_light4_above(bl.z); o.w = p1_light4_above(bl.w); }
+    else { o.z = p1_light4(sun.z, bl.z, surf.z, wy); o.w = p1_light4(sun.w, bl.w, surf.w, wy); }
+    return o;
+}
+
 // One cell of the x = -1 / x = 32 halo columns.  side 0: x = -1, side 1: x = 32.
 GC_HD void p1_xhalo_cell(uint32_t cls, uint32_t light_byte, uint8_t* hx_b, uint8_t* lt, int hr, int side)
 {
     hx_b[hr * 2 + side] = (uint8_t)cls;
-    lt[hr * kLtStride + (side ? 36 : 3)] = (uint8_t)light_byte;
+    lt[kLtBytes + hr * 2 + side] = (uint8_t)light_byte;
 }
 
 // Is halo cell (side, row hr) ever read?  Only by faces / light footprints of an emitting voxel at x = 0 (side 0) or
@@ -363,6 +399,13 @@ GC_HD uint32_t corner_color(uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool
     return s * 5u + (((s * 2u * 171u) >> 9) & 0x001F001Fu);
 }
 
+// light byte of cell (x, row hr), x in -1..32
+GC_HD uint32_t light_at(const uint8_t* lt, int hr, int x)
+{
+    const int off = ((unsigned)x < 32u) ? hr * kLtStride + x : kLtBytes + hr * 2 + (x > 0 ? 1 : 0);
+    return lt[off];
+}
+
 // out: 12 words = 4 vertices x 12 bytes {pos u8x3, uv u8x3, color u8x4 (L,L,L,S), alpha, 0}  (VertexInfo, Mesh.h:37-44)
 GC_HD void p3b_quad(uint32_t entry, const FaceDesc& f, const uint8_t* lt, const uint32_t* plane_o, const uint16_t* hx,
                     MatEntry mat, uint32_t out[12])
@@ -371,15 +414,13 @@ GC_HD void p3b_quad(uint32_t entry, const FaceDesc& f, const uint8_t* lt, const 
     const int ax = x + f.nx, ay = ty + f.ny, az = tz + f.nz;
     const int hr_a = hrow(ay, az);
     const int hr_u = f.uy * kRowsZ + f.uz, hr_v = f.vy * kRowsZ + f.vz;      // row strides of the in-plane axes
-    const int lt_a = hr_a * kLtStride + 4 + ax;
-    const int lt_u = hr_u * kLtStride + f.ux, lt_v = hr_v * kLtStride + f.vx;  // lt byte strides
 
-    // 3x3 light neighbourhood in the layer in front of the face; L[i][j] at a + (i-1)*u + (j-1)*v
-    uint32_t L[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) L[i][j] = unpack_light(lt[lt_a + (i - 1) * lt_u + (j - 1) * lt_v]);
+    // 3x3 light neighbourhood in the layer in front of the face: cell (i, j) = a + i*u + j*v, i, j in -1..1
+    const uint32_t l00 = unpack_light(light_at(lt, hr_a, ax));
+    const uint32_t lm0 = unpack_light(light_at(lt, hr_a - hr_u, ax - f.ux)), lp0 = unpack_light(light_at(lt, hr_a + hr_u, ax + f.ux));
+    const uint32_t l0m = unpack_light(light_at(lt, hr_a - hr_v, ax - f.vx)), l0p = unpack_light(light_at(lt, hr_a + hr_v, ax + f.vx));
+    const uint32_t lmm = unpack_light(light_at(lt, hr_a - hr_u - hr_v, ax - f.ux - f.vx)), lmp = unpack_light(light_at(lt, hr_a - hr_u + hr_v, ax - f.ux + f.vx));
+    const uint32_t lpm = unpack_light(light_at(lt, hr_a + hr_u - hr_v, ax + f.ux - f.vx)), lpp = unpack_light(light_at(lt, hr_a + hr_u + hr_v, ax + f.ux + f.vx));
     // opacity of the four edge cells (only b and c are ever tested, WorldRender.cpp:361-362)
     const uint32_t o_um = opaque_at(plane_o, hx, hr_a - hr_u, ax - f.ux), o_up = opaque_at(plane_o, hx, hr_a + hr_u, ax + f.ux);
     const uint32_t o_vm = opaque_at(plane_o, hx, hr_a - hr_v, ax - f.vx), o_vp = opaque_at(plane_o, hx, hr_a + hr_v, ax + f.vx);
@@ -396,12 +437,14 @@ GC_HD void p3b_quad(uint32_t entry, const FaceDesc& f, const uint8_t* lt, const 
         const int su = f.ux ? cxb : (f.uy ? cyb : czb);
         const int sv = f.vx ? cxb : (f.vy ? cyb : czb);
         const uint32_t ob = su ? o_up : o_um, oc = sv ? o_vp : o_vm;
-        const uint32_t col = corner_color(L[1][1], L[su * 2][1], L[1][sv * 2], L[su * 2][sv * 2], !(ob & oc));
-        const uint32_t l = col & 255u, s = (col >> 16) & 255u;
+        const uint32_t lb = su ? lp0 : lm0, lc = sv ? l0p : l0m;
+        const uint32_t ld = su ? (sv ? lpp : lpm) : (sv ? lmp : lmm);
+        const uint32_t col = corner_color(l00, lb, lc, ld, !(ob & oc));
+        const uint32_t l = col & 255u, sn = (col >> 16) & 255u;
         const uint32_t u = (k >> 1) & 1u, v = (k == 0 || k == 3) ? 1u : 0u;   // uv: (0,1) (0,0) (1,0) (1,1)
         out[3 * k + 0] = (uint32_t)(x + cxb) | ((uint32_t)(ty + cyb) << 8) | ((uint32_t)(tz + czb) << 16) | (u << 24);
         out[3 * k + 1] = v | (tex << 8) | (l << 16) | (l << 24);
-        out[3 * k + 2] = l | (s << 8) | (alpha << 16);
+        out[3 * k + 2] = l | (sn << 8) | (alpha << 16);
     }
 }
 

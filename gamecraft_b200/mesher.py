@@ -306,7 +306,7 @@ class Batch:
         return float(ms.value)
 
     def profile(self):
-        out = (ctypes.c_uint64 * 16)()
+        out = (ctypes.c_uint64 * 512)()
         _check(lib().gcmesh_batch_profile(self.h, out), "gcmesh_batch_profile")
         return [int(v) for v in out]
 

@@ -157,8 +157,8 @@ int gcmesh_batch_elapsed_ms(GcBatch* batch, float* ms);
 /* Number of kernel launches the last submission made. */
 int gcmesh_batch_launches(GcBatch* batch);
 
-/* Development aid: 16 in-kernel cycle counters of the last submission (needs GCMESH_PROFILE=1 in the environment). */
-int gcmesh_batch_profile(GcBatch* batch, unsigned long long* out16);
+/* Development aid: 512 in-kernel cycle counters of the last submission (needs GCMESH_PROFILE=1 in the environment). */
+int gcmesh_batch_profile(GcBatch* batch, unsigned long long* out512);
 /* Registers per thread, dynamic shared memory and block size of the mesh kernel (for reports). */
 int gcmesh_kernel_info(int* regs, int* smem_bytes, int* threads);
 

@@ -48,9 +48,8 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
     }
 
     std::vector<uint32_t> planes((size_t)kPlanes * kHaloRows, 0xDEADBEEFu);
-    std::vector<uint8_t> lt(kLtBytes, 0xAB);
+    std::vector<uint8_t> lt(kLtBytes + kLtxBytes, 0xAB);
     std::vector<uint16_t> hx(kHaloRows, 0xFFFF);
-    uint8_t* planes_b = (uint8_t*)planes.data();
     uint8_t* hx_b = (uint8_t*)hx.data();
 
     // ---- phase 1: centre-x columns of every row (class planes + light), like the kernel's class / light warps ----
@@ -67,32 +66,46 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
             int hr = hrow(ty, tz);
             if (wy < 0 || wy >= 256)
             {
-                uint32_t c = wy < 0 ? cls8[kill_zone] : cls8[0];
-                uint32_t lb = wy < 0 ? 0x00 : 0xFF;
-                for (int o = 0; o < 4; o++) p1_class_const_octet(c, planes_b, hr, o);
-                for (int x = 0; x < 32; x++) lt[hr * kLtStride + 4 + x] = (uint8_t)lb;
+                uint32_t out[8];
+                p1_class_row_const(wy < 0 ? cls8[kill_zone] : cls8[0], out);
+                for (int k = 0; k < 8; k++) planes[k * kHaloRows + hr] = out[k];
+                for (int x = 0; x < 32; x++) lt[hr * kLtStride + x] = wy < 0 ? 0x00 : 0xFF;
                 continue;
             }
             int64_t base = (col * 4 + (wy >> 6)) * 65536 + 32 * ((wy & 63) + 64 * zz);
             const uint32_t* bw = (const uint32_t*)(w.blocks + base);
             const bool centre = ty >= 0 && ty < kTY && tz >= 0 && tz < kTZ;
-            for (int o = 0; o < 4; o++)
             {
-                uint32_t vis = p1_class_octet(bw[4 * o], bw[4 * o + 1], bw[4 * o + 2], bw[4 * o + 3], lut.data(), planes_b, hr, o);
-                if (o == 0) bv[hr] = centre ? (vis & 1u) : 0;
-                if (o == 3) bv[kHaloRows + hr] = centre ? (vis >> 7) : 0;
+                // the kernel reads the four octets rotated by a lane-dependent amount and un-rotates the plane words
+                const int rot = (ty + tz + 2) & 3;
+                Ids8 q[4];
+                for (int k = 0; k < 4; k++)
+                {
+                    const uint32_t* o = bw + 4 * ((k + rot) & 3);
+                    q[k].x = o[0]; q[k].y = o[1]; q[k].z = o[2]; q[k].w = o[3];
+                }
+                uint32_t out[8];
+                p1_class_row(q, lut.data(), out);
+                for (int k = 0; k < 8; k++) { out[k] = rotl_bytes(out[k], rot); planes[k * kHaloRows + hr] = out[k]; }
+                uint32_t vis = centre ? row_emit_mask(out) : 0u;
+                bv[hr] = vis & 1u;
+                bv[kHaloRows + hr] = vis >> 31;
             }
             const uint32_t* sw = (const uint32_t*)(w.sun + base);
             const uint32_t* lw = (const uint32_t*)(w.light + base);
             const uint32_t* fw = (const uint32_t*)srow;
-            for (int q = 0; q < 8; q++)
+            for (int h = 0; h < 2; h++)
             {
-                // the kernel takes the "all above the surface" shortcut per octet; both forms must agree
-                int smax = 0;
-                for (int x = (q / 2) * 8; x < (q / 2) * 8 + 8; x++) smax = srow[x] > smax ? srow[x] : smax;
-                uint32_t v = wy >= smax ? p1_light4_above(lw[q]) : p1_light4(sw[q], lw[q], fw[q], wy);
-                if (v != p1_light4(sw[q], lw[q], fw[q], wy)) return -7;
-                memcpy(&lt[hr * kLtStride + 4 + 4 * q], &v, 4);
+                // the kernel takes the "octet wholly above the surface" shortcut; both forms must agree
+                int smax[2] = { 0, 0 };
+                for (int x = 0; x < 16; x++) { int v = srow[h * 16 + x]; if (v > smax[x >> 3]) smax[x >> 3] = v; }
+                Words4 sn = { sw[4 * h], sw[4 * h + 1], sw[4 * h + 2], sw[4 * h + 3] }, bl = { lw[4 * h], lw[4 * h + 1], lw[4 * h + 2], lw[4 * h + 3] };
+                Words4 sf = { fw[4 * h], fw[4 * h + 1], fw[4 * h + 2], fw[4 * h + 3] };
+                const bool halo_row = ty < 0 || ty >= kTY;     // the kernel's y-halo warp never takes the shortcut
+                Words4 a = p1_light_half(sn, bl, sf, wy, !halo_row && wy >= smax[0], !halo_row && wy >= smax[1]);
+                Words4 b = p1_light_half(sn, bl, sf, wy, false, false);
+                if (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) return -7;
+                memcpy(&lt[hr * kLtStride + h * 16], &a, 16);
             }
         }
     }
