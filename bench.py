@@ -222,7 +222,10 @@ def main():
     host, coords, gen_s = make_world(args.workload, rank, world_size)
     n = len(coords)
 
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream: the library launches on it, torch's events and NCCL ops are ordered on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = mesher.Context(local_rank, stream.cuda_stream)
     world = mesher.World(ctx, host.size_x, host.size_z)
 

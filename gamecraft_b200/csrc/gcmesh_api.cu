@@ -113,7 +113,7 @@ struct GcBatch
     int n;
     int state;                      // 0 idle, 1 submitted, 2 waited
     int launches;
-    cudaEvent_t ev_start, ev_stop, ev_done;
+    cudaEvent_t ev_start, ev_stop, ev_done, ev_coords;
 };
 
 static int encode_map(GcContext* ctx, CUtensorMap* map, CUtensorMapDataType type, int elem_bytes, void* base, size_t n_slots)
@@ -400,6 +400,7 @@ int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBa
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_start);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_stop);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_coords, cudaEventDisableTiming);
     if (e != cudaSuccess) { gcmesh_batch_destroy(b); return fail(GC_ERR_CUDA, "batch allocation", cudaGetErrorString(e)); }
     *out = b;
     return GC_OK;
@@ -418,6 +419,7 @@ int gcmesh_batch_destroy(GcBatch* b)
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     if (b->ev_stop) cudaEventDestroy(b->ev_stop);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
+    if (b->ev_coords) cudaEventDestroy(b->ev_coords);
     delete b;
     return GC_OK;
 }
@@ -437,12 +439,15 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
     }
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
-    if (b->state == 1) GC_CUDA(cudaEventSynchronize(b->ev_done));
+    // the pinned coordinate staging buffer is reused: wait until the previous submission has consumed it (its kernel
+    // may still be queued or running, so back-to-back submissions keep the GPU busy)
+    if (b->state == 1) GC_CUDA(cudaEventSynchronize(b->ev_coords));
     b->n = n;
     b->launches = 0;
     memcpy(b->h_coords, coords, sizeof(GcChunkCoord) * (size_t)n);
     cudaStream_t s = ctx->stream;
     GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, s));
+    GC_CUDA(cudaEventRecord(b->ev_coords, s));
     GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), s));
     GC_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t) * 2, s));
     GC_CUDA(cudaEventRecord(b->ev_start, s));
