@@ -31,7 +31,8 @@ constexpr int kTeams = 4, kTeamWarps = 4, kTeamStages = 2;
 constexpr int kStages = kTeams * kTeamStages;              // 8
 constexpr int kSlabWarps = kTeams * kTeamWarps;            // warps 0 .. 15
 constexpr int kHaloWarp = kSlabWarps;                      // warp 16: the y-halo rows (ty = -1, 64), straight from global memory
-static_assert(kHaloWarp < kWarps, "warp roles");
+constexpr int kFetchWarp = kHaloWarp + 1;                  // warp 17: prefetches the next chunk's id, position and surface rows
+static_assert(kFetchWarp < kWarps, "warp roles");
 constexpr int kYHaloTasks = 2 * kRowsZ;                    // 2 faces x 34 rows
 constexpr int kHaloTasks = kHaloRows * 2;
 constexpr int kHaloPerThread = (kHaloTasks + NT - 1) / NT;
@@ -41,19 +42,19 @@ constexpr int kStBlocks = 0;                       // [64][32] u16
 constexpr int kStSun = 4096;                       // [64][32] u8
 constexpr int kStLight = 6144;
 constexpr int kStageBytes = 8192;
-constexpr int kListCap = kStages * kStageBytes / 4;  // the quad list reuses the staging ring in P3
-static_assert(kListCap >= kMaxQuads, "a whole chunk's quads must fit the list");
+// P3 reuses the staging ring: quad list (u32 per quad) followed by the per-type ranks (u16 per quad)
+constexpr int kOffTList = kMaxQuads * 4;
+static_assert(kMaxQuads * 6 <= kStages * kStageBytes, "a whole chunk's quad list must fit the staging ring");
 
 // ---- shared-memory carve-up (dynamic, 1024-aligned base) ----
 constexpr int kOffStages = 0;
 constexpr int kOffPlanes = kOffStages + kStages * kStageBytes;            // 65536
 constexpr int kOffLt = kOffPlanes + kPlanes * kHaloRows * 4;              // centre bytes, then the x-halo bytes
 constexpr int kOffHx = kOffLt + ((kLtBytes + kLtxBytes + 15) & ~15);
-constexpr int kOffBv = kOffHx + ((kHaloRows * 2 + 15) & ~15);             // [2][2256]: emitting voxel at x = 0 / x = 31 of the row
-constexpr int kBvStride = (kHaloRows + 15) & ~15;
-constexpr int kOffSurf = kOffBv + 2 * kBvStride;                          // [34][32] centre-x surface rows
-constexpr int kOffSurfMax = kOffSurf + kRowsZ * 32;                       // [34][4] max surface per 8-voxel octet
-constexpr int kOffLut = kOffSurfMax + ((kRowsZ * 4 + 15) & ~15);
+constexpr int kOffBv = kOffHx + ((kHaloRows * 2 + 15) & ~15);             // u32[2][132]: per layer, which rows' x = 0 / x = 31 voxel emits
+constexpr int kSurfBytes = kRowsZ * 32 + ((kRowsZ * 4 + 15) & ~15);       // [34][32] centre-x surface rows + [34][4] per-octet maxima
+constexpr int kOffSurf = kOffBv + ((2 * kBvWords * 4 + 15) & ~15);                          // two buffers: this chunk's and the prefetched next one's
+constexpr int kOffLut = kOffSurf + 2 * kSurfBytes;
 constexpr int kOffMat = kOffLut + 256 * 8;
 constexpr int kOffCls = kOffMat + 256 * 8;
 constexpr int kOffLayerCnt = kOffCls + 256;                               // u32[64]
@@ -65,7 +66,8 @@ constexpr int kOffLayerTypBaseB = kOffLayerTypBaseA + 256;
 constexpr int kOffFaces = kOffLayerTypBaseB + 256;                        // FaceDesc[6], 16 B each
 constexpr int kOffBars = kOffFaces + 96;                                  // full[8]
 constexpr int kOffCtx = kOffBars + kStages * 8;
-constexpr int kSmemBytes = kOffCtx + 64;
+constexpr int kOffNext = kOffCtx + 64;                                    // NextChunk[2]
+constexpr int kSmemBytes = kOffNext + 32;
 static_assert(kOffPlanes % 128 == 0 && kOffLt % 16 == 0 && kOffHx % 16 == 0 && kOffBv % 16 == 0 && kOffSurf % 16 == 0, "align");
 static_assert(kOffLut % 8 == 0 && kOffMat % 8 == 0 && kOffBars % 8 == 0 && kOffLayerCnt % 4 == 0 && kOffCtx % 4 == 0, "align");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -73,10 +75,10 @@ static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 struct alignas(16) FaceDesc16 { FaceDesc f; uint8_t pad[3]; };
 static_assert(sizeof(FaceDesc16) == 16, "FaceDesc16");
 
+struct NextChunk { int32_t chunk, cx, cy, cz; };   // chunk = index into coords, or -1 when the work is exhausted
+
 struct ChunkCtx
 {
-    int32_t chunk;        // index into coords, or -1 when the work is exhausted
-    int32_t cx, cy, cz;
     int32_t any_emit;     // some voxel of the chunk emits quads (else P1x / P2 / P3 are skipped)
     int32_t any_bv;       // some emitting voxel sits at x = 0 or x = 31 (else no x-halo cell is ever read)
     int32_t emit;         // P3 runs
@@ -194,14 +196,14 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
 
     uint8_t* s_stage = smem + kOffStages;
     uint32_t* s_list = reinterpret_cast<uint32_t*>(smem + kOffStages);
+    uint16_t* s_tlist = reinterpret_cast<uint16_t*>(smem + kOffStages + kOffTList);
     uint32_t* s_planes = reinterpret_cast<uint32_t*>(smem + kOffPlanes);
     uint8_t* s_planes_b = smem + kOffPlanes;
     uint8_t* s_lt = smem + kOffLt;
     uint16_t* s_hx = reinterpret_cast<uint16_t*>(smem + kOffHx);
     uint8_t* s_hx_b = smem + kOffHx;
-    uint8_t* s_bv = smem + kOffBv;
-    uint8_t* s_surf = smem + kOffSurf;
-    uint8_t* s_surfmax = smem + kOffSurfMax;
+    uint32_t* s_bvm = reinterpret_cast<uint32_t*>(smem + kOffBv);
+    NextChunk* s_next = reinterpret_cast<NextChunk*>(smem + kOffNext);
     LutEntry* s_lut = reinterpret_cast<LutEntry*>(smem + kOffLut);
     MatEntry* s_mat = reinterpret_cast<MatEntry*>(smem + kOffMat);
     uint8_t* s_cls = smem + kOffCls;
@@ -245,41 +247,51 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     uint32_t team_seq = 0;  // slabs this warp's team has staged so far (ring slot / parity source)
     long long prof_t = clock64();
 
-    for (;;)
+    // Claim the next chunk and stage what P1 needs before any voxel arrives: its position and the centre-x surface
+    // rows of the three columns (cz-1, cz, cz+1) with their per-octet maxima.  Run by one warp into buffer `b`,
+    // one chunk ahead of the rest of the CTA.
+    auto fetch_chunk = [&](int b)
     {
-        // ================= P0: next chunk, surface window =================
-        if (tid == 0)
+        int c = 0, fx = 0, fy = 0, fz = 0;
+        if (lane == 0)
         {
-            int c = atomicAdd(p.work_counter, 1);
+            c = atomicAdd(p.work_counter, 1);
             if (c >= p.n_chunks) c = -1;
-            s_ctx->chunk = c;
-            s_ctx->any_emit = 0; s_ctx->any_bv = 0;
-            if (c >= 0)
-            {
-                GcChunkCoord cc = p.coords[c];
-                s_ctx->cx = cc.cx; s_ctx->cy = cc.cy; s_ctx->cz = cc.cz;
-            }
+            if (c >= 0) { const GcChunkCoord cc = p.coords[c]; fx = cc.cx; fy = cc.cy; fz = cc.cz; }
+            s_next[b].chunk = c; s_next[b].cx = fx; s_next[b].cy = fy; s_next[b].cz = fz;
         }
-        __syncthreads();
-        const int chunk = s_ctx->chunk;
-        if (chunk < 0) break;
-        const int cx = s_ctx->cx, cy = s_ctx->cy, cz = s_ctx->cz;
-        const int lwy = cy * kTY;
-
-        // centre-x surface rows of the three columns (cz-1, cz, cz+1): s_surf[(tz+1)*32 + x], and their per-octet maxima
-        if (tid < kRowsZ * 4)
+        c = __shfl_sync(0xffffffffu, c, 0); fx = __shfl_sync(0xffffffffu, fx, 0); fz = __shfl_sync(0xffffffffu, fz, 0);
+        if (c < 0) return;
+        uint8_t* surf = smem + kOffSurf + b * kSurfBytes;
+        for (int i = lane; i < kRowsZ * 4; i += 32)
         {
-            const int r = tid >> 2, q = tid & 3;
+            const int r = i >> 2, q = i & 3;
             const int tz = r - 1;
             const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
-            const size_t col = (size_t)(cz + dcz) * p.size_x + cx;
+            const size_t col = (size_t)(fz + dcz) * p.size_x + fx;
             const uint2 v = __ldg(reinterpret_cast<const uint2*>(p.surface + col * 1024 + (tz & 31) * 32) + q);
-            reinterpret_cast<uint2*>(s_surf)[tid] = v;
+            reinterpret_cast<uint2*>(surf)[i] = v;
             const uint32_t m = max4(v.x, v.y);
             const uint32_t m2 = max4(m, m >> 16);
-            s_surfmax[tid] = (uint8_t)max4(m2, m2 >> 8);
+            surf[kRowsZ * 32 + i] = (uint8_t)max4(m2, m2 >> 8);
         }
+    };
+
+    int buf = 0;
+    if (warp == kFetchWarp) fetch_chunk(0);
+    if (tid == 0) { s_ctx->any_emit = 0; s_ctx->any_bv = 0; }
+    if (tid < 2 * kBvWords) s_bvm[tid] = 0;
+
+    for (;; buf ^= 1)
+    {
+        // ================= P0: the chunk prefetched during the previous chunk's P1 =================
         __syncthreads();
+        const int chunk = s_next[buf].chunk;
+        if (chunk < 0) break;
+        const int cx = s_next[buf].cx, cy = s_next[buf].cy, cz = s_next[buf].cz;
+        const int lwy = cy * kTY;
+        const uint8_t* s_surf = smem + kOffSurf + buf * kSurfBytes;
+        const uint8_t* s_surfmax = s_surf + kRowsZ * 32;
 
         GC_PROF_MARK(0);
         // ================= P1: stage + convert =================
@@ -289,7 +301,8 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         if (warp < kSlabWarps)
         {
             // ---- slab teams: one lane per voxel row (ty = 0..63); the team stages its own slabs ----
-            const int team = warp / kTeamWarps, wt = warp % kTeamWarps;
+            // team = warp % 4 puts each team on its own scheduler partition (SMSP = warp % 4): two class + two light warps each
+            const int team = warp % kTeams, wt = warp / kTeams;
             const bool is_class = wt < 2;
             const int ty = (wt & 1) * 32 + lane;
             const int wy = lwy + ty;
@@ -376,10 +389,13 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                         s_planes[j * kHaloRows + hr] = out[j];
                     }
                     const uint32_t vis = (s >= 1 && s <= kTZ) ? row_emit_mask(out) : 0u;
-                    s_bv[hr] = (uint8_t)(vis & 1u);
-                    s_bv[kBvStride + hr] = (uint8_t)(vis >> 31);
                     if (vis) s_ctx->any_emit = 1;
-                    if (vis & 0x80000001u) s_ctx->any_bv = 1;
+                    if (vis & 0x80000001u)
+                    {
+                        s_ctx->any_bv = 1;
+                        if (vis & 1u) atomicOr(&s_bvm[(ty + 1) * 2 + (s >> 5)], 1u << (s & 31));
+                        if (vis >> 31) atomicOr(&s_bvm[kBvWords + (ty + 1) * 2 + (s >> 5)], 1u << (s & 31));
+                    }
                 }
                 else
                 {
@@ -456,12 +472,11 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 }
 #pragma unroll
                 for (int j = 0; j < 8; j++) s_planes[j * kHaloRows + hr] = out[j];
-                s_bv[hr] = 0;
-                s_bv[kBvStride + hr] = 0;
                 *reinterpret_cast<uint4*>(s_lt + hr * kLtStride) = l0;
                 *reinterpret_cast<uint4*>(s_lt + hr * kLtStride + 16) = l1;
             }
         }
+        else if (warp == kFetchWarp) fetch_chunk(buf ^ 1);
         __syncthreads();
         GC_PROF_MARK(1);
 
@@ -477,10 +492,11 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 const int task = tid + k * NT;
                 if (task < kHaloTasks)
                 {
-                    const int hr = task >> 1, side = task & 1;
-                    const int ty = hr / kRowsZ - 1, tz = hr % kRowsZ - 1;
+                    // consecutive lanes walk up one (side, tz) column: neighbouring y rows share cache lines
+                    const int side = task / kHaloRows, rem = task % kHaloRows;
+                    const int tz = rem / kRowsY - 1, ty = rem % kRowsY - 1;
                     const int wy = lwy + ty;
-                    if (any_bv && wy >= 0 && wy < GC_WORLD_BLOCK_HEIGHT && xhalo_needed(s_bv + side * kBvStride, hr))
+                    if (any_bv && wy >= 0 && wy < GC_WORLD_BLOCK_HEIGHT && xhalo_needed(s_bvm + side * kBvWords, ty, tz))
                     {
                         need |= 1u << k;
                         const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
@@ -500,8 +516,10 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 const int task = tid + k * NT;
                 if (task < kHaloTasks)
                 {
-                    const int hr = task >> 1, side = task & 1;
-                    const int wy = lwy + hr / kRowsZ - 1;
+                    const int side = task / kHaloRows, rem = task % kHaloRows;
+                    const int tz = rem / kRowsY - 1, ty = rem % kRowsY - 1;
+                    const int hr = hrow(ty, tz);
+                    const int wy = lwy + ty;
                     if (wy < 0) p1_xhalo_cell(kill_cls, 0x00u, s_hx_b, s_lt, hr, side);
                     else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_xhalo_cell(air_cls, 0xFFu, s_hx_b, s_lt, hr, side);
                     else if ((need >> k) & 1u) p1_xhalo_cell(s_cls[id[k] & 255u], light_byte_of(sn[k], bl[k], sf[k], wy), s_hx_b, s_lt, hr, side);
@@ -509,6 +527,8 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             }
         }
         __syncthreads();
+        if (tid == 0) { s_ctx->any_emit = 0; s_ctx->any_bv = 0; }   // every thread has read them; P1 of the next chunk sets them again
+        if (any_bv && tid < 2 * kBvWords) s_bvm[tid] = 0;
 
         GC_PROF_MARK(2);
         // ================= P2: face masks, counts, scan, reservation =================
@@ -522,7 +542,6 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 for (int t = 0; t < kMeshTypes; t++) { o.index_count[t] = 0; o.index_offset[t] = 0; }
                 p.out[chunk] = o;
             }
-            __syncthreads();   // s_ctx is rewritten by thread 0 at the top of the loop
             GC_PROF_MARK(3);
             continue;
         }
@@ -608,14 +627,11 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         if (s_ctx->emit)
         {
             const uint32_t quad_base = s_ctx->quad_base, total = s_ctx->total;
-            uint32_t type_off[kMeshTypes];
-#pragma unroll
-            for (int t = 0; t < kMeshTypes; t++) type_off[t] = s_ctx->type_off[t];
             uint32_t* idx_words = reinterpret_cast<uint32_t*>(p.index_arena) + (size_t)quad_base * 3;
             uint4* vtx = reinterpret_cast<uint4*>(p.vertex_arena) + (size_t)quad_base * 3;
             const uint16_t* chunk_blocks = p.blocks + ((size_t)(cz * p.size_x + cx) * 4 + cy) * GC_CHUNK_SIZE_3;
 
-            // ---- 3a: rows -> ordered quad list (whole chunk fits the staging ring) + index words ----
+            // ---- 3a: rows -> ordered quad list + per-type ranks (the whole chunk fits the staging ring) ----
             for (int layer = warp; layer < kTY; layer += kWarps)
             {
                 if (s_layer_base[layer + 1] == s_layer_base[layer]) continue;   // warp-uniform
@@ -635,17 +651,31 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                     const uint32_t rank0 = s_layer_base[layer] + ce;
                     trank[1] = ae & 0xFFFFu; trank[2] = ae >> 16; trank[3] = be & 0xFFFFu; trank[4] = be >> 16;
                     trank[0] = rank0 - trank[1] - trank[2] - trank[3] - trank[4];
-                    p3a_row(rf, layer, lane, rank0, trank, 0u, s_list, idx_words, type_off);
+                    p3a_row(rf, layer, lane, rank0, trank, s_list, s_tlist);
                 }
             }
             __syncthreads();
             GC_PROF_MARK(4);
-            // ---- 3b: one thread per quad ----
+            // ---- 3b: one thread per quad: its index words and its four vertices ----
+            uint32_t id_next = 0;
+            if ((uint32_t)tid < total)
+            {
+                const uint32_t e = s_list[tid];
+                id_next = __ldg(chunk_blocks + ((e >> 3) & 31) + 32 * (((e >> 13) & 63) + 64 * ((e >> 8) & 31)));
+            }
             for (uint32_t i = tid; i < total; i += NT)
             {
                 const uint32_t e = s_list[i];
-                const int x = (e >> 3) & 31, tz = (e >> 8) & 31, ty = (e >> 13) & 63;
-                const uint32_t id = __ldg(chunk_blocks + x + 32 * (ty + 64 * tz)) & 255u;
+                const uint32_t id = id_next & 255u;
+                if (i + NT < total)
+                {
+                    const uint32_t en = s_list[i + NT];   // block id of this thread's next quad: its latency hides behind this one
+                    id_next = __ldg(chunk_blocks + ((en >> 3) & 31) + 32 * (((en >> 13) & 63) + 64 * ((en >> 8) & 31)));
+                }
+                uint32_t iw[3];
+                quad_index_words(i, iw);
+                uint32_t* ip = idx_words + (size_t)(s_ctx->type_off[(e >> 19) & 7] + s_tlist[i]) * 3;
+                ip[0] = iw[0]; ip[1] = iw[1]; ip[2] = iw[2];
                 uint32_t v[12];
                 p3b_quad(e, s_faces[e & 7].f, s_lt, s_planes + P_OPAQUE * kHaloRows, s_hx, s_mat[id], v);
                 uint4* dst = vtx + (size_t)i * 3;
@@ -656,7 +686,6 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         }
         // the staging ring was used as the quad list by the generic proxy: order it before the next TMA writes
         fence_proxy_async();
-        __syncthreads();
         GC_PROF_MARK(5);
     }
 }

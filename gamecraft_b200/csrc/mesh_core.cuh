@@ -165,11 +165,22 @@ GC_HD void p1_class_octet(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, co
 // The caller may pass the octets rotated (q[k] = octet (k + r) & 3, to read shared memory without bank conflicts)
 // and undo it with rotl_bytes(out[j], r).
 struct Ids8 { uint32_t x, y, z, w; };
+GC_HD bool octet_uniform(const Ids8& q) { return (q.x == q.y) && (q.z == q.w) && (q.x == q.z) && ((q.x >> 16) == (q.x & 0xFFFFu)); }
 GC_HD void p1_class_row(const Ids8 q[4], const LutEntry* lut, uint32_t out[8])
 {
     uint32_t lo[4], hi[4];
+    if (octet_uniform(q[0]) && octet_uniform(q[1]) && octet_uniform(q[2]) && octet_uniform(q[3]))
+    {
+        // four single-block octets (air, deep stone, water ...): four independent table lookups, no branches between them
+        const LutEntry e0 = lut[q[0].x & 255u], e1 = lut[q[1].x & 255u], e2 = lut[q[2].x & 255u], e3 = lut[q[3].x & 255u];
+        lo[0] = e0.lo * 255u; lo[1] = e1.lo * 255u; lo[2] = e2.lo * 255u; lo[3] = e3.lo * 255u;
+        hi[0] = e0.hi * 255u; hi[1] = e1.hi * 255u; hi[2] = e2.hi * 255u; hi[3] = e3.hi * 255u;
+    }
+    else
+    {
 #pragma unroll
-    for (int k = 0; k < 4; k++) p1_class_octet(q[k].x, q[k].y, q[k].z, q[k].w, lut, lo[k], hi[k]);
+        for (int k = 0; k < 4; k++) p1_class_octet(q[k].x, q[k].y, q[k].z, q[k].w, lut, lo[k], hi[k]);
+    }
     transpose4x4(lo, out);
     transpose4x4(hi, out + 4);
 }
@@ -224,20 +235,21 @@ GC_HD void p1_xhalo_cell(uint32_t cls, uint32_t light_byte, uint8_t* hx_b, uint8
     lt[kLtBytes + hr * 2 + side] = (uint8_t)light_byte;
 }
 
-// Is halo cell (side, row hr) ever read?  Only by faces / light footprints of an emitting voxel at x = 0 (side 0) or
-// x = 31 (side 1) in one of the 3x3 rows around it.  bv[hr] = that voxel emits (0 for rows outside the chunk).
-GC_HD uint32_t xhalo_needed(const uint8_t* bv, int hr)
+// Is halo cell (side, ty, tz) ever read?  Only by faces / light footprints of an emitting voxel at x = 0 (side 0) or
+// x = 31 (side 1) in one of the 3x3 rows around it.  bvm[(ty + 1) * 2 + w]: bit (tz + 1) of the 64-bit mask of layer ty
+// says "the boundary voxel of row (ty, tz) emits" (set for centre rows only).
+constexpr int kBvWords = kRowsY * 2;   // per side
+GC_HD uint32_t xhalo_needed(const uint32_t* bvm, int ty, int tz)
 {
-    uint32_t n = 0;
+    uint64_t m = 0;
 #pragma unroll
     for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-        for (int dz = -1; dz <= 1; dz++)
-        {
-            const int r = hr + dy * kRowsZ + dz;
-            if (r >= 0 && r < kHaloRows) n |= bv[r];
-        }
-    return n;
+    {
+        const int r = ty + 1 + dy;
+        if (r >= 0 && r < kRowsY) m |= (uint64_t)bvm[r * 2] | ((uint64_t)bvm[r * 2 + 1] << 32);
+    }
+    m |= (m << 1) | (m >> 1);
+    return (uint32_t)(m >> (tz + 1)) & 1u;
 }
 
 GC_HD uint32_t light_byte_of(uint32_t sun, uint32_t bl, uint32_t surf, int wy)
@@ -309,48 +321,59 @@ GC_HD void p2_row_counts(const RowFaces& r, int& total, uint32_t& typ4)
 }
 
 // =====================================================================================================
-// Phase 3a: one row -> quad list entries (in emission order) + its index-stream words
+// Phase 3a: one row -> quad list entries in emission order (x ascending, then BuildBlock's face order)
 // =====================================================================================================
-// list entry: bits 0..2 face, 3..7 x, 8..12 tz, 13..18 ty
+// list entry: bits 0..2 face, 3..7 x, 8..12 tz, 13..18 ty, 19..21 mesh type; tlist = the quad's rank within its mesh type
 GC_HD uint32_t quad_entry(int ty, int tz, int x, int d) { return (uint32_t)d | ((uint32_t)x << 3) | ((uint32_t)tz << 8) | ((uint32_t)ty << 13); }
 
-// rank0: chunk-relative rank of the row's first quad; trank[t]: rank of the row's first quad within mesh type t;
-// list_base: rank of list[0]; idx_words: the chunk's index segment as uint32 (3 words per quad);
-// type_off[t]: quads before mesh type t's stream inside the segment.
-// SetIndices (Mesh.cpp:32-50): o+2, o+1, o, o+3, o+2, o with o = (uint16)vertCount = 4*rank.
-GC_HD void p3a_row(const RowFaces& r, int ty, int tz, uint32_t rank0, const uint32_t trank0[kMeshTypes], uint32_t list_base,
-                   uint32_t* list, uint32_t* idx_words, const uint32_t type_off[kMeshTypes])
+// rank0: chunk-relative rank of the row's first quad; trank0[t]: rank of the row's first quad within mesh type t.
+GC_HD void p3a_row(const RowFaces& r, int ty, int tz, uint32_t rank0, const uint32_t trank0[kMeshTypes], uint32_t* list, uint16_t* tlist)
 {
     uint32_t any = r.f[0] | r.f[1] | r.f[2] | r.f[3] | r.f[4] | r.f[5];
     uint32_t rank = rank0;
+    const uint32_t base = quad_entry(ty, tz, 0, 0);
+    if (!(any & (r.m0 | r.m1 | r.m2)))
+    {
+        // every emitting voxel of the row has mesh type 0 (the common case)
+        uint32_t tr = trank0[0];
+        while (any)
+        {
+            const int x = lowbit(any);
+            any &= any - 1;
+            const uint32_t e = base | ((uint32_t)x << 3);
+#pragma unroll
+            for (int d = 0; d < 6; d++)
+                if ((r.f[d] >> x) & 1u) { list[rank] = e | (uint32_t)d; tlist[rank] = (uint16_t)tr; rank++; tr++; }
+        }
+        return;
+    }
     uint32_t tr[kMeshTypes];
 #pragma unroll
-    for (int t = 0; t < kMeshTypes; t++) tr[t] = trank0[t] + type_off[t];
+    for (int t = 0; t < kMeshTypes; t++) tr[t] = trank0[t];
     while (any)
     {
         const int x = lowbit(any);
         any &= any - 1;
         const uint32_t t = ((r.m0 >> x) & 1u) | (((r.m1 >> x) & 1u) << 1) | (((r.m2 >> x) & 1u) << 2);
-        // select this voxel's running stream position without dynamic register indexing
+        // this voxel's running position in its stream, without dynamic register indexing
         uint32_t pos = tr[0];
         pos = t == 1 ? tr[1] : pos; pos = t == 2 ? tr[2] : pos; pos = t == 3 ? tr[3] : pos; pos = t == 4 ? tr[4] : pos;
+        const uint32_t e = base | ((uint32_t)x << 3) | (t << 19);
         uint32_t n = 0;
 #pragma unroll
         for (int d = 0; d < 6; d++)
-        {
-            if ((r.f[d] >> x) & 1u)
-            {
-                list[rank - list_base] = quad_entry(ty, tz, x, d);
-                const uint32_t o = (rank * 4u) & 0xFFFFu;
-                uint32_t* w = idx_words + (size_t)(pos + n) * 3;
-                w[0] = ((o + 2u) & 0xFFFFu) | (((o + 1u) & 0xFFFFu) << 16);
-                w[1] = o | (((o + 3u) & 0xFFFFu) << 16);
-                w[2] = ((o + 2u) & 0xFFFFu) | (o << 16);
-                rank++; n++;
-            }
-        }
+            if ((r.f[d] >> x) & 1u) { list[rank] = e | (uint32_t)d; tlist[rank] = (uint16_t)(pos + n); rank++; n++; }
         tr[0] += t == 0 ? n : 0; tr[1] += t == 1 ? n : 0; tr[2] += t == 2 ? n : 0; tr[3] += t == 3 ? n : 0; tr[4] += t == 4 ? n : 0;
     }
+}
+
+// SetIndices (Mesh.cpp:32-50): o+2, o+1, o, o+3, o+2, o with o = (uint16)vertCount = 4 * rank, as three 32-bit words
+GC_HD void quad_index_words(uint32_t rank, uint32_t w[3])
+{
+    const uint32_t o = (rank * 4u) & 0xFFFFu;
+    w[0] = ((o + 2u) & 0xFFFFu) | (((o + 1u) & 0xFFFFu) << 16);
+    w[1] = o | (((o + 3u) & 0xFFFFu) << 16);
+    w[2] = ((o + 2u) & 0xFFFFu) | (o << 16);
 }
 
 // =====================================================================================================

@@ -53,7 +53,7 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
     uint8_t* hx_b = (uint8_t*)hx.data();
 
     // ---- phase 1: centre-x columns of every row (class planes + light), like the kernel's class / light warps ----
-    std::vector<uint8_t> bv(2 * kHaloRows, 0);   // [side][hr]: emitting voxel at x = 0 / x = 31 (centre rows only)
+    std::vector<uint32_t> bvm(2 * kBvWords, 0);  // [side][layer]: 64-bit masks of rows whose x = 0 / x = 31 voxel emits
     for (int tz = -1; tz <= kTZ; tz++)
     {
         int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
@@ -88,8 +88,9 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
                 p1_class_row(q, lut.data(), out);
                 for (int k = 0; k < 8; k++) { out[k] = rotl_bytes(out[k], rot); planes[k * kHaloRows + hr] = out[k]; }
                 uint32_t vis = centre ? row_emit_mask(out) : 0u;
-                bv[hr] = vis & 1u;
-                bv[kHaloRows + hr] = vis >> 31;
+                const int sl = tz + 1;
+                if (vis & 1u) bvm[(ty + 1) * 2 + (sl >> 5)] |= 1u << (sl & 31);
+                if (vis >> 31) bvm[kBvWords + (ty + 1) * 2 + (sl >> 5)] |= 1u << (sl & 31);
             }
             const uint32_t* sw = (const uint32_t*)(w.sun + base);
             const uint32_t* lw = (const uint32_t*)(w.light + base);
@@ -118,7 +119,7 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
         {
             if (wy < 0) { p1_xhalo_cell(cls8[kill_zone], 0x00, hx_b, lt.data(), hr, side); continue; }
             if (wy >= 256) { p1_xhalo_cell(cls8[0], 0xFF, hx_b, lt.data(), hr, side); continue; }
-            if (!xhalo_needed(bv.data() + side * kHaloRows, hr)) continue;
+            if (!xhalo_needed(bvm.data() + side * kBvWords, ty, tz)) continue;
             int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
             int zz = tz & 31, xx = side ? 0 : 31;
             int64_t col = (int64_t)(cz + dcz) * w.size_x + (cx + (side ? 1 : -1));
@@ -154,12 +155,13 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
 
     // ---- phase 3a ----
     std::vector<uint32_t> list(total + 1);
+    std::vector<uint16_t> tlist(total + 1);
     uint32_t rank = 0, trank[kMeshTypes] = { 0, 0, 0, 0, 0 };
     for (int R = 0; R < kCenterRows; R++)
     {
         RowFaces rf;
         p2_row_faces(planes.data(), hx.data(), R >> 5, R & 31, rf);
-        p3a_row(rf, R >> 5, R & 31, rank, trank, 0, list.data(), (uint32_t*)idx_out, type_off);
+        p3a_row(rf, R >> 5, R & 31, rank, trank, list.data(), tlist.data());
         uint32_t t4 = rowTyp[R], c = rowCnt[R], nz = 0;
         for (int t = 1; t < kMeshTypes; t++) { uint32_t k = (t4 >> (8 * (t - 1))) & 255u; trank[t] += k; nz += k; }
         trank[0] += c - nz;
@@ -173,9 +175,11 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
         uint32_t e = list[i];
         int x = (e >> 3) & 31, tz = (e >> 8) & 31, ty = (e >> 13) & 63;
         uint32_t id = cb[x + 32 * (ty + 64 * tz)] & 255u;
-        uint32_t v[12];
+        uint32_t v[12], iw[3];
         p3b_quad(e, kFaces[e & 7], lt.data(), planes.data() + P_OPAQUE * kHaloRows, hx.data(), mat[id], v);
         memcpy(verts_out + (size_t)i * 48, v, 48);
+        quad_index_words(i, iw);
+        memcpy((uint32_t*)idx_out + (size_t)(type_off[(e >> 19) & 7] + tlist[i]) * 3, iw, 12);
     }
     return 0;
 }
