@@ -182,12 +182,14 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
+// In-kernel cycle attribution is compiled in only for the profiling instantiation (GCMESH_PROFILE=1).
 #define GC_PROF_MARK(slot)                                                            \
     do {                                                                              \
-        if (p.prof && tid == 0) { const long long t_ = clock64(); atomicAdd(p.prof + (slot), (unsigned long long)(t_ - prof_t)); prof_t = t_; } \
+        if (kProf && tid == 0) { const long long t_ = clock64(); atomicAdd(p.prof + (slot), (unsigned long long)(t_ - prof_t)); prof_t = t_; } \
     } while (0)
 
 // =====================================================================================================
+template <bool kProf>
 __global__ void __launch_bounds__(NT, 1)
 gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
 {
@@ -296,7 +298,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         GC_PROF_MARK(0);
         // ================= P1: stage + convert =================
         const bool has_lo = lwy > 0, has_hi = lwy + kTY < GC_WORLD_BLOCK_HEIGHT;
-        const long long p1_t0 = p.prof ? clock64() : 0;
+        const long long p1_t0 = kProf ? clock64() : 0;
         const int col0 = cz * p.size_x + cx;
         if (warp < kSlabWarps)
         {
@@ -325,7 +327,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 tma_load_4d(d + kStBlocks, &maps.blocks_slab, 0, 0, zz, slot, full);
                 tma_load_4d(d + kStSun, &maps.sun_slab, 0, 0, zz, slot, full);
                 tma_load_4d(d + kStLight, &maps.light_slab, 0, 0, zz, slot, full);
-                if (p.prof && blockIdx.x == 0) p.prof[64 + s] = (unsigned long long)(clock64() - p1_t0);
+                if (kProf && blockIdx.x == 0) p.prof[64 + s] = (unsigned long long)(clock64() - p1_t0);
             };
             auto stage_plain = [&](int k, uint32_t seq)   // debug staging path (GCMESH_NO_TMA=1): the whole warp copies
             {
@@ -361,14 +363,14 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 const uint32_t seq = team_seq + k;
                 const int stage = team * kTeamStages + (int)(seq % kTeamStages);
                 {
-                    const long long w0 = p.prof ? clock64() : 0;
+                    const long long w0 = kProf ? clock64() : 0;
                     mbar_wait(smem_u32(&s_bars[stage]), (seq / kTeamStages) & 1, p.error_flag);
-                    if (p.prof && lane == 0 && warp == 0) atomicAdd(p.prof + 9, (unsigned long long)(clock64() - w0));
-                    if (p.prof && lane == 0 && warp == 2) atomicAdd(p.prof + 10, (unsigned long long)(clock64() - w0));
-                    if (p.prof && lane == 0 && warp == 0 && k == 0) atomicAdd(p.prof + 11, (unsigned long long)(clock64() - p1_t0));
-                    if (p.prof && lane == 0 && wt == 0 && blockIdx.x == 0) p.prof[128 + s] = (unsigned long long)(clock64() - p1_t0);
+                    if (kProf && lane == 0 && warp == 0) atomicAdd(p.prof + 9, (unsigned long long)(clock64() - w0));
+                    if (kProf && lane == 0 && warp == 2) atomicAdd(p.prof + 10, (unsigned long long)(clock64() - w0));
+                    if (kProf && lane == 0 && warp == 0 && k == 0) atomicAdd(p.prof + 11, (unsigned long long)(clock64() - p1_t0));
+                    if (kProf && lane == 0 && wt == 0 && blockIdx.x == 0) p.prof[128 + s] = (unsigned long long)(clock64() - p1_t0);
                 }
-                const long long c0 = p.prof ? clock64() : 0;
+                const long long c0 = kProf ? clock64() : 0;
                 const uint8_t* st = s_stage + stage * kStageBytes;
                 const int hr = hrow(ty, s - 1);
                 if (is_class)
@@ -413,9 +415,9 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                         *reinterpret_cast<uint4*>(s_lt + hr * kLtStride + h * 16) = make_uint4(o.x, o.y, o.z, o.w);
                     }
                 }
-                if (p.prof && lane == 0 && warp == 0) { atomicAdd(p.prof + 12, (unsigned long long)(clock64() - c0)); atomicAdd(p.prof + 13, 1ull); }
-                if (p.prof && lane == 0 && warp == 2) atomicAdd(p.prof + 14, (unsigned long long)(clock64() - c0));
-                if (p.prof && lane == 0 && wt == 0 && blockIdx.x == 0) p.prof[192 + s] = (unsigned long long)(clock64() - p1_t0);
+                if (kProf && lane == 0 && warp == 0) { atomicAdd(p.prof + 12, (unsigned long long)(clock64() - c0)); atomicAdd(p.prof + 13, 1ull); }
+                if (kProf && lane == 0 && warp == 2) atomicAdd(p.prof + 14, (unsigned long long)(clock64() - c0));
+                if (kProf && lane == 0 && wt == 0 && blockIdx.x == 0) p.prof[192 + s] = (unsigned long long)(clock64() - p1_t0);
                 // refill: once all four warps are done with the slot, one of them stages the slab after next into it
                 if (k + kTeamStages < n_mine)
                 {
@@ -729,18 +731,20 @@ cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int gri
     static bool configured = false;
     if (!configured)
     {
-        cudaError_t e = cudaFuncSetAttribute(gc_mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gc_mesh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gc_mesh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    gc_mesh_kernel<<<grid, NT, kSmemBytes, stream>>>(p, maps);
+    if (p.prof) gc_mesh_kernel<true><<<grid, NT, kSmemBytes, stream>>>(p, maps);
+    else gc_mesh_kernel<false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
     return cudaGetLastError();
 }
 
 cudaError_t mesh_kernel_attributes(int* regs, int* static_smem, int* max_dyn_smem)
 {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, gc_mesh_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&a, gc_mesh_kernel<false>);
     if (e != cudaSuccess) return e;
     if (regs) *regs = a.numRegs;
     if (static_smem) *static_smem = (int)a.sharedSizeBytes;
