@@ -52,7 +52,8 @@ constexpr int kOffPlanes = kOffStages + kStages * kStageBytes;            // 655
 constexpr int kOffLt = kOffPlanes + kPlanes * kHaloRows * 4;              // centre bytes, then the x-halo bytes
 constexpr int kOffHx = kOffLt + ((kLtBytes + kLtxBytes + 15) & ~15);
 constexpr int kOffBv = kOffHx + ((kHaloRows * 2 + 15) & ~15);             // u32[2][132]: per layer, which rows' x = 0 / x = 31 voxel emits
-constexpr int kSurfBytes = kRowsZ * 32 + ((kRowsZ * 4 + 15) & ~15);       // [34][32] centre-x surface rows + [34][4] per-octet maxima
+constexpr int kSurfBytes = kRowsZ * 32 + 2 * ((kRowsZ * 4 + 15) & ~15);   // [34][32] centre-x surface rows + [34][4] per-octet maxima + minima
+constexpr int kSurfMinOff = (kRowsZ * 4 + 15) & ~15;
 constexpr int kOffSurf = kOffBv + ((2 * kBvWords * 4 + 15) & ~15);                          // two buffers: this chunk's and the prefetched next one's
 constexpr int kOffLut = kOffSurf + 2 * kSurfBytes;
 constexpr int kOffMat = kOffLut + 256 * 8;
@@ -72,8 +73,7 @@ static_assert(kOffPlanes % 128 == 0 && kOffLt % 16 == 0 && kOffHx % 16 == 0 && k
 static_assert(kOffLut % 8 == 0 && kOffMat % 8 == 0 && kOffBars % 8 == 0 && kOffLayerCnt % 4 == 0 && kOffCtx % 4 == 0, "align");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-struct alignas(16) FaceDesc16 { FaceDesc f; uint8_t pad[3]; };
-static_assert(sizeof(FaceDesc16) == 16, "FaceDesc16");
+static_assert(sizeof(FacePlan) == 16, "FacePlan");
 
 struct NextChunk { int32_t chunk, cx, cy, cz; };   // chunk = index into coords, or -1 when the work is exhausted
 
@@ -215,7 +215,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     uint32_t* s_layer_base = reinterpret_cast<uint32_t*>(smem + kOffLayerBase);
     uint32_t* s_layer_typbase_a = reinterpret_cast<uint32_t*>(smem + kOffLayerTypBaseA);
     uint32_t* s_layer_typbase_b = reinterpret_cast<uint32_t*>(smem + kOffLayerTypBaseB);
-    FaceDesc16* s_faces = reinterpret_cast<FaceDesc16*>(smem + kOffFaces);
+    FacePlan* s_faces = reinterpret_cast<FacePlan*>(smem + kOffFaces);
     uint64_t* s_bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     ChunkCtx* s_ctx = reinterpret_cast<ChunkCtx*>(smem + kOffCtx);
 
@@ -229,7 +229,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     if (tid < 6)
     {
         const FaceDesc table[6] = GC_FACE_TABLE;
-        s_faces[tid].f = table[tid];
+        s_faces[tid] = make_face_plan(table[tid]);
     }
     if (tid == 0)
     {
@@ -276,6 +276,9 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             const uint32_t m = max4(v.x, v.y);
             const uint32_t m2 = max4(m, m >> 16);
             surf[kRowsZ * 32 + i] = (uint8_t)max4(m2, m2 >> 8);
+            const uint32_t n = max4(~v.x, ~v.y);              // per-byte min = ~max(~a, ~b)
+            const uint32_t n2 = max4(n, n >> 16);
+            surf[kRowsZ * 32 + kSurfMinOff + i] = (uint8_t)~max4(n2, n2 >> 8);
         }
     };
 
@@ -309,6 +312,9 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             const int ty = (wt & 1) * 32 + lane;
             const int wy = lwy + ty;
             const int rot4 = (lane >> 1) & 3, rot2 = (lane >> 2) & 1;   // shared-memory read rotations (bank-conflict free)
+            const uint32_t unrot = rot_selector(rot4);
+            const int boff0 = kStBlocks + ty * 64 + ((0 + rot4) & 3) * 16, boff1 = kStBlocks + ty * 64 + ((1 + rot4) & 3) * 16;
+            const int boff2 = kStBlocks + ty * 64 + ((2 + rot4) & 3) * 16, boff3 = kStBlocks + ty * 64 + ((3 + rot4) & 3) * 16;
             const int n_mine = (kSlabs - team + kTeams - 1) / kTeams;  // slabs team, team + 4, ...
 
             // stage slab number k of this team (s = team + 4k) into the team's ring slot for sequence number `seq`
@@ -376,18 +382,18 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 if (is_class)
                 {
                     Ids8 q[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
                     {
-                        const uint4 v = *reinterpret_cast<const uint4*>(st + kStBlocks + ty * 64 + ((j + rot4) & 3) * 16);
-                        q[j].x = v.x; q[j].y = v.y; q[j].z = v.z; q[j].w = v.w;
+                        const uint4 v0 = *reinterpret_cast<const uint4*>(st + boff0), v1 = *reinterpret_cast<const uint4*>(st + boff1);
+                        const uint4 v2 = *reinterpret_cast<const uint4*>(st + boff2), v3 = *reinterpret_cast<const uint4*>(st + boff3);
+                        q[0] = Ids8{ v0.x, v0.y, v0.z, v0.w }; q[1] = Ids8{ v1.x, v1.y, v1.z, v1.w };
+                        q[2] = Ids8{ v2.x, v2.y, v2.z, v2.w }; q[3] = Ids8{ v3.x, v3.y, v3.z, v3.w };
                     }
                     uint32_t out[8];
                     p1_class_row(q, s_lut, out);
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                     {
-                        out[j] = rotl_bytes(out[j], rot4);
+                        out[j] = rotl_bytes(out[j], unrot);
                         s_planes[j * kHaloRows + hr] = out[j];
                     }
                     const uint32_t vis = (s >= 1 && s <= kTZ) ? row_emit_mask(out) : 0u;
@@ -402,6 +408,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 else
                 {
                     const uint32_t smax = *reinterpret_cast<const uint32_t*>(s_surfmax + s * 4);
+                    const uint32_t smin = *reinterpret_cast<const uint32_t*>(s_surfmax + kSurfMinOff + s * 4);
 #pragma unroll
                     for (int j = 0; j < 2; j++)
                     {
@@ -411,7 +418,8 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                         const uint4 sf = *reinterpret_cast<const uint4*>(s_surf + s * 32 + h * 16);
                         const Words4 o = p1_light_half(Words4{ sn.x, sn.y, sn.z, sn.w }, Words4{ bl.x, bl.y, bl.z, bl.w },
                                                        Words4{ sf.x, sf.y, sf.z, sf.w }, wy,
-                                                       wy >= (int)((smax >> (16 * h)) & 255u), wy >= (int)((smax >> (16 * h + 8)) & 255u));
+                                                       light_mode(wy, (smax >> (16 * h)) & 255u, (smin >> (16 * h)) & 255u),
+                                                       light_mode(wy, (smax >> (16 * h + 8)) & 255u, (smin >> (16 * h + 8)) & 255u));
                         *reinterpret_cast<uint4*>(s_lt + hr * kLtStride + h * 16) = make_uint4(o.x, o.y, o.z, o.w);
                     }
                 }
@@ -467,9 +475,9 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                     p1_class_row(q, s_lut, out);
                     const uint4 sf0 = *reinterpret_cast<const uint4*>(s_surf + (tz + 1) * 32), sf1 = *reinterpret_cast<const uint4*>(s_surf + (tz + 1) * 32 + 16);
                     const Words4 a = p1_light_half(Words4{ sn0.x, sn0.y, sn0.z, sn0.w }, Words4{ bl0.x, bl0.y, bl0.z, bl0.w },
-                                                   Words4{ sf0.x, sf0.y, sf0.z, sf0.w }, wy, false, false);
+                                                   Words4{ sf0.x, sf0.y, sf0.z, sf0.w }, wy, 0, 0);
                     const Words4 b2 = p1_light_half(Words4{ sn1.x, sn1.y, sn1.z, sn1.w }, Words4{ bl1.x, bl1.y, bl1.z, bl1.w },
-                                                    Words4{ sf1.x, sf1.y, sf1.z, sf1.w }, wy, false, false);
+                                                    Words4{ sf1.x, sf1.y, sf1.z, sf1.w }, wy, 0, 0);
                     l0 = make_uint4(a.x, a.y, a.z, a.w); l1 = make_uint4(b2.x, b2.y, b2.z, b2.w);
                 }
 #pragma unroll
@@ -679,7 +687,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 uint32_t* ip = idx_words + (size_t)(s_ctx->type_off[(e >> 19) & 7] + s_tlist[i]) * 3;
                 ip[0] = iw[0]; ip[1] = iw[1]; ip[2] = iw[2];
                 uint32_t v[12];
-                p3b_quad(e, s_faces[e & 7].f, s_lt, s_planes + P_OPAQUE * kHaloRows, s_hx, s_mat[id], v);
+                p3b_quad(e, s_faces[e & 7], s_lt, s_planes + P_OPAQUE * kHaloRows, s_hx, s_mat[id], v);
                 uint4* dst = vtx + (size_t)i * 3;
                 dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
                 dst[1] = make_uint4(v[4], v[5], v[6], v[7]);

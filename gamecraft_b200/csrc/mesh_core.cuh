@@ -109,11 +109,9 @@ GC_HD void transpose4x4(const uint32_t in[4], uint32_t out[4])
     out[0] = byte_perm(t0, t1, 0x5410); out[1] = byte_perm(t0, t1, 0x7632);
     out[2] = byte_perm(t2, t3, 0x5410); out[3] = byte_perm(t2, t3, 0x7632);
 }
-GC_HD uint32_t rotl_bytes(uint32_t v, int r)   // rotate left by r bytes, r in 0..3
-{
-    const int sh = (r & 3) * 8;
-    return sh ? ((v << sh) | (v >> (32 - sh))) : v;
-}
+// rotate left by r bytes (r in 0..3) as one PRMT: sel = rot_selector(r), computed once per lane
+GC_HD uint32_t rot_selector(int r) { return (0x32103210u >> (4 * ((4 - r) & 3))) & 0xFFFFu; }
+GC_HD uint32_t rotl_bytes(uint32_t v, uint32_t sel) { return byte_perm(v, v, sel); }
 
 // ---- block table in kernel form ----
 struct LutEntry { uint32_t lo, hi; };  // class bit k at bit position 8k (lo: k 0..3, hi: k 4..7)
@@ -212,19 +210,32 @@ GC_HD uint32_t p1_light4(uint32_t sun, uint32_t bl, uint32_t surf, int wy)
     return (s << 4) | (bl & 0x0F0F0F0Fu);
 }
 
-// Same for cells known to lie at or above their column's surface (sun reads 15 whatever is stored).
+// Same for cells known to lie at or above their column's surface (sun reads 15 whatever is stored) ...
 GC_HD uint32_t p1_light4_above(uint32_t bl) { return 0xF0F0F0F0u | (bl & 0x0F0F0F0Fu); }
+// ... and for cells known to lie below it (stored sunlight, 0 reads as MIN_LIGHT)
+GC_HD uint32_t p1_light4_below(uint32_t sun, uint32_t bl)
+{
+    uint32_t s = sun & 0x0F0F0F0Fu;
+    const uint32_t nz = ((s + 0x0F0F0F0Fu) >> 4) & 0x01010101u;
+    s |= nz ^ 0x01010101u;
+    return (s << 4) | (bl & 0x0F0F0F0Fu);
+}
 
-// Half a row (16 voxels = 4 words).  above_lo / above_hi: the first / second octet lies wholly at or above the surface
-// (wy >= max surface of the octet), so its stored sunlight is never read.
+// Half a row (16 voxels = 4 words).  mode_lo / mode_hi classify the first / second octet against the surface rows
+// under it: 1 = wholly at or above (wy >= max surface of the octet), 2 = wholly below (wy < min), 0 = mixed.
 struct Words4 { uint32_t x, y, z, w; };
-GC_HD Words4 p1_light_half(const Words4& sun, const Words4& bl, const Words4& surf, int wy, bool above_lo, bool above_hi)
+GC_HD int light_mode(int wy, uint32_t smax, uint32_t smin) { return wy >= (int)smax ? 1 : (wy < (int)smin ? 2 : 0); }
+GC_HD void p1_light_octet(uint32_t s0, uint32_t s1, uint32_t b0, uint32_t b1, uint32_t f0, uint32_t f1, int wy, int mode, uint32_t& o0, uint32_t& o1)
+{
+    if (mode == 1) { o0 = p1_light4_above(b0); o1 = p1_light4_above(b1); }
+    else if (mode == 2) { o0 = p1_light4_below(s0, b0); o1 = p1_light4_below(s1, b1); }
+    else { o0 = p1_light4(s0, b0, f0, wy); o1 = p1_light4(s1, b1, f1, wy); }
+}
+GC_HD Words4 p1_light_half(const Words4& sun, const Words4& bl, const Words4& surf, int wy, int mode_lo, int mode_hi)
 {
     Words4 o;
-    if (above_lo) { o.x = p1_light4_above(bl.x); o.y = p1_light4_above(bl.y); }
-    else { o.x = p1_light4(sun.x, bl.x, surf.x, wy); o.y = p1_light4(sun.y, bl.y, surf.y, wy); }
-    if (above_hi) { o.z = p1_light4_above(bl.z); o.w = p1_light4_above(bl.w); }
-    else { o.z = p1_light4(sun.z, bl.z, surf.z, wy); o.w = p1_light4(sun.w, bl.w, surf.w, wy); }
+    p1_light_octet(sun.x, sun.y, bl.x, bl.y, surf.x, surf.y, wy, mode_lo, o.x, o.y);
+    p1_light_octet(sun.z, sun.w, bl.z, bl.w, surf.z, surf.w, wy, mode_hi, o.z, o.w);
     return o;
 }
 
@@ -429,45 +440,84 @@ GC_HD uint32_t light_at(const uint8_t* lt, int hr, int x)
     return lt[off];
 }
 
+// A face's geometry pre-digested for p3b_quad (one 16-byte record per face, built once from FaceDesc):
+//   w0  row offset of the cell in front (ny*34 + nz) as int16 | nx as int8 << 16
+//   w1  row stride of in-plane axis u (uy*34 + uz) | ux << 16        w2  the same for axis v
+//   w3  corner bits of the four vertices (3 bits each: +x, +y, +z) | per-vertex sign along u << 12 | along v << 16
+struct FacePlan { uint32_t w0, w1, w2, w3; };
+GC_HD FacePlan make_face_plan(const FaceDesc& f)
+{
+    FacePlan p;
+    p.w0 = (uint32_t)(uint16_t)(int16_t)(f.ny * kRowsZ + f.nz) | ((uint32_t)(uint8_t)f.nx << 16);
+    p.w1 = (uint32_t)(uint16_t)(int16_t)(f.uy * kRowsZ + f.uz) | ((uint32_t)(uint8_t)f.ux << 16);
+    p.w2 = (uint32_t)(uint16_t)(int16_t)(f.vy * kRowsZ + f.vz) | ((uint32_t)(uint8_t)f.vx << 16);
+    uint32_t corners = 0, su = 0, sv = 0;
+    for (int k = 0; k < 4; k++)
+    {
+        const uint32_t c = f.corners[k];
+        const uint32_t cxb = c & 1u, cyb = (c >> 1) & 1u, czb = (c >> 2) & 1u;
+        corners |= c << (3 * k);
+        su |= (f.ux ? cxb : (f.uy ? cyb : czb)) << k;   // the corner bit of the axis u (v) points along
+        sv |= (f.vx ? cxb : (f.vy ? cyb : czb)) << k;
+    }
+    p.w3 = corners | (su << 12) | (sv << 16);
+    return p;
+}
+
 // out: 12 words = 4 vertices x 12 bytes {pos u8x3, uv u8x3, color u8x4 (L,L,L,S), alpha, 0}  (VertexInfo, Mesh.h:37-44)
-GC_HD void p3b_quad(uint32_t entry, const FaceDesc& f, const uint8_t* lt, const uint32_t* plane_o, const uint16_t* hx,
+GC_HD void p3b_quad(uint32_t entry, const FacePlan& f, const uint8_t* lt, const uint32_t* plane_o, const uint16_t* hx,
                     MatEntry mat, uint32_t out[12])
 {
     const int d = entry & 7, x = (entry >> 3) & 31, tz = (entry >> 8) & 31, ty = (entry >> 13) & 63;
-    const int ax = x + f.nx, ay = ty + f.ny, az = tz + f.nz;
-    const int hr_a = hrow(ay, az);
-    const int hr_u = f.uy * kRowsZ + f.uz, hr_v = f.vy * kRowsZ + f.vz;      // row strides of the in-plane axes
+    const int ux = (int8_t)(f.w1 >> 16), vx = (int8_t)(f.w2 >> 16);
+    const int hr_u = (int16_t)(f.w1 & 0xFFFFu), hr_v = (int16_t)(f.w2 & 0xFFFFu);   // row strides of the in-plane axes
+    const int ax = x + (int8_t)(f.w0 >> 16);
+    const int hr_a = hrow(ty, tz) + (int16_t)(f.w0 & 0xFFFFu);
 
-    // 3x3 light neighbourhood in the layer in front of the face: cell (i, j) = a + i*u + j*v, i, j in -1..1
-    const uint32_t l00 = unpack_light(light_at(lt, hr_a, ax));
-    const uint32_t lm0 = unpack_light(light_at(lt, hr_a - hr_u, ax - f.ux)), lp0 = unpack_light(light_at(lt, hr_a + hr_u, ax + f.ux));
-    const uint32_t l0m = unpack_light(light_at(lt, hr_a - hr_v, ax - f.vx)), l0p = unpack_light(light_at(lt, hr_a + hr_v, ax + f.vx));
-    const uint32_t lmm = unpack_light(light_at(lt, hr_a - hr_u - hr_v, ax - f.ux - f.vx)), lmp = unpack_light(light_at(lt, hr_a - hr_u + hr_v, ax - f.ux + f.vx));
-    const uint32_t lpm = unpack_light(light_at(lt, hr_a + hr_u - hr_v, ax + f.ux - f.vx)), lpp = unpack_light(light_at(lt, hr_a + hr_u + hr_v, ax + f.ux + f.vx));
-    // opacity of the four edge cells (only b and c are ever tested, WorldRender.cpp:361-362)
-    const uint32_t o_um = opaque_at(plane_o, hx, hr_a - hr_u, ax - f.ux), o_up = opaque_at(plane_o, hx, hr_a + hr_u, ax + f.ux);
-    const uint32_t o_vm = opaque_at(plane_o, hx, hr_a - hr_v, ax - f.vx), o_vp = opaque_at(plane_o, hx, hr_a + hr_v, ax + f.vx);
+    // 3x3 light neighbourhood in the layer in front of the face: cell (i, j) = a + i*u + j*v, i, j in -1..1,
+    // and the opacity of the four edge cells (only b and c are ever tested, WorldRender.cpp:361-362)
+    uint32_t l00, lm0, lp0, l0m, l0p, lmm, lmp, lpm, lpp, o_um, o_up, o_vm, o_vp;
+    if ((unsigned)(ax - 1) < 30u)
+    {
+        // the whole footprint has x in 0..31: plain indexing
+        const uint8_t* a = lt + hr_a * kLtStride + ax;
+        const int su = hr_u * kLtStride + ux, sv = hr_v * kLtStride + vx;
+        l00 = a[0]; lm0 = a[-su]; lp0 = a[su]; l0m = a[-sv]; l0p = a[sv];
+        lmm = a[-su - sv]; lmp = a[-su + sv]; lpm = a[su - sv]; lpp = a[su + sv];
+        o_um = (plane_o[hr_a - hr_u] >> (ax - ux)) & 1u; o_up = (plane_o[hr_a + hr_u] >> (ax + ux)) & 1u;
+        o_vm = (plane_o[hr_a - hr_v] >> (ax - vx)) & 1u; o_vp = (plane_o[hr_a + hr_v] >> (ax + vx)) & 1u;
+    }
+    else
+    {
+        l00 = light_at(lt, hr_a, ax);
+        lm0 = light_at(lt, hr_a - hr_u, ax - ux); lp0 = light_at(lt, hr_a + hr_u, ax + ux);
+        l0m = light_at(lt, hr_a - hr_v, ax - vx); l0p = light_at(lt, hr_a + hr_v, ax + vx);
+        lmm = light_at(lt, hr_a - hr_u - hr_v, ax - ux - vx); lmp = light_at(lt, hr_a - hr_u + hr_v, ax - ux + vx);
+        lpm = light_at(lt, hr_a + hr_u - hr_v, ax + ux - vx); lpp = light_at(lt, hr_a + hr_u + hr_v, ax + ux + vx);
+        o_um = opaque_at(plane_o, hx, hr_a - hr_u, ax - ux); o_up = opaque_at(plane_o, hx, hr_a + hr_u, ax + ux);
+        o_vm = opaque_at(plane_o, hx, hr_a - hr_v, ax - vx); o_vp = opaque_at(plane_o, hx, hr_a + hr_v, ax + vx);
+    }
+    l00 = unpack_light(l00); lm0 = unpack_light(lm0); lp0 = unpack_light(lp0); l0m = unpack_light(l0m); l0p = unpack_light(l0p);
+    lmm = unpack_light(lmm); lmp = unpack_light(lmp); lpm = unpack_light(lpm); lpp = unpack_light(lpp);
 
     const uint32_t tex = (d < 4 ? (mat.lo >> (8 * d)) : (mat.hi >> (8 * (d - 4)))) & 255u;
-    const uint32_t alpha = (mat.hi >> 16) & 255u;
+    const uint32_t w1c = tex << 8, w2c = ((mat.hi >> 16) & 255u) << 16;   // constant parts of vertex words 1 and 2
+    const uint32_t pos = (uint32_t)x | ((uint32_t)ty << 8) | ((uint32_t)tz << 16);
 
 #pragma unroll
     for (int k = 0; k < 4; k++)
     {
-        const uint32_t c = f.corners[k];
-        const int cxb = c & 1, cyb = (c >> 1) & 1, czb = (c >> 2) & 1;
-        // corner sign along u / v: the corner bit of the axis u (v) points along
-        const int su = f.ux ? cxb : (f.uy ? cyb : czb);
-        const int sv = f.vx ? cxb : (f.vy ? cyb : czb);
+        const uint32_t c = (f.w3 >> (3 * k)) & 7u;
+        const bool su = (f.w3 >> (12 + k)) & 1u, sv = (f.w3 >> (16 + k)) & 1u;
         const uint32_t ob = su ? o_up : o_um, oc = sv ? o_vp : o_vm;
         const uint32_t lb = su ? lp0 : lm0, lc = sv ? l0p : l0m;
         const uint32_t ld = su ? (sv ? lpp : lpm) : (sv ? lmp : lmm);
         const uint32_t col = corner_color(l00, lb, lc, ld, !(ob & oc));
         const uint32_t l = col & 255u, sn = (col >> 16) & 255u;
         const uint32_t u = (k >> 1) & 1u, v = (k == 0 || k == 3) ? 1u : 0u;   // uv: (0,1) (0,0) (1,0) (1,1)
-        out[3 * k + 0] = (uint32_t)(x + cxb) | ((uint32_t)(ty + cyb) << 8) | ((uint32_t)(tz + czb) << 16) | (u << 24);
-        out[3 * k + 1] = v | (tex << 8) | (l << 16) | (l << 24);
-        out[3 * k + 2] = l | (sn << 8) | (alpha << 16);
+        out[3 * k + 0] = (pos + ((c & 1u) | ((c & 2u) << 7) | ((c & 4u) << 14))) | (u << 24);   // corner offsets never carry (x<=31, y<=63, z<=31)
+        out[3 * k + 1] = v | w1c | (l << 16) | (l << 24);
+        out[3 * k + 2] = l | (sn << 8) | w2c;
     }
 }
 

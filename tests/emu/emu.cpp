@@ -86,7 +86,7 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
                 }
                 uint32_t out[8];
                 p1_class_row(q, lut.data(), out);
-                for (int k = 0; k < 8; k++) { out[k] = rotl_bytes(out[k], rot); planes[k * kHaloRows + hr] = out[k]; }
+                for (int k = 0; k < 8; k++) { out[k] = rotl_bytes(out[k], rot_selector(rot)); planes[k * kHaloRows + hr] = out[k]; }
                 uint32_t vis = centre ? row_emit_mask(out) : 0u;
                 const int sl = tz + 1;
                 if (vis & 1u) bvm[(ty + 1) * 2 + (sl >> 5)] |= 1u << (sl & 31);
@@ -97,14 +97,19 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
             const uint32_t* fw = (const uint32_t*)srow;
             for (int h = 0; h < 2; h++)
             {
-                // the kernel takes the "octet wholly above the surface" shortcut; both forms must agree
-                int smax[2] = { 0, 0 };
-                for (int x = 0; x < 16; x++) { int v = srow[h * 16 + x]; if (v > smax[x >> 3]) smax[x >> 3] = v; }
+                // the kernel classifies each octet against the surface (wholly above / wholly below / mixed); all forms must agree
+                int smax[2] = { 0, 0 }, smin[2] = { 255, 255 };
+                for (int x = 0; x < 16; x++)
+                {
+                    int v = srow[h * 16 + x];
+                    if (v > smax[x >> 3]) smax[x >> 3] = v;
+                    if (v < smin[x >> 3]) smin[x >> 3] = v;
+                }
                 Words4 sn = { sw[4 * h], sw[4 * h + 1], sw[4 * h + 2], sw[4 * h + 3] }, bl = { lw[4 * h], lw[4 * h + 1], lw[4 * h + 2], lw[4 * h + 3] };
                 Words4 sf = { fw[4 * h], fw[4 * h + 1], fw[4 * h + 2], fw[4 * h + 3] };
-                const bool halo_row = ty < 0 || ty >= kTY;     // the kernel's y-halo warp never takes the shortcut
-                Words4 a = p1_light_half(sn, bl, sf, wy, !halo_row && wy >= smax[0], !halo_row && wy >= smax[1]);
-                Words4 b = p1_light_half(sn, bl, sf, wy, false, false);
+                const bool halo_row = ty < 0 || ty >= kTY;     // the kernel's y-halo warp never takes the shortcuts
+                Words4 a = p1_light_half(sn, bl, sf, wy, halo_row ? 0 : light_mode(wy, smax[0], smin[0]), halo_row ? 0 : light_mode(wy, smax[1], smin[1]));
+                Words4 b = p1_light_half(sn, bl, sf, wy, 0, 0);
                 if (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) return -7;
                 memcpy(&lt[hr * kLtStride + h * 16], &a, 16);
             }
@@ -176,7 +181,7 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
         int x = (e >> 3) & 31, tz = (e >> 8) & 31, ty = (e >> 13) & 63;
         uint32_t id = cb[x + 32 * (ty + 64 * tz)] & 255u;
         uint32_t v[12], iw[3];
-        p3b_quad(e, kFaces[e & 7], lt.data(), planes.data() + P_OPAQUE * kHaloRows, hx.data(), mat[id], v);
+        p3b_quad(e, make_face_plan(kFaces[e & 7]), lt.data(), planes.data() + P_OPAQUE * kHaloRows, hx.data(), mat[id], v);
         memcpy(verts_out + (size_t)i * 48, v, 48);
         quad_index_words(i, iw);
         memcpy((uint32_t*)idx_out + (size_t)(type_off[(e >> 19) & 7] + tlist[i]) * 3, iw, 12);
