@@ -4,7 +4,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gcmesh_kernel.cuh"
@@ -91,6 +93,12 @@ struct GcWorld
     uint8_t* d_light;
     uint8_t* d_surface;
     MeshTensorMaps maps;
+    // sparse upload state
+    uint8_t* slot_dirty;      // host: per slot, bit a set = device array a of the slot may hold non-zero data
+    uint8_t* scan_flags;      // host: per slot, bit a set = host array a is non-zero (result of the last scan)
+    uint32_t* h_items;        // pinned: work list of the upload kernel
+    uint32_t* d_items;
+    int launches;             // kernels launched by the last upload call
 };
 
 struct GcBatch
@@ -277,7 +285,12 @@ int gcmesh_world_create(GcContext* ctx, int size_x, int size_z, GcWorld** out)
     if (e == cudaSuccess) e = cudaMemsetAsync(w->d_sun, 0, w->n_slots * GC_CHUNK_SIZE_3, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(w->d_light, 0, w->n_slots * GC_CHUNK_SIZE_3, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(w->d_surface, 0, w->n_cols * GC_CHUNK_SIZE_2, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocHost(&w->h_items, sizeof(uint32_t) * w->n_slots * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_items, sizeof(uint32_t) * w->n_slots * 3);
     if (e != cudaSuccess) { gcmesh_world_destroy(w); return fail(GC_ERR_CUDA, "world allocation", cudaGetErrorString(e)); }
+    w->slot_dirty = (uint8_t*)calloc(w->n_slots, 1);
+    w->scan_flags = (uint8_t*)calloc(w->n_slots, 1);
+    if (!w->slot_dirty || !w->scan_flags) { gcmesh_world_destroy(w); return fail(GC_ERR_ARG, "out of host memory"); }
     int st = GC_OK;
     if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_slab, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots);
     if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots);
@@ -292,7 +305,9 @@ int gcmesh_world_destroy(GcWorld* w)
     if (!w) return GC_OK;
     cudaSetDevice(w->ctx->device);
     cudaStreamSynchronize(w->ctx->stream);
-    cudaFree(w->d_blocks); cudaFree(w->d_sun); cudaFree(w->d_light); cudaFree(w->d_surface);
+    cudaFree(w->d_blocks); cudaFree(w->d_sun); cudaFree(w->d_light); cudaFree(w->d_surface); cudaFree(w->d_items);
+    if (w->h_items) cudaFreeHost(w->h_items);
+    free(w->slot_dirty); free(w->scan_flags);
     delete w;
     return GC_OK;
 }
@@ -305,6 +320,7 @@ int gcmesh_world_upload_chunk(GcWorld* w, int cx, int cy, int cz, const uint16_t
     if (!column_ok(w, cx, cz) || cy < 0 || cy >= GC_WORLD_CHUNK_HEIGHT) return fail(GC_ERR_ARG, "chunk position outside the window");
     GC_CUDA(cudaSetDevice(w->ctx->device));
     const size_t slot = ((size_t)cz * w->size_x + cx) * GC_WORLD_CHUNK_HEIGHT + cy;
+    w->slot_dirty[slot] |= (blocks ? 1 : 0) | (sunlight ? 2 : 0) | (block_light ? 4 : 0);
     if (blocks) GC_CUDA(cudaMemcpyAsync(w->d_blocks + slot * GC_CHUNK_SIZE_3, blocks, GC_CHUNK_SIZE_3 * 2, cudaMemcpyHostToDevice, w->ctx->stream));
     if (sunlight) GC_CUDA(cudaMemcpyAsync(w->d_sun + slot * GC_CHUNK_SIZE_3, sunlight, GC_CHUNK_SIZE_3, cudaMemcpyHostToDevice, w->ctx->stream));
     if (block_light) GC_CUDA(cudaMemcpyAsync(w->d_light + slot * GC_CHUNK_SIZE_3, block_light, GC_CHUNK_SIZE_3, cudaMemcpyHostToDevice, w->ctx->stream));
@@ -327,6 +343,7 @@ int gcmesh_world_upload_rows(GcWorld* w, int cz0, int cz1, const uint16_t* block
     GC_CUDA(cudaSetDevice(w->ctx->device));
     const size_t s0 = (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT * GC_CHUNK_SIZE_3;
     const size_t ns = (size_t)(cz1 - cz0) * w->size_x * GC_WORLD_CHUNK_HEIGHT * GC_CHUNK_SIZE_3;
+    memset(w->slot_dirty + (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, 7, (size_t)(cz1 - cz0) * w->size_x * GC_WORLD_CHUNK_HEIGHT);
     if (blocks) GC_CUDA(cudaMemcpyAsync(w->d_blocks + s0, blocks + s0, ns * 2, cudaMemcpyHostToDevice, w->ctx->stream));
     if (sunlight) GC_CUDA(cudaMemcpyAsync(w->d_sun + s0, sunlight + s0, ns, cudaMemcpyHostToDevice, w->ctx->stream));
     if (block_light) GC_CUDA(cudaMemcpyAsync(w->d_light + s0, block_light + s0, ns, cudaMemcpyHostToDevice, w->ctx->stream));
@@ -343,6 +360,100 @@ int gcmesh_world_upload_all(GcWorld* w, const uint16_t* blocks, const uint8_t* s
     if (!w) return fail(GC_ERR_ARG, "world is null");
     return gcmesh_world_upload_rows(w, 0, w->size_z, blocks, sunlight, block_light, surface);
 }
+
+// Is a 64-byte-aligned buffer all zero?  (8 x 64-bit ORs per 64 bytes; exits at the first non-zero 4 KB block.)
+static bool all_zero(const void* p, size_t bytes)
+{
+    const uint64_t* q = (const uint64_t*)p;
+    const size_t n = bytes / 8;
+    for (size_t i = 0; i < n; i += 512)
+    {
+        uint64_t acc = 0;
+        for (size_t j = 0; j < 512; j += 8) acc |= q[i + j] | q[i + j + 1] | q[i + j + 2] | q[i + j + 3] | q[i + j + 4] | q[i + j + 5] | q[i + j + 6] | q[i + j + 7];
+        if (acc) return false;
+    }
+    return true;
+}
+
+int gcmesh_world_upload_sparse(GcWorld* w, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface,
+                               const uint8_t* nonzero_hint, int threads)
+{
+    if (!w || !blocks || !sunlight || !block_light) return fail(GC_ERR_ARG, "null argument");
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    w->launches = 0;
+    const size_t n = w->n_slots;
+
+    // 1. which host arrays hold anything?  Either the caller's per-slot hint (bit a = array a is non-zero) or a scan.
+    if (nonzero_hint) memcpy(w->scan_flags, nonzero_hint, n);
+    else
+    {
+        int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+        if (nt < 1) nt = 1;
+        if (nt > 64) nt = 64;
+        std::atomic<size_t> next(0);
+        auto work = [&]()
+        {
+            for (;;)
+            {
+                const size_t s0 = next.fetch_add(16);
+                if (s0 >= n) break;
+                const size_t s1 = s0 + 16 < n ? s0 + 16 : n;
+                for (size_t s = s0; s < s1; s++)
+                {
+                    uint8_t f = 0;
+                    if (!all_zero(blocks + s * GC_CHUNK_SIZE_3, (size_t)GC_CHUNK_SIZE_3 * 2)) f |= 1;
+                    if (!all_zero(sunlight + s * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 2;
+                    if (!all_zero(block_light + s * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 4;
+                    w->scan_flags[s] = f;
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; t++) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+    }
+
+    // 2. non-zero arrays are pulled by the GPU; arrays that turned zero are cleared on the device
+    cudaPointerAttributes attr;
+    const bool mapped = cudaPointerGetAttributes(&attr, blocks) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr
+                        && cudaPointerGetAttributes(&attr, sunlight) == cudaSuccess && attr.type == cudaMemoryTypeHost
+                        && cudaPointerGetAttributes(&attr, block_light) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    cudaStream_t s = ctx->stream;
+    int n_items = 0;
+    for (size_t slot = 0; slot < n; slot++)
+    {
+        const uint8_t f = w->scan_flags[slot], dirty = w->slot_dirty[slot];
+        for (int a = 0; a < 3; a++)
+        {
+            const size_t bytes = a == 0 ? (size_t)GC_CHUNK_SIZE_3 * 2 : (size_t)GC_CHUNK_SIZE_3;
+            uint8_t* dst = a == 0 ? (uint8_t*)w->d_blocks + slot * bytes : (a == 1 ? w->d_sun : w->d_light) + slot * bytes;
+            if (f & (1 << a))
+            {
+                if (mapped) w->h_items[n_items++] = (uint32_t)(slot * 4 + a);
+                else
+                {
+                    const uint8_t* src = a == 0 ? (const uint8_t*)blocks + slot * bytes : (a == 1 ? sunlight : block_light) + slot * bytes;
+                    GC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+                }
+            }
+            else if (dirty & (1 << a)) GC_CUDA(cudaMemsetAsync(dst, 0, bytes, s));
+        }
+        w->slot_dirty[slot] = f;
+    }
+    if (n_items)
+    {
+        GC_CUDA(cudaMemcpyAsync(w->d_items, w->h_items, sizeof(uint32_t) * (size_t)n_items, cudaMemcpyHostToDevice, s));
+        GC_CUDA(launch_upload_items(w->d_items, n_items, blocks, sunlight, block_light, w->d_blocks, w->d_sun, w->d_light, s));
+        w->launches = 1;
+    }
+    if (surface) GC_CUDA(cudaMemcpyAsync(w->d_surface, surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyHostToDevice, s));
+    return GC_OK;
+}
+
+int gcmesh_world_upload_launches(const GcWorld* w) { return w ? w->launches : 0; }
 
 int gcmesh_world_device_ptrs(GcWorld* w, void** blocks, void** sunlight, void** block_light, void** surface)
 {

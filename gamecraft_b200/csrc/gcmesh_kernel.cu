@@ -730,7 +730,44 @@ __global__ void gc_halo_copy_kernel(uint16_t* blocks, uint8_t* sun, uint8_t* lig
         if (unpack) *g = sb[i]; else sb[i] = *g;
     }
 }
+// ---- sparse upload: the GPU pulls the non-zero brick arrays straight out of pinned host memory over PCIe ----
+__global__ void __launch_bounds__(256)
+gc_upload_kernel(const uint32_t* __restrict__ items, int n_items, const uint16_t* __restrict__ h_blocks, const uint8_t* __restrict__ h_sun,
+                 const uint8_t* __restrict__ h_light, uint16_t* d_blocks, uint8_t* d_sun, uint8_t* d_light)
+{
+    // each CTA takes 16 KB pieces so that every SM keeps many 16-byte loads in flight on the link
+    constexpr int kPiece = 16384;
+    const long long total = (long long)n_items * 8;   // up to 8 pieces per array (blocks 128 KB = 8, light arrays 64 KB = 4)
+    for (long long w = blockIdx.x; w < total; w += gridDim.x)
+    {
+        const uint32_t item = items[w >> 3];
+        const int piece = (int)(w & 7);
+        const uint32_t slot = item >> 2, arr = item & 3u;
+        const size_t bytes = arr == 0 ? (size_t)GC_CHUNK_SIZE_3 * 2 : (size_t)GC_CHUNK_SIZE_3;
+        if ((size_t)piece * kPiece >= bytes) continue;
+        const uint8_t* src = arr == 0 ? reinterpret_cast<const uint8_t*>(h_blocks) + (size_t)slot * bytes
+                                      : (arr == 1 ? h_sun : h_light) + (size_t)slot * bytes;
+        uint8_t* dst = arr == 0 ? reinterpret_cast<uint8_t*>(d_blocks) + (size_t)slot * bytes : (arr == 1 ? d_sun : d_light) + (size_t)slot * bytes;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src + (size_t)piece * kPiece);
+        uint4* d4 = reinterpret_cast<uint4*>(dst + (size_t)piece * kPiece);
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = s4[threadIdx.x + i * 256];
+#pragma unroll
+        for (int i = 0; i < 4; i++) d4[threadIdx.x + i * 256] = v[i];
+    }
+}
 }  // namespace
+
+cudaError_t launch_upload_items(const uint32_t* items, int n_items, const uint16_t* h_blocks, const uint8_t* h_sun, const uint8_t* h_light,
+                                uint16_t* d_blocks, uint8_t* d_sun, uint8_t* d_light, cudaStream_t stream)
+{
+    if (n_items <= 0) return cudaSuccess;
+    long long pieces = (long long)n_items * 8;
+    int grid = pieces < 148 * 16 ? (int)pieces : 148 * 16;
+    gc_upload_kernel<<<grid, 256, 0, stream>>>(items, n_items, h_blocks, h_sun, h_light, d_blocks, d_sun, d_light);
+    return cudaGetLastError();
+}
 
 size_t mesh_smem_bytes() { return (size_t)kSmemBytes; }
 

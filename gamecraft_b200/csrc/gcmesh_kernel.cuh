@@ -52,6 +52,11 @@ size_t mesh_smem_bytes();
 cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int grid, cudaStream_t stream);
 cudaError_t mesh_kernel_attributes(int* regs, int* static_smem, int* max_dyn_smem);
 
+// Sparse upload: copy the listed brick arrays from (pinned, device-mapped) host memory into their device slots.
+// item = slot * 4 + array (0 blocks, 1 sunlight, 2 blockLight); host pointers are the brick-major arrays.
+cudaError_t launch_upload_items(const uint32_t* items, int n_items, const uint16_t* h_blocks, const uint8_t* h_sun, const uint8_t* h_light,
+                                uint16_t* d_blocks, uint8_t* d_sun, uint8_t* d_light, cudaStream_t stream);
+
 // Slab-halo pack / unpack (multi-GPU): see gcmesh_world_pack_halo in gcmesh.h.
 cudaError_t launch_halo_copy(const uint16_t* blocks, const uint8_t* sun, const uint8_t* light, const uint8_t* surface,
                              int size_x, int cz, int z, uint8_t* buf, bool unpack, cudaStream_t stream);

@@ -69,7 +69,7 @@ EXPORTS = [
     "gcmesh_version", "gcmesh_last_error", "gcmesh_create", "gcmesh_destroy", "gcmesh_set_stream",
     "gcmesh_set_block_table", "gcmesh_default_block_table", "gcmesh_synchronize",
     "gcmesh_world_create", "gcmesh_world_destroy", "gcmesh_world_upload_chunk", "gcmesh_world_upload_surface",
-    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
+    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_upload_launches", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
     "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
     "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_wait", "gcmesh_batch_results",
     "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
@@ -101,6 +101,8 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_upload_surface.argtypes = [vp, ci, ci, vp]
         L.gcmesh_world_upload_all.argtypes = [vp, vp, vp, vp, vp]
         L.gcmesh_world_upload_rows.argtypes = [vp, ci, ci, vp, vp, vp, vp]
+        L.gcmesh_world_upload_sparse.argtypes = [vp, vp, vp, vp, vp, vp, ci]
+        L.gcmesh_world_upload_launches.argtypes = [vp]
         L.gcmesh_world_device_ptrs.argtypes = [vp] + [ctypes.POINTER(vp)] * 4
         L.gcmesh_world_halo_bytes.argtypes = [vp]
         L.gcmesh_world_halo_bytes.restype = ctypes.c_size_t
@@ -193,6 +195,16 @@ class World:
         _check(lib().gcmesh_world_upload_all(self.h, _ptr(host.blocks), _ptr(host.sun), _ptr(host.light), _ptr(host.surface)),
                "gcmesh_world_upload_all")
         return self
+
+    def upload_sparse(self, host, nonzero_hint=None, threads: int = 0) -> "World":
+        """Like :meth:`upload`, moving only the brick arrays that are not all zero (host scan, or the caller's hint)."""
+        assert host.size_x == self.size_x and host.size_z == self.size_z
+        _check(lib().gcmesh_world_upload_sparse(self.h, _ptr(host.blocks), _ptr(host.sun), _ptr(host.light), _ptr(host.surface),
+                                                _ptr(nonzero_hint), threads), "gcmesh_world_upload_sparse")
+        return self
+
+    def upload_launches(self) -> int:
+        return int(lib().gcmesh_world_upload_launches(self.h))
 
     def upload_rows(self, host, cz0: int, cz1: int) -> "World":
         _check(lib().gcmesh_world_upload_rows(self.h, cz0, cz1, _ptr(host.blocks), _ptr(host.sun), _ptr(host.light), _ptr(host.surface)),

@@ -251,3 +251,45 @@ def test_gpu_full_size_properties(ctx):
     for i in rng.choice(4096, 96, replace=False):
         util.assert_same_mesh(meshes[i], o.build_chunk(*coords[i]), str(coords[i]))
     batch.close(); world.close()
+
+
+def test_gpu_sparse_upload_equals_dense(ctx):
+    """gcmesh_world_upload_sparse leaves the device world exactly as a full upload would (pageable and pinned host arrays,
+    host scan and caller hint, and an array that turns zero between uploads)."""
+    import torch
+
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(5, 5, origin=(-2, -2)).build("mixed", 23, radius=100, falloff=60)
+    coords = w.interior_chunks(1)
+    o = ob.OracleWorld(w)
+    want = [o.build_chunk(*c) for c in coords]
+    batch = mesher.Batch(ctx, len(coords), len(coords) * mesher.MAX_QUADS)
+
+    def check(world):
+        for c, m, x in zip(coords, batch.submit(world, coords).wait().meshes(), want):
+            util.assert_same_mesh(m, x, str(c))
+
+    world = mesher.World(ctx, 5, 5).upload_sparse(w)                      # pageable numpy arrays: memcpy path
+    check(world)
+    assert world.upload_launches() == 0
+    pins = [torch.from_numpy(a).pin_memory() for a in (w.blocks, w.sun, w.light, w.surface)]
+
+    class P:
+        size_x, size_z = 5, 5
+        blocks, sun, light, surface = [t.numpy() for t in pins]
+
+    world2 = mesher.World(ctx, 5, 5).upload_sparse(P)                      # pinned arrays: GPU pull kernel
+    assert world2.upload_launches() == 1
+    check(world2)
+    hint = (P.blocks.any(axis=1) * 1 + P.sun.any(axis=1) * 2 + P.light.any(axis=1) * 4).astype(np.uint8)
+    world3 = mesher.World(ctx, 5, 5).upload_sparse(P, nonzero_hint=hint)   # caller's hint instead of the scan
+    check(world3)
+    # a chunk is cleared on the host: the next sparse upload must clear it on the device too
+    s = w.slot(2, 0, 2)
+    P.blocks[s] = 0; P.sun[s] = 0; P.light[s] = 0
+    w.blocks[s] = 0; w.sun[s] = 0; w.light[s] = 0
+    want = [o.build_chunk(*c) for c in coords]
+    world2.upload_sparse(P)
+    check(world2)
+    batch.close(); world.close(); world2.close(); world3.close()
