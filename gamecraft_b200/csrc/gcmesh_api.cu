@@ -81,6 +81,10 @@ struct GcContext
     EncodeTiledFn encode;
     DeviceTables* d_tables;
     int use_tma;
+    // gcmesh_mesh_host pipeline
+    cudaStream_t upload_stream, download_stream;
+    cudaEvent_t ev_fork, ev_join, ev_uploaded[64], ev_meshed[64];
+    unsigned long long* h_strip_cursor;   // pinned [64]
 };
 
 struct GcWorld
@@ -215,7 +219,17 @@ int gcmesh_create(int device, void* stream, GcContext** out)
     ctx->encode = (EncodeTiledFn)fn;
 
     e = cudaMalloc(&ctx->d_tables, sizeof(DeviceTables));
-    if (e != cudaSuccess) { delete ctx; return fail(GC_ERR_CUDA, "cudaMalloc tables", cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->download_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    for (int i = 0; i < 64 && e == cudaSuccess; i++)
+    {
+        e = cudaEventCreateWithFlags(&ctx->ev_uploaded[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_meshed[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_strip_cursor, sizeof(unsigned long long) * 64);
+    if (e != cudaSuccess) { delete ctx; return fail(GC_ERR_CUDA, "context allocation", cudaGetErrorString(e)); }
     GcBlockInfo table[24];
     reference_block_table(table);
     int st = upload_tables(ctx, table, 24, 20);
@@ -230,6 +244,10 @@ int gcmesh_destroy(GcContext* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_tables);
+    cudaStreamDestroy(ctx->upload_stream); cudaStreamDestroy(ctx->download_stream);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    for (int i = 0; i < 64; i++) { cudaEventDestroy(ctx->ev_uploaded[i]); cudaEventDestroy(ctx->ev_meshed[i]); }
+    cudaFreeHost(ctx->h_strip_cursor);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GC_OK;
@@ -375,55 +393,32 @@ static bool all_zero(const void* p, size_t bytes)
     return true;
 }
 
-int gcmesh_world_upload_sparse(GcWorld* w, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface,
-                               const uint8_t* nonzero_hint, int threads)
+// Zero / non-zero classification of the host brick arrays of one slot into w->scan_flags.
+static inline void scan_slot(GcWorld* w, size_t slot, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light)
 {
-    if (!w || !blocks || !sunlight || !block_light) return fail(GC_ERR_ARG, "null argument");
-    GcContext* ctx = w->ctx;
-    GC_CUDA(cudaSetDevice(ctx->device));
-    w->launches = 0;
-    const size_t n = w->n_slots;
+    uint8_t f = 0;
+    if (!all_zero(blocks + slot * GC_CHUNK_SIZE_3, (size_t)GC_CHUNK_SIZE_3 * 2)) f |= 1;
+    if (!all_zero(sunlight + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 2;
+    if (!all_zero(block_light + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 4;
+    w->scan_flags[slot] = f;
+}
 
-    // 1. which host arrays hold anything?  Either the caller's per-slot hint (bit a = array a is non-zero) or a scan.
-    if (nonzero_hint) memcpy(w->scan_flags, nonzero_hint, n);
-    else
-    {
-        int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
-        if (nt < 1) nt = 1;
-        if (nt > 64) nt = 64;
-        std::atomic<size_t> next(0);
-        auto work = [&]()
-        {
-            for (;;)
-            {
-                const size_t s0 = next.fetch_add(16);
-                if (s0 >= n) break;
-                const size_t s1 = s0 + 16 < n ? s0 + 16 : n;
-                for (size_t s = s0; s < s1; s++)
-                {
-                    uint8_t f = 0;
-                    if (!all_zero(blocks + s * GC_CHUNK_SIZE_3, (size_t)GC_CHUNK_SIZE_3 * 2)) f |= 1;
-                    if (!all_zero(sunlight + s * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 2;
-                    if (!all_zero(block_light + s * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 4;
-                    w->scan_flags[s] = f;
-                }
-            }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt; t++) pool.emplace_back(work);
-        work();
-        for (auto& th : pool) th.join();
-    }
+static int scan_threads(int threads)
+{
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    return nt > 64 ? 64 : nt;
+}
 
-    // 2. non-zero arrays are pulled by the GPU; arrays that turned zero are cleared on the device
-    cudaPointerAttributes attr;
-    const bool mapped = cudaPointerGetAttributes(&attr, blocks) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr
-                        && cudaPointerGetAttributes(&attr, sunlight) == cudaSuccess && attr.type == cudaMemoryTypeHost
-                        && cudaPointerGetAttributes(&attr, block_light) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    cudaStream_t s = ctx->stream;
+// Enqueue on `s` the upload of rows [cz0, cz1) according to w->scan_flags: non-zero arrays are pulled by the GPU (or copied
+// one by one when the host arrays are not pinned), arrays that turned zero are cleared.  Returns kernels launched (< 0: error).
+static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light,
+                        bool mapped, cudaStream_t s)
+{
+    const size_t s_begin = (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, s_end = (size_t)cz1 * w->size_x * GC_WORLD_CHUNK_HEIGHT;
+    uint32_t* items = w->h_items + s_begin * 3;   // this row range's own part of the pinned work list
     int n_items = 0;
-    for (size_t slot = 0; slot < n; slot++)
+    for (size_t slot = s_begin; slot < s_end; slot++)
     {
         const uint8_t f = w->scan_flags[slot], dirty = w->slot_dirty[slot];
         for (int a = 0; a < 3; a++)
@@ -432,24 +427,75 @@ int gcmesh_world_upload_sparse(GcWorld* w, const uint16_t* blocks, const uint8_t
             uint8_t* dst = a == 0 ? (uint8_t*)w->d_blocks + slot * bytes : (a == 1 ? w->d_sun : w->d_light) + slot * bytes;
             if (f & (1 << a))
             {
-                if (mapped) w->h_items[n_items++] = (uint32_t)(slot * 4 + a);
+                if (mapped) items[n_items++] = (uint32_t)(slot * 4 + a);
                 else
                 {
                     const uint8_t* src = a == 0 ? (const uint8_t*)blocks + slot * bytes : (a == 1 ? sunlight : block_light) + slot * bytes;
-                    GC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+                    if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
                 }
             }
-            else if (dirty & (1 << a)) GC_CUDA(cudaMemsetAsync(dst, 0, bytes, s));
+            else if (dirty & (1 << a)) { if (cudaMemsetAsync(dst, 0, bytes, s) != cudaSuccess) return -1; }
         }
         w->slot_dirty[slot] = f;
     }
     if (n_items)
     {
-        GC_CUDA(cudaMemcpyAsync(w->d_items, w->h_items, sizeof(uint32_t) * (size_t)n_items, cudaMemcpyHostToDevice, s));
-        GC_CUDA(launch_upload_items(w->d_items, n_items, blocks, sunlight, block_light, w->d_blocks, w->d_sun, w->d_light, s));
-        w->launches = 1;
+        if (cudaMemcpyAsync(w->d_items + s_begin * 3, items, sizeof(uint32_t) * (size_t)n_items, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+        if (launch_upload_items(w->d_items + s_begin * 3, n_items, blocks, sunlight, block_light, w->d_blocks, w->d_sun, w->d_light, s) != cudaSuccess) return -1;
+        return 1;
     }
-    if (surface) GC_CUDA(cudaMemcpyAsync(w->d_surface, surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+// Classify rows [cz0, cz1) (scan with `threads` host threads, or the caller's hint) and enqueue their upload.
+static int upload_rows_sparse(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light,
+                              const uint8_t* nonzero_hint, int threads, bool mapped, cudaStream_t s)
+{
+    const size_t s_begin = (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, s_end = (size_t)cz1 * w->size_x * GC_WORLD_CHUNK_HEIGHT;
+    if (nonzero_hint) memcpy(w->scan_flags + s_begin, nonzero_hint + s_begin, s_end - s_begin);
+    else
+    {
+        const int nt = scan_threads(threads);
+        std::atomic<size_t> next(s_begin);
+        auto work = [&]()
+        {
+            for (;;)
+            {
+                const size_t a0 = next.fetch_add(8);
+                if (a0 >= s_end) break;
+                const size_t a1 = a0 + 8 < s_end ? a0 + 8 : s_end;
+                for (size_t slot = a0; slot < a1; slot++) scan_slot(w, slot, blocks, sunlight, block_light);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; t++) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+    }
+    return enqueue_rows(w, cz0, cz1, blocks, sunlight, block_light, mapped, s);
+}
+
+static bool host_arrays_mapped(const void* blocks, const void* sunlight, const void* block_light)
+{
+    cudaPointerAttributes attr;
+    const bool mapped = cudaPointerGetAttributes(&attr, blocks) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr
+                        && cudaPointerGetAttributes(&attr, sunlight) == cudaSuccess && attr.type == cudaMemoryTypeHost
+                        && cudaPointerGetAttributes(&attr, block_light) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return mapped;
+}
+
+int gcmesh_world_upload_sparse(GcWorld* w, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface,
+                               const uint8_t* nonzero_hint, int threads)
+{
+    if (!w || !blocks || !sunlight || !block_light) return fail(GC_ERR_ARG, "null argument");
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    const int k = upload_rows_sparse(w, 0, w->size_z, blocks, sunlight, block_light, nonzero_hint, threads,
+                                     host_arrays_mapped(blocks, sunlight, block_light), ctx->stream);
+    if (k < 0) return fail(GC_ERR_CUDA, "sparse upload", cudaGetErrorString(cudaGetLastError()));
+    w->launches = k;
+    if (surface) GC_CUDA(cudaMemcpyAsync(w->d_surface, surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyHostToDevice, ctx->stream));
     return GC_OK;
 }
 
@@ -535,12 +581,8 @@ int gcmesh_batch_destroy(GcBatch* b)
     return GC_OK;
 }
 
-int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
+static int validate_coords(const GcWorld* w, const GcChunkCoord* coords, int n)
 {
-    if (!w || !b || (!coords && n > 0)) return fail(GC_ERR_ARG, "null argument");
-    if (w->ctx != b->ctx) return fail(GC_ERR_ARG, "world and batch belong to different contexts");
-    if (n < 0) return fail(GC_ERR_ARG, "negative chunk count");
-    if (n > b->max_chunks) return fail(GC_ERR_CAPACITY, "batch created for fewer chunks");
     for (int i = 0; i < n; i++)
     {
         const GcChunkCoord c = coords[i];
@@ -548,6 +590,35 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
         if (c.cx < 1 || c.cx > w->size_x - 2 || c.cz < 1 || c.cz > w->size_z - 2 || c.cy < 0 || c.cy >= GC_WORLD_CHUNK_HEIGHT)
             return fail(GC_ERR_ARG, "chunk on the window edge or outside the window");
     }
+    return GC_OK;
+}
+
+// Launch the mesh kernel over d_coords[first, first + count) on stream s; descriptors go to d_out[first ...].
+static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cudaStream_t s)
+{
+    GcContext* ctx = w->ctx;
+    cudaError_t e = cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t), s);   // work counter (the error flag persists)
+    if (e != cudaSuccess || count <= 0) return e;
+    MeshParams p;
+    p.blocks = w->d_blocks; p.sun = w->d_sun; p.light = w->d_light; p.surface = w->d_surface;
+    p.size_x = w->size_x; p.size_z = w->size_z;
+    p.coords = b->d_coords + first; p.n_chunks = count; p.out = b->d_out + first;
+    p.vertex_arena = b->d_vertices; p.index_arena = b->d_indices; p.max_quads = b->max_quads;
+    p.quad_cursor = b->d_cursor; p.work_counter = b->d_counters; p.tables = ctx->d_tables;
+    p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma; p.prof = b->d_prof;
+    const int grid = count < ctx->num_sms ? count : ctx->num_sms;
+    e = launch_mesh(p, w->maps, grid, s);
+    if (e == cudaSuccess) b->launches++;
+    return e;
+}
+
+int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
+{
+    if (!w || !b || (!coords && n > 0)) return fail(GC_ERR_ARG, "null argument");
+    if (w->ctx != b->ctx) return fail(GC_ERR_ARG, "world and batch belong to different contexts");
+    if (n < 0) return fail(GC_ERR_ARG, "negative chunk count");
+    if (n > b->max_chunks) return fail(GC_ERR_CAPACITY, "batch created for fewer chunks");
+    if (validate_coords(w, coords, n) != GC_OK) return GC_ERR_ARG;
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
     // the pinned coordinate staging buffer is reused: wait until the previous submission has consumed it (its kernel
@@ -561,21 +632,9 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
     GC_CUDA(cudaEventRecord(b->ev_coords, s));
     GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), s));
     GC_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t) * 2, s));
+    if (b->d_prof) GC_CUDA(cudaMemsetAsync(b->d_prof, 0, sizeof(unsigned long long) * 512, s));
     GC_CUDA(cudaEventRecord(b->ev_start, s));
-    if (n > 0)
-    {
-        MeshParams p;
-        p.blocks = w->d_blocks; p.sun = w->d_sun; p.light = w->d_light; p.surface = w->d_surface;
-        p.size_x = w->size_x; p.size_z = w->size_z;
-        p.coords = b->d_coords; p.n_chunks = n; p.out = b->d_out;
-        p.vertex_arena = b->d_vertices; p.index_arena = b->d_indices; p.max_quads = b->max_quads;
-        p.quad_cursor = b->d_cursor; p.work_counter = b->d_counters; p.tables = ctx->d_tables;
-        p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma; p.prof = b->d_prof;
-        if (b->d_prof) GC_CUDA(cudaMemsetAsync(b->d_prof, 0, sizeof(unsigned long long) * 512, s));
-        const int grid = n < ctx->num_sms ? n : ctx->num_sms;
-        GC_CUDA(launch_mesh(p, w->maps, grid, s));
-        b->launches = 1;
-    }
+    GC_CUDA(launch_range(w, b, 0, n, s));
     GC_CUDA(cudaEventRecord(b->ev_stop, s));
     GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -583,6 +642,137 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
     if (b->d_prof) GC_CUDA(cudaMemcpyAsync(b->h_prof, b->d_prof, sizeof(unsigned long long) * 512, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaEventRecord(b->ev_done, s));
     b->state = 1;
+    return GC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host arrays in, host meshes out — the call a host-side integration makes per frame / per rebuild list.
+// The window is processed in strips of rows so that the zero-scan of strip k+1 (host threads), the PCIe pull of strip
+// k (upload stream), the meshing of strip k-1 (context stream) and the read-back of strip k-2 (download stream) overlap.
+int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light,
+                     const uint8_t* surface, const uint8_t* nonzero_hint, const GcChunkCoord* coords, int n,
+                     void* host_vertices, void* host_indices, uint64_t host_capacity_quads, int threads)
+{
+    if (!w || !b || !blocks || !sunlight || !block_light || !surface || (!coords && n > 0)) return fail(GC_ERR_ARG, "null argument");
+    if (w->ctx != b->ctx) return fail(GC_ERR_ARG, "world and batch belong to different contexts");
+    if (n < 0 || n > b->max_chunks) return fail(GC_ERR_CAPACITY, "batch created for fewer chunks");
+    if (validate_coords(w, coords, n) != GC_OK) return GC_ERR_ARG;
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    if (b->state == 1) GC_CUDA(cudaEventSynchronize(b->ev_done));
+
+    constexpr int kStripRows = 4;
+    const int n_strips = (w->size_z + kStripRows - 1) / kStripRows;
+    if (n_strips > 64) return fail(GC_ERR_ARG, "window deeper than 256 rows: call gcmesh_world_upload_sparse + gcmesh_submit instead");
+
+    // chunks bucketed by strip (stable), `perm` maps the sorted position back to the caller's order
+    std::vector<int> first(n_strips + 1, 0), perm((size_t)n);
+    for (int i = 0; i < n; i++) first[coords[i].cz / kStripRows + 1]++;
+    for (int k = 0; k < n_strips; k++) first[k + 1] += first[k];
+    {
+        std::vector<int> fill(first.begin(), first.end() - 1);
+        for (int i = 0; i < n; i++) { const int pos = fill[coords[i].cz / kStripRows]++; perm[pos] = i; b->h_coords[pos] = coords[i]; }
+    }
+
+    cudaStream_t sm = ctx->stream, su = ctx->upload_stream, sd = ctx->download_stream;
+    const bool mapped = host_arrays_mapped(blocks, sunlight, block_light);
+    b->n = n; b->launches = 0; w->launches = 0;
+    GC_CUDA(cudaEventRecord(ctx->ev_fork, sm));
+    GC_CUDA(cudaStreamWaitEvent(su, ctx->ev_fork, 0));        // the upload overwrites what earlier work on the context stream read
+    GC_CUDA(cudaStreamWaitEvent(sd, ctx->ev_fork, 0));
+    GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, su));
+    GC_CUDA(cudaMemcpyAsync(w->d_surface, surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyHostToDevice, su));
+    GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), su));
+    GC_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t) * 2, su));
+    GC_CUDA(cudaEventRecord(b->ev_start, sm));
+
+    unsigned long long* cursors = ctx->h_strip_cursor;        // pinned: arena cursor after each strip's kernel
+    uint64_t copied = 0;
+    auto read_back = [&](int j) -> int                        // strip j has been meshed: copy its arena range to the host buffers
+    {
+        GC_CUDA(cudaEventSynchronize(ctx->ev_meshed[j]));
+        uint64_t end = cursors[j] < b->max_quads ? cursors[j] : b->max_quads;
+        if (end > host_capacity_quads) end = host_capacity_quads;
+        if (end > copied)
+        {
+            if (host_vertices) GC_CUDA(cudaMemcpyAsync((uint8_t*)host_vertices + copied * 48, b->d_vertices + copied * 48, (size_t)(end - copied) * 48, cudaMemcpyDeviceToHost, sd));
+            if (host_indices) GC_CUDA(cudaMemcpyAsync((uint8_t*)host_indices + copied * 12, (uint8_t*)b->d_indices + copied * 12, (size_t)(end - copied) * 12, cudaMemcpyDeviceToHost, sd));
+            copied = end;
+        }
+        return GC_OK;
+    };
+    auto mesh_strip = [&](int j) -> int                       // strips <= j + 1 are on the device (or queued on the upload stream)
+    {
+        const int up = j + 1 < n_strips ? j + 1 : n_strips - 1;
+        GC_CUDA(cudaStreamWaitEvent(sm, ctx->ev_uploaded[up], 0));
+        GC_CUDA(launch_range(w, b, first[j], first[j + 1] - first[j], sm));
+        GC_CUDA(cudaMemcpyAsync(&cursors[j], b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm));
+        GC_CUDA(cudaEventRecord(ctx->ev_meshed[j], sm));
+        return GC_OK;
+    };
+
+    // the zero-scan runs on background threads over the whole window, slots in ascending order; the pipeline below
+    // consumes it strip by strip (remaining[k] = slots of strip k still to classify)
+    const size_t slots_per_row = (size_t)w->size_x * GC_WORLD_CHUNK_HEIGHT;
+    std::vector<std::atomic<int>> remaining((size_t)n_strips);
+    std::vector<std::thread> pool;
+    std::atomic<size_t> next_slot(0);
+    if (nonzero_hint) memcpy(w->scan_flags, nonzero_hint, w->n_slots);
+    else
+    {
+        for (int k = 0; k < n_strips; k++)
+        {
+            const int cz0 = k * kStripRows, cz1 = cz0 + kStripRows < w->size_z ? cz0 + kStripRows : w->size_z;
+            remaining[k].store((int)((cz1 - cz0) * slots_per_row));
+        }
+        const int nt = scan_threads(threads);
+        auto work = [&, slots_per_row]()
+        {
+            for (;;)
+            {
+                const size_t a0 = next_slot.fetch_add(4);
+                if (a0 >= w->n_slots) break;
+                const size_t a1 = a0 + 4 < w->n_slots ? a0 + 4 : w->n_slots;
+                for (size_t slot = a0; slot < a1; slot++)
+                {
+                    scan_slot(w, slot, blocks, sunlight, block_light);
+                    remaining[(slot / slots_per_row) / kStripRows].fetch_sub(1, std::memory_order_release);
+                }
+            }
+        };
+        for (int t = 0; t < nt; t++) pool.emplace_back(work);
+    }
+    struct Joiner { std::vector<std::thread>& p; ~Joiner() { for (auto& t : p) if (t.joinable()) t.join(); } } joiner{ pool };
+
+    for (int k = 0; k < n_strips; k++)
+    {
+        const int cz0 = k * kStripRows, cz1 = cz0 + kStripRows < w->size_z ? cz0 + kStripRows : w->size_z;
+        if (!nonzero_hint) while (remaining[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+        const int launched = enqueue_rows(w, cz0, cz1, blocks, sunlight, block_light, mapped, su);
+        if (launched < 0) return fail(GC_ERR_CUDA, "sparse upload", cudaGetErrorString(cudaGetLastError()));
+        w->launches += launched;
+        GC_CUDA(cudaEventRecord(ctx->ev_uploaded[k], su));
+        if (k >= 1) { const int st = mesh_strip(k - 1); if (st != GC_OK) return st; }
+        if (k >= 2) { const int st = read_back(k - 2); if (st != GC_OK) return st; }
+    }
+    { const int st = mesh_strip(n_strips - 1); if (st != GC_OK) return st; }
+    GC_CUDA(cudaEventRecord(b->ev_stop, sm));
+    GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, sm));
+    GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm));
+    GC_CUDA(cudaMemcpyAsync(b->h_counters, b->d_counters, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, sm));
+    if (n_strips >= 2) { const int st = read_back(n_strips - 2); if (st != GC_OK) return st; }
+    { const int st = read_back(n_strips - 1); if (st != GC_OK) return st; }
+    GC_CUDA(cudaEventRecord(ctx->ev_join, sd));
+    GC_CUDA(cudaStreamWaitEvent(sm, ctx->ev_join, 0));
+    GC_CUDA(cudaEventRecord(b->ev_done, sm));
+    GC_CUDA(cudaEventRecord(b->ev_coords, sm));
+    GC_CUDA(cudaEventSynchronize(b->ev_done));
+    b->state = 2;
+    if (b->h_counters[1] != 0) return fail(GC_ERR_CUDA, "mesh kernel watchdog fired (mbarrier wait did not complete)");
+
+    // descriptors back into the caller's order
+    std::vector<GcChunkOut> tmp(b->h_out, b->h_out + n);
+    for (int pos = 0; pos < n; pos++) b->h_out[perm[pos]] = tmp[pos];
     return GC_OK;
 }
 

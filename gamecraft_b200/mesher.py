@@ -71,7 +71,7 @@ EXPORTS = [
     "gcmesh_world_create", "gcmesh_world_destroy", "gcmesh_world_upload_chunk", "gcmesh_world_upload_surface",
     "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_upload_launches", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
     "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
-    "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_wait", "gcmesh_batch_results",
+    "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_mesh_host", "gcmesh_wait", "gcmesh_batch_results",
     "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
     "gcmesh_batch_launches", "gcmesh_kernel_info", "gcmesh_batch_profile",
 ]
@@ -112,6 +112,7 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_batch_destroy.argtypes = [vp]
         L.gcmesh_submit.argtypes = [vp, vp, vp, ci]
         L.gcmesh_wait.argtypes = [vp]
+        L.gcmesh_mesh_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, ctypes.c_uint64, ci]
         L.gcmesh_batch_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_uint64)]
         L.gcmesh_batch_download.argtypes = [vp, vp, vp]
         L.gcmesh_batch_fill_meshdata.argtypes = [vp, ci, vp]
@@ -270,6 +271,16 @@ class Batch:
     def submit(self, world: World, coords) -> "Batch":
         self._coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)
         _check(lib().gcmesh_submit(world.h, self.h, _ptr(self._coords), len(self._coords)), "gcmesh_submit")
+        return self
+
+    def mesh_host(self, world: World, host, coords, vertices, indices, nonzero_hint=None, threads: int = 0) -> "Batch":
+        """Host arrays in, host meshes out (gcmesh_mesh_host): ``vertices`` (q*4,12) u8 and ``indices`` (q*6,) u16 receive the
+        arena prefix; descriptors via :meth:`results`."""
+        self._coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)
+        cap = min(len(vertices) // 4, len(indices) // 6)
+        _check(lib().gcmesh_mesh_host(world.h, self.h, _ptr(host.blocks), _ptr(host.sun), _ptr(host.light), _ptr(host.surface),
+                                      _ptr(nonzero_hint), _ptr(self._coords), len(self._coords), _ptr(vertices), _ptr(indices), cap, threads),
+               "gcmesh_mesh_host")
         return self
 
     def wait(self) -> "Batch":

@@ -161,6 +161,15 @@ int gcmesh_batch_download(GcBatch* batch, void* vertices, void* indices);
 /* After gcmesh_wait: chunk i as the reference's MeshData. */
 int gcmesh_batch_fill_meshdata(GcBatch* batch, int i, GcMeshData* out);
 int gcmesh_batch_device_ptrs(GcBatch* batch, void** vertices, void** indices, void** chunk_out);
+/* Host arrays in, host meshes out, in ONE call: what an integration does where the reference queues
+ * RebuildChunksAsync over a vector<Chunk*> (WorldRender.cpp:80-91).  Equivalent to gcmesh_world_upload_sparse +
+ * gcmesh_submit + gcmesh_wait + gcmesh_batch_download, but pipelined in strips of rows on three streams (host zero-scan,
+ * PCIe pull, meshing and read-back overlap).  On return (synchronous) host_vertices / host_indices hold the arena prefix
+ * (min(total quads, host_capacity_quads) quads) and gcmesh_batch_results gives the descriptors in the caller's order.
+ * Host arrays: brick-major as for gcmesh_world_upload_all; pinned memory lets the GPU pull them itself. */
+int gcmesh_mesh_host(GcWorld* world, GcBatch* batch, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light,
+                     const uint8_t* surface, const uint8_t* nonzero_hint, const GcChunkCoord* coords, int n,
+                     void* host_vertices, void* host_indices, uint64_t host_capacity_quads, int threads);
 /* Milliseconds the last submission's kernels took on the device (CUDA events on the context stream). */
 int gcmesh_batch_elapsed_ms(GcBatch* batch, float* ms);
 /* Number of kernel launches the last submission made. */
