@@ -5,6 +5,8 @@
 #include <cstring>
 #include <new>
 #include <atomic>
+#include <chrono>
+#include <immintrin.h>
 #include <string>
 #include <thread>
 #include <vector>
@@ -225,8 +227,8 @@ int gcmesh_create(int device, void* stream, GcContext** out)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     for (int i = 0; i < 64 && e == cudaSuccess; i++)
     {
-        e = cudaEventCreateWithFlags(&ctx->ev_uploaded[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_meshed[i], cudaEventDisableTiming);
+        e = cudaEventCreate(&ctx->ev_uploaded[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_meshed[i]);
     }
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_strip_cursor, sizeof(unsigned long long) * 64);
     if (e != cudaSuccess) { delete ctx; return fail(GC_ERR_CUDA, "context allocation", cudaGetErrorString(e)); }
@@ -379,8 +381,9 @@ int gcmesh_world_upload_all(GcWorld* w, const uint16_t* blocks, const uint8_t* s
     return gcmesh_world_upload_rows(w, 0, w->size_z, blocks, sunlight, block_light, surface);
 }
 
-// Is a 64-byte-aligned buffer all zero?  (8 x 64-bit ORs per 64 bytes; exits at the first non-zero 4 KB block.)
-static bool all_zero(const void* p, size_t bytes)
+// Is a 64-byte-aligned buffer all zero?  Exits at the first non-zero 4 KB block.  The AVX2 form keeps a software prefetch
+// a few KB ahead of the loads so that one thread has more cache lines in flight than its L1 fill buffers allow.
+static bool all_zero_scalar(const void* p, size_t bytes)
 {
     const uint64_t* q = (const uint64_t*)p;
     const size_t n = bytes / 8;
@@ -391,6 +394,44 @@ static bool all_zero(const void* p, size_t bytes)
         if (acc) return false;
     }
     return true;
+}
+
+static int g_scan_prefetch = 2048;   // bytes ahead (GCMESH_SCAN_PREFETCH)
+
+__attribute__((target("avx2"))) static bool all_zero_avx2(const void* p, size_t bytes)
+{
+    const char* q = (const char*)p;
+    const int ahead = g_scan_prefetch;
+    for (size_t i = 0; i < bytes; i += 4096)
+    {
+        __m256i acc = _mm256_setzero_si256();
+        for (size_t j = 0; j < 4096; j += 256)
+        {
+            const char* r = q + i + j;
+            if (ahead) { _mm_prefetch(r + ahead, _MM_HINT_T0); _mm_prefetch(r + ahead + 64, _MM_HINT_T0); _mm_prefetch(r + ahead + 128, _MM_HINT_T0); _mm_prefetch(r + ahead + 192, _MM_HINT_T0); }
+            const __m256i a = _mm256_or_si256(_mm256_loadu_si256((const __m256i*)r), _mm256_loadu_si256((const __m256i*)(r + 32)));
+            const __m256i b = _mm256_or_si256(_mm256_loadu_si256((const __m256i*)(r + 64)), _mm256_loadu_si256((const __m256i*)(r + 96)));
+            const __m256i c = _mm256_or_si256(_mm256_loadu_si256((const __m256i*)(r + 128)), _mm256_loadu_si256((const __m256i*)(r + 160)));
+            const __m256i d = _mm256_or_si256(_mm256_loadu_si256((const __m256i*)(r + 192)), _mm256_loadu_si256((const __m256i*)(r + 224)));
+            acc = _mm256_or_si256(acc, _mm256_or_si256(_mm256_or_si256(a, b), _mm256_or_si256(c, d)));
+        }
+        if (!_mm256_testz_si256(acc, acc)) return false;
+    }
+    return true;
+}
+
+static bool (*g_all_zero)(const void*, size_t) = nullptr;
+static bool all_zero(const void* p, size_t bytes)
+{
+    if (!g_all_zero)
+    {
+        const char* e = getenv("GCMESH_SCAN_PREFETCH");
+        if (e) g_scan_prefetch = atoi(e);
+        const char* v = getenv("GCMESH_SCAN");
+        const bool scalar = (v && atoi(v) == 0) || !__builtin_cpu_supports("avx2");
+        g_all_zero = scalar ? all_zero_scalar : all_zero_avx2;
+    }
+    return g_all_zero(p, bytes);
 }
 
 // Zero / non-zero classification of the host brick arrays of one slot into w->scan_flags.
@@ -661,9 +702,11 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     GC_CUDA(cudaSetDevice(ctx->device));
     if (b->state == 1) GC_CUDA(cudaEventSynchronize(b->ev_done));
 
-    constexpr int kStripRows = 4;
+    // short strips keep the tail (the last strip's upload -> mesh -> read-back, which nothing overlaps) small
+    static const int strip_rows_env = getenv("GCMESH_STRIP_ROWS") ? atoi(getenv("GCMESH_STRIP_ROWS")) : 0;
+    int kStripRows = strip_rows_env > 0 ? strip_rows_env : 2;
+    while ((w->size_z + kStripRows - 1) / kStripRows > 64) kStripRows++;
     const int n_strips = (w->size_z + kStripRows - 1) / kStripRows;
-    if (n_strips > 64) return fail(GC_ERR_ARG, "window deeper than 256 rows: call gcmesh_world_upload_sparse + gcmesh_submit instead");
 
     // chunks bucketed by strip (stable), `perm` maps the sorted position back to the caller's order
     std::vector<int> first(n_strips + 1, 0), perm((size_t)n);
@@ -725,8 +768,10 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
             const int cz0 = k * kStripRows, cz1 = cz0 + kStripRows < w->size_z ? cz0 + kStripRows : w->size_z;
             remaining[k].store((int)((cz1 - cz0) * slots_per_row));
         }
-        const int nt = scan_threads(threads);
-        auto work = [&, slots_per_row]()
+        // one core stays with this thread, which feeds the three streams as strips become ready
+        int nt = scan_threads(threads);
+        if (threads <= 0 && nt > 1) nt--;
+        auto work = [&, slots_per_row, kStripRows]()
         {
             for (;;)
             {
@@ -744,14 +789,20 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     }
     struct Joiner { std::vector<std::thread>& p; ~Joiner() { for (auto& t : p) if (t.joinable()) t.join(); } } joiner{ pool };
 
+    const bool trace = getenv("GCMESH_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_scanned[64], t_enqueued[64];
     for (int k = 0; k < n_strips; k++)
     {
         const int cz0 = k * kStripRows, cz1 = cz0 + kStripRows < w->size_z ? cz0 + kStripRows : w->size_z;
         if (!nonzero_hint) while (remaining[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+        t_scanned[k] = now_ms();
         const int launched = enqueue_rows(w, cz0, cz1, blocks, sunlight, block_light, mapped, su);
         if (launched < 0) return fail(GC_ERR_CUDA, "sparse upload", cudaGetErrorString(cudaGetLastError()));
         w->launches += launched;
         GC_CUDA(cudaEventRecord(ctx->ev_uploaded[k], su));
+        t_enqueued[k] = now_ms();
         if (k >= 1) { const int st = mesh_strip(k - 1); if (st != GC_OK) return st; }
         if (k >= 2) { const int st = read_back(k - 2); if (st != GC_OK) return st; }
     }
@@ -768,6 +819,18 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     GC_CUDA(cudaEventRecord(b->ev_coords, sm));
     GC_CUDA(cudaEventSynchronize(b->ev_done));
     b->state = 2;
+    if (trace)
+    {
+        fprintf(stderr, "[gcmesh_mesh_host] total %.2f ms host\n", now_ms());
+        for (int k = 0; k < n_strips; k++)
+        {
+            float up = 0, me = 0;
+            cudaEventElapsedTime(&up, b->ev_start, ctx->ev_uploaded[k]); cudaEventElapsedTime(&me, b->ev_start, ctx->ev_meshed[k]);
+            fprintf(stderr, "  strip %2d: scanned %.2f  enqueued %.2f | uploaded %.2f  meshed %.2f (device, since start)\n", k, t_scanned[k], t_enqueued[k], up, me);
+        }
+        float dn = 0; cudaEventElapsedTime(&dn, b->ev_start, b->ev_stop);
+        fprintf(stderr, "  last kernel done %.2f\n", dn);
+    }
     if (b->h_counters[1] != 0) return fail(GC_ERR_CUDA, "mesh kernel watchdog fired (mbarrier wait did not complete)");
 
     // descriptors back into the caller's order

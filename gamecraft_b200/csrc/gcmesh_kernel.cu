@@ -14,6 +14,7 @@
 // The per-lane work is in mesh_core.cuh (shared with the host emulator used by the CPU tests).
 //
 // Reference path replaced: BuildChunkAsync / BuildBlock / VertexLight, Code/WorldRender.cpp:6-27,329-383,445-560.
+#include <cstdlib>
 #include "gcmesh_kernel.cuh"
 
 namespace gc
@@ -763,8 +764,12 @@ cudaError_t launch_upload_items(const uint32_t* items, int n_items, const uint16
                                 uint16_t* d_blocks, uint8_t* d_sun, uint8_t* d_light, cudaStream_t stream)
 {
     if (n_items <= 0) return cudaSuccess;
+    // PCIe needs ~100 KB in flight (50 GB/s x 2 us); 16 KB per CTA, so a few dozen CTAs saturate the link and the other
+    // SMs stay free for a mesh kernel running on another stream (its CTA needs a whole SM's registers)
+    static const int ctas_env = getenv("GCMESH_PULL_CTAS") ? atoi(getenv("GCMESH_PULL_CTAS")) : 0;
+    const int cap = ctas_env > 0 ? ctas_env : 32;
     long long pieces = (long long)n_items * 8;
-    int grid = pieces < 148 * 16 ? (int)pieces : 148 * 16;
+    int grid = pieces < cap ? (int)pieces : cap;
     gc_upload_kernel<<<grid, 256, 0, stream>>>(items, n_items, h_blocks, h_sun, h_light, d_blocks, d_sun, d_light);
     return cudaGetLastError();
 }

@@ -27,3 +27,28 @@ print("upload_sparse (hint)           %.2f ms" % t(lambda: world.upload_sparse(P
 print("upload dense                   %.2f ms" % t(lambda: world.upload(P)))
 print("submit+wait                    %.2f ms" % t(lambda: batch.submit(world, coords).wait()))
 print("download                       %.2f ms" % t(lambda: batch.download(hv, hi)))
+coords_np = np.asarray(coords, dtype=np.int32)
+def mh(hint_, threads=0):
+    batch.mesh_host(world, P, coords, hv, hi, nonzero_hint=hint_, threads=threads)
+print("mesh_host (scan)               %.2f ms" % t(lambda: mh(None)))
+for th in (4, 8, 16, 32):
+    print("  mesh_host scan threads %2d: %.2f ms" % (th, t(lambda: mh(None, th))))
+print("mesh_host (hint)               %.2f ms" % t(lambda: mh(hint)))
+# raw PCIe rates
+a = torch.empty(256 << 20, dtype=torch.uint8).pin_memory(); d = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+def cp(dst, src):
+    dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+for name, f in (("H2D", lambda: cp(d, a)), ("D2H", lambda: cp(a, d))):
+    f(); t0 = time.perf_counter(); f(); f(); f(); dt = (time.perf_counter() - t0) / 3
+    print("%s 256 MiB: %.2f ms = %.1f GB/s" % (name, dt * 1e3, (256 << 20) / dt / 1e9))
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+a2 = torch.empty(256 << 20, dtype=torch.uint8).pin_memory(); d2 = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+def both():
+    with torch.cuda.stream(s1): d.copy_(a, non_blocking=True)
+    with torch.cuda.stream(s2): a2.copy_(d2, non_blocking=True)
+    torch.cuda.synchronize()
+both(); t0 = time.perf_counter(); both(); both(); both(); dt = (time.perf_counter() - t0) / 3
+print("H2D+D2H concurrent 256 MiB each: %.2f ms = %.1f GB/s per direction" % (dt * 1e3, (256 << 20) / dt / 1e9))
+# host zero scan alone: numpy view of how fast 16 threads can read the arrays
+import ctypes, threading
+print("host cores", os.cpu_count())
