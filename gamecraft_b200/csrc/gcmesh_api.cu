@@ -80,6 +80,7 @@ struct GcContext
     cudaStream_t stream;
     bool own_stream;
     int num_sms;
+    int mesh_ctas;            // persistent mesh CTAs that fit the device at once (SMs x resident CTAs per SM)
     EncodeTiledFn encode;
     DeviceTables* d_tables;
     int use_tma;
@@ -205,6 +206,12 @@ int gcmesh_create(int device, void* stream, GcContext** out)
     if (!ctx) return fail(GC_ERR_ARG, "out of host memory");
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    {
+        const int per_sm = mesh_ctas_per_sm();
+        if (per_sm < 1) { delete ctx; return fail(GC_ERR_CUDA, "the mesh kernel does not fit this device", cudaGetErrorString(cudaGetLastError())); }
+        static const int cap_env = getenv("GCMESH_CTAS_PER_SM") ? atoi(getenv("GCMESH_CTAS_PER_SM")) : 0;
+        ctx->mesh_ctas = ctx->num_sms * (cap_env > 0 && cap_env < per_sm ? cap_env : per_sm);
+    }
     ctx->own_stream = stream == nullptr;
     ctx->stream = (cudaStream_t)stream;
     const char* env = getenv("GCMESH_NO_TMA");
@@ -647,7 +654,7 @@ static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cu
     p.vertex_arena = b->d_vertices; p.index_arena = b->d_indices; p.max_quads = b->max_quads;
     p.quad_cursor = b->d_cursor; p.work_counter = b->d_counters; p.tables = ctx->d_tables;
     p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma; p.prof = b->d_prof;
-    const int grid = count < ctx->num_sms ? count : ctx->num_sms;
+    const int grid = count < ctx->mesh_ctas ? count : ctx->mesh_ctas;
     e = launch_mesh(p, w->maps, grid, s);
     if (e == cudaSuccess) b->launches++;
     return e;

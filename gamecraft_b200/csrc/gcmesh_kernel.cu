@@ -1,17 +1,21 @@
 // gcmesh — the chunk-mesh kernel for sm_100a (B200).
 //
-// One persistent CTA per SM; each CTA pulls chunks from a work counter and, per chunk:
-//   P0  neighbour columns' surface window -> shared memory
-//   P1  34 z-slabs (32x64 voxels + 2 halo rows, three arrays) are staged by TMA tensor-map box loads
-//       (cp.async.bulk.tensor.4d, 6-stage mbarrier ring, issued by one elected lane) and converted by
-//       role-specialised warps into the resident on-chip form (class bit planes + packed light tile)
-//   P1x the x = -1 / x = 32 halo cells that some face or light footprint will actually read (rows next to an
-//       emitting boundary voxel) are gathered from the neighbour columns; air chunks gather nothing
+// Two persistent CTAs per SM (320 threads, ~112 KB shared memory each); each CTA pulls chunks from a work counter and,
+// per chunk:
+//   P0  the next chunk's position and the surface rows of its three columns (one warp, a chunk ahead)
+//   P1  the 34 z-slabs of BLOCK IDS (32x64 voxels, 4 KB, contiguous in the brick) are staged by TMA tensor-map box
+//       loads (cp.async.bulk.tensor.4d) into team-owned two-slot mbarrier rings and converted, one voxel row per
+//       lane, into the resident on-chip form: eight class bit planes over the chunk + 1-voxel halo
+//   P1x the x = -1 / x = 32 halo classes that some face or corner test will actually read are gathered from the
+//       neighbour columns; air chunks gather nothing and stop here — their light arrays are never touched
 //   P2  face masks per row (bitwise, 32 voxels per op), per-row counts, per-layer warp reductions, scan,
 //       ONE atomicAdd reserves the chunk's contiguous segment in the batch arenas
-//   P3  per batch of layers: (a) rows -> ordered quad list + index words, (b) one thread per quad ->
-//       3x3 light neighbourhood from shared memory -> 4 vertices -> three 16-byte stores
-// The per-lane work is in mesh_core.cuh (shared with the host emulator used by the CPU tests).
+//   P3  per batch of layers: (a) rows -> ordered quad list + per-type ranks, (b) one thread per quad -> its 3x3
+//       light cells gathered straight from the sunlight / blockLight arrays (only cells in front of drawn faces are
+//       ever read, as in the reference's VertexLight) -> 4 vertices -> three 16-byte stores + its index words
+// While one CTA of an SM computes (P2 / P3), the other streams (P1): the SM's issue slots and its share of HBM
+// bandwidth are used at the same time.  The per-lane work is in mesh_core.cuh (shared with the host emulator used by
+// the CPU tests).
 //
 // Reference path replaced: BuildChunkAsync / BuildBlock / VertexLight, Code/WorldRender.cpp:6-27,329-383,445-560.
 #include <cstdlib>
@@ -21,41 +25,39 @@ namespace gc
 {
 namespace
 {
-constexpr int NT = kMeshThreads;          // 20 warps
+constexpr int NT = kMeshThreads;          // 10 warps
 constexpr int kWarps = NT / 32;
 constexpr int kSlabs = kRowsZ;            // 34 z-slabs per chunk: tz = -1 .. 32
-// P1: kTeams teams of 4 warps (2 class + 2 light, one lane per voxel row).  Team t converts slabs t, t+4, ... and
-// stages them itself through its own two-slot ring: after a slab is converted the team syncs on a named barrier and
-// one of its lanes issues the TMA loads of the slab after next into the slot just freed.  (A separate producer warp
-// cost ~700 cycles per slab — try_wait ~140, arrive.expect_tx + UTMALDG ~360, measured — and paced the whole phase.)
-constexpr int kTeams = 4, kTeamWarps = 4, kTeamStages = 2;
+// P1: kTeams teams of 2 warps (rows 0..31 / 32..63 of a slab, one lane per voxel row).  Team t converts slabs t, t+4, ...
+// and stages them itself through its own two-slot ring: as soon as both warps hold a slab in registers they sync on a
+// named barrier and one lane issues the TMA load of the slab after next into the slot just freed.  (A separate
+// producer warp cost ~700 cycles per slab — try_wait ~140, arrive.expect_tx + UTMALDG ~360, measured — and paced
+// the whole phase; a ring shared by independent producers breaks mbarrier parity waits.)
+constexpr int kTeams = 4, kTeamWarps = 2, kTeamStages = 2;
 constexpr int kStages = kTeams * kTeamStages;              // 8
-constexpr int kSlabWarps = kTeams * kTeamWarps;            // warps 0 .. 15
-constexpr int kHaloWarp = kSlabWarps;                      // warp 16: the y-halo rows (ty = -1, 64), straight from global memory
-constexpr int kFetchWarp = kHaloWarp + 1;                  // warp 17: prefetches the next chunk's id, position and surface rows
+constexpr int kSlabWarps = kTeams * kTeamWarps;            // warps 0 .. 7
+constexpr int kHaloWarp = kSlabWarps;                      // warp 8: the y-halo rows (ty = -1, 64), straight from global memory
+constexpr int kFetchWarp = kHaloWarp + 1;                  // warp 9: prefetches the next chunk's id, position and surface rows
 static_assert(kFetchWarp < kWarps, "warp roles");
 constexpr int kYHaloTasks = 2 * kRowsZ;                    // 2 faces x 34 rows
 constexpr int kHaloTasks = kHaloRows * 2;
 constexpr int kHaloPerThread = (kHaloTasks + NT - 1) / NT;
 
-// ---- one staging slot: a z-slab of the three arrays (TMA destinations 128-byte aligned) ----
-constexpr int kStBlocks = 0;                       // [64][32] u16
-constexpr int kStSun = 4096;                       // [64][32] u8
-constexpr int kStLight = 6144;
-constexpr int kStageBytes = 8192;
-// P3 reuses the staging ring: quad list (u32 per quad) followed by the per-type ranks (u16 per quad)
-constexpr int kOffTList = kMaxQuads * 4;
-static_assert(kMaxQuads * 6 <= kStages * kStageBytes, "a whole chunk's quad list must fit the staging ring");
+constexpr int kStageBytes = 4096;                          // one z-slab of block ids: [64][32] u16
 
 // ---- shared-memory carve-up (dynamic, 1024-aligned base) ----
+// The staging ring is dead once P1 ends; P1x .. P3 reuse it for the x-halo classes and the quad list of a batch.
 constexpr int kOffStages = 0;
-constexpr int kOffPlanes = kOffStages + kStages * kStageBytes;            // 65536
-constexpr int kOffLt = kOffPlanes + kPlanes * kHaloRows * 4;              // centre bytes, then the x-halo bytes
-constexpr int kOffHx = kOffLt + ((kLtBytes + kLtxBytes + 15) & ~15);
-constexpr int kOffBv = kOffHx + ((kHaloRows * 2 + 15) & ~15);             // u32[2][132]: per layer, which rows' x = 0 / x = 31 voxel emits
-constexpr int kSurfBytes = kRowsZ * 32 + 2 * ((kRowsZ * 4 + 15) & ~15);   // [34][32] centre-x surface rows + [34][4] per-octet maxima + minima
-constexpr int kSurfMinOff = (kRowsZ * 4 + 15) & ~15;
-constexpr int kOffSurf = kOffBv + ((2 * kBvWords * 4 + 15) & ~15);                          // two buffers: this chunk's and the prefetched next one's
+constexpr int kOffHx = 0;                                                  // u16[2244]
+constexpr int kOffList = (kHaloRows * 2 + 127) & ~127;                     // u32[kListCap] quad entries, then u16[kListCap] per-type ranks
+constexpr int kListCap = ((kStages * kStageBytes - kOffList) / 6) & ~15;   // quads per P3 batch
+constexpr int kOffTList = kOffList + kListCap * 4;
+constexpr int kMaxLayerQuads = 4 * kTX * kTZ + 2 * (kTX + kTZ);            // a layer's faces: <= 2 per cell up/down + 1 per in-layer neighbour pair
+static_assert(kListCap >= kMaxLayerQuads, "one layer must fit a batch");
+constexpr int kOffPlanes = kOffStages + kStages * kStageBytes;            // 32768
+constexpr int kOffBv = kOffPlanes + kPlanes * kHaloRows * 4;              // u32[2][132]: per layer, which rows' x = 0 / x = 31 voxel emits
+constexpr int kSurfBytes = (kSurfRowBytes + 2 * kRowsZ + 15) & ~15;       // [34][32] centre-x surface rows + [2][34] x-halo surface bytes
+constexpr int kOffSurf = kOffBv + ((2 * kBvWords * 4 + 15) & ~15);        // two buffers: this chunk's and the prefetched next one's
 constexpr int kOffLut = kOffSurf + 2 * kSurfBytes;
 constexpr int kOffMat = kOffLut + 256 * 8;
 constexpr int kOffCls = kOffMat + 256 * 8;
@@ -65,16 +67,16 @@ constexpr int kOffLayerTypB = kOffLayerTypA + 256;                        // u32
 constexpr int kOffLayerBase = kOffLayerTypB + 256;                        // u32[65]
 constexpr int kOffLayerTypBaseA = kOffLayerBase + 272;
 constexpr int kOffLayerTypBaseB = kOffLayerTypBaseA + 256;
-constexpr int kOffFaces = kOffLayerTypBaseB + 256;                        // FaceDesc[6], 16 B each
-constexpr int kOffBars = kOffFaces + 96;                                  // full[8]
+constexpr int kOffFaces = kOffLayerTypBaseB + 256;                        // FacePlan[6], 32 B each
+constexpr int kOffBars = kOffFaces + 192;                                 // full[8]
 constexpr int kOffCtx = kOffBars + kStages * 8;
 constexpr int kOffNext = kOffCtx + 64;                                    // NextChunk[2]
 constexpr int kSmemBytes = kOffNext + 32;
-static_assert(kOffPlanes % 128 == 0 && kOffLt % 16 == 0 && kOffHx % 16 == 0 && kOffBv % 16 == 0 && kOffSurf % 16 == 0, "align");
-static_assert(kOffLut % 8 == 0 && kOffMat % 8 == 0 && kOffBars % 8 == 0 && kOffLayerCnt % 4 == 0 && kOffCtx % 4 == 0, "align");
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kOffPlanes % 128 == 0 && kOffBv % 16 == 0 && kOffSurf % 16 == 0 && kOffList % 16 == 0 && kOffTList % 2 == 0, "align");
+static_assert(kOffLut % 8 == 0 && kOffMat % 8 == 0 && kOffBars % 8 == 0 && kOffLayerCnt % 4 == 0 && kOffCtx % 4 == 0 && kOffFaces % 16 == 0, "align");
+static_assert(2 * (kSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM");
 
-static_assert(sizeof(FacePlan) == 16, "FacePlan");
+static_assert(sizeof(FacePlan) == 32, "FacePlan");
 
 struct NextChunk { int32_t chunk, cx, cy, cz; };   // chunk = index into coords, or -1 when the work is exhausted
 
@@ -148,17 +150,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
 }
-// TMA bulk copy (no tensor map): `bytes` contiguous bytes global -> shared, completion on an mbarrier
-__device__ __forceinline__ void tma_load_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int threads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -183,6 +174,25 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
+// bar.sync that also takes a value computed from freshly loaded registers: the loads have completed before the
+// barrier is reached (the compiler cannot sink them below it)
+// (The barrier id is an immediate: a register id makes ptxas reserve all 16 hardware barriers, i.e. one CTA per SM.)
+template <int kId>
+__device__ __forceinline__ void named_bar_sync_imm(uint32_t dep)
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(kId), "n"(kTeamWarps * 32), "r"(dep) : "memory");
+}
+__device__ __forceinline__ void team_bar_sync_after(int team, uint32_t dep)
+{
+    switch (team)
+    {
+    case 0: named_bar_sync_imm<1>(dep); break;
+    case 1: named_bar_sync_imm<2>(dep); break;
+    case 2: named_bar_sync_imm<3>(dep); break;
+    default: named_bar_sync_imm<4>(dep); break;
+    }
+}
+
 // In-kernel cycle attribution is compiled in only for the profiling instantiation (GCMESH_PROFILE=1).
 #define GC_PROF_MARK(slot)                                                            \
     do {                                                                              \
@@ -191,18 +201,16 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
 
 // =====================================================================================================
 template <bool kProf>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     uint8_t* s_stage = smem + kOffStages;
-    uint32_t* s_list = reinterpret_cast<uint32_t*>(smem + kOffStages);
-    uint16_t* s_tlist = reinterpret_cast<uint16_t*>(smem + kOffStages + kOffTList);
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(smem + kOffList);
+    uint16_t* s_tlist = reinterpret_cast<uint16_t*>(smem + kOffTList);
     uint32_t* s_planes = reinterpret_cast<uint32_t*>(smem + kOffPlanes);
-    uint8_t* s_planes_b = smem + kOffPlanes;
-    uint8_t* s_lt = smem + kOffLt;
     uint16_t* s_hx = reinterpret_cast<uint16_t*>(smem + kOffHx);
     uint8_t* s_hx_b = smem + kOffHx;
     uint32_t* s_bvm = reinterpret_cast<uint32_t*>(smem + kOffBv);
@@ -236,12 +244,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     {
         for (int i = 0; i < kStages; i++) mbar_init(smem_u32(&s_bars[i]), 1);   // full: the issuing lane's expect_tx arrive
         fence_barrier_init();
-        if (p.use_tma)
-        {
-            prefetch_tensormap(&maps.blocks_slab);
-            prefetch_tensormap(&maps.sun_slab);
-            prefetch_tensormap(&maps.light_slab);
-        }
+        if (p.use_tma) prefetch_tensormap(&maps.blocks_slab);
     }
     const int kill_cls = p.tables->cls8[p.tables->kill_zone & 255];
     const int air_cls = p.tables->cls8[0];
@@ -250,9 +253,9 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     uint32_t team_seq = 0;  // slabs this warp's team has staged so far (ring slot / parity source)
     long long prof_t = clock64();
 
-    // Claim the next chunk and stage what P1 needs before any voxel arrives: its position and the centre-x surface
-    // rows of the three columns (cz-1, cz, cz+1) with their per-octet maxima.  Run by one warp into buffer `b`,
-    // one chunk ahead of the rest of the CTA.
+    // Claim the next chunk and stage its position and the surface rows of the three columns (cz-1, cz, cz+1) at cx,
+    // plus the x = -1 / x = 32 surface bytes of the same rows.  Run by one warp into buffer `b`, a chunk ahead of the
+    // rest of the CTA.
     auto fetch_chunk = [&](int b)
     {
         int c = 0, fx = 0, fy = 0, fz = 0;
@@ -272,14 +275,14 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             const int tz = r - 1;
             const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
             const size_t col = (size_t)(fz + dcz) * p.size_x + fx;
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p.surface + col * 1024 + (tz & 31) * 32) + q);
-            reinterpret_cast<uint2*>(surf)[i] = v;
-            const uint32_t m = max4(v.x, v.y);
-            const uint32_t m2 = max4(m, m >> 16);
-            surf[kRowsZ * 32 + i] = (uint8_t)max4(m2, m2 >> 8);
-            const uint32_t n = max4(~v.x, ~v.y);              // per-byte min = ~max(~a, ~b)
-            const uint32_t n2 = max4(n, n >> 16);
-            surf[kRowsZ * 32 + kSurfMinOff + i] = (uint8_t)~max4(n2, n2 >> 8);
+            reinterpret_cast<uint2*>(surf)[i] = __ldg(reinterpret_cast<const uint2*>(p.surface + col * 1024 + (tz & 31) * 32) + q);
+        }
+        for (int i = lane; i < 2 * kRowsZ; i += 32)
+        {
+            const int side = i / kRowsZ, tz = i % kRowsZ - 1;
+            const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
+            const size_t col = (size_t)(fz + dcz) * p.size_x + (fx + (side ? 1 : -1));
+            surf[kSurfRowBytes + i] = __ldg(p.surface + col * 1024 + (tz & 31) * 32 + (side ? 0 : 31));
         }
     };
 
@@ -297,25 +300,21 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         const int cx = s_next[buf].cx, cy = s_next[buf].cy, cz = s_next[buf].cz;
         const int lwy = cy * kTY;
         const uint8_t* s_surf = smem + kOffSurf + buf * kSurfBytes;
-        const uint8_t* s_surfmax = s_surf + kRowsZ * 32;
 
         GC_PROF_MARK(0);
-        // ================= P1: stage + convert =================
+        // ================= P1: stage + convert the block ids =================
         const bool has_lo = lwy > 0, has_hi = lwy + kTY < GC_WORLD_BLOCK_HEIGHT;
-        const long long p1_t0 = kProf ? clock64() : 0;
         const int col0 = cz * p.size_x + cx;
         if (warp < kSlabWarps)
         {
             // ---- slab teams: one lane per voxel row (ty = 0..63); the team stages its own slabs ----
-            // team = warp % 4 puts each team on its own scheduler partition (SMSP = warp % 4): two class + two light warps each
+            // team = warp % 4 puts each team on its own scheduler partition (SMSP = warp % 4)
             const int team = warp % kTeams, wt = warp / kTeams;
-            const bool is_class = wt < 2;
-            const int ty = (wt & 1) * 32 + lane;
-            const int wy = lwy + ty;
-            const int rot4 = (lane >> 1) & 3, rot2 = (lane >> 2) & 1;   // shared-memory read rotations (bank-conflict free)
+            const int ty = wt * 32 + lane;
+            const int rot4 = (lane >> 1) & 3;   // shared-memory read rotation (bank-conflict free)
             const uint32_t unrot = rot_selector(rot4);
-            const int boff0 = kStBlocks + ty * 64 + ((0 + rot4) & 3) * 16, boff1 = kStBlocks + ty * 64 + ((1 + rot4) & 3) * 16;
-            const int boff2 = kStBlocks + ty * 64 + ((2 + rot4) & 3) * 16, boff3 = kStBlocks + ty * 64 + ((3 + rot4) & 3) * 16;
+            const int boff0 = ty * 64 + ((0 + rot4) & 3) * 16, boff1 = ty * 64 + ((1 + rot4) & 3) * 16;
+            const int boff2 = ty * 64 + ((2 + rot4) & 3) * 16, boff3 = ty * 64 + ((3 + rot4) & 3) * 16;
             const int n_mine = (kSlabs - team + kTeams - 1) / kTeams;  // slabs team, team + 4, ...
 
             // stage slab number k of this team (s = team + 4k) into the team's ring slot for sequence number `seq`
@@ -325,16 +324,11 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 const int stage = team * kTeamStages + (int)(seq % kTeamStages);
                 const int tz = s - 1;
                 const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
-                const int zz = tz & 31;
                 const int slot = (col0 + dcz * p.size_x) * 4 + cy;
                 const uint32_t full = smem_u32(&s_bars[stage]);
-                const uint32_t d = smem_u32(s_stage + stage * kStageBytes);
-                fence_proxy_async();   // the slot was read (and, as the quad list, written) by the generic proxy
-                mbar_expect_tx(full, 8192u);
-                tma_load_4d(d + kStBlocks, &maps.blocks_slab, 0, 0, zz, slot, full);
-                tma_load_4d(d + kStSun, &maps.sun_slab, 0, 0, zz, slot, full);
-                tma_load_4d(d + kStLight, &maps.light_slab, 0, 0, zz, slot, full);
-                if (kProf && blockIdx.x == 0) p.prof[64 + s] = (unsigned long long)(clock64() - p1_t0);
+                fence_proxy_async();   // the slot was read (and, as hx / the quad list, written) by the generic proxy
+                mbar_expect_tx(full, (uint32_t)kStageBytes);
+                tma_load_4d(smem_u32(s_stage + stage * kStageBytes), &maps.blocks_slab, 0, 0, tz & 31, slot, full);
             };
             auto stage_plain = [&](int k, uint32_t seq)   // debug staging path (GCMESH_NO_TMA=1): the whole warp copies
             {
@@ -345,12 +339,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 const int slot = (col0 + dcz * p.size_x) * 4 + cy;
                 const size_t vox = (size_t)slot * GC_CHUNK_SIZE_3 + (size_t)(tz & 31) * 2048;
                 uint8_t* st = s_stage + stage * kStageBytes;
-                for (int i = lane; i < 256; i += 32) reinterpret_cast<uint4*>(st + kStBlocks)[i] = reinterpret_cast<const uint4*>(p.blocks + vox)[i];
-                for (int i = lane; i < 128; i += 32)
-                {
-                    reinterpret_cast<uint4*>(st + kStSun)[i] = reinterpret_cast<const uint4*>(p.sun + vox)[i];
-                    reinterpret_cast<uint4*>(st + kStLight)[i] = reinterpret_cast<const uint4*>(p.light + vox)[i];
-                }
+                for (int i = lane; i < 256; i += 32) reinterpret_cast<uint4*>(st)[i] = reinterpret_cast<const uint4*>(p.blocks + vox)[i];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&s_bars[stage]));
             };
@@ -369,73 +358,42 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 const int s = team + k * kTeams;
                 const uint32_t seq = team_seq + k;
                 const int stage = team * kTeamStages + (int)(seq % kTeamStages);
-                {
-                    const long long w0 = kProf ? clock64() : 0;
-                    mbar_wait(smem_u32(&s_bars[stage]), (seq / kTeamStages) & 1, p.error_flag);
-                    if (kProf && lane == 0 && warp == 0) atomicAdd(p.prof + 9, (unsigned long long)(clock64() - w0));
-                    if (kProf && lane == 0 && warp == 2) atomicAdd(p.prof + 10, (unsigned long long)(clock64() - w0));
-                    if (kProf && lane == 0 && warp == 0 && k == 0) atomicAdd(p.prof + 11, (unsigned long long)(clock64() - p1_t0));
-                    if (kProf && lane == 0 && wt == 0 && blockIdx.x == 0) p.prof[128 + s] = (unsigned long long)(clock64() - p1_t0);
-                }
-                const long long c0 = kProf ? clock64() : 0;
+                mbar_wait(smem_u32(&s_bars[stage]), (seq / kTeamStages) & 1, p.error_flag);
                 const uint8_t* st = s_stage + stage * kStageBytes;
-                const int hr = hrow(ty, s - 1);
-                if (is_class)
+                Ids8 q[4];
                 {
-                    Ids8 q[4];
-                    {
-                        const uint4 v0 = *reinterpret_cast<const uint4*>(st + boff0), v1 = *reinterpret_cast<const uint4*>(st + boff1);
-                        const uint4 v2 = *reinterpret_cast<const uint4*>(st + boff2), v3 = *reinterpret_cast<const uint4*>(st + boff3);
-                        q[0] = Ids8{ v0.x, v0.y, v0.z, v0.w }; q[1] = Ids8{ v1.x, v1.y, v1.z, v1.w };
-                        q[2] = Ids8{ v2.x, v2.y, v2.z, v2.w }; q[3] = Ids8{ v3.x, v3.y, v3.z, v3.w };
-                    }
-                    uint32_t out[8];
-                    p1_class_row(q, s_lut, out);
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                    {
-                        out[j] = rotl_bytes(out[j], unrot);
-                        s_planes[j * kHaloRows + hr] = out[j];
-                    }
-                    const uint32_t vis = (s >= 1 && s <= kTZ) ? row_emit_mask(out) : 0u;
-                    if (vis) s_ctx->any_emit = 1;
-                    if (vis & 0x80000001u)
-                    {
-                        s_ctx->any_bv = 1;
-                        if (vis & 1u) atomicOr(&s_bvm[(ty + 1) * 2 + (s >> 5)], 1u << (s & 31));
-                        if (vis >> 31) atomicOr(&s_bvm[kBvWords + (ty + 1) * 2 + (s >> 5)], 1u << (s & 31));
-                    }
+                    const uint4 v0 = *reinterpret_cast<const uint4*>(st + boff0), v1 = *reinterpret_cast<const uint4*>(st + boff1);
+                    const uint4 v2 = *reinterpret_cast<const uint4*>(st + boff2), v3 = *reinterpret_cast<const uint4*>(st + boff3);
+                    q[0] = Ids8{ v0.x, v0.y, v0.z, v0.w }; q[1] = Ids8{ v1.x, v1.y, v1.z, v1.w };
+                    q[2] = Ids8{ v2.x, v2.y, v2.z, v2.w }; q[3] = Ids8{ v3.x, v3.y, v3.z, v3.w };
                 }
-                else
-                {
-                    const uint32_t smax = *reinterpret_cast<const uint32_t*>(s_surfmax + s * 4);
-                    const uint32_t smin = *reinterpret_cast<const uint32_t*>(s_surfmax + kSurfMinOff + s * 4);
-#pragma unroll
-                    for (int j = 0; j < 2; j++)
-                    {
-                        const int h = j ^ rot2;
-                        const uint4 sn = *reinterpret_cast<const uint4*>(st + kStSun + ty * 32 + h * 16);
-                        const uint4 bl = *reinterpret_cast<const uint4*>(st + kStLight + ty * 32 + h * 16);
-                        const uint4 sf = *reinterpret_cast<const uint4*>(s_surf + s * 32 + h * 16);
-                        const Words4 o = p1_light_half(Words4{ sn.x, sn.y, sn.z, sn.w }, Words4{ bl.x, bl.y, bl.z, bl.w },
-                                                       Words4{ sf.x, sf.y, sf.z, sf.w }, wy,
-                                                       light_mode(wy, (smax >> (16 * h)) & 255u, (smin >> (16 * h)) & 255u),
-                                                       light_mode(wy, (smax >> (16 * h + 8)) & 255u, (smin >> (16 * h + 8)) & 255u));
-                        *reinterpret_cast<uint4*>(s_lt + hr * kLtStride + h * 16) = make_uint4(o.x, o.y, o.z, o.w);
-                    }
-                }
-                if (kProf && lane == 0 && warp == 0) { atomicAdd(p.prof + 12, (unsigned long long)(clock64() - c0)); atomicAdd(p.prof + 13, 1ull); }
-                if (kProf && lane == 0 && warp == 2) atomicAdd(p.prof + 14, (unsigned long long)(clock64() - c0));
-                if (kProf && lane == 0 && wt == 0 && blockIdx.x == 0) p.prof[192 + s] = (unsigned long long)(clock64() - p1_t0);
-                // refill: once all four warps are done with the slot, one of them stages the slab after next into it
+                const bool uniform = row_uniform(q);   // reads all sixteen words: the row is in registers from here on
+                // refill: both warps hold their rows, so the slot is free — one lane stages the slab after next into it
                 if (k + kTeamStages < n_mine)
                 {
-                    named_bar_sync(1 + team, kTeamWarps * 32);
-                    if (wt == (k & 3))
+                    team_bar_sync_after(team, (uint32_t)uniform);
+                    if (wt == (k & 1))
                     {
                         if (p.use_tma) { if (lane == 0) issue(k + kTeamStages, seq + kTeamStages); }
                         else stage_plain(k + kTeamStages, seq + kTeamStages);
                     }
+                }
+                const int hr = hrow(ty, s - 1);
+                uint32_t out[8];
+                p1_class_row(q, uniform, s_lut, out);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    out[j] = rotl_bytes(out[j], unrot);
+                    s_planes[j * kHaloRows + hr] = out[j];
+                }
+                const uint32_t vis = (s >= 1 && s <= kTZ) ? row_emit_mask(out) : 0u;
+                if (vis) s_ctx->any_emit = 1;
+                if (vis & 0x80000001u)
+                {
+                    s_ctx->any_bv = 1;
+                    if (vis & 1u) atomicOr(&s_bvm[(ty + 1) * 2 + (s >> 5)], 1u << (s & 31));
+                    if (vis >> 31) atomicOr(&s_bvm[kBvWords + (ty + 1) * 2 + (s >> 5)], 1u << (s & 31));
                 }
             }
             team_seq += n_mine;
@@ -447,24 +405,15 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             {
                 const int face = t / kRowsZ, tz = t % kRowsZ - 1;
                 const int ty = face ? kTY : -1;
-                const int wy = lwy + ty;
                 const int hr = hrow(ty, tz);
                 uint32_t out[8];
-                uint4 l0, l1;
-                if (!(face ? has_hi : has_lo))
-                {
-                    p1_class_row_const(face ? air_cls : kill_cls, out);
-                    const uint32_t c = face ? ~0u : 0u;
-                    l0 = make_uint4(c, c, c, c); l1 = l0;
-                }
+                if (!(face ? has_hi : has_lo)) p1_class_row_const(face ? air_cls : kill_cls, out);
                 else
                 {
                     const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
                     const int slot = (col0 + dcz * p.size_x) * 4 + cy + (face ? 1 : -1);
                     const size_t vox = (size_t)slot * GC_CHUNK_SIZE_3 + 32 * ((face ? 0 : 63) + 64 * (tz & 31));
                     const uint4* gb = reinterpret_cast<const uint4*>(p.blocks + vox);
-                    const uint4* gs = reinterpret_cast<const uint4*>(p.sun + vox);
-                    const uint4* gl = reinterpret_cast<const uint4*>(p.light + vox);
                     Ids8 q[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++)
@@ -472,30 +421,21 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                         const uint4 v = __ldg(gb + j);
                         q[j].x = v.x; q[j].y = v.y; q[j].z = v.z; q[j].w = v.w;
                     }
-                    const uint4 sn0 = __ldg(gs), sn1 = __ldg(gs + 1), bl0 = __ldg(gl), bl1 = __ldg(gl + 1);
-                    p1_class_row(q, s_lut, out);
-                    const uint4 sf0 = *reinterpret_cast<const uint4*>(s_surf + (tz + 1) * 32), sf1 = *reinterpret_cast<const uint4*>(s_surf + (tz + 1) * 32 + 16);
-                    const Words4 a = p1_light_half(Words4{ sn0.x, sn0.y, sn0.z, sn0.w }, Words4{ bl0.x, bl0.y, bl0.z, bl0.w },
-                                                   Words4{ sf0.x, sf0.y, sf0.z, sf0.w }, wy, 0, 0);
-                    const Words4 b2 = p1_light_half(Words4{ sn1.x, sn1.y, sn1.z, sn1.w }, Words4{ bl1.x, bl1.y, bl1.z, bl1.w },
-                                                    Words4{ sf1.x, sf1.y, sf1.z, sf1.w }, wy, 0, 0);
-                    l0 = make_uint4(a.x, a.y, a.z, a.w); l1 = make_uint4(b2.x, b2.y, b2.z, b2.w);
+                    p1_class_row(q, row_uniform(q), s_lut, out);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; j++) s_planes[j * kHaloRows + hr] = out[j];
-                *reinterpret_cast<uint4*>(s_lt + hr * kLtStride) = l0;
-                *reinterpret_cast<uint4*>(s_lt + hr * kLtStride + 16) = l1;
             }
         }
         else if (warp == kFetchWarp) fetch_chunk(buf ^ 1);
         __syncthreads();
         GC_PROF_MARK(1);
 
-        // ================= P1x: the x-halo cells that will be read =================
+        // ================= P1x: the x-halo classes that will be read (the staging ring is free from here on) =================
         const bool any_emit = s_ctx->any_emit != 0, any_bv = s_ctx->any_bv != 0;
         if (any_emit)
         {
-            uint32_t id[kHaloPerThread], sn[kHaloPerThread], bl[kHaloPerThread], sf[kHaloPerThread];
+            uint32_t id[kHaloPerThread];
             uint32_t need = 0;
 #pragma unroll
             for (int k = 0; k < kHaloPerThread; k++)
@@ -513,11 +453,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                         const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
                         const int zz = tz & 31, xx = side ? 0 : 31;
                         const size_t col = (size_t)(cz + dcz) * p.size_x + (cx + (side ? 1 : -1));
-                        const size_t vox = (col * 4 + (wy >> 6)) * GC_CHUNK_SIZE_3 + xx + 32 * ((wy & 63) + 64 * zz);
-                        id[k] = __ldg(p.blocks + vox);
-                        sn[k] = __ldg(p.sun + vox);
-                        bl[k] = __ldg(p.light + vox);
-                        sf[k] = __ldg(p.surface + col * 1024 + zz * 32 + xx);
+                        id[k] = __ldg(p.blocks + (col * 4 + (wy >> 6)) * GC_CHUNK_SIZE_3 + xx + 32 * ((wy & 63) + 64 * zz));
                     }
                 }
             }
@@ -531,9 +467,9 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                     const int tz = rem / kRowsY - 1, ty = rem % kRowsY - 1;
                     const int hr = hrow(ty, tz);
                     const int wy = lwy + ty;
-                    if (wy < 0) p1_xhalo_cell(kill_cls, 0x00u, s_hx_b, s_lt, hr, side);
-                    else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_xhalo_cell(air_cls, 0xFFu, s_hx_b, s_lt, hr, side);
-                    else if ((need >> k) & 1u) p1_xhalo_cell(s_cls[id[k] & 255u], light_byte_of(sn[k], bl[k], sf[k], wy), s_hx_b, s_lt, hr, side);
+                    if (wy < 0) p1_xhalo_cell(kill_cls, s_hx_b, hr, side);
+                    else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_xhalo_cell(air_cls, s_hx_b, hr, side);
+                    else if ((need >> k) & 1u) p1_xhalo_cell(s_cls[id[k] & 255u], s_hx_b, hr, side);
                 }
             }
         }
@@ -545,7 +481,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         // ================= P2: face masks, counts, scan, reservation =================
         if (!any_emit)
         {
-            // nothing in the chunk can emit (all AIR / invisible): empty result, no scan, no emission
+            // nothing in the chunk can emit (all AIR / invisible): empty result, no scan, no emission, no light read
             if (tid == 0)
             {
                 GcChunkOut o;
@@ -634,70 +570,87 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         __syncthreads();
 
         GC_PROF_MARK(3);
-        // ================= P3: emission =================
+        // ================= P3: emission, in batches of whole layers that fit the quad list =================
         if (s_ctx->emit)
         {
-            const uint32_t quad_base = s_ctx->quad_base, total = s_ctx->total;
+            const uint32_t quad_base = s_ctx->quad_base;
             uint32_t* idx_words = reinterpret_cast<uint32_t*>(p.index_arena) + (size_t)quad_base * 3;
             uint4* vtx = reinterpret_cast<uint4*>(p.vertex_arena) + (size_t)quad_base * 3;
-            const uint16_t* chunk_blocks = p.blocks + ((size_t)(cz * p.size_x + cx) * 4 + cy) * GC_CHUNK_SIZE_3;
+            LightGather lg;
+            lg.sun = p.sun; lg.light = p.light; lg.surf = s_surf; lg.surf_x = s_surf + kSurfRowBytes;
+            lg.own = ((long long)col0 * 4 + cy) * GC_CHUNK_SIZE_3;
+            lg.size_x = p.size_x; lg.cx = cx; lg.cy = cy; lg.cz = cz;
+            const uint16_t* chunk_blocks = p.blocks + lg.own;
 
-            // ---- 3a: rows -> ordered quad list + per-type ranks (the whole chunk fits the staging ring) ----
-            for (int layer = warp; layer < kTY; layer += kWarps)
+            for (int l0 = 0; l0 < kTY;)
             {
-                if (s_layer_base[layer + 1] == s_layer_base[layer]) continue;   // warp-uniform
-                RowFaces rf;
-                p2_row_faces(s_planes, s_hx, layer, lane, rf);
-                int ci; uint32_t t4;
-                p2_row_counts(rf, ci, t4);
-                const uint32_t c = (uint32_t)ci;
-                const uint32_t ta = (t4 & 255u) | (((t4 >> 8) & 255u) << 16);
-                const uint32_t tb = ((t4 >> 16) & 255u) | ((t4 >> 24) << 16);
-                const uint32_t ce = warp_incl_scan(c, lane) - c;
-                const uint32_t ae = warp_incl_scan(ta, lane) - ta + s_layer_typbase_a[layer];
-                const uint32_t be = warp_incl_scan(tb, lane) - tb + s_layer_typbase_b[layer];
-                if (c)
+                const uint32_t first = s_layer_base[l0];
+                int l1 = l0 + 1;
+                while (l1 < kTY && s_layer_base[l1 + 1] - first <= (uint32_t)kListCap) l1++;
+                const uint32_t count = s_layer_base[l1] - first;
+                if (count)
                 {
-                    uint32_t trank[kMeshTypes];
-                    const uint32_t rank0 = s_layer_base[layer] + ce;
-                    trank[1] = ae & 0xFFFFu; trank[2] = ae >> 16; trank[3] = be & 0xFFFFu; trank[4] = be >> 16;
-                    trank[0] = rank0 - trank[1] - trank[2] - trank[3] - trank[4];
-                    p3a_row(rf, layer, lane, rank0, trank, s_list, s_tlist);
+                    // ---- 3a: rows -> ordered quad list + per-type ranks ----
+                    for (int layer = l0 + warp; layer < l1; layer += kWarps)
+                    {
+                        if (s_layer_base[layer + 1] == s_layer_base[layer]) continue;   // warp-uniform
+                        RowFaces rf;
+                        p2_row_faces(s_planes, s_hx, layer, lane, rf);
+                        int ci; uint32_t t4;
+                        p2_row_counts(rf, ci, t4);
+                        const uint32_t c = (uint32_t)ci;
+                        const uint32_t ta = (t4 & 255u) | (((t4 >> 8) & 255u) << 16);
+                        const uint32_t tb = ((t4 >> 16) & 255u) | ((t4 >> 24) << 16);
+                        const uint32_t ce = warp_incl_scan(c, lane) - c;
+                        const uint32_t ae = warp_incl_scan(ta, lane) - ta + s_layer_typbase_a[layer];
+                        const uint32_t be = warp_incl_scan(tb, lane) - tb + s_layer_typbase_b[layer];
+                        if (c)
+                        {
+                            uint32_t trank[kMeshTypes];
+                            const uint32_t rank0 = s_layer_base[layer] + ce;
+                            trank[1] = ae & 0xFFFFu; trank[2] = ae >> 16; trank[3] = be & 0xFFFFu; trank[4] = be >> 16;
+                            trank[0] = rank0 - trank[1] - trank[2] - trank[3] - trank[4];
+                            p3a_row(rf, layer, lane, rank0 - first, trank, s_list, s_tlist);
+                        }
+                    }
+                    __syncthreads();
+                    GC_PROF_MARK(4);
+                    // ---- 3b: one thread per quad: its index words and its four vertices ----
+                    uint32_t id_next = 0;
+                    if ((uint32_t)tid < count)
+                    {
+                        const uint32_t e = s_list[tid];
+                        id_next = __ldg(chunk_blocks + ((e >> 3) & 31) + 32 * (((e >> 13) & 63) + 64 * ((e >> 8) & 31)));
+                    }
+                    for (uint32_t i = tid; i < count; i += NT)
+                    {
+                        const uint32_t e = s_list[i];
+                        const uint32_t id = id_next & 255u;
+                        if (i + NT < count)
+                        {
+                            const uint32_t en = s_list[i + NT];   // block id of this thread's next quad: its latency hides behind this one
+                            id_next = __ldg(chunk_blocks + ((en >> 3) & 31) + 32 * (((en >> 13) & 63) + 64 * ((en >> 8) & 31)));
+                        }
+                        const uint32_t rank = first + i;
+                        uint32_t iw[3];
+                        quad_index_words(rank, iw);
+                        uint32_t* ip = idx_words + (size_t)(s_ctx->type_off[(e >> 19) & 7] + s_tlist[i]) * 3;
+                        ip[0] = iw[0]; ip[1] = iw[1]; ip[2] = iw[2];
+                        uint32_t v[12];
+                        p3b_quad(e, s_faces[e & 7], lg, s_planes + P_OPAQUE * kHaloRows, s_hx, s_mat[id], v);
+                        uint4* dst = vtx + (size_t)rank * 3;
+                        dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                        dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                        dst[2] = make_uint4(v[8], v[9], v[10], v[11]);
+                    }
+                    if (l1 < kTY) __syncthreads();   // the list is rewritten by the next batch
+                    GC_PROF_MARK(5);
                 }
-            }
-            __syncthreads();
-            GC_PROF_MARK(4);
-            // ---- 3b: one thread per quad: its index words and its four vertices ----
-            uint32_t id_next = 0;
-            if ((uint32_t)tid < total)
-            {
-                const uint32_t e = s_list[tid];
-                id_next = __ldg(chunk_blocks + ((e >> 3) & 31) + 32 * (((e >> 13) & 63) + 64 * ((e >> 8) & 31)));
-            }
-            for (uint32_t i = tid; i < total; i += NT)
-            {
-                const uint32_t e = s_list[i];
-                const uint32_t id = id_next & 255u;
-                if (i + NT < total)
-                {
-                    const uint32_t en = s_list[i + NT];   // block id of this thread's next quad: its latency hides behind this one
-                    id_next = __ldg(chunk_blocks + ((en >> 3) & 31) + 32 * (((en >> 13) & 63) + 64 * ((en >> 8) & 31)));
-                }
-                uint32_t iw[3];
-                quad_index_words(i, iw);
-                uint32_t* ip = idx_words + (size_t)(s_ctx->type_off[(e >> 19) & 7] + s_tlist[i]) * 3;
-                ip[0] = iw[0]; ip[1] = iw[1]; ip[2] = iw[2];
-                uint32_t v[12];
-                p3b_quad(e, s_faces[e & 7], s_lt, s_planes + P_OPAQUE * kHaloRows, s_hx, s_mat[id], v);
-                uint4* dst = vtx + (size_t)i * 3;
-                dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
-                dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
-                dst[2] = make_uint4(v[8], v[9], v[10], v[11]);
+                l0 = l1;
             }
         }
-        // the staging ring was used as the quad list by the generic proxy: order it before the next TMA writes
+        // hx and the quad list were written into the staging ring by the generic proxy: order that before the next TMA writes
         fence_proxy_async();
-        GC_PROF_MARK(5);
     }
 }
 
@@ -776,16 +729,31 @@ cudaError_t launch_upload_items(const uint32_t* items, int n_items, const uint16
 
 size_t mesh_smem_bytes() { return (size_t)kSmemBytes; }
 
-cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int grid, cudaStream_t stream)
+static cudaError_t configure_mesh_kernel()
 {
     static bool configured = false;
-    if (!configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(gc_mesh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gc_mesh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (configured) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(gc_mesh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gc_mesh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    // the whole unified L1 / shared array as shared memory: two ~112 KB CTAs per SM
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gc_mesh_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gc_mesh_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) configured = true;
+    return e;
+}
+
+int mesh_ctas_per_sm()
+{
+    if (configure_mesh_kernel() != cudaSuccess) return 0;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gc_mesh_kernel<false>, NT, kSmemBytes) != cudaSuccess) return 0;
+    return n;
+}
+
+cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int grid, cudaStream_t stream)
+{
+    cudaError_t e0 = configure_mesh_kernel();
+    if (e0 != cudaSuccess) return e0;
     if (p.prof) gc_mesh_kernel<true><<<grid, NT, kSmemBytes, stream>>>(p, maps);
     else gc_mesh_kernel<false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
     return cudaGetLastError();

@@ -47,10 +47,11 @@ struct MeshTensorMaps
     CUtensorMap blocks_slab, sun_slab, light_slab;
 };
 
-constexpr int kMeshThreads = 640;
+constexpr int kMeshThreads = 320;   // two CTAs per SM
 size_t mesh_smem_bytes();
 cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int grid, cudaStream_t stream);
 cudaError_t mesh_kernel_attributes(int* regs, int* static_smem, int* max_dyn_smem);
+int mesh_ctas_per_sm();   // resident mesh CTAs per SM (occupancy query), 0 on error
 
 // Sparse upload: copy the listed brick arrays from (pinned, device-mapped) host memory into their device slots.
 // item = slot * 4 + array (0 blocks, 1 sunlight, 2 blockLight); host pointers are the brick-major arrays.

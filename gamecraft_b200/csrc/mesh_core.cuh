@@ -13,9 +13,10 @@
 //                     4    = opaque (Block.cpp:65-68)
 //                     5..7 = mesh type bits (Mesh.h:8-16); 7 (all ones) = never emits (AIR / invisible)
 //   hx[hr]         uint16: low byte = the 8 class bits of cell x = -1, high byte = of cell x = 32
-//   lt[hr*32+x]    uint8, x in 0..31: (sun << 4) | blockLight with GetSunlight's rules applied (Lighting.cpp:69-79);
-//                  0x00 below the world, 0xFF above it (GetFinalLight, WorldRender.cpp:316-319)
-//   lt[kLtBytes + hr*2 + side]  the same byte for the x = -1 (side 0) / x = 32 (side 1) halo cells
+// Light is NOT staged: only cells in front of a drawn face are ever read (VertexLight, WorldRender.cpp:329-383), so
+// each quad gathers its 3x3 light cells straight from the sunlight / blockLight arrays (LightGather below), as
+//   (sun' << 4) | blockLight with GetSunlight's rules applied (Lighting.cpp:69-79);
+//   0x00 below the world, 0xFF above it (GetFinalLight, WorldRender.cpp:316-319)
 #pragma once
 
 #include <stdint.h>
@@ -32,9 +33,6 @@ constexpr int kTX = 32, kTY = 64, kTZ = 32;
 constexpr int kRowsY = kTY + 2, kRowsZ = kTZ + 2;
 constexpr int kHaloRows = kRowsY * kRowsZ;   // 2244
 constexpr int kCenterRows = kTY * kTZ;       // 2048
-constexpr int kLtStride = 32;
-constexpr int kLtBytes = kHaloRows * kLtStride;  // centre-x bytes; the x-halo bytes follow
-constexpr int kLtxBytes = kHaloRows * 2;
 constexpr int kPlanes = 8;
 constexpr int kMaxQuads = 10000;             // MAX_VERTICES / 4, Mesh.h:5
 constexpr int kMeshTypes = 5;
@@ -164,10 +162,12 @@ GC_HD void p1_class_octet(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, co
 // and undo it with rotl_bytes(out[j], r).
 struct Ids8 { uint32_t x, y, z, w; };
 GC_HD bool octet_uniform(const Ids8& q) { return (q.x == q.y) && (q.z == q.w) && (q.x == q.z) && ((q.x >> 16) == (q.x & 0xFFFFu)); }
-GC_HD void p1_class_row(const Ids8 q[4], const LutEntry* lut, uint32_t out[8])
+// every octet of the row holds a single block id (evaluated without short-circuit: reads all sixteen words)
+GC_HD bool row_uniform(const Ids8 q[4]) { return octet_uniform(q[0]) & octet_uniform(q[1]) & octet_uniform(q[2]) & octet_uniform(q[3]); }
+GC_HD void p1_class_row(const Ids8 q[4], bool uniform, const LutEntry* lut, uint32_t out[8])
 {
     uint32_t lo[4], hi[4];
-    if (octet_uniform(q[0]) && octet_uniform(q[1]) && octet_uniform(q[2]) && octet_uniform(q[3]))
+    if (uniform)
     {
         // four single-block octets (air, deep stone, water ...): four independent table lookups, no branches between them
         const LutEntry e0 = lut[q[0].x & 255u], e1 = lut[q[1].x & 255u], e2 = lut[q[2].x & 255u], e3 = lut[q[3].x & 255u];
@@ -190,63 +190,10 @@ GC_HD void p1_class_row_const(uint32_t cls, uint32_t out[8])
 // emitting voxels of a row (mesh type != 7) from its type planes
 GC_HD uint32_t row_emit_mask(const uint32_t out[8]) { return ~(out[P_M0] & out[P_M1] & out[P_M2]); }
 
-// Four voxels of light: sun/bl/surf hold 4 bytes each (x ascending from the low byte); wy = world y of the row.
-//   sun' = wy >= surface ? 15 : max(sun, 1)      GetSunlight, Lighting.cpp:69-79 (MAX_LIGHT / MIN_LIGHT, Lighting.h:5-6)
-//   out  = sun' << 4 | blockLight
-// Plain 32-bit ops only (byte lanes never carry into each other):
-//   max(s,1), s <= 15:  nz = ((s + 15) >> 4) & 1;  s | (nz ^ 1)
-//   wy >= surf, 8 bit:  7-bit compare by borrow-free subtraction ((wy7 | 0x80) - surf7 keeps bit 7 iff wy7 >= surf7),
-//                       then the top bits: ge = top(wy) ? (ge7 | ~top(surf)) : (ge7 & ~top(surf))
-GC_HD uint32_t p1_light4(uint32_t sun, uint32_t bl, uint32_t surf, int wy)
-{
-    const uint32_t a7 = ((uint32_t)(wy & 0x7F) * 0x01010101u) | 0x80808080u;
-    const uint32_t hi = (wy & 0x80) ? 0xFFFFFFFFu : 0u;
-    const uint32_t t = a7 - (surf & 0x7F7F7F7Fu);
-    const uint32_t ge = (t & ~surf) | (hi & (t | ~surf));
-    const uint32_t above15 = ((ge >> 7) & 0x01010101u) * 15u;
-    uint32_t s = sun & 0x0F0F0F0Fu;
-    const uint32_t nz = ((s + 0x0F0F0F0Fu) >> 4) & 0x01010101u;
-    s |= (nz ^ 0x01010101u) | above15;
-    return (s << 4) | (bl & 0x0F0F0F0Fu);
-}
-
-// Same for cells known to lie at or above their column's surface (sun reads 15 whatever is stored) ...
-GC_HD uint32_t p1_light4_above(uint32_t bl) { return 0xF0F0F0F0u | (bl & 0x0F0F0F0Fu); }
-// ... and for cells known to lie below it (stored sunlight, 0 reads as MIN_LIGHT)
-GC_HD uint32_t p1_light4_below(uint32_t sun, uint32_t bl)
-{
-    uint32_t s = sun & 0x0F0F0F0Fu;
-    const uint32_t nz = ((s + 0x0F0F0F0Fu) >> 4) & 0x01010101u;
-    s |= nz ^ 0x01010101u;
-    return (s << 4) | (bl & 0x0F0F0F0Fu);
-}
-
-// Half a row (16 voxels = 4 words).  mode_lo / mode_hi classify the first / second octet against the surface rows
-// under it: 1 = wholly at or above (wy >= max surface of the octet), 2 = wholly below (wy < min), 0 = mixed.
-struct Words4 { uint32_t x, y, z, w; };
-GC_HD int light_mode(int wy, uint32_t smax, uint32_t smin) { return wy >= (int)smax ? 1 : (wy < (int)smin ? 2 : 0); }
-GC_HD void p1_light_octet(uint32_t s0, uint32_t s1, uint32_t b0, uint32_t b1, uint32_t f0, uint32_t f1, int wy, int mode, uint32_t& o0, uint32_t& o1)
-{
-    if (mode == 1) { o0 = p1_light4_above(b0); o1 = p1_light4_above(b1); }
-    else if (mode == 2) { o0 = p1_light4_below(s0, b0); o1 = p1_light4_below(s1, b1); }
-    else { o0 = p1_light4(s0, b0, f0, wy); o1 = p1_light4(s1, b1, f1, wy); }
-}
-GC_HD Words4 p1_light_half(const Words4& sun, const Words4& bl, const Words4& surf, int wy, int mode_lo, int mode_hi)
-{
-    Words4 o;
-    p1_light_octet(sun.x, sun.y, bl.x, bl.y, surf.x, surf.y, wy, mode_lo, o.x, o.y);
-    p1_light_octet(sun.z, sun.w, bl.z, bl.w, surf.z, surf.w, wy, mode_hi, o.z, o.w);
-    return o;
-}
-
 // One cell of the x = -1 / x = 32 halo columns.  side 0: x = -1, side 1: x = 32.
-GC_HD void p1_xhalo_cell(uint32_t cls, uint32_t light_byte, uint8_t* hx_b, uint8_t* lt, int hr, int side)
-{
-    hx_b[hr * 2 + side] = (uint8_t)cls;
-    lt[kLtBytes + hr * 2 + side] = (uint8_t)light_byte;
-}
+GC_HD void p1_xhalo_cell(uint32_t cls, uint8_t* hx_b, int hr, int side) { hx_b[hr * 2 + side] = (uint8_t)cls; }
 
-// Is halo cell (side, ty, tz) ever read?  Only by faces / light footprints of an emitting voxel at x = 0 (side 0) or
+// Is halo cell (side, ty, tz) ever read?  Only by faces / corner-opacity tests of an emitting voxel at x = 0 (side 0) or
 // x = 31 (side 1) in one of the 3x3 rows around it.  bvm[(ty + 1) * 2 + w]: bit (tz + 1) of the 64-bit mask of layer ty
 // says "the boundary voxel of row (ty, tz) emits" (set for centre rows only).
 constexpr int kBvWords = kRowsY * 2;   // per side
@@ -433,24 +380,57 @@ GC_HD uint32_t corner_color(uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool
     return s * 5u + (((s * 2u * 171u) >> 9) & 0x001F001Fu);
 }
 
-// light byte of cell (x, row hr), x in -1..32
-GC_HD uint32_t light_at(const uint8_t* lt, int hr, int x)
+// ---- light of one cell, gathered from the world arrays ----
+// What a quad needs to find the light of any cell of its chunk's halo tile (x in -1..32, ty in -1..64, tz in -1..32).
+//   surf      [34][32] surface rows of the three columns (cz-1 | cz | cz+1) at the chunk's own cx, row index tz + 1
+//   surf_x    [2][34]  the same for the cells x = -1 (side 0, column cx-1) and x = 32 (side 1, column cx+1)
+struct LightGather
 {
-    const int off = ((unsigned)x < 32u) ? hr * kLtStride + x : kLtBytes + hr * 2 + (x > 0 ? 1 : 0);
-    return lt[off];
+    const uint8_t* sun;       // sunlight arena (slot-major bricks)
+    const uint8_t* light;     // blockLight arena
+    const uint8_t* surf;
+    const uint8_t* surf_x;
+    long long own;            // voxel offset of the chunk's own brick in the arenas
+    int size_x, cx, cy, cz;   // window width (columns) and the chunk's position
+};
+constexpr int kSurfRowBytes = kRowsZ * 32;
+
+GC_HD uint32_t load_u8(const uint8_t* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
 }
 
-// A face's geometry pre-digested for p3b_quad (one 16-byte record per face, built once from FaceDesc):
-//   w0  row offset of the cell in front (ny*34 + nz) as int16 | nx as int8 << 16
-//   w1  row stride of in-plane axis u (uy*34 + uz) | ux << 16        w2  the same for axis v
+// any cell of the halo tile (slow path: picks the neighbour brick / column)
+GC_HD uint32_t gather_cell(const LightGather& g, int x, int ty, int tz)
+{
+    const int wy = g.cy * kTY + ty;
+    if (wy < 0) return 0x00u;
+    if (wy >= 4 * kTY) return 0xFFu;
+    const int dcx = x < 0 ? -1 : (x > 31 ? 1 : 0), dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
+    const long long slot = ((long long)(g.cz + dcz) * g.size_x + (g.cx + dcx)) * 4 + (wy >> 6);
+    const long long vox = slot * (kTX * kTY * kTZ) + (x & 31) + 32 * ((wy & 63) + 64 * (tz & 31));
+    const uint32_t sf = dcx ? g.surf_x[(dcx > 0 ? kRowsZ : 0) + tz + 1] : g.surf[(tz + 1) * 32 + x];
+    return light_byte_of(load_u8(g.sun + vox), load_u8(g.light + vox), sf, wy);
+}
+
+// A face's geometry pre-digested for p3b_quad (built once per face from FaceDesc):
+//   w0  row offset of the cell in front (ny*34 + nz) as int16 | nx as int8 << 16 | ny as int8 << 24
+//   w1  row stride of in-plane axis u (uy*34 + uz) | ux << 16 | uy << 24           w2  the same for axis v
 //   w3  corner bits of the four vertices (3 bits each: +x, +y, +z) | per-vertex sign along u << 12 | along v << 16
-struct FacePlan { uint32_t w0, w1, w2, w3; };
+//   w4  voxel-offset stride of u (ux + 32*uy + 2048*uz) as int16 | of v << 16
+//   w5  surface-row stride of u (ux + 32*uz) as int16 | of v << 16
+//   w6  footprint extent per axis: bit 0 x, bit 1 y, bit 2 z (1 = some in-plane axis runs along it)
+struct FacePlan { uint32_t w0, w1, w2, w3, w4, w5, w6, w7; };
 GC_HD FacePlan make_face_plan(const FaceDesc& f)
 {
     FacePlan p;
-    p.w0 = (uint32_t)(uint16_t)(int16_t)(f.ny * kRowsZ + f.nz) | ((uint32_t)(uint8_t)f.nx << 16);
-    p.w1 = (uint32_t)(uint16_t)(int16_t)(f.uy * kRowsZ + f.uz) | ((uint32_t)(uint8_t)f.ux << 16);
-    p.w2 = (uint32_t)(uint16_t)(int16_t)(f.vy * kRowsZ + f.vz) | ((uint32_t)(uint8_t)f.vx << 16);
+    p.w0 = (uint32_t)(uint16_t)(int16_t)(f.ny * kRowsZ + f.nz) | ((uint32_t)(uint8_t)f.nx << 16) | ((uint32_t)(uint8_t)f.ny << 24);
+    p.w1 = (uint32_t)(uint16_t)(int16_t)(f.uy * kRowsZ + f.uz) | ((uint32_t)(uint8_t)f.ux << 16) | ((uint32_t)(uint8_t)f.uy << 24);
+    p.w2 = (uint32_t)(uint16_t)(int16_t)(f.vy * kRowsZ + f.vz) | ((uint32_t)(uint8_t)f.vx << 16) | ((uint32_t)(uint8_t)f.vy << 24);
     uint32_t corners = 0, su = 0, sv = 0;
     for (int k = 0; k < 4; k++)
     {
@@ -461,39 +441,68 @@ GC_HD FacePlan make_face_plan(const FaceDesc& f)
         sv |= (f.vx ? cxb : (f.vy ? cyb : czb)) << k;
     }
     p.w3 = corners | (su << 12) | (sv << 16);
+    p.w4 = (uint32_t)(uint16_t)(int16_t)(f.ux + 32 * f.uy + 2048 * f.uz) | ((uint32_t)(uint16_t)(int16_t)(f.vx + 32 * f.vy + 2048 * f.vz) << 16);
+    p.w5 = (uint32_t)(uint16_t)(int16_t)(f.ux + 32 * f.uz) | ((uint32_t)(uint16_t)(int16_t)(f.vx + 32 * f.vz) << 16);
+    p.w6 = (uint32_t)((f.ux | f.vx) ? 1 : 0) | ((uint32_t)((f.uy | f.vy) ? 1 : 0) << 1) | ((uint32_t)((f.uz | f.vz) ? 1 : 0) << 2);
+    p.w7 = 0;
     return p;
 }
 
 // out: 12 words = 4 vertices x 12 bytes {pos u8x3, uv u8x3, color u8x4 (L,L,L,S), alpha, 0}  (VertexInfo, Mesh.h:37-44)
-GC_HD void p3b_quad(uint32_t entry, const FacePlan& f, const uint8_t* lt, const uint32_t* plane_o, const uint16_t* hx,
+GC_HD void p3b_quad(uint32_t entry, const FacePlan& f, const LightGather& g, const uint32_t* plane_o, const uint16_t* hx,
                     MatEntry mat, uint32_t out[12])
 {
     const int d = entry & 7, x = (entry >> 3) & 31, tz = (entry >> 8) & 31, ty = (entry >> 13) & 63;
     const int ux = (int8_t)(f.w1 >> 16), vx = (int8_t)(f.w2 >> 16);
+    const int uy = (int8_t)(f.w1 >> 24), vy = (int8_t)(f.w2 >> 24);
     const int hr_u = (int16_t)(f.w1 & 0xFFFFu), hr_v = (int16_t)(f.w2 & 0xFFFFu);   // row strides of the in-plane axes
-    const int ax = x + (int8_t)(f.w0 >> 16);
-    const int hr_a = hrow(ty, tz) + (int16_t)(f.w0 & 0xFFFFu);
+    const int hr_n = (int16_t)(f.w0 & 0xFFFFu);
+    const int ny = (int8_t)(f.w0 >> 24);
+    const int ax = x + (int8_t)(f.w0 >> 16), ay = ty + ny, az = tz + (hr_n - ny * kRowsZ);
+    const int hr_a = hrow(ty, tz) + hr_n;
 
     // 3x3 light neighbourhood in the layer in front of the face: cell (i, j) = a + i*u + j*v, i, j in -1..1,
     // and the opacity of the four edge cells (only b and c are ever tested, WorldRender.cpp:361-362)
     uint32_t l00, lm0, lp0, l0m, l0p, lmm, lmp, lpm, lpp, o_um, o_up, o_vm, o_vp;
+    const int ex = f.w6 & 1u, ey = (f.w6 >> 1) & 1u, ez = (f.w6 >> 2) & 1u;
+    if ((unsigned)(ax - ex) <= (unsigned)(31 - 2 * ex) && (unsigned)(ay - ey) <= (unsigned)(63 - 2 * ey) && (unsigned)(az - ez) <= (unsigned)(31 - 2 * ez))
+    {
+        // the whole footprint lies inside the chunk's own brick: constant strides from the centre cell
+        const long long base = g.own + (ax + 32 * (ay + 64 * az));
+        const uint8_t* ps = g.sun + base;
+        const uint8_t* pl = g.light + base;
+        const uint8_t* sf = g.surf + (az + 1) * 32 + ax;
+        const int du = (int16_t)(f.w4 & 0xFFFFu), dv = (int16_t)(f.w4 >> 16);
+        const int fu = (int16_t)(f.w5 & 0xFFFFu), fv = (int16_t)(f.w5 >> 16);
+        const int wy = g.cy * kTY + ay;
+        // issue the eighteen loads before any of them is consumed
+        const uint32_t s00 = load_u8(ps), sm0 = load_u8(ps - du), sp0 = load_u8(ps + du), s0m = load_u8(ps - dv), s0p = load_u8(ps + dv);
+        const uint32_t smm = load_u8(ps - du - dv), smp = load_u8(ps - du + dv), spm = load_u8(ps + du - dv), spp = load_u8(ps + du + dv);
+        const uint32_t b00 = load_u8(pl), bm0 = load_u8(pl - du), bp0 = load_u8(pl + du), b0m = load_u8(pl - dv), b0p = load_u8(pl + dv);
+        const uint32_t bmm = load_u8(pl - du - dv), bmp = load_u8(pl - du + dv), bpm = load_u8(pl + du - dv), bpp = load_u8(pl + du + dv);
+        l00 = light_byte_of(s00, b00, sf[0], wy);
+        lm0 = light_byte_of(sm0, bm0, sf[-fu], wy - uy); lp0 = light_byte_of(sp0, bp0, sf[fu], wy + uy);
+        l0m = light_byte_of(s0m, b0m, sf[-fv], wy - vy); l0p = light_byte_of(s0p, b0p, sf[fv], wy + vy);
+        lmm = light_byte_of(smm, bmm, sf[-fu - fv], wy - uy - vy); lmp = light_byte_of(smp, bmp, sf[-fu + fv], wy - uy + vy);
+        lpm = light_byte_of(spm, bpm, sf[fu - fv], wy + uy - vy); lpp = light_byte_of(spp, bpp, sf[fu + fv], wy + uy + vy);
+    }
+    else
+    {
+        const int uz = hr_u - uy * kRowsZ, vz = hr_v - vy * kRowsZ;
+        l00 = gather_cell(g, ax, ay, az);
+        lm0 = gather_cell(g, ax - ux, ay - uy, az - uz); lp0 = gather_cell(g, ax + ux, ay + uy, az + uz);
+        l0m = gather_cell(g, ax - vx, ay - vy, az - vz); l0p = gather_cell(g, ax + vx, ay + vy, az + vz);
+        lmm = gather_cell(g, ax - ux - vx, ay - uy - vy, az - uz - vz); lmp = gather_cell(g, ax - ux + vx, ay - uy + vy, az - uz + vz);
+        lpm = gather_cell(g, ax + ux - vx, ay + uy - vy, az + uz - vz); lpp = gather_cell(g, ax + ux + vx, ay + uy + vy, az + uz + vz);
+    }
     if ((unsigned)(ax - 1) < 30u)
     {
-        // the whole footprint has x in 0..31: plain indexing
-        const uint8_t* a = lt + hr_a * kLtStride + ax;
-        const int su = hr_u * kLtStride + ux, sv = hr_v * kLtStride + vx;
-        l00 = a[0]; lm0 = a[-su]; lp0 = a[su]; l0m = a[-sv]; l0p = a[sv];
-        lmm = a[-su - sv]; lmp = a[-su + sv]; lpm = a[su - sv]; lpp = a[su + sv];
+        // x in 1..30: no edge cell touches the x halo
         o_um = (plane_o[hr_a - hr_u] >> (ax - ux)) & 1u; o_up = (plane_o[hr_a + hr_u] >> (ax + ux)) & 1u;
         o_vm = (plane_o[hr_a - hr_v] >> (ax - vx)) & 1u; o_vp = (plane_o[hr_a + hr_v] >> (ax + vx)) & 1u;
     }
     else
     {
-        l00 = light_at(lt, hr_a, ax);
-        lm0 = light_at(lt, hr_a - hr_u, ax - ux); lp0 = light_at(lt, hr_a + hr_u, ax + ux);
-        l0m = light_at(lt, hr_a - hr_v, ax - vx); l0p = light_at(lt, hr_a + hr_v, ax + vx);
-        lmm = light_at(lt, hr_a - hr_u - hr_v, ax - ux - vx); lmp = light_at(lt, hr_a - hr_u + hr_v, ax - ux + vx);
-        lpm = light_at(lt, hr_a + hr_u - hr_v, ax + ux - vx); lpp = light_at(lt, hr_a + hr_u + hr_v, ax + ux + vx);
         o_um = opaque_at(plane_o, hx, hr_a - hr_u, ax - ux); o_up = opaque_at(plane_o, hx, hr_a + hr_u, ax + ux);
         o_vm = opaque_at(plane_o, hx, hr_a - hr_v, ax - vx); o_vp = opaque_at(plane_o, hx, hr_a + hr_v, ax + vx);
     }

@@ -16,13 +16,8 @@ for _ in range(3):
     batch.submit(world, coords).wait()
 pr = batch.profile()
 n = len(coords)
-names = ["P0 fetch+surface", "P1 stage+convert", "P1x x-halo", "P2 faces+scan", "P3a list+indices", "P3b vertices+tail"]
+names = ["P0 next chunk", "P1 stage+convert ids", "P1x x-halo classes", "P2 faces+scan", "P3a quad list", "P3b light gather+vertices"]
 tot = sum(pr[:6])
-print("kernel ms %.3f  chunks %d  total cycles/chunk (thread0 view) %.0f" % (batch.elapsed_ms(), n, tot / n))
+print("kernel ms %.3f  chunks %d  total cycles/chunk (thread 0 of each CTA) %.0f" % (batch.elapsed_ms(), n, tot / n))
 for i, nm in enumerate(names):
-    print("  %-20s %8.0f cycles/chunk  %5.1f%%" % (nm, pr[i] / n, 100.0 * pr[i] / tot))
-print("  producer wait(empty) %8.0f cycles/chunk ; class warp1 wait(full) %8.0f ; light warp wait(full) %8.0f" % (pr[8] / n, pr[9] / n, pr[10] / n))
-print("  first-slab latency %6.0f cycles ; class warp0 per-slab processing %6.0f cycles (%d slabs/chunk) ; light warp per-slab %6.0f ; producer done issuing at %6.0f" % (
-    pr[11] / n, pr[12] / max(pr[13], 1), pr[13] / n, pr[14] / max(pr[13], 1), pr[15] / n))
-print("  CTA 0, last chunk: per slab  issue / ready / done  (cycles since P1 start)")
-print("   " + " ".join("%d:%d/%d/%d" % (i, pr[64 + i], pr[128 + i], pr[192 + i]) for i in range(34)))
+    print("  %-26s %8.0f cycles/chunk  %5.1f%%" % (nm, pr[i] / n, 100.0 * pr[i] / tot))

@@ -2,7 +2,7 @@
 //
 // Runs the exact per-lane functions of gamecraft_b200/csrc/mesh_core.cuh (compiled for the host) in the
 // order the sm_100a kernel runs them, on ordinary memory instead of shared memory.  This checks the
-// bit-level logic (class planes, light packing, face masks, ranks, vertex packing) against the CPU oracle
+// bit-level logic (class planes, face masks, ranks, light gathering, vertex packing) against the CPU oracle
 // on the build box, where there is no GPU.  It is NOT a fallback: nothing in the product links it.
 #include <cstdint>
 #include <cstdlib>
@@ -48,7 +48,6 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
     }
 
     std::vector<uint32_t> planes((size_t)kPlanes * kHaloRows, 0xDEADBEEFu);
-    std::vector<uint8_t> lt(kLtBytes + kLtxBytes, 0xAB);
     std::vector<uint16_t> hx(kHaloRows, 0xFFFF);
     uint8_t* hx_b = (uint8_t*)hx.data();
 
@@ -59,7 +58,6 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
         int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
         int zz = tz & 31;
         int64_t col = (int64_t)(cz + dcz) * w.size_x + cx;
-        const uint8_t* srow = w.surface + col * 1024 + zz * 32;
         for (int ty = -1; ty <= kTY; ty++)
         {
             int wy = cy * 64 + ty;
@@ -69,7 +67,6 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
                 uint32_t out[8];
                 p1_class_row_const(wy < 0 ? cls8[kill_zone] : cls8[0], out);
                 for (int k = 0; k < 8; k++) planes[k * kHaloRows + hr] = out[k];
-                for (int x = 0; x < 32; x++) lt[hr * kLtStride + x] = wy < 0 ? 0x00 : 0xFF;
                 continue;
             }
             int64_t base = (col * 4 + (wy >> 6)) * 65536 + 32 * ((wy & 63) + 64 * zz);
@@ -85,52 +82,30 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
                     q[k].x = o[0]; q[k].y = o[1]; q[k].z = o[2]; q[k].w = o[3];
                 }
                 uint32_t out[8];
-                p1_class_row(q, lut.data(), out);
+                p1_class_row(q, row_uniform(q), lut.data(), out);
                 for (int k = 0; k < 8; k++) { out[k] = rotl_bytes(out[k], rot_selector(rot)); planes[k * kHaloRows + hr] = out[k]; }
                 uint32_t vis = centre ? row_emit_mask(out) : 0u;
                 const int sl = tz + 1;
                 if (vis & 1u) bvm[(ty + 1) * 2 + (sl >> 5)] |= 1u << (sl & 31);
                 if (vis >> 31) bvm[kBvWords + (ty + 1) * 2 + (sl >> 5)] |= 1u << (sl & 31);
             }
-            const uint32_t* sw = (const uint32_t*)(w.sun + base);
-            const uint32_t* lw = (const uint32_t*)(w.light + base);
-            const uint32_t* fw = (const uint32_t*)srow;
-            for (int h = 0; h < 2; h++)
-            {
-                // the kernel classifies each octet against the surface (wholly above / wholly below / mixed); all forms must agree
-                int smax[2] = { 0, 0 }, smin[2] = { 255, 255 };
-                for (int x = 0; x < 16; x++)
-                {
-                    int v = srow[h * 16 + x];
-                    if (v > smax[x >> 3]) smax[x >> 3] = v;
-                    if (v < smin[x >> 3]) smin[x >> 3] = v;
-                }
-                Words4 sn = { sw[4 * h], sw[4 * h + 1], sw[4 * h + 2], sw[4 * h + 3] }, bl = { lw[4 * h], lw[4 * h + 1], lw[4 * h + 2], lw[4 * h + 3] };
-                Words4 sf = { fw[4 * h], fw[4 * h + 1], fw[4 * h + 2], fw[4 * h + 3] };
-                const bool halo_row = ty < 0 || ty >= kTY;     // the kernel's y-halo warp never takes the shortcuts
-                Words4 a = p1_light_half(sn, bl, sf, wy, halo_row ? 0 : light_mode(wy, smax[0], smin[0]), halo_row ? 0 : light_mode(wy, smax[1], smin[1]));
-                Words4 b = p1_light_half(sn, bl, sf, wy, 0, 0);
-                if (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) return -7;
-                memcpy(&lt[hr * kLtStride + h * 16], &a, 16);
-            }
         }
     }
-    // ---- phase 1x: only the x-halo cells something will read; the others stay poisoned (0xFFFF / 0xAB) ----
+    // ---- phase 1x: only the x-halo cells something will read; the others stay poisoned (0xFFFF) ----
     for (int hr = 0; hr < kHaloRows; hr++)
     {
         int ty = hr / kRowsZ - 1, tz = hr % kRowsZ - 1;
         int wy = cy * 64 + ty;
         for (int side = 0; side < 2; side++)
         {
-            if (wy < 0) { p1_xhalo_cell(cls8[kill_zone], 0x00, hx_b, lt.data(), hr, side); continue; }
-            if (wy >= 256) { p1_xhalo_cell(cls8[0], 0xFF, hx_b, lt.data(), hr, side); continue; }
+            if (wy < 0) { p1_xhalo_cell(cls8[kill_zone], hx_b, hr, side); continue; }
+            if (wy >= 256) { p1_xhalo_cell(cls8[0], hx_b, hr, side); continue; }
             if (!xhalo_needed(bvm.data() + side * kBvWords, ty, tz)) continue;
             int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
             int zz = tz & 31, xx = side ? 0 : 31;
             int64_t col = (int64_t)(cz + dcz) * w.size_x + (cx + (side ? 1 : -1));
             int64_t vox = (col * 4 + (wy >> 6)) * 65536 + xx + 32 * ((wy & 63) + 64 * zz);
-            uint32_t lb = light_byte_of(w.sun[vox], w.light[vox], w.surface[col * 1024 + zz * 32 + xx], wy);
-            p1_xhalo_cell(cls8[w.blocks[vox] & 255u], lb, hx_b, lt.data(), hr, side);
+            p1_xhalo_cell(cls8[w.blocks[vox] & 255u], hx_b, hr, side);
         }
     }
 
@@ -173,7 +148,19 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
         rank += c;
     }
 
-    // ---- phase 3b ----
+    // ---- phase 3b: the surface rows the kernel's fetch warp stages, then one gather per quad ----
+    std::vector<uint8_t> surf(kSurfRowBytes), surf_x(2 * kRowsZ);
+    for (int tz = -1; tz <= kTZ; tz++)
+    {
+        int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0), zz = tz & 31;
+        for (int x = 0; x < 32; x++) surf[(tz + 1) * 32 + x] = w.surface[((int64_t)(cz + dcz) * w.size_x + cx) * 1024 + zz * 32 + x];
+        surf_x[tz + 1] = w.surface[((int64_t)(cz + dcz) * w.size_x + cx - 1) * 1024 + zz * 32 + 31];
+        surf_x[kRowsZ + tz + 1] = w.surface[((int64_t)(cz + dcz) * w.size_x + cx + 1) * 1024 + zz * 32 + 0];
+    }
+    LightGather lg;
+    lg.sun = w.sun; lg.light = w.light; lg.surf = surf.data(); lg.surf_x = surf_x.data();
+    lg.own = (((int64_t)cz * w.size_x + cx) * 4 + cy) * 65536;
+    lg.size_x = w.size_x; lg.cx = cx; lg.cy = cy; lg.cz = cz;
     const uint16_t* cb = w.blocks + (((int64_t)cz * w.size_x + cx) * 4 + cy) * 65536;
     for (uint32_t i = 0; i < total; i++)
     {
@@ -181,7 +168,7 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
         int x = (e >> 3) & 31, tz = (e >> 8) & 31, ty = (e >> 13) & 63;
         uint32_t id = cb[x + 32 * (ty + 64 * tz)] & 255u;
         uint32_t v[12], iw[3];
-        p3b_quad(e, make_face_plan(kFaces[e & 7]), lt.data(), planes.data() + P_OPAQUE * kHaloRows, hx.data(), mat[id], v);
+        p3b_quad(e, make_face_plan(kFaces[e & 7]), lg, planes.data() + P_OPAQUE * kHaloRows, hx.data(), mat[id], v);
         memcpy(verts_out + (size_t)i * 48, v, 48);
         quad_index_words(i, iw);
         memcpy((uint32_t*)idx_out + (size_t)(type_off[(e >> 19) & 7] + tlist[i]) * 3, iw, 12);
