@@ -4,8 +4,8 @@
 // per chunk:
 //   P0  the next chunk's position and the surface rows of its three columns (one warp, a chunk ahead)
 //   P1  the 34 z-slabs of BLOCK IDS (32x64 voxels, 4 KB, contiguous in the brick) are staged by TMA tensor-map box
-//       loads (cp.async.bulk.tensor.4d) into team-owned two-slot mbarrier rings and converted, one voxel row per
-//       lane, into the resident on-chip form: eight class bit planes over the chunk + 1-voxel halo
+//       loads (cp.async.bulk.tensor.4d) into warp-owned mbarrier slots and converted, two voxel rows per lane, into
+//       the resident on-chip form: eight class bit planes over the chunk + 1-voxel halo
 //   P1x the x = -1 / x = 32 halo classes that some face or corner test will actually read are gathered from the
 //       neighbour columns; air chunks gather nothing and stop here — their light arrays are never touched
 //   P2  face masks per row (bitwise, 32 voxels per op), per-row counts, per-layer warp reductions, scan,
@@ -28,20 +28,22 @@ namespace
 constexpr int NT = kMeshThreads;          // 10 warps
 constexpr int kWarps = NT / 32;
 constexpr int kSlabs = kRowsZ;            // 34 z-slabs per chunk: tz = -1 .. 32
-// P1: kTeams teams of 2 warps (rows 0..31 / 32..63 of a slab, one lane per voxel row).  Team t converts slabs t, t+4, ...
-// and stages them itself through its own two-slot ring: as soon as both warps hold a slab in registers they sync on a
-// named barrier and one lane issues the TMA load of the slab after next into the slot just freed.  (A separate
-// producer warp cost ~700 cycles per slab — try_wait ~140, arrive.expect_tx + UTMALDG ~360, measured — and paced
-// the whole phase; a ring shared by independent producers breaks mbarrier parity waits.)
-constexpr int kTeams = 4, kTeamWarps = 2, kTeamStages = 2;
-constexpr int kStages = kTeams * kTeamStages;              // 8
-constexpr int kSlabWarps = kTeams * kTeamWarps;            // warps 0 .. 7
+// P1: eight slab warps, each with its own ring slot and mbarrier.  Warp w converts slabs w, w + 8, ...: it waits for its
+// slot, pulls the slab's 64 voxel rows into registers (two per lane), immediately re-arms the slot with the TMA load of
+// its next slab, and converts the rows while that load is in flight.  (Measured: a lane's conversion is one long
+// dependency chain, ~1400 cycles per row whatever the memory system does, so two rows per lane double the phase's
+// throughput; a separate producer warp cost ~700 cycles per slab and paced the phase; a ring shared by independent
+// producers breaks mbarrier parity waits.)
+constexpr int kSlabWarps = 8;                              // warps 0 .. 7
+constexpr int kSlabsPerWarp = kTZ / kSlabWarps;            // the 32 centre slabs; the two z-halo slabs go to the fetch warp
+constexpr int kStages = kSlabWarps;                        // one slot per slab warp
 constexpr int kHaloWarp = kSlabWarps;                      // warp 8: the y-halo rows (ty = -1, 64), straight from global memory
 constexpr int kFetchWarp = kHaloWarp + 1;                  // warp 9: prefetches the next chunk's id, position and surface rows
 static_assert(kFetchWarp < kWarps, "warp roles");
 constexpr int kYHaloTasks = 2 * kRowsZ;                    // 2 faces x 34 rows
 constexpr int kHaloTasks = kHaloRows * 2;
-constexpr int kHaloPerThread = (kHaloTasks + NT - 1) / NT;
+constexpr int kHaloBatch = 4;                              // x-halo loads in flight per thread
+constexpr int kHaloPerThread = ((kHaloTasks + NT - 1) / NT + kHaloBatch - 1) / kHaloBatch * kHaloBatch;
 
 constexpr int kStageBytes = 4096;                          // one z-slab of block ids: [64][32] u16
 
@@ -56,9 +58,9 @@ constexpr int kMaxLayerQuads = 4 * kTX * kTZ + 2 * (kTX + kTZ);            // a 
 static_assert(kListCap >= kMaxLayerQuads, "one layer must fit a batch");
 constexpr int kOffPlanes = kOffStages + kStages * kStageBytes;            // 32768
 constexpr int kOffBv = kOffPlanes + kPlanes * kHaloRows * 4;              // u32[2][132]: per layer, which rows' x = 0 / x = 31 voxel emits
-constexpr int kSurfBytes = (kSurfRowBytes + 2 * kRowsZ + 15) & ~15;       // [34][32] centre-x surface rows + [2][34] x-halo surface bytes
-constexpr int kOffSurf = kOffBv + ((2 * kBvWords * 4 + 15) & ~15);        // two buffers: this chunk's and the prefetched next one's
-constexpr int kOffLut = kOffSurf + 2 * kSurfBytes;
+constexpr int kSurfBytes = (kSurfTileBytes + 15) & ~15;                   // [34][34] surface heights under the halo tile
+constexpr int kOffSurf = kOffBv + ((2 * kBvWords * 4 + 15) & ~15);        // staged at the start of P3, for chunks that emit
+constexpr int kOffLut = kOffSurf + kSurfBytes;
 constexpr int kOffMat = kOffLut + 256 * 8;
 constexpr int kOffCls = kOffMat + 256 * 8;
 constexpr int kOffLayerCnt = kOffCls + 256;                               // u32[64]
@@ -174,25 +176,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
-// bar.sync that also takes a value computed from freshly loaded registers: the loads have completed before the
-// barrier is reached (the compiler cannot sink them below it)
-// (The barrier id is an immediate: a register id makes ptxas reserve all 16 hardware barriers, i.e. one CTA per SM.)
-template <int kId>
-__device__ __forceinline__ void named_bar_sync_imm(uint32_t dep)
-{
-    asm volatile("bar.sync %0, %1;" ::"n"(kId), "n"(kTeamWarps * 32), "r"(dep) : "memory");
-}
-__device__ __forceinline__ void team_bar_sync_after(int team, uint32_t dep)
-{
-    switch (team)
-    {
-    case 0: named_bar_sync_imm<1>(dep); break;
-    case 1: named_bar_sync_imm<2>(dep); break;
-    case 2: named_bar_sync_imm<3>(dep); break;
-    default: named_bar_sync_imm<4>(dep); break;
-    }
-}
-
 // In-kernel cycle attribution is compiled in only for the profiling instantiation (GCMESH_PROFILE=1).
 #define GC_PROF_MARK(slot)                                                            \
     do {                                                                              \
@@ -214,6 +197,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     uint16_t* s_hx = reinterpret_cast<uint16_t*>(smem + kOffHx);
     uint8_t* s_hx_b = smem + kOffHx;
     uint32_t* s_bvm = reinterpret_cast<uint32_t*>(smem + kOffBv);
+    uint8_t* s_surf = smem + kOffSurf;
     NextChunk* s_next = reinterpret_cast<NextChunk*>(smem + kOffNext);
     LutEntry* s_lut = reinterpret_cast<LutEntry*>(smem + kOffLut);
     MatEntry* s_mat = reinterpret_cast<MatEntry*>(smem + kOffMat);
@@ -250,39 +234,18 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     const int air_cls = p.tables->cls8[0];
     __syncthreads();
 
-    uint32_t team_seq = 0;  // slabs this warp's team has staged so far (ring slot / parity source)
+    uint32_t warp_seq = 0;  // slabs this warp has staged so far (mbarrier parity source)
     long long prof_t = clock64();
 
-    // Claim the next chunk and stage its position and the surface rows of the three columns (cz-1, cz, cz+1) at cx,
-    // plus the x = -1 / x = 32 surface bytes of the same rows.  Run by one warp into buffer `b`, a chunk ahead of the
-    // rest of the CTA.
+    // Claim the next chunk, a chunk ahead of the rest of the CTA (one warp, into buffer `b`).
     auto fetch_chunk = [&](int b)
     {
-        int c = 0, fx = 0, fy = 0, fz = 0;
         if (lane == 0)
         {
-            c = atomicAdd(p.work_counter, 1);
+            int c = atomicAdd(p.work_counter, 1), fx = 0, fy = 0, fz = 0;
             if (c >= p.n_chunks) c = -1;
             if (c >= 0) { const GcChunkCoord cc = p.coords[c]; fx = cc.cx; fy = cc.cy; fz = cc.cz; }
             s_next[b].chunk = c; s_next[b].cx = fx; s_next[b].cy = fy; s_next[b].cz = fz;
-        }
-        c = __shfl_sync(0xffffffffu, c, 0); fx = __shfl_sync(0xffffffffu, fx, 0); fz = __shfl_sync(0xffffffffu, fz, 0);
-        if (c < 0) return;
-        uint8_t* surf = smem + kOffSurf + b * kSurfBytes;
-        for (int i = lane; i < kRowsZ * 4; i += 32)
-        {
-            const int r = i >> 2, q = i & 3;
-            const int tz = r - 1;
-            const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
-            const size_t col = (size_t)(fz + dcz) * p.size_x + fx;
-            reinterpret_cast<uint2*>(surf)[i] = __ldg(reinterpret_cast<const uint2*>(p.surface + col * 1024 + (tz & 31) * 32) + q);
-        }
-        for (int i = lane; i < 2 * kRowsZ; i += 32)
-        {
-            const int side = i / kRowsZ, tz = i % kRowsZ - 1;
-            const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
-            const size_t col = (size_t)(fz + dcz) * p.size_x + (fx + (side ? 1 : -1));
-            surf[kSurfRowBytes + i] = __ldg(p.surface + col * 1024 + (tz & 31) * 32 + (side ? 0 : 31));
         }
     };
 
@@ -299,104 +262,105 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         if (chunk < 0) break;
         const int cx = s_next[buf].cx, cy = s_next[buf].cy, cz = s_next[buf].cz;
         const int lwy = cy * kTY;
-        const uint8_t* s_surf = smem + kOffSurf + buf * kSurfBytes;
 
         GC_PROF_MARK(0);
         // ================= P1: stage + convert the block ids =================
         const bool has_lo = lwy > 0, has_hi = lwy + kTY < GC_WORLD_BLOCK_HEIGHT;
         const int col0 = cz * p.size_x + cx;
-        if (warp < kSlabWarps)
+        // two voxel rows of slab s (ty = lane, lane + 32; the octets rotated as `unrot` undoes) -> their plane words
+        // one voxel row (ty, slab s; the octets rotated as `unrot` undoes) -> its plane words; returns the row's emitting voxels
+        auto convert_row = [&](const Ids8 (&q)[4], int u, uint32_t unrot, int ty, int s) -> uint32_t
         {
-            // ---- slab teams: one lane per voxel row (ty = 0..63); the team stages its own slabs ----
-            // team = warp % 4 puts each team on its own scheduler partition (SMSP = warp % 4)
-            const int team = warp % kTeams, wt = warp / kTeams;
-            const int ty = wt * 32 + lane;
-            const int rot4 = (lane >> 1) & 3;   // shared-memory read rotation (bank-conflict free)
-            const uint32_t unrot = rot_selector(rot4);
-            const int boff0 = ty * 64 + ((0 + rot4) & 3) * 16, boff1 = ty * 64 + ((1 + rot4) & 3) * 16;
-            const int boff2 = ty * 64 + ((2 + rot4) & 3) * 16, boff3 = ty * 64 + ((3 + rot4) & 3) * 16;
-            const int n_mine = (kSlabs - team + kTeams - 1) / kTeams;  // slabs team, team + 4, ...
-
-            // stage slab number k of this team (s = team + 4k) into the team's ring slot for sequence number `seq`
-            auto issue = [&](int k, uint32_t seq)
+            uint32_t o[8];
+            p1_class_row(q, u, s_lut, o);
+            if (u != 2)   // (all-zero / all-one words need no un-rotation)
             {
-                const int s = team + k * kTeams;
-                const int stage = team * kTeamStages + (int)(seq % kTeamStages);
-                const int tz = s - 1;
-                const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
-                const int slot = (col0 + dcz * p.size_x) * 4 + cy;
-                const uint32_t full = smem_u32(&s_bars[stage]);
-                fence_proxy_async();   // the slot was read (and, as hx / the quad list, written) by the generic proxy
-                mbar_expect_tx(full, (uint32_t)kStageBytes);
-                tma_load_4d(smem_u32(s_stage + stage * kStageBytes), &maps.blocks_slab, 0, 0, tz & 31, slot, full);
-            };
-            auto stage_plain = [&](int k, uint32_t seq)   // debug staging path (GCMESH_NO_TMA=1): the whole warp copies
-            {
-                const int s = team + k * kTeams;
-                const int stage = team * kTeamStages + (int)(seq % kTeamStages);
-                const int tz = s - 1;
-                const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
-                const int slot = (col0 + dcz * p.size_x) * 4 + cy;
-                const size_t vox = (size_t)slot * GC_CHUNK_SIZE_3 + (size_t)(tz & 31) * 2048;
-                uint8_t* st = s_stage + stage * kStageBytes;
-                for (int i = lane; i < 256; i += 32) reinterpret_cast<uint4*>(st)[i] = reinterpret_cast<const uint4*>(p.blocks + vox)[i];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&s_bars[stage]));
-            };
-
-            // prologue: the first kTeamStages slabs (all slots are free: the previous chunk ended with a CTA-wide sync)
-            if (wt == 0)
-            {
-                for (int k = 0; k < kTeamStages && k < n_mine; k++)
-                {
-                    if (p.use_tma) { if (lane == 0) issue(k, team_seq + k); }
-                    else stage_plain(k, team_seq + k);
-                }
-            }
-            for (int k = 0; k < n_mine; k++)
-            {
-                const int s = team + k * kTeams;
-                const uint32_t seq = team_seq + k;
-                const int stage = team * kTeamStages + (int)(seq % kTeamStages);
-                mbar_wait(smem_u32(&s_bars[stage]), (seq / kTeamStages) & 1, p.error_flag);
-                const uint8_t* st = s_stage + stage * kStageBytes;
-                Ids8 q[4];
-                {
-                    const uint4 v0 = *reinterpret_cast<const uint4*>(st + boff0), v1 = *reinterpret_cast<const uint4*>(st + boff1);
-                    const uint4 v2 = *reinterpret_cast<const uint4*>(st + boff2), v3 = *reinterpret_cast<const uint4*>(st + boff3);
-                    q[0] = Ids8{ v0.x, v0.y, v0.z, v0.w }; q[1] = Ids8{ v1.x, v1.y, v1.z, v1.w };
-                    q[2] = Ids8{ v2.x, v2.y, v2.z, v2.w }; q[3] = Ids8{ v3.x, v3.y, v3.z, v3.w };
-                }
-                const bool uniform = row_uniform(q);   // reads all sixteen words: the row is in registers from here on
-                // refill: both warps hold their rows, so the slot is free — one lane stages the slab after next into it
-                if (k + kTeamStages < n_mine)
-                {
-                    team_bar_sync_after(team, (uint32_t)uniform);
-                    if (wt == (k & 1))
-                    {
-                        if (p.use_tma) { if (lane == 0) issue(k + kTeamStages, seq + kTeamStages); }
-                        else stage_plain(k + kTeamStages, seq + kTeamStages);
-                    }
-                }
-                const int hr = hrow(ty, s - 1);
-                uint32_t out[8];
-                p1_class_row(q, uniform, s_lut, out);
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                {
-                    out[j] = rotl_bytes(out[j], unrot);
-                    s_planes[j * kHaloRows + hr] = out[j];
-                }
-                const uint32_t vis = (s >= 1 && s <= kTZ) ? row_emit_mask(out) : 0u;
-                if (vis) s_ctx->any_emit = 1;
-                if (vis & 0x80000001u)
+                for (int j = 0; j < 8; j++) o[j] = rotl_bytes(o[j], unrot);
+            }
+            const int hr = hrow(ty, s - 1);
+#pragma unroll
+            for (int j = 0; j < 8; j++) s_planes[j * kHaloRows + hr] = o[j];
+            return row_emit_mask(o);
+        };
+        // two voxel rows of slab s (ty = lane, lane + 32)
+        auto convert_rows = [&](const Ids8 (&qa)[4], const Ids8 (&qb)[4], int ua, int ub, uint32_t unrot, int s)
+        {
+            const uint32_t va = convert_row(qa, ua, unrot, lane, s), vb = convert_row(qb, ub, unrot, lane + 32, s);
+            if (s >= 1 && s <= kTZ)
+            {
+                if (va | vb) s_ctx->any_emit = 1;
+                if ((va | vb) & 0x80000001u)
                 {
                     s_ctx->any_bv = 1;
-                    if (vis & 1u) atomicOr(&s_bvm[(ty + 1) * 2 + (s >> 5)], 1u << (s & 31));
-                    if (vis >> 31) atomicOr(&s_bvm[kBvWords + (ty + 1) * 2 + (s >> 5)], 1u << (s & 31));
+                    if (va & 1u) atomicOr(&s_bvm[(lane + 1) * 2 + (s >> 5)], 1u << (s & 31));
+                    if (va >> 31) atomicOr(&s_bvm[kBvWords + (lane + 1) * 2 + (s >> 5)], 1u << (s & 31));
+                    if (vb & 1u) atomicOr(&s_bvm[(lane + 33) * 2 + (s >> 5)], 1u << (s & 31));
+                    if (vb >> 31) atomicOr(&s_bvm[kBvWords + (lane + 33) * 2 + (s >> 5)], 1u << (s & 31));
                 }
             }
-            team_seq += n_mine;
+        };
+        if (warp < kSlabWarps)
+        {
+            // ---- slab warps: warp w converts the centre slabs tz = w, w + 8, w + 16, w + 24 out of its own ring slot; a lane
+            // holds two voxel rows (ty = lane, lane + 32) so that two independent dependency chains are in flight ----
+            const int rot4 = (lane >> 1) & 3;   // shared-memory read rotation (bank-conflict free)
+            const uint32_t unrot = rot_selector(rot4);
+            const int boff0 = lane * 64 + ((0 + rot4) & 3) * 16, boff1 = lane * 64 + ((1 + rot4) & 3) * 16;
+            const int boff2 = lane * 64 + ((2 + rot4) & 3) * 16, boff3 = lane * 64 + ((3 + rot4) & 3) * 16;
+            const uint32_t full = smem_u32(&s_bars[warp]);
+            uint8_t* const st = s_stage + warp * kStageBytes;
+            const int own_slot = col0 * 4 + cy;
+
+            auto issue = [&](int k)   // stage this warp's slab number k into its slot
+            {
+                fence_proxy_async();   // the slot was read (and, as hx / the quad list, written) by the generic proxy
+                mbar_expect_tx(full, (uint32_t)kStageBytes);
+                tma_load_4d(smem_u32(st), &maps.blocks_slab, 0, 0, warp + k * kSlabWarps, own_slot, full);
+            };
+            auto stage_plain = [&](int k)   // debug staging path (GCMESH_NO_TMA=1): the whole warp copies
+            {
+                const size_t vox = (size_t)own_slot * GC_CHUNK_SIZE_3 + (size_t)(warp + k * kSlabWarps) * 2048;
+                for (int i = lane; i < 256; i += 32) reinterpret_cast<uint4*>(st)[i] = reinterpret_cast<const uint4*>(p.blocks + vox)[i];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full);
+            };
+
+            // the slot is free: the previous chunk ended with a CTA-wide sync
+            if (p.use_tma) { if (lane == 0) issue(0); }
+            else stage_plain(0);
+            for (int k = 0; k < kSlabsPerWarp; k++)
+            {
+                const int s = 1 + warp + k * kSlabWarps;
+                const long long w0 = kProf ? clock64() : 0;
+                mbar_wait(full, (warp_seq + k) & 1, p.error_flag);
+                const long long w1 = kProf ? clock64() : 0;
+                if (kProf && warp == 0 && lane == 0) { atomicAdd(p.prof + 8, (unsigned long long)(w1 - w0)); atomicAdd(p.prof + 10, 1ull); }
+                Ids8 qa[4], qb[4];
+                {
+                    const uint4 a0 = *reinterpret_cast<const uint4*>(st + boff0), a1 = *reinterpret_cast<const uint4*>(st + boff1);
+                    const uint4 a2 = *reinterpret_cast<const uint4*>(st + boff2), a3 = *reinterpret_cast<const uint4*>(st + boff3);
+                    const uint4 b0 = *reinterpret_cast<const uint4*>(st + 2048 + boff0), b1 = *reinterpret_cast<const uint4*>(st + 2048 + boff1);
+                    const uint4 b2 = *reinterpret_cast<const uint4*>(st + 2048 + boff2), b3 = *reinterpret_cast<const uint4*>(st + 2048 + boff3);
+                    qa[0] = Ids8{ a0.x, a0.y, a0.z, a0.w }; qa[1] = Ids8{ a1.x, a1.y, a1.z, a1.w };
+                    qa[2] = Ids8{ a2.x, a2.y, a2.z, a2.w }; qa[3] = Ids8{ a3.x, a3.y, a3.z, a3.w };
+                    qb[0] = Ids8{ b0.x, b0.y, b0.z, b0.w }; qb[1] = Ids8{ b1.x, b1.y, b1.z, b1.w };
+                    qb[2] = Ids8{ b2.x, b2.y, b2.z, b2.w }; qb[3] = Ids8{ b3.x, b3.y, b3.z, b3.w };
+                }
+                int ua = row_uniformity(qa), ub = row_uniformity(qb);   // read all thirty-two words: both rows are in registers from here on
+                // refill: the instructions above consumed every loaded register before this point of the (in-order) instruction
+                // stream, so the slot is free — one lane stages the warp's next slab into it while the rows are converted
+                asm volatile("" : "+r"(ua), "+r"(ub)::"memory");
+                if (k + 1 < kSlabsPerWarp)
+                {
+                    __syncwarp();
+                    if (p.use_tma) { if (lane == 0) issue(k + 1); }
+                    else stage_plain(k + 1);
+                }
+                convert_rows(qa, qb, ua, ub, unrot, s);
+                if (kProf && warp == 0 && lane == 0) atomicAdd(p.prof + 9, (unsigned long long)(clock64() - w1));
+            }
+            warp_seq += kSlabsPerWarp;
         }
         else if (warp == kHaloWarp)
         {
@@ -421,13 +385,32 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                         const uint4 v = __ldg(gb + j);
                         q[j].x = v.x; q[j].y = v.y; q[j].z = v.z; q[j].w = v.w;
                     }
-                    p1_class_row(q, row_uniform(q), s_lut, out);
+                    p1_class_row(q, row_uniformity(q), s_lut, out);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; j++) s_planes[j * kHaloRows + hr] = out[j];
             }
         }
-        else if (warp == kFetchWarp) fetch_chunk(buf ^ 1);
+        else if (warp == kFetchWarp)
+        {
+            // ---- the next chunk's claim, then the two z-halo slabs (tz = -1, 32): contiguous 4 KB of the bricks in front / behind,
+            // two rows per lane straight from global memory ----
+            fetch_chunk(buf ^ 1);
+#pragma unroll 1
+            for (int side = 0; side < 2; side++)
+            {
+                const int slot = (col0 + (side ? p.size_x : -p.size_x)) * 4 + cy;
+                const uint4* g = reinterpret_cast<const uint4*>(p.blocks + (size_t)slot * GC_CHUNK_SIZE_3 + (size_t)(side ? 0 : 31) * 2048) + lane * 4;
+                Ids8 qa[4], qb[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    const uint4 a = __ldg(g + j), b = __ldg(g + 128 + j);
+                    qa[j] = Ids8{ a.x, a.y, a.z, a.w }; qb[j] = Ids8{ b.x, b.y, b.z, b.w };
+                }
+                convert_rows(qa, qb, row_uniformity(qa), row_uniformity(qb), rot_selector(0), side ? kSlabs - 1 : 0);
+            }
+        }
         __syncthreads();
         GC_PROF_MARK(1);
 
@@ -435,41 +418,49 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         const bool any_emit = s_ctx->any_emit != 0, any_bv = s_ctx->any_bv != 0;
         if (any_emit)
         {
-            uint32_t id[kHaloPerThread];
-            uint32_t need = 0;
-#pragma unroll
-            for (int k = 0; k < kHaloPerThread; k++)
+            // which halo cells can be read at all: per (side, layer) the rows next to an emitting boundary voxel
+            uint64_t* s_need = reinterpret_cast<uint64_t*>(smem + kOffList);   // [2][66], the quad list's space (not yet in use)
+            if (tid < 2 * kRowsY) s_need[tid] = any_bv ? xhalo_needed_mask(s_bvm + (tid / kRowsY) * kBvWords, tid % kRowsY - 1) : 0ull;
+            __syncthreads();
+#pragma unroll 1
+            for (int k0 = 0; k0 < kHaloPerThread; k0 += kHaloBatch)
             {
-                const int task = tid + k * NT;
-                if (task < kHaloTasks)
+                uint32_t id[kHaloBatch];
+                uint32_t need = 0;
+#pragma unroll
+                for (int k = 0; k < kHaloBatch; k++)
                 {
-                    // consecutive lanes walk up one (side, tz) column: neighbouring y rows share cache lines
-                    const int side = task / kHaloRows, rem = task % kHaloRows;
-                    const int tz = rem / kRowsY - 1, ty = rem % kRowsY - 1;
-                    const int wy = lwy + ty;
-                    if (any_bv && wy >= 0 && wy < GC_WORLD_BLOCK_HEIGHT && xhalo_needed(s_bvm + side * kBvWords, ty, tz))
+                    const int task = tid + (k0 + k) * NT;
+                    if (task < kHaloTasks)
                     {
-                        need |= 1u << k;
-                        const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
-                        const int zz = tz & 31, xx = side ? 0 : 31;
-                        const size_t col = (size_t)(cz + dcz) * p.size_x + (cx + (side ? 1 : -1));
-                        id[k] = __ldg(p.blocks + (col * 4 + (wy >> 6)) * GC_CHUNK_SIZE_3 + xx + 32 * ((wy & 63) + 64 * zz));
+                        // consecutive lanes walk up one (side, tz) column: neighbouring y rows share cache lines
+                        const int side = task / kHaloRows, rem = task % kHaloRows;
+                        const int tz = rem / kRowsY - 1, ty = rem % kRowsY - 1;
+                        const int wy = lwy + ty;
+                        if (wy >= 0 && wy < GC_WORLD_BLOCK_HEIGHT && ((s_need[side * kRowsY + ty + 1] >> (tz + 1)) & 1ull))
+                        {
+                            need |= 1u << k;
+                            const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
+                            const int zz = tz & 31, xx = side ? 0 : 31;
+                            const size_t col = (size_t)(cz + dcz) * p.size_x + (cx + (side ? 1 : -1));
+                            id[k] = __ldg(p.blocks + (col * 4 + (wy >> 6)) * GC_CHUNK_SIZE_3 + xx + 32 * ((wy & 63) + 64 * zz));
+                        }
                     }
                 }
-            }
 #pragma unroll
-            for (int k = 0; k < kHaloPerThread; k++)
-            {
-                const int task = tid + k * NT;
-                if (task < kHaloTasks)
+                for (int k = 0; k < kHaloBatch; k++)
                 {
-                    const int side = task / kHaloRows, rem = task % kHaloRows;
-                    const int tz = rem / kRowsY - 1, ty = rem % kRowsY - 1;
-                    const int hr = hrow(ty, tz);
-                    const int wy = lwy + ty;
-                    if (wy < 0) p1_xhalo_cell(kill_cls, s_hx_b, hr, side);
-                    else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_xhalo_cell(air_cls, s_hx_b, hr, side);
-                    else if ((need >> k) & 1u) p1_xhalo_cell(s_cls[id[k] & 255u], s_hx_b, hr, side);
+                    const int task = tid + (k0 + k) * NT;
+                    if (task < kHaloTasks)
+                    {
+                        const int side = task / kHaloRows, rem = task % kHaloRows;
+                        const int tz = rem / kRowsY - 1, ty = rem % kRowsY - 1;
+                        const int hr = hrow(ty, tz);
+                        const int wy = lwy + ty;
+                        if (wy < 0) p1_xhalo_cell(kill_cls, s_hx_b, hr, side);
+                        else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_xhalo_cell(air_cls, s_hx_b, hr, side);
+                        else if ((need >> k) & 1u) p1_xhalo_cell(s_cls[id[k] & 255u], s_hx_b, hr, side);
+                    }
                 }
             }
         }
@@ -577,16 +568,29 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             uint32_t* idx_words = reinterpret_cast<uint32_t*>(p.index_arena) + (size_t)quad_base * 3;
             uint4* vtx = reinterpret_cast<uint4*>(p.vertex_arena) + (size_t)quad_base * 3;
             LightGather lg;
-            lg.sun = p.sun; lg.light = p.light; lg.surf = s_surf; lg.surf_x = s_surf + kSurfRowBytes;
+            lg.sun = p.sun; lg.light = p.light; lg.surf = s_surf;
             lg.own = ((long long)col0 * 4 + cy) * GC_CHUNK_SIZE_3;
             lg.size_x = p.size_x; lg.cx = cx; lg.cy = cy; lg.cz = cz;
             const uint16_t* chunk_blocks = p.blocks + lg.own;
+            // the surface heights under the halo tile ([34][34] bytes out of the nine columns around the chunk); P3b reads
+            // them after the barrier that follows P3a
+            for (int i = tid; i < kSurfTileBytes; i += NT)
+            {
+                const int tz = i / kSurfStride - 1, x = i % kSurfStride - 1;
+                const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0), dcx = x < 0 ? -1 : (x > 31 ? 1 : 0);
+                const size_t col = (size_t)(cz + dcz) * p.size_x + (cx + dcx);
+                s_surf[i] = __ldg(p.surface + col * 1024 + (tz & 31) * 32 + (x & 31));
+            }
 
             for (int l0 = 0; l0 < kTY;)
             {
                 const uint32_t first = s_layer_base[l0];
-                int l1 = l0 + 1;
-                while (l1 < kTY && s_layer_base[l1 + 1] - first <= (uint32_t)kListCap) l1++;
+                int l1 = kTY;                                               // nearly always: the rest of the chunk fits
+                if (s_layer_base[kTY] - first > (uint32_t)kListCap)
+                {
+                    l1 = l0 + 1;
+                    while (s_layer_base[l1 + 1] - first <= (uint32_t)kListCap) l1++;
+                }
                 const uint32_t count = s_layer_base[l1] - first;
                 if (count)
                 {

@@ -47,7 +47,10 @@ struct MeshTensorMaps
     CUtensorMap blocks_slab, sun_slab, light_slab;
 };
 
-constexpr int kMeshThreads = 320;   // two CTAs per SM
+#ifndef GCMESH_THREADS
+#define GCMESH_THREADS 448
+#endif
+constexpr int kMeshThreads = GCMESH_THREADS;   // two CTAs per SM
 size_t mesh_smem_bytes();
 cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int grid, cudaStream_t stream);
 cudaError_t mesh_kernel_attributes(int* regs, int* static_smem, int* max_dyn_smem);

@@ -162,14 +162,34 @@ GC_HD void p1_class_octet(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, co
 // and undo it with rotl_bytes(out[j], r).
 struct Ids8 { uint32_t x, y, z, w; };
 GC_HD bool octet_uniform(const Ids8& q) { return (q.x == q.y) && (q.z == q.w) && (q.x == q.z) && ((q.x >> 16) == (q.x & 0xFFFFu)); }
-// every octet of the row holds a single block id (evaluated without short-circuit: reads all sixteen words)
-GC_HD bool row_uniform(const Ids8 q[4]) { return octet_uniform(q[0]) & octet_uniform(q[1]) & octet_uniform(q[2]) & octet_uniform(q[3]); }
-GC_HD void p1_class_row(const Ids8 q[4], bool uniform, const LutEntry* lut, uint32_t out[8])
+// How uniform is a row?  2: one block id throughout (air, deep stone: the bulk of a world), 1: every octet holds a
+// single id, 0: mixed.  Reads all sixteen words whatever the answer.
+GC_HD int row_uniformity(const Ids8 q[4])
 {
-    uint32_t lo[4], hi[4];
-    if (uniform)
+    const uint32_t w = q[0].x;
+    const uint32_t diff = (q[0].y ^ w) | (q[0].z ^ w) | (q[0].w ^ w) | (q[1].x ^ w) | (q[1].y ^ w) | (q[1].z ^ w) | (q[1].w ^ w)
+                        | (q[2].x ^ w) | (q[2].y ^ w) | (q[2].z ^ w) | (q[2].w ^ w) | (q[3].x ^ w) | (q[3].y ^ w) | (q[3].z ^ w) | (q[3].w ^ w);
+    if ((diff | ((w >> 16) ^ (w & 0xFFFFu))) == 0) return 2;
+    return (octet_uniform(q[0]) & octet_uniform(q[1]) & octet_uniform(q[2]) & octet_uniform(q[3])) ? 1 : 0;
+}
+GC_HD void p1_class_row(const Ids8 q[4], int uniformity, const LutEntry* lut, uint32_t out[8])
+{
+    if (uniformity == 2)
     {
-        // four single-block octets (air, deep stone, water ...): four independent table lookups, no branches between them
+        // all-zero / all-one plane words: nothing to transpose (or to un-rotate)
+        const LutEntry e = lut[q[0].x & 255u];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            out[k] = 0u - ((e.lo >> (8 * k)) & 1u);
+            out[4 + k] = 0u - ((e.hi >> (8 * k)) & 1u);
+        }
+        return;
+    }
+    uint32_t lo[4], hi[4];
+    if (uniformity == 1)
+    {
+        // four single-block octets (water over sand ...): four independent table lookups, no branches between them
         const LutEntry e0 = lut[q[0].x & 255u], e1 = lut[q[1].x & 255u], e2 = lut[q[2].x & 255u], e3 = lut[q[3].x & 255u];
         lo[0] = e0.lo * 255u; lo[1] = e1.lo * 255u; lo[2] = e2.lo * 255u; lo[3] = e3.lo * 255u;
         hi[0] = e0.hi * 255u; hi[1] = e1.hi * 255u; hi[2] = e2.hi * 255u; hi[3] = e3.hi * 255u;
@@ -197,7 +217,7 @@ GC_HD void p1_xhalo_cell(uint32_t cls, uint8_t* hx_b, int hr, int side) { hx_b[h
 // x = 31 (side 1) in one of the 3x3 rows around it.  bvm[(ty + 1) * 2 + w]: bit (tz + 1) of the 64-bit mask of layer ty
 // says "the boundary voxel of row (ty, tz) emits" (set for centre rows only).
 constexpr int kBvWords = kRowsY * 2;   // per side
-GC_HD uint32_t xhalo_needed(const uint32_t* bvm, int ty, int tz)
+GC_HD uint64_t xhalo_needed_mask(const uint32_t* bvm, int ty)   // bit tz + 1 = halo cell (ty, tz) of this side may be read
 {
     uint64_t m = 0;
 #pragma unroll
@@ -206,9 +226,9 @@ GC_HD uint32_t xhalo_needed(const uint32_t* bvm, int ty, int tz)
         const int r = ty + 1 + dy;
         if (r >= 0 && r < kRowsY) m |= (uint64_t)bvm[r * 2] | ((uint64_t)bvm[r * 2 + 1] << 32);
     }
-    m |= (m << 1) | (m >> 1);
-    return (uint32_t)(m >> (tz + 1)) & 1u;
+    return m | (m << 1) | (m >> 1);
 }
+GC_HD uint32_t xhalo_needed(const uint32_t* bvm, int ty, int tz) { return (uint32_t)(xhalo_needed_mask(bvm, ty) >> (tz + 1)) & 1u; }
 
 GC_HD uint32_t light_byte_of(uint32_t sun, uint32_t bl, uint32_t surf, int wy)
 {
@@ -382,18 +402,18 @@ GC_HD uint32_t corner_color(uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool
 
 // ---- light of one cell, gathered from the world arrays ----
 // What a quad needs to find the light of any cell of its chunk's halo tile (x in -1..32, ty in -1..64, tz in -1..32).
-//   surf      [34][32] surface rows of the three columns (cz-1 | cz | cz+1) at the chunk's own cx, row index tz + 1
-//   surf_x    [2][34]  the same for the cells x = -1 (side 0, column cx-1) and x = 32 (side 1, column cx+1)
+//   surf      [34][34] surface heights under the tile: row tz + 1 (columns cz-1 | cz | cz+1), byte x + 1 (cx-1 | cx | cx+1)
 struct LightGather
 {
     const uint8_t* sun;       // sunlight arena (slot-major bricks)
     const uint8_t* light;     // blockLight arena
     const uint8_t* surf;
-    const uint8_t* surf_x;
     long long own;            // voxel offset of the chunk's own brick in the arenas
     int size_x, cx, cy, cz;   // window width (columns) and the chunk's position
 };
-constexpr int kSurfRowBytes = kRowsZ * 32;
+constexpr int kSurfStride = kTX + 2;
+constexpr int kSurfTileBytes = kRowsZ * kSurfStride;
+constexpr int kColumnVoxels = 4 * kTX * kTY * kTZ;   // a column's four bricks are consecutive slots
 
 GC_HD uint32_t load_u8(const uint8_t* p)
 {
@@ -404,6 +424,9 @@ GC_HD uint32_t load_u8(const uint8_t* p)
 #endif
 }
 
+// voxel offset of tile coordinate x in -1..32 relative to the start of its row in the chunk's own brick
+GC_HD int x_term(int x) { return (x < 0 ? -kColumnVoxels : (x > 31 ? kColumnVoxels : 0)) + (x & 31); }
+
 // any cell of the halo tile (slow path: picks the neighbour brick / column)
 GC_HD uint32_t gather_cell(const LightGather& g, int x, int ty, int tz)
 {
@@ -413,8 +436,7 @@ GC_HD uint32_t gather_cell(const LightGather& g, int x, int ty, int tz)
     const int dcx = x < 0 ? -1 : (x > 31 ? 1 : 0), dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
     const long long slot = ((long long)(g.cz + dcz) * g.size_x + (g.cx + dcx)) * 4 + (wy >> 6);
     const long long vox = slot * (kTX * kTY * kTZ) + (x & 31) + 32 * ((wy & 63) + 64 * (tz & 31));
-    const uint32_t sf = dcx ? g.surf_x[(dcx > 0 ? kRowsZ : 0) + tz + 1] : g.surf[(tz + 1) * 32 + x];
-    return light_byte_of(load_u8(g.sun + vox), load_u8(g.light + vox), sf, wy);
+    return light_byte_of(load_u8(g.sun + vox), load_u8(g.light + vox), g.surf[(tz + 1) * kSurfStride + x + 1], wy);
 }
 
 // A face's geometry pre-digested for p3b_quad (built once per face from FaceDesc):
@@ -424,6 +446,7 @@ GC_HD uint32_t gather_cell(const LightGather& g, int x, int ty, int tz)
 //   w4  voxel-offset stride of u (ux + 32*uy + 2048*uz) as int16 | of v << 16
 //   w5  surface-row stride of u (ux + 32*uz) as int16 | of v << 16
 //   w6  footprint extent per axis: bit 0 x, bit 1 y, bit 2 z (1 = some in-plane axis runs along it)
+// (v never runs along x: the in-plane axes are (x,z), (x,y) or (y,z), see GC_FACE_TABLE.)
 struct FacePlan { uint32_t w0, w1, w2, w3, w4, w5, w6, w7; };
 GC_HD FacePlan make_face_plan(const FaceDesc& f)
 {
@@ -442,7 +465,7 @@ GC_HD FacePlan make_face_plan(const FaceDesc& f)
     }
     p.w3 = corners | (su << 12) | (sv << 16);
     p.w4 = (uint32_t)(uint16_t)(int16_t)(f.ux + 32 * f.uy + 2048 * f.uz) | ((uint32_t)(uint16_t)(int16_t)(f.vx + 32 * f.vy + 2048 * f.vz) << 16);
-    p.w5 = (uint32_t)(uint16_t)(int16_t)(f.ux + 32 * f.uz) | ((uint32_t)(uint16_t)(int16_t)(f.vx + 32 * f.vz) << 16);
+    p.w5 = (uint32_t)(uint16_t)(int16_t)(f.ux + kSurfStride * f.uz) | ((uint32_t)(uint16_t)(int16_t)(f.vx + kSurfStride * f.vz) << 16);
     p.w6 = (uint32_t)((f.ux | f.vx) ? 1 : 0) | ((uint32_t)((f.uy | f.vy) ? 1 : 0) << 1) | ((uint32_t)((f.uz | f.vz) ? 1 : 0) << 2);
     p.w7 = 0;
     return p;
@@ -464,27 +487,33 @@ GC_HD void p3b_quad(uint32_t entry, const FacePlan& f, const LightGather& g, con
     // 3x3 light neighbourhood in the layer in front of the face: cell (i, j) = a + i*u + j*v, i, j in -1..1,
     // and the opacity of the four edge cells (only b and c are ever tested, WorldRender.cpp:361-362)
     uint32_t l00, lm0, lp0, l0m, l0p, lmm, lmp, lpm, lpp, o_um, o_up, o_vm, o_vp;
-    const int ex = f.w6 & 1u, ey = (f.w6 >> 1) & 1u, ez = (f.w6 >> 2) & 1u;
-    if ((unsigned)(ax - ex) <= (unsigned)(31 - 2 * ex) && (unsigned)(ay - ey) <= (unsigned)(63 - 2 * ey) && (unsigned)(az - ez) <= (unsigned)(31 - 2 * ez))
+    const int ey = (f.w6 >> 1) & 1u, ez = (f.w6 >> 2) & 1u;
+    if ((unsigned)(ay - ey) <= (unsigned)(63 - 2 * ey) && (unsigned)(az - ez) <= (unsigned)(31 - 2 * ez))
     {
-        // the whole footprint lies inside the chunk's own brick: constant strides from the centre cell
-        const long long base = g.own + (ax + 32 * (ay + 64 * az));
+        // the footprint stays inside the chunk's own y / z range: constant strides along y and z; along x (axis u or
+        // the normal, never v) each of the up to three positions picks its own column — the brick at the same height of
+        // column cx-1 / cx+1 lies a fixed number of voxels away — so a row's quads at x = 0 and x = 31 take this path too
+        const int x0 = ax - ux, x2 = ax + ux;
+        const int dm = x_term(x0), d0 = x_term(ax), dp = x_term(x2);
+        const int du = (int16_t)(f.w4 & 0xFFFFu) - ux, dv = (int16_t)(f.w4 >> 16);       // strides without the x part
+        const int fu = (int16_t)(f.w5 & 0xFFFFu) - ux, fv = (int16_t)(f.w5 >> 16);
+        const long long base = g.own + 32 * (ay + 64 * az);
         const uint8_t* ps = g.sun + base;
         const uint8_t* pl = g.light + base;
-        const uint8_t* sf = g.surf + (az + 1) * 32 + ax;
-        const int du = (int16_t)(f.w4 & 0xFFFFu), dv = (int16_t)(f.w4 >> 16);
-        const int fu = (int16_t)(f.w5 & 0xFFFFu), fv = (int16_t)(f.w5 >> 16);
+        const uint8_t* sf = g.surf + (az + 1) * kSurfStride + 1;
+        const int om = dm - du, o0 = d0, op = dp + du;          // voxel offsets of the cells (-1, 0), (0, 0), (+1, 0)
+        const int gm = x0 - fu, g0 = ax, gp = x2 + fu;          // their surface offsets
         const int wy = g.cy * kTY + ay;
         // issue the eighteen loads before any of them is consumed
-        const uint32_t s00 = load_u8(ps), sm0 = load_u8(ps - du), sp0 = load_u8(ps + du), s0m = load_u8(ps - dv), s0p = load_u8(ps + dv);
-        const uint32_t smm = load_u8(ps - du - dv), smp = load_u8(ps - du + dv), spm = load_u8(ps + du - dv), spp = load_u8(ps + du + dv);
-        const uint32_t b00 = load_u8(pl), bm0 = load_u8(pl - du), bp0 = load_u8(pl + du), b0m = load_u8(pl - dv), b0p = load_u8(pl + dv);
-        const uint32_t bmm = load_u8(pl - du - dv), bmp = load_u8(pl - du + dv), bpm = load_u8(pl + du - dv), bpp = load_u8(pl + du + dv);
-        l00 = light_byte_of(s00, b00, sf[0], wy);
-        lm0 = light_byte_of(sm0, bm0, sf[-fu], wy - uy); lp0 = light_byte_of(sp0, bp0, sf[fu], wy + uy);
-        l0m = light_byte_of(s0m, b0m, sf[-fv], wy - vy); l0p = light_byte_of(s0p, b0p, sf[fv], wy + vy);
-        lmm = light_byte_of(smm, bmm, sf[-fu - fv], wy - uy - vy); lmp = light_byte_of(smp, bmp, sf[-fu + fv], wy - uy + vy);
-        lpm = light_byte_of(spm, bpm, sf[fu - fv], wy + uy - vy); lpp = light_byte_of(spp, bpp, sf[fu + fv], wy + uy + vy);
+        const uint32_t s00 = load_u8(ps + o0), sm0 = load_u8(ps + om), sp0 = load_u8(ps + op), s0m = load_u8(ps + o0 - dv), s0p = load_u8(ps + o0 + dv);
+        const uint32_t smm = load_u8(ps + om - dv), smp = load_u8(ps + om + dv), spm = load_u8(ps + op - dv), spp = load_u8(ps + op + dv);
+        const uint32_t b00 = load_u8(pl + o0), bm0 = load_u8(pl + om), bp0 = load_u8(pl + op), b0m = load_u8(pl + o0 - dv), b0p = load_u8(pl + o0 + dv);
+        const uint32_t bmm = load_u8(pl + om - dv), bmp = load_u8(pl + om + dv), bpm = load_u8(pl + op - dv), bpp = load_u8(pl + op + dv);
+        l00 = light_byte_of(s00, b00, sf[g0], wy);
+        lm0 = light_byte_of(sm0, bm0, sf[gm], wy - uy); lp0 = light_byte_of(sp0, bp0, sf[gp], wy + uy);
+        l0m = light_byte_of(s0m, b0m, sf[g0 - fv], wy - vy); l0p = light_byte_of(s0p, b0p, sf[g0 + fv], wy + vy);
+        lmm = light_byte_of(smm, bmm, sf[gm - fv], wy - uy - vy); lmp = light_byte_of(smp, bmp, sf[gm + fv], wy - uy + vy);
+        lpm = light_byte_of(spm, bpm, sf[gp - fv], wy + uy - vy); lpp = light_byte_of(spp, bpp, sf[gp + fv], wy + uy + vy);
     }
     else
     {

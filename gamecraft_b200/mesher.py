@@ -17,7 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libgcmesh.so")
+LIB_PATH = os.environ.get("GCMESH_LIB") or os.path.join(CSRC, "libgcmesh.so")   # GCMESH_LIB: development A/B builds
 
 CHUNK_VOXELS = 65536
 MESH_TYPES = 5

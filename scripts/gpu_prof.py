@@ -21,3 +21,5 @@ tot = sum(pr[:6])
 print("kernel ms %.3f  chunks %d  total cycles/chunk (thread 0 of each CTA) %.0f" % (batch.elapsed_ms(), n, tot / n))
 for i, nm in enumerate(names):
     print("  %-26s %8.0f cycles/chunk  %5.1f%%" % (nm, pr[i] / n, 100.0 * pr[i] / tot))
+print("  P1, warp 0 of each CTA: mbarrier wait %.0f cycles per slab, load + convert + refill %.0f cycles per slab (%.1f slabs per chunk)" % (
+    pr[8] / max(pr[10], 1), pr[9] / max(pr[10], 1), pr[10] / n))

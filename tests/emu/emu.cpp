@@ -82,7 +82,7 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
                     q[k].x = o[0]; q[k].y = o[1]; q[k].z = o[2]; q[k].w = o[3];
                 }
                 uint32_t out[8];
-                p1_class_row(q, row_uniform(q), lut.data(), out);
+                p1_class_row(q, row_uniformity(q), lut.data(), out);
                 for (int k = 0; k < 8; k++) { out[k] = rotl_bytes(out[k], rot_selector(rot)); planes[k * kHaloRows + hr] = out[k]; }
                 uint32_t vis = centre ? row_emit_mask(out) : 0u;
                 const int sl = tz + 1;
@@ -149,16 +149,15 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
     }
 
     // ---- phase 3b: the surface rows the kernel's fetch warp stages, then one gather per quad ----
-    std::vector<uint8_t> surf(kSurfRowBytes), surf_x(2 * kRowsZ);
+    std::vector<uint8_t> surf(kSurfTileBytes);
     for (int tz = -1; tz <= kTZ; tz++)
-    {
-        int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0), zz = tz & 31;
-        for (int x = 0; x < 32; x++) surf[(tz + 1) * 32 + x] = w.surface[((int64_t)(cz + dcz) * w.size_x + cx) * 1024 + zz * 32 + x];
-        surf_x[tz + 1] = w.surface[((int64_t)(cz + dcz) * w.size_x + cx - 1) * 1024 + zz * 32 + 31];
-        surf_x[kRowsZ + tz + 1] = w.surface[((int64_t)(cz + dcz) * w.size_x + cx + 1) * 1024 + zz * 32 + 0];
-    }
+        for (int x = -1; x <= kTX; x++)
+        {
+            int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0), dcx = x < 0 ? -1 : (x > 31 ? 1 : 0);
+            surf[(tz + 1) * kSurfStride + x + 1] = w.surface[((int64_t)(cz + dcz) * w.size_x + cx + dcx) * 1024 + (tz & 31) * 32 + (x & 31)];
+        }
     LightGather lg;
-    lg.sun = w.sun; lg.light = w.light; lg.surf = surf.data(); lg.surf_x = surf_x.data();
+    lg.sun = w.sun; lg.light = w.light; lg.surf = surf.data();
     lg.own = (((int64_t)cz * w.size_x + cx) * 4 + cy) * 65536;
     lg.size_x = w.size_x; lg.cx = cx; lg.cy = cy; lg.cz = cz;
     const uint16_t* cb = w.blocks + (((int64_t)cz * w.size_x + cx) * 4 + cy) * 65536;
