@@ -279,8 +279,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 for (int j = 0; j < 8; j++) o[j] = rotl_bytes(o[j], unrot);
             }
             const int hr = hrow(ty, s - 1);
-#pragma unroll
-            for (int j = 0; j < 8; j++) s_planes[j * kHaloRows + hr] = o[j];
+            store_row_planes(s_planes, hr, o);
             return row_emit_mask(o);
         };
         // two voxel rows of slab s (ty = lane, lane + 32)
@@ -387,8 +386,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                     }
                     p1_class_row(q, row_uniformity(q), s_lut, out);
                 }
-#pragma unroll
-                for (int j = 0; j < 8; j++) s_planes[j * kHaloRows + hr] = out[j];
+                store_row_planes(s_planes, hr, out);
             }
         }
         else if (warp == kFetchWarp)
@@ -485,6 +483,15 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         }
         for (int layer = warp; layer < kTY; layer += kWarps)
         {
+            {
+                // a layer without a single emitting voxel (air above the terrain) has no faces
+                const Planes4 mv = planes_m(s_planes)[hrow(layer, lane)];
+                if (!__any_sync(0xffffffffu, ~(mv.y & mv.z & mv.w) != 0u))
+                {
+                    if (lane == 0) { s_layer_cnt[layer] = 0; s_layer_typa[layer] = 0; s_layer_typb[layer] = 0; }
+                    continue;
+                }
+            }
             RowFaces rf;
             p2_row_faces(s_planes, s_hx, layer, lane, rf);
             int c; uint32_t t4;
@@ -641,7 +648,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                         uint32_t* ip = idx_words + (size_t)(s_ctx->type_off[(e >> 19) & 7] + s_tlist[i]) * 3;
                         ip[0] = iw[0]; ip[1] = iw[1]; ip[2] = iw[2];
                         uint32_t v[12];
-                        p3b_quad(e, s_faces[e & 7], lg, s_planes + P_OPAQUE * kHaloRows, s_hx, s_mat[id], v);
+                        p3b_quad(e, s_faces[e & 7], lg, s_planes + 4 * kHaloRows, s_hx, s_mat[id], v);
                         uint4* dst = vtx + (size_t)rank * 3;
                         dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
                         dst[1] = make_uint4(v[4], v[5], v[6], v[7]);

@@ -8,7 +8,9 @@
 //
 // On-chip form of one chunk + 1-voxel halo (tile cell (x,ty,tz), x in -1..32, ty in -1..64, tz in -1..32):
 //   row index      hr(ty,tz) = (ty+1)*34 + (tz+1)                      2244 rows, z fastest
-//   planes[k][hr]  uint32, bit x = class bit k of cell (x,ty,tz), x in 0..31
+//   planes         two arrays of 16-byte records, one record per row: G[hr] = {plane 0..3}, M[hr] = {plane 4..7} (M follows G),
+//                  so a row's four cull planes (or opaque + type planes) move as one 128-bit shared-memory access;
+//                  plane word k: bit x = class bit k of cell (x,ty,tz), x in 0..31
 //                  k: 0..3 = cull >= 1..4 (thermometer code of CullValue, Block.h:40-47)
 //                     4    = opaque (Block.cpp:65-68)
 //                     5..7 = mesh type bits (Mesh.h:8-16); 7 (all ones) = never emits (AIR / invisible)
@@ -41,6 +43,16 @@ constexpr int kNoEmitType = 7;
 enum { P_G1 = 0, P_G2 = 1, P_G3 = 2, P_G4 = 3, P_OPAQUE = 4, P_M0 = 5, P_M1 = 6, P_M2 = 7 };
 
 GC_HD int hrow(int ty, int tz) { return (ty + 1) * kRowsZ + (tz + 1); }
+
+struct alignas(16) Planes4 { uint32_t x, y, z, w; };
+constexpr int kPlaneWords = kPlanes * kHaloRows;                     // the whole tile, in 32-bit words
+GC_HD const Planes4* planes_g(const uint32_t* planes) { return reinterpret_cast<const Planes4*>(planes); }
+GC_HD const Planes4* planes_m(const uint32_t* planes) { return reinterpret_cast<const Planes4*>(planes) + kHaloRows; }
+GC_HD void store_row_planes(uint32_t* planes, int hr, const uint32_t o[8])
+{
+    reinterpret_cast<Planes4*>(planes)[hr] = Planes4{ o[0], o[1], o[2], o[3] };
+    reinterpret_cast<Planes4*>(planes)[kHaloRows + hr] = Planes4{ o[4], o[5], o[6], o[7] };
+}
 
 // ---- small portable intrinsics ----
 GC_HD int popc(uint32_t v)
@@ -258,20 +270,18 @@ GC_HD uint32_t lt_mask(const uint32_t g[4], uint32_t n0, uint32_t n1, uint32_t n
 GC_HD void p2_row_faces(const uint32_t* planes, const uint16_t* hx, int ty, int tz, RowFaces& r)
 {
     const int hr = hrow(ty, tz);
-    uint32_t g[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) g[k] = planes[k * kHaloRows + hr];
-    r.m0 = planes[P_M0 * kHaloRows + hr];
-    r.m1 = planes[P_M1 * kHaloRows + hr];
-    r.m2 = planes[P_M2 * kHaloRows + hr];
+    const Planes4* G = planes_g(planes);
+    const Planes4 gv = G[hr], mv = planes_m(planes)[hr];
+    const uint32_t g[4] = { gv.x, gv.y, gv.z, gv.w };
+    r.m0 = mv.y; r.m1 = mv.z; r.m2 = mv.w;
     const uint32_t vis = ~(r.m0 & r.m1 & r.m2);
     const uint32_t h = hx[hr];
 
-    const int up = hr + kRowsZ, dn = hr - kRowsZ, fr = hr + 1, bk = hr - 1;
-    r.f[0] = vis & lt_mask(g, planes[up], planes[kHaloRows + up], planes[2 * kHaloRows + up], planes[3 * kHaloRows + up]);
-    r.f[1] = vis & lt_mask(g, planes[dn], planes[kHaloRows + dn], planes[2 * kHaloRows + dn], planes[3 * kHaloRows + dn]);
-    r.f[2] = vis & lt_mask(g, planes[fr], planes[kHaloRows + fr], planes[2 * kHaloRows + fr], planes[3 * kHaloRows + fr]);
-    r.f[3] = vis & lt_mask(g, planes[bk], planes[kHaloRows + bk], planes[2 * kHaloRows + bk], planes[3 * kHaloRows + bk]);
+    const Planes4 up = G[hr + kRowsZ], dn = G[hr - kRowsZ], fr = G[hr + 1], bk = G[hr - 1];
+    r.f[0] = vis & lt_mask(g, up.x, up.y, up.z, up.w);
+    r.f[1] = vis & lt_mask(g, dn.x, dn.y, dn.z, dn.w);
+    r.f[2] = vis & lt_mask(g, fr.x, fr.y, fr.z, fr.w);
+    r.f[3] = vis & lt_mask(g, bk.x, bk.y, bk.z, bk.w);
     // +x neighbour of voxel x is voxel x+1 (bit x+1), voxel 31's is the x = 32 halo cell (hx high byte)
     r.f[4] = vis & lt_mask(g, (g[0] >> 1) | (((h >> 8) & 1u) << 31), (g[1] >> 1) | (((h >> 9) & 1u) << 31),
                            (g[2] >> 1) | (((h >> 10) & 1u) << 31), (g[3] >> 1) | (((h >> 11) & 1u) << 31));
@@ -384,10 +394,11 @@ struct MatEntry { uint32_t lo, hi; };
 GC_HD uint32_t unpack_light(uint32_t b) { return (b & 15u) | ((b >> 4) << 16); }
 
 // opaque bit of cell (x, row hr), x in -1..32
+// (plane_o points at the M records: the opaque word of row hr is plane_o[hr * 4])
 GC_HD uint32_t opaque_at(const uint32_t* plane_o, const uint16_t* hx, int hr, int x)
 {
     const uint32_t h = hx[hr];
-    const uint64_t w = ((uint64_t)plane_o[hr] << 1) | ((h >> P_OPAQUE) & 1u) | ((uint64_t)((h >> (8 + P_OPAQUE)) & 1u) << 33);
+    const uint64_t w = ((uint64_t)plane_o[hr * 4] << 1) | ((h >> P_OPAQUE) & 1u) | ((uint64_t)((h >> (8 + P_OPAQUE)) & 1u) << 33);
     return (uint32_t)(w >> (x + 1)) & 1u;
 }
 
@@ -527,8 +538,8 @@ GC_HD void p3b_quad(uint32_t entry, const FacePlan& f, const LightGather& g, con
     if ((unsigned)(ax - 1) < 30u)
     {
         // x in 1..30: no edge cell touches the x halo
-        o_um = (plane_o[hr_a - hr_u] >> (ax - ux)) & 1u; o_up = (plane_o[hr_a + hr_u] >> (ax + ux)) & 1u;
-        o_vm = (plane_o[hr_a - hr_v] >> (ax - vx)) & 1u; o_vp = (plane_o[hr_a + hr_v] >> (ax + vx)) & 1u;
+        o_um = (plane_o[(hr_a - hr_u) * 4] >> (ax - ux)) & 1u; o_up = (plane_o[(hr_a + hr_u) * 4] >> (ax + ux)) & 1u;
+        o_vm = (plane_o[(hr_a - hr_v) * 4] >> (ax - vx)) & 1u; o_vp = (plane_o[(hr_a + hr_v) * 4] >> (ax + vx)) & 1u;
     }
     else
     {

@@ -47,7 +47,8 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
         mat[i].hi = b.textures[4] | (b.textures[5] << 8) | (b.alpha << 16);
     }
 
-    std::vector<uint32_t> planes((size_t)kPlanes * kHaloRows, 0xDEADBEEFu);
+    std::vector<uint32_t> planes_store((size_t)kPlaneWords + 4, 0xDEADBEEFu);
+    struct AlignedView { uint32_t* p; uint32_t* data() { return p; } } planes{ (uint32_t*)(((uintptr_t)planes_store.data() + 15) & ~(uintptr_t)15) };
     std::vector<uint16_t> hx(kHaloRows, 0xFFFF);
     uint8_t* hx_b = (uint8_t*)hx.data();
 
@@ -66,7 +67,7 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
             {
                 uint32_t out[8];
                 p1_class_row_const(wy < 0 ? cls8[kill_zone] : cls8[0], out);
-                for (int k = 0; k < 8; k++) planes[k * kHaloRows + hr] = out[k];
+                store_row_planes(planes.data(), hr, out);
                 continue;
             }
             int64_t base = (col * 4 + (wy >> 6)) * 65536 + 32 * ((wy & 63) + 64 * zz);
@@ -83,7 +84,8 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
                 }
                 uint32_t out[8];
                 p1_class_row(q, row_uniformity(q), lut.data(), out);
-                for (int k = 0; k < 8; k++) { out[k] = rotl_bytes(out[k], rot_selector(rot)); planes[k * kHaloRows + hr] = out[k]; }
+                for (int k = 0; k < 8; k++) out[k] = rotl_bytes(out[k], rot_selector(rot));
+                store_row_planes(planes.data(), hr, out);
                 uint32_t vis = centre ? row_emit_mask(out) : 0u;
                 const int sl = tz + 1;
                 if (vis & 1u) bvm[(ty + 1) * 2 + (sl >> 5)] |= 1u << (sl & 31);
@@ -167,7 +169,7 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
         int x = (e >> 3) & 31, tz = (e >> 8) & 31, ty = (e >> 13) & 63;
         uint32_t id = cb[x + 32 * (ty + 64 * tz)] & 255u;
         uint32_t v[12], iw[3];
-        p3b_quad(e, make_face_plan(kFaces[e & 7]), lg, planes.data() + P_OPAQUE * kHaloRows, hx.data(), mat[id], v);
+        p3b_quad(e, make_face_plan(kFaces[e & 7]), lg, planes.data() + 4 * kHaloRows, hx.data(), mat[id], v);
         memcpy(verts_out + (size_t)i * 48, v, 48);
         quad_index_words(i, iw);
         memcpy((uint32_t*)idx_out + (size_t)(type_off[(e >> 19) & 7] + tlist[i]) * 3, iw, 12);
