@@ -289,6 +289,8 @@ int gcmesh_synchronize(GcContext* ctx)
     if (!ctx) return fail(GC_ERR_ARG, "ctx is null");
     GC_CUDA(cudaSetDevice(ctx->device));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
+    GC_CUDA(cudaStreamSynchronize(ctx->upload_stream));
+    GC_CUDA(cudaStreamSynchronize(ctx->download_stream));
     return GC_OK;
 }
 
@@ -595,13 +597,14 @@ int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBa
     if (e == cudaSuccess) e = cudaMalloc(&b->d_out, sizeof(GcChunkOut) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_vertices, (size_t)max_quads * 48);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_indices, (size_t)max_quads * 12);
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_cursor, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_counters, sizeof(int32_t) * 2);
+    // one 16-byte control block {quad cursor, work counter, error flag}: one memset and one read-back per submission
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_cursor, 16);
+    if (e == cudaSuccess) b->d_counters = reinterpret_cast<int32_t*>(b->d_cursor + 1);
     if (e == cudaSuccess && getenv("GCMESH_PROFILE")) e = cudaMalloc(&b->d_prof, sizeof(unsigned long long) * 512);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_out, sizeof(GcChunkOut) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_coords, sizeof(GcChunkCoord) * (size_t)max_chunks);
-    if (e == cudaSuccess) e = cudaMallocHost(&b->h_cursor, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMallocHost(&b->h_counters, sizeof(int32_t) * 2);
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_cursor, 16);
+    if (e == cudaSuccess) b->h_counters = reinterpret_cast<int32_t*>(b->h_cursor + 1);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_start);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_stop);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
@@ -616,11 +619,11 @@ int gcmesh_batch_destroy(GcBatch* b)
     if (!b) return GC_OK;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    cudaFree(b->d_coords); cudaFree(b->d_out); cudaFree(b->d_vertices); cudaFree(b->d_indices); cudaFree(b->d_cursor); cudaFree(b->d_counters); cudaFree(b->d_prof);
+    cudaStreamSynchronize(b->ctx->download_stream);
+    cudaFree(b->d_coords); cudaFree(b->d_out); cudaFree(b->d_vertices); cudaFree(b->d_indices); cudaFree(b->d_cursor); cudaFree(b->d_prof);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_coords) cudaFreeHost(b->h_coords);
     if (b->h_cursor) cudaFreeHost(b->h_cursor);
-    if (b->h_counters) cudaFreeHost(b->h_counters);
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     if (b->ev_stop) cudaEventDestroy(b->ev_stop);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
@@ -642,10 +645,10 @@ static int validate_coords(const GcWorld* w, const GcChunkCoord* coords, int n)
 }
 
 // Launch the mesh kernel over d_coords[first, first + count) on stream s; descriptors go to d_out[first ...].
-static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cudaStream_t s)
+static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cudaStream_t s, bool reset_work_counter = true)
 {
     GcContext* ctx = w->ctx;
-    cudaError_t e = cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t), s);   // work counter (the error flag persists)
+    cudaError_t e = reset_work_counter ? cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t), s) : cudaSuccess;   // (the error flag persists)
     if (e != cudaSuccess || count <= 0) return e;
     MeshParams p;
     p.blocks = w->d_blocks; p.sun = w->d_sun; p.light = w->d_light; p.surface = w->d_surface;
@@ -678,17 +681,18 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
     cudaStream_t s = ctx->stream;
     GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, s));
     GC_CUDA(cudaEventRecord(b->ev_coords, s));
-    GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), s));
-    GC_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t) * 2, s));
+    GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, 16, s));
     if (b->d_prof) GC_CUDA(cudaMemsetAsync(b->d_prof, 0, sizeof(unsigned long long) * 512, s));
     GC_CUDA(cudaEventRecord(b->ev_start, s));
-    GC_CUDA(launch_range(w, b, 0, n, s));
+    GC_CUDA(launch_range(w, b, 0, n, s, false));
     GC_CUDA(cudaEventRecord(b->ev_stop, s));
-    GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, s));
-    GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    GC_CUDA(cudaMemcpyAsync(b->h_counters, b->d_counters, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, s));
-    if (b->d_prof) GC_CUDA(cudaMemcpyAsync(b->h_prof, b->d_prof, sizeof(unsigned long long) * 512, cudaMemcpyDeviceToHost, s));
-    GC_CUDA(cudaEventRecord(b->ev_done, s));
+    // the descriptors travel back on the download stream: the context stream is free for the next submission's kernel
+    cudaStream_t sd = ctx->download_stream;
+    GC_CUDA(cudaStreamWaitEvent(sd, b->ev_stop, 0));
+    GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, sd));
+    GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, 16, cudaMemcpyDeviceToHost, sd));
+    if (b->d_prof) GC_CUDA(cudaMemcpyAsync(b->h_prof, b->d_prof, sizeof(unsigned long long) * 512, cudaMemcpyDeviceToHost, sd));
+    GC_CUDA(cudaEventRecord(b->ev_done, sd));
     b->state = 1;
     return GC_OK;
 }
@@ -732,8 +736,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     GC_CUDA(cudaStreamWaitEvent(sd, ctx->ev_fork, 0));
     GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, su));
     GC_CUDA(cudaMemcpyAsync(w->d_surface, surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyHostToDevice, su));
-    GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), su));
-    GC_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t) * 2, su));
+    GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, 16, su));
     GC_CUDA(cudaEventRecord(b->ev_start, sm));
 
     unsigned long long* cursors = ctx->h_strip_cursor;        // pinned: arena cursor after each strip's kernel
@@ -816,8 +819,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     { const int st = mesh_strip(n_strips - 1); if (st != GC_OK) return st; }
     GC_CUDA(cudaEventRecord(b->ev_stop, sm));
     GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, sm));
-    GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm));
-    GC_CUDA(cudaMemcpyAsync(b->h_counters, b->d_counters, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, sm));
+    GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, 16, cudaMemcpyDeviceToHost, sm));
     if (n_strips >= 2) { const int st = read_back(n_strips - 2); if (st != GC_OK) return st; }
     { const int st = read_back(n_strips - 1); if (st != GC_OK) return st; }
     GC_CUDA(cudaEventRecord(ctx->ev_join, sd));
