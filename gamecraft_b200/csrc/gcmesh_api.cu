@@ -216,9 +216,6 @@ int gcmesh_create(int device, void* stream, GcContext** out)
     ctx->stream = (cudaStream_t)stream;
     const char* env = getenv("GCMESH_NO_TMA");
     ctx->use_tma = (env && env[0] == '1') ? 0 : 1;
-    const char* bulk = getenv("GCMESH_BULK");
-    if (ctx->use_tma && bulk && bulk[0] == '1') ctx->use_tma = 2;
-    if (ctx->use_tma && bulk && bulk[0] == '3') ctx->use_tma = 3;   // timing experiment only (wrong results)   // contiguous slabs by cp.async.bulk instead of tensor-map boxes
     if (ctx->own_stream) { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); if (e != cudaSuccess) { delete ctx; return fail(GC_ERR_CUDA, "cudaStreamCreate", cudaGetErrorString(e)); } }
 
     void* fn = nullptr;
@@ -322,8 +319,6 @@ int gcmesh_world_create(GcContext* ctx, int size_x, int size_z, GcWorld** out)
     if (!w->slot_dirty || !w->scan_flags) { gcmesh_world_destroy(w); return fail(GC_ERR_ARG, "out of host memory"); }
     int st = GC_OK;
     if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_slab, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.sun_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_sun, w->n_slots);
-    if (st == GC_OK) st = encode_map(ctx, &w->maps.light_slab, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->d_light, w->n_slots);
     if (st != GC_OK) { gcmesh_world_destroy(w); return st; }
     *out = w;
     return GC_OK;

@@ -40,11 +40,11 @@ struct MeshParams
     unsigned long long* prof;          // optional: 512 cycle counters (phase / wait attribution), null = off
 };
 
-// Three tensor maps, one per brick arena (blocks / sunlight / blockLight), each viewing the arena as
-// (256, 8, z = 32, slot) so that one box (256, 8, 1, 1) is one whole z-slab of a brick (32 x 64 voxels).
+// The block-id arena viewed as (256, 8, z = 32, slot): one box (256, 8, 1, 1) is one whole z-slab of a brick
+// (32 x 64 voxels, 4 KB contiguous).  The light arenas need no map: light is gathered per quad, never staged.
 struct MeshTensorMaps
 {
-    CUtensorMap blocks_slab, sun_slab, light_slab;
+    CUtensorMap blocks_slab;
 };
 
 #ifndef GCMESH_THREADS
