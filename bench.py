@@ -250,6 +250,7 @@ def main():
         probe.submit(world, coords).wait()
         desc, _ = probe.results()
     flags_bad = int((desc["flags"] != 0).sum())
+    desc = desc.copy()                                   # (a view of the batch's pinned memory until here)
     probe.close()
     batch = mesher.Batch(ctx, n, total_quads + 1)
 

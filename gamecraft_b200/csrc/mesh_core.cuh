@@ -242,12 +242,14 @@ GC_HD uint64_t xhalo_needed_mask(const uint32_t* bvm, int ty)   // bit tz + 1 = 
 }
 GC_HD uint32_t xhalo_needed(const uint32_t* bvm, int ty, int tz) { return (uint32_t)(xhalo_needed_mask(bvm, ty) >> (tz + 1)) & 1u; }
 
-GC_HD uint32_t light_byte_of(uint32_t sun, uint32_t bl, uint32_t surf, int wy)
+// One cell's light as the packed pair VertexLight sums, blockLight | sun' << 16, with GetSunlight's rules
+// (Lighting.cpp:69-79): sun' = 15 at or above the column's surface, else the stored value with 0 read as MIN_LIGHT = 1
+GC_HD uint32_t light_pair_of(uint32_t sun, uint32_t bl, uint32_t surf, int wy)
 {
     uint32_t s = sun & 15u;
     if (s == 0) s = 1;
     if ((uint32_t)wy >= surf) s = 15;
-    return (s << 4) | (bl & 15u);
+    return (bl & 15u) | (s << 16);
 }
 
 // =====================================================================================================
@@ -390,9 +392,6 @@ struct FaceDesc
 // material word of a block type: bytes 0..5 texture layer per face, byte 6 alpha
 struct MatEntry { uint32_t lo, hi; };
 
-// light byte -> packed (blockLight | sun << 16)
-GC_HD uint32_t unpack_light(uint32_t b) { return (b & 15u) | ((b >> 4) << 16); }
-
 // opaque bit of cell (x, row hr), x in -1..32
 // (plane_o points at the M records: the opaque word of row hr is plane_o[hr * 4])
 GC_HD uint32_t opaque_at(const uint32_t* plane_o, const uint16_t* hx, int hr, int x)
@@ -438,16 +437,16 @@ GC_HD uint32_t load_u8(const uint8_t* p)
 // voxel offset of tile coordinate x in -1..32 relative to the start of its row in the chunk's own brick
 GC_HD int x_term(int x) { return (x < 0 ? -kColumnVoxels : (x > 31 ? kColumnVoxels : 0)) + (x & 31); }
 
-// any cell of the halo tile (slow path: picks the neighbour brick / column)
+// any cell of the halo tile as blockLight | sun' << 16 (slow path: picks the neighbour brick / column)
 GC_HD uint32_t gather_cell(const LightGather& g, int x, int ty, int tz)
 {
     const int wy = g.cy * kTY + ty;
-    if (wy < 0) return 0x00u;
-    if (wy >= 4 * kTY) return 0xFFu;
+    if (wy < 0) return 0u;                       // (0, 0, 0, 0) below the world
+    if (wy >= 4 * kTY) return 0x000F000Fu;       // full light above it
     const int dcx = x < 0 ? -1 : (x > 31 ? 1 : 0), dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
     const long long slot = ((long long)(g.cz + dcz) * g.size_x + (g.cx + dcx)) * 4 + (wy >> 6);
     const long long vox = slot * (kTX * kTY * kTZ) + (x & 31) + 32 * ((wy & 63) + 64 * (tz & 31));
-    return light_byte_of(load_u8(g.sun + vox), load_u8(g.light + vox), g.surf[(tz + 1) * kSurfStride + x + 1], wy);
+    return light_pair_of(load_u8(g.sun + vox), load_u8(g.light + vox), g.surf[(tz + 1) * kSurfStride + x + 1], wy);
 }
 
 // A face's geometry pre-digested for p3b_quad (built once per face from FaceDesc):
@@ -520,11 +519,11 @@ GC_HD void p3b_quad(uint32_t entry, const FacePlan& f, const LightGather& g, con
         const uint32_t smm = load_u8(ps + om - dv), smp = load_u8(ps + om + dv), spm = load_u8(ps + op - dv), spp = load_u8(ps + op + dv);
         const uint32_t b00 = load_u8(pl + o0), bm0 = load_u8(pl + om), bp0 = load_u8(pl + op), b0m = load_u8(pl + o0 - dv), b0p = load_u8(pl + o0 + dv);
         const uint32_t bmm = load_u8(pl + om - dv), bmp = load_u8(pl + om + dv), bpm = load_u8(pl + op - dv), bpp = load_u8(pl + op + dv);
-        l00 = light_byte_of(s00, b00, sf[g0], wy);
-        lm0 = light_byte_of(sm0, bm0, sf[gm], wy - uy); lp0 = light_byte_of(sp0, bp0, sf[gp], wy + uy);
-        l0m = light_byte_of(s0m, b0m, sf[g0 - fv], wy - vy); l0p = light_byte_of(s0p, b0p, sf[g0 + fv], wy + vy);
-        lmm = light_byte_of(smm, bmm, sf[gm - fv], wy - uy - vy); lmp = light_byte_of(smp, bmp, sf[gm + fv], wy - uy + vy);
-        lpm = light_byte_of(spm, bpm, sf[gp - fv], wy + uy - vy); lpp = light_byte_of(spp, bpp, sf[gp + fv], wy + uy + vy);
+        l00 = light_pair_of(s00, b00, sf[g0], wy);
+        lm0 = light_pair_of(sm0, bm0, sf[gm], wy - uy); lp0 = light_pair_of(sp0, bp0, sf[gp], wy + uy);
+        l0m = light_pair_of(s0m, b0m, sf[g0 - fv], wy - vy); l0p = light_pair_of(s0p, b0p, sf[g0 + fv], wy + vy);
+        lmm = light_pair_of(smm, bmm, sf[gm - fv], wy - uy - vy); lmp = light_pair_of(smp, bmp, sf[gm + fv], wy - uy + vy);
+        lpm = light_pair_of(spm, bpm, sf[gp - fv], wy + uy - vy); lpp = light_pair_of(spp, bpp, sf[gp + fv], wy + uy + vy);
     }
     else
     {
@@ -546,8 +545,6 @@ GC_HD void p3b_quad(uint32_t entry, const FacePlan& f, const LightGather& g, con
         o_um = opaque_at(plane_o, hx, hr_a - hr_u, ax - ux); o_up = opaque_at(plane_o, hx, hr_a + hr_u, ax + ux);
         o_vm = opaque_at(plane_o, hx, hr_a - hr_v, ax - vx); o_vp = opaque_at(plane_o, hx, hr_a + hr_v, ax + vx);
     }
-    l00 = unpack_light(l00); lm0 = unpack_light(lm0); lp0 = unpack_light(lp0); l0m = unpack_light(l0m); l0p = unpack_light(l0p);
-    lmm = unpack_light(lmm); lmp = unpack_light(lmp); lpm = unpack_light(lpm); lpp = unpack_light(lpp);
 
     const uint32_t tex = (d < 4 ? (mat.lo >> (8 * d)) : (mat.hi >> (8 * (d - 4)))) & 255u;
     const uint32_t w1c = tex << 8, w2c = ((mat.hi >> 16) & 255u) << 16;   // constant parts of vertex words 1 and 2
