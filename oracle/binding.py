@@ -97,6 +97,9 @@ def oracle_lib() -> ctypes.CDLL:
         L.gcor_fnv1a64.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
         L.gcor_fnv1a64.restype = ctypes.c_uint64
         L.gcor_default_block_table.argtypes = [ctypes.POINTER(BlockInfo), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+        L.gcor_compute_surface.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.gcor_light_fill.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6
+        L.gcor_default_light_rules.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         _olib = L
     return _olib
 
@@ -110,6 +113,7 @@ def ref_lib() -> ctypes.CDLL:
         L.gcref_world_destroy.argtypes = [ctypes.c_void_p]
         L.gcref_block_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.gcref_block_light_steps.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.gcref_block_light_emitted.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.gcref_set_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.gcref_get_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.gcref_set_surface.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
@@ -124,6 +128,32 @@ def ref_lib() -> ctypes.CDLL:
         L.gcref_bench_build.restype = ctypes.c_double
         _rlib = L
     return _rlib
+
+
+def default_light_rules():
+    """(step u8[256] with 255 = opaque, emitted u8[256]) as restated in gc_light_cpu.c from Code/Block.cpp:139-276."""
+    step, emitted = np.zeros(256, np.uint8), np.zeros(256, np.uint8)
+    oracle_lib().gcor_default_light_rules(step.ctypes.data, emitted.ctypes.data)
+    return step, emitted
+
+
+def compute_surface(host) -> np.ndarray:
+    """gcor_compute_surface over a HostWorld's blocks -> a new surface array shaped like host.surface."""
+    out = np.zeros_like(host.surface)
+    oracle_lib().gcor_compute_surface(host.size_x, host.size_z, host.blocks.ctypes.data, out.ctypes.data)
+    return out
+
+
+def light_fill(host, surface=None, step=None, emitted=None):
+    """gcor_light_fill over a HostWorld's blocks (+ surface) -> (sun, light) arrays shaped like host.sun / host.light."""
+    if step is None:
+        step, emitted = default_light_rules()
+    surface = host.surface if surface is None else surface
+    sun, light = np.zeros_like(host.sun), np.zeros_like(host.light)
+    oracle_lib().gcor_light_fill(host.size_x, host.size_z, host.blocks.ctypes.data, np.ascontiguousarray(surface).ctypes.data,
+                                 np.ascontiguousarray(step, np.uint8).ctypes.data, np.ascontiguousarray(emitted, np.uint8).ctypes.data,
+                                 sun.ctypes.data, light.ctypes.data)
+    return sun, light
 
 
 def default_block_table():
@@ -228,6 +258,11 @@ class RefWorld:
     def light_steps(self):
         out = np.zeros(24, np.int32)
         self.L.gcref_block_light_steps(self.h, out.ctypes.data)
+        return out
+
+    def light_emitted(self):
+        out = np.zeros(24, np.int32)
+        self.L.gcref_block_light_emitted(self.h, out.ctypes.data)
         return out
 
     def build_chunk(self, cx, cy, cz) -> Mesh:

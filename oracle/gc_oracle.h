@@ -78,6 +78,15 @@ int gcor_build_chunk(const GcOrWorld* w, int cx, int cy, int cz, GcOrMesh* out);
 int gcor_chunk_overflowed(const GcOrWorld* w, int cx, int cy, int cz, int x, int y, int z, int total_vertices);
 /* One-chunk-per-job pool (Async.cpp:5-35 restated as an atomic counter). Returns seconds. */
 double gcor_bench_build(const GcOrWorld* w, const int32_t* coords, int n, int threads, int64_t* quads_out);
+/* ---- column pre-processing (gc_light_cpu.c): the producers of the mesher's light inputs ---- */
+/* ComputeSurface (Lighting.cpp:5-26) over the whole window. */
+void gcor_compute_surface(int size_x, int size_z, const uint16_t* blocks, uint8_t* surface);
+/* SetLightNodes / ScatterSunlight / ScatterBlockLight (Lighting.cpp:28-281) over all non-edge columns, as the least
+ * fixpoint of the reference's push rule (block light: canonical max form, see gc_light_cpu.c).  step[id] = lightStep,
+ * 255 = opaque; emitted[id] = lightEmitted.  sun / light (whole-window arenas) are overwritten. */
+void gcor_light_fill(int size_x, int size_z, const uint16_t* blocks, const uint8_t* surface, const uint8_t* step, const uint8_t* emitted,
+                     uint8_t* sun, uint8_t* light);
+void gcor_default_light_rules(uint8_t* step, uint8_t* emitted);
 /* FNV-1a-64 over bytes (used for golden digests). */
 uint64_t gcor_fnv1a64(const void* data, uint64_t n, uint64_t h);
 

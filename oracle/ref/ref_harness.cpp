@@ -221,6 +221,11 @@ void gcref_block_light_steps(GcRefWorld* w, int32_t* out)
     for (int b = 0; b < BLOCK_COUNT; b++) out[b] = w->world->blockData[b].lightStep;
 }
 
+void gcref_block_light_emitted(GcRefWorld* w, int32_t* out)
+{
+    for (int b = 0; b < BLOCK_COUNT; b++) out[b] = w->world->blockData[b].lightEmitted;
+}
+
 void gcref_set_chunk(GcRefWorld* w, int cx, int cy, int cz, const uint16_t* blocks, const uint8_t* sun, const uint8_t* light)
 {
     Chunk* c = RefGroup(w, cx, cz)->chunks + cy;
