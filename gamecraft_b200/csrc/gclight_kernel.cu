@@ -1,0 +1,238 @@
+// gclight — surface map and light flood fill on the device (see gclight_kernel.cuh).
+//
+// The reference fills light with two FIFO queues per column (Lighting.cpp:109-143, 195-229).  What the queues compute
+// is the least fixpoint of one push rule — a cell v offers  l = value(v) - lightStep[block(v)]  to each in-window,
+// in-height neighbour whose block is not opaque, accepted when l > MIN_LIGHT and l > the neighbour's value — so the
+// device runs it as an in-place relaxation over the cells that can change at all:
+//   sunlight    candidates = non-opaque cells below their column's surface; sources = the sky cells (read as 15,
+//               Lighting.cpp:69-79) of the pre-processed (non-edge) columns
+//   blockLight  seeds = emitters of the pre-processed columns up to maxY (Lighting.cpp:231-281); candidates = the
+//               non-opaque cells of the bricks within one brick of a seed (light travels < 15 voxels)
+// A value falls by at least one per hop, so 14 sweeps reach the fixpoint whatever the order of the updates.
+// Canonical form of the reference's column-order dependent block-light seeding: see oracle/gc_light_cpu.c.
+#include "gclight_kernel.cuh"
+
+namespace gc
+{
+namespace
+{
+constexpr int kVox = GC_CHUNK_SIZE_3;
+
+__device__ __forceinline__ int surf_of(const LightWorld& w, int col, int x, int z) { return w.surface[(size_t)col * 1024 + z * 32 + x]; }
+
+// ---- ComputeSurface: one warp per (column, z) row, lanes = x; walks down from y = 254 until every lane has hit a block ----
+__global__ void __launch_bounds__(256) gc_surface_kernel(LightWorld w)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int n_rows = w.size_x * w.size_z * 32;
+    if (row >= n_rows) return;
+    const int col = row >> 5, z = row & 31;
+    int s = 0;
+    for (int y = GC_WORLD_BLOCK_HEIGHT - 2; y >= 0; y--)
+    {
+        const uint16_t id = w.blocks[((size_t)col * 4 + (y >> 6)) * kVox + lane + 32 * ((y & 63) + 64 * z)];
+        if (s == 0 && id != 0) s = y + 1;
+        if (__all_sync(0xffffffffu, s != 0)) break;
+    }
+    w.surface[(size_t)col * 1024 + z * 32 + lane] = (uint8_t)s;
+}
+
+// ---- scan of every column cell up to maxY ----
+template <bool kFill>
+__global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32_t* sun_list, uint8_t* brick_flags, uint32_t* counters)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int n_rows = w.size_x * w.size_z * 32;
+    if (row >= n_rows) return;
+    const int col = row >> 5, z = row & 31, x = lane;
+    const int cx = col % w.size_x, cz = col / w.size_x;
+    const bool inner = cx >= 1 && cx < w.size_x - 1 && cz >= 1 && cz < w.size_z - 1;   // pre-processed columns (SetLightNodes)
+    const int s = surf_of(w, col, x, z);
+    // ComputeMaxY (Lighting.cpp:28-67); edge columns are never seeded, their cells only receive
+    int my = s;
+    if (inner)
+    {
+        const int sf = z < 31 ? surf_of(w, col, x, z + 1) : surf_of(w, col + w.size_x, x, 0);
+        const int sb = z > 0 ? surf_of(w, col, x, z - 1) : surf_of(w, col - w.size_x, x, 31);
+        const int sl = x > 0 ? surf_of(w, col, x - 1, z) : surf_of(w, col - 1, 31, z);
+        const int sr = x < 31 ? surf_of(w, col, x + 1, z) : surf_of(w, col + 1, 0, z);
+        my = max(max(max(my, sf), max(sb, sl)), sr);
+        if (my > GC_WORLD_BLOCK_HEIGHT - 1) my = GC_WORLD_BLOCK_HEIGHT - 1;
+    }
+    // candidates lie below the own surface; seeds up to maxY
+    const int top = inner ? my : s - 1;
+    int top_w = top;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) top_w = max(top_w, __shfl_xor_sync(0xffffffffu, top_w, d));
+    uint32_t count = 0;
+    for (int y = 0; y <= top_w; y++)
+    {
+        const size_t slot = (size_t)col * 4 + (y >> 6);
+        const uint32_t v = (uint32_t)(slot * kVox + x + 32 * ((y & 63) + 64 * z));
+        const uint32_t id = w.blocks[v] & 255u;
+        const bool cand = y < s && w.rules->step[id] != 255;
+        if (kFill)
+        {
+            const uint32_t m = __ballot_sync(0xffffffffu, cand);
+            if (m)
+            {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&counters[LC_SUN_CAND], (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (cand) sun_list[base + __popc(m & ((1u << lane) - 1u))] = v;
+            }
+            const uint32_t e = w.rules->emitted[id];
+            if (inner && y <= my && e > 1)   // CheckForBlockLight (Lighting.cpp:231-245); the arrays were cleared, so this is a max
+            {
+                w.light[v] = (uint8_t)e;
+                brick_flags[slot] = 1;
+                atomicAdd(&counters[LC_SEEDS], 1u);
+            }
+        }
+        else count += cand ? 1u : 0u;
+    }
+    if (!kFill)
+    {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) count += __shfl_xor_sync(0xffffffffu, count, d);
+        if (lane == 0 && count) atomicAdd(&counters[LC_SUN_CAND], count);
+    }
+}
+
+__global__ void gc_active_bricks_kernel(LightWorld w, const uint8_t* brick_flags, uint32_t* active_list, uint32_t* counters)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_slots = w.size_x * w.size_z * 4;
+    if (slot >= n_slots) return;
+    const int col = slot >> 2, cy = slot & 3, cx = col % w.size_x, cz = col / w.size_x;
+    bool on = false;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dx = -1; dx <= 1; dx++)
+            for (int dy = -1; dy <= 1; dy++)
+            {
+                const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+                if (nx < 0 || nx >= w.size_x || nz < 0 || nz >= w.size_z || ny < 0 || ny > 3) continue;
+                on |= brick_flags[((size_t)nz * w.size_x + nx) * 4 + ny] != 0;
+            }
+    if (on) active_list[atomicAdd(&counters[LC_ACTIVE_BRICKS], 1u)] = (uint32_t)slot;
+}
+
+template <bool kFill>
+__global__ void __launch_bounds__(256) gc_light_candidates_kernel(LightWorld w, const uint32_t* active_list, uint32_t* light_list, uint32_t* counters)
+{
+    const uint32_t slot = active_list[blockIdx.x];
+    const int lane = threadIdx.x & 31;
+    uint32_t count = 0;
+    for (int i = threadIdx.x; i < kVox; i += blockDim.x)
+    {
+        const uint32_t v = slot * (uint32_t)kVox + (uint32_t)i;
+        const bool cand = w.rules->step[w.blocks[v] & 255u] != 255;
+        if (kFill)
+        {
+            const uint32_t m = __ballot_sync(0xffffffffu, cand);
+            if (m)
+            {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&counters[LC_LIGHT_CAND], (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (cand) light_list[base + __popc(m & ((1u << lane) - 1u))] = v;
+            }
+        }
+        else count += cand ? 1u : 0u;
+    }
+    if (!kFill)
+    {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) count += __shfl_xor_sync(0xffffffffu, count, d);
+        if (lane == 0 && count) atomicAdd(&counters[LC_LIGHT_CAND], count);
+    }
+}
+
+// ---- one relaxation sweep ----
+template <bool kSun>
+__global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint32_t* __restrict__ list, uint32_t n, uint32_t* counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = list[i];
+    uint8_t* arr = kSun ? w.sun : w.light;
+    const int cur = arr[v];
+    const uint32_t slot = v >> 16, in = v & 65535u;
+    const int x = in & 31, y = (in >> 5) & 63, z = in >> 11;
+    const int col = slot >> 2, cy = slot & 3, cx = col % w.size_x, cz = col / w.size_x;
+    int best = cur;
+#pragma unroll
+    for (int d = 0; d < 6; d++)
+    {
+        // Utils.h:106-111 order is irrelevant here: the maximum over the six face neighbours
+        int nx = x, ny = y, nz = z, ncx = cx, ncy = cy, ncz = cz;
+        if (d == 0) { if (++ny > 63) { ny = 0; ncy++; } }
+        else if (d == 1) { if (--ny < 0) { ny = 63; ncy--; } }
+        else if (d == 2) { if (++nz > 31) { nz = 0; ncz++; } }
+        else if (d == 3) { if (--nz < 0) { nz = 31; ncz--; } }
+        else if (d == 4) { if (--nx < 0) { nx = 31; ncx--; } }
+        else { if (++nx > 31) { nx = 0; ncx++; } }
+        if (ncy < 0 || ncy > 3 || ncx < 0 || ncx >= w.size_x || ncz < 0 || ncz >= w.size_z) continue;   // world height / window edge
+        const int ncol = ncz * w.size_x + ncx;
+        const uint32_t nv = (uint32_t)(((size_t)ncol * 4 + ncy) * kVox + nx + 32 * (ny + 64 * nz));
+        const int st = w.rules->step[w.blocks[nv] & 255u];
+        if (st == 255) continue;                                  // opaque cells neither hold nor pass light
+        int val;
+        if (kSun && ncy * 64 + ny >= surf_of(w, ncol, nx, nz))
+        {
+            // a sky cell reads 15 (GetSunlight); only those of the pre-processed columns were ever queued (SetLightNodes)
+            if (ncx < 1 || ncx >= w.size_x - 1 || ncz < 1 || ncz >= w.size_z - 1) continue;
+            val = 15;
+        }
+        else val = arr[nv];                                       // (a stored 0 reads as MIN_LIGHT = 1: offers nothing either way)
+        best = max(best, val - st);
+    }
+    if (best > cur && best > 1)
+    {
+        arr[v] = (uint8_t)best;
+        counters[LC_CHANGED] = 1;
+    }
+}
+}  // namespace
+
+static int rows_grid(const LightWorld& w) { return (int)(((size_t)w.size_x * w.size_z * 32 * 32 + 255) / 256); }
+
+cudaError_t launch_surface(const LightWorld& w, cudaStream_t s)
+{
+    gc_surface_kernel<<<rows_grid(w), 256, 0, s>>>(w);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_light_scan(const LightWorld& w, bool fill, uint32_t* sun_list, uint8_t* brick_flags, uint32_t* counters, cudaStream_t s)
+{
+    if (fill) gc_light_scan_kernel<true><<<rows_grid(w), 256, 0, s>>>(w, sun_list, brick_flags, counters);
+    else gc_light_scan_kernel<false><<<rows_grid(w), 256, 0, s>>>(w, sun_list, brick_flags, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_active_bricks(const LightWorld& w, const uint8_t* brick_flags, uint32_t* active_list, uint32_t* counters, cudaStream_t s)
+{
+    const int n_slots = w.size_x * w.size_z * 4;
+    gc_active_bricks_kernel<<<(n_slots + 127) / 128, 128, 0, s>>>(w, brick_flags, active_list, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_light_candidates(const LightWorld& w, const uint32_t* active_list, int n_active, bool fill, uint32_t* light_list, uint32_t* counters, cudaStream_t s)
+{
+    if (n_active <= 0) return cudaSuccess;
+    if (fill) gc_light_candidates_kernel<true><<<n_active, 256, 0, s>>>(w, active_list, light_list, counters);
+    else gc_light_candidates_kernel<false><<<n_active, 256, 0, s>>>(w, active_list, light_list, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* counters, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (n + 255u) / 256u;
+    if (sun) gc_relax_kernel<true><<<grid, 256, 0, s>>>(w, list, n, counters);
+    else gc_relax_kernel<false><<<grid, 256, 0, s>>>(w, list, n, counters);
+    return cudaGetLastError();
+}
+}  // namespace gc

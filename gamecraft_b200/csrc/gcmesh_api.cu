@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "gcmesh_kernel.cuh"
+#include "gclight_kernel.cuh"
 
 using namespace gc;
 
@@ -83,6 +84,7 @@ struct GcContext
     int mesh_ctas;            // persistent mesh CTAs that fit the device at once (SMs x resident CTAs per SM)
     EncodeTiledFn encode;
     DeviceTables* d_tables;
+    LightRules* d_light_rules;
     int use_tma;
     // gcmesh_mesh_host pipeline
     cudaStream_t upload_stream, download_stream;
@@ -106,6 +108,14 @@ struct GcWorld
     uint32_t* h_items;        // pinned: work list of the upload kernel
     uint32_t* d_items;
     int launches;             // kernels launched by the last upload call
+    // light fill scratch (grown on demand)
+    uint32_t* d_light_counters;   // 8 x u32
+    uint32_t* h_light_counters;   // pinned
+    uint8_t* d_brick_flags;
+    uint32_t* d_active_list;
+    uint32_t* d_sun_list; size_t sun_list_cap;
+    uint32_t* d_light_list; size_t light_list_cap;
+    int light_launches; uint32_t light_stats[4];   // last gcmesh_world_light: sunlight candidates, blockLight candidates, active bricks, seeds
 };
 
 struct GcBatch
@@ -148,6 +158,30 @@ static int encode_map(GcContext* ctx, CUtensorMap* map, CUtensorMapDataType type
         snprintf(buf, sizeof(buf), "CUresult %d", (int)r);
         return fail(GC_ERR_CUDA, "cuTensorMapEncodeTiled", buf);
     }
+    return GC_OK;
+}
+
+// lightStep / lightEmitted of the reference's block table (Block.cpp:139-276); 255 = opaque (lightStep == INT_MAX)
+static void reference_light_rules(uint8_t* step, uint8_t* emitted)
+{
+    for (int i = 0; i < 256; i++) { step[i] = 255; emitted[i] = 0; }
+    step[0] = 1;                      // AIR        Block.cpp:146
+    step[8] = 2;                      // WATER      :167
+    step[13] = 2;                     // ICE        :211
+    step[14] = 1; emitted[14] = 15;   // LANTERN    :217-218
+    step[17] = 1; emitted[17] = 10;   // MAGMA      :235-236
+    step[20] = 1;                     // KILL_ZONE  :252
+    step[21] = 1; emitted[21] = 10;   // LAVA       :261-262
+    step[22] = 1;                     // GLASS      :272
+}
+
+static int upload_light_rules(GcContext* ctx, const uint8_t* step, const uint8_t* emitted)
+{
+    LightRules h;
+    memcpy(h.step, step, 256); memcpy(h.emitted, emitted, 256);
+    cudaError_t e = cudaMemcpyAsync(ctx->d_light_rules, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "upload light rules", cudaGetErrorString(e));
     return GC_OK;
 }
 
@@ -239,7 +273,12 @@ int gcmesh_create(int device, void* stream, GcContext** out)
     GcBlockInfo table[24];
     reference_block_table(table);
     int st = upload_tables(ctx, table, 24, 20);
-    if (st != GC_OK) { cudaFree(ctx->d_tables); delete ctx; return st; }
+    if (st == GC_OK)
+    {
+        if (cudaMalloc(&ctx->d_light_rules, sizeof(LightRules)) != cudaSuccess) st = fail(GC_ERR_CUDA, "cudaMalloc", "light rules");
+        else { uint8_t step[256], emitted[256]; reference_light_rules(step, emitted); st = upload_light_rules(ctx, step, emitted); }
+    }
+    if (st != GC_OK) { cudaFree(ctx->d_tables); cudaFree(ctx->d_light_rules); delete ctx; return st; }
     *out = ctx;
     return GC_OK;
 }
@@ -249,7 +288,7 @@ int gcmesh_destroy(GcContext* ctx)
     if (!ctx) return GC_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_tables); cudaFree(ctx->d_light_rules);
     cudaStreamDestroy(ctx->upload_stream); cudaStreamDestroy(ctx->download_stream);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (int i = 0; i < 64; i++) { cudaEventDestroy(ctx->ev_uploaded[i]); cudaEventDestroy(ctx->ev_meshed[i]); }
@@ -331,6 +370,8 @@ int gcmesh_world_destroy(GcWorld* w)
     cudaStreamSynchronize(w->ctx->stream);
     cudaFree(w->d_blocks); cudaFree(w->d_sun); cudaFree(w->d_light); cudaFree(w->d_surface); cudaFree(w->d_items);
     if (w->h_items) cudaFreeHost(w->h_items);
+    cudaFree(w->d_light_counters); cudaFree(w->d_brick_flags); cudaFree(w->d_active_list); cudaFree(w->d_sun_list); cudaFree(w->d_light_list);
+    if (w->h_light_counters) cudaFreeHost(w->h_light_counters);
     free(w->slot_dirty); free(w->scan_flags);
     delete w;
     return GC_OK;
@@ -573,6 +614,135 @@ int gcmesh_world_unpack_halo(GcWorld* w, int cz, int z, const void* device_buf)
     if (cz < 0 || cz >= w->size_z || z < 0 || z >= GC_CHUNK_SIZE_H) return fail(GC_ERR_ARG, "row / plane outside the window");
     GC_CUDA(cudaSetDevice(w->ctx->device));
     GC_CUDA(launch_halo_copy(w->d_blocks, w->d_sun, w->d_light, w->d_surface, w->size_x, cz, z, (uint8_t*)device_buf, true, w->ctx->stream));
+    return GC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Column pre-processing on the device: the producers of the mesher's light inputs (ComputeSurface, SetLightNodes).
+int gcmesh_default_light_rules(uint8_t* step, uint8_t* emitted)
+{
+    if (!step || !emitted) return fail(GC_ERR_ARG, "null argument");
+    reference_light_rules(step, emitted);
+    return GC_OK;
+}
+
+int gcmesh_set_light_rules(GcContext* ctx, const uint8_t* step, const uint8_t* emitted)
+{
+    if (!ctx || !step || !emitted) return fail(GC_ERR_ARG, "null argument");
+    for (int i = 0; i < 256; i++)
+        if (emitted[i] > 15 || (step[i] != 255 && (step[i] < 1 || step[i] > 15))) return fail(GC_ERR_ARG, "lightStep must be 1..15 or 255 (opaque), lightEmitted 0..15");
+    GC_CUDA(cudaSetDevice(ctx->device));
+    return upload_light_rules(ctx, step, emitted);
+}
+
+static LightWorld light_world(GcWorld* w)
+{
+    LightWorld lw;
+    lw.blocks = w->d_blocks; lw.sun = w->d_sun; lw.light = w->d_light; lw.surface = w->d_surface;
+    lw.size_x = w->size_x; lw.size_z = w->size_z; lw.rules = w->ctx->d_light_rules;
+    return lw;
+}
+
+int gcmesh_world_compute_surface(GcWorld* w)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    GC_CUDA(launch_surface(light_world(w), w->ctx->stream));
+    return GC_OK;
+}
+
+static int grow_list(uint32_t** list, size_t* cap, size_t need)
+{
+    if (need <= *cap) return GC_OK;
+    cudaFree(*list); *list = nullptr; *cap = 0;
+    const size_t n = need + need / 8 + 1024;
+    if (cudaMalloc(list, n * sizeof(uint32_t)) != cudaSuccess) return fail(GC_ERR_CUDA, "cudaMalloc", "light candidate list");
+    *cap = n;
+    return GC_OK;
+}
+
+int gcmesh_world_light(GcWorld* w)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    if (w->n_slots > 65535) return fail(GC_ERR_CAPACITY, "light fill addresses voxels with 32 bits: at most 65535 bricks per window");
+    if (w->size_x < 3 || w->size_z < 3) return fail(GC_ERR_ARG, "a window needs an edge ring of columns around the pre-processed ones");
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (!w->d_light_counters)
+    {
+        GC_CUDA(cudaMalloc(&w->d_light_counters, 8 * sizeof(uint32_t)));
+        GC_CUDA(cudaMallocHost(&w->h_light_counters, 8 * sizeof(uint32_t)));
+        GC_CUDA(cudaMalloc(&w->d_brick_flags, w->n_slots));
+        GC_CUDA(cudaMalloc(&w->d_active_list, w->n_slots * sizeof(uint32_t)));
+    }
+    const LightWorld lw = light_world(w);
+    uint32_t* c = w->d_light_counters;
+    uint32_t* hc = w->h_light_counters;
+    w->light_launches = 0;
+    auto read_counters = [&]() -> int
+    {
+        GC_CUDA(cudaMemcpyAsync(hc, c, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        GC_CUDA(cudaStreamSynchronize(s));
+        return GC_OK;
+    };
+    // freshly generated chunks hold no light (World.cpp:632): the fill starts from zero
+    GC_CUDA(cudaMemsetAsync(w->d_sun, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
+    GC_CUDA(cudaMemsetAsync(w->d_light, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
+    GC_CUDA(cudaMemsetAsync(w->d_brick_flags, 0, w->n_slots, s));
+    GC_CUDA(cudaMemsetAsync(c, 0, 8 * sizeof(uint32_t), s));
+    // 1. count the sunlight candidates, size the list, fill it (the filling pass also seeds the emitters)
+    GC_CUDA(launch_light_scan(lw, false, nullptr, nullptr, c, s)); w->light_launches++;
+    if (read_counters() != GC_OK) return GC_ERR_CUDA;
+    const uint32_t n_sun = hc[LC_SUN_CAND];
+    if (grow_list(&w->d_sun_list, &w->sun_list_cap, n_sun) != GC_OK) return GC_ERR_CUDA;
+    GC_CUDA(cudaMemsetAsync(c, 0, 8 * sizeof(uint32_t), s));
+    GC_CUDA(launch_light_scan(lw, true, w->d_sun_list, w->d_brick_flags, c, s)); w->light_launches++;
+    // 2. bricks in reach of a seed, their non-opaque cells
+    GC_CUDA(launch_active_bricks(lw, w->d_brick_flags, w->d_active_list, c, s)); w->light_launches++;
+    if (read_counters() != GC_OK) return GC_ERR_CUDA;
+    const uint32_t n_active = hc[LC_ACTIVE_BRICKS], n_seeds = hc[LC_SEEDS];
+    uint32_t n_light = 0;
+    if (n_active)
+    {
+        GC_CUDA(launch_light_candidates(lw, w->d_active_list, (int)n_active, false, nullptr, c, s)); w->light_launches++;
+        if (read_counters() != GC_OK) return GC_ERR_CUDA;
+        n_light = hc[LC_LIGHT_CAND];
+        if (grow_list(&w->d_light_list, &w->light_list_cap, n_light) != GC_OK) return GC_ERR_CUDA;
+        GC_CUDA(cudaMemsetAsync(c + LC_LIGHT_CAND, 0, sizeof(uint32_t), s));
+        GC_CUDA(launch_light_candidates(lw, w->d_active_list, (int)n_active, true, w->d_light_list, c, s)); w->light_launches++;
+    }
+    // 3. relaxation: a value falls by at least one per hop and nothing at or below MIN_LIGHT is stored, so 14 in-place
+    // sweeps reach the fixpoint (the sweeps are enqueued back to back; no host round trip in between)
+    for (int sweep = 0; sweep < 14; sweep++)
+    {
+        GC_CUDA(launch_relax(lw, true, w->d_sun_list, n_sun, c, s)); if (n_sun) w->light_launches++;
+        GC_CUDA(launch_relax(lw, false, w->d_light_list, n_light, c, s)); if (n_light) w->light_launches++;
+    }
+    w->light_stats[0] = n_sun; w->light_stats[1] = n_light; w->light_stats[2] = n_active; w->light_stats[3] = n_seeds;
+    // the sparse-upload bookkeeping no longer knows what the device arrays hold
+    memset(w->slot_dirty, 7, w->n_slots);
+    return GC_OK;
+}
+
+int gcmesh_world_light_stats(const GcWorld* w, uint32_t* stats4, int* launches)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    if (stats4) memcpy(stats4, w->light_stats, sizeof(w->light_stats));
+    if (launches) *launches = w->light_launches;
+    return GC_OK;
+}
+
+int gcmesh_world_download(GcWorld* w, uint16_t* blocks, uint8_t* sunlight, uint8_t* block_light, uint8_t* surface)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    cudaStream_t s = w->ctx->stream;
+    if (blocks) GC_CUDA(cudaMemcpyAsync(blocks, w->d_blocks, w->n_slots * GC_CHUNK_SIZE_3 * 2, cudaMemcpyDeviceToHost, s));
+    if (sunlight) GC_CUDA(cudaMemcpyAsync(sunlight, w->d_sun, w->n_slots * GC_CHUNK_SIZE_3, cudaMemcpyDeviceToHost, s));
+    if (block_light) GC_CUDA(cudaMemcpyAsync(block_light, w->d_light, w->n_slots * GC_CHUNK_SIZE_3, cudaMemcpyDeviceToHost, s));
+    if (surface) GC_CUDA(cudaMemcpyAsync(surface, w->d_surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyDeviceToHost, s));
+    GC_CUDA(cudaStreamSynchronize(s));
     return GC_OK;
 }
 

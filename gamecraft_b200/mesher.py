@@ -28,8 +28,8 @@ CHUNK_NO_SPACE = 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["gcmesh_kernel.cu", "gcmesh_api.cu"]
-HEADERS = ["gcmesh_kernel.cuh", "mesh_core.cuh", os.path.join("..", "..", "include", "gcmesh.h")]
+SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcmesh_api.cu"]
+HEADERS = ["gcmesh_kernel.cuh", "gclight_kernel.cuh", "mesh_core.cuh", os.path.join("..", "..", "include", "gcmesh.h")]
 
 
 class GcMeshError(RuntimeError):
@@ -71,6 +71,8 @@ EXPORTS = [
     "gcmesh_world_create", "gcmesh_world_destroy", "gcmesh_world_upload_chunk", "gcmesh_world_upload_surface",
     "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_upload_launches", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
     "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
+    "gcmesh_default_light_rules", "gcmesh_set_light_rules", "gcmesh_world_compute_surface", "gcmesh_world_light",
+    "gcmesh_world_light_stats", "gcmesh_world_download",
     "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_mesh_host", "gcmesh_wait", "gcmesh_batch_results",
     "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
     "gcmesh_batch_launches", "gcmesh_kernel_info", "gcmesh_batch_profile",
@@ -108,6 +110,12 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_halo_bytes.restype = ctypes.c_size_t
         L.gcmesh_world_pack_halo.argtypes = [vp, ci, ci, vp]
         L.gcmesh_world_unpack_halo.argtypes = [vp, ci, ci, vp]
+        L.gcmesh_default_light_rules.argtypes = [vp, vp]
+        L.gcmesh_set_light_rules.argtypes = [vp, vp, vp]
+        L.gcmesh_world_compute_surface.argtypes = [vp]
+        L.gcmesh_world_light.argtypes = [vp]
+        L.gcmesh_world_light_stats.argtypes = [vp, vp, ctypes.POINTER(ci)]
+        L.gcmesh_world_download.argtypes = [vp, vp, vp, vp, vp]
         L.gcmesh_batch_create.argtypes = [vp, ci, ctypes.c_uint64, ctypes.POINTER(vp)]
         L.gcmesh_batch_destroy.argtypes = [vp]
         L.gcmesh_submit.argtypes = [vp, vp, vp, ci]
@@ -139,6 +147,12 @@ def _ptr(a) -> ctypes.c_void_p:
     return ctypes.c_void_p(int(a))
 
 
+def default_light_rules():
+    step, emitted = np.zeros(256, np.uint8), np.zeros(256, np.uint8)
+    _check(lib().gcmesh_default_light_rules(_ptr(step), _ptr(emitted)), "gcmesh_default_light_rules")
+    return step, emitted
+
+
 def default_block_table():
     """The reference's 24 block types (Code/Block.cpp:139-276) as (list[BlockInfo], kill_zone_id)."""
     arr = (BlockInfo * 256)()
@@ -161,6 +175,12 @@ class Context:
 
     def set_stream(self, stream: int) -> None:
         _check(lib().gcmesh_set_stream(self.h, ctypes.c_void_p(stream)), "gcmesh_set_stream")
+
+    def set_light_rules(self, step, emitted) -> None:
+        """lightStep (1..15, 255 = opaque) and lightEmitted (0..15) per block id, 256 entries each (Code/Block.h:94-95)."""
+        step, emitted = np.ascontiguousarray(step, np.uint8), np.ascontiguousarray(emitted, np.uint8)
+        assert step.shape == (256,) and emitted.shape == (256,)
+        _check(lib().gcmesh_set_light_rules(self.h, _ptr(step), _ptr(emitted)), "gcmesh_set_light_rules")
 
     def synchronize(self) -> None:
         _check(lib().gcmesh_synchronize(self.h), "gcmesh_synchronize")
@@ -225,6 +245,26 @@ class World:
 
     def halo_bytes(self) -> int:
         return int(lib().gcmesh_world_halo_bytes(self.h))
+
+    # -- column pre-processing on the device (ComputeSurface / SetLightNodes, Code/Lighting.cpp) --
+    def compute_surface(self) -> "World":
+        _check(lib().gcmesh_world_compute_surface(self.h), "gcmesh_world_compute_surface")
+        return self
+
+    def light(self) -> "World":
+        """Clear and fill the sunlight / blockLight arenas from the block ids and the surface map."""
+        _check(lib().gcmesh_world_light(self.h), "gcmesh_world_light")
+        return self
+
+    def light_stats(self):
+        st, n = np.zeros(4, np.uint32), ctypes.c_int(0)
+        _check(lib().gcmesh_world_light_stats(self.h, _ptr(st), ctypes.byref(n)), "gcmesh_world_light_stats")
+        return {"sun_candidates": int(st[0]), "light_candidates": int(st[1]), "active_bricks": int(st[2]), "seeds": int(st[3]), "launches": n.value}
+
+    def download(self, host, blocks: bool = False, sun: bool = True, light: bool = True, surface: bool = True) -> None:
+        """Device -> host copy into a HostWorld-shaped object's arrays."""
+        _check(lib().gcmesh_world_download(self.h, _ptr(host.blocks) if blocks else None, _ptr(host.sun) if sun else None,
+                                           _ptr(host.light) if light else None, _ptr(host.surface) if surface else None), "gcmesh_world_download")
 
     def pack_halo(self, cz: int, z: int, device_buf: int) -> None:
         _check(lib().gcmesh_world_pack_halo(self.h, cz, z, ctypes.c_void_p(device_buf)), "gcmesh_world_pack_halo")

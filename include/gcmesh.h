@@ -145,6 +145,26 @@ size_t gcmesh_world_halo_bytes(const GcWorld* world);
 int gcmesh_world_pack_halo(GcWorld* world, int cz, int z, void* device_buf);
 int gcmesh_world_unpack_halo(GcWorld* world, int cz, int z, const void* device_buf);
 
+/* ---- column pre-processing on the device: the producers of the mesher's light inputs ----
+ * Replaces, for a window whose block ids are on the device, ComputeSurface (Code/Lighting.cpp:5-26) and SetLightNodes /
+ * ScatterSunlight / ScatterBlockLight (Lighting.cpp:28-281) as PreprocessGroup runs them over every non-edge column
+ * (WorldRender.cpp:240-262).  The flood fill is computed as the least fixpoint of the reference's push rule: sunlight is
+ * identical to the reference's; block light is identical except where the reference's result depends on the order in
+ * which columns are processed (an emitter re-assigned below light it had already received, Lighting.cpp:240) — there
+ * the brighter, order-independent value is kept. */
+/* lightStep per block id (1..15, 255 = opaque i.e. INT_MAX, Block.cpp:65-68) and lightEmitted (0..15), Block.h:94-95. */
+int gcmesh_default_light_rules(uint8_t* step256, uint8_t* emitted256);
+int gcmesh_set_light_rules(GcContext* ctx, const uint8_t* step256, const uint8_t* emitted256);
+/* surface[column][z*32 + x] = highest non-AIR y in 0..254, plus one (0 for an empty column cell).  Asynchronous. */
+int gcmesh_world_compute_surface(GcWorld* world);
+/* Clears the sunlight / blockLight arenas and fills them from the block ids and the surface map.  Enqueued on the
+ * context stream; the call itself synchronises twice to size its work lists. */
+int gcmesh_world_light(GcWorld* world);
+/* Of the last gcmesh_world_light: {sunlight candidates, blockLight candidates, active bricks, seeded emitters}, kernels launched. */
+int gcmesh_world_light_stats(const GcWorld* world, uint32_t* stats4, int* launches);
+/* Device -> host copy of the window's arrays (NULL skips one); synchronous. */
+int gcmesh_world_download(GcWorld* world, uint16_t* blocks, uint8_t* sunlight, uint8_t* block_light, uint8_t* surface);
+
 /* ---- batches: one GPU submission = the reference's vector<Chunk*> job (WorldRender.cpp:29-37) ---- */
 /* Arenas for up to max_chunks chunks and max_quads quads in total (48 B of vertices + 12 B of indices per quad). */
 int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBatch** out);
