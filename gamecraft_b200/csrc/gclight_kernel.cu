@@ -29,18 +29,30 @@ __global__ void __launch_bounds__(256) gc_surface_kernel(LightWorld w)
     if (row >= n_rows) return;
     const int col = row >> 5, z = row & 31;
     int s = 0;
-    for (int y = GC_WORLD_BLOCK_HEIGHT - 2; y >= 0; y--)
+    // eight layers per step so that eight loads are in flight per lane (y = 255 is never looked at, Lighting.cpp:9)
+    for (int y0 = GC_WORLD_BLOCK_HEIGHT - 1; y0 > 0; y0 -= 8)
     {
-        const uint16_t id = w.blocks[((size_t)col * 4 + (y >> 6)) * kVox + lane + 32 * ((y & 63) + 64 * z)];
-        if (s == 0 && id != 0) s = y + 1;
+        uint16_t id[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            const int y = y0 - k;
+            id[k] = w.blocks[((size_t)col * 4 + (y >> 6)) * kVox + lane + 32 * ((y & 63) + 64 * z)];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            const int y = y0 - k;
+            if (s == 0 && id[k] != 0 && y < GC_WORLD_BLOCK_HEIGHT - 1) s = y + 1;
+        }
         if (__all_sync(0xffffffffu, s != 0)) break;
     }
     w.surface[(size_t)col * 1024 + z * 32 + lane] = (uint8_t)s;
 }
 
-// ---- scan of every column cell up to maxY ----
-template <bool kFill>
-__global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32_t* sun_list, uint8_t* brick_flags, uint32_t* counters)
+// ---- scan of every column cell up to maxY: appends the sunlight candidates, seeds the emitters ----
+// Entries beyond `cap` are counted but not written (the caller grows the list and scans again).
+__global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32_t* sun_list, uint32_t cap, uint8_t* brick_flags, uint32_t* counters)
 {
     const int lane = threadIdx.x & 31;
     const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
@@ -61,29 +73,36 @@ __global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32
         my = max(max(max(my, sf), max(sb, sl)), sr);
         if (my > GC_WORLD_BLOCK_HEIGHT - 1) my = GC_WORLD_BLOCK_HEIGHT - 1;
     }
-    // candidates lie below the own surface; seeds up to maxY
-    const int top = inner ? my : s - 1;
-    int top_w = top;
+    // candidates lie below the own surface; seeds reach up to maxY
+    int top_w = inner ? my : s - 1;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) top_w = max(top_w, __shfl_xor_sync(0xffffffffu, top_w, d));
-    uint32_t count = 0;
-    for (int y = 0; y <= top_w; y++)
+    for (int y0 = 0; y0 <= top_w; y0 += 8)
     {
-        const size_t slot = (size_t)col * 4 + (y >> 6);
-        const uint32_t v = (uint32_t)(slot * kVox + x + 32 * ((y & 63) + 64 * z));
-        const uint32_t id = w.blocks[v] & 255u;
-        const bool cand = y < s && w.rules->step[id] != 255;
-        if (kFill)
+        uint32_t id[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)   // eight loads in flight per lane
         {
+            const int y = min(y0 + k, GC_WORLD_BLOCK_HEIGHT - 1);
+            id[k] = w.blocks[((size_t)col * 4 + (y >> 6)) * kVox + x + 32 * ((y & 63) + 64 * z)] & 255u;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            const int y = y0 + k;
+            const size_t slot = (size_t)col * 4 + (y >> 6);
+            const uint32_t v = (uint32_t)(slot * kVox + x + 32 * ((y & 63) + 64 * z));
+            const bool cand = y < s && w.rules->step[id[k]] != 255;
             const uint32_t m = __ballot_sync(0xffffffffu, cand);
             if (m)
             {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(&counters[LC_SUN_CAND], (uint32_t)__popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (cand) sun_list[base + __popc(m & ((1u << lane) - 1u))] = v;
+                const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                if (cand && pos < cap) sun_list[pos] = v;
             }
-            const uint32_t e = w.rules->emitted[id];
+            const uint32_t e = w.rules->emitted[id[k]];
             if (inner && y <= my && e > 1)   // CheckForBlockLight (Lighting.cpp:231-245); the arrays were cleared, so this is a max
             {
                 w.light[v] = (uint8_t)e;
@@ -91,13 +110,6 @@ __global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32
                 atomicAdd(&counters[LC_SEEDS], 1u);
             }
         }
-        else count += cand ? 1u : 0u;
-    }
-    if (!kFill)
-    {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) count += __shfl_xor_sync(0xffffffffu, count, d);
-        if (lane == 0 && count) atomicAdd(&counters[LC_SUN_CAND], count);
     }
 }
 
@@ -119,43 +131,34 @@ __global__ void gc_active_bricks_kernel(LightWorld w, const uint8_t* brick_flags
     if (on) active_list[atomicAdd(&counters[LC_ACTIVE_BRICKS], 1u)] = (uint32_t)slot;
 }
 
-template <bool kFill>
-__global__ void __launch_bounds__(256) gc_light_candidates_kernel(LightWorld w, const uint32_t* active_list, uint32_t* light_list, uint32_t* counters)
+__global__ void __launch_bounds__(256) gc_light_candidates_kernel(LightWorld w, const uint32_t* active_list, uint32_t* light_list, uint32_t cap, uint32_t* counters)
 {
     const uint32_t slot = active_list[blockIdx.x];
     const int lane = threadIdx.x & 31;
-    uint32_t count = 0;
     for (int i = threadIdx.x; i < kVox; i += blockDim.x)
     {
         const uint32_t v = slot * (uint32_t)kVox + (uint32_t)i;
         const bool cand = w.rules->step[w.blocks[v] & 255u] != 255;
-        if (kFill)
+        const uint32_t m = __ballot_sync(0xffffffffu, cand);
+        if (m)
         {
-            const uint32_t m = __ballot_sync(0xffffffffu, cand);
-            if (m)
-            {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&counters[LC_LIGHT_CAND], (uint32_t)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (cand) light_list[base + __popc(m & ((1u << lane) - 1u))] = v;
-            }
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&counters[LC_LIGHT_CAND], (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+            if (cand && pos < cap) light_list[pos] = v;
         }
-        else count += cand ? 1u : 0u;
-    }
-    if (!kFill)
-    {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) count += __shfl_xor_sync(0xffffffffu, count, d);
-        if (lane == 0 && count) atomicAdd(&counters[LC_LIGHT_CAND], count);
     }
 }
 
-// ---- one relaxation sweep ----
+// `changed` points at this sweep's flag word; the previous sweep's is at changed[-1] (sweep 0: a word preset to 1).  A sweep
+// that changed nothing has reached the fixpoint, so every later sweep returns at once.
 template <bool kSun>
-__global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint32_t* __restrict__ list, uint32_t n, uint32_t* counters)
+__global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint32_t* __restrict__ list, uint32_t n, uint32_t* changed)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (changed[-1] == 0) return;
     const uint32_t v = list[i];
     uint8_t* arr = kSun ? w.sun : w.light;
     const int cur = arr[v];
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint3
     if (best > cur && best > 1)
     {
         arr[v] = (uint8_t)best;
-        counters[LC_CHANGED] = 1;
+        *changed = 1;
     }
 }
 }  // namespace
@@ -205,10 +208,9 @@ cudaError_t launch_surface(const LightWorld& w, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_light_scan(const LightWorld& w, bool fill, uint32_t* sun_list, uint8_t* brick_flags, uint32_t* counters, cudaStream_t s)
+cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_list, uint32_t cap, uint8_t* brick_flags, uint32_t* counters, cudaStream_t s)
 {
-    if (fill) gc_light_scan_kernel<true><<<rows_grid(w), 256, 0, s>>>(w, sun_list, brick_flags, counters);
-    else gc_light_scan_kernel<false><<<rows_grid(w), 256, 0, s>>>(w, sun_list, brick_flags, counters);
+    gc_light_scan_kernel<<<rows_grid(w), 256, 0, s>>>(w, sun_list, cap, brick_flags, counters);
     return cudaGetLastError();
 }
 
@@ -219,20 +221,19 @@ cudaError_t launch_active_bricks(const LightWorld& w, const uint8_t* brick_flags
     return cudaGetLastError();
 }
 
-cudaError_t launch_light_candidates(const LightWorld& w, const uint32_t* active_list, int n_active, bool fill, uint32_t* light_list, uint32_t* counters, cudaStream_t s)
+cudaError_t launch_light_candidates(const LightWorld& w, const uint32_t* active_list, int n_active, uint32_t* light_list, uint32_t cap, uint32_t* counters, cudaStream_t s)
 {
     if (n_active <= 0) return cudaSuccess;
-    if (fill) gc_light_candidates_kernel<true><<<n_active, 256, 0, s>>>(w, active_list, light_list, counters);
-    else gc_light_candidates_kernel<false><<<n_active, 256, 0, s>>>(w, active_list, light_list, counters);
+    gc_light_candidates_kernel<<<n_active, 256, 0, s>>>(w, active_list, light_list, cap, counters);
     return cudaGetLastError();
 }
 
-cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* counters, cudaStream_t s)
+cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (n + 255u) / 256u;
-    if (sun) gc_relax_kernel<true><<<grid, 256, 0, s>>>(w, list, n, counters);
-    else gc_relax_kernel<false><<<grid, 256, 0, s>>>(w, list, n, counters);
+    if (sun) gc_relax_kernel<true><<<grid, 256, 0, s>>>(w, list, n, changed);
+    else gc_relax_kernel<false><<<grid, 256, 0, s>>>(w, list, n, changed);
     return cudaGetLastError();
 }
 }  // namespace gc

@@ -26,17 +26,21 @@ struct LightWorld
     const LightRules* rules;
 };
 
-// counters written by the scan kernels (device memory, 8 x u32)
-enum { LC_SUN_CAND = 0, LC_LIGHT_CAND = 1, LC_ACTIVE_BRICKS = 2, LC_CHANGED = 3, LC_SEEDS = 4 };
+// counters written by the scan kernels (device memory, kLightCounterWords x u32); from LC_FLAGS on: the relaxation sweeps'
+// "something changed" words, one preset word + one per sweep for sunlight, then the same for blockLight
+enum { LC_SUN_CAND = 0, LC_LIGHT_CAND = 1, LC_ACTIVE_BRICKS = 2, LC_SEEDS = 4, LC_FLAGS = 8 };
+constexpr int kLightSweeps = 14;
+constexpr int kLightCounterWords = LC_FLAGS + 2 * (kLightSweeps + 1);
 
 cudaError_t launch_surface(const LightWorld& w, cudaStream_t s);
-// pass over every column cell up to its maxY: counts (fill = false) or appends (fill = true) the sunlight candidates
-// (non-opaque cells below their column's surface); the filling pass also seeds the emitters and flags their bricks
-cudaError_t launch_light_scan(const LightWorld& w, bool fill, uint32_t* sun_list, uint8_t* brick_flags, uint32_t* counters, cudaStream_t s);
+// pass over every column cell up to its maxY: appends the sunlight candidates (non-opaque cells below their column's
+// surface; entries beyond `cap` are only counted), seeds the emitters and flags their bricks
+cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_list, uint32_t cap, uint8_t* brick_flags, uint32_t* counters, cudaStream_t s);
 // bricks within one brick of a flagged brick -> active list
 cudaError_t launch_active_bricks(const LightWorld& w, const uint8_t* brick_flags, uint32_t* active_list, uint32_t* counters, cudaStream_t s);
-// non-opaque cells of the active bricks: count / append
-cudaError_t launch_light_candidates(const LightWorld& w, const uint32_t* active_list, int n_active, bool fill, uint32_t* light_list, uint32_t* counters, cudaStream_t s);
-// one in-place relaxation sweep over a candidate list (sun = true: sunlight rules with the sky sources)
-cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* counters, cudaStream_t s);
+// non-opaque cells of the active bricks: append (entries beyond `cap` are only counted)
+cudaError_t launch_light_candidates(const LightWorld& w, const uint32_t* active_list, int n_active, uint32_t* light_list, uint32_t cap, uint32_t* counters, cudaStream_t s);
+// one in-place relaxation sweep over a candidate list (sun = true: sunlight rules with the sky sources); `changed`: this
+// sweep's flag word, the previous sweep's at changed[-1]
+cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s);
 }  // namespace gc

@@ -671,8 +671,8 @@ int gcmesh_world_light(GcWorld* w)
     cudaStream_t s = ctx->stream;
     if (!w->d_light_counters)
     {
-        GC_CUDA(cudaMalloc(&w->d_light_counters, 8 * sizeof(uint32_t)));
-        GC_CUDA(cudaMallocHost(&w->h_light_counters, 8 * sizeof(uint32_t)));
+        GC_CUDA(cudaMalloc(&w->d_light_counters, kLightCounterWords * sizeof(uint32_t)));
+        GC_CUDA(cudaMallocHost(&w->h_light_counters, kLightCounterWords * sizeof(uint32_t)));
         GC_CUDA(cudaMalloc(&w->d_brick_flags, w->n_slots));
         GC_CUDA(cudaMalloc(&w->d_active_list, w->n_slots * sizeof(uint32_t)));
     }
@@ -682,42 +682,56 @@ int gcmesh_world_light(GcWorld* w)
     w->light_launches = 0;
     auto read_counters = [&]() -> int
     {
-        GC_CUDA(cudaMemcpyAsync(hc, c, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        GC_CUDA(cudaMemcpyAsync(hc, c, LC_FLAGS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         GC_CUDA(cudaStreamSynchronize(s));
         return GC_OK;
     };
     // freshly generated chunks hold no light (World.cpp:632): the fill starts from zero
     GC_CUDA(cudaMemsetAsync(w->d_sun, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
     GC_CUDA(cudaMemsetAsync(w->d_light, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
-    GC_CUDA(cudaMemsetAsync(w->d_brick_flags, 0, w->n_slots, s));
-    GC_CUDA(cudaMemsetAsync(c, 0, 8 * sizeof(uint32_t), s));
-    // 1. count the sunlight candidates, size the list, fill it (the filling pass also seeds the emitters)
-    GC_CUDA(launch_light_scan(lw, false, nullptr, nullptr, c, s)); w->light_launches++;
-    if (read_counters() != GC_OK) return GC_ERR_CUDA;
-    const uint32_t n_sun = hc[LC_SUN_CAND];
-    if (grow_list(&w->d_sun_list, &w->sun_list_cap, n_sun) != GC_OK) return GC_ERR_CUDA;
-    GC_CUDA(cudaMemsetAsync(c, 0, 8 * sizeof(uint32_t), s));
-    GC_CUDA(launch_light_scan(lw, true, w->d_sun_list, w->d_brick_flags, c, s)); w->light_launches++;
-    // 2. bricks in reach of a seed, their non-opaque cells
-    GC_CUDA(launch_active_bricks(lw, w->d_brick_flags, w->d_active_list, c, s)); w->light_launches++;
-    if (read_counters() != GC_OK) return GC_ERR_CUDA;
-    const uint32_t n_active = hc[LC_ACTIVE_BRICKS], n_seeds = hc[LC_SEEDS];
-    uint32_t n_light = 0;
+    GC_CUDA(cudaMemsetAsync(c, 0, kLightCounterWords * sizeof(uint32_t), s));
+    // 1. one pass over the column cells up to maxY: sunlight candidates into the list, emitters seeded.  The list keeps
+    // its capacity between calls; when it turns out too small the pass is repeated once with the exact size.
+    if (!w->d_sun_list && grow_list(&w->d_sun_list, &w->sun_list_cap, w->n_slots * 1024) != GC_OK) return GC_ERR_CUDA;
+    uint32_t n_sun = 0, n_seeds = 0, n_active = 0, n_light = 0;
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        GC_CUDA(cudaMemsetAsync(c, 0, LC_FLAGS * sizeof(uint32_t), s));
+        GC_CUDA(cudaMemsetAsync(w->d_brick_flags, 0, w->n_slots, s));
+        GC_CUDA(launch_light_scan(lw, w->d_sun_list, (uint32_t)w->sun_list_cap, w->d_brick_flags, c, s)); w->light_launches++;
+        // 2. bricks in reach of a seed
+        GC_CUDA(launch_active_bricks(lw, w->d_brick_flags, w->d_active_list, c, s)); w->light_launches++;
+        if (read_counters() != GC_OK) return GC_ERR_CUDA;
+        n_sun = hc[LC_SUN_CAND]; n_seeds = hc[LC_SEEDS]; n_active = hc[LC_ACTIVE_BRICKS];
+        if (n_sun <= w->sun_list_cap) break;
+        if (grow_list(&w->d_sun_list, &w->sun_list_cap, n_sun) != GC_OK) return GC_ERR_CUDA;
+    }
+    //    ... and their non-opaque cells (same capacity policy)
     if (n_active)
     {
-        GC_CUDA(launch_light_candidates(lw, w->d_active_list, (int)n_active, false, nullptr, c, s)); w->light_launches++;
-        if (read_counters() != GC_OK) return GC_ERR_CUDA;
-        n_light = hc[LC_LIGHT_CAND];
-        if (grow_list(&w->d_light_list, &w->light_list_cap, n_light) != GC_OK) return GC_ERR_CUDA;
-        GC_CUDA(cudaMemsetAsync(c + LC_LIGHT_CAND, 0, sizeof(uint32_t), s));
-        GC_CUDA(launch_light_candidates(lw, w->d_active_list, (int)n_active, true, w->d_light_list, c, s)); w->light_launches++;
+        if (!w->d_light_list && grow_list(&w->d_light_list, &w->light_list_cap, (size_t)n_active * 8192) != GC_OK) return GC_ERR_CUDA;
+        for (int attempt = 0; attempt < 2; attempt++)
+        {
+            GC_CUDA(cudaMemsetAsync(c + LC_LIGHT_CAND, 0, sizeof(uint32_t), s));
+            GC_CUDA(launch_light_candidates(lw, w->d_active_list, (int)n_active, w->d_light_list, (uint32_t)w->light_list_cap, c, s)); w->light_launches++;
+            if (read_counters() != GC_OK) return GC_ERR_CUDA;
+            n_light = hc[LC_LIGHT_CAND];
+            if (n_light <= w->light_list_cap) break;
+            if (grow_list(&w->d_light_list, &w->light_list_cap, n_light) != GC_OK) return GC_ERR_CUDA;
+        }
     }
     // 3. relaxation: a value falls by at least one per hop and nothing at or below MIN_LIGHT is stored, so 14 in-place
     // sweeps reach the fixpoint (the sweeps are enqueued back to back; no host round trip in between)
-    for (int sweep = 0; sweep < 14; sweep++)
+    // (a sweep that changes nothing ends the relaxation: later sweeps see its flag and return at once)
     {
-        GC_CUDA(launch_relax(lw, true, w->d_sun_list, n_sun, c, s)); if (n_sun) w->light_launches++;
-        GC_CUDA(launch_relax(lw, false, w->d_light_list, n_light, c, s)); if (n_light) w->light_launches++;
+        const uint32_t one = 1;
+        GC_CUDA(cudaMemcpyAsync(c + LC_FLAGS, &one, sizeof(one), cudaMemcpyHostToDevice, s));
+        GC_CUDA(cudaMemcpyAsync(c + LC_FLAGS + kLightSweeps + 1, &one, sizeof(one), cudaMemcpyHostToDevice, s));
+    }
+    for (int sweep = 0; sweep < kLightSweeps; sweep++)
+    {
+        GC_CUDA(launch_relax(lw, true, w->d_sun_list, n_sun, c + LC_FLAGS + 1 + sweep, s)); if (n_sun) w->light_launches++;
+        GC_CUDA(launch_relax(lw, false, w->d_light_list, n_light, c + LC_FLAGS + kLightSweeps + 2 + sweep, s)); if (n_light) w->light_launches++;
     }
     w->light_stats[0] = n_sun; w->light_stats[1] = n_light; w->light_stats[2] = n_active; w->light_stats[3] = n_seeds;
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
