@@ -139,6 +139,12 @@ struct GcBatch
     int state;                      // 0 idle, 1 submitted, 2 waited
     int launches;
     cudaEvent_t ev_start, ev_stop, ev_done, ev_coords;
+    // work order: chunks are claimed heaviest first so that the kernel's tail is made of cheap ones
+    int32_t* d_order;
+    int32_t* h_order;               // pinned
+    GcChunkCoord* order_coords;     // host copy of the coordinates the order was built for
+    int order_n;
+    bool order_from_history;        // built from the quad counts of a finished submission of the same list
 };
 
 static int encode_map(GcContext* ctx, CUtensorMap* map, CUtensorMapDataType type, int elem_bytes, void* base, size_t n_slots)
@@ -782,6 +788,9 @@ int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBa
     if (e == cudaSuccess && getenv("GCMESH_PROFILE")) e = cudaMalloc(&b->d_prof, sizeof(unsigned long long) * 512);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_out, sizeof(GcChunkOut) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_coords, sizeof(GcChunkCoord) * (size_t)max_chunks);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_order, sizeof(int32_t) * (size_t)max_chunks);
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_order, sizeof(int32_t) * (size_t)max_chunks);
+    if (e == cudaSuccess) { b->order_coords = (GcChunkCoord*)malloc(sizeof(GcChunkCoord) * (size_t)max_chunks); if (!b->order_coords) e = cudaErrorMemoryAllocation; }
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_cursor, 16);
     if (e == cudaSuccess) b->h_counters = reinterpret_cast<int32_t*>(b->h_cursor + 1);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_start);
@@ -799,6 +808,7 @@ int gcmesh_batch_destroy(GcBatch* b)
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     cudaStreamSynchronize(b->ctx->download_stream);
+    cudaFree(b->d_order); if (b->h_order) cudaFreeHost(b->h_order); free(b->order_coords);
     cudaFree(b->d_coords); cudaFree(b->d_out); cudaFree(b->d_vertices); cudaFree(b->d_indices); cudaFree(b->d_cursor); cudaFree(b->d_prof);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_coords) cudaFreeHost(b->h_coords);
@@ -824,7 +834,7 @@ static int validate_coords(const GcWorld* w, const GcChunkCoord* coords, int n)
 }
 
 // Launch the mesh kernel over d_coords[first, first + count) on stream s; descriptors go to d_out[first ...].
-static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cudaStream_t s, bool reset_work_counter = true)
+static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cudaStream_t s, bool reset_work_counter = true, const int32_t* order = nullptr)
 {
     GcContext* ctx = w->ctx;
     cudaError_t e = reset_work_counter ? cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t), s) : cudaSuccess;   // (the error flag persists)
@@ -832,7 +842,7 @@ static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cu
     MeshParams p;
     p.blocks = w->d_blocks; p.sun = w->d_sun; p.light = w->d_light; p.surface = w->d_surface;
     p.size_x = w->size_x; p.size_z = w->size_z;
-    p.coords = b->d_coords + first; p.n_chunks = count; p.out = b->d_out + first;
+    p.coords = b->d_coords + first; p.order = order; p.n_chunks = count; p.out = b->d_out + first;
     p.vertex_arena = b->d_vertices; p.index_arena = b->d_indices; p.max_quads = b->max_quads;
     p.quad_cursor = b->d_cursor; p.work_counter = b->d_counters; p.tables = ctx->d_tables;
     p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma; p.prof = b->d_prof;
@@ -854,16 +864,39 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
     // the pinned coordinate staging buffer is reused: wait until the previous submission has consumed it (its kernel
     // may still be queued or running, so back-to-back submissions keep the GPU busy)
     if (b->state == 1) GC_CUDA(cudaEventSynchronize(b->ev_coords));
+    // Work order (longest first): a chunk with thousands of quads costs several times an air chunk, and the chunks claimed
+    // last decide when the kernel ends.  With the quad counts of a finished submission of the same list the order is by
+    // those; otherwise lower chunks first (terrain sits at the bottom of the world, the sky above it is air).
+    const bool same_list = n == b->order_n && n > 0 && memcmp(coords, b->order_coords, sizeof(GcChunkCoord) * (size_t)n) == 0;
+    const bool order_reused = same_list && (b->order_from_history || b->state != 2);
+    if (!order_reused)
+    {
+        constexpr int kBuckets = 24;
+        const bool history = same_list && b->state == 2;
+        int start[kBuckets + 1] = { 0 };
+        auto bucket = [&](int i) -> int
+        {
+            if (!history) return kBuckets - 1 - (coords[i].cy < 4 ? coords[i].cy : 3);       // cy 0 first
+            const uint32_t q = b->h_out[i].quads;
+            return q == 0 ? 0 : 1 + (q >= 11264 ? 22 : (int)(q >> 9));                       // 512-quad classes, heaviest last
+        };
+        for (int i = 0; i < n; i++) start[bucket(i) + 1]++;
+        for (int k = 0; k < kBuckets; k++) start[k + 1] += start[k];
+        for (int i = 0; i < n; i++) b->h_order[n - 1 - start[bucket(i)]++] = i;             // descending bucket
+        memcpy(b->order_coords, coords, sizeof(GcChunkCoord) * (size_t)n);
+        b->order_n = n; b->order_from_history = history;
+    }
     b->n = n;
     b->launches = 0;
     memcpy(b->h_coords, coords, sizeof(GcChunkCoord) * (size_t)n);
     cudaStream_t s = ctx->stream;
     GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, s));
+    if (!order_reused) GC_CUDA(cudaMemcpyAsync(b->d_order, b->h_order, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
     GC_CUDA(cudaEventRecord(b->ev_coords, s));
     GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, 16, s));
     if (b->d_prof) GC_CUDA(cudaMemsetAsync(b->d_prof, 0, sizeof(unsigned long long) * 512, s));
     GC_CUDA(cudaEventRecord(b->ev_start, s));
-    GC_CUDA(launch_range(w, b, 0, n, s, false));
+    GC_CUDA(launch_range(w, b, 0, n, s, false, b->d_order));
     GC_CUDA(cudaEventRecord(b->ev_stop, s));
     // the descriptors travel back on the download stream: the context stream is free for the next submission's kernel
     cudaStream_t sd = ctx->download_stream;
@@ -898,13 +931,16 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     while ((w->size_z + kStripRows - 1) / kStripRows > 64) kStripRows++;
     const int n_strips = (w->size_z + kStripRows - 1) / kStripRows;
 
-    // chunks bucketed by strip (stable), `perm` maps the sorted position back to the caller's order
+    // chunks bucketed by strip and, inside a strip, lower chunks first (the heavy ones: terrain sits at the bottom of the
+    // world); `perm` maps the sorted position back to the caller's order
     std::vector<int> first(n_strips + 1, 0), perm((size_t)n);
-    for (int i = 0; i < n; i++) first[coords[i].cz / kStripRows + 1]++;
-    for (int k = 0; k < n_strips; k++) first[k + 1] += first[k];
     {
-        std::vector<int> fill(first.begin(), first.end() - 1);
-        for (int i = 0; i < n; i++) { const int pos = fill[coords[i].cz / kStripRows]++; perm[pos] = i; b->h_coords[pos] = coords[i]; }
+        std::vector<int> sub((size_t)n_strips * 4 + 1, 0);
+        auto key = [&](int i) { return (coords[i].cz / kStripRows) * 4 + coords[i].cy; };
+        for (int i = 0; i < n; i++) sub[key(i) + 1]++;
+        for (size_t k = 0; k + 1 < sub.size(); k++) sub[k + 1] += sub[k];
+        for (int k = 0; k <= n_strips; k++) first[k] = sub[(size_t)k * 4];
+        for (int i = 0; i < n; i++) { const int pos = sub[key(i)]++; perm[pos] = i; b->h_coords[pos] = coords[i]; }
     }
 
     cudaStream_t sm = ctx->stream, su = ctx->upload_stream, sd = ctx->download_stream;

@@ -244,6 +244,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         {
             int c = atomicAdd(p.work_counter, 1), fx = 0, fy = 0, fz = 0;
             if (c >= p.n_chunks) c = -1;
+            else if (p.order) c = p.order[c];
             if (c >= 0) { const GcChunkCoord cc = p.coords[c]; fx = cc.cx; fy = cc.cy; fz = cc.cz; }
             s_next[b].chunk = c; s_next[b].cx = fx; s_next[b].cy = fy; s_next[b].cz = fz;
         }

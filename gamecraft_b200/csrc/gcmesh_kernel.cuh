@@ -27,6 +27,7 @@ struct MeshParams
     const uint8_t* surface;
     int32_t size_x, size_z;
     const GcChunkCoord* coords;
+    const int32_t* order;              // optional: the k-th claimed work item is chunk order[k] (heaviest first), null = k
     int32_t n_chunks;
     GcChunkOut* out;
     uint8_t* vertex_arena;

@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -168,6 +169,7 @@ class Context:
         self.h = ctypes.c_void_p()
         _check(lib().gcmesh_create(int(device), ctypes.c_void_p(stream or 0), ctypes.byref(self.h)), "gcmesh_create")
         self.device = device
+        self._children = weakref.WeakSet()   # worlds and batches: destroyed before the context, whatever order the GC picks
 
     def set_block_table(self, infos, kill_zone_id: int = 20) -> None:
         arr = (BlockInfo * len(infos))(*infos)
@@ -192,6 +194,8 @@ class Context:
 
     def close(self) -> None:
         if self.h:
+            for child in list(self._children):
+                child.close()
             lib().gcmesh_destroy(self.h)
             self.h = ctypes.c_void_p()
 
@@ -209,6 +213,7 @@ class World:
         self.ctx, self.size_x, self.size_z = ctx, int(size_x), int(size_z)
         self.h = ctypes.c_void_p()
         _check(lib().gcmesh_world_create(ctx.h, self.size_x, self.size_z, ctypes.byref(self.h)), "gcmesh_world_create")
+        ctx._children.add(self)
 
     def upload(self, host) -> "World":
         """All columns of a HostWorld-shaped object (``blocks``/``sun``/``light``/``surface`` arrays)."""
@@ -306,6 +311,7 @@ class Batch:
         self.ctx, self.max_chunks, self.max_quads = ctx, int(max_chunks), int(max_quads)
         self.h = ctypes.c_void_p()
         _check(lib().gcmesh_batch_create(ctx.h, self.max_chunks, self.max_quads, ctypes.byref(self.h)), "gcmesh_batch_create")
+        ctx._children.add(self)
         self._coords = None
 
     def submit(self, world: World, coords) -> "Batch":
