@@ -890,7 +890,8 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
     b->launches = 0;
     memcpy(b->h_coords, coords, sizeof(GcChunkCoord) * (size_t)n);
     cudaStream_t s = ctx->stream;
-    GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, s));
+    // (a list identical to the previous submission's is already on the device)
+    if (!same_list) GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, s));
     if (!order_reused) GC_CUDA(cudaMemcpyAsync(b->d_order, b->h_order, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
     GC_CUDA(cudaEventRecord(b->ev_coords, s));
     GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, 16, s));
@@ -946,6 +947,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     cudaStream_t sm = ctx->stream, su = ctx->upload_stream, sd = ctx->download_stream;
     const bool mapped = host_arrays_mapped(blocks, sunlight, block_light);
     b->n = n; b->launches = 0; w->launches = 0;
+    b->order_n = 0;                                           // d_coords is about to hold the strip-sorted list
     GC_CUDA(cudaEventRecord(ctx->ev_fork, sm));
     GC_CUDA(cudaStreamWaitEvent(su, ctx->ev_fork, 0));        // the upload overwrites what earlier work on the context stream read
     GC_CUDA(cudaStreamWaitEvent(sd, ctx->ev_fork, 0));
