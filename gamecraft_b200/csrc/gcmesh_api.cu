@@ -432,8 +432,9 @@ int gcmesh_world_upload_all(GcWorld* w, const uint16_t* blocks, const uint8_t* s
     return gcmesh_world_upload_rows(w, 0, w->size_z, blocks, sunlight, block_light, surface);
 }
 
-// Is a 64-byte-aligned buffer all zero?  Exits at the first non-zero 4 KB block.  The AVX2 form keeps a software prefetch
-// a few KB ahead of the loads so that one thread has more cache lines in flight than its L1 fill buffers allow.
+// Is a buffer (a multiple of 4 KB) all zero?  Exits at the first non-zero 4 KB block.  Memory-bound: ~20 GB/s per thread
+// with AVX2, ~12 GB/s with the scalar form (measured on the B200 box's Xeon); a software prefetch ahead of the loads
+// changed nothing.
 static bool all_zero_scalar(const void* p, size_t bytes)
 {
     const uint64_t* q = (const uint64_t*)p;
@@ -447,19 +448,15 @@ static bool all_zero_scalar(const void* p, size_t bytes)
     return true;
 }
 
-static int g_scan_prefetch = 2048;   // bytes ahead (GCMESH_SCAN_PREFETCH)
-
 __attribute__((target("avx2"))) static bool all_zero_avx2(const void* p, size_t bytes)
 {
     const char* q = (const char*)p;
-    const int ahead = g_scan_prefetch;
     for (size_t i = 0; i < bytes; i += 4096)
     {
         __m256i acc = _mm256_setzero_si256();
         for (size_t j = 0; j < 4096; j += 256)
         {
             const char* r = q + i + j;
-            if (ahead) { _mm_prefetch(r + ahead, _MM_HINT_T0); _mm_prefetch(r + ahead + 64, _MM_HINT_T0); _mm_prefetch(r + ahead + 128, _MM_HINT_T0); _mm_prefetch(r + ahead + 192, _MM_HINT_T0); }
             const __m256i a = _mm256_or_si256(_mm256_loadu_si256((const __m256i*)r), _mm256_loadu_si256((const __m256i*)(r + 32)));
             const __m256i b = _mm256_or_si256(_mm256_loadu_si256((const __m256i*)(r + 64)), _mm256_loadu_si256((const __m256i*)(r + 96)));
             const __m256i c = _mm256_or_si256(_mm256_loadu_si256((const __m256i*)(r + 128)), _mm256_loadu_si256((const __m256i*)(r + 160)));
@@ -471,18 +468,10 @@ __attribute__((target("avx2"))) static bool all_zero_avx2(const void* p, size_t 
     return true;
 }
 
-static bool (*g_all_zero)(const void*, size_t) = nullptr;
 static bool all_zero(const void* p, size_t bytes)
 {
-    if (!g_all_zero)
-    {
-        const char* e = getenv("GCMESH_SCAN_PREFETCH");
-        if (e) g_scan_prefetch = atoi(e);
-        const char* v = getenv("GCMESH_SCAN");
-        const bool scalar = (v && atoi(v) == 0) || !__builtin_cpu_supports("avx2");
-        g_all_zero = scalar ? all_zero_scalar : all_zero_avx2;
-    }
-    return g_all_zero(p, bytes);
+    static bool (*const impl)(const void*, size_t) = __builtin_cpu_supports("avx2") ? all_zero_avx2 : all_zero_scalar;
+    return impl(p, bytes);
 }
 
 // Zero / non-zero classification of the host brick arrays of one slot into w->scan_flags.

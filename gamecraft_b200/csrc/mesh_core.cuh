@@ -331,9 +331,15 @@ GC_HD void p3a_row(const RowFaces& r, int ty, int tz, uint32_t rank0, const uint
             const int x = lowbit(any);
             any &= any - 1;
             const uint32_t e = base | ((uint32_t)x << 3);
-#pragma unroll
-            for (int d = 0; d < 6; d++)
-                if ((r.f[d] >> x) & 1u) { list[rank] = e | (uint32_t)d; tlist[rank] = (uint16_t)tr; rank++; tr++; }
+            // the voxel's drawn faces as a 6-bit set, then one step per face (most surface voxels draw one)
+            uint32_t fb = ((r.f[0] >> x) & 1u) | (((r.f[1] >> x) & 1u) << 1) | (((r.f[2] >> x) & 1u) << 2)
+                        | (((r.f[3] >> x) & 1u) << 3) | (((r.f[4] >> x) & 1u) << 4) | (((r.f[5] >> x) & 1u) << 5);
+            do
+            {
+                const int d = lowbit(fb);
+                fb &= fb - 1;
+                list[rank] = e | (uint32_t)d; tlist[rank] = (uint16_t)tr; rank++; tr++;
+            } while (fb);
         }
         return;
     }
