@@ -333,3 +333,31 @@ def test_gpu_mesh_host_pipeline(ctx):
     for m, x in zip(batch.submit(world, coords).wait().meshes(), want):
         util.assert_same_mesh(m, x)
     batch.close(); world.close()
+
+
+def test_gpu_work_order_does_not_change_results(ctx):
+    """The library claims chunks heaviest-first (by cy, then by the quad counts of the previous finished submission of the same
+    list).  Whatever the caller's order and whatever the internal order, every chunk's mesh is the oracle's."""
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(6, 6, origin=(-3, -3)).build("mixed", 17, radius=100, falloff=60)
+    coords = w.interior_chunks(1)
+    o = ob.OracleWorld(w)
+    want = {tuple(c): o.build_chunk(*c) for c in coords.tolist()}
+    world = mesher.World(ctx, 6, 6).upload(w)
+    batch = mesher.Batch(ctx, len(coords), len(coords) * 4000)
+    rng = np.random.default_rng(5)
+    shuffled = coords[rng.permutation(len(coords))]
+    for round_, cs in enumerate((coords, coords, coords, shuffled, shuffled, coords[::-1].copy(), coords[:7].copy(), coords)):
+        batch.submit(world, cs).wait()            # 2nd / 3rd submission of a list: ordered by the previous result's quad counts
+        desc, q = batch.results()
+        assert q == sum(want[tuple(c)].quads for c in cs.tolist())
+        for c, m in zip(cs.tolist(), batch.meshes()):
+            util.assert_same_mesh(m, want[tuple(c)], "round %d chunk %s" % (round_, c))
+    # back-to-back submissions without a wait in between reuse the order already on the device
+    for _ in range(3):
+        batch.submit(world, shuffled)
+    batch.wait()
+    for c, m in zip(shuffled.tolist(), batch.meshes()):
+        util.assert_same_mesh(m, want[tuple(c)], "back to back %s" % (c,))
+    batch.close(); world.close()
