@@ -69,8 +69,8 @@ constexpr int kOffLayerTypB = kOffLayerTypA + 256;                        // u32
 constexpr int kOffLayerBase = kOffLayerTypB + 256;                        // u32[65]
 constexpr int kOffLayerTypBaseA = kOffLayerBase + 272;
 constexpr int kOffLayerTypBaseB = kOffLayerTypBaseA + 256;
-constexpr int kOffFaces = kOffLayerTypBaseB + 256;                        // FacePlan[6], 32 B each
-constexpr int kOffBars = kOffFaces + 192;                                 // full[8]
+constexpr int kOffFaces = kOffLayerTypBaseB + 256;                        // FacePlan[6], 48 B each
+constexpr int kOffBars = kOffFaces + 6 * 48;                              // full[8]
 constexpr int kOffCtx = kOffBars + kStages * 8;
 constexpr int kOffNext = kOffCtx + 64;                                    // NextChunk[2]
 constexpr int kSmemBytes = kOffNext + 32;
@@ -78,7 +78,7 @@ static_assert(kOffPlanes % 128 == 0 && kOffBv % 16 == 0 && kOffSurf % 16 == 0 &&
 static_assert(kOffLut % 8 == 0 && kOffMat % 8 == 0 && kOffBars % 8 == 0 && kOffLayerCnt % 4 == 0 && kOffCtx % 4 == 0 && kOffFaces % 16 == 0, "align");
 static_assert(2 * (kSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM");
 
-static_assert(sizeof(FacePlan) == 32, "FacePlan");
+static_assert(sizeof(FacePlan) == 48, "FacePlan");
 
 struct NextChunk { int32_t chunk, cx, cy, cz; };   // chunk = index into coords, or -1 when the work is exhausted
 

@@ -458,28 +458,30 @@ GC_HD uint32_t gather_cell(const LightGather& g, int x, int ty, int tz)
 // A face's geometry pre-digested for p3b_quad (built once per face from FaceDesc):
 //   w0  row offset of the cell in front (ny*34 + nz) as int16 | nx as int8 << 16 | ny as int8 << 24
 //   w1  row stride of in-plane axis u (uy*34 + uz) | ux << 16 | uy << 24           w2  the same for axis v
-//   w3  corner bits of the four vertices (3 bits each: +x, +y, +z) | per-vertex sign along u << 12 | along v << 16
+//   w3  PRMT selector: nibble k = which of the four footprint corners (bit 0: +u side, bit 1: +v side) vertex k sits on
 //   w4  voxel-offset stride of u (ux + 32*uy + 2048*uz) as int16 | of v << 16
 //   w5  surface-row stride of u (ux + 32*uz) as int16 | of v << 16
 //   w6  footprint extent per axis: bit 0 x, bit 1 y, bit 2 z (1 = some in-plane axis runs along it)
+//   off[k]  vertex k's first output word minus the voxel position: corner offset (x | y << 8 | z << 16) | u texcoord << 24
 // (v never runs along x: the in-plane axes are (x,z), (x,y) or (y,z), see GC_FACE_TABLE.)
-struct FacePlan { uint32_t w0, w1, w2, w3, w4, w5, w6, w7; };
+struct FacePlan { uint32_t w0, w1, w2, w3, w4, w5, w6, w7, off[4]; };
 GC_HD FacePlan make_face_plan(const FaceDesc& f)
 {
     FacePlan p;
     p.w0 = (uint32_t)(uint16_t)(int16_t)(f.ny * kRowsZ + f.nz) | ((uint32_t)(uint8_t)f.nx << 16) | ((uint32_t)(uint8_t)f.ny << 24);
     p.w1 = (uint32_t)(uint16_t)(int16_t)(f.uy * kRowsZ + f.uz) | ((uint32_t)(uint8_t)f.ux << 16) | ((uint32_t)(uint8_t)f.uy << 24);
     p.w2 = (uint32_t)(uint16_t)(int16_t)(f.vy * kRowsZ + f.vz) | ((uint32_t)(uint8_t)f.vx << 16) | ((uint32_t)(uint8_t)f.vy << 24);
-    uint32_t corners = 0, su = 0, sv = 0;
+    p.w3 = 0;
     for (int k = 0; k < 4; k++)
     {
         const uint32_t c = f.corners[k];
         const uint32_t cxb = c & 1u, cyb = (c >> 1) & 1u, czb = (c >> 2) & 1u;
-        corners |= c << (3 * k);
-        su |= (f.ux ? cxb : (f.uy ? cyb : czb)) << k;   // the corner bit of the axis u (v) points along
-        sv |= (f.vx ? cxb : (f.vy ? cyb : czb)) << k;
+        const uint32_t su = f.ux ? cxb : (f.uy ? cyb : czb);   // the corner bit of the axis u (v) points along
+        const uint32_t sv = f.vx ? cxb : (f.vy ? cyb : czb);
+        p.w3 |= (su | (sv << 1)) << (4 * k);
+        const uint32_t u = (uint32_t)(k >> 1) & 1u;            // uv of the four vertices: (0,1) (0,0) (1,0) (1,1)  (WorldRender.cpp:475-553)
+        p.off[k] = cxb | (cyb << 8) | (czb << 16) | (u << 24);
     }
-    p.w3 = corners | (su << 12) | (sv << 16);
     p.w4 = (uint32_t)(uint16_t)(int16_t)(f.ux + 32 * f.uy + 2048 * f.uz) | ((uint32_t)(uint16_t)(int16_t)(f.vx + 32 * f.vy + 2048 * f.vz) << 16);
     p.w5 = (uint32_t)(uint16_t)(int16_t)(f.ux + kSurfStride * f.uz) | ((uint32_t)(uint16_t)(int16_t)(f.vx + kSurfStride * f.vz) << 16);
     p.w6 = (uint32_t)((f.ux | f.vx) ? 1 : 0) | ((uint32_t)((f.uy | f.vy) ? 1 : 0) << 1) | ((uint32_t)((f.uz | f.vz) ? 1 : 0) << 2);
@@ -556,18 +558,19 @@ GC_HD void p3b_quad(uint32_t entry, const FacePlan& f, const LightGather& g, con
     const uint32_t w1c = tex << 8, w2c = ((mat.hi >> 16) & 255u) << 16;   // constant parts of vertex words 1 and 2
     const uint32_t pos = (uint32_t)x | ((uint32_t)ty << 8) | ((uint32_t)tz << 16);
 
+    // the four footprint corners in (side along u, side along v) order, then the face's vertex order by one PRMT each:
+    // byte k of lv / sv = block light / sunlight colour of vertex k
+    const uint32_t c0 = corner_color(l00, lm0, l0m, lmm, !(o_um & o_vm)), c1 = corner_color(l00, lp0, l0m, lpm, !(o_up & o_vm));
+    const uint32_t c2 = corner_color(l00, lm0, l0p, lmp, !(o_um & o_vp)), c3 = corner_color(l00, lp0, l0p, lpp, !(o_up & o_vp));
+    const uint32_t l4 = byte_perm(byte_perm(c0, c1, 0x0040), byte_perm(c2, c3, 0x0040), 0x5410);
+    const uint32_t s4 = byte_perm(byte_perm(c0, c1, 0x0062), byte_perm(c2, c3, 0x0062), 0x5410);
+    const uint32_t lv = byte_perm(l4, 0u, f.w3), sv = byte_perm(s4, 0u, f.w3);
 #pragma unroll
     for (int k = 0; k < 4; k++)
     {
-        const uint32_t c = (f.w3 >> (3 * k)) & 7u;
-        const bool su = (f.w3 >> (12 + k)) & 1u, sv = (f.w3 >> (16 + k)) & 1u;
-        const uint32_t ob = su ? o_up : o_um, oc = sv ? o_vp : o_vm;
-        const uint32_t lb = su ? lp0 : lm0, lc = sv ? l0p : l0m;
-        const uint32_t ld = su ? (sv ? lpp : lpm) : (sv ? lmp : lmm);
-        const uint32_t col = corner_color(l00, lb, lc, ld, !(ob & oc));
-        const uint32_t l = col & 255u, sn = (col >> 16) & 255u;
-        const uint32_t u = (k >> 1) & 1u, v = (k == 0 || k == 3) ? 1u : 0u;   // uv: (0,1) (0,0) (1,0) (1,1)
-        out[3 * k + 0] = (pos + ((c & 1u) | ((c & 2u) << 7) | ((c & 4u) << 14))) | (u << 24);   // corner offsets never carry (x<=31, y<=63, z<=31)
+        const uint32_t l = (lv >> (8 * k)) & 255u, sn = (sv >> (8 * k)) & 255u;
+        const uint32_t v = (k == 0 || k == 3) ? 1u : 0u;
+        out[3 * k + 0] = pos + f.off[k];             // corner offsets never carry (x <= 31, y <= 63, z <= 31)
         out[3 * k + 1] = v | w1c | (l << 16) | (l << 24);
         out[3 * k + 2] = l | (sn << 8) | w2c;
     }
