@@ -20,34 +20,46 @@ constexpr int kVox = GC_CHUNK_SIZE_3;
 
 __device__ __forceinline__ int surf_of(const LightWorld& w, int col, int x, int z) { return w.surface[(size_t)col * 1024 + z * 32 + x]; }
 
-// ---- ComputeSurface: one warp per (column, z) row, lanes = x; walks down from y = 254 until every lane has hit a block ----
+// ---- ComputeSurface: a thread owns eight x of one (column, z) row (one 16-byte load per layer), a warp eight rows of a column;
+// walks down from y = 254, four layers in flight per thread, until every voxel of the warp has hit a block ----
 __global__ void __launch_bounds__(256) gc_surface_kernel(LightWorld w)
 {
     const int lane = threadIdx.x & 31;
-    const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-    const int n_rows = w.size_x * w.size_z * 32;
-    if (row >= n_rows) return;
-    const int col = row >> 5, z = row & 31;
-    int s = 0;
-    // eight layers per step so that eight loads are in flight per lane (y = 255 is never looked at, Lighting.cpp:9)
-    for (int y0 = GC_WORLD_BLOCK_HEIGHT - 1; y0 > 0; y0 -= 8)
+    const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int n_warps = w.size_x * w.size_z * 4;          // 32 rows per column, 8 per warp
+    if (warp >= n_warps) return;
+    const int col = warp >> 2, z = (warp & 3) * 8 + (lane >> 2), x0 = (lane & 3) * 8;
+    uint32_t lo = 0, hi = 0;                               // surface of the eight voxels, one byte each
+    uint32_t found = 0;                                    // bit i: voxel i has its surface
+    for (int y0 = GC_WORLD_BLOCK_HEIGHT - 2; y0 >= 0; y0 -= 4)   // y = 255 is never looked at (Lighting.cpp:9)
     {
-        uint16_t id[8];
+        uint4 v[4];
 #pragma unroll
-        for (int k = 0; k < 8; k++)
+        for (int k = 0; k < 4; k++)
         {
-            const int y = y0 - k;
-            id[k] = w.blocks[((size_t)col * 4 + (y >> 6)) * kVox + lane + 32 * ((y & 63) + 64 * z)];
+            const int y = max(y0 - k, 0);
+            v[k] = *reinterpret_cast<const uint4*>(w.blocks + ((size_t)col * 4 + (y >> 6)) * kVox + x0 + 32 * ((y & 63) + 64 * z));
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++)
+        for (int k = 0; k < 4; k++)
         {
             const int y = y0 - k;
-            if (s == 0 && id[k] != 0 && y < GC_WORLD_BLOCK_HEIGHT - 1) s = y + 1;
+            if (y < 0) break;
+            const uint32_t wds[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                const uint32_t id = (wds[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+                if (id != 0 && !((found >> i) & 1u))
+                {
+                    found |= 1u << i;
+                    if (i < 4) lo |= (uint32_t)(y + 1) << (8 * i); else hi |= (uint32_t)(y + 1) << (8 * (i - 4));
+                }
+            }
         }
-        if (__all_sync(0xffffffffu, s != 0)) break;
+        if (__all_sync(0xffffffffu, found == 0xFFu)) break;
     }
-    w.surface[(size_t)col * 1024 + z * 32 + lane] = (uint8_t)s;
+    *reinterpret_cast<uint2*>(w.surface + (size_t)col * 1024 + z * 32 + x0) = make_uint2(lo, hi);
 }
 
 // ---- scan of every column cell up to maxY: appends the sunlight candidates, seeds the emitters ----
@@ -204,7 +216,8 @@ static int rows_grid(const LightWorld& w) { return (int)(((size_t)w.size_x * w.s
 
 cudaError_t launch_surface(const LightWorld& w, cudaStream_t s)
 {
-    gc_surface_kernel<<<rows_grid(w), 256, 0, s>>>(w);
+    const int grid = (int)(((size_t)w.size_x * w.size_z * 4 * 32 + 255) / 256);
+    gc_surface_kernel<<<grid, 256, 0, s>>>(w);
     return cudaGetLastError();
 }
 
