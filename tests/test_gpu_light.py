@@ -95,3 +95,24 @@ def test_custom_light_rules(ctx):
     sun, light = ob.light_fill(w, surface, step, emitted)
     assert stats["seeds"] > 0
     assert np.array_equal(got.sun, sun) and np.array_equal(got.light, light)
+
+
+def test_non_square_window(ctx):
+    """size_x != size_z: column strides of the mesher and of the light fill (the reference's window is always square)."""
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(7, 4, origin=(-3, -2)).generate("mixed", 23, radius=80, falloff=40)
+    surface = ob.compute_surface(w)
+    sun, light = ob.light_fill(w, surface)
+    got, _ = device_fill(ctx, w)
+    assert np.array_equal(got.surface, surface) and np.array_equal(got.sun, sun) and np.array_equal(got.light, light)
+    w.surface[:] = surface; w.sun[:] = sun; w.light[:] = light
+    coords = w.interior_chunks(1)
+    assert len(coords) == 5 * 2 * 4
+    world = mesher.World(ctx, 7, 4).upload(w)
+    batch = mesher.Batch(ctx, len(coords), len(coords) * 6000)
+    batch.submit(world, coords).wait()
+    o = ob.OracleWorld(w)
+    for (cx, cy, cz), m in zip(coords, batch.meshes()):
+        util.assert_same_mesh(m, o.build_chunk(cx, cy, cz), "%s" % ((cx, cy, cz),))
+    batch.close(); world.close()
