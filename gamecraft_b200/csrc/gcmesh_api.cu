@@ -475,11 +475,24 @@ static bool all_zero(const void* p, size_t bytes)
 }
 
 // Zero / non-zero classification of the host brick arrays of one slot into w->scan_flags.
-static inline void scan_slot(GcWorld* w, size_t slot, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light)
+// A sunlight brick that lies wholly at or above its column's surface is never read: every cell there reads 15 whatever
+// is stored (GetSunlight, Lighting.cpp:69-79; light_pair_of in mesh_core.cuh).  With the surface map at hand such bricks
+// are classified "nothing to transfer" without being scanned — in a terrain world that is most of the sky.
+static inline bool sun_brick_never_read(const uint8_t* surface, size_t slot)
+{
+    if (!surface) return false;
+    const uint8_t* s = surface + (slot >> 2) * GC_CHUNK_SIZE_2;
+    const unsigned y0 = (unsigned)(slot & 3) * GC_CHUNK_SIZE_V;
+    for (int i = 0; i < GC_CHUNK_SIZE_2; i++)
+        if (s[i] > y0) return false;
+    return true;
+}
+
+static inline void scan_slot(GcWorld* w, size_t slot, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface)
 {
     uint8_t f = 0;
     if (!all_zero(blocks + slot * GC_CHUNK_SIZE_3, (size_t)GC_CHUNK_SIZE_3 * 2)) f |= 1;
-    if (!all_zero(sunlight + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 2;
+    if (!sun_brick_never_read(surface, slot) && !all_zero(sunlight + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 2;
     if (!all_zero(block_light + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 4;
     w->scan_flags[slot] = f;
 }
@@ -530,7 +543,7 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
 
 // Classify rows [cz0, cz1) (scan with `threads` host threads, or the caller's hint) and enqueue their upload.
 static int upload_rows_sparse(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light,
-                              const uint8_t* nonzero_hint, int threads, bool mapped, cudaStream_t s)
+                              const uint8_t* surface, const uint8_t* nonzero_hint, int threads, bool mapped, cudaStream_t s)
 {
     const size_t s_begin = (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, s_end = (size_t)cz1 * w->size_x * GC_WORLD_CHUNK_HEIGHT;
     if (nonzero_hint) memcpy(w->scan_flags + s_begin, nonzero_hint + s_begin, s_end - s_begin);
@@ -545,7 +558,7 @@ static int upload_rows_sparse(GcWorld* w, int cz0, int cz1, const uint16_t* bloc
                 const size_t a0 = next.fetch_add(8);
                 if (a0 >= s_end) break;
                 const size_t a1 = a0 + 8 < s_end ? a0 + 8 : s_end;
-                for (size_t slot = a0; slot < a1; slot++) scan_slot(w, slot, blocks, sunlight, block_light);
+                for (size_t slot = a0; slot < a1; slot++) scan_slot(w, slot, blocks, sunlight, block_light, surface);
             }
         };
         std::vector<std::thread> pool;
@@ -572,7 +585,7 @@ int gcmesh_world_upload_sparse(GcWorld* w, const uint16_t* blocks, const uint8_t
     if (!w || !blocks || !sunlight || !block_light) return fail(GC_ERR_ARG, "null argument");
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
-    const int k = upload_rows_sparse(w, 0, w->size_z, blocks, sunlight, block_light, nonzero_hint, threads,
+    const int k = upload_rows_sparse(w, 0, w->size_z, blocks, sunlight, block_light, surface, nonzero_hint, threads,
                                      host_arrays_mapped(blocks, sunlight, block_light), ctx->stream);
     if (k < 0) return fail(GC_ERR_CUDA, "sparse upload", cudaGetErrorString(cudaGetLastError()));
     w->launches = k;
@@ -996,7 +1009,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
                 const size_t a1 = a0 + 4 < w->n_slots ? a0 + 4 : w->n_slots;
                 for (size_t slot = a0; slot < a1; slot++)
                 {
-                    scan_slot(w, slot, blocks, sunlight, block_light);
+                    scan_slot(w, slot, blocks, sunlight, block_light, surface);
                     remaining[(slot / slots_per_row) / kStripRows].fetch_sub(1, std::memory_order_release);
                 }
             }

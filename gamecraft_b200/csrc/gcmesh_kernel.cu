@@ -729,10 +729,10 @@ cudaError_t launch_upload_items(const uint32_t* items, int n_items, const uint16
                                 uint16_t* d_blocks, uint8_t* d_sun, uint8_t* d_light, cudaStream_t stream)
 {
     if (n_items <= 0) return cudaSuccess;
-    // PCIe needs ~100 KB in flight (50 GB/s x 2 us); 16 KB per CTA, so a few dozen CTAs saturate the link and the other
+    // PCIe needs ~100 KB in flight (50 GB/s x 2 us); 16 KB per CTA, so a few dozen CTAs saturate the link (measured: 16 is too few, 64 .. 512 are alike) and the other
     // SMs stay free for a mesh kernel running on another stream (its CTA needs a whole SM's registers)
     static const int ctas_env = getenv("GCMESH_PULL_CTAS") ? atoi(getenv("GCMESH_PULL_CTAS")) : 0;
-    const int cap = ctas_env > 0 ? ctas_env : 32;
+    const int cap = ctas_env > 0 ? ctas_env : 64;
     long long pieces = (long long)n_items * 8;
     int grid = pieces < cap ? (int)pieces : cap;
     gc_upload_kernel<<<grid, 256, 0, stream>>>(items, n_items, h_blocks, h_sun, h_light, d_blocks, d_sun, d_light);

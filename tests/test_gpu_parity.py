@@ -361,3 +361,48 @@ def test_gpu_work_order_does_not_change_results(ctx):
     for c, m in zip(shuffled.tolist(), batch.meshes()):
         util.assert_same_mesh(m, want[tuple(c)], "back to back %s" % (c,))
     batch.close(); world.close()
+
+
+def test_gpu_sky_sunlight_bricks_are_never_read(ctx):
+    """Stored sunlight at or above a column's surface is ignored (GetSunlight, Lighting.cpp:69-79): the sparse upload skips
+    such bricks without scanning them.  Junk written there must not change a single byte of any mesh."""
+    import torch
+
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(6, 6).build("forest", 31)
+    coords = w.interior_chunks(1)
+    o = ob.OracleWorld(w)
+    want = [o.build_chunk(*c) for c in coords]
+    junk = 0
+    for col in range(36):
+        top = int(w.surface[col].max())
+        for cy in range(4):
+            if cy * 64 >= top:
+                w.sun[col * 4 + cy] = 7          # never read: every cell of the brick lies at or above its column's surface
+                junk += 1
+    assert junk > 36
+    o2 = ob.OracleWorld(w)
+    for c, x in zip(coords, want):
+        util.assert_same_mesh(o2.build_chunk(*c), x, "oracle %s" % (c,))
+    pins = [torch.from_numpy(a).pin_memory() for a in (w.blocks, w.sun, w.light, w.surface)]
+
+    class P:
+        size_x, size_z = 6, 6
+        blocks, sun, light, surface = [t.numpy() for t in pins]
+
+    batch = mesher.Batch(ctx, len(coords), len(coords) * 4000)
+    for world in (mesher.World(ctx, 6, 6).upload(P), mesher.World(ctx, 6, 6).upload_sparse(P)):
+        for c, m, x in zip(coords, batch.submit(world, coords).wait().meshes(), want):
+            util.assert_same_mesh(m, x, str(c))
+        world.close()
+    world = mesher.World(ctx, 6, 6)
+    _, q = batch.results()
+    hv = np.zeros((q * 4, 12), np.uint8); hi = np.zeros(q * 6, np.uint16)
+    batch.mesh_host(world, P, coords, hv, hi)
+    desc, q2 = batch.results()
+    assert q2 == q
+    for (c, d, x) in zip(coords, desc, want):
+        v0 = int(d["quad_base"]) * 4
+        assert np.array_equal(hv[v0:v0 + int(d["vert_count"])], x.vertices), str(c)
+    batch.close(); world.close()
