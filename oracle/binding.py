@@ -100,6 +100,8 @@ def oracle_lib() -> ctypes.CDLL:
         L.gcor_compute_surface.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.gcor_light_fill.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6
         L.gcor_default_light_rules.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.gcor_rle_encode_chunk.argtypes = [ctypes.c_void_p, ctypes.c_uint16, ctypes.c_void_p]
+        L.gcor_rle_decode_chunk.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         _olib = L
     return _olib
 
@@ -114,6 +116,8 @@ def ref_lib() -> ctypes.CDLL:
         L.gcref_block_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.gcref_block_light_steps.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.gcref_block_light_emitted.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.gcref_rle_save_group.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.gcref_rle_load_group.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.gcref_set_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.gcref_get_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.gcref_set_surface.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
@@ -154,6 +158,21 @@ def light_fill(host, surface=None, step=None, emitted=None):
                                  np.ascontiguousarray(step, np.uint8).ctypes.data, np.ascontiguousarray(emitted, np.uint8).ctypes.data,
                                  sun.ctypes.data, light.ctypes.data)
     return sun, light
+
+
+def rle_encode_chunk(blocks: np.ndarray, offset: int = 0) -> np.ndarray:
+    """gcor_rle_encode_chunk: one chunk's block ids (65536 uint16) -> its region record."""
+    out = np.zeros(2 + 2 * 65536, np.uint16)
+    n = oracle_lib().gcor_rle_encode_chunk(np.ascontiguousarray(blocks, np.uint16).ctypes.data, offset, out.ctypes.data)
+    return out[:n].copy()
+
+
+def rle_decode_chunk(record: np.ndarray):
+    """gcor_rle_decode_chunk: a region record -> (status, 65536 uint16)."""
+    rec = np.ascontiguousarray(record, np.uint16)
+    out = np.zeros(65536, np.uint16)
+    st = oracle_lib().gcor_rle_decode_chunk(rec.ctypes.data, len(rec), out.ctypes.data)
+    return st, out
 
 
 def default_block_table():
@@ -259,6 +278,21 @@ class RefWorld:
         out = np.zeros(24, np.int32)
         self.L.gcref_block_light_steps(self.h, out.ctypes.data)
         return out
+
+    def rle_save_group(self, cx, cz):
+        """SaveGroup on one column -> list of four uint16 records."""
+        out = np.zeros(4 * (2 + 2 * 65536), np.uint16)
+        sizes = np.zeros(4, np.int32)
+        total = self.L.gcref_rle_save_group(self.h, cx, cz, out.ctypes.data, len(out), sizes.ctypes.data)
+        assert total >= 0
+        recs, p = [], 0
+        for n in sizes:
+            recs.append(out[p:p + n].copy()); p += int(n)
+        return recs
+
+    def rle_load_group(self, cx, cz) -> bool:
+        """LoadGroupFromDisk on one column (decodes what rle_save_group stored into the column's chunks)."""
+        return bool(self.L.gcref_rle_load_group(self.h, cx, cz))
 
     def light_emitted(self):
         out = np.zeros(24, np.int32)

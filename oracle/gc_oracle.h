@@ -87,6 +87,9 @@ void gcor_compute_surface(int size_x, int size_z, const uint16_t* blocks, uint8_
 void gcor_light_fill(int size_x, int size_z, const uint16_t* blocks, const uint8_t* surface, const uint8_t* step, const uint8_t* emitted,
                      uint8_t* sun, uint8_t* light);
 void gcor_default_light_rules(uint8_t* step, uint8_t* emitted);
+/* ---- region chunk format (gc_rle_cpu.c): SaveGroup / LoadGroupFromDisk's run-length coding of a chunk's block ids ---- */
+int gcor_rle_encode_chunk(const uint16_t* blocks, uint16_t offset, uint16_t* out /* 2 + 131072 words */);
+int gcor_rle_decode_chunk(const uint16_t* record, int words, uint16_t* blocks);
 /* FNV-1a-64 over bytes (used for golden digests). */
 uint64_t gcor_fnv1a64(const void* data, uint64_t n, uint64_t h);
 

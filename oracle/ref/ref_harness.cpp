@@ -45,6 +45,7 @@ struct AudioEngine { int unused; };
 #include "Generation.h"
 #include "World.h"
 #include "WorldIO.h"
+static void SaveWorld(GameState*, World*);
 #include "Renderer.h"
 #include "Lighting.h"
 #include "WorldRender.h"
@@ -64,16 +65,11 @@ static void KillCollideFunc(GameState*, World*, vec3&, vec3, Block) {}
 static bool OverlapsBlock(Player*, int, int, int) { return false; }
 static void QueueAsync(GameState*, AsyncFunc, World*, void*, AsyncCallback) {}
 static FrustumVisibility TestFrustum(Camera*, vec3, vec3) { return FRUSTUM_VISIBLE; }
-static bool LoadGroupFromDisk(World*, ChunkGroup*) { return false; }
-static void SaveGroup(GameState*, World*, void*) {}
 static void DeleteRegions(World*) {}
-static bool LoadWorldFileData(GameState*, World*) { return false; }
-static void RemoveFromRegion(World*, ChunkGroup*) {}
 static void SpawnPlayer(GameState*, World*, Player*, Rectf) {}
 static void TeleportPlayer(GameState*, WorldLocation) {}
 static void CreateBiomes(GameState*, World*) {}
 static void ResetEnvironment(GameState*, World*) {}
-static void SaveWorld(GameState*, World*) {}
 static void GenerateDungeonTerrain(World*, ChunkGroup*) {}
 static void MoveCamera(Camera*, vec3) {}
 static void UpdateCameraVectors(Camera*) {}
@@ -84,6 +80,10 @@ static void DeleteDirectory(char*) {}
 #include "Mesh.cpp"
 #include "Block.cpp"
 #include "World.cpp"
+// WorldIO.cpp:29 returns `false` from a function returning Region* (accepted by MSVC); g++ needs a null pointer constant there
+#define false 0
+#include "WorldIO.cpp"
+#undef false
 #include "Lighting.cpp"
 #include "WorldRender.cpp"
 #include "Generation.cpp"
@@ -279,6 +279,36 @@ void gcref_light_all(GcRefWorld* w)
             g->state = GROUP_PREPROCESSED;
         }
     }
+}
+
+// SaveGroup (WorldIO.cpp:245-307) on one column: the four chunks' RLE records as the reference stores them in
+// region->chunks[] ([offset][items][(count, block) ...]).  Records are concatenated into `out` (capacity `cap` words);
+// sizes[cy] = words of chunk cy's record.  Returns the total, or -1 when `out` is too small.
+int gcref_rle_save_group(GcRefWorld* w, int cx, int cz, uint16_t* out, int cap, int32_t* sizes)
+{
+    World* world = w->world;
+    ChunkGroup* group = RefGroup(w, cx, cz);
+    Region* region = GetOrLoadRegion(world, ChunkToRegionP(group->pos));   // no file behind it: an empty region from the pool
+    for (int y = 0; y < WORLD_CHUNK_HEIGHT; y++) group->chunks[y].modified = true;
+    SaveGroup(w->state, world, group);
+    int total = 0;
+    for (int y = 0; y < WORLD_CHUNK_HEIGHT; y++)
+    {
+        ivec3 local = ivec3(group->pos.x & REGION_MASK, y, group->pos.z & REGION_MASK);
+        List<uint16_t>& store = region->chunks[RegionIndex(local)];
+        sizes[y] = store.size;
+        if (total + store.size > cap) return -1;
+        memcpy(out + total, store.items, (size_t)store.size * sizeof(uint16_t));
+        total += store.size;
+    }
+    return total;
+}
+
+// LoadGroupFromDisk (WorldIO.cpp:167-221): the records currently stored for column (cx, cz) decoded into its chunks'
+// block arrays (which the caller may have cleared in between).  Returns 1 when all four chunks had data.
+int gcref_rle_load_group(GcRefWorld* w, int cx, int cz)
+{
+    return LoadGroupFromDisk(w->world, RefGroup(w, cx, cz)) ? 1 : 0;
 }
 
 // BuildChunkAsync (WorldRender.cpp:6-27) on one chunk with a fresh MeshData.

@@ -97,6 +97,27 @@ static inline void WakeConditionVariable(CONDITION_VARIABLE*) {}
 static inline void SleepConditionVariableCS(CONDITION_VARIABLE*, CRITICAL_SECTION*, DWORD) {}
 #define INFINITE 0xFFFFFFFF
 
+// ---- Win32 file API: inert (WorldIO.cpp names it for region files; the harness only drives the in-memory RLE
+// encode / decode of SaveGroup / LoadGroupFromDisk, never a file) ----
+#define INVALID_HANDLE_VALUE ((HANDLE)(long long)-1)
+#define GENERIC_READ 0
+#define GENERIC_WRITE 0
+#define OPEN_EXISTING 0
+#define CREATE_ALWAYS 0
+#define FILE_ATTRIBUTE_NORMAL 0
+#define FILE_END 0
+#define INVALID_SET_FILE_POINTER 0xFFFFFFFFul
+static inline bool PathFileExists(const char*) { return false; }
+static inline HANDLE CreateFile(const char*, int, int, void*, int, int, void*) { return INVALID_HANDLE_VALUE; }
+static inline bool ReadFile(HANDLE, void*, DWORD, DWORD* n, void*) { if (n) *n = 0; return false; }
+static inline bool WriteFile(HANDLE, const void*, DWORD, DWORD* n, void*) { if (n) *n = 0; return false; }
+static inline void CloseHandle(HANDLE) {}
+static inline DWORD SetFilePointer(HANDLE, long, long*, DWORD) { return 0; }
+static inline bool CreateDirectory(const char*, void*) { return true; }
+static inline std::string GetLastErrorText() { return "no file system in the test harness"; }
+static inline void WriteBinary(char*, char*, int) {}
+static inline void ReadBinary(char*, char*) {}
+
 // ---- FastNoiseSIMD: API-shaped stand-in (deterministic hash noise, NOT the real library) ----
 class FastNoiseSIMD
 {
