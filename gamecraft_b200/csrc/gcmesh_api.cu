@@ -13,6 +13,7 @@
 
 #include "gcmesh_kernel.cuh"
 #include "gclight_kernel.cuh"
+#include "gcrle_kernel.cuh"
 
 using namespace gc;
 
@@ -115,7 +116,13 @@ struct GcWorld
     uint32_t* d_active_list;
     uint32_t* d_sun_list; size_t sun_list_cap;
     uint32_t* d_light_list; size_t light_list_cap;
-    int light_launches; uint32_t light_stats[4];   // last gcmesh_world_light: sunlight candidates, blockLight candidates, active bricks, seeds
+    int light_launches; uint32_t light_stats[4];
+    // region-record (RLE) transfer scratch, grown on demand
+    uint16_t* d_rle_data; size_t rle_data_cap;         // the uint16 stream
+    uint32_t* d_rle_ends; size_t rle_ends_cap;         // one run end per (count, block) pair
+    RleJob* d_rle_jobs; RleJob* h_rle_jobs; size_t rle_jobs_cap;
+    uint32_t* d_rle_bad; uint32_t* h_rle_bad;          // records refused by the last decode
+    uint16_t* d_rle_out; uint32_t* d_rle_words; uint32_t* h_rle_words; uint32_t* d_rle_slots; uint16_t* d_rle_offsets;   // encode scratch (kRleGroup bricks)   // last gcmesh_world_light: sunlight candidates, blockLight candidates, active bricks, seeds
 };
 
 struct GcBatch
@@ -211,6 +218,17 @@ static int upload_tables(GcContext* ctx, const GcBlockInfo* table, int n, int ki
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     delete h;
     if (e != cudaSuccess) return fail(GC_ERR_CUDA, "upload block table", cudaGetErrorString(e));
+    return GC_OK;
+}
+
+template <class T>
+static int grow_device(T** p, size_t* cap, size_t need)
+{
+    if (need <= *cap) return GC_OK;
+    cudaFree(*p); *p = nullptr; *cap = 0;
+    const size_t n = need + need / 4 + 1024;
+    if (cudaMalloc(p, n * sizeof(T)) != cudaSuccess) return fail(GC_ERR_CUDA, "cudaMalloc", "region record scratch");
+    *cap = n;
     return GC_OK;
 }
 
@@ -376,6 +394,11 @@ int gcmesh_world_destroy(GcWorld* w)
     cudaStreamSynchronize(w->ctx->stream);
     cudaFree(w->d_blocks); cudaFree(w->d_sun); cudaFree(w->d_light); cudaFree(w->d_surface); cudaFree(w->d_items);
     if (w->h_items) cudaFreeHost(w->h_items);
+    cudaFree(w->d_rle_data); cudaFree(w->d_rle_ends); cudaFree(w->d_rle_jobs); cudaFree(w->d_rle_bad);
+    cudaFree(w->d_rle_out); cudaFree(w->d_rle_words); cudaFree(w->d_rle_slots); cudaFree(w->d_rle_offsets);
+    if (w->h_rle_jobs) cudaFreeHost(w->h_rle_jobs);
+    if (w->h_rle_bad) cudaFreeHost(w->h_rle_bad);
+    if (w->h_rle_words) cudaFreeHost(w->h_rle_words);
     cudaFree(w->d_light_counters); cudaFree(w->d_brick_flags); cudaFree(w->d_active_list); cudaFree(w->d_sun_list); cudaFree(w->d_light_list);
     if (w->h_light_counters) cudaFreeHost(w->h_light_counters);
     free(w->slot_dirty); free(w->scan_flags);
@@ -765,6 +788,115 @@ int gcmesh_world_download(GcWorld* w, uint16_t* blocks, uint8_t* sunlight, uint8
     if (block_light) GC_CUDA(cudaMemcpyAsync(block_light, w->d_light, w->n_slots * GC_CHUNK_SIZE_3, cudaMemcpyDeviceToHost, s));
     if (surface) GC_CUDA(cudaMemcpyAsync(surface, w->d_surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaStreamSynchronize(s));
+    return GC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Region records (the reference's saved-chunk format, WorldIO.cpp:167-307) in and out of the device world.
+int gcmesh_world_upload_rle(GcWorld* w, const GcRleChunk* chunks, int n, const uint16_t* data, size_t data_words)
+{
+    if (!w || (!chunks && n > 0) || (!data && data_words > 0)) return fail(GC_ERR_ARG, "null argument");
+    if (n < 0) return fail(GC_ERR_ARG, "negative record count");
+    if (n == 0) return GC_OK;
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if ((size_t)n > w->rle_jobs_cap)
+    {
+        cudaFree(w->d_rle_jobs); if (w->h_rle_jobs) cudaFreeHost(w->h_rle_jobs);
+        w->d_rle_jobs = nullptr; w->h_rle_jobs = nullptr; w->rle_jobs_cap = 0;
+        const size_t cap = (size_t)n + 1024;
+        GC_CUDA(cudaMalloc(&w->d_rle_jobs, cap * sizeof(RleJob)));
+        GC_CUDA(cudaMallocHost(&w->h_rle_jobs, cap * sizeof(RleJob)));
+        w->rle_jobs_cap = cap;
+    }
+    if (!w->d_rle_bad)
+    {
+        GC_CUDA(cudaMalloc(&w->d_rle_bad, sizeof(uint32_t)));
+        GC_CUDA(cudaMallocHost(&w->h_rle_bad, sizeof(uint32_t)));
+    }
+    // the staging list of the previous call may still be in flight
+    GC_CUDA(cudaStreamSynchronize(s));
+    size_t pairs = 0;
+    for (int i = 0; i < n; i++)
+    {
+        const GcRleChunk& c = chunks[i];
+        if (!column_ok(w, c.cx, c.cz) || c.cy < 0 || c.cy >= GC_WORLD_CHUNK_HEIGHT) return fail(GC_ERR_ARG, "record for a chunk outside the window");
+        if ((c.first_word & 1u) || c.words < 4 || (c.words & 1u) || (size_t)c.first_word + c.words > data_words)
+            return fail(GC_ERR_ARG, "record outside the stream, odd-aligned or shorter than one run");
+        RleJob& j = w->h_rle_jobs[i];
+        j.slot = (uint32_t)(((size_t)c.cz * w->size_x + c.cx) * GC_WORLD_CHUNK_HEIGHT + c.cy);
+        j.first_word = c.first_word; j.words = c.words; j.pair_base = (uint32_t)pairs;
+        pairs += (c.words - 2) / 2;
+        w->slot_dirty[j.slot] |= 1;
+    }
+    if (grow_device(&w->d_rle_data, &w->rle_data_cap, data_words) != GC_OK) return GC_ERR_CUDA;
+    if (grow_device(&w->d_rle_ends, &w->rle_ends_cap, pairs) != GC_OK) return GC_ERR_CUDA;
+    GC_CUDA(cudaMemcpyAsync(w->d_rle_data, data, data_words * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    GC_CUDA(cudaMemcpyAsync(w->d_rle_jobs, w->h_rle_jobs, (size_t)n * sizeof(RleJob), cudaMemcpyHostToDevice, s));
+    GC_CUDA(cudaMemsetAsync(w->d_rle_bad, 0, sizeof(uint32_t), s));
+    GC_CUDA(launch_rle_decode(w->d_rle_jobs, n, w->d_rle_data, w->d_rle_ends, w->d_blocks, w->d_rle_bad, s));
+    GC_CUDA(cudaMemcpyAsync(w->h_rle_bad, w->d_rle_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    return GC_OK;
+}
+
+int gcmesh_world_rle_refused(GcWorld* w, int* refused)
+{
+    if (!w || !refused) return fail(GC_ERR_ARG, "null argument");
+    *refused = 0;
+    if (!w->h_rle_bad) return GC_OK;
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    GC_CUDA(cudaStreamSynchronize(w->ctx->stream));
+    *refused = (int)*w->h_rle_bad;
+    return GC_OK;
+}
+
+int gcmesh_world_encode_rle(GcWorld* w, const GcChunkCoord* coords, int n, uint16_t* records, size_t capacity_words, GcRleChunk* out)
+{
+    if (!w || (!coords && n > 0) || !records || !out) return fail(GC_ERR_ARG, "null argument");
+    if (n < 0) return fail(GC_ERR_ARG, "negative chunk count");
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    constexpr int kRleGroup = 128;                            // bricks encoded per launch (worst-case record: 256 KB each)
+    if (!w->d_rle_out)
+    {
+        GC_CUDA(cudaMalloc(&w->d_rle_out, (size_t)kRleGroup * kRleMaxWords * sizeof(uint16_t)));
+        GC_CUDA(cudaMalloc(&w->d_rle_words, kRleGroup * sizeof(uint32_t)));
+        GC_CUDA(cudaMalloc(&w->d_rle_slots, kRleGroup * sizeof(uint32_t)));
+        GC_CUDA(cudaMalloc(&w->d_rle_offsets, kRleGroup * sizeof(uint16_t)));
+        GC_CUDA(cudaMallocHost(&w->h_rle_words, kRleGroup * (sizeof(uint32_t) * 2 + sizeof(uint16_t))));
+    }
+    uint32_t* h_words = w->h_rle_words;
+    uint32_t* h_slots = h_words + kRleGroup;
+    uint16_t* h_offsets = reinterpret_cast<uint16_t*>(h_slots + kRleGroup);
+    size_t used = 0;
+    for (int g0 = 0; g0 < n; g0 += kRleGroup)
+    {
+        const int m = n - g0 < kRleGroup ? n - g0 : kRleGroup;
+        for (int i = 0; i < m; i++)
+        {
+            const GcChunkCoord c = coords[g0 + i];
+            if (!column_ok(w, c.cx, c.cz) || c.cy < 0 || c.cy >= GC_WORLD_CHUNK_HEIGHT) return fail(GC_ERR_ARG, "chunk outside the window");
+            h_slots[i] = (uint32_t)(((size_t)c.cz * w->size_x + c.cx) * GC_WORLD_CHUNK_HEIGHT + c.cy);
+            h_offsets[i] = (uint16_t)((c.cx & 7) + 8 * (c.cy + GC_WORLD_CHUNK_HEIGHT * (c.cz & 7)));   // RegionIndex of (pos & REGION_MASK), WorldIO.cpp:5-8,259
+        }
+        GC_CUDA(cudaMemcpyAsync(w->d_rle_slots, h_slots, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        GC_CUDA(cudaMemcpyAsync(w->d_rle_offsets, h_offsets, m * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+        GC_CUDA(launch_rle_encode(w->d_rle_slots, w->d_rle_offsets, m, w->d_blocks, w->d_rle_out, w->d_rle_words, s));
+        GC_CUDA(cudaMemcpyAsync(h_words, w->d_rle_words, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        GC_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < m; i++)
+        {
+            const GcChunkCoord c = coords[g0 + i];
+            if (used + h_words[i] > capacity_words) return fail(GC_ERR_CAPACITY, "record buffer too small");
+            GC_CUDA(cudaMemcpyAsync(records + used, w->d_rle_out + (size_t)i * kRleMaxWords, h_words[i] * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+            out[g0 + i].cx = c.cx; out[g0 + i].cy = c.cy; out[g0 + i].cz = c.cz;
+            out[g0 + i].first_word = (uint32_t)used; out[g0 + i].words = h_words[i];
+            used += h_words[i];
+        }
+        GC_CUDA(cudaStreamSynchronize(s));
+    }
     return GC_OK;
 }
 

@@ -29,8 +29,8 @@ CHUNK_NO_SPACE = 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcmesh_api.cu"]
-HEADERS = ["gcmesh_kernel.cuh", "gclight_kernel.cuh", "mesh_core.cuh", os.path.join("..", "..", "include", "gcmesh.h")]
+SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcmesh_api.cu"]
+HEADERS = ["gcmesh_kernel.cuh", "gclight_kernel.cuh", "gcrle_kernel.cuh", "mesh_core.cuh", os.path.join("..", "..", "include", "gcmesh.h")]
 
 
 class GcMeshError(RuntimeError):
@@ -65,6 +65,7 @@ class ChunkOut(ctypes.Structure):
 CHUNK_OUT_DTYPE = np.dtype([("quad_base", "<u4"), ("vert_count", "<u4"), ("index_count", "<u4", (5,)),
                             ("index_offset", "<u4", (5,)), ("quads", "<u4"), ("flags", "<u4"), ("reserved", "<u4", (2,))])
 assert CHUNK_OUT_DTYPE.itemsize == ctypes.sizeof(ChunkOut) == 64
+RLE_CHUNK_DTYPE = np.dtype([("cx", "<i4"), ("cy", "<i4"), ("cz", "<i4"), ("first_word", "<u4"), ("words", "<u4")])   # GcRleChunk
 
 EXPORTS = [
     "gcmesh_version", "gcmesh_last_error", "gcmesh_create", "gcmesh_destroy", "gcmesh_set_stream",
@@ -74,6 +75,7 @@ EXPORTS = [
     "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
     "gcmesh_default_light_rules", "gcmesh_set_light_rules", "gcmesh_world_compute_surface", "gcmesh_world_light",
     "gcmesh_world_light_stats", "gcmesh_world_download",
+    "gcmesh_world_upload_rle", "gcmesh_world_rle_refused", "gcmesh_world_encode_rle",
     "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_mesh_host", "gcmesh_wait", "gcmesh_batch_results",
     "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
     "gcmesh_batch_launches", "gcmesh_kernel_info", "gcmesh_batch_profile",
@@ -117,6 +119,9 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_light.argtypes = [vp]
         L.gcmesh_world_light_stats.argtypes = [vp, vp, ctypes.POINTER(ci)]
         L.gcmesh_world_download.argtypes = [vp, vp, vp, vp, vp]
+        L.gcmesh_world_upload_rle.argtypes = [vp, vp, ci, vp, ctypes.c_size_t]
+        L.gcmesh_world_rle_refused.argtypes = [vp, ctypes.POINTER(ci)]
+        L.gcmesh_world_encode_rle.argtypes = [vp, vp, ci, vp, ctypes.c_size_t, vp]
         L.gcmesh_batch_create.argtypes = [vp, ci, ctypes.c_uint64, ctypes.POINTER(vp)]
         L.gcmesh_batch_destroy.argtypes = [vp]
         L.gcmesh_submit.argtypes = [vp, vp, vp, ci]
@@ -265,6 +270,30 @@ class World:
         st, n = np.zeros(4, np.uint32), ctypes.c_int(0)
         _check(lib().gcmesh_world_light_stats(self.h, _ptr(st), ctypes.byref(n)), "gcmesh_world_light_stats")
         return {"sun_candidates": int(st[0]), "light_candidates": int(st[1]), "active_bricks": int(st[2]), "seeds": int(st[3]), "launches": n.value}
+
+    # -- region records (the reference's saved-chunk format, Code/WorldIO.cpp:167-307) --
+    def upload_rle(self, chunks: np.ndarray, data: np.ndarray) -> "World":
+        """``chunks``: structured array (RLE_CHUNK_DTYPE) locating each record in the uint16 stream ``data``."""
+        chunks = np.ascontiguousarray(chunks, RLE_CHUNK_DTYPE)
+        self._rle_keep = (chunks, np.ascontiguousarray(data, np.uint16))          # asynchronous: keep the stream alive
+        _check(lib().gcmesh_world_upload_rle(self.h, _ptr(chunks), len(chunks), _ptr(self._rle_keep[1]), len(self._rle_keep[1])),
+               "gcmesh_world_upload_rle")
+        return self
+
+    def rle_refused(self) -> int:
+        n = ctypes.c_int(0)
+        _check(lib().gcmesh_world_rle_refused(self.h, ctypes.byref(n)), "gcmesh_world_rle_refused")
+        return n.value
+
+    def encode_rle(self, coords, capacity_words: int | None = None):
+        """Device bricks -> (chunks locating array, uint16 record stream)."""
+        coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)
+        cap = capacity_words or len(coords) * (2 + 2 * CHUNK_VOXELS)
+        data = np.zeros(cap, np.uint16)
+        out = np.zeros(len(coords), RLE_CHUNK_DTYPE)
+        _check(lib().gcmesh_world_encode_rle(self.h, _ptr(coords), len(coords), _ptr(data), cap, _ptr(out)), "gcmesh_world_encode_rle")
+        used = int(out["first_word"][-1] + out["words"][-1]) if len(out) else 0
+        return out, data[:used]
 
     def download(self, host, blocks: bool = False, sun: bool = True, light: bool = True, surface: bool = True) -> None:
         """Device -> host copy into a HostWorld-shaped object's arrays."""

@@ -167,6 +167,25 @@ int gcmesh_world_light_stats(const GcWorld* world, uint32_t* stats4, int* launch
 /* Device -> host copy of the window's arrays (NULL skips one); synchronous. */
 int gcmesh_world_download(GcWorld* world, uint16_t* blocks, uint8_t* sunlight, uint8_t* block_light, uint8_t* surface);
 
+/* ---- region records: the reference's saved-chunk format (Code/WorldIO.cpp:167-307) ----
+ * A chunk's block ids as SaveGroup stores them in region->chunks[]: [offset][items][(count, block) ...], all uint16, runs in
+ * voxel index order; a chunk of one block is the single pair (0, block) (65 536 wrapped).  Saved chunks cross PCIe as
+ * these records (a few KB) and are expanded / produced on the device. */
+typedef struct GcRleChunk
+{
+    int32_t cx, cy, cz;     /* chunk position in the window */
+    uint32_t first_word;    /* where its record starts in the uint16 stream (even) */
+    uint32_t words;         /* record length in uint16, the two header words included */
+} GcRleChunk;
+/* LoadGroupFromDisk's decode (WorldIO.cpp:196-216) for `n` records of `data` into their bricks.  Asynchronous on the
+ * context stream (`data` must stay valid until gcmesh_synchronize).  A record whose runs do not add up to exactly one chunk
+ * is refused: its brick is cleared and counted (gcmesh_world_rle_refused); the reference would write past the array. */
+int gcmesh_world_upload_rle(GcWorld* world, const GcRleChunk* chunks, int n, const uint16_t* data, size_t data_words);
+int gcmesh_world_rle_refused(GcWorld* world, int* refused);
+/* SaveGroup's encode (WorldIO.cpp:272-303) of `n` bricks of the device world: records are appended to `records` (host,
+ * `capacity_words` uint16), out[i] says where chunk i's record lies; offset = RegionIndex(pos & REGION_MASK).  Synchronous. */
+int gcmesh_world_encode_rle(GcWorld* world, const GcChunkCoord* coords, int n, uint16_t* records, size_t capacity_words, GcRleChunk* out);
+
 /* ---- batches: one GPU submission = the reference's vector<Chunk*> job (WorldRender.cpp:29-37) ---- */
 /* Arenas for up to max_chunks chunks and max_quads quads in total (48 B of vertices + 12 B of indices per quad). */
 int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBatch** out);
