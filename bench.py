@@ -200,6 +200,76 @@ def preprocess_leg(ctx, host, pinned, args):
     return out
 
 
+def load_path_leg(ctx, world, batch, host, coords, total_quads, args):
+    """The reference's chunk-load path on the device (SURVEY 8(f4) + 8(f1) + the mesher): saved region records (the RLE
+    format of SaveGroup / LoadGroupFromDisk) in host memory -> block ids -> surface + light -> meshes back in host memory."""
+    import torch
+    from gamecraft_b200 import mesher
+
+    every = np.asarray([(cx, cy, cz) for cz in range(host.size_z) for cx in range(host.size_x) for cy in range(4)], np.int32)
+    loc, data = world.encode_rle(every)                       # untimed: the saved form of this window, written by the device encoder
+    data = torch.from_numpy(data.copy()).pin_memory().numpy()
+    lw = mesher.World(ctx, host.size_x, host.size_z)
+    h_verts = torch.empty((total_quads * 4 + 4, 12), dtype=torch.uint8).pin_memory().numpy()
+    h_idx = torch.empty(total_quads * 6 + 6, dtype=torch.uint16).pin_memory().numpy()
+
+    def one():
+        lw.upload_rle(loc, data)
+        lw.compute_surface().light()
+        batch.submit(lw, coords).wait()
+        batch.download(h_verts, h_idx)
+
+    for _ in range(2):
+        one()
+    ctx.synchronize()
+    k = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        one()
+    ctx.synchronize()
+    sec = (time.perf_counter() - t0) / k
+    desc, q = batch.results()
+    ok = int(q) == int(total_quads) and lw.rle_refused() == 0
+    lw.close()
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import binding as ob
+            from gamecraft_b200.worldgen import HostWorld
+            if ob.have_ref():
+                # the same path through the reference's own code on one host thread, on a 10x10-column cut of the window:
+                # LoadGroupFromDisk (decode) + ComputeSurface + SetLightNodes + BuildChunkAsync of the 8x8x4 inner chunks
+                kk = min(10, host.size_x, host.size_z)
+                small = HostWorld(kk, kk)
+                cols = [(cz + (host.size_z - kk) // 2) * host.size_x + cx + (host.size_x - kk) // 2 for cz in range(kk) for cx in range(kk)]
+                for i, c in enumerate(cols):
+                    small.blocks[4 * i:4 * i + 4] = host.blocks[4 * c:4 * c + 4]
+                r = ob.RefWorld(small)
+                for cz in range(kk):
+                    for cx in range(kk):
+                        r.rle_save_group(cx, cz)              # untimed: puts the records into the reference's region store
+                inner = small.interior_chunks(1)
+                t0 = time.perf_counter()
+                for cz in range(kk):
+                    for cx in range(kk):
+                        r.rle_load_group(cx, cz)
+                r.compute_surface(); r.compute_light()
+                sec_mesh, _ = r.bench(inner, 1)
+                sec_cpu = time.perf_counter() - t0
+                r.close()
+                cpu = {"value": len(inner) / sec_cpu, "unit": "chunks/s", "cores": 1, "kind": "reference",
+                       "sample": "a %dx%d-column cut: LoadGroupFromDisk + ComputeSurface + SetLightNodes for every column, BuildChunkAsync for the "
+                                 "%d inner chunks, the reference's own code (oracle/_ref), one thread" % (kk, kk, len(inner))}
+        except Exception as e:
+            cpu = {"unavailable": str(e)}
+    return {"metric": "chunks_meshed_per_s", "value": len(coords) / sec, "unit": "chunks/s", "ms_per_step": 1e3 * sec, "steps": k,
+            "cpu_reference": cpu,
+            "h2d_bytes_per_step": int(data.nbytes + loc.nbytes), "d2h_bytes_per_step": int(len(coords) * 64 + total_quads * 60),
+            "records": int(len(loc)), "same_quads_as_host_prepared_world": bool(ok),
+            "call": "gcmesh_world_upload_rle (every chunk of the window as its region record) + gcmesh_world_compute_surface + "
+                    "gcmesh_world_light + gcmesh_submit + gcmesh_wait + gcmesh_batch_download"}
+
+
 def cpu_reference_run(host, coords, seconds: float, threads: int | None = None):
     """Times the reference CPU mesher on the host cores: oracle/_ref (the reference compiled verbatim) when that
     library travelled with the repo, else the plain-C port.  Returns the cpu_baseline object."""
@@ -454,8 +524,10 @@ def main():
 
     # ---- column pre-processing on the device: surface map + light flood fill from the block ids ----
     preprocess = None
+    load_path = None
     if not args.no_preprocess and world_size == 1:
         preprocess = preprocess_leg(ctx, host, Pinned, args)
+        load_path = load_path_leg(ctx, world, batch, host, coords, total_quads, args)
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -486,6 +558,8 @@ def main():
             line["cpu_baseline"] = cpu_reference_run(host, coords, args.cpu_seconds)
         if preprocess:
             line["preprocess"] = preprocess
+        if load_path:
+            line["load_path"] = load_path
         print(json.dumps(line), flush=True)
 
     batch.close(); world.close(); ctx.close()
