@@ -125,3 +125,15 @@ def custom_table():
     infos[8].mesh_type = 2
     infos[10].opaque = 0   # leaves let light through the corner test
     return infos, 25
+
+
+def arbitrary_world(seed, fill=0.03, size=3):
+    """Inputs no generator would produce: random block ids (all 24 kinds), random light nibbles and a random surface map that
+    has nothing to do with the blocks.  The mesher is a function of its arrays, whatever they hold."""
+    rng = np.random.default_rng(seed)
+    w = HostWorld(size, size)
+    w.blocks[:] = rng.integers(1, 24, w.blocks.shape, dtype=np.uint16) * (rng.random(w.blocks.shape) < fill)
+    w.sun[:] = rng.integers(0, 16, w.sun.shape, dtype=np.uint8)
+    w.light[:] = rng.integers(0, 16, w.light.shape, dtype=np.uint8)
+    w.surface[:] = rng.integers(0, 256, w.surface.shape, dtype=np.uint8)
+    return w

@@ -49,3 +49,17 @@ def test_emulator_custom_block_table():
             assert got.overflow
         else:
             util.assert_same_mesh(got, want, "cy=%d" % cy)
+
+
+@pytest.mark.parametrize("seed,fill", [(1, 0.03), (2, 0.01), (3, 0.05)])
+def test_emulator_arbitrary_inputs(seed, fill):
+    """Random ids, random light nibbles, a surface map unrelated to the blocks: every chunk of the centre column."""
+    w = util.arbitrary_world(seed, fill)
+    o = ob.OracleWorld(w)
+    for cy in range(4):
+        want = o.build_chunk(1, cy, 1)
+        got = util.emu_build_chunk(w, 1, cy, 1)
+        if want.overflow:
+            assert got.overflow
+        else:
+            util.assert_same_mesh(got, want, "seed %d cy %d" % (seed, cy))

@@ -406,3 +406,18 @@ def test_gpu_sky_sunlight_bricks_are_never_read(ctx):
         v0 = int(d["quad_base"]) * 4
         assert np.array_equal(hv[v0:v0 + int(d["vert_count"])], x.vertices), str(c)
     batch.close(); world.close()
+
+
+@pytest.mark.parametrize("seed,fill", [(1, 0.03), (2, 0.01), (3, 0.05), (4, 0.002)])
+def test_gpu_arbitrary_inputs(ctx, seed, fill):
+    """Random ids, random light nibbles, a surface map unrelated to the blocks (inputs no generator would produce)."""
+    w = util.arbitrary_world(seed, fill, size=4)
+    coords = w.interior_chunks(1)
+    meshes, desc, _ = gpu_meshes(ctx, w, coords)
+    o = ob.OracleWorld(w)
+    for (cx, cy, cz), m, d in zip(coords, meshes, desc):
+        want = o.build_chunk(cx, cy, cz)
+        if want.overflow:
+            assert d["flags"] & 1
+        else:
+            util.assert_same_mesh(m, want, "seed %d %s" % (seed, (cx, cy, cz)))
