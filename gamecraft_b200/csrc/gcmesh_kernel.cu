@@ -41,9 +41,6 @@ constexpr int kHaloWarp = kSlabWarps;                      // warp 8: the y-halo
 constexpr int kFetchWarp = kHaloWarp + 1;                  // warp 9: prefetches the next chunk's id, position and surface rows
 static_assert(kFetchWarp < kWarps, "warp roles");
 constexpr int kYHaloTasks = 2 * kRowsZ;                    // 2 faces x 34 rows
-constexpr int kHaloTasks = kHaloRows * 2;
-constexpr int kHaloBatch = 4;                              // x-halo loads in flight per thread
-constexpr int kHaloPerThread = ((kHaloTasks + NT - 1) / NT + kHaloBatch - 1) / kHaloBatch * kHaloBatch;
 
 constexpr int kStageBytes = 4096;                          // one z-slab of block ids: [64][32] u16
 
@@ -421,41 +418,35 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             uint64_t* s_need = reinterpret_cast<uint64_t*>(smem + kOffList);   // [2][66], the quad list's space (not yet in use)
             if (tid < 2 * kRowsY) s_need[tid] = any_bv ? xhalo_needed_mask(s_bvm + (tid / kRowsY) * kBvWords, tid % kRowsY - 1) : 0ull;
             __syncthreads();
+            // a warp takes whole (side, tz) columns of halo cells: the column's brick row is computed once, lanes walk up
+            // its 66 rows in three passes (three loads in flight per lane), neighbouring rows share cache lines
 #pragma unroll 1
-            for (int k0 = 0; k0 < kHaloPerThread; k0 += kHaloBatch)
+            for (int c = warp; c < 2 * kRowsZ; c += kWarps)
             {
-                uint32_t id[kHaloBatch];
+                const int side = c / kRowsZ, tz = c % kRowsZ - 1;
+                const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
+                const size_t col = (size_t)(cz + dcz) * p.size_x + (cx + (side ? 1 : -1));
+                const uint16_t* src = p.blocks + col * 4 * GC_CHUNK_SIZE_3 + (side ? 0 : 31) + 32 * 64 * (tz & 31);
+                const uint64_t* need_rows = s_need + side * kRowsY;
+                uint32_t id[3];
                 uint32_t need = 0;
 #pragma unroll
-                for (int k = 0; k < kHaloBatch; k++)
+                for (int k = 0; k < 3; k++)
                 {
-                    const int task = tid + (k0 + k) * NT;
-                    if (task < kHaloTasks)
+                    const int r = lane + 32 * k, wy = lwy + r - 1;
+                    if (r < kRowsY && wy >= 0 && wy < GC_WORLD_BLOCK_HEIGHT && ((need_rows[r] >> (tz + 1)) & 1ull))
                     {
-                        // consecutive lanes walk up one (side, tz) column: neighbouring y rows share cache lines
-                        const int side = task / kHaloRows, rem = task % kHaloRows;
-                        const int tz = rem / kRowsY - 1, ty = rem % kRowsY - 1;
-                        const int wy = lwy + ty;
-                        if (wy >= 0 && wy < GC_WORLD_BLOCK_HEIGHT && ((s_need[side * kRowsY + ty + 1] >> (tz + 1)) & 1ull))
-                        {
-                            need |= 1u << k;
-                            const int dcz = tz < 0 ? -1 : (tz > 31 ? 1 : 0);
-                            const int zz = tz & 31, xx = side ? 0 : 31;
-                            const size_t col = (size_t)(cz + dcz) * p.size_x + (cx + (side ? 1 : -1));
-                            id[k] = __ldg(p.blocks + (col * 4 + (wy >> 6)) * GC_CHUNK_SIZE_3 + xx + 32 * ((wy & 63) + 64 * zz));
-                        }
+                        need |= 1u << k;
+                        id[k] = __ldg(src + (size_t)(wy >> 6) * GC_CHUNK_SIZE_3 + 32 * (wy & 63));
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < kHaloBatch; k++)
+                for (int k = 0; k < 3; k++)
                 {
-                    const int task = tid + (k0 + k) * NT;
-                    if (task < kHaloTasks)
+                    const int r = lane + 32 * k, wy = lwy + r - 1;
+                    if (r < kRowsY)
                     {
-                        const int side = task / kHaloRows, rem = task % kHaloRows;
-                        const int tz = rem / kRowsY - 1, ty = rem % kRowsY - 1;
-                        const int hr = hrow(ty, tz);
-                        const int wy = lwy + ty;
+                        const int hr = r * kRowsZ + tz + 1;
                         if (wy < 0) p1_xhalo_cell(kill_cls, s_hx_b, hr, side);
                         else if (wy >= GC_WORLD_BLOCK_HEIGHT) p1_xhalo_cell(air_cls, s_hx_b, hr, side);
                         else if ((need >> k) & 1u) p1_xhalo_cell(s_cls[id[k] & 255u], s_hx_b, hr, side);
