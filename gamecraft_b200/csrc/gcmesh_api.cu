@@ -122,7 +122,7 @@ struct GcWorld
     uint32_t* d_rle_ends; size_t rle_ends_cap;         // one run end per (count, block) pair
     RleJob* d_rle_jobs; RleJob* h_rle_jobs; size_t rle_jobs_cap;
     uint32_t* d_rle_bad; uint32_t* h_rle_bad;          // records refused by the last decode
-    uint16_t* d_rle_out; uint32_t* d_rle_words; uint32_t* h_rle_words; uint32_t* d_rle_slots; uint16_t* d_rle_offsets;   // encode scratch (kRleGroup bricks)   // last gcmesh_world_light: sunlight candidates, blockLight candidates, active bricks, seeds
+    uint16_t* d_rle_out; uint16_t* d_rle_dense; uint32_t* d_rle_words; uint32_t* h_rle_words; uint32_t* d_rle_slots; uint16_t* d_rle_offsets;   // encode scratch (kRleGroup bricks)   // last gcmesh_world_light: sunlight candidates, blockLight candidates, active bricks, seeds
 };
 
 struct GcBatch
@@ -395,7 +395,7 @@ int gcmesh_world_destroy(GcWorld* w)
     cudaFree(w->d_blocks); cudaFree(w->d_sun); cudaFree(w->d_light); cudaFree(w->d_surface); cudaFree(w->d_items);
     if (w->h_items) cudaFreeHost(w->h_items);
     cudaFree(w->d_rle_data); cudaFree(w->d_rle_ends); cudaFree(w->d_rle_jobs); cudaFree(w->d_rle_bad);
-    cudaFree(w->d_rle_out); cudaFree(w->d_rle_words); cudaFree(w->d_rle_slots); cudaFree(w->d_rle_offsets);
+    cudaFree(w->d_rle_out); cudaFree(w->d_rle_dense); cudaFree(w->d_rle_words); cudaFree(w->d_rle_slots); cudaFree(w->d_rle_offsets);
     if (w->h_rle_jobs) cudaFreeHost(w->h_rle_jobs);
     if (w->h_rle_bad) cudaFreeHost(w->h_rle_bad);
     if (w->h_rle_words) cudaFreeHost(w->h_rle_words);
@@ -858,17 +858,18 @@ int gcmesh_world_encode_rle(GcWorld* w, const GcChunkCoord* coords, int n, uint1
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    constexpr int kRleGroup = 128;                            // bricks encoded per launch (worst-case record: 256 KB each)
+    constexpr int kRleGroup = 256;                            // bricks encoded per launch (worst-case record: 256 KB each)
     if (!w->d_rle_out)
     {
         GC_CUDA(cudaMalloc(&w->d_rle_out, (size_t)kRleGroup * kRleMaxWords * sizeof(uint16_t)));
-        GC_CUDA(cudaMalloc(&w->d_rle_words, kRleGroup * sizeof(uint32_t)));
+        GC_CUDA(cudaMalloc(&w->d_rle_dense, (size_t)kRleGroup * kRleMaxWords * sizeof(uint16_t)));
+        GC_CUDA(cudaMalloc(&w->d_rle_words, (kRleGroup + 1) * sizeof(uint32_t)));      // [kRleGroup] = the group's total
         GC_CUDA(cudaMalloc(&w->d_rle_slots, kRleGroup * sizeof(uint32_t)));
         GC_CUDA(cudaMalloc(&w->d_rle_offsets, kRleGroup * sizeof(uint16_t)));
-        GC_CUDA(cudaMallocHost(&w->h_rle_words, kRleGroup * (sizeof(uint32_t) * 2 + sizeof(uint16_t))));
+        GC_CUDA(cudaMallocHost(&w->h_rle_words, (kRleGroup + 1) * sizeof(uint32_t) + kRleGroup * (sizeof(uint32_t) + sizeof(uint16_t))));
     }
     uint32_t* h_words = w->h_rle_words;
-    uint32_t* h_slots = h_words + kRleGroup;
+    uint32_t* h_slots = h_words + kRleGroup + 1;
     uint16_t* h_offsets = reinterpret_cast<uint16_t*>(h_slots + kRleGroup);
     size_t used = 0;
     for (int g0 = 0; g0 < n; g0 += kRleGroup)
@@ -884,13 +885,16 @@ int gcmesh_world_encode_rle(GcWorld* w, const GcChunkCoord* coords, int n, uint1
         GC_CUDA(cudaMemcpyAsync(w->d_rle_slots, h_slots, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         GC_CUDA(cudaMemcpyAsync(w->d_rle_offsets, h_offsets, m * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
         GC_CUDA(launch_rle_encode(w->d_rle_slots, w->d_rle_offsets, m, w->d_blocks, w->d_rle_out, w->d_rle_words, s));
-        GC_CUDA(cudaMemcpyAsync(h_words, w->d_rle_words, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        // the group's records packed back to back on the device, then one copy
+        GC_CUDA(launch_rle_pack(w->d_rle_out, w->d_rle_words, m, w->d_rle_dense, w->d_rle_words + kRleGroup, s));
+        GC_CUDA(cudaMemcpyAsync(h_words, w->d_rle_words, (kRleGroup + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         GC_CUDA(cudaStreamSynchronize(s));
+        const uint32_t total = h_words[kRleGroup];
+        if (used + total > capacity_words) return fail(GC_ERR_CAPACITY, "record buffer too small");
+        GC_CUDA(cudaMemcpyAsync(records + used, w->d_rle_dense, (size_t)total * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
         for (int i = 0; i < m; i++)
         {
             const GcChunkCoord c = coords[g0 + i];
-            if (used + h_words[i] > capacity_words) return fail(GC_ERR_CAPACITY, "record buffer too small");
-            GC_CUDA(cudaMemcpyAsync(records + used, w->d_rle_out + (size_t)i * kRleMaxWords, h_words[i] * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
             out[g0 + i].cx = c.cx; out[g0 + i].cy = c.cy; out[g0 + i].cz = c.cz;
             out[g0 + i].first_word = (uint32_t)used; out[g0 + i].words = h_words[i];
             used += h_words[i];

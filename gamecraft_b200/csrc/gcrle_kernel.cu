@@ -183,7 +183,41 @@ __global__ void __launch_bounds__(kThreads) gc_rle_encode_kernel(const uint32_t*
         out_words[blockIdx.x] = 2 + 2 * n_runs;
     }
 }
+// ---- pack a group's records back to back: record i goes to dense + sum(words[0 .. i)) ----
+__global__ void __launch_bounds__(kThreads) gc_rle_pack_kernel(const uint16_t* __restrict__ out_all, const uint32_t* __restrict__ words, int n,
+                                                               uint16_t* __restrict__ dense, uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t s_warp[kThreads / 32];
+    const int tid = threadIdx.x, i = blockIdx.x;
+    uint32_t before = 0, all = 0;
+    for (int j = tid; j < n; j += kThreads)
+    {
+        const uint32_t wj = words[j];
+        all += wj;
+        if (j < i) before += wj;
+    }
+    uint32_t sum_all;
+    const uint32_t incl = cta_incl_scan(before, s_warp, &sum_all);   // sum_all = words before record i
+    (void)incl;
+    if (i == 0)
+    {
+        uint32_t t;
+        cta_incl_scan(all, s_warp, &t);
+        if (tid == 0) *total = t;
+    }
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(out_all + (size_t)i * kRleMaxWords);   // records are even-sized, even-placed
+    uint32_t* dst = reinterpret_cast<uint32_t*>(dense + sum_all);
+    const uint32_t pairs = words[i] / 2;
+    for (uint32_t k = tid; k < pairs; k += kThreads) dst[k] = src[k];
+}
 }  // namespace
+
+cudaError_t launch_rle_pack(const uint16_t* out_all, const uint32_t* words, int n, uint16_t* dense, uint32_t* total, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    gc_rle_pack_kernel<<<n, kThreads, 0, s>>>(out_all, words, n, dense, total);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_rle_decode(const RleJob* jobs, int n, const uint16_t* data, uint32_t* run_ends, uint16_t* blocks, uint32_t* bad_records, cudaStream_t s)
 {

@@ -27,4 +27,6 @@ cudaError_t launch_rle_decode(const RleJob* jobs, int n, const uint16_t* data, u
 // out + i * kRleMaxWords (worst case: every voxel its own run).  offsets[i] = the record's [offset] word.
 constexpr int kRleMaxWords = 2 + 2 * GC_CHUNK_SIZE_3;
 cudaError_t launch_rle_encode(const uint32_t* slots, const uint16_t* offsets, int n, const uint16_t* blocks, uint16_t* out, uint32_t* out_words, cudaStream_t s);
+// Records of one encoded group packed back to back into `dense`; *total = their words.  words[n] as written by the encoder.
+cudaError_t launch_rle_pack(const uint16_t* out_all, const uint32_t* words, int n, uint16_t* dense, uint32_t* total, cudaStream_t s);
 }  // namespace gc
