@@ -311,7 +311,9 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
 
             auto issue = [&](int k)   // stage this warp's slab number k into its slot
             {
-                fence_proxy_async();   // the slot was read (and, as hx / the quad list, written) by the generic proxy
+                // (no proxy fence here: the slot's last generic accesses were reads that have completed — the refill follows them in
+                // this lane's instruction stream — and the generic writes of P1x .. P3 were fenced by every thread at the end of
+                // the previous chunk)
                 mbar_expect_tx(full, (uint32_t)kStageBytes);
                 tma_load_4d(smem_u32(st), &maps.blocks_slab, 0, 0, warp + k * kSlabWarps, own_slot, full);
             };
