@@ -69,7 +69,7 @@ constexpr int kOffLayerTypBaseB = kOffLayerTypBaseA + 256;
 constexpr int kOffFaces = kOffLayerTypBaseB + 256;                        // FacePlan[6], 48 B each
 constexpr int kOffBars = kOffFaces + 6 * 48;                              // full[8]
 constexpr int kOffCtx = kOffBars + kStages * 8;
-constexpr int kOffNext = kOffCtx + 64;                                    // NextChunk[2]
+constexpr int kOffNext = kOffCtx + 128;                                    // NextChunk[2]
 constexpr int kSmemBytes = kOffNext + 32;
 static_assert(kOffPlanes % 128 == 0 && kOffBv % 16 == 0 && kOffSurf % 16 == 0 && kOffList % 16 == 0 && kOffTList % 2 == 0, "align");
 static_assert(kOffLut % 8 == 0 && kOffMat % 8 == 0 && kOffBars % 8 == 0 && kOffLayerCnt % 4 == 0 && kOffCtx % 4 == 0 && kOffFaces % 16 == 0, "align");
@@ -87,6 +87,8 @@ struct ChunkCtx
     uint32_t quad_base;   // arena segment (quads)
     uint32_t total;
     uint32_t type_off[kMeshTypes];
+    uint8_t slab_cls[kSlabs + 2];   // per z-slab: 0xFF = its plane rows are written; else the class byte of the one non-emitting block
+                                    // (air, as a rule) that fills it — such rows are only written if the chunk turns out to need them
 };
 
 // ---- PTX helpers ----
@@ -283,6 +285,16 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         // two voxel rows of slab s (ty = lane, lane + 32)
         auto convert_rows = [&](const Ids8 (&qa)[4], const Ids8 (&qb)[4], int ua, int ub, uint32_t unrot, int s)
         {
+            {
+                // The whole slab one non-emitting block (the air above the terrain): nothing is written now.  Three quarters of a
+                // terrain world's chunks are nothing but such slabs and are never looked at again; if the chunk does emit, the
+                // rows are filled in after P1.
+                const uint32_t id0 = __shfl_sync(0xffffffffu, qa[0].x, 0);
+                const uint32_t cls = s_cls[id0 & 255u];
+                const bool skip = __all_sync(0xffffffffu, ua == 2 && ub == 2 && qa[0].x == id0 && qb[0].x == id0) && (cls >> P_M0) == (uint32_t)kNoEmitType;
+                if (lane == 0) s_ctx->slab_cls[s] = skip ? (uint8_t)cls : (uint8_t)0xFF;
+                if (skip) return;
+            }
             const uint32_t va = convert_row(qa, ua, unrot, lane, s), vb = convert_row(qb, ub, unrot, lane + 32, s);
             if (s >= 1 && s <= kTZ)
             {
@@ -416,6 +428,18 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         const bool any_emit = s_ctx->any_emit != 0, any_bv = s_ctx->any_bv != 0;
         if (any_emit)
         {
+            // the plane rows of the slabs P1 skipped (one non-emitting block throughout): constant words
+            for (int t = tid; t < kSlabs * kTY; t += NT)
+            {
+                const int s = t / kTY, ty = t % kTY;
+                const uint32_t cls = s_ctx->slab_cls[s];
+                if (cls != 0xFFu)
+                {
+                    uint32_t o[8];
+                    p1_class_row_const(cls, o);
+                    store_row_planes(s_planes, hrow(ty, s - 1), o);
+                }
+            }
             // which halo cells can be read at all: per (side, layer) the rows next to an emitting boundary voxel
             uint64_t* s_need = reinterpret_cast<uint64_t*>(smem + kOffList);   // [2][66], the quad list's space (not yet in use)
             if (tid < 2 * kRowsY) s_need[tid] = any_bv ? xhalo_needed_mask(s_bvm + (tid / kRowsY) * kBvWords, tid % kRowsY - 1) : 0ull;
