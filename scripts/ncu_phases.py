@@ -8,24 +8,38 @@ for r in csv.reader(io.StringIO(src)):
     if r and r[0] == 'Line No': h = r; ie = r.index('Instructions Executed'); isamp = r.index('# Samples'); continue
     if h and len(r) > ie and r[0].isdigit():
         agg[(cur, int(r[0]))] = (int(r[ie]) if r[ie].isdigit() else 0, int(r[isamp]) if r[isamp].isdigit() else 0)
+import os, re
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+def first_line(path, pattern):
+    for i, line in enumerate(open(os.path.join(ROOT, path)), 1):
+        if re.search(pattern, line):
+            return i
+    raise SystemExit("marker not found: " + pattern)
+K = "gamecraft_b200/csrc/gcmesh_kernel.cu"
+C = "gamecraft_b200/csrc/mesh_core.cuh"
+k_p0 = first_line(K, r"=+ P0:"); k_p1 = first_line(K, r"=+ P1: stage"); k_halo = first_line(K, r"---- y-halo rows")
+k_p1x = first_line(K, r"=+ P1x:"); k_p2 = first_line(K, r"=+ P2:"); k_p3 = first_line(K, r"=+ P3: emission")
+k_p3a = first_line(K, r"---- 3a:"); k_p3b = first_line(K, r"---- 3b:")
+c_p1 = first_line(C, r"Phase 1: raw voxels"); c_p1x = first_line(C, r"GC_HD void p1_xhalo_cell"); c_light = first_line(C, r"GC_HD uint32_t light_pair_of")
+c_p2 = first_line(C, r"Phase 2: face masks"); c_p3a = first_line(C, r"Phase 3a:"); c_p3b = first_line(C, r"GC_HD void quad_index_words")
 def grp(f, l):
     if f == 'gcmesh_kernel.cu':
-        if l < 260: return 'setup / helpers (mbarrier waits, barriers)'
-        if l < 268: return 'P0'
-        if l < 367: return 'P1 (kernel)'
-        if l < 416: return 'y-halo + z-halo slabs'
-        if l < 471: return 'P1x'
-        if l < 572: return 'P2 (kernel)'
-        if l < 605: return 'P3 setup (surface tile, batches)'
-        if l < 630: return 'P3a (kernel)'
+        if l < k_p0: return 'setup / helpers (mbarrier waits, barriers)'
+        if l < k_p1: return 'P0'
+        if l < k_halo: return 'P1 (kernel)'
+        if l < k_p1x: return 'y-halo + z-halo slabs'
+        if l < k_p2: return 'P1x'
+        if l < k_p3: return 'P2 (kernel)'
+        if l < k_p3a: return 'P3 setup (surface tile, batches)'
+        if l < k_p3b: return 'P3a (kernel)'
         return 'P3b (kernel)'
     if f == 'mesh_core.cuh':
-        if l < 148: return 'core helpers (byte_perm, transpose, planes store)'
-        if l < 226: return 'P1 (core: uniformity, class rows)'
-        if l < 247: return 'P1x (core)'
-        if l < 255: return 'P3b light_pair_of'
-        if l < 313: return 'P2 / P3a row faces + counts'
-        if l < 367: return 'P3a p3a_row'
+        if l < c_p1: return 'core helpers (byte_perm, transpose, planes store)'
+        if l < c_p1x: return 'P1 (core: uniformity, class rows)'
+        if l < c_light: return 'P1x (core)'
+        if l < c_p2: return 'P3b light_pair_of'
+        if l < c_p3a: return 'P2 / P3a row faces + counts'
+        if l < c_p3b: return 'P3a p3a_row'
         return 'P3b (core)'
     return f
 g = {}
