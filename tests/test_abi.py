@@ -57,3 +57,11 @@ def test_argument_errors_without_gpu():
     assert L.gcmesh_world_create(None, 4, 4, ctypes.byref(ctypes.c_void_p())) == -1
     assert L.gcmesh_wait(None) == -1
     assert b"null" in L.gcmesh_last_error()
+    # the pre-processing and region-record entry points refuse null handles the same way (no device is touched)
+    assert L.gcmesh_world_compute_surface(None) == -1
+    assert L.gcmesh_world_light(None) == -1
+    assert L.gcmesh_set_light_rules(None, None, None) == -1
+    assert L.gcmesh_world_upload_rle(None, None, 0, None, 0) == -1
+    assert L.gcmesh_world_encode_rle(None, None, 0, None, 0, None) == -1
+    step, emitted = mesher.default_light_rules()
+    assert step[0] == 1 and step[3] == 255 and emitted[14] == 15 and emitted[17] == 10
