@@ -270,6 +270,80 @@ def load_path_leg(ctx, world, batch, host, coords, total_quads, args):
                     "gcmesh_world_light + gcmesh_submit + gcmesh_wait + gcmesh_batch_download"}
 
 
+def edit_path_leg(ctx, world, host, args):
+    """The interactive caller on the device: SetBlock -> overflow pre-check -> relight -> rebuild list, then the
+    remesh of the flagged chunks with their meshes read back — dig the top block of a column, then put it back."""
+    from gamecraft_b200 import mesher
+
+    rng = np.random.default_rng(7)
+    small = mesher.Batch(ctx, 64, 64 * 4096)
+    spots = []
+    for _ in range(12):
+        wx, wz = int(rng.integers(64, 32 * (host.size_x - 2))), int(rng.integers(64, 32 * (host.size_z - 2)))
+        s = int(host.surface[(wz >> 5) * host.size_x + (wx >> 5)][(wz & 31) * 32 + (wx & 31)])
+        if 1 <= s <= 254:
+            spots.append((wx, s - 1, wz, int(host.get_block(wx, s - 1, wz))))
+    t_edit, t_total, flagged, applied = [], [], [], 0
+    for i, (wx, wy, wz, old) in enumerate(spots + spots):
+        block = 0 if i < len(spots) else old
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        status, rebuild = world.set_blocks([(wx, wy, wz, block)])
+        t1 = time.perf_counter()
+        if len(rebuild):
+            small.submit(world, rebuild[:64]).wait()
+            small.download()
+        t2 = time.perf_counter()
+        if i >= 2:                                            # the first calls allocate the scratch
+            t_edit.append(t1 - t0); t_total.append(t2 - t0); flagged.append(len(rebuild))
+        applied += int(status[0] == mesher.EDIT_APPLIED)
+    small.close()
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import binding as ob
+            from gamecraft_b200.worldgen import HostWorld
+            if ob.have_ref():
+                kk = min(10, host.size_x, host.size_z)
+                ox, oz = (host.size_x - kk) // 2, (host.size_z - kk) // 2
+                cut = HostWorld(kk, kk)
+                for cz in range(kk):
+                    for cx in range(kk):
+                        c, i = (cz + oz) * host.size_x + cx + ox, cz * kk + cx
+                        cut.blocks[4 * i:4 * i + 4] = host.blocks[4 * c:4 * c + 4]
+                r = ob.RefWorld(cut)
+                r.compute_surface(); r.compute_light()
+                for cz in range(kk):
+                    for cx in range(kk):
+                        for cy in range(4):
+                            r.set_chunk_built(cx, cy, cz, True, 0)
+                r.download(cut)
+                r.pending_updates(clear=True)
+                secs = []
+                for k in range(16):
+                    wx, wz = int(rng.integers(64, 32 * (kk - 2))), int(rng.integers(64, 32 * (kk - 2)))
+                    s = int(cut.surface[(wz >> 5) * kk + (wx >> 5)][(wz & 31) * 32 + (wx & 31)])
+                    if not 1 <= s <= 254:
+                        continue
+                    t0 = time.perf_counter()
+                    r.set_block(wx, s - 1, wz, 0)
+                    pend = r.pending_updates(clear=True)
+                    todo = [(cx, cy, cz) for cz in range(1, kk - 1) for cx in range(1, kk - 1) for cy in range(4) if pend[cz, cx, cy]]
+                    if todo:
+                        r.bench(np.asarray(todo, np.int32), 1)
+                    secs.append(time.perf_counter() - t0)
+                r.close()
+                cpu = {"ms_per_edit_and_remesh": 1e3 * float(np.median(secs)), "cores": 1, "kind": "reference",
+                       "sample": "%d edits on a %dx%d-column cut: the reference's own SetBlock (RecomputeLight, FlagChunkForUpdate) + "
+                                 "BuildChunkAsync of the chunks it left pending (oracle/_ref), one thread" % (len(secs), kk, kk)}
+        except Exception as e:
+            cpu = {"unavailable": str(e)}
+    return {"ms_per_edit": 1e3 * float(np.median(t_edit)), "ms_per_edit_and_remesh": 1e3 * float(np.median(t_total)),
+            "edits": len(t_edit), "applied": applied, "chunks_flagged_per_edit": float(np.mean(flagged)), "cpu_reference": cpu,
+            "call": "gcmesh_world_set_blocks (one edit: 33 kernels, one synchronisation) + gcmesh_submit of the flagged chunks + "
+                    "gcmesh_wait + gcmesh_batch_download"}
+
+
 def cpu_reference_run(host, coords, seconds: float, threads: int | None = None):
     """Times the reference CPU mesher on the host cores: oracle/_ref (the reference compiled verbatim) when that
     library travelled with the repo, else the plain-C port.  Returns the cpu_baseline object."""
@@ -525,9 +599,11 @@ def main():
     # ---- column pre-processing on the device: surface map + light flood fill from the block ids ----
     preprocess = None
     load_path = None
+    edit_path = None
     if not args.no_preprocess and world_size == 1:
         preprocess = preprocess_leg(ctx, host, Pinned, args)
         load_path = load_path_leg(ctx, world, batch, host, coords, total_quads, args)
+        edit_path = edit_path_leg(ctx, world, host, args)     # last: it edits the device world
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -560,6 +636,8 @@ def main():
             line["preprocess"] = preprocess
         if load_path:
             line["load_path"] = load_path
+        if edit_path:
+            line["edit_path"] = edit_path
         print(json.dumps(line), flush=True)
 
     batch.close(); world.close(); ctx.close()

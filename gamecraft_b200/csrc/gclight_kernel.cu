@@ -166,11 +166,12 @@ __global__ void __launch_bounds__(256) gc_light_candidates_kernel(LightWorld w, 
 // `changed` points at this sweep's flag word; the previous sweep's is at changed[-1] (sweep 0: a word preset to 1).  A sweep
 // that changed nothing has reached the fixpoint, so every later sweep returns at once.
 template <bool kSun>
-__global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint32_t* __restrict__ list, uint32_t n, uint32_t* changed)
+__global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint32_t* __restrict__ list, uint32_t n, const uint32_t* __restrict__ n_dev, uint32_t* changed)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (changed[-1] == 0) return;
+    if (n_dev && i >= *n_dev) return;   // list length known on the device only (edit path): n is the capacity
     const uint32_t v = list[i];
     uint8_t* arr = kSun ? w.sun : w.light;
     const int cur = arr[v];
@@ -241,12 +242,12 @@ cudaError_t launch_light_candidates(const LightWorld& w, const uint32_t* active_
     return cudaGetLastError();
 }
 
-cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s)
+cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s, const uint32_t* n_dev)
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (n + 255u) / 256u;
-    if (sun) gc_relax_kernel<true><<<grid, 256, 0, s>>>(w, list, n, changed);
-    else gc_relax_kernel<false><<<grid, 256, 0, s>>>(w, list, n, changed);
+    if (sun) gc_relax_kernel<true><<<grid, 256, 0, s>>>(w, list, n, n_dev, changed);
+    else gc_relax_kernel<false><<<grid, 256, 0, s>>>(w, list, n, n_dev, changed);
     return cudaGetLastError();
 }
 }  // namespace gc

@@ -42,5 +42,6 @@ cudaError_t launch_active_bricks(const LightWorld& w, const uint8_t* brick_flags
 cudaError_t launch_light_candidates(const LightWorld& w, const uint32_t* active_list, int n_active, uint32_t* light_list, uint32_t cap, uint32_t* counters, cudaStream_t s);
 // one in-place relaxation sweep over a candidate list (sun = true: sunlight rules with the sky sources); `changed`: this
 // sweep's flag word, the previous sweep's at changed[-1]
-cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s);
+// n_dev (optional): the list's length in device memory, n then being its capacity
+cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s, const uint32_t* n_dev = nullptr);
 }  // namespace gc

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <immintrin.h>
@@ -14,6 +15,7 @@
 #include "gcmesh_kernel.cuh"
 #include "gclight_kernel.cuh"
 #include "gcrle_kernel.cuh"
+#include "gcedit_kernel.cuh"
 
 using namespace gc;
 
@@ -117,6 +119,13 @@ struct GcWorld
     uint32_t* d_sun_list; size_t sun_list_cap;
     uint32_t* d_light_list; size_t light_list_cap;
     int light_launches; uint32_t light_stats[4];
+    // block edits (gcmesh_world_set_blocks)
+    int32_t* d_vert_table;        // per brick: vertices of its last build (written by the mesh kernel), -1 = never built
+    uint8_t* d_edit_dirty;        // per brick: flagged for rebuild
+    uint32_t* d_edit_state; uint8_t* d_edit_save; uint32_t* d_edit_sun_list; uint32_t* d_edit_light_list;
+    GcBlockEdit* d_edits; size_t edits_cap;
+    int32_t* d_edit_status; size_t edit_status_cap;
+    GcChunkCoord* d_edit_coords; GcChunkCoord* h_edit_coords; uint32_t* h_edit_count;   // rebuild list (n_slots entries) + its length, host copies pinned
     // region-record (RLE) transfer scratch, grown on demand
     uint16_t* d_rle_data; size_t rle_data_cap;         // the uint16 stream
     uint32_t* d_rle_ends; size_t rle_ends_cap;         // one run end per (count, block) pair
@@ -376,6 +385,8 @@ int gcmesh_world_create(GcContext* ctx, int size_x, int size_z, GcWorld** out)
     if (e == cudaSuccess) e = cudaMemsetAsync(w->d_surface, 0, w->n_cols * GC_CHUNK_SIZE_2, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_items, sizeof(uint32_t) * w->n_slots * 3);
     if (e == cudaSuccess) e = cudaMalloc(&w->d_items, sizeof(uint32_t) * w->n_slots * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_vert_table, sizeof(int32_t) * w->n_slots);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w->d_vert_table, 0xFF, sizeof(int32_t) * w->n_slots, ctx->stream);   // -1: never built
     if (e != cudaSuccess) { gcmesh_world_destroy(w); return fail(GC_ERR_CUDA, "world allocation", cudaGetErrorString(e)); }
     w->slot_dirty = (uint8_t*)calloc(w->n_slots, 1);
     w->scan_flags = (uint8_t*)calloc(w->n_slots, 1);
@@ -401,6 +412,10 @@ int gcmesh_world_destroy(GcWorld* w)
     if (w->h_rle_words) cudaFreeHost(w->h_rle_words);
     cudaFree(w->d_light_counters); cudaFree(w->d_brick_flags); cudaFree(w->d_active_list); cudaFree(w->d_sun_list); cudaFree(w->d_light_list);
     if (w->h_light_counters) cudaFreeHost(w->h_light_counters);
+    cudaFree(w->d_vert_table); cudaFree(w->d_edit_dirty); cudaFree(w->d_edit_state); cudaFree(w->d_edit_save);
+    cudaFree(w->d_edit_sun_list); cudaFree(w->d_edit_light_list); cudaFree(w->d_edits); cudaFree(w->d_edit_status); cudaFree(w->d_edit_coords);
+    if (w->h_edit_coords) cudaFreeHost(w->h_edit_coords);
+    if (w->h_edit_count) cudaFreeHost(w->h_edit_count);
     free(w->slot_dirty); free(w->scan_flags);
     delete w;
     return GC_OK;
@@ -792,6 +807,86 @@ int gcmesh_world_download(GcWorld* w, uint16_t* blocks, uint8_t* sunlight, uint8
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Block edits on the device window: SetBlock -> ChunkOverflowed -> RecomputeLight -> FlagChunkForUpdate
+// (World.cpp:507-582, WorldRender.cpp:412-439, Lighting.cpp:283-449); kernels in gcedit_kernel.cu.
+int gcmesh_world_set_blocks(GcWorld* w, const GcBlockEdit* edits, int n, int32_t* status, GcChunkCoord* rebuild, int rebuild_capacity, int* n_rebuild)
+{
+    if (n_rebuild) *n_rebuild = 0;
+    if (!w || (!edits && n > 0)) return fail(GC_ERR_ARG, "null argument");
+    if (n < 0 || rebuild_capacity < 0 || (!rebuild && rebuild_capacity > 0)) return fail(GC_ERR_ARG, "bad edit or rebuild list size");
+    if (w->n_slots > 65535) return fail(GC_ERR_CAPACITY, "light fill addresses voxels with 32 bits: at most 65535 bricks per window");
+    for (int i = 0; i < n; i++)
+    {
+        // SetBlock asserts !IsEdgeChunk (World.cpp:560); a position outside the window has no chunk at all
+        const int cx = edits[i].wx >> 5, cz = edits[i].wz >> 5;
+        if (edits[i].wx < 0 || edits[i].wz < 0 || cx < 1 || cx >= w->size_x - 1 || cz < 1 || cz >= w->size_z - 1)
+            return fail(GC_ERR_ARG, "edit outside the pre-processed (non-edge) columns of the window");
+    }
+    if (n == 0) return GC_OK;
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (!w->d_edit_state)
+    {
+        GC_CUDA(cudaMalloc(&w->d_edit_dirty, w->n_slots));
+        GC_CUDA(cudaMemsetAsync(w->d_edit_dirty, 0, w->n_slots, s));
+        GC_CUDA(cudaMalloc(&w->d_edit_save, 2 * (size_t)kEditBoxCells));
+        GC_CUDA(cudaMalloc(&w->d_edit_sun_list, sizeof(uint32_t) * kEditBoxCells));
+        GC_CUDA(cudaMalloc(&w->d_edit_light_list, sizeof(uint32_t) * kEditBoxCells));
+        GC_CUDA(cudaMalloc(&w->d_edit_coords, sizeof(GcChunkCoord) * w->n_slots));
+        GC_CUDA(cudaMallocHost(&w->h_edit_coords, sizeof(GcChunkCoord) * w->n_slots));
+        GC_CUDA(cudaMallocHost(&w->h_edit_count, sizeof(uint32_t)));
+        GC_CUDA(cudaMalloc(&w->d_edit_state, sizeof(uint32_t) * (kEditStateWords + 1)));   // + the rebuild count
+    }
+    if (grow_device(&w->d_edits, &w->edits_cap, (size_t)n) != GC_OK) return GC_ERR_CUDA;
+    if (grow_device(&w->d_edit_status, &w->edit_status_cap, (size_t)n) != GC_OK) return GC_ERR_CUDA;
+    GC_CUDA(cudaMemcpyAsync(w->d_edits, edits, sizeof(GcBlockEdit) * n, cudaMemcpyHostToDevice, s));
+    EditArgs a;
+    a.w = light_world(w); a.blocks_rw = w->d_blocks; a.tables = ctx->d_tables; a.vert_table = w->d_vert_table;
+    a.edits = w->d_edits; a.status = w->d_edit_status; a.dirty = w->d_edit_dirty; a.state = w->d_edit_state;
+    a.save = w->d_edit_save; a.sun_list = w->d_edit_sun_list; a.light_list = w->d_edit_light_list;
+    for (int i = 0; i < n; i++)
+    {
+        EditBox box;
+        box.x0 = edits[i].wx - kEditRadius; box.z0 = edits[i].wz - kEditRadius; box.nx = kEditSpan; box.nz = kEditSpan;
+        GC_CUDA(launch_edit(a, i, box, s));
+    }
+    uint32_t* d_count = w->d_edit_state + kEditStateWords;
+    GC_CUDA(launch_edit_list(a.w, w->d_edit_dirty, w->d_edit_coords, d_count, s));
+    GC_CUDA(cudaMemcpyAsync(w->h_edit_count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (status) GC_CUDA(cudaMemcpyAsync(status, w->d_edit_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    GC_CUDA(cudaStreamSynchronize(s));
+    const uint32_t flagged = *w->h_edit_count;
+    if (flagged)
+    {
+        GC_CUDA(cudaMemcpyAsync(w->h_edit_coords, w->d_edit_coords, sizeof(GcChunkCoord) * flagged, cudaMemcpyDeviceToHost, s));
+        GC_CUDA(cudaStreamSynchronize(s));
+        std::sort(w->h_edit_coords, w->h_edit_coords + flagged, [](const GcChunkCoord& p, const GcChunkCoord& q)
+        {
+            if (p.cz != q.cz) return p.cz < q.cz;
+            if (p.cx != q.cx) return p.cx < q.cx;
+            return p.cy < q.cy;
+        });
+    }
+    // the sparse-upload bookkeeping no longer knows what the device arrays hold
+    memset(w->slot_dirty, 7, w->n_slots);
+    if (n_rebuild) *n_rebuild = (int)flagged;
+    const uint32_t stored = flagged < (uint32_t)rebuild_capacity ? flagged : (uint32_t)rebuild_capacity;
+    if (stored) memcpy(rebuild, w->h_edit_coords, sizeof(GcChunkCoord) * stored);
+    if (flagged > (uint32_t)rebuild_capacity) return fail(GC_ERR_CAPACITY, "more chunks flagged for rebuild than the list holds");
+    return GC_OK;
+}
+
+int gcmesh_world_vertex_counts(GcWorld* w, int32_t* counts)
+{
+    if (!w || !counts) return fail(GC_ERR_ARG, "null argument");
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    GC_CUDA(cudaMemcpyAsync(counts, w->d_vert_table, sizeof(int32_t) * w->n_slots, cudaMemcpyDeviceToHost, w->ctx->stream));
+    GC_CUDA(cudaStreamSynchronize(w->ctx->stream));
+    return GC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Region records (the reference's saved-chunk format, WorldIO.cpp:167-307) in and out of the device world.
 int gcmesh_world_upload_rle(GcWorld* w, const GcRleChunk* chunks, int n, const uint16_t* data, size_t data_words)
 {
@@ -984,6 +1079,7 @@ static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cu
     p.vertex_arena = b->d_vertices; p.index_arena = b->d_indices; p.max_quads = b->max_quads;
     p.quad_cursor = b->d_cursor; p.work_counter = b->d_counters; p.tables = ctx->d_tables;
     p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma; p.prof = b->d_prof;
+    p.vert_table = w->d_vert_table;
     const int grid = count < ctx->mesh_ctas ? count : ctx->mesh_ctas;
     e = launch_mesh(p, w->maps, grid, s);
     if (e == cudaSuccess) b->launches++;

@@ -495,6 +495,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 o.quad_base = 0; o.vert_count = 0; o.quads = 0; o.flags = 0; o.reserved[0] = 0; o.reserved[1] = 0;
                 for (int t = 0; t < kMeshTypes; t++) { o.index_count[t] = 0; o.index_offset[t] = 0; }
                 p.out[chunk] = o;
+                if (p.vert_table) { const GcChunkCoord c = p.coords[chunk]; p.vert_table[(c.cz * p.size_x + c.cx) * 4 + c.cy] = 0; }
             }
             GC_PROF_MARK(3);
             continue;
@@ -581,6 +582,11 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 s_ctx->quad_base = o.quad_base;
                 s_ctx->total = total;
                 p.out[chunk] = o;
+                if (p.vert_table)   // chunk->totalVertices (WorldRender.cpp:559)
+                {
+                    const GcChunkCoord c = p.coords[chunk];
+                    p.vert_table[(c.cz * p.size_x + c.cx) * 4 + c.cy] = (int32_t)(total * 4);
+                }
             }
         }
         __syncthreads();

@@ -30,6 +30,7 @@ struct MeshParams
     const int32_t* order;              // optional: the k-th claimed work item is chunk order[k] (heaviest first), null = k
     int32_t n_chunks;
     GcChunkOut* out;
+    int32_t* vert_table;               // optional, per brick of the window: vertices of its last build (chunk->totalVertices), -1 = never built
     uint8_t* vertex_arena;
     uint16_t* index_arena;
     unsigned long long max_quads;

@@ -29,7 +29,7 @@ CHUNK_NO_SPACE = 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcmesh_api.cu"]
+SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcedit_kernel.cu", "gcmesh_api.cu"]
 HEADERS = ["gcmesh_kernel.cuh", "gclight_kernel.cuh", "gcrle_kernel.cuh", "mesh_core.cuh", os.path.join("..", "..", "include", "gcmesh.h")]
 
 
@@ -65,6 +65,8 @@ class ChunkOut(ctypes.Structure):
 CHUNK_OUT_DTYPE = np.dtype([("quad_base", "<u4"), ("vert_count", "<u4"), ("index_count", "<u4", (5,)),
                             ("index_offset", "<u4", (5,)), ("quads", "<u4"), ("flags", "<u4"), ("reserved", "<u4", (2,))])
 assert CHUNK_OUT_DTYPE.itemsize == ctypes.sizeof(ChunkOut) == 64
+BLOCK_EDIT_DTYPE = np.dtype([("wx", "<i4"), ("wy", "<i4"), ("wz", "<i4"), ("block", "<u2"), ("reserved", "<u2")])   # GcBlockEdit
+EDIT_APPLIED, EDIT_UNCHANGED, EDIT_IGNORED, EDIT_NOT_BUILT, EDIT_OVERFLOW = range(5)                                   # GC_EDIT_*
 RLE_CHUNK_DTYPE = np.dtype([("cx", "<i4"), ("cy", "<i4"), ("cz", "<i4"), ("first_word", "<u4"), ("words", "<u4")])   # GcRleChunk
 
 EXPORTS = [
@@ -76,6 +78,7 @@ EXPORTS = [
     "gcmesh_default_light_rules", "gcmesh_set_light_rules", "gcmesh_world_compute_surface", "gcmesh_world_light",
     "gcmesh_world_light_stats", "gcmesh_world_download",
     "gcmesh_world_upload_rle", "gcmesh_world_rle_refused", "gcmesh_world_encode_rle",
+    "gcmesh_world_set_blocks", "gcmesh_world_vertex_counts",
     "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_mesh_host", "gcmesh_wait", "gcmesh_batch_results",
     "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
     "gcmesh_batch_launches", "gcmesh_kernel_info", "gcmesh_batch_profile",
@@ -122,6 +125,8 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_upload_rle.argtypes = [vp, vp, ci, vp, ctypes.c_size_t]
         L.gcmesh_world_rle_refused.argtypes = [vp, ctypes.POINTER(ci)]
         L.gcmesh_world_encode_rle.argtypes = [vp, vp, ci, vp, ctypes.c_size_t, vp]
+        L.gcmesh_world_set_blocks.argtypes = [vp, vp, ci, vp, vp, ci, ctypes.POINTER(ci)]
+        L.gcmesh_world_vertex_counts.argtypes = [vp, vp]
         L.gcmesh_batch_create.argtypes = [vp, ci, ctypes.c_uint64, ctypes.POINTER(vp)]
         L.gcmesh_batch_destroy.argtypes = [vp]
         L.gcmesh_submit.argtypes = [vp, vp, vp, ci]
@@ -294,6 +299,24 @@ class World:
         _check(lib().gcmesh_world_encode_rle(self.h, _ptr(coords), len(coords), _ptr(data), cap, _ptr(out)), "gcmesh_world_encode_rle")
         used = int(out["first_word"][-1] + out["words"][-1]) if len(out) else 0
         return out, data[:used]
+
+    def set_blocks(self, edits, rebuild_capacity: int | None = None):
+        """SetBlock for each (wx, wy, wz, block) in order on the device window -> (status per edit, (n, 3) chunks to rebuild)."""
+        rows = [tuple(int(v) for v in e) + (0,) for e in edits]
+        ed = np.array(rows, BLOCK_EDIT_DTYPE) if rows else np.zeros(0, BLOCK_EDIT_DTYPE)
+        status = np.full(len(ed), -1, np.int32)
+        cap = self.size_x * self.size_z * 4 if rebuild_capacity is None else int(rebuild_capacity)
+        rebuild = np.zeros((max(cap, 1), 3), np.int32)
+        n = ctypes.c_int(0)
+        _check(lib().gcmesh_world_set_blocks(self.h, _ptr(ed) if len(ed) else None, len(ed), _ptr(status) if len(ed) else None,
+                                             _ptr(rebuild) if cap else None, cap, ctypes.byref(n)), "gcmesh_world_set_blocks")
+        return status, rebuild[: n.value].copy()
+
+    def vertex_counts(self) -> np.ndarray:
+        """chunk->totalVertices per brick, shaped (size_z, size_x, 4); -1 = never meshed."""
+        out = np.zeros(self.size_x * self.size_z * 4, np.int32)
+        _check(lib().gcmesh_world_vertex_counts(self.h, _ptr(out)), "gcmesh_world_vertex_counts")
+        return out.reshape(self.size_z, self.size_x, 4)
 
     def download(self, host, blocks: bool = False, sun: bool = True, light: bool = True, surface: bool = True) -> None:
         """Device -> host copy into a HostWorld-shaped object's arrays."""

@@ -186,6 +186,44 @@ int gcmesh_world_rle_refused(GcWorld* world, int* refused);
  * `capacity_words` uint16), out[i] says where chunk i's record lies; offset = RegionIndex(pos & REGION_MASK).  Synchronous. */
 int gcmesh_world_encode_rle(GcWorld* world, const GcChunkCoord* coords, int n, uint16_t* records, size_t capacity_words, GcRleChunk* out);
 
+/* ---- block edits on a device-resident window: the interactive caller of the mesher ----
+ * SetBlock(world, lwX, lwY, lwZ, block) (Code/World.cpp:548-582) for a window whose block ids, surface map and light
+ * arrays are on the device (gcmesh_world_compute_surface + gcmesh_world_light, or uploads):
+ *   - the reference's decisions: y outside the world is ignored; a chunk that was never meshed refuses the edit
+ *     (chunk->state < CHUNK_NEEDS_FILL; here: no gcmesh_submit has covered it); an unchanged block does nothing;
+ *     ChunkOverflowed (WorldRender.cpp:412-439) — the new block's own drawable faces on top of the chunk's vertex count
+ *     of its last build — leaves AIR in the cell and neither relights nor flags, exactly as the reference does;
+ *   - RecomputeLight (Lighting.cpp:283-449): the column's surface entry is recomputed (a column left without any block
+ *     reads 0, the value a freshly generated empty column has) and both light arrays are refilled inside the full-height
+ *     box of radius 16 around the edited column from the unchanged cells around it.  The result is what
+ *     gcmesh_world_light computes from scratch on the edited blocks — the reference's own fill of that world when it is
+ *     next loaded; its incremental queues can stop a few cells short of that;
+ *   - FlagChunkForUpdate (World.cpp:507-546): the chunks around the edited cell, plus every chunk that has a cell whose
+ *     block, blockLight or effective sunlight changed inside its one-voxel halo.  Chunks outside the list mesh to the
+ *     bytes they meshed to before.
+ * Edits are applied in order; the caller's player-overlap test (World.cpp:552) stays with the caller. */
+typedef struct GcBlockEdit
+{
+    int32_t wx, wy, wz;     /* window voxel coordinates (LWorldP): 0 <= wx < 32*size_x, 0 <= wz < 32*size_z; edge columns are rejected */
+    uint16_t block;
+    uint16_t reserved;
+} GcBlockEdit;
+enum
+{
+    GC_EDIT_APPLIED = 0,        /* block stored, light refilled, chunks flagged */
+    GC_EDIT_UNCHANGED = 1,      /* the cell already held this block */
+    GC_EDIT_IGNORED = 2,        /* wy outside 0..255 (World.cpp:550) */
+    GC_EDIT_NOT_BUILT = 3,      /* the chunk has never been meshed (World.cpp:562-565) */
+    GC_EDIT_OVERFLOW = 4        /* ChunkOverflowed: the cell now holds AIR (World.cpp:572-573) */
+};
+/* status: n entries (GC_EDIT_*), may be NULL.  rebuild: up to rebuild_capacity coordinates, sorted by (cz, cx, cy);
+ * *n_rebuild = how many chunks are flagged (GC_ERR_CAPACITY when more than fit; the first rebuild_capacity are stored).
+ * Runs on the context stream behind earlier submissions; synchronous. */
+int gcmesh_world_set_blocks(GcWorld* world, const GcBlockEdit* edits, int n, int32_t* status,
+                            GcChunkCoord* rebuild, int rebuild_capacity, int* n_rebuild);
+/* chunk->totalVertices of every brick ((cz * size_x + cx) * 4 + cy; -1 = never meshed) as the last submissions left it. */
+int gcmesh_world_vertex_counts(GcWorld* world, int32_t* counts);
+
 /* ---- batches: one GPU submission = the reference's vector<Chunk*> job (WorldRender.cpp:29-37) ---- */
 /* Arenas for up to max_chunks chunks and max_quads quads in total (48 B of vertices + 12 B of indices per quad). */
 int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBatch** out);

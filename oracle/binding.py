@@ -102,6 +102,7 @@ def oracle_lib() -> ctypes.CDLL:
         L.gcor_default_light_rules.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.gcor_rle_encode_chunk.argtypes = [ctypes.c_void_p, ctypes.c_uint16, ctypes.c_void_p]
         L.gcor_rle_decode_chunk.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.gcor_set_block.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_void_p]
         _olib = L
     return _olib
 
@@ -128,6 +129,9 @@ def ref_lib() -> ctypes.CDLL:
         L.gcref_light_all.argtypes = [ctypes.c_void_p]
         L.gcref_build_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.gcref_chunk_overflowed.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 7
+        L.gcref_set_block.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4
+        L.gcref_set_chunk_built.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5
+        L.gcref_pending_updates.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.gcref_bench_build.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
         L.gcref_bench_build.restype = ctypes.c_double
         _rlib = L
@@ -173,6 +177,18 @@ def rle_decode_chunk(record: np.ndarray):
     out = np.zeros(65536, np.uint16)
     st = oracle_lib().gcor_rle_decode_chunk(rec.ctypes.data, len(rec), out.ctypes.data)
     return st, out
+
+
+def set_block(host, vert_table, wx, wy, wz, block, flagged, cull=None, kill_zone=20) -> int:
+    """SetBlock's decisions on a HostWorld's blocks / surface (edited in place) -> GC_EDIT_* status; marks flagged[slot]."""
+    if cull is None:
+        cull = np.zeros(256, np.uint8)
+        table, n, kill_zone = default_block_table()
+        for i in range(n):
+            cull[i] = table[i].cull
+    vert_table = np.ascontiguousarray(vert_table, np.int32)
+    return oracle_lib().gcor_set_block(host.size_x, host.size_z, host.blocks.ctypes.data, host.surface.ctypes.data, vert_table.ctypes.data,
+                                       cull.ctypes.data, kill_zone, int(wx), int(wy), int(wz), int(block), flagged.ctypes.data)
 
 
 def default_block_table():
@@ -311,6 +327,19 @@ class RefWorld:
 
     def chunk_overflowed(self, cx, cy, cz, x, y, z, total_vertices) -> bool:
         return bool(self.L.gcref_chunk_overflowed(self.h, cx, cy, cz, x, y, z, total_vertices))
+
+    def set_block(self, wx, wy, wz, block) -> bool:
+        """The reference's own SetBlock (overflow pre-check, RecomputeLight, FlagChunkForUpdate); True if the stored block changed."""
+        return bool(self.L.gcref_set_block(self.h, int(wx), int(wy), int(wz), int(block)))
+
+    def set_chunk_built(self, cx, cy, cz, built=True, total_vertices=0):
+        self.L.gcref_set_chunk_built(self.h, int(cx), int(cy), int(cz), int(bool(built)), int(total_vertices))
+
+    def pending_updates(self, clear=True) -> np.ndarray:
+        """chunk->pendingUpdate of every chunk, shaped (size_z, size_x, 4)."""
+        out = np.zeros(self.size * self.size * 4, np.uint8)
+        self.L.gcref_pending_updates(self.h, out.ctypes.data, int(clear))
+        return out.reshape(self.size, self.size, 4)
 
     def bench(self, coords: np.ndarray, threads: int):
         coords = np.ascontiguousarray(coords, np.int32)

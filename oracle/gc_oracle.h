@@ -90,6 +90,9 @@ void gcor_default_light_rules(uint8_t* step, uint8_t* emitted);
 /* ---- region chunk format (gc_rle_cpu.c): SaveGroup / LoadGroupFromDisk's run-length coding of a chunk's block ids ---- */
 int gcor_rle_encode_chunk(const uint16_t* blocks, uint16_t offset, uint16_t* out /* 2 + 131072 words */);
 int gcor_rle_decode_chunk(const uint16_t* record, int words, uint16_t* blocks);
+/* ---- block edits (gc_edit_cpu.c): SetBlock's decisions, stored block, surface entry and FlagChunkForUpdate set ---- */
+int gcor_set_block(int size_x, int size_z, uint16_t* blocks, uint8_t* surface, const int32_t* vert_table, const uint8_t* cull,
+                   int kill_zone, int wx, int wy, int wz, int block, uint8_t* flagged);
 /* FNV-1a-64 over bytes (used for golden digests). */
 uint64_t gcor_fnv1a64(const void* data, uint64_t n, uint64_t h);
 

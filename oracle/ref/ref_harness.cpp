@@ -336,6 +336,38 @@ int gcref_chunk_overflowed(GcRefWorld* w, int cx, int cy, int cz, int x, int y, 
     return ChunkOverflowed(w->world, chunk, x, y, z) ? 1 : 0;
 }
 
+// SetBlock (World.cpp:548-582) as the interactive caller runs it: ChunkOverflowed pre-check, RecomputeLight,
+// FlagChunkForUpdate.  The player-overlap test is stubbed to "no overlap".  Returns 1 when the stored block differs from
+// what it was before the call.
+int gcref_set_block(GcRefWorld* w, int lwX, int lwY, int lwZ, int block)
+{
+    if (lwY < 0 || lwY >= WORLD_BLOCK_HEIGHT) { SetBlock(w->world, lwX, lwY, lwZ, (Block)block); return 0; }
+    const Block before = GetBlock(w->world, lwX, lwY, lwZ);
+    SetBlock(w->world, lwX, lwY, lwZ, (Block)block);
+    return GetBlock(w->world, lwX, lwY, lwZ) != before ? 1 : 0;
+}
+
+// chunk->state / totalVertices / pendingUpdate as the edit path reads and writes them (World.h:74-99)
+void gcref_set_chunk_built(GcRefWorld* w, int cx, int cy, int cz, int built, int totalVertices)
+{
+    Chunk* chunk = RefGroup(w, cx, cz)->chunks + cy;
+    chunk->state = built ? CHUNK_BUILT : CHUNK_LOADED_DATA;
+    chunk->totalVertices = totalVertices;
+}
+
+// out[(cz * size + cx) * 4 + cy] = pendingUpdate; clear != 0 resets the flags afterwards
+void gcref_pending_updates(GcRefWorld* w, uint8_t* out, int clear)
+{
+    for (int cz = 0; cz < w->size; cz++)
+        for (int cx = 0; cx < w->size; cx++)
+            for (int cy = 0; cy < WORLD_CHUNK_HEIGHT; cy++)
+            {
+                Chunk* chunk = RefGroup(w, cx, cz)->chunks + cy;
+                out[(cz * w->size + cx) * 4 + cy] = chunk->pendingUpdate ? 1 : 0;
+                if (clear) { chunk->pendingUpdate = false; chunk->modified = false; }
+            }
+}
+
 // Multi-threaded mesh-build timing: the reference's one-chunk-per-job queue (Async.cpp:5-35) restated as
 // an atomic counter; each worker owns a private MeshData (the pool hands one per job, WorldRender.cpp:61-67).
 // coords: n x (cx,cy,cz).  Returns seconds; *quadsOut = total quads.

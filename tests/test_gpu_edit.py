@@ -1,0 +1,201 @@
+"""Block edits on a device-resident window (gcmesh_world_set_blocks, through the C ABI) against the edit oracle
+(oracle/gc_edit_cpu.c for the decisions, the from-scratch fill of oracle/gc_light_cpu.c for the light) and against the
+mesher oracle for the chunks the call flags — and for the ones it does not."""
+import numpy as np
+import pytest
+
+import gcutil as util
+from oracle import binding as ob
+from test_edit_oracle import random_edit, effective_sun, APPLIED, UNCHANGED, IGNORED, NOT_BUILT, OVERFLOW
+
+pytestmark = pytest.mark.gpu
+
+LANTERN, STONE, WATER, GLASS, MAGMA = 14, 3, 8, 22, 17
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gamecraft_b200 import mesher
+
+    c = mesher.Context(0)
+    yield c
+    c.close()
+
+
+def to_window(w, arr):
+    """brick-major (slot, voxel) -> (Z, Y, X) over the whole window."""
+    a = arr.reshape(w.size_z, w.size_x, 4, 32, 64, 32)                       # cz, cx, cy, z, y, x
+    return a.transpose(0, 3, 2, 4, 1, 5).reshape(w.size_z * 32, 256, w.size_x * 32)
+
+
+def chunks_seeing(w, changed):
+    """(Z, Y, X) mask of changed cells -> per-slot flags of the chunks that have one inside their one-voxel halo."""
+    d = changed.copy()
+    for axis in range(3):
+        lo = [slice(None)] * 3; hi = [slice(None)] * 3
+        lo[axis] = slice(0, -1); hi[axis] = slice(1, None)
+        e = d.copy()
+        e[tuple(lo)] |= d[tuple(hi)]
+        e[tuple(hi)] |= d[tuple(lo)]
+        d = e
+    per = d.reshape(w.size_z, 32, 4, 64, w.size_x, 32).any(axis=(1, 3, 5))   # cz, cy, cx
+    return per.transpose(0, 2, 1).reshape(-1).astype(np.uint8)               # slot = (cz * size_x + cx) * 4 + cy
+
+
+def interior_only(w, flags):
+    f = flags.reshape(w.size_z, w.size_x, 4).copy()
+    f[0] = 0; f[-1] = 0; f[:, 0] = 0; f[:, -1] = 0
+    return [(cx, cy, cz) for cz in range(w.size_z) for cx in range(w.size_x) for cy in range(4) if f[cz, cx, cy]]
+
+
+def device_world(ctx, host):
+    """blocks only up, surface + light computed on the device, every interior chunk meshed once."""
+    from gamecraft_b200 import mesher
+
+    world = mesher.World(ctx, host.size_x, host.size_z).upload(host)
+    world.compute_surface().light()
+    meshes = mesher.rebuild_chunks(world, host.interior_chunks())
+    return world, meshes
+
+
+def snapshot(world, like):
+    out = util.HostWorld(like.size_x, like.size_z)
+    world.download(out, blocks=True)
+    return out
+
+
+def oracle_edit(h, verts, edit):
+    """One edit on the host copy: status, FlagChunkForUpdate flags, and the from-scratch fill of the edited blocks."""
+    flagged = np.zeros(h.size_x * h.size_z * 4, np.uint8)
+    before_sun, before_light = to_window(h, effective_sun(h)), to_window(h, h.light).copy()
+    status = ob.set_block(h, verts, *edit, flagged)
+    if status == APPLIED:
+        h.sun[:], h.light[:] = ob.light_fill(h, h.surface)
+        changed = (to_window(h, effective_sun(h)) != before_sun) | (to_window(h, h.light) != before_light)
+        flagged |= chunks_seeing(h, changed)
+    return status, flagged
+
+
+@pytest.mark.parametrize("kind,seed", [("forest", 1), ("noise", 2), ("mixed", 3), ("islands", 8)])
+def test_edits_relight_and_flag_like_the_oracle(ctx, kind, seed):
+    from gamecraft_b200 import mesher
+
+    size = 5
+    kw = dict(radius=90, falloff=50) if kind in ("islands", "mixed") else {}
+    src = util.HostWorld(size, size).generate(kind, seed, **kw)
+    blank = util.HostWorld(size, size)
+    blank.blocks[:] = src.blocks
+    world, meshes = device_world(ctx, blank)
+    h = snapshot(world, blank)
+    assert np.array_equal(h.surface, ob.compute_surface(h))
+    coords = h.interior_chunks()
+    verts = world.vertex_counts().reshape(-1)
+    for (cx, cy, cz), m in zip(coords, meshes):
+        assert verts[(cz * size + cx) * 4 + cy] == m.vert_count
+    edge = verts.reshape(size, size, 4)
+    assert (edge[0] == -1).all() and (edge[:, 0] == -1).all()                # never meshed
+    current = {tuple(c): m for c, m in zip(coords.tolist(), meshes)}
+    rng = np.random.default_rng(seed)
+    extra = [WATER, GLASS, MAGMA, 21, 13]
+    for step in range(8):
+        edits = []
+        for k in range(1 if step % 3 else 3):                                # single edits and short batches
+            wx, wy, wz, b = random_edit(rng, h, size)
+            if (step + k) % 4 == 1:
+                b = extra[(step + k) % len(extra)]
+            edits.append((wx, wy, wz, b))
+        want_status, want_flags = [], np.zeros(size * size * 4, np.uint8)
+        for e in edits:
+            st, fl = oracle_edit(h, verts, e)
+            want_status.append(st); want_flags |= fl
+        status, rebuild = world.set_blocks(edits)
+        assert status.tolist() == want_status, "step %d %r" % (step, edits)
+        got = snapshot(world, h)
+        assert np.array_equal(got.blocks, h.blocks)
+        assert np.array_equal(got.surface, h.surface)
+        assert np.array_equal(got.sun, h.sun), "step %d: %d sunlight cells differ" % (step, int((got.sun != h.sun).sum()))
+        assert np.array_equal(got.light, h.light), "step %d: %d blockLight cells differ" % (step, int((got.light != h.light).sum()))
+        assert [tuple(c) for c in rebuild.tolist()] == sorted(interior_only(h, want_flags), key=lambda c: (c[2], c[0], c[1]))
+        # the flagged chunks mesh to the oracle's bytes of the edited world ...
+        if len(rebuild):
+            orc = ob.OracleWorld(h)
+            for c, m in zip(rebuild.tolist(), mesher.rebuild_chunks(world, rebuild)):
+                util.assert_same_mesh(m, orc.build_chunk(*c), "step %d chunk %r" % (step, c))
+                current[tuple(c)] = m
+        # ... and every other chunk to the bytes it had before
+        if step in (2, 7):
+            orc = ob.OracleWorld(h)
+            for c, m in current.items():
+                util.assert_same_mesh(m, orc.build_chunk(*c), "step %d unflagged chunk %r" % (step, c))
+        verts = world.vertex_counts().reshape(-1)
+    world.close()
+
+
+def test_edit_equals_a_fresh_fill_on_the_device(ctx):
+    """Same blocks, two routes on the device: edits with the regional refill vs upload + gcmesh_world_light from scratch."""
+    from gamecraft_b200 import mesher
+
+    size = 6
+    src = util.HostWorld(size, size).generate("mixed", 5, radius=90, falloff=50)
+    blank = util.HostWorld(size, size)
+    blank.blocks[:] = src.blocks
+    world, _ = device_world(ctx, blank)
+    h = snapshot(world, blank)
+    rng = np.random.default_rng(11)
+    edits = [random_edit(rng, h, size) for _ in range(12)]
+    # window corners of the interior: the refill box hangs over the window edge there
+    edits += [(32, 70, 32, LANTERN), (32 * (size - 1) - 1, 40, 32 * (size - 1) - 1, 0), (32, 254, 32 * (size - 1) - 1, STONE)]
+    status, rebuild = world.set_blocks(edits)
+    got = snapshot(world, h)
+    fresh = util.HostWorld(size, size)
+    fresh.blocks[:] = got.blocks
+    w2 = mesher.World(ctx, size, size).upload(fresh)
+    w2.compute_surface().light()
+    want = snapshot(w2, h)
+    w2.close(); world.close()
+    assert (status == APPLIED).sum() >= 10
+    assert np.array_equal(got.surface, want.surface)
+    assert np.array_equal(got.sun, want.sun)
+    assert np.array_equal(got.light, want.light)
+    assert len(rebuild) > 0
+
+
+def test_refusals(ctx):
+    """Never-built chunk, unchanged block, y outside the world, overflow (AIR left behind), edge columns, list capacity."""
+    from gamecraft_b200 import mesher
+
+    # centre chunk (1,1,1) with 1666 isolated voxels = 9 996 quads = 39 984 vertices: 16 vertices short of the cap
+    cells = [(x, y, z) for y in range(1, 63, 2) for z in range(1, 31, 2) for x in range(1, 29, 3)]
+    host = util.HostWorld(3, 3)
+    for i in range(1666):
+        x, y, z = cells[i]
+        host.set_block(32 + x, 64 + y, 32 + z, STONE)
+    world = mesher.World(ctx, 3, 3).upload(host)
+    world.compute_surface().light()
+    status, rebuild = world.set_blocks([(40, 70, 40, STONE)])
+    assert status.tolist() == [NOT_BUILT] and len(rebuild) == 0           # nothing meshed yet (World.cpp:562-565)
+    mesher.rebuild_chunks(world, [(1, 1, 1)])
+    assert world.vertex_counts()[1, 1, 1] == 1666 * 24
+    x, y, z = cells[1700]
+    free = (32 + x, 64 + y, 32 + z)
+    status, rebuild = world.set_blocks([free + (STONE,), (free[0], 300, free[2], STONE), (free[0], -1, free[2], STONE)])
+    # 39 984 + 24 > 40 000: refused, and the cell holds AIR
+    assert status.tolist() == [OVERFLOW, IGNORED, IGNORED] and len(rebuild) == 0
+    got = snapshot(world, host)
+    assert np.array_equal(got.blocks, host.blocks)
+    x, y, z = cells[0]
+    status, rebuild = world.set_blocks([(32 + x, 64 + y, 32 + z, STONE)])
+    assert status.tolist() == [UNCHANGED] and len(rebuild) == 0
+    status, rebuild = world.set_blocks([(32 + x + 1, 64 + y, 32 + z, STONE)])   # touches one voxel: 5 faces, 20 vertices > 16 left
+    assert status.tolist() == [OVERFLOW]
+    status, rebuild = world.set_blocks([(32 + x, 64 + y, 32 + z, 0)])           # removing never overflows
+    assert status.tolist() == [APPLIED] and [1, 1, 1] in rebuild.tolist()
+    with pytest.raises(mesher.GcMeshError):
+        world.set_blocks([(5, 70, 40, STONE)])                                # edge column (World.cpp:560)
+    with pytest.raises(mesher.GcMeshError):
+        world.set_blocks([(40, 70, 32 * 3 + 1, STONE)])                       # outside the window
+    # a list too short for the flagged chunks: the count is reported with GC_ERR_CAPACITY
+    mesher.rebuild_chunks(world, host.interior_chunks())
+    with pytest.raises(mesher.GcMeshError):
+        world.set_blocks([(48, 64, 48, STONE)], rebuild_capacity=1)           # y = 64: two chunks of the column see it
+    world.close()
