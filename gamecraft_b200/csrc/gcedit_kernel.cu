@@ -1,7 +1,8 @@
 // gcedit — one block edit on a device-resident window (see gcedit_kernel.cuh).
 //
 // Five steps per edit, each a small kernel over the full-height box of radius kEditRadius around the edited column
-// (33 x 33 x 256 cells, ~280 k threads: launch-latency bound, no host round trip in between):
+// (33 x 33 x 256 cells, ~280 k threads: launch-latency bound, no host round trip in between).  The kernels find the edit
+// through a device-side cursor, so their arguments never change and the host replays the sequence as one CUDA graph:
 //   save     effective sunlight (GetSunlight, Lighting.cpp:69-79: 15 at or above the surface, a stored 0 reads 1) and
 //            blockLight of every cell, as the mesher would read them before the edit
 //   apply    one warp: the decisions of SetBlock (World.cpp:548-582), the ChunkOverflowed count
@@ -30,15 +31,18 @@ struct Cell
     uint32_t v;           // index into the brick arenas
 };
 
-__device__ __forceinline__ Cell box_cell(const LightWorld& w, const EditBox& b, uint32_t i)
+// cell i of the box around the current edit (x fastest, then y, then z); cells outside the window are skipped
+__device__ __forceinline__ Cell box_cell(const EditArgs& a, uint32_t i)
 {
+    const LightWorld& w = a.w;
+    const GcBlockEdit e = a.edits[a.state[EP_CURSOR]];
     Cell c;
-    const int lx = (int)(i % (uint32_t)b.nx);
-    const uint32_t r = i / (uint32_t)b.nx;
+    const int lx = (int)(i % (uint32_t)kEditSpan);
+    const uint32_t r = i / (uint32_t)kEditSpan;
     c.y = (int)(r % GC_WORLD_BLOCK_HEIGHT);
     const int lz = (int)(r / GC_WORLD_BLOCK_HEIGHT);
-    c.x = b.x0 + lx; c.z = b.z0 + lz;
-    c.inside = lz < b.nz && c.x >= 0 && c.z >= 0 && c.x < w.size_x * 32 && c.z < w.size_z * 32;
+    c.x = e.wx - kEditRadius + lx; c.z = e.wz - kEditRadius + lz;
+    c.inside = c.x >= 0 && c.z >= 0 && c.x < w.size_x * 32 && c.z < w.size_z * 32;
     c.col = 0; c.v = 0;
     if (c.inside)
     {
@@ -78,11 +82,11 @@ __device__ void flag_around(const LightWorld& w, uint8_t* dirty, int x, int y, i
                 dirty[((size_t)cz * w.size_x + cx) * 4 + cy] = 1;
 }
 
-__global__ void __launch_bounds__(256) gc_edit_save_kernel(EditArgs a, EditBox b)
+__global__ void __launch_bounds__(256) gc_edit_save_kernel(EditArgs a)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kEditBoxCells) return;
-    const Cell c = box_cell(a.w, b, i);
+    const Cell c = box_cell(a, i);
     if (!c.inside) return;
     a.save[i] = (uint8_t)effective_sun(a.w, c);
     a.save[kEditBoxCells + i] = a.w.light[c.v];
@@ -99,9 +103,10 @@ __device__ __forceinline__ uint32_t block_safe(const EditArgs& a, int x, int y, 
     return a.blocks_rw[((size_t)col * 4 + (y >> 6)) * kVox + (x & 31) + 32 * ((y & 63) + 64 * (z & 31))];
 }
 
-__global__ void __launch_bounds__(32) gc_edit_apply_kernel(EditArgs a, int edit_index)
+__global__ void __launch_bounds__(32) gc_edit_apply_kernel(EditArgs a)
 {
     const int lane = threadIdx.x;
+    const uint32_t edit_index = a.state[EP_CURSOR];
     const GcBlockEdit e = a.edits[edit_index];
     const int x = e.wx, y = e.wy, z = e.wz;
     int status = GC_EDIT_APPLIED;
@@ -166,13 +171,13 @@ __global__ void __launch_bounds__(32) gc_edit_apply_kernel(EditArgs a, int edit_
     }
 }
 
-__global__ void __launch_bounds__(256) gc_edit_prepare_kernel(EditArgs a, EditBox b)
+__global__ void __launch_bounds__(256) gc_edit_prepare_kernel(EditArgs a)
 {
     if (a.state[ES_SKIP]) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     Cell c; c.inside = false;
-    if (i < kEditBoxCells) c = box_cell(a.w, b, i);
+    if (i < kEditBoxCells) c = box_cell(a, i);
     bool sun_cand = false, light_cand = false;
     if (c.inside)
     {
@@ -208,15 +213,17 @@ __global__ void __launch_bounds__(256) gc_edit_prepare_kernel(EditArgs a, EditBo
     if (light_cand) a.light_list[bl + __popc(ml & below)] = c.v;
 }
 
-__global__ void __launch_bounds__(256) gc_edit_diff_kernel(EditArgs a, EditBox b)
+__global__ void __launch_bounds__(256) gc_edit_diff_kernel(EditArgs a)
 {
     if (a.state[ES_SKIP]) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kEditBoxCells) return;
-    const Cell c = box_cell(a.w, b, i);
+    const Cell c = box_cell(a, i);
     if (!c.inside) return;
     if (effective_sun(a.w, c) != a.save[i] || a.w.light[c.v] != a.save[kEditBoxCells + i]) flag_around(a.w, a.dirty, c.x, c.y, c.z);
 }
+
+__global__ void gc_edit_next_kernel(EditArgs a) { a.state[EP_CURSOR] += 1; }
 
 __global__ void __launch_bounds__(256) gc_edit_list_kernel(LightWorld w, uint8_t* dirty, GcChunkCoord* out, uint32_t* n_out)
 {
@@ -231,14 +238,14 @@ __global__ void __launch_bounds__(256) gc_edit_list_kernel(LightWorld w, uint8_t
 }
 }  // namespace
 
-cudaError_t launch_edit(const EditArgs& a, int edit_index, const EditBox& box, cudaStream_t s)
+cudaError_t launch_edit(const EditArgs& a, cudaStream_t s)
 {
     const unsigned grid = (kEditBoxCells + 255u) / 256u;
     cudaError_t e = cudaMemsetAsync(a.state, 0, kEditStateWords * sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
-    gc_edit_save_kernel<<<grid, 256, 0, s>>>(a, box);
-    gc_edit_apply_kernel<<<1, 32, 0, s>>>(a, edit_index);
-    gc_edit_prepare_kernel<<<grid, 256, 0, s>>>(a, box);
+    gc_edit_save_kernel<<<grid, 256, 0, s>>>(a);
+    gc_edit_apply_kernel<<<1, 32, 0, s>>>(a);
+    gc_edit_prepare_kernel<<<grid, 256, 0, s>>>(a);
     for (int sweep = 0; sweep < kLightSweeps; sweep++)
     {
         e = launch_relax(a.w, true, a.sun_list, kEditBoxCells, a.state + ES_FLAGS + 1 + sweep, s, a.state + ES_SUN_CAND);
@@ -246,7 +253,8 @@ cudaError_t launch_edit(const EditArgs& a, int edit_index, const EditBox& box, c
         e = launch_relax(a.w, false, a.light_list, kEditBoxCells, a.state + ES_FLAGS + kLightSweeps + 2 + sweep, s, a.state + ES_LIGHT_CAND);
         if (e != cudaSuccess) return e;
     }
-    gc_edit_diff_kernel<<<grid, 256, 0, s>>>(a, box);
+    gc_edit_diff_kernel<<<grid, 256, 0, s>>>(a);
+    gc_edit_next_kernel<<<1, 1, 0, s>>>(a);
     return cudaGetLastError();
 }
 

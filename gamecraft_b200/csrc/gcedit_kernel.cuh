@@ -20,15 +20,11 @@ constexpr int kEditRadius = 16;
 constexpr int kEditSpan = 2 * kEditRadius + 1;
 constexpr uint32_t kEditBoxCells = (uint32_t)kEditSpan * kEditSpan * GC_WORLD_BLOCK_HEIGHT;
 
-struct EditBox
-{
-    int32_t x0, z0;       // window voxel coordinates of the box's low corner (may lie outside the window: cells are clipped)
-    int32_t nx, nz;       // kEditSpan each
-};
-
-// device words of one edit's progress; the relaxation flag words follow the layout of LC_FLAGS
+// device words of one edit's progress (cleared before each edit); the relaxation flag words follow the layout of LC_FLAGS
 enum { ES_SUN_CAND = 0, ES_LIGHT_CAND = 1, ES_SKIP = 2, ES_FLAGS = 8 };
 constexpr int kEditStateWords = ES_FLAGS + 2 * (kLightSweeps + 1);
+// ... followed by two words that live across the edits of one call: the rebuild count and the index of the current edit
+enum { EP_REBUILD_COUNT = kEditStateWords, EP_CURSOR = kEditStateWords + 1, kEditWords = kEditStateWords + 2 };
 
 struct EditArgs
 {
@@ -39,14 +35,16 @@ struct EditArgs
     const GcBlockEdit* edits;     // device copy of the caller's list
     int32_t* status;              // per edit: GC_EDIT_*
     uint8_t* dirty;               // per brick: 1 = rebuild
-    uint32_t* state;              // kEditStateWords
+    uint32_t* state;              // kEditWords
     uint8_t* save;                // 2 x kEditBoxCells: effective sunlight, blockLight before the edit
     uint32_t* sun_list;           // kEditBoxCells each
     uint32_t* light_list;
 };
 
-// the five kernels of one edit, enqueued back to back on `s` (no host round trip in between)
-cudaError_t launch_edit(const EditArgs& a, int edit_index, const EditBox& box, cudaStream_t s);
+// The kernels of one edit — the one state[EP_CURSOR] points at, which the last kernel advances — enqueued back to back
+// on `s`.  Nothing in the argument list depends on the edit, so the sequence can be captured once into a CUDA graph and
+// replayed per edit.
+cudaError_t launch_edit(const EditArgs& a, cudaStream_t s);
 // dirty bricks of the pre-processed (non-edge) columns -> coords (unordered), count in *n_out; clears the flags
 cudaError_t launch_edit_list(const LightWorld& w, uint8_t* dirty, GcChunkCoord* out, uint32_t* n_out, cudaStream_t s);
 }  // namespace gc

@@ -123,8 +123,8 @@ struct GcWorld
     int32_t* d_vert_table;        // per brick: vertices of its last build (written by the mesh kernel), -1 = never built
     uint8_t* d_edit_dirty;        // per brick: flagged for rebuild
     uint32_t* d_edit_state; uint8_t* d_edit_save; uint32_t* d_edit_sun_list; uint32_t* d_edit_light_list;
-    GcBlockEdit* d_edits; size_t edits_cap;
-    int32_t* d_edit_status; size_t edit_status_cap;
+    GcBlockEdit* d_edits; int32_t* d_edit_status;   // kEditsPerPass entries each (fixed, so the graph's arguments stay valid)
+    cudaGraphExec_t edit_graph; bool edit_graph_tried;
     GcChunkCoord* d_edit_coords; GcChunkCoord* h_edit_coords; uint32_t* h_edit_count;   // rebuild list (n_slots entries) + its length, host copies pinned
     // region-record (RLE) transfer scratch, grown on demand
     uint16_t* d_rle_data; size_t rle_data_cap;         // the uint16 stream
@@ -414,6 +414,7 @@ int gcmesh_world_destroy(GcWorld* w)
     if (w->h_light_counters) cudaFreeHost(w->h_light_counters);
     cudaFree(w->d_vert_table); cudaFree(w->d_edit_dirty); cudaFree(w->d_edit_state); cudaFree(w->d_edit_save);
     cudaFree(w->d_edit_sun_list); cudaFree(w->d_edit_light_list); cudaFree(w->d_edits); cudaFree(w->d_edit_status); cudaFree(w->d_edit_coords);
+    if (w->edit_graph) cudaGraphExecDestroy(w->edit_graph);
     if (w->h_edit_coords) cudaFreeHost(w->h_edit_coords);
     if (w->h_edit_count) cudaFreeHost(w->h_edit_count);
     free(w->slot_dirty); free(w->scan_flags);
@@ -826,6 +827,7 @@ int gcmesh_world_set_blocks(GcWorld* w, const GcBlockEdit* edits, int n, int32_t
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    constexpr int kEditsPerPass = 4096;
     if (!w->d_edit_state)
     {
         GC_CUDA(cudaMalloc(&w->d_edit_dirty, w->n_slots));
@@ -836,25 +838,50 @@ int gcmesh_world_set_blocks(GcWorld* w, const GcBlockEdit* edits, int n, int32_t
         GC_CUDA(cudaMalloc(&w->d_edit_coords, sizeof(GcChunkCoord) * w->n_slots));
         GC_CUDA(cudaMallocHost(&w->h_edit_coords, sizeof(GcChunkCoord) * w->n_slots));
         GC_CUDA(cudaMallocHost(&w->h_edit_count, sizeof(uint32_t)));
-        GC_CUDA(cudaMalloc(&w->d_edit_state, sizeof(uint32_t) * (kEditStateWords + 1)));   // + the rebuild count
+        GC_CUDA(cudaMalloc(&w->d_edits, sizeof(GcBlockEdit) * kEditsPerPass));
+        GC_CUDA(cudaMalloc(&w->d_edit_status, sizeof(int32_t) * kEditsPerPass));
+        GC_CUDA(cudaMalloc(&w->d_edit_state, sizeof(uint32_t) * kEditWords));
     }
-    if (grow_device(&w->d_edits, &w->edits_cap, (size_t)n) != GC_OK) return GC_ERR_CUDA;
-    if (grow_device(&w->d_edit_status, &w->edit_status_cap, (size_t)n) != GC_OK) return GC_ERR_CUDA;
-    GC_CUDA(cudaMemcpyAsync(w->d_edits, edits, sizeof(GcBlockEdit) * n, cudaMemcpyHostToDevice, s));
     EditArgs a;
     a.w = light_world(w); a.blocks_rw = w->d_blocks; a.tables = ctx->d_tables; a.vert_table = w->d_vert_table;
     a.edits = w->d_edits; a.status = w->d_edit_status; a.dirty = w->d_edit_dirty; a.state = w->d_edit_state;
     a.save = w->d_edit_save; a.sun_list = w->d_edit_sun_list; a.light_list = w->d_edit_light_list;
-    for (int i = 0; i < n; i++)
+    // One edit is ~34 tiny launches whose arguments never change (the kernels find the edit through a device-side cursor):
+    // captured once per world into a CUDA graph and replayed per edit.  GCMESH_EDIT_GRAPH=0, a stream that cannot be
+    // captured (the legacy default stream) or a failed capture fall back to plain launches of the same sequence.
+    if (!w->edit_graph_tried)
     {
-        EditBox box;
-        box.x0 = edits[i].wx - kEditRadius; box.z0 = edits[i].wz - kEditRadius; box.nx = kEditSpan; box.nz = kEditSpan;
-        GC_CUDA(launch_edit(a, i, box, s));
+        w->edit_graph_tried = true;
+        const char* env = getenv("GCMESH_EDIT_GRAPH");
+        if (!(env && env[0] == '0') && s != nullptr && s != cudaStreamLegacy)
+        {
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess)
+            {
+                const cudaError_t le = launch_edit(a, s);
+                const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                if (le == cudaSuccess && ce == cudaSuccess && graph && cudaGraphInstantiate(&w->edit_graph, graph, 0) != cudaSuccess) w->edit_graph = nullptr;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            cudaGetLastError();   // a failed capture leaves a sticky-free error behind; the fallback path starts clean
+        }
     }
-    uint32_t* d_count = w->d_edit_state + kEditStateWords;
+    for (int first = 0; first < n; first += kEditsPerPass)
+    {
+        const int count = n - first < kEditsPerPass ? n - first : kEditsPerPass;
+        GC_CUDA(cudaMemcpyAsync(w->d_edits, edits + first, sizeof(GcBlockEdit) * count, cudaMemcpyHostToDevice, s));
+        GC_CUDA(cudaMemsetAsync(w->d_edit_state + EP_CURSOR, 0, sizeof(uint32_t), s));
+        for (int i = 0; i < count; i++)
+        {
+            if (w->edit_graph) GC_CUDA(cudaGraphLaunch(w->edit_graph, s));
+            else GC_CUDA(launch_edit(a, s));
+        }
+        if (status) GC_CUDA(cudaMemcpyAsync(status + first, w->d_edit_status, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, s));
+        if (first + count < n) GC_CUDA(cudaStreamSynchronize(s));   // `edits` of the next pass overwrite the device copy
+    }
+    uint32_t* d_count = w->d_edit_state + EP_REBUILD_COUNT;
     GC_CUDA(launch_edit_list(a.w, w->d_edit_dirty, w->d_edit_coords, d_count, s));
     GC_CUDA(cudaMemcpyAsync(w->h_edit_count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (status) GC_CUDA(cudaMemcpyAsync(status, w->d_edit_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaStreamSynchronize(s));
     const uint32_t flagged = *w->h_edit_count;
     if (flagged)

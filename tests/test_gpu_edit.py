@@ -160,6 +160,30 @@ def test_edit_equals_a_fresh_fill_on_the_device(ctx):
     assert len(rebuild) > 0
 
 
+def test_graph_replay_equals_plain_launches(ctx, monkeypatch):
+    """The per-edit kernel sequence replayed as a CUDA graph (default) and launched kernel by kernel (GCMESH_EDIT_GRAPH=0)."""
+    size = 5
+    src = util.HostWorld(size, size).generate("noise", 9)
+    blank = util.HostWorld(size, size)
+    blank.blocks[:] = src.blocks
+    rng = np.random.default_rng(3)
+    results = []
+    for graph in ("1", "0"):
+        monkeypatch.setenv("GCMESH_EDIT_GRAPH", graph)
+        world, _ = device_world(ctx, blank)
+        h = snapshot(world, blank)
+        if not results:
+            edits = [random_edit(rng, h, size) for _ in range(10)]
+        status, rebuild = world.set_blocks(edits[:1])
+        status2, rebuild2 = world.set_blocks(edits[1:])
+        results.append((status.tolist() + status2.tolist(), rebuild.tolist(), rebuild2.tolist(), snapshot(world, h)))
+        world.close()
+    (s0, r0, q0, a0), (s1, r1, q1, a1) = results
+    assert s0 == s1 and r0 == r1 and q0 == q1
+    for x, y in ((a0.blocks, a1.blocks), (a0.sun, a1.sun), (a0.light, a1.light), (a0.surface, a1.surface)):
+        assert np.array_equal(x, y)
+
+
 def test_refusals(ctx):
     """Never-built chunk, unchanged block, y outside the world, overflow (AIR left behind), edge columns, list capacity."""
     from gamecraft_b200 import mesher
