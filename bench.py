@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p", help="N > 1: how slab neighbours trade boundary planes")
     ap.add_argument("--no-preprocess", action="store_true", help="skip the surface + light-fill leg (SURVEY 8(f1))")
     return ap.parse_args()
 
@@ -400,12 +401,14 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(workload, n_gpus, host, coords):
+def workload_config(workload, n_gpus, host, coords, exchange=None):
     kind, mx, mz, seed, radius = WORKLOADS[workload]
+    how = {"p2p": "boundary voxel planes stored straight into the neighbours' windows over NVLink peer memory (no collective)",
+           "nccl": "NCCL send/recv of boundary voxel planes"}.get(exchange, "")
     return {
         "workload": workload, "world": kind, "seed": seed, "chunks_per_gpu": int(len(coords)),
         "window_columns_per_gpu": [host.size_x, host.size_z], "chunk_voxels": "32x64x32",
-        "parallelism": "z-slab per GPU, NCCL send/recv of boundary voxel planes" if n_gpus > 1 else "single GPU",
+        "parallelism": ("z-slab per GPU, " + how) if n_gpus > 1 else "single GPU",
         "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" % (len(coords) * 262144 / 1e6),
     }
 
@@ -468,13 +471,38 @@ def main():
     batch = mesher.Batch(ctx, n, total_quads + 1)
 
     # ---- slab halo exchange (N > 1): boundary voxel planes to / from the z-neighbours ----
+    # Default: each rank stores its planes straight into its neighbours' windows over NVLink peer memory (CUDA IPC handles,
+    # gcmesh_world_halo_push: three small kernels, flags in peer memory, no collective).  --exchange nccl keeps the
+    # pack -> NCCL send/recv -> unpack form (also the fallback when the IPC handles cannot be opened).
     halo = None
+    exchange_kind = None
     if world_size > 1:
-        hb = world.halo_bytes()
-        halo = {k: torch.empty(hb, dtype=torch.uint8, device="cuda") for k in ("send_up", "send_down", "recv_up", "recv_down")}
         top_row, bottom_row = host.size_z - 3, 2          # last / first meshed row of columns
+        exchange_kind = args.exchange
+        if exchange_kind == "p2p":
+            handles = [None] * world_size
+            dist.all_gather_object(handles, world.halo_export())
+            ok = 1
+            try:
+                if rank + 1 < world_size:
+                    world.halo_connect_ipc(1, handles[rank + 1], bottom_row - 1)
+                if rank > 0:
+                    world.halo_connect_ipc(0, handles[rank - 1], top_row + 1)
+            except mesher.GcMeshError as e:
+                print("rank %d: peer-memory exchange unavailable (%s); using NCCL send/recv" % (rank, e), file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                exchange_kind = "nccl"
+        if exchange_kind == "nccl":
+            hb = world.halo_bytes()
+            halo = {k: torch.empty(hb, dtype=torch.uint8, device="cuda") for k in ("send_up", "send_down", "recv_up", "recv_down")}
 
     def exchange():
+        if exchange_kind == "p2p":
+            world.halo_push(bottom_row, top_row)
+            return 3
         ops = []
         if rank + 1 < world_size:
             world.pack_halo(top_row, 31, halo["send_up"].data_ptr())
@@ -488,12 +516,12 @@ def main():
             world.unpack_halo(top_row + 1, 0, halo["recv_up"].data_ptr())
         if rank > 0:
             world.unpack_halo(bottom_row - 1, 31, halo["recv_down"].data_ptr())
+        return 2 * ((rank + 1 < world_size) + (rank > 0))
 
     def step():
         launches = 0
         if world_size > 1:
-            exchange()
-            launches += 2 * ((rank + 1 < world_size) + (rank > 0))
+            launches += exchange()
         batch.submit(world, coords)
         return launches + 1
 
@@ -615,7 +643,7 @@ def main():
             "metric": "chunks_meshed_per_s", "value": value, "unit": "chunks/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args.workload, args.gpus, host, coords),
+            "config": workload_config(args.workload, args.gpus, host, coords, exchange_kind),
             "quads_per_s": all_quads / (ms_per_step * 1e-3), "quads_per_chunk": total_quads / n, "chunks_flagged": flags_bad,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
@@ -640,9 +668,14 @@ def main():
             line["edit_path"] = edit_path
         print(json.dumps(line), flush=True)
 
+    halo_timed_out = world.halo_status()[0] if exchange_kind == "p2p" else False
+    if world_size > 1:
+        dist.barrier()                                    # nobody unmaps a window a neighbour may still write to
     batch.close(); world.close(); ctx.close()
     if world_size > 1:
         dist.destroy_process_group()
+    if halo_timed_out:
+        raise SystemExit("rank %d: a halo exchange timed out waiting for a neighbour" % rank)
 
 
 if __name__ == "__main__":

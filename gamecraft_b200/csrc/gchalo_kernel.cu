@@ -1,0 +1,128 @@
+// gchalo — slab halo exchange over peer memory (see gchalo_kernel.cuh).
+//
+// Per exchange k, on every rank's own stream:
+//   ready  one warp: tells both neighbours "I have entered exchange k" (whatever read my halo rows before is finished)
+//          and waits until both have said the same — only then may their halo rows be overwritten
+//   copy   boundary planes (blocks | sunlight | blockLight of every chunk of the row, plus the surface row) stored with
+//          16-byte accesses straight into the neighbours' arrays; the last CTA to finish publishes "arrived k" in both
+//          neighbours' flag blocks behind a system-scope fence
+//   wait   one warp: until both neighbours' planes of exchange k have arrived here
+// Every wait is bounded (kHaloWaitNs): a missing neighbour raises HF_ERROR instead of hanging the stream.
+#include "gchalo_kernel.cuh"
+
+namespace gc
+{
+namespace
+{
+constexpr unsigned long long kHaloWaitNs = 2000000000ull;
+
+__device__ __forceinline__ void store_release_sys(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t load_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// a wait that gives up records which one it was: HF_ERROR = (serial << 8) | (flag word + 1), first failure only
+__device__ bool wait_at_least(uint32_t* flags, int word, uint32_t serial)
+{
+    const unsigned long long t0 = now_ns();
+    while ((int32_t)(load_acquire_sys(flags + word) - serial) < 0)
+    {
+        if (now_ns() - t0 > kHaloWaitNs) { atomicCAS(flags + HF_ERROR, 0u, (serial << 8) | (uint32_t)(word + 1)); return false; }
+        __nanosleep(200);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(32) gc_halo_ready_kernel(HaloPushArgs a)
+{
+    const int d = threadIdx.x;
+    if (d >= 2 || !a.peer[d].connected) return;
+    // I am the upper neighbour of the rank below me, the lower neighbour of the rank above
+    store_release_sys(a.peer[d].flags + (d == 0 ? HF_READY_FROM_UP : HF_READY_FROM_DOWN), a.serial);
+    wait_at_least(a.flags, d == 0 ? HF_READY_FROM_DOWN : HF_READY_FROM_UP, a.serial);
+}
+
+__global__ void __launch_bounds__(256) gc_halo_copy_kernel_p2p(HaloPushArgs a)
+{
+    const int per_chunk = 8192 / 16;                      // uint4 per (column, cy): 256 blocks, 128 sunlight, 128 blockLight
+    const int total = a.size_x * 4 * per_chunk;
+    const int surf_words = a.size_x * 8;
+    for (int d = 0; d < 2; d++)
+    {
+        const HaloPeer& p = a.peer[d];
+        if (!p.connected) continue;
+        const int z = d == 0 ? 0 : 31;
+        const int src_row = a.send_row[d];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        {
+            const int plane = i / per_chunk, q = i % per_chunk;
+            const int cx = plane >> 2, cy = plane & 3;
+            const size_t src = (((size_t)src_row * a.size_x + cx) * 4 + cy) * GC_CHUNK_SIZE_3 + (size_t)z * 2048;
+            const size_t dst = (((size_t)p.row * a.size_x + cx) * 4 + cy) * GC_CHUNK_SIZE_3 + (size_t)z * 2048;
+            if (q < 256) reinterpret_cast<uint4*>(p.blocks + dst)[q] = reinterpret_cast<const uint4*>(a.blocks + src)[q];
+            else if (q < 384) reinterpret_cast<uint4*>(p.sun + dst)[q - 256] = reinterpret_cast<const uint4*>(a.sun + src)[q - 256];
+            else reinterpret_cast<uint4*>(p.light + dst)[q - 384] = reinterpret_cast<const uint4*>(a.light + src)[q - 384];
+        }
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < surf_words; i += gridDim.x * blockDim.x)
+        {
+            const int cx = i >> 3, q = i & 7;
+            reinterpret_cast<uint32_t*>(p.surface + ((size_t)p.row * a.size_x + cx) * 1024 + z * 32)[q] =
+                reinterpret_cast<const uint32_t*>(a.surface + ((size_t)src_row * a.size_x + cx) * 1024 + z * 32)[q];
+        }
+    }
+    // last CTA out publishes the arrival: every CTA's stores are fenced system-wide before its ticket
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(a.flags + HF_TICKET, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x < 2 && a.peer[threadIdx.x].connected)
+    {
+        __threadfence_system();
+        store_release_sys(a.peer[threadIdx.x].flags + (threadIdx.x == 0 ? HF_ARRIVED_FROM_UP : HF_ARRIVED_FROM_DOWN), a.serial);
+    }
+    if (last && threadIdx.x == 0) a.flags[HF_TICKET] = 0;
+}
+
+__global__ void __launch_bounds__(32) gc_halo_wait_kernel(HaloPushArgs a)
+{
+    const int d = threadIdx.x;
+    if (d >= 2 || !a.peer[d].connected) return;
+    wait_at_least(a.flags, d == 0 ? HF_ARRIVED_FROM_DOWN : HF_ARRIVED_FROM_UP, a.serial);
+}
+}  // namespace
+
+// With lazy module loading the first launch of a kernel can synchronise the context — behind a ready / wait kernel that
+// is spinning for a neighbour whose own launch is what got stuck.  Loading all three up front removes that cycle.
+cudaError_t preload_halo_kernels()
+{
+    cudaFuncAttributes attr;
+    cudaError_t e = cudaFuncGetAttributes(&attr, gc_halo_ready_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&attr, gc_halo_copy_kernel_p2p);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&attr, gc_halo_wait_kernel);
+    return e;
+}
+
+cudaError_t launch_halo_push(const HaloPushArgs& a, int num_sms, cudaStream_t s)
+{
+    if (!a.peer[0].connected && !a.peer[1].connected) return cudaSuccess;
+    const int total = a.size_x * 4 * 512;
+    int grid = (total + 255) / 256;
+    if (grid > num_sms) grid = num_sms;                    // one CTA per SM: 1 MB per direction is latency, not bandwidth
+    gc_halo_ready_kernel<<<1, 32, 0, s>>>(a);
+    gc_halo_copy_kernel_p2p<<<grid, 256, 0, s>>>(a);
+    gc_halo_wait_kernel<<<1, 32, 0, s>>>(a);
+    return cudaGetLastError();
+}
+}  // namespace gc

@@ -16,6 +16,7 @@
 #include "gclight_kernel.cuh"
 #include "gcrle_kernel.cuh"
 #include "gcedit_kernel.cuh"
+#include "gchalo_kernel.cuh"
 
 using namespace gc;
 
@@ -119,6 +120,11 @@ struct GcWorld
     uint32_t* d_sun_list; size_t sun_list_cap;
     uint32_t* d_light_list; size_t light_list_cap;
     int light_launches; uint32_t light_stats[4];
+    // peer-memory halo exchange (gcmesh_world_halo_*)
+    uint32_t* d_halo_flags;
+    HaloPeer halo_peer[2];        // [0]: the rank below, [1]: the rank above
+    void* halo_ipc[2][5];         // pointers opened with cudaIpcOpenMemHandle (closed on destroy)
+    uint32_t halo_serial;
     // block edits (gcmesh_world_set_blocks)
     int32_t* d_vert_table;        // per brick: vertices of its last build (written by the mesh kernel), -1 = never built
     uint8_t* d_edit_dirty;        // per brick: flagged for rebuild
@@ -412,6 +418,10 @@ int gcmesh_world_destroy(GcWorld* w)
     if (w->h_rle_words) cudaFreeHost(w->h_rle_words);
     cudaFree(w->d_light_counters); cudaFree(w->d_brick_flags); cudaFree(w->d_active_list); cudaFree(w->d_sun_list); cudaFree(w->d_light_list);
     if (w->h_light_counters) cudaFreeHost(w->h_light_counters);
+    for (int d = 0; d < 2; d++)
+        for (int k = 0; k < 5; k++)
+            if (w->halo_ipc[d][k]) cudaIpcCloseMemHandle(w->halo_ipc[d][k]);
+    cudaFree(w->d_halo_flags);
     cudaFree(w->d_vert_table); cudaFree(w->d_edit_dirty); cudaFree(w->d_edit_state); cudaFree(w->d_edit_save);
     cudaFree(w->d_edit_sun_list); cudaFree(w->d_edit_light_list); cudaFree(w->d_edits); cudaFree(w->d_edit_status); cudaFree(w->d_edit_coords);
     if (w->edit_graph) cudaGraphExecDestroy(w->edit_graph);
@@ -804,6 +814,120 @@ int gcmesh_world_download(GcWorld* w, uint16_t* blocks, uint8_t* sunlight, uint8
     if (block_light) GC_CUDA(cudaMemcpyAsync(block_light, w->d_light, w->n_slots * GC_CHUNK_SIZE_3, cudaMemcpyDeviceToHost, s));
     if (surface) GC_CUDA(cudaMemcpyAsync(surface, w->d_surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaStreamSynchronize(s));
+    return GC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Slab halo exchange over peer memory (multi-GPU, one process per GPU): kernels in gchalo_kernel.cu.
+static int halo_flags(GcWorld* w)
+{
+    if (w->d_halo_flags) return GC_OK;
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    GC_CUDA(preload_halo_kernels());
+    GC_CUDA(cudaMalloc(&w->d_halo_flags, HF_WORDS * sizeof(uint32_t)));
+    // cleared on the context stream and waited for: a neighbour may write the block as soon as it knows the pointer
+    GC_CUDA(cudaMemsetAsync(w->d_halo_flags, 0, HF_WORDS * sizeof(uint32_t), w->ctx->stream));
+    GC_CUDA(cudaStreamSynchronize(w->ctx->stream));
+    return GC_OK;
+}
+
+int gcmesh_world_halo_export(GcWorld* w, void* handles)
+{
+    if (!w || !handles) return fail(GC_ERR_ARG, "null argument");
+    if (halo_flags(w) != GC_OK) return GC_ERR_CUDA;
+    void* ptrs[5] = { w->d_blocks, w->d_sun, w->d_light, w->d_surface, w->d_halo_flags };
+    cudaIpcMemHandle_t* out = (cudaIpcMemHandle_t*)handles;
+    static_assert(sizeof(cudaIpcMemHandle_t) * 5 == GC_HALO_HANDLE_BYTES, "GC_HALO_HANDLE_BYTES");
+    for (int k = 0; k < 5; k++) GC_CUDA(cudaIpcGetMemHandle(out + k, ptrs[k]));
+    return GC_OK;
+}
+
+static int halo_side_ok(GcWorld* w, int side, int peer_row)
+{
+    if (side < 0 || side > 1) return fail(GC_ERR_ARG, "side is 0 (the rank below, z - 1) or 1 (the rank above)");
+    if (peer_row < 0 || peer_row >= w->size_z) return fail(GC_ERR_ARG, "peer row outside the window (neighbours have windows of one size)");
+    if (w->halo_peer[side].connected) return fail(GC_ERR_ARG, "side already connected");
+    return GC_OK;
+}
+
+int gcmesh_world_halo_connect_ipc(GcWorld* w, int side, const void* handles, int peer_row)
+{
+    if (!w || !handles) return fail(GC_ERR_ARG, "null argument");
+    if (halo_side_ok(w, side, peer_row) != GC_OK) return GC_ERR_ARG;
+    if (halo_flags(w) != GC_OK) return GC_ERR_CUDA;
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    const cudaIpcMemHandle_t* in = (const cudaIpcMemHandle_t*)handles;
+    for (int k = 0; k < 5; k++)
+    {
+        cudaError_t e = cudaIpcOpenMemHandle(&w->halo_ipc[side][k], in[k], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+        {
+            for (int j = 0; j < k; j++) { cudaIpcCloseMemHandle(w->halo_ipc[side][j]); w->halo_ipc[side][j] = nullptr; }
+            w->halo_ipc[side][k] = nullptr;
+            return fail(GC_ERR_CUDA, "cudaIpcOpenMemHandle", cudaGetErrorString(e));
+        }
+    }
+    HaloPeer& p = w->halo_peer[side];
+    p.blocks = (uint16_t*)w->halo_ipc[side][0]; p.sun = (uint8_t*)w->halo_ipc[side][1]; p.light = (uint8_t*)w->halo_ipc[side][2];
+    p.surface = (uint8_t*)w->halo_ipc[side][3]; p.flags = (uint32_t*)w->halo_ipc[side][4];
+    p.row = peer_row; p.connected = 1;
+    return GC_OK;
+}
+
+int gcmesh_world_halo_connect_local(GcWorld* w, int side, GcWorld* peer, int peer_row)
+{
+    if (!w || !peer) return fail(GC_ERR_ARG, "null argument");
+    if (peer->size_x != w->size_x || peer->size_z != w->size_z) return fail(GC_ERR_ARG, "neighbour windows must have one size");
+    if (halo_side_ok(w, side, peer_row) != GC_OK) return GC_ERR_ARG;
+    if (halo_flags(w) != GC_OK || halo_flags(peer) != GC_OK) return GC_ERR_CUDA;
+    if (peer->ctx->device != w->ctx->device)
+    {
+        GC_CUDA(cudaSetDevice(w->ctx->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->ctx->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return fail(GC_ERR_CUDA, "cudaDeviceEnablePeerAccess", cudaGetErrorString(e));
+    }
+    HaloPeer& p = w->halo_peer[side];
+    p.blocks = peer->d_blocks; p.sun = peer->d_sun; p.light = peer->d_light; p.surface = peer->d_surface; p.flags = peer->d_halo_flags;
+    p.row = peer_row; p.connected = 1;
+    return GC_OK;
+}
+
+int gcmesh_world_halo_push(GcWorld* w, int send_row_down, int send_row_up)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    if (!w->halo_peer[0].connected && !w->halo_peer[1].connected) return fail(GC_ERR_ARG, "no neighbour connected");
+    if ((w->halo_peer[0].connected && (send_row_down < 0 || send_row_down >= w->size_z)) ||
+        (w->halo_peer[1].connected && (send_row_up < 0 || send_row_up >= w->size_z))) return fail(GC_ERR_ARG, "send row outside the window");
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    HaloPushArgs a;
+    a.blocks = w->d_blocks; a.sun = w->d_sun; a.light = w->d_light; a.surface = w->d_surface; a.flags = w->d_halo_flags;
+    a.size_x = w->size_x; a.send_row[0] = send_row_down; a.send_row[1] = send_row_up;
+    a.peer[0] = w->halo_peer[0]; a.peer[1] = w->halo_peer[1];
+    a.serial = ++w->halo_serial;
+    GC_CUDA(launch_halo_push(a, ctx->num_sms, ctx->stream));
+    // the neighbours' planes land in this window's halo rows: the sparse-upload bookkeeping no longer knows them
+    for (int d = 0; d < 2; d++)
+        if (w->halo_peer[d].connected)
+        {
+            const int row = d == 0 ? send_row_down - 1 : send_row_up + 1;
+            if (row >= 0 && row < w->size_z) memset(w->slot_dirty + (size_t)row * w->size_x * GC_WORLD_CHUNK_HEIGHT, 7, (size_t)w->size_x * GC_WORLD_CHUNK_HEIGHT);
+        }
+    return GC_OK;
+}
+
+int gcmesh_world_halo_status(GcWorld* w, int* timed_out, uint32_t* serial)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    if (timed_out) *timed_out = 0;
+    if (serial) *serial = w->halo_serial;
+    if (!w->d_halo_flags) return GC_OK;
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    uint32_t flags[HF_WORDS];
+    GC_CUDA(cudaMemcpyAsync(flags, w->d_halo_flags, sizeof(flags), cudaMemcpyDeviceToHost, w->ctx->stream));
+    GC_CUDA(cudaStreamSynchronize(w->ctx->stream));
+    if (timed_out) *timed_out = (int)flags[HF_ERROR];
     return GC_OK;
 }
 

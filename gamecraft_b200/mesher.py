@@ -29,7 +29,7 @@ CHUNK_NO_SPACE = 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcedit_kernel.cu", "gcmesh_api.cu"]
+SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcedit_kernel.cu", "gchalo_kernel.cu", "gcmesh_api.cu"]
 HEADERS = ["gcmesh_kernel.cuh", "gclight_kernel.cuh", "gcrle_kernel.cuh", "mesh_core.cuh", os.path.join("..", "..", "include", "gcmesh.h")]
 
 
@@ -65,6 +65,7 @@ class ChunkOut(ctypes.Structure):
 CHUNK_OUT_DTYPE = np.dtype([("quad_base", "<u4"), ("vert_count", "<u4"), ("index_count", "<u4", (5,)),
                             ("index_offset", "<u4", (5,)), ("quads", "<u4"), ("flags", "<u4"), ("reserved", "<u4", (2,))])
 assert CHUNK_OUT_DTYPE.itemsize == ctypes.sizeof(ChunkOut) == 64
+HALO_HANDLE_BYTES = 320                                                                                                # GC_HALO_HANDLE_BYTES
 BLOCK_EDIT_DTYPE = np.dtype([("wx", "<i4"), ("wy", "<i4"), ("wz", "<i4"), ("block", "<u2"), ("reserved", "<u2")])   # GcBlockEdit
 EDIT_APPLIED, EDIT_UNCHANGED, EDIT_IGNORED, EDIT_NOT_BUILT, EDIT_OVERFLOW = range(5)                                   # GC_EDIT_*
 RLE_CHUNK_DTYPE = np.dtype([("cx", "<i4"), ("cy", "<i4"), ("cz", "<i4"), ("first_word", "<u4"), ("words", "<u4")])   # GcRleChunk
@@ -75,6 +76,7 @@ EXPORTS = [
     "gcmesh_world_create", "gcmesh_world_destroy", "gcmesh_world_upload_chunk", "gcmesh_world_upload_surface",
     "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_upload_launches", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
     "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
+    "gcmesh_world_halo_export", "gcmesh_world_halo_connect_ipc", "gcmesh_world_halo_connect_local", "gcmesh_world_halo_push", "gcmesh_world_halo_status",
     "gcmesh_default_light_rules", "gcmesh_set_light_rules", "gcmesh_world_compute_surface", "gcmesh_world_light",
     "gcmesh_world_light_stats", "gcmesh_world_download",
     "gcmesh_world_upload_rle", "gcmesh_world_rle_refused", "gcmesh_world_encode_rle",
@@ -116,6 +118,11 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_halo_bytes.restype = ctypes.c_size_t
         L.gcmesh_world_pack_halo.argtypes = [vp, ci, ci, vp]
         L.gcmesh_world_unpack_halo.argtypes = [vp, ci, ci, vp]
+        L.gcmesh_world_halo_export.argtypes = [vp, vp]
+        L.gcmesh_world_halo_connect_ipc.argtypes = [vp, ci, vp, ci]
+        L.gcmesh_world_halo_connect_local.argtypes = [vp, ci, vp, ci]
+        L.gcmesh_world_halo_push.argtypes = [vp, ci, ci]
+        L.gcmesh_world_halo_status.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_uint32)]
         L.gcmesh_default_light_rules.argtypes = [vp, vp]
         L.gcmesh_set_light_rules.argtypes = [vp, vp, vp]
         L.gcmesh_world_compute_surface.argtypes = [vp]
@@ -328,6 +335,28 @@ class World:
 
     def unpack_halo(self, cz: int, z: int, device_buf: int) -> None:
         _check(lib().gcmesh_world_unpack_halo(self.h, cz, z, ctypes.c_void_p(device_buf)), "gcmesh_world_unpack_halo")
+
+    # -- peer-memory halo exchange (side 0: the rank below, 1: the rank above) --
+    def halo_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(HALO_HANDLE_BYTES)
+        _check(lib().gcmesh_world_halo_export(self.h, buf), "gcmesh_world_halo_export")
+        return buf.raw
+
+    def halo_connect_ipc(self, side: int, handles: bytes, peer_row: int) -> None:
+        assert len(handles) == HALO_HANDLE_BYTES
+        _check(lib().gcmesh_world_halo_connect_ipc(self.h, side, ctypes.c_char_p(handles), peer_row), "gcmesh_world_halo_connect_ipc")
+
+    def halo_connect_local(self, side: int, peer: "World", peer_row: int) -> None:
+        _check(lib().gcmesh_world_halo_connect_local(self.h, side, peer.h, peer_row), "gcmesh_world_halo_connect_local")
+
+    def halo_push(self, send_row_down: int, send_row_up: int) -> None:
+        _check(lib().gcmesh_world_halo_push(self.h, send_row_down, send_row_up), "gcmesh_world_halo_push")
+
+    def halo_status(self):
+        """(timed_out, exchanges so far); synchronises the context stream."""
+        t, n = ctypes.c_int(0), ctypes.c_uint32(0)
+        _check(lib().gcmesh_world_halo_status(self.h, ctypes.byref(t), ctypes.byref(n)), "gcmesh_world_halo_status")
+        return int(t.value), int(n.value)
 
     def close(self) -> None:
         if self.h:

@@ -146,6 +146,27 @@ int gcmesh_world_device_ptrs(GcWorld* world, void** blocks, void** sunlight, voi
 size_t gcmesh_world_halo_bytes(const GcWorld* world);
 int gcmesh_world_pack_halo(GcWorld* world, int cz, int z, void* device_buf);
 int gcmesh_world_unpack_halo(GcWorld* world, int cz, int z, const void* device_buf);
+/* The same exchange without a buffer or a collective: each rank stores its boundary planes straight into its
+ * neighbours' window arrays over NVLink peer memory (one process per GPU: CUDA IPC handles; one process, several
+ * worlds: direct).  Neighbouring windows have one size.  side 0 = the rank below (z - 1), 1 = the rank above.
+ *   gcmesh_world_halo_export        GC_HALO_HANDLE_BYTES of handles for this window (send them to both neighbours)
+ *   gcmesh_world_halo_connect_ipc   open a neighbour's handles; peer_row = the neighbour's halo row that receives this
+ *                                   rank's plane (its first owned row - 1 for the rank above, its last owned row + 1 below)
+ *   gcmesh_world_halo_connect_local the neighbour is a world of this process (any device with peer access)
+ *   gcmesh_world_halo_push          one exchange, enqueued on the context stream: tell the neighbours this rank's earlier
+ *                                   work is done and wait for the same from them (their halo rows may then be
+ *                                   overwritten), copy the z = 0 plane of row send_row_down to the rank below and the
+ *                                   z = 31 plane of row send_row_up to the rank above, wait for the neighbours' planes.
+ *                                   Work enqueued afterwards (gcmesh_submit) sees the new halo.  Every rank of a chain
+ *                                   calls it the same number of times.
+ *   gcmesh_world_halo_status        synchronises; timed_out != 0: a neighbour did not show up within 2 s (no hang);
+ *                                   the value is (exchange serial << 8) | (1 + flag word waited for) of the first such wait */
+#define GC_HALO_HANDLE_BYTES 320
+int gcmesh_world_halo_export(GcWorld* world, void* handles);
+int gcmesh_world_halo_connect_ipc(GcWorld* world, int side, const void* handles, int peer_row);
+int gcmesh_world_halo_connect_local(GcWorld* world, int side, GcWorld* peer, int peer_row);
+int gcmesh_world_halo_push(GcWorld* world, int send_row_down, int send_row_up);
+int gcmesh_world_halo_status(GcWorld* world, int* timed_out, uint32_t* serial);
 
 /* ---- column pre-processing on the device: the producers of the mesher's light inputs ----
  * Replaces, for a window whose block ids are on the device, ComputeSurface (Code/Lighting.cpp:5-26) and SetLightNodes /

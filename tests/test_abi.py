@@ -63,5 +63,9 @@ def test_argument_errors_without_gpu():
     assert L.gcmesh_set_light_rules(None, None, None) == -1
     assert L.gcmesh_world_upload_rle(None, None, 0, None, 0) == -1
     assert L.gcmesh_world_encode_rle(None, None, 0, None, 0, None) == -1
+    n = ctypes.c_int(7)
+    assert L.gcmesh_world_set_blocks(None, None, 0, None, None, 0, ctypes.byref(n)) == -1 and n.value == 0
+    assert L.gcmesh_world_vertex_counts(None, None) == -1
+    assert ctypes.sizeof(ctypes.c_int32) * 4 == mesher.BLOCK_EDIT_DTYPE.itemsize          # GcBlockEdit: three int32 + two uint16
     step, emitted = mesher.default_light_rules()
     assert step[0] == 1 and step[3] == 255 and emitted[14] == 15 and emitted[17] == 10
