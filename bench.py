@@ -472,7 +472,7 @@ def main():
 
     # ---- slab halo exchange (N > 1): boundary voxel planes to / from the z-neighbours ----
     # Default: each rank stores its planes straight into its neighbours' windows over NVLink peer memory (CUDA IPC handles,
-    # gcmesh_world_halo_push: three small kernels, flags in peer memory, no collective).  --exchange nccl keeps the
+    # gcmesh_world_halo_push: one kernel, flags in peer memory, no collective).  --exchange nccl keeps the
     # pack -> NCCL send/recv -> unpack form (also the fallback when the IPC handles cannot be opened).
     halo = None
     exchange_kind = None
@@ -502,7 +502,7 @@ def main():
     def exchange():
         if exchange_kind == "p2p":
             world.halo_push(bottom_row, top_row)
-            return 3
+            return 1
         ops = []
         if rank + 1 < world_size:
             world.pack_halo(top_row, 31, halo["send_up"].data_ptr())

@@ -1,12 +1,12 @@
 // gchalo — slab halo exchange over peer memory (see gchalo_kernel.cuh).
 //
-// Per exchange k, on every rank's own stream:
-//   ready  one warp: tells both neighbours "I have entered exchange k" (whatever read my halo rows before is finished)
-//          and waits until both have said the same — only then may their halo rows be overwritten
+// Per exchange k, one kernel on every rank's own stream:
+//   ready  tells both neighbours "I have entered exchange k" (whatever read my halo rows before is finished) and waits
+//          until both have said the same — only then may their halo rows be overwritten
 //   copy   boundary planes (blocks | sunlight | blockLight of every chunk of the row, plus the surface row) stored with
 //          16-byte accesses straight into the neighbours' arrays; the last CTA to finish publishes "arrived k" in both
 //          neighbours' flag blocks behind a system-scope fence
-//   wait   one warp: until both neighbours' planes of exchange k have arrived here
+//   wait   until both neighbours' planes of exchange k have arrived here
 // Every wait is bounded (kHaloWaitNs): a missing neighbour raises HF_ERROR instead of hanging the stream.
 #include "gchalo_kernel.cuh"
 
@@ -44,17 +44,19 @@ __device__ bool wait_at_least(uint32_t* flags, int word, uint32_t serial)
     return true;
 }
 
-__global__ void __launch_bounds__(32) gc_halo_ready_kernel(HaloPushArgs a)
+// One kernel per exchange.  No CTA waits for another CTA of the grid — only for flags the neighbours write — so the grid
+// needs no co-residency: CTA 0 tells the neighbours this rank has entered the exchange, every CTA waits until both
+// neighbours have said the same, copies its share, and leaves once the neighbours' planes have arrived here.
+__global__ void __launch_bounds__(256) gc_halo_exchange_kernel(HaloPushArgs a)
 {
-    const int d = threadIdx.x;
-    if (d >= 2 || !a.peer[d].connected) return;
-    // I am the upper neighbour of the rank below me, the lower neighbour of the rank above
-    store_release_sys(a.peer[d].flags + (d == 0 ? HF_READY_FROM_UP : HF_READY_FROM_DOWN), a.serial);
-    wait_at_least(a.flags, d == 0 ? HF_READY_FROM_DOWN : HF_READY_FROM_UP, a.serial);
-}
+    // ---- ready: I am the upper neighbour of the rank below me, the lower neighbour of the rank above ----
+    if (blockIdx.x == 0 && threadIdx.x < 2 && a.peer[threadIdx.x].connected)
+        store_release_sys(a.peer[threadIdx.x].flags + (threadIdx.x == 0 ? HF_READY_FROM_UP : HF_READY_FROM_DOWN), a.serial);
+    if (threadIdx.x < 2 && a.peer[threadIdx.x].connected)
+        wait_at_least(a.flags, threadIdx.x == 0 ? HF_READY_FROM_DOWN : HF_READY_FROM_UP, a.serial);
+    __syncthreads();
 
-__global__ void __launch_bounds__(256) gc_halo_copy_kernel_p2p(HaloPushArgs a)
-{
+    // ---- copy ----
     const int per_chunk = 8192 / 16;                      // uint4 per (column, cy): 256 blocks, 128 sunlight, 128 blockLight
     const int total = a.size_x * 4 * per_chunk;
     const int surf_words = a.size_x * 8;
@@ -93,25 +95,19 @@ __global__ void __launch_bounds__(256) gc_halo_copy_kernel_p2p(HaloPushArgs a)
         store_release_sys(a.peer[threadIdx.x].flags + (threadIdx.x == 0 ? HF_ARRIVED_FROM_UP : HF_ARRIVED_FROM_DOWN), a.serial);
     }
     if (last && threadIdx.x == 0) a.flags[HF_TICKET] = 0;
-}
 
-__global__ void __launch_bounds__(32) gc_halo_wait_kernel(HaloPushArgs a)
-{
-    const int d = threadIdx.x;
-    if (d >= 2 || !a.peer[d].connected) return;
-    wait_at_least(a.flags, d == 0 ? HF_ARRIVED_FROM_DOWN : HF_ARRIVED_FROM_UP, a.serial);
+    // ---- wait: the kernel (and with it the stream) goes on once both neighbours' planes are here ----
+    if (threadIdx.x < 2 && a.peer[threadIdx.x].connected)
+        wait_at_least(a.flags, threadIdx.x == 0 ? HF_ARRIVED_FROM_DOWN : HF_ARRIVED_FROM_UP, a.serial);
 }
 }  // namespace
 
-// With lazy module loading the first launch of a kernel can synchronise the context — behind a ready / wait kernel that
-// is spinning for a neighbour whose own launch is what got stuck.  Loading all three up front removes that cycle.
+// With lazy module loading the first launch of a kernel can synchronise the context — behind an exchange kernel that is
+// spinning for a neighbour whose own launch is what got stuck (worlds of one process).  Loading it up front removes that.
 cudaError_t preload_halo_kernels()
 {
     cudaFuncAttributes attr;
-    cudaError_t e = cudaFuncGetAttributes(&attr, gc_halo_ready_kernel);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&attr, gc_halo_copy_kernel_p2p);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&attr, gc_halo_wait_kernel);
-    return e;
+    return cudaFuncGetAttributes(&attr, gc_halo_exchange_kernel);
 }
 
 cudaError_t launch_halo_push(const HaloPushArgs& a, int num_sms, cudaStream_t s)
@@ -120,9 +116,7 @@ cudaError_t launch_halo_push(const HaloPushArgs& a, int num_sms, cudaStream_t s)
     const int total = a.size_x * 4 * 512;
     int grid = (total + 255) / 256;
     if (grid > num_sms) grid = num_sms;                    // one CTA per SM: 1 MB per direction is latency, not bandwidth
-    gc_halo_ready_kernel<<<1, 32, 0, s>>>(a);
-    gc_halo_copy_kernel_p2p<<<grid, 256, 0, s>>>(a);
-    gc_halo_wait_kernel<<<1, 32, 0, s>>>(a);
+    gc_halo_exchange_kernel<<<grid, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 }  // namespace gc

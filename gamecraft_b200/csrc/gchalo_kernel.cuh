@@ -40,8 +40,8 @@ struct HaloPushArgs
     uint32_t serial;            // 1, 2, ... per exchange
 };
 
-// loads the three kernels (call before the first exchange; see gchalo_kernel.cu)
+// loads the kernel (call before the first exchange; see gchalo_kernel.cu)
 cudaError_t preload_halo_kernels();
-// ready -> copy -> wait, enqueued back to back on `s`
+// one exchange (ready -> copy -> wait inside one kernel), enqueued on `s`
 cudaError_t launch_halo_push(const HaloPushArgs& a, int num_sms, cudaStream_t s);
 }  // namespace gc

@@ -153,7 +153,7 @@ int gcmesh_world_unpack_halo(GcWorld* world, int cz, int z, const void* device_b
  *   gcmesh_world_halo_connect_ipc   open a neighbour's handles; peer_row = the neighbour's halo row that receives this
  *                                   rank's plane (its first owned row - 1 for the rank above, its last owned row + 1 below)
  *   gcmesh_world_halo_connect_local the neighbour is a world of this process (any device with peer access)
- *   gcmesh_world_halo_push          one exchange, enqueued on the context stream: tell the neighbours this rank's earlier
+ *   gcmesh_world_halo_push          one exchange, one kernel enqueued on the context stream: tell the neighbours this rank's earlier
  *                                   work is done and wait for the same from them (their halo rows may then be
  *                                   overwritten), copy the z = 0 plane of row send_row_down to the rank below and the
  *                                   z = 31 plane of row send_row_up to the rank above, wait for the neighbours' planes.
