@@ -271,6 +271,56 @@ def load_path_leg(ctx, world, batch, host, coords, total_quads, args):
                     "gcmesh_world_light + gcmesh_submit + gcmesh_wait + gcmesh_batch_download"}
 
 
+def stream_path_leg(ctx, batch, host, coords, total_quads, workload, gen_s):
+    """Columns born in HBM (SURVEY 8(f2) + 8(f1) + the mesher): terrain generated on the device -> surface -> light -> meshes,
+    nothing crossing PCIe but the per-chunk descriptors.  Same window as the host-prepared one of the main line."""
+    from gamecraft_b200 import mesher
+    from gamecraft_b200.worldgen import INT_MAX
+
+    kind, mx, mz, seed, radius = WORKLOADS[workload]
+    if kind not in ("forest", "islands", "flat"):
+        return None
+    radius = radius if radius else INT_MAX
+    lw = mesher.World(ctx, host.size_x, host.size_z)
+
+    def gen():
+        lw.generate(kind, seed, origin=host.origin, radius=radius)
+
+    def one():
+        gen()
+        lw.compute_surface().light()
+        batch.submit(lw, coords).wait()
+
+    for _ in range(2):
+        one()
+    ctx.synchronize()
+    k = 5
+    t0 = time.perf_counter()
+    for _ in range(k):
+        one()
+    ctx.synchronize()
+    sec = (time.perf_counter() - t0) / k
+    desc, q = batch.results()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        gen()
+    ctx.synchronize()
+    gen_sec = (time.perf_counter() - t0) / k
+    from gamecraft_b200.worldgen import HostWorld
+    got = HostWorld(host.size_x, host.size_z)
+    lw.download(got, blocks=True, sun=False, light=False, surface=False)
+    same = bool(np.array_equal(got.blocks, host.blocks))
+    lw.close()
+    n_cols = host.size_x * host.size_z
+    return {"metric": "chunks_meshed_per_s", "value": len(coords) / sec, "unit": "chunks/s", "ms_per_step": 1e3 * sec, "steps": k,
+            "generate_ms": 1e3 * gen_sec, "columns_generated_per_s": n_cols / gen_sec,
+            "host_producer": {"seconds": gen_s, "columns_per_s": n_cols / gen_s if gen_s else None, "cores": os.cpu_count(),
+                              "what": "gamecraft_b200/worldgen on the host cores: generate + surface + light of the same window (the run's own input preparation)"},
+            "blocks_identical_to_host_producer": same, "same_quads_as_host_prepared_world": bool(int(q) == int(total_quads)),
+            "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(len(coords) * 64),
+            "call": "gcmesh_world_generate + gcmesh_world_compute_surface + gcmesh_world_light + gcmesh_submit + gcmesh_wait"}
+
+
 def edit_path_leg(ctx, world, host, args):
     """The interactive caller on the device: SetBlock -> overflow pre-check -> relight -> rebuild list, then the
     remesh of the flagged chunks with their meshes read back — dig the top block of a column, then put it back."""
@@ -627,10 +677,12 @@ def main():
     # ---- column pre-processing on the device: surface map + light flood fill from the block ids ----
     preprocess = None
     load_path = None
+    stream_path = None
     edit_path = None
     if not args.no_preprocess and world_size == 1:
         preprocess = preprocess_leg(ctx, host, Pinned, args)
         load_path = load_path_leg(ctx, world, batch, host, coords, total_quads, args)
+        stream_path = stream_path_leg(ctx, batch, host, coords, total_quads, args.workload, gen_s)
         edit_path = edit_path_leg(ctx, world, host, args)     # last: it edits the device world
 
     if rank == 0:
@@ -664,6 +716,8 @@ def main():
             line["preprocess"] = preprocess
         if load_path:
             line["load_path"] = load_path
+        if stream_path:
+            line["stream_path"] = stream_path
         if edit_path:
             line["edit_path"] = edit_path
         print(json.dumps(line), flush=True)

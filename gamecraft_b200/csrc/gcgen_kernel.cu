@@ -1,0 +1,338 @@
+// gcgen — terrain generation on the device (see gcgen_kernel.cuh).
+//
+// Three kernels per window:
+//   heights  one thread per (column, z, x): island test, biome / flat / mountain noise, terrain height; column maximum
+//   layers   one thread per (column, z, x) walking up to the column maximum: stone pockets (3-D fBm), grass, dirt, water
+//   trees    one thread per column: the column's own PRNG stream places trunks and leaf boxes in order (later trees
+//            overwrite earlier ones, as in the host producer)
+// Every float operation is an explicitly rounded single operation (__fmul_rn / __fadd_rn / ...), never a fused
+// multiply-add, in the order the host producer evaluates it (compiled with -ffp-contract=off), so both give the same
+// heights; powf is taken through double precision.
+#include "gcgen_kernel.cuh"
+
+namespace gc
+{
+namespace
+{
+enum { B_AIR = 0, B_GRASS = 1, B_DIRT = 2, B_STONE = 3, B_WATER = 8, B_WOOD = 9, B_LEAVES = 10 };   // Code/Block.h:11-38
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ uint32_t mix32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ uint32_t hash3(uint32_t seed, int32_t a, int32_t b, int32_t c)
+{
+    uint32_t h = seed ^ 0x9E3779B9u;
+    h = mix32(h + (uint32_t)a * 0x85EBCA6Bu);
+    h = mix32(h + (uint32_t)b * 0xC2B2AE35u);
+    h = mix32(h + (uint32_t)c * 0x27D4EB2Fu);
+    return h;
+}
+struct Rng { uint64_t s; };
+__device__ __forceinline__ uint32_t rng_next(Rng& r)
+{
+    r.s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = r.s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return (uint32_t)((z ^ (z >> 31)) >> 16);
+}
+__device__ __forceinline__ int rng_range(Rng& r, int lo, int hi) { return lo + (int)(rng_next(r) % (uint32_t)(hi + 1 - lo)); }
+
+__device__ float grad2(uint32_t h, float x, float y)
+{
+    const float d = 0.70710678f;
+    float gx, gy;
+    switch (h & 7u)
+    {
+        case 0: gx = 1; gy = 0; break;
+        case 1: gx = -1; gy = 0; break;
+        case 2: gx = 0; gy = 1; break;
+        case 3: gx = 0; gy = -1; break;
+        case 4: gx = d; gy = d; break;
+        case 5: gx = -d; gy = d; break;
+        case 6: gx = d; gy = -d; break;
+        default: gx = -d; gy = -d; break;
+    }
+    return add(mul(gx, x), mul(gy, y));
+}
+
+__device__ float corner2(uint32_t seed, int i, int j, float x, float y)
+{
+    // a corner out of reach contributes +0.0f: adding it leaves n as the host's skipped statement does
+    float a = sub(sub(0.5f, mul(x, x)), mul(y, y));
+    if (!(a > 0)) return 0.0f;
+    a = mul(a, a);
+    return mul(mul(a, a), grad2(hash3(seed, i, j, 0), x, y));
+}
+
+__device__ float simplex2(uint32_t seed, float x, float y)
+{
+    const float F2 = 0.36602540f, G2 = 0.21132487f;
+    const float s = mul(add(x, y), F2);
+    const int i = (int)floorf(add(x, s)), j = (int)floorf(add(y, s));
+    const float t = mul((float)(i + j), G2);
+    const float x0 = sub(x, sub((float)i, t)), y0 = sub(y, sub((float)j, t));
+    const int i1 = x0 > y0, j1 = !i1;
+    const float x1 = add(sub(x0, (float)i1), G2), y1 = add(sub(y0, (float)j1), G2);
+    const float g22 = mul(2.0f, G2);
+    const float x2 = add(sub(x0, 1.0f), g22), y2 = add(sub(y0, 1.0f), g22);
+    float n = 0.0f;
+    n = add(n, corner2(seed, i, j, x0, y0));
+    n = add(n, corner2(seed, i + i1, j + j1, x1, y1));
+    n = add(n, corner2(seed, i + 1, j + 1, x2, y2));
+    n = mul(n, 70.0f);
+    return n < -1.0f ? -1.0f : (n > 1.0f ? 1.0f : n);
+}
+
+__device__ float grad3(uint32_t h, float x, float y, float z)
+{
+    // G[h % 12] = (gx, gy, gz) with entries in {-1, 0, 1}: g0*x + g1*y + g2*z, zero terms included (x*0 = +-0 adds exactly)
+    float gx, gy, gz;
+    switch (h % 12u)
+    {
+        case 0: gx = 1; gy = 1; gz = 0; break;
+        case 1: gx = -1; gy = 1; gz = 0; break;
+        case 2: gx = 1; gy = -1; gz = 0; break;
+        case 3: gx = -1; gy = -1; gz = 0; break;
+        case 4: gx = 1; gy = 0; gz = 1; break;
+        case 5: gx = -1; gy = 0; gz = 1; break;
+        case 6: gx = 1; gy = 0; gz = -1; break;
+        case 7: gx = -1; gy = 0; gz = -1; break;
+        case 8: gx = 0; gy = 1; gz = 1; break;
+        case 9: gx = 0; gy = -1; gz = 1; break;
+        case 10: gx = 0; gy = 1; gz = -1; break;
+        default: gx = 0; gy = -1; gz = -1; break;
+    }
+    return add(add(mul(gx, x), mul(gy, y)), mul(gz, z));
+}
+
+__device__ float corner3(uint32_t seed, int i, int j, int k, float x, float y, float z)
+{
+    float a = sub(sub(sub(0.6f, mul(x, x)), mul(y, y)), mul(z, z));
+    if (!(a > 0)) return 0.0f;
+    a = mul(a, a);
+    return mul(mul(a, a), grad3(hash3(seed, i, j, k), x, y, z));
+}
+
+__device__ float simplex3(uint32_t seed, float x, float y, float z)
+{
+    const float F3 = __fdiv_rn(1.0f, 3.0f), G3 = __fdiv_rn(1.0f, 6.0f);
+    const float s = mul(add(add(x, y), z), F3);
+    const int i = (int)floorf(add(x, s)), j = (int)floorf(add(y, s)), k = (int)floorf(add(z, s));
+    const float t = mul((float)(i + j + k), G3);
+    const float x0 = sub(x, sub((float)i, t)), y0 = sub(y, sub((float)j, t)), z0 = sub(z, sub((float)k, t));
+    int i1, j1, k1, i2, j2, k2;
+    if (x0 >= y0)
+    {
+        if (y0 >= z0) { i1 = 1; j1 = 0; k1 = 0; i2 = 1; j2 = 1; k2 = 0; }
+        else if (x0 >= z0) { i1 = 1; j1 = 0; k1 = 0; i2 = 1; j2 = 0; k2 = 1; }
+        else { i1 = 0; j1 = 0; k1 = 1; i2 = 1; j2 = 0; k2 = 1; }
+    }
+    else
+    {
+        if (y0 < z0) { i1 = 0; j1 = 0; k1 = 1; i2 = 0; j2 = 1; k2 = 1; }
+        else if (x0 < z0) { i1 = 0; j1 = 1; k1 = 0; i2 = 0; j2 = 1; k2 = 1; }
+        else { i1 = 0; j1 = 1; k1 = 0; i2 = 1; j2 = 1; k2 = 0; }
+    }
+    const float g2 = mul(2.0f, G3), g3 = mul(3.0f, G3);
+    const float x1 = add(sub(x0, (float)i1), G3), y1 = add(sub(y0, (float)j1), G3), z1 = add(sub(z0, (float)k1), G3);
+    const float x2 = add(sub(x0, (float)i2), g2), y2 = add(sub(y0, (float)j2), g2), z2 = add(sub(z0, (float)k2), g2);
+    const float x3 = add(sub(x0, 1.0f), g3), y3 = add(sub(y0, 1.0f), g3), z3 = add(sub(z0, 1.0f), g3);
+    float n = 0.0f;
+    n = add(n, corner3(seed, i, j, k, x0, y0, z0));
+    n = add(n, corner3(seed, i + i1, j + j1, k + k1, x1, y1, z1));
+    n = add(n, corner3(seed, i + i2, j + j2, k + k2, x2, y2, z2));
+    n = add(n, corner3(seed, i + 1, j + 1, k + 1, x3, y3, z3));
+    n = mul(n, 32.0f);
+    return n < -1.0f ? -1.0f : (n > 1.0f ? 1.0f : n);
+}
+
+__device__ float fractal_bounding(int octaves)
+{
+    float amp = 0.5f, sum = 1.0f;
+    for (int i = 1; i < octaves; i++) { sum = add(sum, amp); amp = mul(amp, 0.5f); }
+    return __fdiv_rn(1.0f, sum);
+}
+
+__device__ float ridged2(uint32_t seed, float x, float y, int octaves)
+{
+    float sum = sub(1.0f, fabsf(simplex2(seed, x, y))), amp = 1.0f;
+    for (int i = 1; i < octaves; i++)
+    {
+        x = mul(x, 2.0f); y = mul(y, 2.0f); amp = mul(amp, 0.5f);
+        sum = sub(sum, mul(sub(1.0f, fabsf(simplex2(seed + (uint32_t)i, x, y))), amp));
+    }
+    return sum;
+}
+
+__device__ float billow2(uint32_t seed, float x, float y, int octaves)
+{
+    float sum = sub(mul(fabsf(simplex2(seed, x, y)), 2.0f), 1.0f), amp = 1.0f;
+    for (int i = 1; i < octaves; i++)
+    {
+        x = mul(x, 2.0f); y = mul(y, 2.0f); amp = mul(amp, 0.5f);
+        sum = add(sum, mul(sub(mul(fabsf(simplex2(seed + (uint32_t)i, x, y)), 2.0f), 1.0f), amp));
+    }
+    return mul(sum, fractal_bounding(octaves));
+}
+
+__device__ float fbm3(uint32_t seed, float x, float y, float z, int octaves)
+{
+    float sum = simplex3(seed, x, y, z), amp = 1.0f;
+    for (int i = 1; i < octaves; i++)
+    {
+        x = mul(x, 2.0f); y = mul(y, 2.0f); z = mul(z, 2.0f); amp = mul(amp, 0.5f);
+        sum = add(sum, mul(simplex3(seed + (uint32_t)i, x, y, z), amp));
+    }
+    return mul(sum, fractal_bounding(octaves));
+}
+
+__device__ __forceinline__ float scurve3(float a) { return mul(mul(a, a), sub(3.0f, mul(2.0f, a))); }
+
+__device__ __forceinline__ void set_block(const GenArgs& a, int col, int x, int wy, int z, int b)
+{
+    if (wy < 0 || wy >= GC_WORLD_BLOCK_HEIGHT) return;
+    a.blocks[((size_t)col * 4 + (wy >> 6)) * GC_CHUNK_SIZE_3 + x + 32 * ((wy & 63) + 64 * z)] = (uint16_t)b;
+}
+
+// ---- heights (Generation.cpp:83-130 / :228-275 as gcworld.c gen_terrain_column restates them) ----
+__global__ void __launch_bounds__(256) gc_gen_height_kernel(GenArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = a.size_x * a.size_z * 1024;
+    if (i >= n) return;
+    const int col = i >> 10, z = (i >> 5) & 31, x = i & 31;
+    const int cx = col % a.size_x, cz = col / a.size_x;
+    const int sea = a.islands ? 20 : 10;
+    const float mscale = a.islands ? 60.0f : 30.0f, mbase = a.islands ? 20.0f : 10.0f;
+    const int wx = (a.origin_cx + cx) * 32 + x, wz = (a.origin_cz + cz) * 32 + z;
+    int h = 0, m = sea;
+    // IsWithinIsland (Generation.cpp:66-81)
+    const int v = (int)sqrt((double)wx * wx + (double)wz * wz);
+    if (v < a.radius)
+    {
+        float p = 1.0f;
+        if (v > a.falloff) p = sub(1.0f, __fdiv_rn((float)(v - a.falloff), (float)(a.radius - a.falloff)));
+        const float bx = (float)wx, bz = (float)wz;
+        const float biome = simplex2(a.seed + 101u, mul(bx, 0.01f), mul(bz, 0.01f));
+        float flat = mul(add(billow2(a.seed + 202u, mul(mul(bx, 0.025f), 0.5f), mul(mul(bz, 0.025f), 0.5f), 4), 1.0f), 0.5f);
+        flat = add(mul(mul(flat, 0.2f), 30.0f), 10.0f);
+        float mount = mul(add(ridged2(a.seed + 303u, mul(mul(bx, 0.015f), 0.5f), mul(mul(bz, 0.015f), 0.5f), 4), 1.0f), 0.5f);
+        if (mount < 0.0f) mount = 0.0f;
+        mount = add(mul((float)pow((double)mount, 3.5), mscale), mbase);
+        float terrain;
+        if (biome < 0.0f) terrain = flat;
+        else if (biome > 0.6f) terrain = mount;
+        else terrain = add(flat, mul(scurve3(__fdiv_rn(biome, 0.6f)), sub(mount, flat)));
+        h = (int)mul(terrain, p);
+        if (h > GC_WORLD_BLOCK_HEIGHT - 12) h = GC_WORLD_BLOCK_HEIGHT - 12;
+        if (h > m) m = h;
+    }
+    a.height[i] = (int16_t)h;
+    // column maximum of m: warp first, one atomic per warp (a warp is one z-row of one column)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(a.max_y + col, m);
+}
+
+// ---- layers (Generation.cpp:132-200): stone pockets, grass on top, dirt below, water up to sea level ----
+// A CTA owns eight z-rows of one column (a warp = one row of 32 x) and walks up to the column's highest layer.
+__global__ void __launch_bounds__(256) gc_gen_layers_kernel(GenArgs a)
+{
+    const int col = blockIdx.x >> 2;
+    const int z = (blockIdx.x & 3) * 8 + (threadIdx.x >> 5), x = threadIdx.x & 31;
+    const int cx = col % a.size_x, cz = col / a.size_x;
+    const int sea = a.islands ? 20 : 10;
+    const int h = a.height[col * 1024 + z * 32 + x];
+    const int top = a.max_y[col];
+    const int wx = (a.origin_cx + cx) * 32 + x, wz = (a.origin_cz + cz) * 32 + z;
+    const float fx = mul(mul((float)wx, 0.015f), 0.2f), fz = mul(mul((float)wz, 0.015f), 0.2f);
+    for (int wy = 0; wy <= top; wy++)
+    {
+        int b = B_AIR;
+        bool stone = false;
+        if (wy <= h - 4)
+        {
+            const float comp = mul(add(fbm3(a.seed + 404u, fx, mul(mul((float)wy, 0.015f), 0.2f), fz, 2), 1.0f), 0.5f);
+            stone = comp <= 0.2f;
+        }
+        if (stone) b = B_STONE;
+        else if (wy == h) b = B_GRASS;
+        else if (wy > h && wy <= sea) b = B_WATER;
+        else if (wy < h) b = B_DIRT;
+        if (b != B_AIR) set_block(a, col, x, wy, z, b);
+    }
+}
+
+__device__ void box(const GenArgs& a, int col, int x0, int y0, int z0, int x1, int y1, int z1, int b)
+{
+    for (int z = z0; z <= z1; z++)
+        for (int y = y0; y <= y1; y++)
+            for (int x = x0; x <= x1; x++) set_block(a, col, x, y, z, b);
+}
+
+// ---- trees (Generation.cpp:50-64, :204-215): the column's own PRNG stream, in order ----
+__global__ void gc_gen_trees_kernel(GenArgs a)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= a.size_x * a.size_z) return;
+    const int cx = col % a.size_x, cz = col / a.size_x;
+    const int wcx = a.origin_cx + cx, wcz = a.origin_cz + cz;
+    const int sea = a.islands ? 20 : 10;
+    Rng r = { ((uint64_t)hash3(a.seed, wcx, wcz, 77) << 32) | hash3(a.seed, wcz, wcx, 78) };
+    const int trees = a.islands ? rng_range(r, 1, 3) : rng_range(r, 3, 6);
+    for (int i = 0; i < trees; i++)
+    {
+        const int rx = rng_range(r, 3, 32 - 4);
+        const int rz = rng_range(r, 3, 32 - 4);
+        const int s = a.height[col * 1024 + rz * 32 + rx];
+        if (s <= sea) continue;
+        // CreateTree: trunk then five leaf boxes
+        const int by = s + 1;
+        const int th = rng_range(r, 3, 5);
+        for (int j = 0; j < th; j++) set_block(a, col, rx, by + j, rz, B_WOOD);
+        const int sy = by + th;
+        box(a, col, rx - 1, sy, rz - 1, rx + 1, sy, rz + 1, B_LEAVES);
+        box(a, col, rx - 2, sy + 1, rz - 1, rx + 2, sy + 2, rz + 1, B_LEAVES);
+        box(a, col, rx - 1, sy + 1, rz + 2, rx + 1, sy + 2, rz + 2, B_LEAVES);
+        box(a, col, rx - 1, sy + 1, rz - 2, rx + 1, sy + 2, rz - 2, B_LEAVES);
+        box(a, col, rx - 1, sy + 3, rz - 1, rx + 1, sy + 3, rz + 1, B_LEAVES);
+    }
+}
+
+// GenerateFlatTerrain (Generation.cpp:772-836) with radius -> infinity: dirt 0..11, grass 12
+__global__ void __launch_bounds__(256) gc_gen_flat_kernel(GenArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = a.size_x * a.size_z * 1024 * 13;
+    if (i >= n) return;
+    const int col = i / (1024 * 13), r = i % (1024 * 13);
+    const int wy = r >> 10, z = (r >> 5) & 31, x = r & 31;
+    set_block(a, col, x, wy, z, wy == 12 ? B_GRASS : B_DIRT);
+}
+}  // namespace
+
+cudaError_t launch_generate_terrain(const GenArgs& a, cudaStream_t s)
+{
+    const int n_cols = a.size_x * a.size_z;
+    cudaError_t e = cudaMemsetAsync(a.max_y, 0, sizeof(int32_t) * n_cols, s);
+    if (e != cudaSuccess) return e;
+    gc_gen_height_kernel<<<(n_cols * 1024 + 255) / 256, 256, 0, s>>>(a);
+    gc_gen_layers_kernel<<<n_cols * 4, 256, 0, s>>>(a);
+    gc_gen_trees_kernel<<<(n_cols + 63) / 64, 64, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_generate_flat(const GenArgs& a, cudaStream_t s)
+{
+    const int n = a.size_x * a.size_z * 1024 * 13;
+    gc_gen_flat_kernel<<<(n + 255) / 256, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+}  // namespace gc

@@ -1,0 +1,28 @@
+// gcgen kernels (sm_100a): terrain of freshly created columns written straight into the device window — the forest,
+// islands and flat generators (Code/Generation.cpp:83-226, :228-369, :772-836) in the form the input producer
+// gamecraft_b200/worldgen/gcworld.c restates them (the reference's FastNoiseSIMD is not vendored, so the noise is this
+// project's own seeded simplex; the layering, tree and island fall-off rules are the reference's).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gcmesh.h"
+
+namespace gc
+{
+struct GenArgs
+{
+    uint16_t* blocks;       // the window's brick arena (cleared by the caller)
+    int16_t* height;        // scratch: terrain height per (column, z, x)
+    int32_t* max_y;         // scratch: per column, the highest y the layering loop visits
+    int32_t size_x, size_z;
+    int32_t origin_cx, origin_cz;   // world-space column of window column (0, 0): noise is sampled in world space
+    uint32_t seed;
+    int32_t islands;        // 0 forest rules, 1 islands rules
+    int32_t radius, falloff;
+};
+
+cudaError_t launch_generate_terrain(const GenArgs& a, cudaStream_t s);   // heights -> layers -> trees
+cudaError_t launch_generate_flat(const GenArgs& a, cudaStream_t s);
+}  // namespace gc

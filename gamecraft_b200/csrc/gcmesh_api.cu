@@ -17,6 +17,7 @@
 #include "gcrle_kernel.cuh"
 #include "gcedit_kernel.cuh"
 #include "gchalo_kernel.cuh"
+#include "gcgen_kernel.cuh"
 
 using namespace gc;
 
@@ -120,6 +121,8 @@ struct GcWorld
     uint32_t* d_sun_list; size_t sun_list_cap;
     uint32_t* d_light_list; size_t light_list_cap;
     int light_launches; uint32_t light_stats[4];
+    // terrain generation scratch (gcmesh_world_generate)
+    int16_t* d_gen_height; int32_t* d_gen_max_y;
     // peer-memory halo exchange (gcmesh_world_halo_*)
     uint32_t* d_halo_flags;
     HaloPeer halo_peer[2];        // [0]: the rank below, [1]: the rank above
@@ -422,6 +425,7 @@ int gcmesh_world_destroy(GcWorld* w)
         for (int k = 0; k < 5; k++)
             if (w->halo_ipc[d][k]) cudaIpcCloseMemHandle(w->halo_ipc[d][k]);
     cudaFree(w->d_halo_flags);
+    cudaFree(w->d_gen_height); cudaFree(w->d_gen_max_y);
     cudaFree(w->d_vert_table); cudaFree(w->d_edit_dirty); cudaFree(w->d_edit_state); cudaFree(w->d_edit_save);
     cudaFree(w->d_edit_sun_list); cudaFree(w->d_edit_light_list); cudaFree(w->d_edits); cudaFree(w->d_edit_status); cudaFree(w->d_edit_coords);
     if (w->edit_graph) cudaGraphExecDestroy(w->edit_graph);
@@ -814,6 +818,37 @@ int gcmesh_world_download(GcWorld* w, uint16_t* blocks, uint8_t* sunlight, uint8
     if (block_light) GC_CUDA(cudaMemcpyAsync(block_light, w->d_light, w->n_slots * GC_CHUNK_SIZE_3, cudaMemcpyDeviceToHost, s));
     if (surface) GC_CUDA(cudaMemcpyAsync(surface, w->d_surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaStreamSynchronize(s));
+    return GC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Terrain of freshly created columns, generated in place (Generation.cpp:83-369, :772-836); kernels in gcgen_kernel.cu.
+int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, int origin_cz, int radius, int falloff)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    if (kind != GC_GEN_FLAT && kind != GC_GEN_FOREST && kind != GC_GEN_ISLANDS) return fail(GC_ERR_ARG, "unknown generator");
+    if (kind != GC_GEN_FLAT && (radius <= 0 || falloff < 0 || falloff >= radius)) return fail(GC_ERR_ARG, "need 0 <= falloff < radius");
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (!w->d_gen_height)
+    {
+        GC_CUDA(cudaMalloc(&w->d_gen_height, sizeof(int16_t) * w->n_cols * GC_CHUNK_SIZE_2));
+        GC_CUDA(cudaMalloc(&w->d_gen_max_y, sizeof(int32_t) * w->n_cols));
+    }
+    // CreateChunkGroup hands out zeroed chunks (World.cpp:624-643): all AIR, no light, surface 0
+    GC_CUDA(cudaMemsetAsync(w->d_blocks, 0, w->n_slots * GC_CHUNK_SIZE_3 * 2, s));
+    GC_CUDA(cudaMemsetAsync(w->d_sun, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
+    GC_CUDA(cudaMemsetAsync(w->d_light, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
+    GC_CUDA(cudaMemsetAsync(w->d_surface, 0, w->n_cols * GC_CHUNK_SIZE_2, s));
+    GenArgs a;
+    a.blocks = w->d_blocks; a.height = w->d_gen_height; a.max_y = w->d_gen_max_y;
+    a.size_x = w->size_x; a.size_z = w->size_z; a.origin_cx = origin_cx; a.origin_cz = origin_cz;
+    a.seed = seed; a.islands = kind == GC_GEN_ISLANDS; a.radius = radius; a.falloff = falloff;
+    if (kind == GC_GEN_FLAT) GC_CUDA(launch_generate_flat(a, s));
+    else GC_CUDA(launch_generate_terrain(a, s));
+    // the sparse-upload bookkeeping no longer knows what the device arrays hold
+    memset(w->slot_dirty, 7, w->n_slots);
     return GC_OK;
 }
 

@@ -29,7 +29,7 @@ CHUNK_NO_SPACE = 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcedit_kernel.cu", "gchalo_kernel.cu", "gcmesh_api.cu"]
+SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcedit_kernel.cu", "gchalo_kernel.cu", "gcgen_kernel.cu", "gcmesh_api.cu"]
 HEADERS = ["gcmesh_kernel.cuh", "gclight_kernel.cuh", "gcrle_kernel.cuh", "mesh_core.cuh", os.path.join("..", "..", "include", "gcmesh.h")]
 
 
@@ -80,7 +80,7 @@ EXPORTS = [
     "gcmesh_default_light_rules", "gcmesh_set_light_rules", "gcmesh_world_compute_surface", "gcmesh_world_light",
     "gcmesh_world_light_stats", "gcmesh_world_download",
     "gcmesh_world_upload_rle", "gcmesh_world_rle_refused", "gcmesh_world_encode_rle",
-    "gcmesh_world_set_blocks", "gcmesh_world_vertex_counts",
+    "gcmesh_world_set_blocks", "gcmesh_world_vertex_counts", "gcmesh_world_generate",
     "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_mesh_host", "gcmesh_wait", "gcmesh_batch_results",
     "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
     "gcmesh_batch_launches", "gcmesh_kernel_info", "gcmesh_batch_profile",
@@ -134,6 +134,7 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_encode_rle.argtypes = [vp, vp, ci, vp, ctypes.c_size_t, vp]
         L.gcmesh_world_set_blocks.argtypes = [vp, vp, ci, vp, vp, ci, ctypes.POINTER(ci)]
         L.gcmesh_world_vertex_counts.argtypes = [vp, vp]
+        L.gcmesh_world_generate.argtypes = [vp, ci, ctypes.c_uint32, ci, ci, ci, ci]
         L.gcmesh_batch_create.argtypes = [vp, ci, ctypes.c_uint64, ctypes.POINTER(vp)]
         L.gcmesh_batch_destroy.argtypes = [vp]
         L.gcmesh_submit.argtypes = [vp, vp, vp, ci]
@@ -306,6 +307,15 @@ class World:
         _check(lib().gcmesh_world_encode_rle(self.h, _ptr(coords), len(coords), _ptr(data), cap, _ptr(out)), "gcmesh_world_encode_rle")
         used = int(out["first_word"][-1] + out["words"][-1]) if len(out) else 0
         return out, data[:used]
+
+    def generate(self, kind, seed: int = 1337, origin=(0, 0), radius: int = 2**31 - 1, falloff: int | None = None) -> "World":
+        """Terrain of every column of the window, generated on the device ("flat", "forest" or "islands")."""
+        k = {"flat": 0, "forest": 1, "islands": 2}[kind] if isinstance(kind, str) else int(kind)
+        if falloff is None:
+            falloff = radius - 64                                                   # World.cpp:911
+        _check(lib().gcmesh_world_generate(self.h, k, seed & 0xFFFFFFFF, int(origin[0]), int(origin[1]), int(radius), int(falloff)),
+               "gcmesh_world_generate")
+        return self
 
     def set_blocks(self, edits, rebuild_capacity: int | None = None):
         """SetBlock for each (wx, wy, wz, block) in order on the device window -> (status per edit, (n, 3) chunks to rebuild)."""

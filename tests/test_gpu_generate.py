@@ -1,0 +1,78 @@
+"""Terrain generated on the device (gcmesh_world_generate, through the C ABI) against the host input producer
+(gamecraft_b200/worldgen/gcworld.c: the reference's layering / tree / island fall-off rules over this project's own seeded
+noise — the reference's FastNoiseSIMD is not vendored, so parity with the reference's *noise* is unpinned by construction):
+block ids identical, and the device-only pipeline generate -> surface -> light -> mesh equal to the oracle's meshes."""
+import numpy as np
+import pytest
+
+import gcutil as util
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gamecraft_b200 import mesher
+
+    c = mesher.Context(0)
+    yield c
+    c.close()
+
+
+CASES = [
+    ("forest", 6, 1337, (-3, -3), {}),
+    ("forest", 5, 7, (40, -17), {}),
+    ("islands", 7, 4242, (-3, -4), dict(radius=90, falloff=50)),          # the island's edge and fall-off ring cross the window
+    ("islands", 5, 8, (9, 9), dict(radius=512, falloff=448)),
+    ("flat", 4, 1, (0, 0), {}),
+]
+
+
+@pytest.mark.parametrize("kind,size,seed,origin,kw", CASES)
+def test_generated_blocks_equal_host_producer(ctx, kind, size, seed, origin, kw):
+    from gamecraft_b200 import mesher
+
+    host = util.HostWorld(size, size, origin=origin).generate(kind, seed, **kw)
+    junk = util.HostWorld(size, size)
+    junk.blocks[:] = 5; junk.sun[:] = 3; junk.light[:] = 9; junk.surface[:] = 77      # the call has to clear all of it
+    world = mesher.World(ctx, size, size).upload(junk)
+    world.generate(kind, seed, origin=origin, **kw)
+    got = util.HostWorld(size, size)
+    world.download(got, blocks=True)
+    world.close()
+    diff = int((got.blocks != host.blocks).sum())
+    assert diff == 0, "%d of %d block ids differ" % (diff, host.blocks.size)
+    assert not got.sun.any() and not got.light.any() and not got.surface.any()
+    if kind != "flat":
+        assert len(np.unique(host.blocks)) >= 5                                    # air, grass, dirt, stone, water and / or trees
+
+
+def test_device_only_pipeline_meshes_like_the_oracle(ctx):
+    from gamecraft_b200 import mesher
+
+    size, seed, origin = 5, 21, (-2, 3)
+    world = mesher.World(ctx, size, size)
+    world.generate("forest", seed, origin=origin).compute_surface().light()
+    host = util.HostWorld(size, size, origin=origin).generate("forest", seed)
+    host.surface[:] = ob.compute_surface(host)
+    host.sun[:], host.light[:] = ob.light_fill(host, host.surface)
+    coords = host.interior_chunks()
+    orc = ob.OracleWorld(host)
+    quads = 0
+    for c, m in zip(coords.tolist(), mesher.rebuild_chunks(world, coords)):
+        util.assert_same_mesh(m, orc.build_chunk(*c), "chunk %r" % (c,))
+        quads += m.vert_count // 4
+    assert quads > 10000
+    world.close()
+
+
+def test_bad_arguments(ctx):
+    from gamecraft_b200 import mesher
+
+    world = mesher.World(ctx, 3, 3)
+    with pytest.raises(mesher.GcMeshError):
+        world.generate(5, 1)
+    with pytest.raises(mesher.GcMeshError):
+        world.generate("islands", 1, radius=50, falloff=50)
+    world.close()
