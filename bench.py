@@ -391,7 +391,7 @@ def edit_path_leg(ctx, world, host, args):
             cpu = {"unavailable": str(e)}
     return {"ms_per_edit": 1e3 * float(np.median(t_edit)), "ms_per_edit_and_remesh": 1e3 * float(np.median(t_total)),
             "edits": len(t_edit), "applied": applied, "chunks_flagged_per_edit": float(np.mean(flagged)), "cpu_reference": cpu,
-            "call": "gcmesh_world_set_blocks (one edit: a 34-kernel CUDA graph replay, one synchronisation) + gcmesh_submit of the flagged chunks + "
+            "call": "gcmesh_world_set_blocks (one edit: a CUDA graph replay of 19 small kernels) + gcmesh_submit of the flagged chunks + "
                     "gcmesh_wait + gcmesh_batch_download"}
 
 

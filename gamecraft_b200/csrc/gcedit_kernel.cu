@@ -10,7 +10,7 @@
 //            the 27 chunks of FlagChunkForUpdate (World.cpp:507-546)
 //   prepare  resets the box to the state a from-scratch fill starts from (zero, emitters seeded) and lists its
 //            candidate cells
-//   relax    the fill's own sweeps (gc_relax_kernel) over those lists; cells outside the box are read, never written:
+//   relax    the fill's own sweeps (relax_cell, both fills per launch) over those lists; cells outside the box are read, never written:
 //            they hold the fixpoint already and light does not reach further than the box
 //   diff     every cell whose block light or effective sunlight differs from the saved value flags the chunks that
 //            have it inside their one-voxel halo
@@ -248,9 +248,8 @@ cudaError_t launch_edit(const EditArgs& a, cudaStream_t s)
     gc_edit_prepare_kernel<<<grid, 256, 0, s>>>(a);
     for (int sweep = 0; sweep < kLightSweeps; sweep++)
     {
-        e = launch_relax(a.w, true, a.sun_list, kEditBoxCells, a.state + ES_FLAGS + 1 + sweep, s, a.state + ES_SUN_CAND);
-        if (e != cudaSuccess) return e;
-        e = launch_relax(a.w, false, a.light_list, kEditBoxCells, a.state + ES_FLAGS + kLightSweeps + 2 + sweep, s, a.state + ES_LIGHT_CAND);
+        e = launch_relax_pair(a.w, a.sun_list, a.light_list, kEditBoxCells, a.state + ES_SUN_CAND, a.state + ES_LIGHT_CAND,
+                              a.state + ES_FLAGS + 1 + sweep, a.state + ES_FLAGS + kLightSweeps + 2 + sweep, s);
         if (e != cudaSuccess) return e;
     }
     gc_edit_diff_kernel<<<grid, 256, 0, s>>>(a);

@@ -166,12 +166,8 @@ __global__ void __launch_bounds__(256) gc_light_candidates_kernel(LightWorld w, 
 // `changed` points at this sweep's flag word; the previous sweep's is at changed[-1] (sweep 0: a word preset to 1).  A sweep
 // that changed nothing has reached the fixpoint, so every later sweep returns at once.
 template <bool kSun>
-__global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint32_t* __restrict__ list, uint32_t n, const uint32_t* __restrict__ n_dev, uint32_t* changed)
+__device__ __forceinline__ void relax_cell(const LightWorld& w, const uint32_t* __restrict__ list, uint32_t i, uint32_t* changed)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (changed[-1] == 0) return;
-    if (n_dev && i >= *n_dev) return;   // list length known on the device only (edit path): n is the capacity
     const uint32_t v = list[i];
     uint8_t* arr = kSun ? w.sun : w.light;
     const int cur = arr[v];
@@ -211,6 +207,36 @@ __global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint3
         *changed = 1;
     }
 }
+
+template <bool kSun>
+__global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint32_t* __restrict__ list, uint32_t n, uint32_t* changed)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (changed[-1] == 0) return;
+    relax_cell<kSun>(w, list, i, changed);
+}
+
+// One sweep of both fills in one launch, list lengths read from device memory (the edit path: launch-latency bound, and
+// only the device knows how many candidates the box holds).  Threads [0, cap) take the sunlight list, [cap, 2 cap) the
+// blockLight list; each fill has its own chain of "changed" words.
+__global__ void __launch_bounds__(256) gc_relax_pair_kernel(LightWorld w, const uint32_t* __restrict__ sun_list, const uint32_t* __restrict__ light_list,
+                                                            uint32_t cap, const uint32_t* __restrict__ n_sun, const uint32_t* __restrict__ n_light,
+                                                            uint32_t* changed_sun, uint32_t* changed_light)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap)
+    {
+        if (changed_sun[-1] == 0 || i >= *n_sun) return;
+        relax_cell<true>(w, sun_list, i, changed_sun);
+    }
+    else
+    {
+        i -= cap;
+        if (i >= cap || changed_light[-1] == 0 || i >= *n_light) return;
+        relax_cell<false>(w, light_list, i, changed_light);
+    }
+}
 }  // namespace
 
 static int rows_grid(const LightWorld& w) { return (int)(((size_t)w.size_x * w.size_z * 32 * 32 + 255) / 256); }
@@ -242,12 +268,21 @@ cudaError_t launch_light_candidates(const LightWorld& w, const uint32_t* active_
     return cudaGetLastError();
 }
 
-cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s, const uint32_t* n_dev)
+cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (n + 255u) / 256u;
-    if (sun) gc_relax_kernel<true><<<grid, 256, 0, s>>>(w, list, n, n_dev, changed);
-    else gc_relax_kernel<false><<<grid, 256, 0, s>>>(w, list, n, n_dev, changed);
+    if (sun) gc_relax_kernel<true><<<grid, 256, 0, s>>>(w, list, n, changed);
+    else gc_relax_kernel<false><<<grid, 256, 0, s>>>(w, list, n, changed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_relax_pair(const LightWorld& w, const uint32_t* sun_list, const uint32_t* light_list, uint32_t cap, const uint32_t* n_sun,
+                              const uint32_t* n_light, uint32_t* changed_sun, uint32_t* changed_light, cudaStream_t s)
+{
+    // threads [0, cap) and [cap, 2 cap): a CTA may straddle the split
+    const unsigned grid = (2u * cap + 255u) / 256u;
+    gc_relax_pair_kernel<<<grid, 256, 0, s>>>(w, sun_list, light_list, cap, n_sun, n_light, changed_sun, changed_light);
     return cudaGetLastError();
 }
 }  // namespace gc

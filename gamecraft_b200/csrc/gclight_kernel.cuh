@@ -42,6 +42,8 @@ cudaError_t launch_active_bricks(const LightWorld& w, const uint8_t* brick_flags
 cudaError_t launch_light_candidates(const LightWorld& w, const uint32_t* active_list, int n_active, uint32_t* light_list, uint32_t cap, uint32_t* counters, cudaStream_t s);
 // one in-place relaxation sweep over a candidate list (sun = true: sunlight rules with the sky sources); `changed`: this
 // sweep's flag word, the previous sweep's at changed[-1]
-// n_dev (optional): the list's length in device memory, n then being its capacity
-cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s, const uint32_t* n_dev = nullptr);
+cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s);
+// one sweep of both fills in one launch; the lists' lengths are read from device memory, `cap` is their capacity
+cudaError_t launch_relax_pair(const LightWorld& w, const uint32_t* sun_list, const uint32_t* light_list, uint32_t cap, const uint32_t* n_sun,
+                              const uint32_t* n_light, uint32_t* changed_sun, uint32_t* changed_light, cudaStream_t s);
 }  // namespace gc

@@ -184,6 +184,44 @@ def test_graph_replay_equals_plain_launches(ctx, monkeypatch):
         assert np.array_equal(x, y)
 
 
+def test_more_edits_than_one_pass_holds(ctx):
+    """4 200 edits in one call (the device copy of the list holds 4 096 per pass): statuses against the decision oracle,
+    final arrays against a from-scratch fill on the device."""
+    from gamecraft_b200 import mesher
+
+    size = 4
+    src = util.HostWorld(size, size).generate("forest", 4)
+    blank = util.HostWorld(size, size)
+    blank.blocks[:] = src.blocks
+    world, _ = device_world(ctx, blank)
+    h = snapshot(world, blank)
+    verts = world.vertex_counts().reshape(-1)
+    rng = np.random.default_rng(5)
+    edits, want = [], []
+    flagged = np.zeros(size * size * 4, np.uint8)
+    for i in range(4200):
+        wx, wz = int(rng.integers(32, 32 * (size - 1))), int(rng.integers(32, 32 * (size - 1)))
+        wy = int(rng.integers(-2, 130))
+        b = int(rng.choice([0, 0, STONE, LANTERN, WATER, GLASS]))
+        edits.append((wx, wy, wz, b))
+        want.append(ob.set_block(h, verts, wx, wy, wz, b, flagged))        # decisions need blocks and vertex counts only
+    status, rebuild = world.set_blocks(edits)
+    assert status.tolist() == want
+    assert {APPLIED, UNCHANGED, IGNORED} <= set(want)
+    got = snapshot(world, h)
+    assert np.array_equal(got.blocks, h.blocks)
+    assert np.array_equal(got.surface, h.surface)
+    fresh = mesher.World(ctx, size, size).upload(blank)
+    fresh_host = util.HostWorld(size, size)
+    fresh_host.blocks[:] = h.blocks
+    fresh.upload(fresh_host).compute_surface().light()
+    ref = snapshot(fresh, h)
+    fresh.close(); world.close()
+    assert np.array_equal(got.sun, ref.sun)
+    assert np.array_equal(got.light, ref.light)
+    assert len(rebuild) > 0
+
+
 def test_refusals(ctx):
     """Never-built chunk, unchanged block, y outside the world, overflow (AIR left behind), edge columns, list capacity."""
     from gamecraft_b200 import mesher
