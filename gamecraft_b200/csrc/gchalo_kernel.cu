@@ -7,15 +7,13 @@
 //          16-byte accesses straight into the neighbours' arrays; the last CTA to finish publishes "arrived k" in both
 //          neighbours' flag blocks behind a system-scope fence
 //   wait   until both neighbours' planes of exchange k have arrived here
-// Every wait is bounded (kHaloWaitNs): a missing neighbour raises HF_ERROR instead of hanging the stream.
+// Every wait is bounded (HaloPushArgs::wait_ns): a missing neighbour raises HF_ERROR instead of hanging the stream.
 #include "gchalo_kernel.cuh"
 
 namespace gc
 {
 namespace
 {
-constexpr unsigned long long kHaloWaitNs = 2000000000ull;
-
 __device__ __forceinline__ void store_release_sys(uint32_t* p, uint32_t v)
 {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -33,12 +31,12 @@ __device__ __forceinline__ unsigned long long now_ns()
     return t;
 }
 // a wait that gives up records which one it was: HF_ERROR = (serial << 8) | (flag word + 1), first failure only
-__device__ bool wait_at_least(uint32_t* flags, int word, uint32_t serial)
+__device__ bool wait_at_least(uint32_t* flags, int word, uint32_t serial, unsigned long long limit_ns)
 {
     const unsigned long long t0 = now_ns();
     while ((int32_t)(load_acquire_sys(flags + word) - serial) < 0)
     {
-        if (now_ns() - t0 > kHaloWaitNs) { atomicCAS(flags + HF_ERROR, 0u, (serial << 8) | (uint32_t)(word + 1)); return false; }
+        if (now_ns() - t0 > limit_ns) { atomicCAS(flags + HF_ERROR, 0u, (serial << 8) | (uint32_t)(word + 1)); return false; }
         __nanosleep(200);
     }
     return true;
@@ -53,7 +51,7 @@ __global__ void __launch_bounds__(256) gc_halo_exchange_kernel(HaloPushArgs a)
     if (blockIdx.x == 0 && threadIdx.x < 2 && a.peer[threadIdx.x].connected)
         store_release_sys(a.peer[threadIdx.x].flags + (threadIdx.x == 0 ? HF_READY_FROM_UP : HF_READY_FROM_DOWN), a.serial);
     if (threadIdx.x < 2 && a.peer[threadIdx.x].connected)
-        wait_at_least(a.flags, threadIdx.x == 0 ? HF_READY_FROM_DOWN : HF_READY_FROM_UP, a.serial);
+        wait_at_least(a.flags, threadIdx.x == 0 ? HF_READY_FROM_DOWN : HF_READY_FROM_UP, a.serial, a.wait_ns);
     __syncthreads();
 
     // ---- copy ----
@@ -98,7 +96,7 @@ __global__ void __launch_bounds__(256) gc_halo_exchange_kernel(HaloPushArgs a)
 
     // ---- wait: the kernel (and with it the stream) goes on once both neighbours' planes are here ----
     if (threadIdx.x < 2 && a.peer[threadIdx.x].connected)
-        wait_at_least(a.flags, threadIdx.x == 0 ? HF_ARRIVED_FROM_DOWN : HF_ARRIVED_FROM_UP, a.serial);
+        wait_at_least(a.flags, threadIdx.x == 0 ? HF_ARRIVED_FROM_DOWN : HF_ARRIVED_FROM_UP, a.serial, a.wait_ns);
 }
 }  // namespace
 

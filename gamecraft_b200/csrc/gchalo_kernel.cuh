@@ -17,7 +17,7 @@ enum
     HF_ARRIVED_FROM_UP = 1,
     HF_READY_FROM_DOWN = 2,     // serial of the last exchange the rank below has entered: everything it had enqueued before
     HF_READY_FROM_UP = 3,       //   (the mesh kernel reading ITS halo) is done, so its halo rows may be overwritten
-    HF_ERROR = 4,               // a wait gave up (kHaloWaitNs)
+    HF_ERROR = 4,               // a wait gave up (wait_ns)
     HF_TICKET = 5,              // CTA counter of the copy kernel
     HF_WORDS = 8
 };
@@ -38,6 +38,7 @@ struct HaloPushArgs
     int32_t send_row[2];        // [0]: first owned row (its z = 0 plane goes down), [1]: last owned row (z = 31 plane goes up)
     HaloPeer peer[2];           // [0]: the rank below (z - 1), [1]: the rank above
     uint32_t serial;            // 1, 2, ... per exchange
+    unsigned long long wait_ns; // how long a wait for a neighbour may last before it gives up
 };
 
 // loads the kernel (call before the first exchange; see gchalo_kernel.cu)

@@ -941,6 +941,13 @@ int gcmesh_world_halo_push(GcWorld* w, int send_row_down, int send_row_up)
     a.size_x = w->size_x; a.send_row[0] = send_row_down; a.send_row[1] = send_row_up;
     a.peer[0] = w->halo_peer[0]; a.peer[1] = w->halo_peer[1];
     a.serial = ++w->halo_serial;
+    static const unsigned long long wait_ms = []() -> unsigned long long
+    {
+        const char* env = getenv("GCMESH_HALO_WAIT_MS");
+        const long v = env ? atol(env) : 0;
+        return v > 0 ? (unsigned long long)v : 10000ull;
+    }();
+    a.wait_ns = wait_ms * 1000000ull;
     GC_CUDA(launch_halo_push(a, ctx->num_sms, ctx->stream));
     // the neighbours' planes land in this window's halo rows: the sparse-upload bookkeeping no longer knows them
     for (int d = 0; d < 2; d++)

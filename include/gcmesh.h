@@ -159,7 +159,8 @@ int gcmesh_world_unpack_halo(GcWorld* world, int cz, int z, const void* device_b
  *                                   z = 31 plane of row send_row_up to the rank above, wait for the neighbours' planes.
  *                                   Work enqueued afterwards (gcmesh_submit) sees the new halo.  Every rank of a chain
  *                                   calls it the same number of times.
- *   gcmesh_world_halo_status        synchronises; timed_out != 0: a neighbour did not show up within 2 s (no hang);
+ *   gcmesh_world_halo_status        synchronises; timed_out != 0: a neighbour did not show up within 10 s
+ *                                   (GCMESH_HALO_WAIT_MS, read at the first exchange of the process) — an error, not a hang;
  *                                   the value is (exchange serial << 8) | (1 + flag word waited for) of the first such wait */
 #define GC_HALO_HANDLE_BYTES 320
 int gcmesh_world_halo_export(GcWorld* world, void* handles);

@@ -84,6 +84,18 @@ def test_three_slabs_one_gpu_local_peers():
 
 
 def test_missing_neighbour_times_out_instead_of_hanging():
+    """Own process: the wait bound is read once per process (GCMESH_HALO_WAIT_MS)."""
+    import subprocess
+
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import test_gpu_halo_p2p as t; t.missing_neighbour()\n" % (ROOT, os.path.join(ROOT, "tests")))
+    env = dict(os.environ, GCMESH_HALO_WAIT_MS="300")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "timed out as expected" in r.stdout
+
+
+def missing_neighbour():
     from gamecraft_b200 import mesher
 
     w, _, fo, lo = build_window(0, 2)
@@ -94,9 +106,13 @@ def test_missing_neighbour_times_out_instead_of_hanging():
     a.halo_push(fo, lo)                                                         # b never calls halo_push
     timed_out, serial = a.halo_status()
     assert timed_out and serial == 1
-    with pytest.raises(mesher.GcMeshError):
+    try:
         b.halo_push(fo, lo)                                                     # no neighbour connected
+        raise AssertionError("expected GcMeshError")
+    except mesher.GcMeshError:
+        pass
     a.close(); b.close(); ctx_a.close(); ctx_b.close()
+    print("timed out as expected: 0x%x" % timed_out)
 
 
 def _ipc_worker(rank, world_size, port, out_dir):
