@@ -841,6 +841,7 @@ int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, in
     GC_CUDA(cudaMemsetAsync(w->d_sun, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
     GC_CUDA(cudaMemsetAsync(w->d_light, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
     GC_CUDA(cudaMemsetAsync(w->d_surface, 0, w->n_cols * GC_CHUNK_SIZE_2, s));
+    GC_CUDA(cudaMemsetAsync(w->d_vert_table, 0xFF, sizeof(int32_t) * w->n_slots, s));   // new chunks have never been built
     GenArgs a;
     a.blocks = w->d_blocks; a.height = w->d_gen_height; a.max_y = w->d_gen_max_y;
     a.size_x = w->size_x; a.size_z = w->size_z; a.origin_cx = origin_cx; a.origin_cz = origin_cz;

@@ -64,6 +64,12 @@ def test_device_only_pipeline_meshes_like_the_oracle(ctx):
         util.assert_same_mesh(m, orc.build_chunk(*c), "chunk %r" % (c,))
         quads += m.vert_count // 4
     assert quads > 10000
+    # freshly generated chunks have never been built: SetBlock refuses them (World.cpp:562-565) until they are meshed again
+    assert (world.vertex_counts()[1:-1, 1:-1] >= 0).all()
+    world.generate("forest", seed, origin=origin)
+    assert (world.vertex_counts() == -1).all()
+    status, rebuild = world.set_blocks([(40, 5, 40, 0)])
+    assert status.tolist() == [mesher.EDIT_NOT_BUILT] and len(rebuild) == 0
     world.close()
 
 
