@@ -631,6 +631,10 @@ def main():
         sparse_h2d = nz[0] * 131072 + (nz[1] + nz[2]) * 65536 + Pinned.surface.nbytes + 4 * sum(nz)
         d2h = n * 64 + total_quads * 60
 
+        # the ranks of one box share its host cores: each takes its share of them for the zero-scan
+        cores = os.cpu_count() or 2
+        scan_threads = max((cores - 1) // world_size, 1) if world_size > 1 else 0
+
         def timed(one):
             ksteps = max(1, min(args.steps, 10))
             for _ in range(2):
@@ -658,15 +662,15 @@ def main():
         def pipelined():
             # gcmesh_mesh_host: scan / PCIe pull / mesh / read-back overlapped strip by strip.  With slabs on several GPUs the
             # boundary planes arrive with the host arrays themselves (every rank's window holds its halo rows), so no exchange.
-            batch.mesh_host(world, Pinned, coords, h_verts, h_idx)
+            batch.mesh_host(world, Pinned, coords, h_verts, h_idx, threads=scan_threads)
 
         sec, ksteps = timed(pipelined)
         e2e = {"value": all_chunks / sec, "unit": "chunks/s", "h2d_bytes_per_step": int(sparse_h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * sec, "steps": ksteps, "gpu_launches_per_step": batch.launches() + world.upload_launches(),
-               "call": "gcmesh_mesh_host: zero/non-zero scan of the host arrays on %d host threads (one core is left to the thread that "
+               "call": "gcmesh_mesh_host: zero/non-zero scan of the host arrays on %d host threads%s (one core is left to the thread that "
                        "feeds the streams), GPU pull of the non-zero brick arrays, meshing and read-back pipelined in strips of 2 rows "
-                       "on three streams" % max((os.cpu_count() or 2) - 1, 1)}
-        sec, ksteps = timed(staged(lambda: world.upload_sparse(Pinned)))
+                       "on three streams" % (scan_threads or max(cores - 1, 1), " per rank" if world_size > 1 else "")}
+        sec, ksteps = timed(staged(lambda: world.upload_sparse(Pinned, threads=scan_threads)))
         e2e_staged = {"value": all_chunks / sec, "unit": "chunks/s", "ms_per_step": 1e3 * sec, "steps": ksteps,
                       "call": "gcmesh_world_upload_sparse + gcmesh_submit + gcmesh_wait + gcmesh_batch_download, one after the other"}
         sec, ksteps = timed(staged(lambda: world.upload(Pinned)))
