@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <algorithm>
 #include <atomic>
@@ -110,6 +111,7 @@ struct GcWorld
     // sparse upload state
     uint8_t* slot_dirty;      // host: per slot, bit a set = device array a of the slot may hold non-zero data
     uint8_t* scan_flags;      // host: per slot, bit a set = host array a is non-zero (result of the last scan)
+    uint8_t* block_flags;     // host: per slot, 1 = the host block array is non-zero (first stage of the scan)
     uint32_t* h_items;        // pinned: work list of the upload kernel
     uint32_t* d_items;
     int launches;             // kernels launched by the last upload call
@@ -399,7 +401,8 @@ int gcmesh_world_create(GcContext* ctx, int size_x, int size_z, GcWorld** out)
     if (e != cudaSuccess) { gcmesh_world_destroy(w); return fail(GC_ERR_CUDA, "world allocation", cudaGetErrorString(e)); }
     w->slot_dirty = (uint8_t*)calloc(w->n_slots, 1);
     w->scan_flags = (uint8_t*)calloc(w->n_slots, 1);
-    if (!w->slot_dirty || !w->scan_flags) { gcmesh_world_destroy(w); return fail(GC_ERR_ARG, "out of host memory"); }
+    w->block_flags = (uint8_t*)calloc(w->n_slots, 1);
+    if (!w->slot_dirty || !w->scan_flags || !w->block_flags) { gcmesh_world_destroy(w); return fail(GC_ERR_ARG, "out of host memory"); }
     int st = GC_OK;
     if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_slab, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots);
     if (st != GC_OK) { gcmesh_world_destroy(w); return st; }
@@ -431,7 +434,7 @@ int gcmesh_world_destroy(GcWorld* w)
     if (w->edit_graph) cudaGraphExecDestroy(w->edit_graph);
     if (w->h_edit_coords) cudaFreeHost(w->h_edit_coords);
     if (w->h_edit_count) cudaFreeHost(w->h_edit_count);
-    free(w->slot_dirty); free(w->scan_flags);
+    free(w->slot_dirty); free(w->scan_flags); free(w->block_flags);
     delete w;
     return GC_OK;
 }
@@ -541,14 +544,98 @@ static inline bool sun_brick_never_read(const uint8_t* surface, size_t slot)
     return true;
 }
 
-static inline void scan_slot(GcWorld* w, size_t slot, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface)
+// The scan of a window runs in two stages per brick.  Stage A classifies the block ids.  Stage B classifies the two light
+// arrays, and skips them — nothing to scan, nothing to transfer — for a brick whose whole 3 x 3 x 3 brick neighbourhood
+// holds no block at all: light is only ever read for a quad, within one voxel of the block the quad belongs to
+// (VertexLight, WorldRender.cpp:329-383), so no chunk that gets meshed can reach such a brick's light.  In a terrain
+// world that is most of the sky.  (Like the sunlight rule above this leaves the device copy of such an array as it was.)
+static inline void scan_blocks(GcWorld* w, size_t slot, const uint16_t* blocks)
 {
-    uint8_t f = 0;
-    if (!all_zero(blocks + slot * GC_CHUNK_SIZE_3, (size_t)GC_CHUNK_SIZE_3 * 2)) f |= 1;
-    if (!sun_brick_never_read(surface, slot) && !all_zero(sunlight + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 2;
-    if (!all_zero(block_light + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 4;
+    w->block_flags[slot] = all_zero(blocks + slot * GC_CHUNK_SIZE_3, (size_t)GC_CHUNK_SIZE_3 * 2) ? 0 : 1;
+}
+
+static inline bool brick_neighbourhood_is_air(const GcWorld* w, size_t slot)
+{
+    const int cy = (int)(slot & 3), col = (int)(slot >> 2), cx = col % w->size_x, cz = col / w->size_x;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dx = -1; dx <= 1; dx++)
+        {
+            const int nx = cx + dx, nz = cz + dz;
+            if (nx < 0 || nx >= w->size_x || nz < 0 || nz >= w->size_z) continue;
+            const uint8_t* f = w->block_flags + ((size_t)nz * w->size_x + nx) * GC_WORLD_CHUNK_HEIGHT;
+            for (int ny = cy - 1; ny <= cy + 1; ny++)
+                if (ny >= 0 && ny < GC_WORLD_CHUNK_HEIGHT && f[ny]) return false;
+        }
+    return true;
+}
+
+static inline void scan_lights(GcWorld* w, size_t slot, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface)
+{
+    uint8_t f = w->block_flags[slot];
+    if (!brick_neighbourhood_is_air(w, slot))
+    {
+        if (!sun_brick_never_read(surface, slot) && !all_zero(sunlight + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 2;
+        if (!all_zero(block_light + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 4;
+    }
     w->scan_flags[slot] = f;
 }
+
+// Work order of the two stages over the rows of a window: A0, A1, B0, A2, B1, ... so that stage B of a row starts as soon
+// as stage A of the rows around it can be done, and rows still finish in ascending order (the strip pipeline of
+// gcmesh_mesh_host consumes them that way).  Unit u of 2 * rows -> (stage, row).
+struct ScanPlan
+{
+    GcWorld* w;
+    const uint16_t* blocks; const uint8_t* sunlight; const uint8_t* block_light; const uint8_t* surface;
+    size_t slots_per_row;
+    int rows;
+    std::vector<std::atomic<int>> a_remaining;   // per row: slots whose stage A is still to do
+    std::atomic<size_t> next;
+
+    ScanPlan(GcWorld* w_, const uint16_t* b, const uint8_t* s, const uint8_t* l, const uint8_t* sf)
+        : w(w_), blocks(b), sunlight(s), block_light(l), surface(sf), slots_per_row((size_t)w_->size_x * GC_WORLD_CHUNK_HEIGHT), rows(w_->size_z),
+          a_remaining((size_t)w_->size_z), next(0)
+    {
+        for (auto& r : a_remaining) r.store((int)slots_per_row);
+    }
+
+    // runs on every scan thread; done(slot) is called when both stages of a slot are finished
+    void work(const std::function<void(size_t)>& done)
+    {
+        const size_t total = 2 * slots_per_row * (size_t)rows;
+        for (;;)
+        {
+            const size_t t0 = next.fetch_add(4);
+            if (t0 >= total) break;
+            const size_t t1 = t0 + 4 < total ? t0 + 4 : total;
+            for (size_t t = t0; t < t1; t++)
+            {
+                const int u = (int)(t / slots_per_row);
+                const size_t in_row = t % slots_per_row;
+                bool stage_b; int row;
+                if (u == 0) { stage_b = false; row = 0; }
+                else if (u == 2 * rows - 1) { stage_b = true; row = rows - 1; }
+                else if (u & 1) { stage_b = false; row = (u + 1) / 2; }
+                else { stage_b = true; row = u / 2 - 1; }
+                const size_t slot = (size_t)row * slots_per_row + in_row;
+                if (!stage_b)
+                {
+                    scan_blocks(w, slot, blocks);
+                    a_remaining[(size_t)row].fetch_sub(1, std::memory_order_release);
+                }
+                else
+                {
+                    // stage A of the rows around was claimed before this task; wait for whoever still runs it
+                    for (int r = row - 1; r <= row + 1; r++)
+                        if (r >= 0 && r < rows)
+                            while (a_remaining[(size_t)r].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+                    scan_lights(w, slot, sunlight, block_light, surface);
+                    done(slot);
+                }
+            }
+        }
+    }
+};
 
 static int scan_threads(int threads)
 {
@@ -602,18 +689,10 @@ static int upload_rows_sparse(GcWorld* w, int cz0, int cz1, const uint16_t* bloc
     if (nonzero_hint) memcpy(w->scan_flags + s_begin, nonzero_hint + s_begin, s_end - s_begin);
     else
     {
+        // (the two-stage scan looks at neighbouring rows: the window is always classified as a whole)
         const int nt = scan_threads(threads);
-        std::atomic<size_t> next(s_begin);
-        auto work = [&]()
-        {
-            for (;;)
-            {
-                const size_t a0 = next.fetch_add(8);
-                if (a0 >= s_end) break;
-                const size_t a1 = a0 + 8 < s_end ? a0 + 8 : s_end;
-                for (size_t slot = a0; slot < a1; slot++) scan_slot(w, slot, blocks, sunlight, block_light, surface);
-            }
-        };
+        ScanPlan plan(w, blocks, sunlight, block_light, surface);
+        auto work = [&]() { plan.work([](size_t) {}); };
         std::vector<std::thread> pool;
         for (int t = 1; t < nt; t++) pool.emplace_back(work);
         work();
@@ -1414,7 +1493,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     const size_t slots_per_row = (size_t)w->size_x * GC_WORLD_CHUNK_HEIGHT;
     std::vector<std::atomic<int>> remaining((size_t)n_strips);
     std::vector<std::thread> pool;
-    std::atomic<size_t> next_slot(0);
+    ScanPlan plan(w, blocks, sunlight, block_light, surface);
     if (nonzero_hint) memcpy(w->scan_flags, nonzero_hint, w->n_slots);
     else
     {
@@ -1428,17 +1507,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         if (threads <= 0 && nt > 1) nt--;
         auto work = [&, slots_per_row, kStripRows]()
         {
-            for (;;)
-            {
-                const size_t a0 = next_slot.fetch_add(4);
-                if (a0 >= w->n_slots) break;
-                const size_t a1 = a0 + 4 < w->n_slots ? a0 + 4 : w->n_slots;
-                for (size_t slot = a0; slot < a1; slot++)
-                {
-                    scan_slot(w, slot, blocks, sunlight, block_light, surface);
-                    remaining[(slot / slots_per_row) / kStripRows].fetch_sub(1, std::memory_order_release);
-                }
-            }
+            plan.work([&](size_t slot) { remaining[(slot / slots_per_row) / kStripRows].fetch_sub(1, std::memory_order_release); });
         };
         for (int t = 0; t < nt; t++) pool.emplace_back(work);
     }

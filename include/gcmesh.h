@@ -127,9 +127,11 @@ int gcmesh_world_upload_surface(GcWorld* world, int cx, int cz, const uint8_t* s
 int gcmesh_world_upload_all(GcWorld* world, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface);
 /* Rows [cz0, cz1) of columns only (a z-slab of the window), same host layout as upload_all (pointers to the full arrays). */
 int gcmesh_world_upload_rows(GcWorld* world, int cz0, int cz1, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface);
-/* Same meshes as after gcmesh_world_upload_all, moving only what is not zero (and the same device contents, except that a
- * sunlight brick lying wholly at or above its column's `surface` is left cleared: nothing ever reads stored sunlight
- * there, Lighting.cpp:69-79, so with a surface map it is neither scanned nor transferred).  Each brick array of each chunk
+/* Same meshes as after gcmesh_world_upload_all, moving only what is not zero (and the same device contents, with two
+ * exceptions that no mesh can see: a sunlight brick lying wholly at or above its column's `surface` — nothing ever reads
+ * stored sunlight there, Lighting.cpp:69-79 — and the sunlight / blockLight of a brick whose 3 x 3 x 3 brick
+ * neighbourhood holds no block at all — light is only read within one voxel of a block that emits a quad,
+ * WorldRender.cpp:329-383 — are left cleared: neither scanned nor transferred).  Each brick array of each chunk
  * is classified zero / non-zero — by a multi-threaded host scan (nonzero_hint == NULL; `threads` <= 0 = all cores), or by
  * the caller's per-slot hint byte (bit 0 blocks, bit 1 sunlight, bit 2 blockLight non-zero; the caller vouches for it).
  * Non-zero arrays are pulled by a GPU copy kernel straight from the host arrays when those are pinned (cudaHostAlloc /

@@ -363,7 +363,7 @@ def test_gpu_work_order_does_not_change_results(ctx):
     batch.close(); world.close()
 
 
-def test_gpu_sky_sunlight_bricks_are_never_read(ctx):
+def test_gpu_light_that_is_never_read_is_not_transferred(ctx):
     """Stored sunlight at or above a column's surface is ignored (GetSunlight, Lighting.cpp:69-79): the sparse upload skips
     such bricks without scanning them.  Junk written there must not change a single byte of any mesh."""
     import torch
@@ -382,6 +382,18 @@ def test_gpu_sky_sunlight_bricks_are_never_read(ctx):
                 w.sun[col * 4 + cy] = 7          # never read: every cell of the brick lies at or above its column's surface
                 junk += 1
     assert junk > 36
+    # ... and light of either kind in a brick whose 3 x 3 x 3 brick neighbourhood holds no block at all is out of reach of
+    # every quad (VertexLight looks one voxel around the block it lights): the sparse upload skips those arrays as well
+    solid = w.blocks.reshape(6, 6, 4, -1).any(axis=3)                       # [cz][cx][cy]
+    far = 0
+    for cz in range(6):
+        for cx in range(6):
+            for cy in range(4):
+                if not solid[max(cz - 1, 0):cz + 2, max(cx - 1, 0):cx + 2, max(cy - 1, 0):cy + 2].any():
+                    w.light[(cz * 6 + cx) * 4 + cy] = 9
+                    w.sun[(cz * 6 + cx) * 4 + cy] = 5
+                    far += 1
+    assert far >= 36
     o2 = ob.OracleWorld(w)
     for c, x in zip(coords, want):
         util.assert_same_mesh(o2.build_chunk(*c), x, "oracle %s" % (c,))
