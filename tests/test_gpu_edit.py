@@ -104,6 +104,10 @@ def test_edits_relight_and_flag_like_the_oracle(ctx, kind, seed):
             if (step + k) % 4 == 1:
                 b = extra[(step + k) % len(extra)]
             edits.append((wx, wy, wz, b))
+        if step == 5:
+            # the world's top layer: y = 255 is outside ComputeSurface's walk (Lighting.cpp:9), an emitter there is seeded only
+            # when a neighbouring column's surface reaches 255 (ComputeMaxY, Lighting.cpp:28-67)
+            edits = [(70, 255, 70, LANTERN), (71, 254, 70, STONE), (70, 255, 71, MAGMA), (70, 254, 70, GLASS)]
         want_status, want_flags = [], np.zeros(size * size * 4, np.uint8)
         for e in edits:
             st, fl = oracle_edit(h, verts, e)
