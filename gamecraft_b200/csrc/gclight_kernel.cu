@@ -218,23 +218,22 @@ __global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint3
 }
 
 // One sweep of both fills in one launch, list lengths read from device memory (the edit path: launch-latency bound, and
-// only the device knows how many candidates the box holds).  Threads [0, cap) take the sunlight list, [cap, 2 cap) the
-// blockLight list; each fill has its own chain of "changed" words.
+// only the device knows how many candidates the box holds).  The lower half of the grid strides over the sunlight list,
+// the upper half over the blockLight list; each fill has its own chain of "changed" words.
 __global__ void __launch_bounds__(256) gc_relax_pair_kernel(LightWorld w, const uint32_t* __restrict__ sun_list, const uint32_t* __restrict__ light_list,
-                                                            uint32_t cap, const uint32_t* __restrict__ n_sun, const uint32_t* __restrict__ n_light,
+                                                            const uint32_t* __restrict__ n_sun, const uint32_t* __restrict__ n_light,
                                                             uint32_t* changed_sun, uint32_t* changed_light)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cap)
+    const uint32_t half = gridDim.x >> 1;
+    const bool sun = blockIdx.x < half;
+    const uint32_t* changed = sun ? changed_sun : changed_light;
+    if (changed[-1] == 0) return;
+    const uint32_t n = sun ? *n_sun : *n_light;
+    const uint32_t stride = half * blockDim.x;
+    for (uint32_t i = (sun ? blockIdx.x : blockIdx.x - half) * blockDim.x + threadIdx.x; i < n; i += stride)
     {
-        if (changed_sun[-1] == 0 || i >= *n_sun) return;
-        relax_cell<true>(w, sun_list, i, changed_sun);
-    }
-    else
-    {
-        i -= cap;
-        if (i >= cap || changed_light[-1] == 0 || i >= *n_light) return;
-        relax_cell<false>(w, light_list, i, changed_light);
+        if (sun) relax_cell<true>(w, sun_list, i, changed_sun);
+        else relax_cell<false>(w, light_list, i, changed_light);
     }
 }
 }  // namespace
@@ -280,9 +279,10 @@ cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, ui
 cudaError_t launch_relax_pair(const LightWorld& w, const uint32_t* sun_list, const uint32_t* light_list, uint32_t cap, const uint32_t* n_sun,
                               const uint32_t* n_light, uint32_t* changed_sun, uint32_t* changed_light, cudaStream_t s)
 {
-    // threads [0, cap) and [cap, 2 cap): a CTA may straddle the split
-    const unsigned grid = (2u * cap + 255u) / 256u;
-    gc_relax_pair_kernel<<<grid, 256, 0, s>>>(w, sun_list, light_list, cap, n_sun, n_light, changed_sun, changed_light);
+    // enough CTAs to cover `cap` cells per fill in at most a few strides, few enough that a sweep with nothing to do is cheap
+    unsigned half = (cap + 255u) / 256u;
+    if (half > 296u) half = 296u;
+    gc_relax_pair_kernel<<<2 * half, 256, 0, s>>>(w, sun_list, light_list, n_sun, n_light, changed_sun, changed_light);
     return cudaGetLastError();
 }
 }  // namespace gc

@@ -1092,7 +1092,7 @@ int gcmesh_world_set_blocks(GcWorld* w, const GcBlockEdit* edits, int n, int32_t
     a.w = light_world(w); a.blocks_rw = w->d_blocks; a.tables = ctx->d_tables; a.vert_table = w->d_vert_table;
     a.edits = w->d_edits; a.status = w->d_edit_status; a.dirty = w->d_edit_dirty; a.state = w->d_edit_state;
     a.save = w->d_edit_save; a.sun_list = w->d_edit_sun_list; a.light_list = w->d_edit_light_list;
-    // One edit is ~34 tiny launches whose arguments never change (the kernels find the edit through a device-side cursor):
+    // One edit is 19 tiny launches whose arguments never change (the kernels find the edit through a device-side cursor):
     // captured once per world into a CUDA graph and replayed per edit.  GCMESH_EDIT_GRAPH=0, a stream that cannot be
     // captured (the legacy default stream) or a failed capture fall back to plain launches of the same sequence.
     if (!w->edit_graph_tried)
@@ -1128,12 +1128,18 @@ int gcmesh_world_set_blocks(GcWorld* w, const GcBlockEdit* edits, int n, int32_t
     uint32_t* d_count = w->d_edit_state + EP_REBUILD_COUNT;
     GC_CUDA(launch_edit_list(a.w, w->d_edit_dirty, w->d_edit_coords, d_count, s));
     GC_CUDA(cudaMemcpyAsync(w->h_edit_count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    // the first coordinates travel with the count (an edit usually flags a handful of chunks): one synchronisation
+    const uint32_t eager = w->n_slots < 64 ? (uint32_t)w->n_slots : 64u;
+    GC_CUDA(cudaMemcpyAsync(w->h_edit_coords, w->d_edit_coords, sizeof(GcChunkCoord) * eager, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaStreamSynchronize(s));
     const uint32_t flagged = *w->h_edit_count;
     if (flagged)
     {
-        GC_CUDA(cudaMemcpyAsync(w->h_edit_coords, w->d_edit_coords, sizeof(GcChunkCoord) * flagged, cudaMemcpyDeviceToHost, s));
-        GC_CUDA(cudaStreamSynchronize(s));
+        if (flagged > eager)
+        {
+            GC_CUDA(cudaMemcpyAsync(w->h_edit_coords + eager, w->d_edit_coords + eager, sizeof(GcChunkCoord) * (flagged - eager), cudaMemcpyDeviceToHost, s));
+            GC_CUDA(cudaStreamSynchronize(s));
+        }
         std::sort(w->h_edit_coords, w->h_edit_coords + flagged, [](const GcChunkCoord& p, const GcChunkCoord& q)
         {
             if (p.cz != q.cz) return p.cz < q.cz;
