@@ -14,7 +14,7 @@ namespace gc
 {
 namespace
 {
-enum { B_AIR = 0, B_GRASS = 1, B_DIRT = 2, B_STONE = 3, B_WATER = 8, B_WOOD = 9, B_LEAVES = 10 };   // Code/Block.h:11-38
+enum { B_AIR = 0, B_GRASS = 1, B_DIRT = 2, B_STONE = 3, B_METAL_CRATE = 7, B_WATER = 8, B_WOOD = 9, B_LEAVES = 10 };   // Code/Block.h:11-38
 
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
@@ -306,7 +306,19 @@ __global__ void gc_gen_trees_kernel(GenArgs a)
     }
 }
 
-// GenerateFlatTerrain (Generation.cpp:772-836) with radius -> infinity: dirt 0..11, grass 12
+// ---- the reference's three generators that use no noise: reproduced exactly (pinned against the reference's own code) ----
+// IsWithinIsland (Generation.cpp:66-81)
+__device__ __forceinline__ bool within_island(const GenArgs& a, int wx, int wz, float& p)
+{
+    const int v = (int)sqrt((double)(wx * wx) + (double)(wz * wz));          // Square() is integer arithmetic
+    if (v >= a.radius) return false;
+    p = 1.0f;
+    if (v > a.falloff) p = sub(1.0f, __fdiv_rn((float)(v - a.falloff), (float)(a.radius - a.falloff)));
+    return true;
+}
+
+// GenerateFlatTerrain (Generation.cpp:772-836): sea level 12; inside the island grass at (int)(12 * p) with dirt below and
+// water up to sea level, outside it height 0 (one grass layer under the sea)
 __global__ void __launch_bounds__(256) gc_gen_flat_kernel(GenArgs a)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -314,7 +326,49 @@ __global__ void __launch_bounds__(256) gc_gen_flat_kernel(GenArgs a)
     if (i >= n) return;
     const int col = i / (1024 * 13), r = i % (1024 * 13);
     const int wy = r >> 10, z = (r >> 5) & 31, x = r & 31;
-    set_block(a, col, x, wy, z, wy == 12 ? B_GRASS : B_DIRT);
+    const int cx = col % a.size_x, cz = col / a.size_x;
+    const int sea = 12;
+    float p;
+    int height = 0;
+    if (within_island(a, (a.origin_cx + cx) * 32 + x, (a.origin_cz + cz) * 32 + z, p)) height = (int)mul((float)sea, p);
+    int b = B_AIR;
+    if (wy == height) b = B_GRASS;
+    else if (wy > height && wy <= sea) b = B_WATER;
+    else if (wy < height) b = B_DIRT;
+    if (b != B_AIR) set_block(a, col, x, wy, z, b);
+}
+
+// GenerateGridTerrain (Generation.cpp:371-410): in each of the column's four chunks, metal crates on the even lattice
+// inside the radius, a 3 x 3 bundle of pillars and a mast in the middle.  The mast's last crate is stored at chunk-local
+// y = 64: BlockIndex (World.cpp:278-281) carries it to (16, 0, 17) of the same chunk, which is where it is put here.
+__global__ void __launch_bounds__(256) gc_gen_grid_kernel(GenArgs a)
+{
+    const int brick = blockIdx.x;                             // one CTA per chunk
+    const int col = brick >> 2;
+    const int cx = col % a.size_x, cz = col / a.size_x;
+    uint16_t* chunk = a.blocks + (size_t)brick * GC_CHUNK_SIZE_3;
+    const int t = threadIdx.x;                                // 16 x 16 lattice points
+    const int x = (t & 15) * 2, z = (t >> 4) * 2;
+    const int wx = (a.origin_cx + cx) * 32 + x, wz = (a.origin_cz + cz) * 32 + z;
+    if ((int)sqrt((double)(wx * wx) + (double)(wz * wz)) < a.radius)
+        for (int y = 2; y < 14; y += 2) chunk[x + 32 * (y + 64 * z)] = B_METAL_CRATE;
+    __syncthreads();
+    if (t < 9)
+    {
+        const int px = (t % 3) * 2 - 2 + 16, pz = (t / 3) * 2 - 2 + 16;
+        for (int y = 14; y < 40; y += 2) chunk[px + 32 * (y + 64 * pz)] = B_METAL_CRATE;
+    }
+    if (t == 9)
+        for (int y = 40; y <= 64; y += 2) chunk[16 + 32 * (y + 64 * 16)] = B_METAL_CRATE;
+}
+
+// GenerateVoidTerrain (Generation.cpp:838-852): a grass plate at y = 40 in the column at the world origin, nothing else
+__global__ void gc_gen_void_kernel(GenArgs a)
+{
+    const int cx = -a.origin_cx, cz = -a.origin_cz;
+    if (cx < 0 || cx >= a.size_x || cz < 0 || cz >= a.size_z) return;
+    const int col = cz * a.size_x + cx;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) set_block(a, col, i & 31, 40, i >> 5, B_GRASS);
 }
 }  // namespace
 
@@ -333,6 +387,18 @@ cudaError_t launch_generate_flat(const GenArgs& a, cudaStream_t s)
 {
     const int n = a.size_x * a.size_z * 1024 * 13;
     gc_gen_flat_kernel<<<(n + 255) / 256, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_generate_grid(const GenArgs& a, cudaStream_t s)
+{
+    gc_gen_grid_kernel<<<a.size_x * a.size_z * 4, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_generate_void(const GenArgs& a, cudaStream_t s)
+{
+    gc_gen_void_kernel<<<1, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 }  // namespace gc

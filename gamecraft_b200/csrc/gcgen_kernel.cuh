@@ -1,7 +1,8 @@
-// gcgen kernels (sm_100a): terrain of freshly created columns written straight into the device window — the forest,
-// islands and flat generators (Code/Generation.cpp:83-226, :228-369, :772-836) in the form the input producer
-// gamecraft_b200/worldgen/gcworld.c restates them (the reference's FastNoiseSIMD is not vendored, so the noise is this
-// project's own seeded simplex; the layering, tree and island fall-off rules are the reference's).
+// gcgen kernels (sm_100a): terrain of freshly created columns written straight into the device window.
+//   flat, grid, void   (Code/Generation.cpp:772-836, :371-410, :838-852) use no noise: reproduced exactly
+//   forest, islands    (:83-226, :228-369) in the form the input producer gamecraft_b200/worldgen/gcworld.c restates them:
+//                      the reference's FastNoiseSIMD is not vendored, so the noise is this project's own seeded simplex;
+//                      the layering, tree and island fall-off rules are the reference's
 #pragma once
 
 #include <cuda_runtime.h>
@@ -25,4 +26,6 @@ struct GenArgs
 
 cudaError_t launch_generate_terrain(const GenArgs& a, cudaStream_t s);   // heights -> layers -> trees
 cudaError_t launch_generate_flat(const GenArgs& a, cudaStream_t s);
+cudaError_t launch_generate_grid(const GenArgs& a, cudaStream_t s);
+cudaError_t launch_generate_void(const GenArgs& a, cudaStream_t s);
 }  // namespace gc

@@ -905,8 +905,15 @@ int gcmesh_world_download(GcWorld* w, uint16_t* blocks, uint8_t* sunlight, uint8
 int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, int origin_cz, int radius, int falloff)
 {
     if (!w) return fail(GC_ERR_ARG, "world is null");
-    if (kind != GC_GEN_FLAT && kind != GC_GEN_FOREST && kind != GC_GEN_ISLANDS) return fail(GC_ERR_ARG, "unknown generator");
-    if (kind != GC_GEN_FLAT && (radius <= 0 || falloff < 0 || falloff >= radius)) return fail(GC_ERR_ARG, "need 0 <= falloff < radius");
+    if (kind < GC_GEN_FLAT || kind > GC_GEN_VOID) return fail(GC_ERR_ARG, "unknown generator");
+    if (kind != GC_GEN_VOID && (radius <= 0 || falloff < 0 || falloff >= radius)) return fail(GC_ERR_ARG, "need 0 <= falloff < radius");
+    // Square() in IsWithinIsland is integer arithmetic (Generation.cpp:68): keep world coordinates where it cannot overflow
+    {
+        const long long lim = 32000;
+        const long long x0 = (long long)origin_cx * 32, x1 = ((long long)origin_cx + w->size_x) * 32;
+        const long long z0 = (long long)origin_cz * 32, z1 = ((long long)origin_cz + w->size_z) * 32;
+        if (x0 < -lim || x1 > lim || z0 < -lim || z1 > lim) return fail(GC_ERR_ARG, "window further than 32 000 blocks from the world origin");
+    }
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
@@ -926,6 +933,8 @@ int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, in
     a.size_x = w->size_x; a.size_z = w->size_z; a.origin_cx = origin_cx; a.origin_cz = origin_cz;
     a.seed = seed; a.islands = kind == GC_GEN_ISLANDS; a.radius = radius; a.falloff = falloff;
     if (kind == GC_GEN_FLAT) GC_CUDA(launch_generate_flat(a, s));
+    else if (kind == GC_GEN_GRID) GC_CUDA(launch_generate_grid(a, s));
+    else if (kind == GC_GEN_VOID) GC_CUDA(launch_generate_void(a, s));
     else GC_CUDA(launch_generate_terrain(a, s));
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
     memset(w->slot_dirty, 7, w->n_slots);

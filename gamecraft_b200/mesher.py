@@ -309,8 +309,8 @@ class World:
         return out, data[:used]
 
     def generate(self, kind, seed: int = 1337, origin=(0, 0), radius: int = 2**31 - 1, falloff: int | None = None) -> "World":
-        """Terrain of every column of the window, generated on the device ("flat", "forest" or "islands")."""
-        k = {"flat": 0, "forest": 1, "islands": 2}[kind] if isinstance(kind, str) else int(kind)
+        """Terrain of every column of the window, generated on the device ("flat", "forest", "islands", "grid" or "void")."""
+        k = {"flat": 0, "forest": 1, "islands": 2, "grid": 3, "void": 4}[kind] if isinstance(kind, str) else int(kind)
         if falloff is None:
             falloff = radius - 64                                                   # World.cpp:911
         _check(lib().gcmesh_world_generate(self.h, k, seed & 0xFFFFFFFF, int(origin[0]), int(origin[1]), int(radius), int(falloff)),

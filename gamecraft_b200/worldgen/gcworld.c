@@ -344,13 +344,23 @@ static void gen_terrain_column(GcwWorld* w, int cx, int cz, uint32_t seed, int i
     }
 }
 
-/* GenerateFlatTerrain rules (Generation.cpp:772-836) with radius -> infinity: dirt 0..11, grass 12. */
-static void gen_flat_column(GcwWorld* w, int cx, int cz)
+/* GenerateFlatTerrain (Generation.cpp:772-836): sea level 12; inside the island grass at (int)(12 * p) over dirt, water up
+ * to sea level; outside it height 0.  With radius -> infinity: dirt 0..11, grass 12. */
+static void gen_flat_column(GcwWorld* w, int cx, int cz, int radius, int falloff)
 {
+    const int sea = 12;
+    int wcx = w->origin_cx + cx, wcz = w->origin_cz + cz;
     for (int z = 0; z < CH; z++) for (int x = 0; x < CH; x++)
     {
-        for (int wy = 0; wy < 12; wy++) set_block(w, cx, cz, x, wy, z, B_DIRT);
-        set_block(w, cx, cz, x, 12, z, B_GRASS);
+        float p;
+        int h = 0;
+        if (within_island(wcx * CH + x, wcz * CH + z, radius, falloff, &p)) h = (int)((float)sea * p);
+        for (int wy = 0; wy <= sea; wy++)
+        {
+            if (wy == h) set_block(w, cx, cz, x, wy, z, B_GRASS);
+            else if (wy > h) set_block(w, cx, cz, x, wy, z, B_WATER);
+            else set_block(w, cx, cz, x, wy, z, B_DIRT);
+        }
     }
 }
 
@@ -435,7 +445,7 @@ static void gen_column(void* p, int c, int worker)
     memset(w->light + (size_t)c * WCY * CVOX, 0, (size_t)WCY * CVOX);
     switch (g->kind)
     {
-        case GCW_FLAT: gen_flat_column(w, cx, cz); break;
+        case GCW_FLAT: gen_flat_column(w, cx, cz, g->radius, g->falloff); break;
         case GCW_FOREST: gen_terrain_column(w, cx, cz, g->seed, 0, g->radius, g->falloff); break;
         case GCW_ISLANDS: gen_terrain_column(w, cx, cz, g->seed, 1, g->radius, g->falloff); break;
         case GCW_CHECKER: gen_checker_column(w, cx, cz, g->seed); break;

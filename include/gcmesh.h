@@ -211,15 +211,16 @@ int gcmesh_world_rle_refused(GcWorld* world, int* refused);
 int gcmesh_world_encode_rle(GcWorld* world, const GcChunkCoord* coords, int n, uint16_t* records, size_t capacity_words, GcRleChunk* out);
 
 /* ---- terrain generation on the device: columns are born in HBM ----
- * The forest, islands and flat generators (GenerateForestTerrain Code/Generation.cpp:83-226, GenerateIslandsTerrain
- * :228-369, GenerateFlatTerrain :772-836; CreateTree :50-64, IsWithinIsland :66-81) fill the block ids of every column
+ * Five of the reference's generators (GenerateFlatTerrain Code/Generation.cpp:772-836, GenerateGridTerrain :371-410,
+ * GenerateVoidTerrain :838-852 — no noise involved: identical to the reference's own output; GenerateForestTerrain :83-226,
+ * GenerateIslandsTerrain :228-369 with CreateTree :50-64, IsWithinIsland :66-81) fill the block ids of every column
  * of the window; sunlight, blockLight and the surface map are cleared (follow with gcmesh_world_compute_surface and
  * gcmesh_world_light) and every chunk counts as never built (gcmesh_world_set_blocks refuses it until it is meshed).  origin = world-space column of window column (0, 0); radius / falloff = WorldProperties::radius
- * and World::falloffRadius in blocks (forest: INT_MAX and INT_MAX - 64).  The layering, tree and fall-off rules are the
- * reference's; its noise (FastNoiseSIMD, not vendored) and its thread-timing dependent rand() are replaced by a seeded
+ * and World::falloffRadius in blocks (an unbounded world: INT_MAX and INT_MAX - 64).  For forest and islands the layering,
+ * tree and fall-off rules are the reference's; its noise (FastNoiseSIMD, not vendored) and its thread-timing dependent rand() are replaced by a seeded
  * simplex noise and a per-column PRNG — the same ones as the host input producer gamecraft_b200/worldgen, whose worlds
  * this call reproduces block for block.  Asynchronous on the context stream. */
-enum { GC_GEN_FLAT = 0, GC_GEN_FOREST = 1, GC_GEN_ISLANDS = 2 };
+enum { GC_GEN_FLAT = 0, GC_GEN_FOREST = 1, GC_GEN_ISLANDS = 2, GC_GEN_GRID = 3, GC_GEN_VOID = 4 };
 int gcmesh_world_generate(GcWorld* world, int kind, uint32_t seed, int origin_cx, int origin_cz, int radius, int falloff);
 
 /* ---- block edits on a device-resident window: the interactive caller of the mesher ----

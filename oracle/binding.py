@@ -124,6 +124,7 @@ def ref_lib() -> ctypes.CDLL:
         L.gcref_set_surface.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.gcref_get_surface.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.gcref_generate_flat.argtypes = [ctypes.c_void_p]
+        L.gcref_generate.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.gcref_compute_surface.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.gcref_compute_surface_all.argtypes = [ctypes.c_void_p]
         L.gcref_light_all.argtypes = [ctypes.c_void_p]
@@ -237,13 +238,13 @@ class OracleWorld:
 class RefWorld:
     """The reference's own mesher (compiled verbatim) over a copy of a HostWorld (must be square)."""
 
-    def __init__(self, host=None, size=None, seed=1337):
+    def __init__(self, host=None, size=None, seed=1337, radius=2**31 - 1, falloff=None):
         self.L = ref_lib()
         if host is not None:
             assert host.size_x == host.size_z, "the reference window is square (World::size)"
             size = host.size_x
         self.size = size
-        self.h = ctypes.c_void_p(self.L.gcref_world_create(size, seed, 2**31 - 1, 2**31 - 1 - 64))
+        self.h = ctypes.c_void_p(self.L.gcref_world_create(size, seed, radius, radius - 64 if falloff is None else falloff))
         if host is not None:
             self.upload(host)
 
@@ -278,6 +279,10 @@ class RefWorld:
 
     def generate_flat(self):
         self.L.gcref_generate_flat(self.h)
+
+    def generate(self, kind):
+        """The reference's own noise-free generators over every column: "flat", "grid" or "void"."""
+        assert self.L.gcref_generate(self.h, {"flat": 0, "grid": 3, "void": 4}[kind]) == 0
 
     def compute_surface(self):
         self.L.gcref_compute_surface_all(self.h)

@@ -251,6 +251,21 @@ void gcref_generate_flat(GcRefWorld* w)
     for (int i = 0; i < w->world->totalGroups; i++) GenerateFlatTerrain(w->world, w->world->groups[i]);
 }
 
+// The reference's generators that need no FastNoiseSIMD, on every column of the window (group->pos = window position):
+// 0 GenerateFlatTerrain (Generation.cpp:772-836), 3 GenerateGridTerrain (:371-410), 4 GenerateVoidTerrain (:838-852).
+int gcref_generate(GcRefWorld* w, int kind)
+{
+    for (int i = 0; i < w->world->totalGroups; i++)
+    {
+        ChunkGroup* g = w->world->groups[i];
+        if (kind == 0) GenerateFlatTerrain(w->world, g);
+        else if (kind == 3) GenerateGridTerrain(w->world, g);
+        else if (kind == 4) GenerateVoidTerrain(w->world, g);
+        else return -1;
+    }
+    return 0;
+}
+
 // ComputeSurface (Lighting.cpp:19-26) on one column / all columns.
 void gcref_compute_surface(GcRefWorld* w, int cx, int cz)
 {

@@ -26,6 +26,7 @@ CASES = [
     ("islands", 7, 4242, (-3, -4), dict(radius=90, falloff=50)),          # the island's edge and fall-off ring cross the window
     ("islands", 5, 8, (9, 9), dict(radius=512, falloff=448)),
     ("flat", 4, 1, (0, 0), {}),
+    ("flat", 5, 1, (-2, -3), dict(radius=70, falloff=30)),
 ]
 
 
@@ -46,6 +47,42 @@ def test_generated_blocks_equal_host_producer(ctx, kind, size, seed, origin, kw)
     assert not got.sun.any() and not got.light.any() and not got.surface.any()
     if kind != "flat":
         assert len(np.unique(host.blocks)) >= 5                                    # air, grass, dirt, stone, water and / or trees
+
+
+needs_ref = pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref/libgcref.so not built (no reference tree)")
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,radius,falloff", [("flat", 2**31 - 1, 2**31 - 1 - 64), ("flat", 100, 36), ("flat", 33, 1),
+                                                 ("grid", 2**31 - 1, 0), ("grid", 90, 0), ("void", 50, 0)])
+def test_noise_free_generators_equal_the_reference_itself(ctx, kind, radius, falloff):
+    """GenerateFlatTerrain / GenerateGridTerrain / GenerateVoidTerrain run from the reference's own sources (oracle/_ref)."""
+    from gamecraft_b200 import mesher
+    from test_generate_oracle import reference_blocks
+
+    size = 5
+    want = reference_blocks(kind, size, radius, falloff)
+    world = mesher.World(ctx, size, size)
+    world.generate(kind, 1, origin=(0, 0), radius=radius, falloff=falloff)
+    got = util.HostWorld(size, size)
+    world.download(got, blocks=True)
+    world.close()
+    diff = int((got.blocks != want).sum())
+    assert diff == 0, "%d block ids differ from the reference's own %s generator" % (diff, kind)
+
+
+def test_void_plate_follows_the_origin(ctx):
+    from gamecraft_b200 import mesher
+
+    world = mesher.World(ctx, 4, 4)
+    got = util.HostWorld(4, 4)
+    world.generate("void", 1, origin=(-2, -1))                                    # the world origin is window column (2, 1)
+    world.download(got, blocks=True)
+    assert int((got.blocks != 0).sum()) == 1024 and (got.blocks[(1 * 4 + 2) * 4].reshape(32, 64, 32)[:, 40, :] == 1).all()
+    world.generate("void", 1, origin=(5, 5))                                      # origin outside the window: nothing
+    world.download(got, blocks=True)
+    assert not got.blocks.any()
+    world.close()
 
 
 def test_device_only_pipeline_meshes_like_the_oracle(ctx):
@@ -79,6 +116,8 @@ def test_bad_arguments(ctx):
     world = mesher.World(ctx, 3, 3)
     with pytest.raises(mesher.GcMeshError):
         world.generate(5, 1)
+    with pytest.raises(mesher.GcMeshError):
+        world.generate("flat", 1, origin=(2000, 0))                                # Square() of the reference would overflow
     with pytest.raises(mesher.GcMeshError):
         world.generate("islands", 1, radius=50, falloff=50)
     world.close()
