@@ -19,6 +19,7 @@
 #include "gcedit_kernel.cuh"
 #include "gchalo_kernel.cuh"
 #include "gcgen_kernel.cuh"
+#include "gcfill_kernel.cuh"
 
 using namespace gc;
 
@@ -172,6 +173,7 @@ struct GcBatch
     GcChunkCoord* order_coords;     // host copy of the coordinates the order was built for
     int order_n;
     bool order_from_history;        // built from the quad counts of a finished submission of the same list
+    FillJob* d_fill_jobs; size_t fill_jobs_cap;   // gcmesh_batch_fill_device
 };
 
 static int encode_map(GcContext* ctx, CUtensorMap* map, CUtensorMapDataType type, int elem_bytes, void* base, size_t n_slots)
@@ -1329,7 +1331,7 @@ int gcmesh_batch_destroy(GcBatch* b)
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     cudaStreamSynchronize(b->ctx->download_stream);
-    cudaFree(b->d_order); if (b->h_order) cudaFreeHost(b->h_order); free(b->order_coords);
+    cudaFree(b->d_order); if (b->h_order) cudaFreeHost(b->h_order); free(b->order_coords); cudaFree(b->d_fill_jobs);
     cudaFree(b->d_coords); cudaFree(b->d_out); cudaFree(b->d_vertices); cudaFree(b->d_indices); cudaFree(b->d_cursor); cudaFree(b->d_prof);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_coords) cudaFreeHost(b->h_coords);
@@ -1627,6 +1629,41 @@ int gcmesh_batch_fill_meshdata(GcBatch* b, int i, GcMeshData* out)
         if (c.index_count[t])
             GC_CUDA(cudaMemcpyAsync(out->indices[t], b->d_indices + (size_t)c.quad_base * 6 + c.index_offset[t], (size_t)c.index_count[t] * 2, cudaMemcpyDeviceToHost, s));
     GC_CUDA(cudaStreamSynchronize(s));
+    return GC_OK;
+}
+
+int gcmesh_batch_fill_device(GcBatch* b, const GcDeviceMesh* targets, int n)
+{
+    if (!b || (!targets && n > 0)) return fail(GC_ERR_ARG, "null argument");
+    if (b->state != 2) return fail(GC_ERR_STATE, "call gcmesh_wait first");
+    if (n < 0) return fail(GC_ERR_ARG, "negative target count");
+    for (int i = 0; i < n; i++)
+        if (targets[i].chunk < 0 || targets[i].chunk >= b->n) return fail(GC_ERR_ARG, "chunk index outside the batch");
+    if (n == 0) return GC_OK;
+    GC_CUDA(cudaSetDevice(b->ctx->device));
+    if (grow_device(&b->d_fill_jobs, &b->fill_jobs_cap, (size_t)n) != GC_OK) return GC_ERR_CUDA;
+    // resolved from the host copy of the descriptors (the caller's order, also after gcmesh_mesh_host)
+    std::vector<FillJob> jobs((size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+        const GcChunkOut& c = b->h_out[targets[i].chunk];
+        FillJob& j = jobs[(size_t)i];
+        memset(&j, 0, sizeof(j));
+        if (c.vert_count == 0) continue;
+        if (targets[i].vertices)
+        {
+            j.src[0] = b->d_vertices + (size_t)c.quad_base * 48; j.dst[0] = targets[i].vertices; j.bytes[0] = c.vert_count * GC_VERTEX_BYTES;
+        }
+        for (int t = 0; t < GC_MESH_TYPE_COUNT; t++)
+            if (targets[i].indices[t] && c.index_count[t])
+            {
+                j.src[1 + t] = b->d_indices + (size_t)c.quad_base * 6 + c.index_offset[t]; j.dst[1 + t] = targets[i].indices[t];
+                j.bytes[1 + t] = c.index_count[t] * 2;
+            }
+    }
+    cudaStream_t s = b->ctx->stream;
+    GC_CUDA(cudaMemcpyAsync(b->d_fill_jobs, jobs.data(), sizeof(FillJob) * (size_t)n, cudaMemcpyHostToDevice, s));   // pageable: staged before the call returns
+    GC_CUDA(launch_fill_device(b->d_fill_jobs, n, s));
     return GC_OK;
 }
 

@@ -29,7 +29,7 @@ CHUNK_NO_SPACE = 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcedit_kernel.cu", "gchalo_kernel.cu", "gcgen_kernel.cu", "gcmesh_api.cu"]
+SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcedit_kernel.cu", "gchalo_kernel.cu", "gcgen_kernel.cu", "gcfill_kernel.cu", "gcmesh_api.cu"]
 HEADERS = ["gcmesh_kernel.cuh", "gclight_kernel.cuh", "gcrle_kernel.cuh", "mesh_core.cuh", os.path.join("..", "..", "include", "gcmesh.h")]
 
 
@@ -66,6 +66,7 @@ CHUNK_OUT_DTYPE = np.dtype([("quad_base", "<u4"), ("vert_count", "<u4"), ("index
                             ("index_offset", "<u4", (5,)), ("quads", "<u4"), ("flags", "<u4"), ("reserved", "<u4", (2,))])
 assert CHUNK_OUT_DTYPE.itemsize == ctypes.sizeof(ChunkOut) == 64
 HALO_HANDLE_BYTES = 320                                                                                                # GC_HALO_HANDLE_BYTES
+DEVICE_MESH_DTYPE = np.dtype([("chunk", "<i4"), ("reserved", "<i4"), ("vertices", "<u8"), ("indices", "<u8", (5,))])           # GcDeviceMesh
 BLOCK_EDIT_DTYPE = np.dtype([("wx", "<i4"), ("wy", "<i4"), ("wz", "<i4"), ("block", "<u2"), ("reserved", "<u2")])   # GcBlockEdit
 EDIT_APPLIED, EDIT_UNCHANGED, EDIT_IGNORED, EDIT_NOT_BUILT, EDIT_OVERFLOW = range(5)                                   # GC_EDIT_*
 RLE_CHUNK_DTYPE = np.dtype([("cx", "<i4"), ("cy", "<i4"), ("cz", "<i4"), ("first_word", "<u4"), ("words", "<u4")])   # GcRleChunk
@@ -82,7 +83,7 @@ EXPORTS = [
     "gcmesh_world_upload_rle", "gcmesh_world_rle_refused", "gcmesh_world_encode_rle",
     "gcmesh_world_set_blocks", "gcmesh_world_vertex_counts", "gcmesh_world_generate",
     "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_mesh_host", "gcmesh_wait", "gcmesh_batch_results",
-    "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
+    "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_fill_device", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
     "gcmesh_batch_launches", "gcmesh_kernel_info", "gcmesh_batch_profile",
 ]
 
@@ -143,6 +144,7 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_batch_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_uint64)]
         L.gcmesh_batch_download.argtypes = [vp, vp, vp]
         L.gcmesh_batch_fill_meshdata.argtypes = [vp, ci, vp]
+        L.gcmesh_batch_fill_device.argtypes = [vp, vp, ci]
         L.gcmesh_batch_device_ptrs.argtypes = [vp] + [ctypes.POINTER(vp)] * 3
         L.gcmesh_batch_elapsed_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
         L.gcmesh_batch_launches.argtypes = [vp]
@@ -454,6 +456,17 @@ class Batch:
             ii = [idx[qb * 6 + int(d["index_offset"][t]): qb * 6 + int(d["index_offset"][t]) + int(d["index_count"][t])] for t in range(MESH_TYPES)]
             out.append(ChunkMesh(v, ii, d["flags"], d["quads"]))
         return out
+
+    def fill_device(self, targets) -> "Batch":
+        """FillMeshData onto device buffers: ``targets`` = [(chunk index, vertices device pointer or 0, five index-stream
+        device pointers or 0), ...] (e.g. graphics buffers mapped into CUDA).  Asynchronous on the context stream."""
+        arr = np.zeros(len(targets), DEVICE_MESH_DTYPE)
+        for k, (chunk, v, idx) in enumerate(targets):
+            arr[k]["chunk"] = chunk
+            arr[k]["vertices"] = v or 0
+            arr[k]["indices"] = [p or 0 for p in idx]
+        _check(lib().gcmesh_batch_fill_device(self.h, _ptr(arr) if len(arr) else None, len(arr)), "gcmesh_batch_fill_device")
+        return self
 
     def device_ptrs(self):
         p = [ctypes.c_void_p() for _ in range(3)]

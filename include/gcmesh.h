@@ -277,6 +277,21 @@ int gcmesh_batch_download(GcBatch* batch, void* vertices, void* indices);
 /* After gcmesh_wait: chunk i as the reference's MeshData. */
 int gcmesh_batch_fill_meshdata(GcBatch* batch, int i, GcMeshData* out);
 int gcmesh_batch_device_ptrs(GcBatch* batch, void** vertices, void** indices, void** chunk_out);
+/* FillMeshData (Code/Mesh.cpp:71-130) for buffers that live on the device: where the reference uploads a chunk's
+ * MeshData with glBufferData — one GL_ARRAY_BUFFER of vert_count * 12 bytes (attributes: position 3 x u8 at 0, texture
+ * coordinates 3 x u8 at 3, colour 4 x u8 normalised at 6, alpha u8 normalised at 10; Mesh.h:37-44) and one
+ * GL_ELEMENT_ARRAY_BUFFER of index_count[t] uint16 per mesh type with indices — an integration maps those buffers into
+ * CUDA (cudaGraphicsGLRegisterBuffer) and passes the mapped pointers here: the streams go from the batch arenas to the
+ * graphics buffers without crossing PCIe.  After gcmesh_wait (sizes come from gcmesh_batch_results); NULL skips a
+ * stream; asynchronous on the context stream, `targets` is copied. */
+typedef struct GcDeviceMesh
+{
+    int32_t chunk;                              /* index into the batch, submit order */
+    int32_t reserved;
+    void* vertices;                             /* device memory, vert_count * 12 bytes */
+    void* indices[GC_MESH_TYPE_COUNT];          /* device memory, index_count[t] * 2 bytes each */
+} GcDeviceMesh;
+int gcmesh_batch_fill_device(GcBatch* batch, const GcDeviceMesh* targets, int n);
 /* Host arrays in, host meshes out, in ONE call: what an integration does where the reference queues
  * RebuildChunksAsync over a vector<Chunk*> (WorldRender.cpp:80-91).  Equivalent to gcmesh_world_upload_sparse +
  * gcmesh_submit + gcmesh_wait + gcmesh_batch_download, but pipelined in strips of rows on three streams (host zero-scan,

@@ -433,3 +433,65 @@ def test_gpu_arbitrary_inputs(ctx, seed, fill):
             assert d["flags"] & 1
         else:
             util.assert_same_mesh(m, want, "seed %d %s" % (seed, (cx, cy, cz)))
+
+
+def test_gpu_fill_device_buffers(ctx):
+    """FillMeshData onto device buffers (gcmesh_batch_fill_device): per chunk one vertex buffer and one element buffer per
+    mesh type, as the reference creates them with glBufferData (Mesh.cpp:71-130) — here torch tensors stand in for
+    graphics buffers mapped into CUDA.  After gcmesh_submit and after gcmesh_mesh_host (descriptors in the caller's order)."""
+    import torch
+
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(5, 5).build("mixed", 9, radius=90, falloff=50)
+    coords = w.interior_chunks(1)
+    o = ob.OracleWorld(w)
+    want = [o.build_chunk(*c) for c in coords]
+    world = mesher.World(ctx, 5, 5).upload(w)
+    batch = mesher.Batch(ctx, len(coords), len(coords) * 6000)
+
+    def check():
+        desc, q = batch.results()
+        bufs, targets = [], []
+        for i, d in enumerate(desc):
+            v = torch.full((max(int(d["vert_count"]), 1) * 12 + 16,), 0xEE, dtype=torch.uint8, device="cuda")
+            idx = [torch.full((max(int(n), 1) + 8,), 0xEEEE, dtype=torch.uint16, device="cuda") for n in d["index_count"]]
+            bufs.append((v, idx))
+            # odd chunks get a vertex buffer that is only 4-byte aligned, and no buffer for their opaque index stream
+            vp = v.data_ptr() + (4 if i % 2 else 0)
+            targets.append((i, vp, [0 if (i % 2 and t == 0) else x.data_ptr() for t, x in enumerate(idx)]))
+        batch.fill_device(targets)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        for i, (d, m) in enumerate(zip(desc, want)):
+            v, idx = bufs[i]
+            n = int(d["vert_count"]) * 12
+            off = 4 if i % 2 else 0
+            got = v.cpu().numpy()
+            assert np.array_equal(got[off:off + n].reshape(-1, 12), np.asarray(m.vertices).reshape(-1, 12)), "chunk %d vertices" % i
+            assert (got[off + n:] == 0xEE).all() and (got[:off] == 0xEE).all()                     # nothing written past the stream
+            for t in range(5):
+                k = int(d["index_count"][t])
+                g = idx[t].cpu().numpy()
+                if i % 2 and t == 0:
+                    assert (g == 0xEEEE).all()
+                else:
+                    assert np.array_equal(g[:k], m.indices[t]) and (g[k:] == 0xEEEE).all(), "chunk %d stream %d" % (i, t)
+
+    batch.submit(world, coords).wait()
+    check()
+    _, q = batch.results()
+    pins = [torch.from_numpy(a).pin_memory() for a in (w.blocks, w.sun, w.light, w.surface)]
+
+    class P:
+        size_x, size_z = 5, 5
+        blocks, sun, light, surface = [t.numpy() for t in pins]
+
+    hv = np.zeros((q * 4, 12), np.uint8); hi = np.zeros(q * 6, np.uint16)
+    shuffled = coords[np.random.default_rng(2).permutation(len(coords))]
+    want = [o.build_chunk(*c) for c in shuffled]
+    batch.mesh_host(world, P, shuffled, hv, hi)
+    check()
+    with pytest.raises(mesher.GcMeshError):
+        batch.fill_device([(len(coords), 0, [0] * 5)])
+    batch.close(); world.close()
