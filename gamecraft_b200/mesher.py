@@ -460,11 +460,14 @@ class Batch:
     def fill_device(self, targets) -> "Batch":
         """FillMeshData onto device buffers: ``targets`` = [(chunk index, vertices device pointer or 0, five index-stream
         device pointers or 0), ...] (e.g. graphics buffers mapped into CUDA).  Asynchronous on the context stream."""
-        arr = np.zeros(len(targets), DEVICE_MESH_DTYPE)
-        for k, (chunk, v, idx) in enumerate(targets):
-            arr[k]["chunk"] = chunk
-            arr[k]["vertices"] = v or 0
-            arr[k]["indices"] = [p or 0 for p in idx]
+        if isinstance(targets, np.ndarray) and targets.dtype == DEVICE_MESH_DTYPE:
+            arr = np.ascontiguousarray(targets)                                     # prepared once, reused every frame
+        else:
+            arr = np.zeros(len(targets), DEVICE_MESH_DTYPE)
+            for k, (chunk, v, idx) in enumerate(targets):
+                arr[k]["chunk"] = chunk
+                arr[k]["vertices"] = v or 0
+                arr[k]["indices"] = [p or 0 for p in idx]
         _check(lib().gcmesh_batch_fill_device(self.h, _ptr(arr) if len(arr) else None, len(arr)), "gcmesh_batch_fill_device")
         return self
 
