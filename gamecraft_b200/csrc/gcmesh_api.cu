@@ -124,6 +124,9 @@ struct GcWorld
     uint32_t* d_sun_list; size_t sun_list_cap;
     uint32_t* d_light_list; size_t light_list_cap;
     int light_launches; uint32_t light_stats[4];
+    // both light arenas are known to hold zeros (fresh window, gcmesh_world_generate): gcmesh_world_light need not clear them.
+    // Every writer of the arenas resets it; handing out the raw pointers or connecting a halo peer disables it for good.
+    bool light_zero, light_untracked;
     // terrain generation scratch (gcmesh_world_generate)
     int16_t* d_gen_height; int32_t* d_gen_max_y;
     // peer-memory halo exchange (gcmesh_world_halo_*)
@@ -405,6 +408,7 @@ int gcmesh_world_create(GcContext* ctx, int size_x, int size_z, GcWorld** out)
     w->scan_flags = (uint8_t*)calloc(w->n_slots, 1);
     w->block_flags = (uint8_t*)calloc(w->n_slots, 1);
     if (!w->slot_dirty || !w->scan_flags || !w->block_flags) { gcmesh_world_destroy(w); return fail(GC_ERR_ARG, "out of host memory"); }
+    w->light_zero = true;
     int st = GC_OK;
     if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_slab, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots);
     if (st != GC_OK) { gcmesh_world_destroy(w); return st; }
@@ -450,6 +454,7 @@ int gcmesh_world_upload_chunk(GcWorld* w, int cx, int cy, int cz, const uint16_t
     GC_CUDA(cudaSetDevice(w->ctx->device));
     const size_t slot = ((size_t)cz * w->size_x + cx) * GC_WORLD_CHUNK_HEIGHT + cy;
     w->slot_dirty[slot] |= (blocks ? 1 : 0) | (sunlight ? 2 : 0) | (block_light ? 4 : 0);
+    if (sunlight || block_light) w->light_zero = false;
     if (blocks) GC_CUDA(cudaMemcpyAsync(w->d_blocks + slot * GC_CHUNK_SIZE_3, blocks, GC_CHUNK_SIZE_3 * 2, cudaMemcpyHostToDevice, w->ctx->stream));
     if (sunlight) GC_CUDA(cudaMemcpyAsync(w->d_sun + slot * GC_CHUNK_SIZE_3, sunlight, GC_CHUNK_SIZE_3, cudaMemcpyHostToDevice, w->ctx->stream));
     if (block_light) GC_CUDA(cudaMemcpyAsync(w->d_light + slot * GC_CHUNK_SIZE_3, block_light, GC_CHUNK_SIZE_3, cudaMemcpyHostToDevice, w->ctx->stream));
@@ -474,6 +479,7 @@ int gcmesh_world_upload_rows(GcWorld* w, int cz0, int cz1, const uint16_t* block
     const size_t ns = (size_t)(cz1 - cz0) * w->size_x * GC_WORLD_CHUNK_HEIGHT * GC_CHUNK_SIZE_3;
     memset(w->slot_dirty + (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, 7, (size_t)(cz1 - cz0) * w->size_x * GC_WORLD_CHUNK_HEIGHT);
     if (blocks) GC_CUDA(cudaMemcpyAsync(w->d_blocks + s0, blocks + s0, ns * 2, cudaMemcpyHostToDevice, w->ctx->stream));
+    if (sunlight || block_light) w->light_zero = false;
     if (sunlight) GC_CUDA(cudaMemcpyAsync(w->d_sun + s0, sunlight + s0, ns, cudaMemcpyHostToDevice, w->ctx->stream));
     if (block_light) GC_CUDA(cudaMemcpyAsync(w->d_light + s0, block_light + s0, ns, cudaMemcpyHostToDevice, w->ctx->stream));
     if (surface)
@@ -653,6 +659,7 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
 {
     const size_t s_begin = (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, s_end = (size_t)cz1 * w->size_x * GC_WORLD_CHUNK_HEIGHT;
     uint32_t* items = w->h_items + s_begin * 3;   // this row range's own part of the pinned work list
+    w->light_zero = false;
     int n_items = 0;
     for (size_t slot = s_begin; slot < s_end; slot++)
     {
@@ -735,6 +742,7 @@ int gcmesh_world_device_ptrs(GcWorld* w, void** blocks, void** sunlight, void** 
     if (blocks) *blocks = w->d_blocks;
     if (sunlight) *sunlight = w->d_sun;
     if (block_light) *block_light = w->d_light;
+    if (sunlight || block_light) w->light_untracked = true;   // a producer outside this library may write them from now on
     if (surface) *surface = w->d_surface;
     return GC_OK;
 }
@@ -755,6 +763,7 @@ int gcmesh_world_unpack_halo(GcWorld* w, int cz, int z, const void* device_buf)
     if (!w || !device_buf) return fail(GC_ERR_ARG, "null argument");
     if (cz < 0 || cz >= w->size_z || z < 0 || z >= GC_CHUNK_SIZE_H) return fail(GC_ERR_ARG, "row / plane outside the window");
     GC_CUDA(cudaSetDevice(w->ctx->device));
+    w->light_zero = false;
     GC_CUDA(launch_halo_copy(w->d_blocks, w->d_sun, w->d_light, w->d_surface, w->size_x, cz, z, (uint8_t*)device_buf, true, w->ctx->stream));
     return GC_OK;
 }
@@ -828,9 +837,13 @@ int gcmesh_world_light(GcWorld* w)
         GC_CUDA(cudaStreamSynchronize(s));
         return GC_OK;
     };
-    // freshly generated chunks hold no light (World.cpp:632): the fill starts from zero
-    GC_CUDA(cudaMemsetAsync(w->d_sun, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
-    GC_CUDA(cudaMemsetAsync(w->d_light, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
+    // freshly generated chunks hold no light (World.cpp:632): the fill starts from zero (arenas known to be zero are not cleared again)
+    if (!(w->light_zero && !w->light_untracked))
+    {
+        GC_CUDA(cudaMemsetAsync(w->d_sun, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
+        GC_CUDA(cudaMemsetAsync(w->d_light, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
+    }
+    w->light_zero = false;
     GC_CUDA(cudaMemsetAsync(c, 0, kLightCounterWords * sizeof(uint32_t), s));
     // 1. one pass over the column cells up to maxY: sunlight candidates into the list, emitters seeded.  The list keeps
     // its capacity between calls; when it turns out too small the pass is repeated once with the exact size.
@@ -940,6 +953,7 @@ int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, in
     else GC_CUDA(launch_generate_terrain(a, s));
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
     memset(w->slot_dirty, 7, w->n_slots);
+    w->light_zero = true;
     return GC_OK;
 }
 
@@ -961,6 +975,7 @@ int gcmesh_world_halo_export(GcWorld* w, void* handles)
 {
     if (!w || !handles) return fail(GC_ERR_ARG, "null argument");
     if (halo_flags(w) != GC_OK) return GC_ERR_CUDA;
+    w->light_untracked = true;   // neighbours write this window's halo rows from now on
     void* ptrs[5] = { w->d_blocks, w->d_sun, w->d_light, w->d_surface, w->d_halo_flags };
     cudaIpcMemHandle_t* out = (cudaIpcMemHandle_t*)handles;
     static_assert(sizeof(cudaIpcMemHandle_t) * 5 == GC_HALO_HANDLE_BYTES, "GC_HALO_HANDLE_BYTES");
@@ -1013,6 +1028,7 @@ int gcmesh_world_halo_connect_local(GcWorld* w, int side, GcWorld* peer, int pee
         if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
         else if (e != cudaSuccess) return fail(GC_ERR_CUDA, "cudaDeviceEnablePeerAccess", cudaGetErrorString(e));
     }
+    peer->light_untracked = true;   // this world writes the neighbour's halo rows from now on
     HaloPeer& p = w->halo_peer[side];
     p.blocks = peer->d_blocks; p.sun = peer->d_sun; p.light = peer->d_light; p.surface = peer->d_surface; p.flags = peer->d_halo_flags;
     p.row = peer_row; p.connected = 1;
@@ -1081,6 +1097,7 @@ int gcmesh_world_set_blocks(GcWorld* w, const GcBlockEdit* edits, int n, int32_t
             return fail(GC_ERR_ARG, "edit outside the pre-processed (non-edge) columns of the window");
     }
     if (n == 0) return GC_OK;
+    w->light_zero = false;
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;

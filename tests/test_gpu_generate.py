@@ -110,6 +110,29 @@ def test_device_only_pipeline_meshes_like_the_oracle(ctx):
     world.close()
 
 
+def test_light_after_generate_skips_the_clear_only_while_the_arenas_are_known_zero(ctx):
+    """gcmesh_world_generate leaves both light arenas zero, so the fill that follows does not clear them again; any writer in
+    between (a second fill, an upload) brings the clear back."""
+    from gamecraft_b200 import mesher
+
+    size, seed = 4, 3
+    world = mesher.World(ctx, size, size)
+    world.generate("islands", seed, origin=(-2, -2), radius=60, falloff=20).compute_surface().light()
+    a = util.HostWorld(size, size); world.download(a, blocks=True)
+    want_sun, want_light = ob.light_fill(a, ob.compute_surface(a))
+    assert np.array_equal(a.sun, want_sun) and np.array_equal(a.light, want_light)
+    world.light()                                                                  # arenas hold the first fill now
+    b = util.HostWorld(size, size); world.download(b)
+    assert np.array_equal(b.sun, want_sun) and np.array_equal(b.light, want_light)
+    world.generate("islands", seed, origin=(-2, -2), radius=60, falloff=20)
+    junk = np.full(65536, 13, np.uint8)
+    mesher._check(mesher.lib().gcmesh_world_upload_chunk(world.h, 1, 0, 1, None, junk.ctypes.data, junk.ctypes.data), "upload_chunk")
+    world.compute_surface().light()
+    c = util.HostWorld(size, size); world.download(c)
+    assert np.array_equal(c.sun, want_sun) and np.array_equal(c.light, want_light)
+    world.close()
+
+
 def test_bad_arguments(ctx):
     from gamecraft_b200 import mesher
 
