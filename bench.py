@@ -328,8 +328,8 @@ def stream_path_leg(ctx, batch, host, coords, total_quads, workload, gen_s):
         lw.generate(kind, seed, origin=host.origin, radius=radius)
 
     def one():
-        gen()
-        lw.compute_surface().light()
+        gen()                                                 # (block ids and the surface map)
+        lw.light()
         batch.submit(lw, coords).wait()
 
     for _ in range(2):
@@ -349,8 +349,8 @@ def stream_path_leg(ctx, batch, host, coords, total_quads, workload, gen_s):
     gen_sec = (time.perf_counter() - t0) / k
     from gamecraft_b200.worldgen import HostWorld
     got = HostWorld(host.size_x, host.size_z)
-    lw.download(got, blocks=True, sun=False, light=False, surface=False)
-    same = bool(np.array_equal(got.blocks, host.blocks))
+    lw.download(got, blocks=True, sun=False, light=False, surface=True)
+    same = bool(np.array_equal(got.blocks, host.blocks)) and bool(np.array_equal(got.surface, host.surface))
     lw.close()
     n_cols = host.size_x * host.size_z
     return {"metric": "chunks_meshed_per_s", "value": len(coords) / sec, "unit": "chunks/s", "ms_per_step": 1e3 * sec, "steps": k,
@@ -359,7 +359,7 @@ def stream_path_leg(ctx, batch, host, coords, total_quads, workload, gen_s):
                               "what": "gamecraft_b200/worldgen on the host cores: generate + surface + light of the same window (the run's own input preparation)"},
             "blocks_identical_to_host_producer": same, "same_quads_as_host_prepared_world": bool(int(q) == int(total_quads)),
             "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(len(coords) * 64),
-            "call": "gcmesh_world_generate + gcmesh_world_compute_surface + gcmesh_world_light + gcmesh_submit + gcmesh_wait"}
+            "call": "gcmesh_world_generate (block ids + surface map) + gcmesh_world_light + gcmesh_submit + gcmesh_wait"}
 
 
 def edit_path_leg(ctx, world, host, args):

@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(256) gc_gen_height_kernel(GenArgs a)
         if (h > m) m = h;
     }
     a.height[i] = (int16_t)h;
+    // ComputeSurface's entry for this cell (Lighting.cpp:5-17) before trees: the layering fills 0..h and water up to sea level
+    a.surface[i] = (uint8_t)(max(h, sea) + 1);
     // column maximum of m: warp first, one atomic per warp (a warp is one z-row of one column)
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
@@ -277,6 +279,19 @@ __device__ void box(const GenArgs& a, int col, int x0, int y0, int z0, int x1, i
             for (int x = x0; x <= x1; x++) set_block(a, col, x, y, z, b);
 }
 
+// surface = highest non-AIR y in 0..254, plus one (Lighting.cpp:5-17): cells under a box whose top layer is `top`
+__device__ void raise_surface(const GenArgs& a, int col, int x0, int z0, int x1, int z1, int top)
+{
+    if (top > GC_WORLD_BLOCK_HEIGHT - 2) top = GC_WORLD_BLOCK_HEIGHT - 2;
+    if (top < 0) return;
+    for (int z = z0; z <= z1; z++)
+        for (int x = x0; x <= x1; x++)
+        {
+            uint8_t* s = a.surface + (size_t)col * 1024 + z * 32 + x;
+            if (*s < top + 1) *s = (uint8_t)(top + 1);
+        }
+}
+
 // ---- trees (Generation.cpp:50-64, :204-215): the column's own PRNG stream, in order ----
 __global__ void gc_gen_trees_kernel(GenArgs a)
 {
@@ -303,6 +318,11 @@ __global__ void gc_gen_trees_kernel(GenArgs a)
         box(a, col, rx - 1, sy + 1, rz + 2, rx + 1, sy + 2, rz + 2, B_LEAVES);
         box(a, col, rx - 1, sy + 1, rz - 2, rx + 1, sy + 2, rz - 2, B_LEAVES);
         box(a, col, rx - 1, sy + 3, rz - 1, rx + 1, sy + 3, rz + 1, B_LEAVES);
+        // the surface entries under the crown (the trunk's cell is under its top box); a tree tops out below y = 254
+        raise_surface(a, col, rx - 1, rz - 1, rx + 1, rz + 1, sy + 3);
+        raise_surface(a, col, rx - 2, rz - 1, rx + 2, rz + 1, sy + 2);
+        raise_surface(a, col, rx - 1, rz + 2, rx + 1, rz + 2, sy + 2);
+        raise_surface(a, col, rx - 1, rz - 2, rx + 1, rz - 2, sy + 2);
     }
 }
 
@@ -336,6 +356,7 @@ __global__ void __launch_bounds__(256) gc_gen_flat_kernel(GenArgs a)
     else if (wy > height && wy <= sea) b = B_WATER;
     else if (wy < height) b = B_DIRT;
     if (b != B_AIR) set_block(a, col, x, wy, z, b);
+    if (wy == 0) a.surface[(size_t)col * 1024 + z * 32 + x] = (uint8_t)(max(height, sea) + 1);
 }
 
 // GenerateGridTerrain (Generation.cpp:371-410): in each of the column's four chunks, metal crates on the even lattice

@@ -15,6 +15,7 @@ namespace gc
 struct GenArgs
 {
     uint16_t* blocks;       // the window's brick arena (cleared by the caller)
+    uint8_t* surface;       // the window's surface map (cleared by the caller): filled as ComputeSurface would (forest, islands, flat)
     int16_t* height;        // scratch: terrain height per (column, z, x)
     int32_t* max_y;         // scratch: per column, the highest y the layering loop visits
     int32_t size_x, size_z;

@@ -944,13 +944,13 @@ int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, in
     GC_CUDA(cudaMemsetAsync(w->d_surface, 0, w->n_cols * GC_CHUNK_SIZE_2, s));
     GC_CUDA(cudaMemsetAsync(w->d_vert_table, 0xFF, sizeof(int32_t) * w->n_slots, s));   // new chunks have never been built
     GenArgs a;
-    a.blocks = w->d_blocks; a.height = w->d_gen_height; a.max_y = w->d_gen_max_y;
+    a.blocks = w->d_blocks; a.surface = w->d_surface; a.height = w->d_gen_height; a.max_y = w->d_gen_max_y;
     a.size_x = w->size_x; a.size_z = w->size_z; a.origin_cx = origin_cx; a.origin_cz = origin_cz;
     a.seed = seed; a.islands = kind == GC_GEN_ISLANDS; a.radius = radius; a.falloff = falloff;
     if (kind == GC_GEN_FLAT) GC_CUDA(launch_generate_flat(a, s));
-    else if (kind == GC_GEN_GRID) GC_CUDA(launch_generate_grid(a, s));
-    else if (kind == GC_GEN_VOID) GC_CUDA(launch_generate_void(a, s));
-    else GC_CUDA(launch_generate_terrain(a, s));
+    else if (kind == GC_GEN_GRID) { GC_CUDA(launch_generate_grid(a, s)); GC_CUDA(launch_surface(light_world(w), s)); }
+    else if (kind == GC_GEN_VOID) { GC_CUDA(launch_generate_void(a, s)); GC_CUDA(launch_surface(light_world(w), s)); }
+    else GC_CUDA(launch_generate_terrain(a, s));   // (the terrain and flat kernels know their columns' tops: they write the surface map themselves)
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
     memset(w->slot_dirty, 7, w->n_slots);
     w->light_zero = true;

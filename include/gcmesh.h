@@ -214,8 +214,8 @@ int gcmesh_world_encode_rle(GcWorld* world, const GcChunkCoord* coords, int n, u
  * Five of the reference's generators (GenerateFlatTerrain Code/Generation.cpp:772-836, GenerateGridTerrain :371-410,
  * GenerateVoidTerrain :838-852 — no noise involved: identical to the reference's own output; GenerateForestTerrain :83-226,
  * GenerateIslandsTerrain :228-369 with CreateTree :50-64, IsWithinIsland :66-81) fill the block ids of every column
- * of the window; sunlight, blockLight and the surface map are cleared (follow with gcmesh_world_compute_surface and
- * gcmesh_world_light) and every chunk counts as never built (gcmesh_world_set_blocks refuses it until it is meshed).  origin = world-space column of window column (0, 0); radius / falloff = WorldProperties::radius
+ * of the window and its surface map (as ComputeSurface would, Lighting.cpp:5-26); sunlight and blockLight are cleared
+ * (follow with gcmesh_world_light) and every chunk counts as never built (gcmesh_world_set_blocks refuses it until it is meshed).  origin = world-space column of window column (0, 0); radius / falloff = WorldProperties::radius
  * and World::falloffRadius in blocks (an unbounded world: INT_MAX and INT_MAX - 64).  For forest and islands the layering,
  * tree and fall-off rules are the reference's; its noise (FastNoiseSIMD, not vendored) and its thread-timing dependent rand() are replaced by a seeded
  * simplex noise and a per-column PRNG — the same ones as the host input producer gamecraft_b200/worldgen, whose worlds

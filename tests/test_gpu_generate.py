@@ -44,7 +44,8 @@ def test_generated_blocks_equal_host_producer(ctx, kind, size, seed, origin, kw)
     world.close()
     diff = int((got.blocks != host.blocks).sum())
     assert diff == 0, "%d of %d block ids differ" % (diff, host.blocks.size)
-    assert not got.sun.any() and not got.light.any() and not got.surface.any()
+    assert not got.sun.any() and not got.light.any()
+    assert np.array_equal(got.surface, ob.compute_surface(host)), "the generator's surface map is not ComputeSurface's"
     if kind != "flat":
         assert len(np.unique(host.blocks)) >= 5                                    # air, grass, dirt, stone, water and / or trees
 
@@ -69,6 +70,7 @@ def test_noise_free_generators_equal_the_reference_itself(ctx, kind, radius, fal
     world.close()
     diff = int((got.blocks != want).sum())
     assert diff == 0, "%d block ids differ from the reference's own %s generator" % (diff, kind)
+    assert np.array_equal(got.surface, ob.compute_surface(got))
 
 
 def test_void_plate_follows_the_origin(ctx):
@@ -90,7 +92,7 @@ def test_device_only_pipeline_meshes_like_the_oracle(ctx):
 
     size, seed, origin = 5, 21, (-2, 3)
     world = mesher.World(ctx, size, size)
-    world.generate("forest", seed, origin=origin).compute_surface().light()
+    world.generate("forest", seed, origin=origin).light()                          # the generator leaves the surface map behind
     host = util.HostWorld(size, size, origin=origin).generate("forest", seed)
     host.surface[:] = ob.compute_surface(host)
     host.sun[:], host.light[:] = ob.light_fill(host, host.surface)
