@@ -20,26 +20,26 @@ constexpr int kVox = GC_CHUNK_SIZE_3;
 
 __device__ __forceinline__ int surf_of(const LightWorld& w, int col, int x, int z) { return w.surface[(size_t)col * 1024 + z * 32 + x]; }
 
-// ---- ComputeSurface: a thread owns eight x of one (column, z) row (one 16-byte load per layer), a warp eight rows of a column;
-// walks down from y = 254, four layers in flight per thread, until every voxel of the warp has hit a block ----
-__global__ void __launch_bounds__(256) gc_surface_kernel(LightWorld w)
+// ---- ComputeSurface in two steps.  (1) Every brick on its own: a thread owns eight x of one z row (one 16-byte load per
+// layer), a warp eight rows of the brick; it walks down from the brick's top layer, four layers in flight per thread,
+// until every voxel of the warp has hit a block, and leaves "world y + 1 of the highest block in this brick" (0: none) in
+// a per-brick scratch map.  Bricks are independent, so the walk has four times the warps of a per-column walk and the air
+// above the terrain streams at the memory rate.  (2) Per column cell, the entry of the highest brick that has one. ----
+__global__ void __launch_bounds__(256) gc_surface_brick_kernel(LightWorld w, uint8_t* __restrict__ brick_top)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-    const int n_warps = w.size_x * w.size_z * 4;          // 32 rows per column, 8 per warp
+    const int n_warps = w.size_x * w.size_z * 4 * 4;       // per brick: 32 rows, 8 per warp
     if (warp >= n_warps) return;
-    const int col = warp >> 2, z = (warp & 3) * 8 + (lane >> 2), x0 = (lane & 3) * 8;
-    uint32_t lo = 0, hi = 0;                               // surface of the eight voxels, one byte each
-    uint32_t found = 0;                                    // bit i: voxel i has its surface
-    for (int y0 = GC_WORLD_BLOCK_HEIGHT - 2; y0 >= 0; y0 -= 4)   // y = 255 is never looked at (Lighting.cpp:9)
+    const int slot = warp >> 2, cy = slot & 3, z = (warp & 3) * 8 + (lane >> 2), x0 = (lane & 3) * 8;
+    const uint16_t* brick = w.blocks + (size_t)slot * kVox + x0 + 32 * 64 * z;
+    uint32_t lo = 0, hi = 0;                               // entry of the eight voxels, one byte each
+    uint32_t found = 0;                                    // bit i: voxel i has its entry
+    for (int y0 = cy == 3 ? 62 : 63; y0 >= 0; y0 -= 4)     // world y = 255 is never looked at (Lighting.cpp:9)
     {
         uint4 v[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-        {
-            const int y = max(y0 - k, 0);
-            v[k] = *reinterpret_cast<const uint4*>(w.blocks + ((size_t)col * 4 + (y >> 6)) * kVox + x0 + 32 * ((y & 63) + 64 * z));
-        }
+        for (int k = 0; k < 4; k++) v[k] = *reinterpret_cast<const uint4*>(brick + 32 * max(y0 - k, 0));
 #pragma unroll
         for (int k = 0; k < 4; k++)
         {
@@ -53,13 +53,29 @@ __global__ void __launch_bounds__(256) gc_surface_kernel(LightWorld w)
                 if (id != 0 && !((found >> i) & 1u))
                 {
                     found |= 1u << i;
-                    if (i < 4) lo |= (uint32_t)(y + 1) << (8 * i); else hi |= (uint32_t)(y + 1) << (8 * (i - 4));
+                    const uint32_t top = (uint32_t)(cy * 64 + y + 1);
+                    if (i < 4) lo |= top << (8 * i); else hi |= top << (8 * (i - 4));
                 }
             }
         }
         if (__all_sync(0xffffffffu, found == 0xFFu)) break;
     }
-    *reinterpret_cast<uint2*>(w.surface + (size_t)col * 1024 + z * 32 + x0) = make_uint2(lo, hi);
+    *reinterpret_cast<uint2*>(brick_top + (size_t)slot * 1024 + z * 32 + x0) = make_uint2(lo, hi);
+}
+
+__global__ void __launch_bounds__(256) gc_surface_max_kernel(LightWorld w, const uint8_t* __restrict__ brick_top)
+{
+    // a thread: four cells of one column (one 32-bit word per brick); entries grow with the brick, so the maximum per byte
+    // is the entry of the highest brick that has one
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = w.size_x * w.size_z * 256;
+    if (i >= n) return;
+    const int col = i >> 8, q = i & 255;
+    uint32_t best = 0;
+#pragma unroll
+    for (int cy = 0; cy < 4; cy++)
+        best = __vmaxu4(best, reinterpret_cast<const uint32_t*>(brick_top + ((size_t)col * 4 + cy) * 1024)[q]);
+    reinterpret_cast<uint32_t*>(w.surface + (size_t)col * 1024)[q] = best;
 }
 
 // ---- scan of every column cell up to maxY: appends the sunlight candidates, seeds the emitters ----
@@ -240,10 +256,11 @@ __global__ void __launch_bounds__(256) gc_relax_pair_kernel(LightWorld w, const 
 
 static int rows_grid(const LightWorld& w) { return (int)(((size_t)w.size_x * w.size_z * 32 * 32 + 255) / 256); }
 
-cudaError_t launch_surface(const LightWorld& w, cudaStream_t s)
+cudaError_t launch_surface(const LightWorld& w, uint8_t* brick_top, cudaStream_t s)
 {
-    const int grid = (int)(((size_t)w.size_x * w.size_z * 4 * 32 + 255) / 256);
-    gc_surface_kernel<<<grid, 256, 0, s>>>(w);
+    const int grid = (int)(((size_t)w.size_x * w.size_z * 16 * 32 + 255) / 256);
+    gc_surface_brick_kernel<<<grid, 256, 0, s>>>(w, brick_top);
+    gc_surface_max_kernel<<<(w.size_x * w.size_z * 256 + 255) / 256, 256, 0, s>>>(w, brick_top);
     return cudaGetLastError();
 }
 

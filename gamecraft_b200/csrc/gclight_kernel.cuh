@@ -32,7 +32,8 @@ enum { LC_SUN_CAND = 0, LC_LIGHT_CAND = 1, LC_ACTIVE_BRICKS = 2, LC_SEEDS = 4, L
 constexpr int kLightSweeps = 14;
 constexpr int kLightCounterWords = LC_FLAGS + 2 * (kLightSweeps + 1);
 
-cudaError_t launch_surface(const LightWorld& w, cudaStream_t s);
+// brick_top: scratch, 1024 bytes per brick of the window
+cudaError_t launch_surface(const LightWorld& w, uint8_t* brick_top, cudaStream_t s);
 // pass over every column cell up to its maxY: appends the sunlight candidates (non-opaque cells below their column's
 // surface; entries beyond `cap` are only counted), seeds the emitters and flags their bricks
 cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_list, uint32_t cap, uint8_t* brick_flags, uint32_t* counters, cudaStream_t s);

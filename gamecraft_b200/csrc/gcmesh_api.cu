@@ -120,6 +120,7 @@ struct GcWorld
     uint32_t* d_light_counters;   // 8 x u32
     uint32_t* h_light_counters;   // pinned
     uint8_t* d_brick_flags;
+    uint8_t* d_brick_top;         // compute_surface scratch: per brick, the highest block of every column cell
     uint32_t* d_active_list;
     uint32_t* d_sun_list; size_t sun_list_cap;
     uint32_t* d_light_list; size_t light_list_cap;
@@ -428,6 +429,7 @@ int gcmesh_world_destroy(GcWorld* w)
     if (w->h_rle_jobs) cudaFreeHost(w->h_rle_jobs);
     if (w->h_rle_bad) cudaFreeHost(w->h_rle_bad);
     if (w->h_rle_words) cudaFreeHost(w->h_rle_words);
+    cudaFree(w->d_brick_top);
     cudaFree(w->d_light_counters); cudaFree(w->d_brick_flags); cudaFree(w->d_active_list); cudaFree(w->d_sun_list); cudaFree(w->d_light_list);
     if (w->h_light_counters) cudaFreeHost(w->h_light_counters);
     for (int d = 0; d < 2; d++)
@@ -786,6 +788,14 @@ int gcmesh_set_light_rules(GcContext* ctx, const uint8_t* step, const uint8_t* e
     return upload_light_rules(ctx, step, emitted);
 }
 
+static int surface_scratch(GcWorld* w)
+{
+    if (w->d_brick_top) return GC_OK;
+    GC_CUDA(cudaSetDevice(w->ctx->device));
+    GC_CUDA(cudaMalloc(&w->d_brick_top, w->n_slots * GC_CHUNK_SIZE_2));
+    return GC_OK;
+}
+
 static LightWorld light_world(GcWorld* w)
 {
     LightWorld lw;
@@ -798,7 +808,8 @@ int gcmesh_world_compute_surface(GcWorld* w)
 {
     if (!w) return fail(GC_ERR_ARG, "world is null");
     GC_CUDA(cudaSetDevice(w->ctx->device));
-    GC_CUDA(launch_surface(light_world(w), w->ctx->stream));
+    if (surface_scratch(w) != GC_OK) return GC_ERR_CUDA;
+    GC_CUDA(launch_surface(light_world(w), w->d_brick_top, w->ctx->stream));
     return GC_OK;
 }
 
@@ -948,8 +959,12 @@ int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, in
     a.size_x = w->size_x; a.size_z = w->size_z; a.origin_cx = origin_cx; a.origin_cz = origin_cz;
     a.seed = seed; a.islands = kind == GC_GEN_ISLANDS; a.radius = radius; a.falloff = falloff;
     if (kind == GC_GEN_FLAT) GC_CUDA(launch_generate_flat(a, s));
-    else if (kind == GC_GEN_GRID) { GC_CUDA(launch_generate_grid(a, s)); GC_CUDA(launch_surface(light_world(w), s)); }
-    else if (kind == GC_GEN_VOID) { GC_CUDA(launch_generate_void(a, s)); GC_CUDA(launch_surface(light_world(w), s)); }
+    else if (kind == GC_GEN_GRID || kind == GC_GEN_VOID)
+    {
+        if (surface_scratch(w) != GC_OK) return GC_ERR_CUDA;
+        if (kind == GC_GEN_GRID) GC_CUDA(launch_generate_grid(a, s)); else GC_CUDA(launch_generate_void(a, s));
+        GC_CUDA(launch_surface(light_world(w), w->d_brick_top, s));
+    }
     else GC_CUDA(launch_generate_terrain(a, s));   // (the terrain and flat kernels know their columns' tops: they write the surface map themselves)
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
     memset(w->slot_dirty, 7, w->n_slots);
