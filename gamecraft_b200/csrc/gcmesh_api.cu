@@ -582,7 +582,8 @@ static inline bool brick_neighbourhood_is_air(const GcWorld* w, size_t slot)
 static inline void scan_lights(GcWorld* w, size_t slot, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface)
 {
     uint8_t f = w->block_flags[slot];
-    if (!brick_neighbourhood_is_air(w, slot))
+    static const bool skip_rule = []() { const char* e = getenv("GCMESH_SCAN_LIGHT_SKIP"); return !(e && e[0] == '0'); }();
+    if (!skip_rule || !brick_neighbourhood_is_air(w, slot))
     {
         if (!sun_brick_never_read(surface, slot) && !all_zero(sunlight + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 2;
         if (!all_zero(block_light + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 4;
