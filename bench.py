@@ -42,7 +42,16 @@ WORKLOADS = {
     "islands4096": ("islands", 32, 32, 4242, 512),
     "checker1024": ("checker", 16, 16, 99, None),
     "noise1024": ("noise", 16, 16, 77, None),
+    # BASELINE config 5: one 128 x 128-column forest (65 536 chunks) split into z-slabs over the ranks (strong scaling);
+    # rows per rank = 128 / N (the entry holds the total)
+    "forest65536": ("forest", 128, 128, 1337, None),
 }
+STRONG = {"forest65536"}
+
+
+def rows_per_rank(workload: str, world_size: int) -> int:
+    mz = WORKLOADS[workload][2]
+    return mz // world_size if workload in STRONG else mz
 
 
 def parse_args():
@@ -67,6 +76,7 @@ def make_world(workload: str, rank: int, world_size: int):
     from gamecraft_b200.worldgen import HostWorld, INT_MAX
 
     kind, mx, mz, seed, radius = WORKLOADS[workload]
+    mz = rows_per_rank(workload, world_size)
     size_x, size_z = mx + 4, mz + 4
     origin = (-(size_x // 2), rank * mz - (world_size * mz + 4) // 2)
     t0 = time.time()
@@ -738,7 +748,8 @@ def main():
         traffic = dram_traffic_per_launch(args.workload)
         line = {
             "metric": "chunks_meshed_per_s", "value": value, "unit": "chunks/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.workload in STRONG else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args.workload, args.gpus, host, coords, exchange_kind),
             "quads_per_s": all_quads / (ms_per_step * 1e-3), "quads_per_chunk": total_quads / n, "chunks_flagged": flags_bad,
