@@ -5,9 +5,13 @@
 
 One JSON line on stdout (rank 0).  A *step* is one pass of the hot path over one batch: every chunk of the
 workload is meshed once (all vertex + index streams written).  N = 1 workload: BASELINE.json configs[1], 4096
-seeded forest chunks (36x36-column window, inner 32x32 columns x 4 meshed).  N > 1: weak scaling — every rank
-owns a z-slab of 32 rows of columns (4096 chunks) of one 36 x (32N+4) world and exchanges the boundary voxel
-planes with its slab neighbours over NCCL send/recv inside the timed step.
+seeded forest chunks (36x36-column window, inner 32x32 columns x 4 meshed).  N > 1: BASELINE.json configs[4] —
+one 128 x 128-column forest (65 536 chunks) split into z-slabs over the ranks (strong scaling); every step each
+rank meshes its slab and trades the boundary voxel planes with its slab neighbours over NVLink peer memory
+inside the same kernel (gcmesh_submit_exchange); the weak-scaling run (4096 chunks per rank) is a second leg
+of the same line.  Before the first exchange the margin rows a neighbour owns are overwritten with junk on the
+device, and after the timed region EVERY chunk of the last submission is compared byte for byte with the CPU
+oracle ("parity"): a broken exchange or kernel fails the run.
 
   value          whole-job chunks/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
   e2e            same metric through the host-facing C ABI: H2D of the window from pinned host memory + mesh + D2H of
@@ -60,11 +64,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="forest4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="default: forest4096 at N = 1, forest65536 (BASELINE config 5) at N > 1")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p", help="N > 1: how slab neighbours trade boundary planes")
+    ap.add_argument("--exchange", choices=["fused", "p2p", "nccl"], default="fused", help="N > 1: how slab neighbours trade boundary planes")
+    ap.add_argument("--no-parity", action="store_true", help="skip the byte comparison of every chunk of the timed output with the oracle")
+    ap.add_argument("--no-surface-hint", action="store_true", help="e2e: scan every block brick (GC_WORLD_SURFACE_BOUNDS_BLOCKS off)")
+    ap.add_argument("--no-weak-leg", action="store_true", help="N > 1 default run: skip the weak-scaling (forest4096 per rank) second leg")
     ap.add_argument("--no-preprocess", action="store_true", help="skip the surface + light-fill leg (SURVEY 8(f1))")
     return ap.parse_args()
 
@@ -84,6 +91,28 @@ def make_world(workload: str, rank: int, world_size: int):
     host.build(kind, seed, radius=radius if radius else INT_MAX)
     coords = host.interior_chunks(2)
     return host, coords, time.time() - t0
+
+
+def pin_to_local_cpus(local_rank: int, world_size: int):
+    """One process per GPU: keep the rank's threads (zero-scan, stream feeding) and the pages they first touch (pinned host
+    buffers) on the CPUs next to its GPU (the device's local_cpulist in sysfs).  A single-node host is left alone."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        local = cpus & allowed
+        if local and len(local) < len(allowed):
+            os.sched_setaffinity(0, local)
+            return sorted(local)
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -472,28 +501,36 @@ def cpu_reference_run(host, coords, seconds: float, threads: int | None = None):
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's own BuildChunkAsync (oracle/_ref, compiled verbatim) — or its plain-C port where that
+    library did not travel — on all host threads, over the same chunk list as the N = 1 line of this arm.  Every step is
+    timed on its own; `value` is the rate of the median step (a noisy neighbour on the host shows up as best << worst)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    host, coords, gen_s = make_world(args.workload, 0, 1)
+    workload = args.workload or "forest4096"
+    host, coords, gen_s = make_world(workload, 0, 1)
     threads = os.cpu_count() or 1
     from oracle import binding as ob
 
     impl, kind = (ob.RefWorld(host), "reference") if (ob.have_ref() and host.size_x == host.size_z) else (ob.OracleWorld(host), "port")
     n = len(coords)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 1)):
         impl.bench(coords, threads)
-    t, q = 0.0, 0
+    secs, q = [], 0
     for _ in range(args.steps):
         sec, quads = impl.bench(coords, threads)
-        t += sec; q += quads
-    value = n * args.steps / t
+        secs.append(sec); q += quads
+    med, best, worst, mean = float(np.median(secs)), float(np.min(secs)), float(np.max(secs)), float(np.mean(secs))
+    value = n / med
     line = {
         "impl": "reference", "metric": "chunks_meshed_per_s", "value": value, "unit": "chunks/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * med, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args.workload, 1, host, coords),
-        "quads_per_s": q / t,
+        "config": workload_config(workload, 1, host, coords),
+        "quads_per_s": q / args.steps / med,
+        "step_ms": {"median": 1e3 * med, "best": 1e3 * best, "worst": 1e3 * worst, "mean": 1e3 * mean,
+                    "note": "value = chunks / median step; each step spawns its workers (one per host thread, pinned to the process's CPUs in turn)"},
+        "best_step_chunks_per_s": n / best, "mean_chunks_per_s": n / mean,
         "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": kind,
                          "sample": "every step = the full %d-chunk list on %d host threads" % (n, threads)},
         "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -504,8 +541,10 @@ def run_reference_arm(args):
 
 def workload_config(workload, n_gpus, host, coords, exchange=None):
     kind, mx, mz, seed, radius = WORKLOADS[workload]
-    how = {"p2p": "boundary voxel planes stored straight into the neighbours' windows over NVLink peer memory (no collective)",
-           "nccl": "NCCL send/recv of boundary voxel planes"}.get(exchange, "")
+    how = {"fused": "boundary voxel planes stored into the neighbours' windows over NVLink peer memory by the mesh kernel itself "
+                    "(its first work items; boundary-row chunks wait for the neighbour's arrival flag): one kernel per step, no collective",
+           "p2p": "boundary voxel planes stored straight into the neighbours' windows over NVLink peer memory by an exchange kernel ahead of the mesh kernel (no collective)",
+           "nccl": "NCCL send/recv of packed boundary voxel planes"}.get(exchange, "")
     return {
         "workload": workload, "world": kind, "seed": seed, "chunks_per_gpu": int(len(coords)),
         "window_columns_per_gpu": [host.size_x, host.size_z], "chunk_voxels": "32x64x32",
@@ -514,29 +553,29 @@ def workload_config(workload, n_gpus, host, coords, exchange=None):
     }
 
 
-def main():
-    args = parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
+def scribble_margin_rows(world, host, rows, seed):
+    """Overwrites whole rows of columns of the DEVICE window with junk (random block ids, light nibbles and surface heights).
+    bench.py does this to the margin rows a slab neighbour owns before the first exchange: the rank's window was generated
+    with correct margins (world-space noise), so without this a broken exchange would go unseen."""
+    rng = np.random.default_rng(seed)
+    jb = rng.integers(0, 24, 65536, dtype=np.uint16)
+    js = rng.integers(0, 16, 65536, dtype=np.uint8)
+    jl = rng.integers(0, 16, 65536, dtype=np.uint8)
+    jf = rng.integers(0, 256, 1024, dtype=np.uint8)
+    for cz in rows:
+        for cx in range(host.size_x):
+            for cy in range(4):
+                world.upload_chunk(cx, cy, cz, np.roll(jb, cx * 4 + cy), np.roll(js, cx), np.roll(jl, cy))
+            world.upload_surface(cx, cz, jf)
+    world.ctx.synchronize()
 
-    import torch
-    import torch.distributed as dist
 
+def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs):
+    """One workload: device-resident timing, parity of every chunk against the oracle, kernel-only timing, and (full_legs) the
+    end-to-end and §8(f) legs.  Returns the JSON line (rank 0) or None."""
     from gamecraft_b200 import mesher
 
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world_size != args.gpus and world_size > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world_size))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the mesher has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    host, coords, gen_s = make_world(args.workload, rank, world_size)
+    host, coords, gen_s = make_world(workload, rank, world_size)
     n = len(coords)
 
     # an explicit (non-default) stream: the library launches on it, torch's events and NCCL ops are ordered on it
@@ -547,40 +586,34 @@ def main():
     world = mesher.World(ctx, host.size_x, host.size_z)
 
     # pinned host copies: the e2e leg uploads from these every step
-    pin = [torch.from_numpy(a).pin_memory() for a in (host.blocks, host.sun, host.light, host.surface)]
+    want_e2e = full_legs and not args.no_e2e
+    if want_e2e:
+        pin = [torch.from_numpy(a).pin_memory() for a in (host.blocks, host.sun, host.light, host.surface)]
 
-    class Pinned:
-        size_x, size_z = host.size_x, host.size_z
-        blocks, sun, light, surface = [t.numpy() for t in pin]
+        class Pinned:
+            size_x, size_z = host.size_x, host.size_z
+            blocks, sun, light, surface = [t.numpy() for t in pin]
+    else:
+        Pinned = host
 
     world.upload(Pinned)
     ctx.synchronize()
 
-    # size the arenas from a first pass
-    probe = mesher.Batch(ctx, n, n * mesher.MAX_QUADS // 8 + 1)
-    probe.submit(world, coords).wait()
-    desc, _ = probe.results()
-    total_quads = int(desc["quads"].sum())
-    if (desc["flags"] != 0).any():
-        probe.close()
-        probe = mesher.Batch(ctx, n, total_quads + 1)
-        probe.submit(world, coords).wait()
-        desc, _ = probe.results()
-    flags_bad = int((desc["flags"] != 0).sum())
-    desc = desc.copy()                                   # (a view of the batch's pinned memory until here)
-    probe.close()
-    batch = mesher.Batch(ctx, n, total_quads + 1)
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     # ---- slab halo exchange (N > 1): boundary voxel planes to / from the z-neighbours ----
-    # Default: each rank stores its planes straight into its neighbours' windows over NVLink peer memory (CUDA IPC handles,
-    # gcmesh_world_halo_push: one kernel, flags in peer memory, no collective).  --exchange nccl keeps the
-    # pack -> NCCL send/recv -> unpack form (also the fallback when the IPC handles cannot be opened).
+    #   fused (default): gcmesh_submit_exchange — the mesh kernel itself stores the planes into the neighbours' windows
+    #   p2p: gcmesh_world_halo_push (an exchange kernel over peer memory) ahead of gcmesh_submit
+    #   nccl: pack -> NCCL send/recv -> unpack (also the fallback when the IPC handles cannot be opened)
     halo = None
     exchange_kind = None
+    top_row, bottom_row = host.size_z - 3, 2              # last / first meshed row of columns
     if world_size > 1:
-        top_row, bottom_row = host.size_z - 3, 2          # last / first meshed row of columns
         exchange_kind = args.exchange
-        if exchange_kind == "p2p":
+        if exchange_kind in ("fused", "p2p"):
             handles = [None] * world_size
             dist.all_gather_object(handles, world.halo_export())
             ok = 1
@@ -599,6 +632,15 @@ def main():
         if exchange_kind == "nccl":
             hb = world.halo_bytes()
             halo = {k: torch.empty(hb, dtype=torch.uint8, device="cuda") for k in ("send_up", "send_down", "recv_up", "recv_down")}
+        # the margin rows that belong to a neighbour are junk on the device from here on: only the exchange can make the
+        # boundary-row chunks come out right (parity below compares them with the oracle of the correct window)
+        scribbled = []
+        if rank > 0:
+            scribbled += list(range(0, bottom_row))
+        if rank + 1 < world_size:
+            scribbled += list(range(top_row + 1, host.size_z))
+        scribble_margin_rows(world, host, scribbled, 1000 + rank)
+        barrier()
 
     def exchange():
         if exchange_kind == "p2p":
@@ -619,49 +661,108 @@ def main():
             world.unpack_halo(bottom_row - 1, 31, halo["recv_down"].data_ptr())
         return 2 * ((rank + 1 < world_size) + (rank > 0))
 
-    def step():
-        launches = 0
-        if world_size > 1:
-            launches += exchange()
-        batch.submit(world, coords)
+    def step(b):
+        if world_size > 1 and exchange_kind == "fused":
+            b.submit_exchange(world, coords, bottom_row, top_row)
+            return 1
+        launches = exchange() if world_size > 1 else 0
+        b.submit(world, coords)
         return launches + 1
 
-    def barrier():
-        if world_size > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # size the arenas from a first pass (with its exchange: every rank steps the same number of times)
+    probe = mesher.Batch(ctx, n, n * mesher.MAX_QUADS // 8 + 1)
+    step(probe); probe.wait()
+    desc, _ = probe.results()
+    total_quads = int(desc["quads"].sum())
+    again = torch.tensor([1 if (desc["flags"] != 0).any() else 0], dtype=torch.int32, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(again, op=dist.ReduceOp.MAX)
+    if int(again.item()):
+        probe.close()
+        probe = mesher.Batch(ctx, n, total_quads + 1)
+        step(probe); probe.wait()
+        desc, _ = probe.results()
+    flags_bad = int((desc["flags"] != 0).sum())
+    probe.close()
+
+    # the first submission of a list has no quad history to order the work by (the reference's streaming caller meshes a chunk
+    # once, WorldRender.cpp:177-180): time it on fresh batches
+    cold_ms = []
+    if world_size == 1:
+        for _ in range(3):
+            cold = mesher.Batch(ctx, n, total_quads + 1)
+            cold.submit(world, coords).wait()
+            cold_ms.append(cold.elapsed_ms())
+            cold.close()
+
+    batch = mesher.Batch(ctx, n, total_quads + 1)
+    batch.set_timing(False)                              # nothing but the launch between back-to-back kernels
 
     # ---- device-resident timing ----
     for _ in range(max(args.warmup, 3)):
-        step()
+        step(batch)
     batch.wait()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
     barrier()
     ev0.record()
     launches = 0
     for _ in range(args.steps):
-        launches += step()
+        launches += step(batch)
     ev1.record()
     batch.wait()
     barrier()
     total_ms = ev0.elapsed_time(ev1)
-    # mean duration of the mesh kernel alone (the library's own events bracket exactly the launch)
-    for _ in range(min(args.steps, 10)):
-        batch.submit(world, coords).wait()
-        kernel_ms.append(batch.elapsed_ms())
     clocks = sampler.stop()
+
+    # ---- parity: every chunk of the last timed submission, byte for byte, against the oracle of this rank's (correct) window ----
+    parity = None
     desc, tq = batch.results()
     assert int(desc["quads"].sum()) == total_quads
+    if not args.no_parity:
+        from oracle import binding as ob
+
+        t0 = time.perf_counter()
+        verts, idx = batch.download()
+        cores = os.cpu_count() or 1
+        bad, result, quads_checked = ob.OracleWorld(host).check_batch(coords, desc.copy(), verts, idx, threads=max(cores // world_size, 1))
+        edge = (coords[:, 2] == bottom_row) | (coords[:, 2] == top_row)
+        mine = [float(n), float(bad), float(quads_checked), float(int(edge.sum()) if world_size > 1 else 0), float(int((result[edge] != 0).sum()) if world_size > 1 else 0)]
+        del verts, idx
+        acc = torch.tensor(mine, dtype=torch.float64, device="cuda")
+        per_rank = [None] * world_size
+        if world_size > 1:
+            dist.all_gather_object(per_rank, int(bad))
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        else:
+            per_rank = [int(bad)]
+        a = [int(v) for v in acc.tolist()]
+        parity = {"chunks": a[0], "mismatches": a[1], "quads_compared": a[2], "mismatches_per_rank": per_rank,
+                  "checker": "oracle/gc_mesh_cpu.c (plain-C restatement, pinned to the reference compiled verbatim): every chunk of the last timed "
+                             "submission rebuilt on the host and compared byte for byte (counts, vertex stream, five index streams)",
+                  "seconds": time.perf_counter() - t0}
+        if world_size > 1:
+            parity["boundary_row_chunks"] = a[3]
+            parity["boundary_row_mismatches"] = a[4]
+            parity["halo_rows_scribbled_before_first_exchange"] = True
+
+    # mean duration of the mesh kernel alone (the library's own events bracket exactly the launch)
+    batch.set_timing(True)
+    kernel_ms = []
+    for _ in range(min(args.steps, 10)):
+        step(batch); batch.wait()
+        kernel_ms.append(batch.elapsed_ms())
+    batch.set_timing(False)
 
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    km = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
     cq = torch.tensor([float(n), float(total_quads)], dtype=torch.float64, device="cuda")
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(km, op=dist.ReduceOp.MAX)
         dist.all_reduce(cq, op=dist.ReduceOp.SUM)
     total_ms = float(t.item())
     all_chunks, all_quads = float(cq[0].item()), float(cq[1].item())
@@ -674,20 +775,18 @@ def main():
     # streams back.  "e2e_dense" is the same with a plain full upload (every array of every chunk, cudaMemcpyAsync).
     e2e = None
     e2e_dense = None
-    if not args.no_e2e:
+    if want_e2e:
         h_verts = torch.empty((total_quads * 4 + 4, 12), dtype=torch.uint8).pin_memory().numpy()
         h_idx = torch.empty(total_quads * 6 + 6, dtype=torch.uint16).pin_memory().numpy()
         dense_h2d = sum(a.nbytes for a in (Pinned.blocks, Pinned.sun, Pinned.light, Pinned.surface))
-        nz = [int(a.reshape(a.shape[0], -1).any(axis=1).sum()) for a in (Pinned.blocks, Pinned.sun, Pinned.light)]
-        sparse_h2d = nz[0] * 131072 + (nz[1] + nz[2]) * 65536 + Pinned.surface.nbytes + 4 * sum(nz)
         d2h = n * 64 + total_quads * 60
 
         # the ranks of one box share its host cores: each takes its share of them for the zero-scan
         cores = os.cpu_count() or 2
         scan_threads = max((cores - 1) // world_size, 1) if world_size > 1 else 0
 
-        def timed(one):
-            ksteps = max(1, min(args.steps, 10))
+        def timed(one, ksteps=None):
+            ksteps = ksteps or max(1, min(args.steps, 10))
             for _ in range(2):
                 one()
             barrier()
@@ -704,8 +803,6 @@ def main():
         def staged(upload):
             def one():
                 upload()
-                if world_size > 1:
-                    exchange()
                 batch.submit(world, coords).wait()
                 batch.download(h_verts, h_idx)
             return one
@@ -715,77 +812,134 @@ def main():
             # boundary planes arrive with the host arrays themselves (every rank's window holds its halo rows), so no exchange.
             batch.mesh_host(world, Pinned, coords, h_verts, h_idx, threads=scan_threads)
 
+        # the windows' surface maps are ComputeSurface of their block ids (as ChunkGroup::surface always is): the scan may take the
+        # bricks above them for AIR unread (GC_WORLD_SURFACE_BOUNDS_BLOCKS)
+        world.set_option(mesher.WORLD_SURFACE_BOUNDS_BLOCKS, 0 if args.no_surface_hint else 1)
         sec, ksteps = timed(pipelined)
-        e2e = {"value": all_chunks / sec, "unit": "chunks/s", "h2d_bytes_per_step": int(sparse_h2d), "d2h_bytes_per_step": int(d2h),
+        h2d = world.upload_bytes()
+        e2e = {"value": all_chunks / sec, "unit": "chunks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * sec, "steps": ksteps, "gpu_launches_per_step": batch.launches() + world.upload_launches(),
                "call": "gcmesh_mesh_host: zero/non-zero scan of the host arrays on %d host threads%s (one core is left to the thread that "
-                       "feeds the streams), GPU pull of the non-zero brick arrays, meshing and read-back pipelined in strips of 2 rows "
-                       "on three streams" % (scan_threads or max(cores - 1, 1), " per rank" if world_size > 1 else "")}
-        sec, ksteps = timed(staged(lambda: world.upload_sparse(Pinned, threads=scan_threads)))
-        e2e_staged = {"value": all_chunks / sec, "unit": "chunks/s", "ms_per_step": 1e3 * sec, "steps": ksteps,
-                      "call": "gcmesh_world_upload_sparse + gcmesh_submit + gcmesh_wait + gcmesh_batch_download, one after the other"}
-        sec, ksteps = timed(staged(lambda: world.upload(Pinned)))
-        e2e_dense = {"value": all_chunks / sec, "unit": "chunks/s", "h2d_bytes_per_step": int(dense_h2d), "d2h_bytes_per_step": int(d2h),
-                     "ms_per_step": 1e3 * sec, "steps": ksteps, "call": "gcmesh_world_upload_all (every array of every chunk) + submit + wait + download"}
-        e2e_dense["staged_sparse"] = e2e_staged
+                       "feeds the streams; %s), GPU pull of the non-zero brick arrays, meshing and read-back pipelined in strips of 2 rows "
+                       "on three streams" % (scan_threads or max(cores - 1, 1), " per rank" if world_size > 1 else "",
+                                             "every block brick is scanned" if args.no_surface_hint else
+                                             "GC_WORLD_SURFACE_BOUNDS_BLOCKS: block bricks above their column's surface map are AIR by ComputeSurface's definition and are not read")}
+        if not args.no_parity:
+            # the meshes that came back over PCIe, every chunk, against the oracle
+            from oracle import binding as ob
+
+            d2, _ = batch.results()
+            bad2, _, _ = ob.OracleWorld(host).check_batch(coords, d2.copy(), h_verts, h_idx, threads=max(cores // world_size, 1))
+            acc = torch.tensor([float(bad2)], dtype=torch.float64, device="cuda")
+            if world_size > 1:
+                dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            e2e["parity_mismatches"] = int(acc.item())
+        if world_size == 1:
+            sec, ksteps = timed(staged(lambda: world.upload_sparse(Pinned, threads=scan_threads)))
+            e2e_staged = {"value": all_chunks / sec, "unit": "chunks/s", "ms_per_step": 1e3 * sec, "steps": ksteps,
+                          "call": "gcmesh_world_upload_sparse + gcmesh_submit + gcmesh_wait + gcmesh_batch_download, one after the other"}
+            sec, ksteps = timed(staged(lambda: world.upload(Pinned)), 3)
+            e2e_dense = {"value": all_chunks / sec, "unit": "chunks/s", "h2d_bytes_per_step": int(dense_h2d), "d2h_bytes_per_step": int(d2h),
+                         "ms_per_step": 1e3 * sec, "steps": ksteps, "call": "gcmesh_world_upload_all (every array of every chunk) + submit + wait + download"}
+            e2e_dense["staged_sparse"] = e2e_staged
 
     # ---- column pre-processing on the device: surface map + light flood fill from the block ids ----
-    preprocess = None
-    load_path = None
-    stream_path = None
-    edit_path = None
-    if not args.no_preprocess and world_size == 1:
+    preprocess = load_path = stream_path = edit_path = None
+    if full_legs and not args.no_preprocess and world_size == 1:
         preprocess = preprocess_leg(ctx, host, Pinned, args)
         load_path = load_path_leg(ctx, world, batch, host, coords, total_quads, args)
-        stream_path = stream_path_leg(ctx, batch, host, coords, total_quads, args.workload, gen_s)
+        stream_path = stream_path_leg(ctx, batch, host, coords, total_quads, workload, gen_s)
         edit_path = edit_path_leg(ctx, world, host, args)     # last: it edits the device world
 
+    line = None
     if rank == 0:
         peak, peak_src = hbm_peak()
-        kms = float(np.mean(kernel_ms))
+        kms = float(km.item())
         alg_bytes = n * ALG_BYTES_PER_CHUNK + total_quads * ALG_BYTES_PER_QUAD
         achieved = alg_bytes / (kms * 1e-3) / 1e9
-        traffic = dram_traffic_per_launch(args.workload)
+        traffic = dram_traffic_per_launch(workload) if world_size == 1 else None
         line = {
             "metric": "chunks_meshed_per_s", "value": value, "unit": "chunks/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if args.workload in STRONG else "weak",
+            "scaling": "strong" if workload in STRONG else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args.workload, args.gpus, host, coords, exchange_kind),
+            "config": workload_config(workload, args.gpus, host, coords, exchange_kind),
             "quads_per_s": all_quads / (ms_per_step * 1e-3), "quads_per_chunk": total_quads / n, "chunks_flagged": flags_bad,
+            "parity": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": "gc_mesh_kernel", "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms_note": "mean over %d launches, CUDA events around the launch on the launching stream%s" %
+                                           (len(kernel_ms), "; rank 0's launch moves rank 0's bytes, the duration is the slowest rank's" if world_size > 1 else ""),
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          # light is only read where quads are, so fewer bytes move than the algorithmic figure credits;
                          # the physical rate (ncu DRAM bytes of one launch / this run's kernel time) is reported next to it
                          "physical_gbs": (traffic / (kms * 1e-3) / 1e9) if traffic else None,
                          "physical_frac": (traffic / (kms * 1e-3) / 1e9 / peak) if traffic else None},
             "gpu_launches": launches, "clocks": clocks, "kernel_info": ctx.kernel_info(), "worldgen_s": gen_s,
+            "between_kernels_us": 1e3 * (ms_per_step - kms),
         }
+        if cold_ms:
+            line["cold_order"] = {"kernel_ms": float(np.median(cold_ms)), "chunks_per_s": n / (float(np.median(cold_ms)) * 1e-3),
+                                  "note": "first submission of the list on a fresh batch: no quad history, work order = lower chunks first"}
+        if world_size > 1:
+            line["exchange"] = {"kind": exchange_kind, "collective": "none (peer-memory stores + flags)" if exchange_kind != "nccl" else "NCCL send/recv",
+                                "process_group": "NCCL (barrier and all-reduce of the timings only)"}
         if e2e:
             line["e2e"] = e2e
-            line["e2e_dense"] = e2e_dense
-        if not args.no_cpu_baseline and world_size == 1:
+            if e2e_dense:
+                line["e2e_dense"] = e2e_dense
+        if full_legs and not args.no_cpu_baseline and world_size == 1:
             line["cpu_baseline"] = cpu_reference_run(host, coords, args.cpu_seconds)
-        if preprocess:
-            line["preprocess"] = preprocess
-        if load_path:
-            line["load_path"] = load_path
-        if stream_path:
-            line["stream_path"] = stream_path
-        if edit_path:
-            line["edit_path"] = edit_path
-        print(json.dumps(line), flush=True)
+        for k, v in (("preprocess", preprocess), ("load_path", load_path), ("stream_path", stream_path), ("edit_path", edit_path)):
+            if v:
+                line[k] = v
 
-    halo_timed_out = world.halo_status()[0] if exchange_kind == "p2p" else False
+    halo_timed_out = world.halo_status()[0] if exchange_kind in ("p2p", "fused") else False
     if world_size > 1:
         dist.barrier()                                    # nobody unmaps a window a neighbour may still write to
     batch.close(); world.close(); ctx.close()
-    if world_size > 1:
-        dist.destroy_process_group()
     if halo_timed_out:
         raise SystemExit("rank %d: a halo exchange timed out waiting for a neighbour" % rank)
+    if parity and parity["mismatches"]:
+        raise SystemExit("rank %d: PARITY FAILURE — %d of %d chunks differ from the oracle (per rank: %s)" %
+                         (rank, parity["mismatches"], parity["chunks"], parity["mismatches_per_rank"]))
+    return line
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size != args.gpus and world_size > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world_size))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the mesher has no CPU path")
+    torch.cuda.set_device(local_rank)
+    pin_to_local_cpus(local_rank, world_size)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # N = 1: BASELINE config 2 (4096 forest chunks).  N > 1: BASELINE config 5 (65 536 forest chunks, one world split into
+    # z-slabs: strong scaling) with the weak-scaling run (4096 chunks per rank) as a second leg of the same line.
+    workload = args.workload or ("forest4096" if world_size == 1 else "forest65536")
+    line = measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs=True)
+    if world_size > 1 and not args.workload and not args.no_weak_leg:
+        weak = measure(args, "forest4096", torch, dist, world_size, rank, local_rank, full_legs=False)
+        if rank == 0:
+            line["weak_scaling_leg"] = {k: weak[k] for k in ("value", "unit", "ms_per_step", "scaling", "config", "quads_per_s", "parity", "roofline", "gpu_launches", "between_kernels_us")}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -14,34 +14,6 @@ namespace gc
 {
 namespace
 {
-__device__ __forceinline__ void store_release_sys(uint32_t* p, uint32_t v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t load_acquire_sys(const uint32_t* p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long now_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// a wait that gives up records which one it was: HF_ERROR = (serial << 8) | (flag word + 1), first failure only
-__device__ bool wait_at_least(uint32_t* flags, int word, uint32_t serial, unsigned long long limit_ns)
-{
-    const unsigned long long t0 = now_ns();
-    while ((int32_t)(load_acquire_sys(flags + word) - serial) < 0)
-    {
-        if (now_ns() - t0 > limit_ns) { atomicCAS(flags + HF_ERROR, 0u, (serial << 8) | (uint32_t)(word + 1)); return false; }
-        __nanosleep(200);
-    }
-    return true;
-}
-
 // One kernel per exchange.  No CTA waits for another CTA of the grid — only for flags the neighbours write — so the grid
 // needs no co-residency: CTA 0 tells the neighbours this rank has entered the exchange, every CTA waits until both
 // neighbours have said the same, copies its share, and leaves once the neighbours' planes have arrived here.
@@ -49,9 +21,13 @@ __global__ void __launch_bounds__(256) gc_halo_exchange_kernel(HaloPushArgs a)
 {
     // ---- ready: I am the upper neighbour of the rank below me, the lower neighbour of the rank above ----
     if (blockIdx.x == 0 && threadIdx.x < 2 && a.peer[threadIdx.x].connected)
-        store_release_sys(a.peer[threadIdx.x].flags + (threadIdx.x == 0 ? HF_READY_FROM_UP : HF_READY_FROM_DOWN), a.serial);
-    if (threadIdx.x < 2 && a.peer[threadIdx.x].connected)
-        wait_at_least(a.flags, threadIdx.x == 0 ? HF_READY_FROM_DOWN : HF_READY_FROM_UP, a.serial, a.wait_ns);
+        halo_store_release_sys(a.peer[threadIdx.x].flags + (threadIdx.x == 0 ? HF_READY_FROM_UP : HF_READY_FROM_DOWN), a.serial);
+    // a neighbour that does not enter the exchange in time is left alone: nothing is stored into its halo rows (its mesh
+    // kernel may still be reading them), no arrival is published to it, and the failure is recorded in both flag blocks
+    __shared__ int ready[2];
+    if (threadIdx.x < 2)
+        ready[threadIdx.x] = a.peer[threadIdx.x].connected &&
+                             halo_wait_at_least(a.flags, threadIdx.x == 0 ? HF_READY_FROM_DOWN : HF_READY_FROM_UP, a.serial, a.wait_ns, a.peer[threadIdx.x].flags);
     __syncthreads();
 
     // ---- copy ----
@@ -61,7 +37,7 @@ __global__ void __launch_bounds__(256) gc_halo_exchange_kernel(HaloPushArgs a)
     for (int d = 0; d < 2; d++)
     {
         const HaloPeer& p = a.peer[d];
-        if (!p.connected) continue;
+        if (!ready[d]) continue;
         const int z = d == 0 ? 0 : 31;
         const int src_row = a.send_row[d];
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
@@ -87,16 +63,16 @@ __global__ void __launch_bounds__(256) gc_halo_exchange_kernel(HaloPushArgs a)
     __shared__ bool last;
     if (threadIdx.x == 0) last = atomicAdd(a.flags + HF_TICKET, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (last && threadIdx.x < 2 && a.peer[threadIdx.x].connected)
+    if (last && threadIdx.x < 2 && ready[threadIdx.x])
     {
         __threadfence_system();
-        store_release_sys(a.peer[threadIdx.x].flags + (threadIdx.x == 0 ? HF_ARRIVED_FROM_UP : HF_ARRIVED_FROM_DOWN), a.serial);
+        halo_store_release_sys(a.peer[threadIdx.x].flags + (threadIdx.x == 0 ? HF_ARRIVED_FROM_UP : HF_ARRIVED_FROM_DOWN), a.serial);
     }
     if (last && threadIdx.x == 0) a.flags[HF_TICKET] = 0;
 
     // ---- wait: the kernel (and with it the stream) goes on once both neighbours' planes are here ----
-    if (threadIdx.x < 2 && a.peer[threadIdx.x].connected)
-        wait_at_least(a.flags, threadIdx.x == 0 ? HF_ARRIVED_FROM_DOWN : HF_ARRIVED_FROM_UP, a.serial, a.wait_ns);
+    if (threadIdx.x < 2 && ready[threadIdx.x])
+        halo_wait_at_least(a.flags, threadIdx.x == 0 ? HF_ARRIVED_FROM_DOWN : HF_ARRIVED_FROM_UP, a.serial, a.wait_ns);
 }
 }  // namespace
 

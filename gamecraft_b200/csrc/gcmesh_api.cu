@@ -116,6 +116,8 @@ struct GcWorld
     uint32_t* h_items;        // pinned: work list of the upload kernel
     uint32_t* d_items;
     int launches;             // kernels launched by the last upload call
+    unsigned long long upload_bytes;   // host -> device bytes the last sparse upload / gcmesh_mesh_host call moved
+    bool surface_bounds_blocks;        // GC_WORLD_SURFACE_BOUNDS_BLOCKS
     // light fill scratch (grown on demand)
     uint32_t* d_light_counters;   // 8 x u32
     uint32_t* h_light_counters;   // pinned
@@ -159,8 +161,8 @@ struct GcBatch
     GcChunkOut* d_out;
     uint8_t* d_vertices;
     uint16_t* d_indices;
-    unsigned long long* d_cursor;   // [0] quad cursor
-    int32_t* d_counters;            // [0] work counter, [1] error flag
+    unsigned long long* d_cursor;   // control block, 32 bytes: [0] quad cursor | work counter, error flag | CTAs done, pad | [3] quads of the last launch
+    int32_t* d_counters;            // [0] work counter, [1] error flag (1: mbarrier watchdog, 2: a halo plane never arrived)
     unsigned long long* d_prof;     // 16 cycle counters when GCMESH_PROFILE=1
     unsigned long long h_prof[512];
     GcChunkOut* h_out;              // pinned
@@ -170,7 +172,10 @@ struct GcBatch
     int n;
     int state;                      // 0 idle, 1 submitted, 2 waited
     int launches;
-    cudaEvent_t ev_start, ev_stop, ev_done, ev_coords;
+    cudaEvent_t ev_start, ev_stop, ev_done, ev_coords, ev_kernel;
+    bool timing;                    // record ev_start / ev_stop around the kernel (gcmesh_batch_set_timing)
+    bool timed;                     // ... and the last submission did
+    int order_rows[2];              // gcmesh_submit_exchange: the boundary rows the order was built for (-1: plain submission)
     // work order: chunks are claimed heaviest first so that the kernel's tail is made of cheap ones
     int32_t* d_order;
     int32_t* h_order;               // pinned
@@ -534,6 +539,14 @@ __attribute__((target("avx2"))) static bool all_zero_avx2(const void* p, size_t 
     return true;
 }
 
+static inline bool all_zero_small(const void* p, size_t bytes)   // a multiple of 8
+{
+    const uint64_t* q = (const uint64_t*)p;
+    uint64_t acc = 0;
+    for (size_t i = 0; i < bytes / 8; i++) acc |= q[i];
+    return acc == 0;
+}
+
 static bool all_zero(const void* p, size_t bytes)
 {
     static bool (*const impl)(const void*, size_t) = __builtin_cpu_supports("avx2") ? all_zero_avx2 : all_zero_scalar;
@@ -559,9 +572,24 @@ static inline bool sun_brick_never_read(const uint8_t* surface, size_t slot)
 // holds no block at all: light is only ever read for a quad, within one voxel of the block the quad belongs to
 // (VertexLight, WorldRender.cpp:329-383), so no chunk that gets meshed can reach such a brick's light.  In a terrain
 // world that is most of the sky.  (Like the sunlight rule above this leaves the device copy of such an array as it was.)
-static inline void scan_blocks(GcWorld* w, size_t slot, const uint16_t* blocks)
+// With GC_WORLD_SURFACE_BOUNDS_BLOCKS the caller vouches that `surface` is ComputeSurface of the blocks (Lighting.cpp:5-26:
+// highest non-AIR y in 0..254, plus one — what ChunkGroup::surface holds for every pre-processed column; ComputeSurfaceAt
+// keeps it so on edits, a stale entry is only ever too high).  A brick lying wholly at or above its column's highest entry
+// is then AIR by definition and is not read — except layer y = 255, which ComputeSurface never looks at: the top brick's
+// last layer (32 rows of 64 bytes) is still checked.  In a terrain world that is three quarters of the block ids.
+static inline void scan_blocks(GcWorld* w, size_t slot, const uint16_t* blocks, const uint8_t* surface)
 {
-    w->block_flags[slot] = all_zero(blocks + slot * GC_CHUNK_SIZE_3, (size_t)GC_CHUNK_SIZE_3 * 2) ? 0 : 1;
+    const uint16_t* b = blocks + slot * GC_CHUNK_SIZE_3;
+    if (w->surface_bounds_blocks && sun_brick_never_read(surface, slot))
+    {
+        uint8_t any = 0;
+        if ((slot & 3) == GC_WORLD_CHUNK_HEIGHT - 1)
+            for (int z = 0; z < GC_CHUNK_SIZE_H && !any; z++)
+                any = all_zero_small(b + 32 * (63 + 64 * z), 64) ? 0 : 1;
+        w->block_flags[slot] = any;
+        return;
+    }
+    w->block_flags[slot] = all_zero(b, (size_t)GC_CHUNK_SIZE_3 * 2) ? 0 : 1;
 }
 
 static inline bool brick_neighbourhood_is_air(const GcWorld* w, size_t slot)
@@ -631,7 +659,7 @@ struct ScanPlan
                 const size_t slot = (size_t)row * slots_per_row + in_row;
                 if (!stage_b)
                 {
-                    scan_blocks(w, slot, blocks);
+                    scan_blocks(w, slot, blocks, surface);
                     a_remaining[(size_t)row].fetch_sub(1, std::memory_order_release);
                 }
                 else
@@ -673,6 +701,7 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
             uint8_t* dst = a == 0 ? (uint8_t*)w->d_blocks + slot * bytes : (a == 1 ? w->d_sun : w->d_light) + slot * bytes;
             if (f & (1 << a))
             {
+                w->upload_bytes += bytes;
                 if (mapped) items[n_items++] = (uint32_t)(slot * 4 + a);
                 else
                 {
@@ -686,6 +715,7 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
     }
     if (n_items)
     {
+        w->upload_bytes += sizeof(uint32_t) * (size_t)n_items;
         if (cudaMemcpyAsync(w->d_items + s_begin * 3, items, sizeof(uint32_t) * (size_t)n_items, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
         if (launch_upload_items(w->d_items + s_begin * 3, n_items, blocks, sunlight, block_light, w->d_blocks, w->d_sun, w->d_light, s) != cudaSuccess) return -1;
         return 1;
@@ -729,6 +759,7 @@ int gcmesh_world_upload_sparse(GcWorld* w, const uint16_t* blocks, const uint8_t
     if (!w || !blocks || !sunlight || !block_light) return fail(GC_ERR_ARG, "null argument");
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
+    w->upload_bytes = surface ? w->n_cols * GC_CHUNK_SIZE_2 : 0;
     const int k = upload_rows_sparse(w, 0, w->size_z, blocks, sunlight, block_light, surface, nonzero_hint, threads,
                                      host_arrays_mapped(blocks, sunlight, block_light), ctx->stream);
     if (k < 0) return fail(GC_ERR_CUDA, "sparse upload", cudaGetErrorString(cudaGetLastError()));
@@ -737,7 +768,15 @@ int gcmesh_world_upload_sparse(GcWorld* w, const uint16_t* blocks, const uint8_t
     return GC_OK;
 }
 
+int gcmesh_world_set_option(GcWorld* w, int option, int value)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    if (option == GC_WORLD_SURFACE_BOUNDS_BLOCKS) { w->surface_bounds_blocks = value != 0; return GC_OK; }
+    return fail(GC_ERR_ARG, "unknown world option");
+}
+
 int gcmesh_world_upload_launches(const GcWorld* w) { return w ? w->launches : 0; }
+unsigned long long gcmesh_world_upload_bytes(const GcWorld* w) { return w ? w->upload_bytes : 0; }
 
 int gcmesh_world_device_ptrs(GcWorld* w, void** blocks, void** sunlight, void** block_light, void** surface)
 {
@@ -1035,6 +1074,9 @@ int gcmesh_world_halo_connect_local(GcWorld* w, int side, GcWorld* peer, int pee
 {
     if (!w || !peer) return fail(GC_ERR_ARG, "null argument");
     if (peer->size_x != w->size_x || peer->size_z != w->size_z) return fail(GC_ERR_ARG, "neighbour windows must have one size");
+    // each side's exchange waits for the other's: on one stream the second could never start (it would only time out)
+    if (peer == w || peer->ctx == w->ctx || peer->ctx->stream == w->ctx->stream)
+        return fail(GC_ERR_ARG, "neighbour worlds need contexts (streams) of their own");
     if (halo_side_ok(w, side, peer_row) != GC_OK) return GC_ERR_ARG;
     if (halo_flags(w) != GC_OK || halo_flags(peer) != GC_OK) return GC_ERR_CUDA;
     if (peer->ctx->device != w->ctx->device)
@@ -1051,6 +1093,17 @@ int gcmesh_world_halo_connect_local(GcWorld* w, int side, GcWorld* peer, int pee
     return GC_OK;
 }
 
+static unsigned long long halo_wait_ns()
+{
+    static const unsigned long long wait_ms = []() -> unsigned long long
+    {
+        const char* env = getenv("GCMESH_HALO_WAIT_MS");
+        const long v = env ? atol(env) : 0;
+        return v > 0 ? (unsigned long long)v : 10000ull;
+    }();
+    return wait_ms * 1000000ull;
+}
+
 int gcmesh_world_halo_push(GcWorld* w, int send_row_down, int send_row_up)
 {
     if (!w) return fail(GC_ERR_ARG, "world is null");
@@ -1064,13 +1117,7 @@ int gcmesh_world_halo_push(GcWorld* w, int send_row_down, int send_row_up)
     a.size_x = w->size_x; a.send_row[0] = send_row_down; a.send_row[1] = send_row_up;
     a.peer[0] = w->halo_peer[0]; a.peer[1] = w->halo_peer[1];
     a.serial = ++w->halo_serial;
-    static const unsigned long long wait_ms = []() -> unsigned long long
-    {
-        const char* env = getenv("GCMESH_HALO_WAIT_MS");
-        const long v = env ? atol(env) : 0;
-        return v > 0 ? (unsigned long long)v : 10000ull;
-    }();
-    a.wait_ns = wait_ms * 1000000ull;
+    a.wait_ns = halo_wait_ns();
     GC_CUDA(launch_halo_push(a, ctx->num_sms, ctx->stream));
     // the neighbours' planes land in this window's halo rows: the sparse-upload bookkeeping no longer knows them
     for (int d = 0; d < 2; d++)
@@ -1338,8 +1385,10 @@ int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBa
     if (e == cudaSuccess) e = cudaMalloc(&b->d_out, sizeof(GcChunkOut) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_vertices, (size_t)max_quads * 48);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_indices, (size_t)max_quads * 12);
-    // one 16-byte control block {quad cursor, work counter, error flag}: one memset and one read-back per submission
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_cursor, 16);
+    // one 32-byte control block {quad cursor | work counter, error flag | CTAs done, pad | quads of the last launch}: cleared
+    // here once — the last CTA of every launch leaves it ready for the next one — and read back once per submission
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_cursor, 32);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_cursor, 0, 32, ctx->stream);
     if (e == cudaSuccess) b->d_counters = reinterpret_cast<int32_t*>(b->d_cursor + 1);
     if (e == cudaSuccess && getenv("GCMESH_PROFILE")) e = cudaMalloc(&b->d_prof, sizeof(unsigned long long) * 512);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_out, sizeof(GcChunkOut) * (size_t)max_chunks);
@@ -1347,13 +1396,16 @@ int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBa
     if (e == cudaSuccess) e = cudaMalloc(&b->d_order, sizeof(int32_t) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_order, sizeof(int32_t) * (size_t)max_chunks);
     if (e == cudaSuccess) { b->order_coords = (GcChunkCoord*)malloc(sizeof(GcChunkCoord) * (size_t)max_chunks); if (!b->order_coords) e = cudaErrorMemoryAllocation; }
-    if (e == cudaSuccess) e = cudaMallocHost(&b->h_cursor, 16);
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_cursor, 32);
     if (e == cudaSuccess) b->h_counters = reinterpret_cast<int32_t*>(b->h_cursor + 1);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_start);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_stop);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_coords, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_kernel, cudaEventDisableTiming);
     if (e != cudaSuccess) { gcmesh_batch_destroy(b); return fail(GC_ERR_CUDA, "batch allocation", cudaGetErrorString(e)); }
+    b->order_rows[0] = b->order_rows[1] = -1;
+    b->timing = true;
     *out = b;
     return GC_OK;
 }
@@ -1373,6 +1425,7 @@ int gcmesh_batch_destroy(GcBatch* b)
     if (b->ev_stop) cudaEventDestroy(b->ev_stop);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
     if (b->ev_coords) cudaEventDestroy(b->ev_coords);
+    if (b->ev_kernel) cudaEventDestroy(b->ev_kernel);
     delete b;
     return GC_OK;
 }
@@ -1389,12 +1442,14 @@ static int validate_coords(const GcWorld* w, const GcChunkCoord* coords, int n)
     return GC_OK;
 }
 
-// Launch the mesh kernel over d_coords[first, first + count) on stream s; descriptors go to d_out[first ...].
-static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cudaStream_t s, bool reset_work_counter = true, const int32_t* order = nullptr)
+// Launch the mesh kernel over d_coords[first, first + count) on stream s; descriptors go to d_out[first ...].  The last CTA of
+// a launch resets the work counter and (unless keep_cursor) the quad cursor, and leaves the cursor's value in word 3 of the
+// control block: no memset between launches.
+static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cudaStream_t s, bool keep_cursor = false, const int32_t* order = nullptr,
+                                const HaloFused* halo = nullptr)
 {
     GcContext* ctx = w->ctx;
-    cudaError_t e = reset_work_counter ? cudaMemsetAsync(b->d_counters, 0, sizeof(int32_t), s) : cudaSuccess;   // (the error flag persists)
-    if (e != cudaSuccess || count <= 0) return e;
+    if (count <= 0) return cudaSuccess;
     MeshParams p;
     p.blocks = w->d_blocks; p.sun = w->d_sun; p.light = w->d_light; p.surface = w->d_surface;
     p.size_x = w->size_x; p.size_z = w->size_z;
@@ -1402,14 +1457,24 @@ static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cu
     p.vertex_arena = b->d_vertices; p.index_arena = b->d_indices; p.max_quads = b->max_quads;
     p.quad_cursor = b->d_cursor; p.work_counter = b->d_counters; p.tables = ctx->d_tables;
     p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma; p.prof = b->d_prof;
+    p.done_counter = reinterpret_cast<uint32_t*>(b->d_cursor + 2); p.total_out = b->d_cursor + 3; p.keep_cursor = keep_cursor ? 1 : 0;
     p.vert_table = w->d_vert_table;
-    const int grid = count < ctx->mesh_ctas ? count : ctx->mesh_ctas;
-    e = launch_mesh(p, w->maps, grid, s);
+    p.n_push = 0;
+    memset(&p.halo, 0, sizeof(p.halo));
+    if (halo && halo->enabled)
+    {
+        p.halo = *halo;
+        p.n_push = halo->tasks_per_dir * ((halo->peer[0].connected ? 1 : 0) + (halo->peer[1].connected ? 1 : 0));
+    }
+    const int items = count + p.n_push;
+    const int grid = items < ctx->mesh_ctas ? items : ctx->mesh_ctas;
+    cudaError_t e = launch_mesh(p, w->maps, grid, s);
     if (e == cudaSuccess) b->launches++;
     return e;
 }
 
-int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
+// gcmesh_submit / gcmesh_submit_exchange.  rows: null, or {send_row_down, send_row_up} for the fused halo exchange.
+static int submit_impl(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n, const int* rows)
 {
     if (!w || !b || (!coords && n > 0)) return fail(GC_ERR_ARG, "null argument");
     if (w->ctx != b->ctx) return fail(GC_ERR_ARG, "world and batch belong to different contexts");
@@ -1418,30 +1483,52 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
     if (validate_coords(w, coords, n) != GC_OK) return GC_ERR_ARG;
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
+    HaloFused halo;
+    memset(&halo, 0, sizeof(halo));
+    if (rows)
+    {
+        if (!w->halo_peer[0].connected && !w->halo_peer[1].connected) return fail(GC_ERR_ARG, "no neighbour connected");
+        if ((w->halo_peer[0].connected && (rows[0] < 1 || rows[0] >= w->size_z - 1)) || (w->halo_peer[1].connected && (rows[1] < 1 || rows[1] >= w->size_z - 1)))
+            return fail(GC_ERR_ARG, "send row outside the meshable rows of the window");
+        if (n == 0) return fail(GC_ERR_ARG, "an exchange needs at least one chunk to mesh (every rank of a chain launches one kernel per exchange)");
+        static const int tasks_env = getenv("GCMESH_HALO_TASKS") ? atoi(getenv("GCMESH_HALO_TASKS")) : 0;
+        halo.enabled = 1;
+        halo.tasks_per_dir = tasks_env > 0 ? tasks_env : 16;
+        if (halo.tasks_per_dir > w->size_x * 4) halo.tasks_per_dir = w->size_x * 4;
+        halo.blocks = w->d_blocks; halo.sun = w->d_sun; halo.light = w->d_light; halo.surface = w->d_surface; halo.size_x = w->size_x;
+        halo.send_row[0] = rows[0]; halo.send_row[1] = rows[1];
+        halo.peer[0] = w->halo_peer[0]; halo.peer[1] = w->halo_peer[1];
+        halo.flags = w->d_halo_flags;
+        halo.wait_ns = halo_wait_ns();
+    }
     // the pinned coordinate staging buffer is reused: wait until the previous submission has consumed it (its kernel
     // may still be queued or running, so back-to-back submissions keep the GPU busy)
     if (b->state == 1) GC_CUDA(cudaEventSynchronize(b->ev_coords));
     // Work order (longest first): a chunk with thousands of quads costs several times an air chunk, and the chunks claimed
     // last decide when the kernel ends.  With the quad counts of a finished submission of the same list the order is by
-    // those; otherwise lower chunks first (terrain sits at the bottom of the world, the sky above it is air).
-    const bool same_list = n == b->order_n && n > 0 && memcmp(coords, b->order_coords, sizeof(GcChunkCoord) * (size_t)n) == 0;
+    // those; otherwise lower chunks first (terrain sits at the bottom of the world, the sky above it is air).  With a fused
+    // exchange the chunks of the boundary rows come after all others (by then the neighbours' planes have long arrived).
+    const int r0 = rows && w->halo_peer[0].connected ? rows[0] : -1, r1 = rows && w->halo_peer[1].connected ? rows[1] : -1;
+    const bool same_list = n == b->order_n && n > 0 && r0 == b->order_rows[0] && r1 == b->order_rows[1] &&
+                           memcmp(coords, b->order_coords, sizeof(GcChunkCoord) * (size_t)n) == 0;
     const bool order_reused = same_list && (b->order_from_history || b->state != 2);
     if (!order_reused)
     {
         constexpr int kBuckets = 24;
         const bool history = same_list && b->state == 2;
-        int start[kBuckets + 1] = { 0 };
+        int start[2 * kBuckets + 1] = { 0 };
         auto bucket = [&](int i) -> int
         {
-            if (!history) return kBuckets - 1 - (coords[i].cy < 4 ? coords[i].cy : 3);       // cy 0 first
+            const int interior = (coords[i].cz == r0 || coords[i].cz == r1) ? 0 : kBuckets;
+            if (!history) return interior + kBuckets - 1 - (coords[i].cy < 4 ? coords[i].cy : 3);       // cy 0 first
             const uint32_t q = b->h_out[i].quads;
-            return q == 0 ? 0 : 1 + (q >= 11264 ? 22 : (int)(q >> 9));                       // 512-quad classes, heaviest last
+            return interior + (q == 0 ? 0 : 1 + (q >= 11264 ? 22 : (int)(q >> 9)));                    // 512-quad classes, heaviest last
         };
         for (int i = 0; i < n; i++) start[bucket(i) + 1]++;
-        for (int k = 0; k < kBuckets; k++) start[k + 1] += start[k];
+        for (int k = 0; k < 2 * kBuckets; k++) start[k + 1] += start[k];
         for (int i = 0; i < n; i++) b->h_order[n - 1 - start[bucket(i)]++] = i;             // descending bucket
         memcpy(b->order_coords, coords, sizeof(GcChunkCoord) * (size_t)n);
-        b->order_n = n; b->order_from_history = history;
+        b->order_n = n; b->order_from_history = history; b->order_rows[0] = r0; b->order_rows[1] = r1;
     }
     b->n = n;
     b->launches = 0;
@@ -1450,20 +1537,48 @@ int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n)
     // (a list identical to the previous submission's is already on the device)
     if (!same_list) GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, s));
     if (!order_reused) GC_CUDA(cudaMemcpyAsync(b->d_order, b->h_order, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
-    GC_CUDA(cudaEventRecord(b->ev_coords, s));
-    GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, 16, s));
+    if (!same_list || !order_reused) GC_CUDA(cudaEventRecord(b->ev_coords, s));
+    if (n == 0) GC_CUDA(cudaMemsetAsync(b->d_cursor + 3, 0, sizeof(unsigned long long), s));
     if (b->d_prof) GC_CUDA(cudaMemsetAsync(b->d_prof, 0, sizeof(unsigned long long) * 512, s));
-    GC_CUDA(cudaEventRecord(b->ev_start, s));
-    GC_CUDA(launch_range(w, b, 0, n, s, false, b->d_order));
-    GC_CUDA(cudaEventRecord(b->ev_stop, s));
+    b->timed = b->timing;
+    if (b->timing) GC_CUDA(cudaEventRecord(b->ev_start, s));
+    if (halo.enabled)
+    {
+        halo.serial = ++w->halo_serial;
+        // the neighbours' planes land in this window's halo rows: the sparse-upload bookkeeping no longer knows them
+        for (int d = 0; d < 2; d++)
+            if (w->halo_peer[d].connected)
+            {
+                const int row = d == 0 ? rows[0] - 1 : rows[1] + 1;
+                memset(w->slot_dirty + (size_t)row * w->size_x * GC_WORLD_CHUNK_HEIGHT, 7, (size_t)w->size_x * GC_WORLD_CHUNK_HEIGHT);
+            }
+    }
+    GC_CUDA(launch_range(w, b, 0, n, s, false, b->d_order, &halo));
+    if (b->timing) GC_CUDA(cudaEventRecord(b->ev_stop, s));
+    GC_CUDA(cudaEventRecord(b->ev_kernel, s));
     // the descriptors travel back on the download stream: the context stream is free for the next submission's kernel
     cudaStream_t sd = ctx->download_stream;
-    GC_CUDA(cudaStreamWaitEvent(sd, b->ev_stop, 0));
+    GC_CUDA(cudaStreamWaitEvent(sd, b->ev_kernel, 0));
     GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, sd));
-    GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, 16, cudaMemcpyDeviceToHost, sd));
+    GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, 32, cudaMemcpyDeviceToHost, sd));
     if (b->d_prof) GC_CUDA(cudaMemcpyAsync(b->h_prof, b->d_prof, sizeof(unsigned long long) * 512, cudaMemcpyDeviceToHost, sd));
     GC_CUDA(cudaEventRecord(b->ev_done, sd));
     b->state = 1;
+    return GC_OK;
+}
+
+int gcmesh_submit(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n) { return submit_impl(w, b, coords, n, nullptr); }
+
+int gcmesh_submit_exchange(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n, int send_row_down, int send_row_up)
+{
+    const int rows[2] = { send_row_down, send_row_up };
+    return submit_impl(w, b, coords, n, rows);
+}
+
+int gcmesh_batch_set_timing(GcBatch* b, int on)
+{
+    if (!b) return fail(GC_ERR_ARG, "batch is null");
+    b->timing = on != 0;
     return GC_OK;
 }
 
@@ -1504,14 +1619,21 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     cudaStream_t sm = ctx->stream, su = ctx->upload_stream, sd = ctx->download_stream;
     const bool mapped = host_arrays_mapped(blocks, sunlight, block_light);
     b->n = n; b->launches = 0; w->launches = 0;
+    w->upload_bytes = w->n_cols * GC_CHUNK_SIZE_2 + sizeof(GcChunkCoord) * (size_t)n;
     b->order_n = 0;                                           // d_coords is about to hold the strip-sorted list
     GC_CUDA(cudaEventRecord(ctx->ev_fork, sm));
     GC_CUDA(cudaStreamWaitEvent(su, ctx->ev_fork, 0));        // the upload overwrites what earlier work on the context stream read
     GC_CUDA(cudaStreamWaitEvent(sd, ctx->ev_fork, 0));
     GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, su));
     GC_CUDA(cudaMemcpyAsync(w->d_surface, surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyHostToDevice, su));
-    GC_CUDA(cudaMemsetAsync(b->d_cursor, 0, 16, su));
+    // (the quad cursor and the work counter are zero: the last CTA of every launch leaves them so; the strips of this call keep
+    // the cursor running and the last one resets it)
+    GC_CUDA(cudaMemsetAsync(b->d_cursor + 3, 0, sizeof(unsigned long long), su));
     GC_CUDA(cudaEventRecord(b->ev_start, sm));
+    b->timed = true;
+    int last_nonempty = -1;
+    for (int j = 0; j < n_strips; j++)
+        if (first[j + 1] > first[j]) last_nonempty = j;
 
     unsigned long long* cursors = ctx->h_strip_cursor;        // pinned: arena cursor after each strip's kernel
     uint64_t copied = 0;
@@ -1532,8 +1654,8 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     {
         const int up = j + 1 < n_strips ? j + 1 : n_strips - 1;
         GC_CUDA(cudaStreamWaitEvent(sm, ctx->ev_uploaded[up], 0));
-        GC_CUDA(launch_range(w, b, first[j], first[j + 1] - first[j], sm));
-        GC_CUDA(cudaMemcpyAsync(&cursors[j], b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm));
+        GC_CUDA(launch_range(w, b, first[j], first[j + 1] - first[j], sm, j != last_nonempty));
+        GC_CUDA(cudaMemcpyAsync(&cursors[j], b->d_cursor + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm));
         GC_CUDA(cudaEventRecord(ctx->ev_meshed[j], sm));
         return GC_OK;
     };
@@ -1583,7 +1705,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     { const int st = mesh_strip(n_strips - 1); if (st != GC_OK) return st; }
     GC_CUDA(cudaEventRecord(b->ev_stop, sm));
     GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, sm));
-    GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, 16, cudaMemcpyDeviceToHost, sm));
+    GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, 32, cudaMemcpyDeviceToHost, sm));
     if (n_strips >= 2) { const int st = read_back(n_strips - 2); if (st != GC_OK) return st; }
     { const int st = read_back(n_strips - 1); if (st != GC_OK) return st; }
     GC_CUDA(cudaEventRecord(ctx->ev_join, sd));
@@ -1619,6 +1741,7 @@ int gcmesh_wait(GcBatch* b)
     GC_CUDA(cudaSetDevice(b->ctx->device));
     GC_CUDA(cudaEventSynchronize(b->ev_done));
     b->state = 2;
+    if (b->h_counters[1] == 2) return fail(GC_ERR_CUDA, "halo exchange: a neighbour's boundary plane never arrived (chunks flagged GC_CHUNK_HALO_MISSING)");
     if (b->h_counters[1] != 0) return fail(GC_ERR_CUDA, "mesh kernel watchdog fired (mbarrier wait did not complete)");
     return GC_OK;
 }
@@ -1629,7 +1752,7 @@ int gcmesh_batch_results(GcBatch* b, const GcChunkOut** out, int* n, uint64_t* t
     if (b->state != 2) return fail(GC_ERR_STATE, "call gcmesh_wait first");
     if (out) *out = b->h_out;
     if (n) *n = b->n;
-    if (total_quads) *total_quads = *b->h_cursor < b->max_quads ? *b->h_cursor : b->max_quads;
+    if (total_quads) *total_quads = b->h_cursor[3] < b->max_quads ? b->h_cursor[3] : b->max_quads;
     return GC_OK;
 }
 
@@ -1638,7 +1761,7 @@ int gcmesh_batch_download(GcBatch* b, void* vertices, void* indices)
     if (!b) return fail(GC_ERR_ARG, "batch is null");
     if (b->state != 2) return fail(GC_ERR_STATE, "call gcmesh_wait first");
     GC_CUDA(cudaSetDevice(b->ctx->device));
-    const uint64_t q = *b->h_cursor < b->max_quads ? *b->h_cursor : b->max_quads;
+    const uint64_t q = b->h_cursor[3] < b->max_quads ? b->h_cursor[3] : b->max_quads;
     if (q == 0) return GC_OK;
     if (vertices) GC_CUDA(cudaMemcpyAsync(vertices, b->d_vertices, (size_t)q * 48, cudaMemcpyDeviceToHost, b->ctx->stream));
     if (indices) GC_CUDA(cudaMemcpyAsync(indices, b->d_indices, (size_t)q * 12, cudaMemcpyDeviceToHost, b->ctx->stream));
@@ -1713,6 +1836,7 @@ int gcmesh_batch_elapsed_ms(GcBatch* b, float* ms)
 {
     if (!b || !ms) return fail(GC_ERR_ARG, "null argument");
     if (b->state != 2) return fail(GC_ERR_STATE, "call gcmesh_wait first");
+    if (!b->timed) return fail(GC_ERR_STATE, "the last submission was not timed (gcmesh_batch_set_timing)");
     GC_CUDA(cudaEventElapsedTime(ms, b->ev_start, b->ev_stop));
     return GC_OK;
 }

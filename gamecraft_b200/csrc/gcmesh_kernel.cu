@@ -1,7 +1,7 @@
 // gcmesh — the chunk-mesh kernel for sm_100a (B200).
 //
-// Two persistent CTAs per SM (320 threads, ~112 KB shared memory each); each CTA pulls chunks from a work counter and,
-// per chunk:
+// Two persistent CTAs per SM (448 threads = 14 warps, ~111 KB shared memory each); each CTA pulls chunks from a work counter
+// and, per chunk:
 //   P0  the next chunk's position and the surface rows of its three columns (one warp, a chunk ahead)
 //   P1  the 34 z-slabs of BLOCK IDS (32x64 voxels, 4 KB, contiguous in the brick) are staged by TMA tensor-map box
 //       loads (cp.async.bulk.tensor.4d) into warp-owned mbarrier slots and converted, two voxel rows per lane, into
@@ -25,7 +25,7 @@ namespace gc
 {
 namespace
 {
-constexpr int NT = kMeshThreads;          // 10 warps
+constexpr int NT = kMeshThreads;          // 448 threads = 14 warps
 constexpr int kWarps = NT / 32;
 constexpr int kSlabs = kRowsZ;            // 34 z-slabs per chunk: tz = -1 .. 32
 // P1: eight slab warps, each with its own ring slot and mbarrier.  Warp w converts slabs w, w + 8, ...: it waits for its
@@ -38,7 +38,7 @@ constexpr int kSlabWarps = 8;                              // warps 0 .. 7
 constexpr int kSlabsPerWarp = kTZ / kSlabWarps;            // the 32 centre slabs; the two z-halo slabs go to the fetch warp
 constexpr int kStages = kSlabWarps;                        // one slot per slab warp
 constexpr int kHaloWarp = kSlabWarps;                      // warp 8: the y-halo rows (ty = -1, 64), straight from global memory
-constexpr int kFetchWarp = kHaloWarp + 1;                  // warp 9: prefetches the next chunk's id, position and surface rows
+constexpr int kFetchWarp = kHaloWarp + 1;                  // warp 9: claims the next work item and reads the two z-halo slabs (warps 10 .. 13 join in from P1x on)
 static_assert(kFetchWarp < kWarps, "warp roles");
 constexpr int kYHaloTasks = 2 * kRowsZ;                    // 2 faces x 34 rows
 
@@ -77,7 +77,8 @@ static_assert(2 * (kSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM");
 
 static_assert(sizeof(FacePlan) == 48, "FacePlan");
 
-struct NextChunk { int32_t chunk, cx, cy, cz; };   // chunk = index into coords, or -1 when the work is exhausted
+struct NextChunk { int32_t chunk, cx, cy, cz; };   // chunk = index into coords, -1 when the work is exhausted, kPushItem: halo push task cx
+constexpr int kPushItem = -2;
 
 struct ChunkCtx
 {
@@ -89,7 +90,9 @@ struct ChunkCtx
     uint32_t type_off[kMeshTypes];
     uint8_t slab_cls[kSlabs + 2];   // per z-slab: 0xFF = its plane rows are written; else the class byte of the one non-emitting block
                                     // (air, as a rule) that fills it — such rows are only written if the chunk turns out to need them
+    int32_t halo_ok;      // fused exchange: result of a wait for a neighbour, broadcast to the CTA
 };
+static_assert(sizeof(ChunkCtx) <= 128, "ChunkCtx outgrew its slot");
 
 // ---- PTX helpers ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,6 +178,61 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
+// ---- fused slab halo exchange: one push task ----
+// Task t of direction d (d = the t / tasks_per_dir-th connected neighbour) stores planes [part * P / T, (part + 1) * P / T) of
+// this rank's boundary row — P = size_x * 4 planes of 8 KB: blocks | sunlight | blockLight of one chunk at z = 0 (down) or
+// z = 31 (up) — and the surface rows of the same share of columns into the neighbour's halo row, with 16-byte stores over
+// NVLink.  The task that completes a direction publishes "arrived" in the neighbour's flag block behind a system-scope fence.
+__device__ void halo_push_task(const HaloFused& h, int task, int* s_flag)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int T = h.tasks_per_dir;
+    int d = task / T;
+    const int part = task % T;
+    if (!h.peer[0].connected) d = 1;                       // one neighbour only: every task is for it
+    const HaloPeer& peer = h.peer[d];
+    // the neighbour must have entered this exchange: until then its previous kernel may still read its halo rows
+    if (tid == 0) *s_flag = halo_wait_at_least(h.flags, d == 0 ? HF_READY_FROM_DOWN : HF_READY_FROM_UP, h.serial, h.wait_ns, peer.flags) ? 1 : 0;
+    __syncthreads();
+    const bool ready = *s_flag != 0;
+    __syncthreads();
+    if (!ready) return;                                    // (both flag blocks carry the error; no arrival is published)
+    const int z = d == 0 ? 0 : 31;
+    const int src_row = h.send_row[d];
+    const int planes = h.size_x * 4;
+    const int p0 = (int)((long long)planes * part / T), p1 = (int)((long long)planes * (part + 1) / T);
+    const int per_plane = 8192 / 16;                       // uint4 per plane: 256 blocks, 128 sunlight, 128 blockLight
+    for (int i = p0 * per_plane + tid; i < p1 * per_plane; i += nt)
+    {
+        const int plane = i / per_plane, q = i % per_plane;
+        const int cx = plane >> 2, cy = plane & 3;
+        const size_t src = (((size_t)src_row * h.size_x + cx) * 4 + cy) * GC_CHUNK_SIZE_3 + (size_t)z * 2048;
+        const size_t dst = (((size_t)peer.row * h.size_x + cx) * 4 + cy) * GC_CHUNK_SIZE_3 + (size_t)z * 2048;
+        if (q < 256) reinterpret_cast<uint4*>(peer.blocks + dst)[q] = reinterpret_cast<const uint4*>(h.blocks + src)[q];
+        else if (q < 384) reinterpret_cast<uint4*>(peer.sun + dst)[q - 256] = reinterpret_cast<const uint4*>(h.sun + src)[q - 256];
+        else reinterpret_cast<uint4*>(peer.light + dst)[q - 384] = reinterpret_cast<const uint4*>(h.light + src)[q - 384];
+    }
+    const int c0 = (p0 + 3) >> 2, c1 = (p1 + 3) >> 2;      // columns whose first plane lies in this share
+    for (int i = c0 * 8 + tid; i < c1 * 8; i += nt)
+    {
+        const int cx = i >> 3, q = i & 7;
+        reinterpret_cast<uint32_t*>(peer.surface + ((size_t)peer.row * h.size_x + cx) * 1024 + z * 32)[q] =
+            reinterpret_cast<const uint32_t*>(h.surface + ((size_t)src_row * h.size_x + cx) * 1024 + z * 32)[q];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0)
+    {
+        uint32_t* ticket = h.flags + (d == 0 ? HF_TICKET : HF_TICKET_UP);
+        if (atomicAdd(ticket, 1u) == (uint32_t)T - 1)
+        {
+            *ticket = 0;
+            __threadfence_system();
+            halo_store_release_sys(peer.flags + (d == 0 ? HF_ARRIVED_FROM_UP : HF_ARRIVED_FROM_DOWN), h.serial);
+        }
+    }
+}
+
 // In-kernel cycle attribution is compiled in only for the profiling instantiation (GCMESH_PROFILE=1).
 #define GC_PROF_MARK(slot)                                                            \
     do {                                                                              \
@@ -182,7 +240,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     } while (0)
 
 // =====================================================================================================
-template <bool kProf>
+template <bool kProf, bool kHalo>
 __global__ void __launch_bounds__(NT, 2)
 gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
 {
@@ -242,12 +300,23 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         if (lane == 0)
         {
             int c = atomicAdd(p.work_counter, 1), fx = 0, fy = 0, fz = 0;
-            if (c >= p.n_chunks) c = -1;
-            else if (p.order) c = p.order[c];
-            if (c >= 0) { const GcChunkCoord cc = p.coords[c]; fx = cc.cx; fy = cc.cy; fz = cc.cz; }
+            if (kHalo && c < p.n_push) { fx = c; c = kPushItem; }          // a halo push task (fused exchange): its number travels in cx
+            else
+            {
+                if (kHalo) c -= p.n_push;
+                if (c >= p.n_chunks) c = -1;
+                else if (p.order) c = p.order[c];
+                if (c >= 0) { const GcChunkCoord cc = p.coords[c]; fx = cc.cx; fy = cc.cy; fz = cc.cz; }
+            }
             s_next[b].chunk = c; s_next[b].cx = fx; s_next[b].cy = fy; s_next[b].cz = fz;
         }
     };
+
+    // fused exchange: tell both neighbours that this rank has entered exchange `serial` — its previous kernel, the last reader
+    // of its halo rows, has finished (stream order), so they may be overwritten
+    if (kHalo && blockIdx.x == 0 && tid < 2 && p.halo.peer[tid].connected)
+        halo_store_release_sys(p.halo.peer[tid].flags + (tid == 0 ? HF_READY_FROM_UP : HF_READY_FROM_DOWN), p.halo.serial);
+    uint32_t halo_seen = 0, halo_failed = 0;   // bit d: the plane from neighbour d is known to have arrived / was given up on (CTA-uniform)
 
     int buf = 0;
     if (warp == kFetchWarp) fetch_chunk(0);
@@ -259,9 +328,54 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         // ================= P0: the chunk prefetched during the previous chunk's P1 =================
         __syncthreads();
         const int chunk = s_next[buf].chunk;
-        if (chunk < 0) break;
+        if (chunk == -1) break;
+        if (kHalo && chunk == kPushItem)
+        {
+            // ---- a halo push task: a share of this rank's boundary planes goes into a neighbour's halo row over peer memory ----
+            if (warp == kFetchWarp) fetch_chunk(buf ^ 1);
+            halo_push_task(p.halo, s_next[buf].cx, &s_ctx->halo_ok);
+            continue;
+        }
         const int cx = s_next[buf].cx, cy = s_next[buf].cy, cz = s_next[buf].cz;
         const int lwy = cy * kTY;
+        if (kHalo)
+        {
+            // a chunk of the first / last owned row reads the neighbour's plane: wait (once per CTA and side) until it has arrived
+            uint32_t need = ((cz == p.halo.send_row[0] && p.halo.peer[0].connected) ? 1u : 0u) | ((cz == p.halo.send_row[1] && p.halo.peer[1].connected) ? 2u : 0u);
+            need &= ~halo_seen;
+            if (need)
+            {
+                int* s_halo_ok = &s_ctx->halo_ok;
+                if (tid == 0)
+                {
+                    bool ok = (need & halo_failed) == 0;   // (a plane this CTA already gave up on is not waited for again)
+                    if (ok && (need & 1u)) ok = halo_wait_at_least(p.halo.flags, HF_ARRIVED_FROM_DOWN, p.halo.serial, p.halo.wait_ns) && ok;
+                    if (ok && (need & 2u)) ok = halo_wait_at_least(p.halo.flags, HF_ARRIVED_FROM_UP, p.halo.serial, p.halo.wait_ns);
+                    // the planes were written by another GPU (generic proxy); this CTA reads them through TMA as well
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    *s_halo_ok = ok ? 1 : 0;
+                }
+                __syncthreads();
+                const bool ok = *s_halo_ok != 0;
+                __syncthreads();
+                if (!ok)
+                {
+                    // the neighbour never delivered: the chunk is flagged, nothing is emitted
+                    halo_failed |= need;
+                    if (warp == kFetchWarp) fetch_chunk(buf ^ 1);
+                    if (tid == 0)
+                    {
+                        GcChunkOut o;
+                        o.quad_base = 0; o.vert_count = 0; o.quads = 0; o.flags = GC_CHUNK_HALO_MISSING; o.reserved[0] = 0; o.reserved[1] = 0;
+                        for (int t = 0; t < kMeshTypes; t++) { o.index_count[t] = 0; o.index_offset[t] = 0; }
+                        p.out[chunk] = o;
+                        atomicExch(p.error_flag, 2);
+                    }
+                    continue;
+                }
+                halo_seen |= need;
+            }
+        }
 
         GC_PROF_MARK(0);
         // ================= P1: stage + convert the block ids =================
@@ -687,6 +801,17 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         // hx and the quad list were written into the staging ring by the generic proxy: order that before the next TMA writes
         fence_proxy_async();
     }
+    // the last CTA out leaves the control block ready for the next launch (no memset between launches): every CTA's claims and
+    // arena reservations precede its increment of the done counter, which wraps to zero by itself
+    if (tid == 0)
+    {
+        __threadfence();
+        if (atomicInc(p.done_counter, gridDim.x - 1) == gridDim.x - 1)
+        {
+            *p.total_out = p.keep_cursor ? atomicAdd(p.quad_cursor, 0ull) : atomicExch(p.quad_cursor, 0ull);
+            atomicExch(p.work_counter, 0);
+        }
+    }
 }
 
 // ---- slab halo pack / unpack (multi-GPU) ----
@@ -768,11 +893,14 @@ static cudaError_t configure_mesh_kernel()
 {
     static bool configured = false;
     if (configured) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(gc_mesh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gc_mesh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    // the whole unified L1 / shared array as shared memory: two ~112 KB CTAs per SM
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gc_mesh_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gc_mesh_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = cudaSuccess;
+    const void* kernels[3] = { (const void*)gc_mesh_kernel<false, false>, (const void*)gc_mesh_kernel<true, false>, (const void*)gc_mesh_kernel<false, true> };
+    for (int k = 0; k < 3 && e == cudaSuccess; k++)
+    {
+        e = cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        // the whole unified L1 / shared array as shared memory: two ~112 KB CTAs per SM
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernels[k], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     if (e == cudaSuccess) configured = true;
     return e;
 }
@@ -781,23 +909,26 @@ int mesh_ctas_per_sm()
 {
     if (configure_mesh_kernel() != cudaSuccess) return 0;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gc_mesh_kernel<false>, NT, kSmemBytes) != cudaSuccess) return 0;
-    return n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gc_mesh_kernel<false, false>, NT, kSmemBytes) != cudaSuccess) return 0;
+    int nh = 0;   // (the exchange instantiation must fit as many: its waiting CTAs rely on the grid being resident)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nh, gc_mesh_kernel<false, true>, NT, kSmemBytes) != cudaSuccess) return 0;
+    return n < nh ? n : nh;
 }
 
 cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int grid, cudaStream_t stream)
 {
     cudaError_t e0 = configure_mesh_kernel();
     if (e0 != cudaSuccess) return e0;
-    if (p.prof) gc_mesh_kernel<true><<<grid, NT, kSmemBytes, stream>>>(p, maps);
-    else gc_mesh_kernel<false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
+    if (p.halo.enabled) gc_mesh_kernel<false, true><<<grid, NT, kSmemBytes, stream>>>(p, maps);   // (no profiling instantiation of the exchange form)
+    else if (p.prof) gc_mesh_kernel<true, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
+    else gc_mesh_kernel<false, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
     return cudaGetLastError();
 }
 
 cudaError_t mesh_kernel_attributes(int* regs, int* static_smem, int* max_dyn_smem)
 {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, gc_mesh_kernel<false>);
+    cudaError_t e = cudaFuncGetAttributes(&a, gc_mesh_kernel<false, false>);
     if (e != cudaSuccess) return e;
     if (regs) *regs = a.numRegs;
     if (static_smem) *static_smem = (int)a.sharedSizeBytes;

@@ -7,6 +7,7 @@
 
 #include "../../include/gcmesh.h"
 #include "mesh_core.cuh"
+#include "gchalo_kernel.cuh"
 
 namespace gc
 {
@@ -36,10 +37,17 @@ struct MeshParams
     unsigned long long max_quads;
     unsigned long long* quad_cursor;   // arena reservation cursor (quads)
     int32_t* work_counter;             // dynamic chunk scheduler
+    uint32_t* done_counter;            // CTAs that have left the work loop; the last one resets the scheduler for the next launch
+    unsigned long long* total_out;     // ... and leaves the quad cursor's final value here
+    int32_t keep_cursor;               // 1: the cursor keeps running into the next launch (strips of one gcmesh_mesh_host call)
     const DeviceTables* tables;
     int32_t* error_flag;               // set by the mbarrier watchdog
     int32_t use_tma;                   // 0: the producer warp stages slabs with plain loads (debug aid)
     unsigned long long* prof;          // optional: 512 cycle counters (phase / wait attribution), null = off
+    // slab halo exchange fused into this kernel (gcmesh_submit_exchange): work items [0, n_push) store this rank's boundary
+    // planes into the neighbours' windows, item n_push + k is chunk order[k]
+    int32_t n_push;
+    HaloFused halo;
 };
 
 // The block-id arena viewed as (256, 8, z = 32, slot): one box (256, 8, 1, 1) is one whole z-slab of a brick

@@ -26,11 +26,12 @@ MAX_QUADS = 10000
 MESH_OPAQUE, MESH_CUTOUT, MESH_TRANSPARENT, MESH_FLUID, MESH_MAGMA = range(5)
 CHUNK_OVERFLOW = 1
 CHUNK_NO_SPACE = 2
+CHUNK_HALO_MISSING = 4
+WORLD_SURFACE_BOUNDS_BLOCKS = 1      # GC_WORLD_SURFACE_BOUNDS_BLOCKS
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcedit_kernel.cu", "gchalo_kernel.cu", "gcgen_kernel.cu", "gcfill_kernel.cu", "gcmesh_api.cu"]
-HEADERS = ["gcmesh_kernel.cuh", "gclight_kernel.cuh", "gcrle_kernel.cuh", "mesh_core.cuh", os.path.join("..", "..", "include", "gcmesh.h")]
 
 
 class GcMeshError(RuntimeError):
@@ -39,8 +40,10 @@ class GcMeshError(RuntimeError):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libgcmesh.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    import glob
+
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS]
+    deps = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(_HERE, "..", "include", "gcmesh.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB_PATH, "-lcudart"]
@@ -75,14 +78,14 @@ EXPORTS = [
     "gcmesh_version", "gcmesh_last_error", "gcmesh_create", "gcmesh_destroy", "gcmesh_set_stream",
     "gcmesh_set_block_table", "gcmesh_default_block_table", "gcmesh_synchronize",
     "gcmesh_world_create", "gcmesh_world_destroy", "gcmesh_world_upload_chunk", "gcmesh_world_upload_surface",
-    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_upload_launches", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
+    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_set_option", "gcmesh_world_upload_launches", "gcmesh_world_upload_bytes", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
     "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
     "gcmesh_world_halo_export", "gcmesh_world_halo_connect_ipc", "gcmesh_world_halo_connect_local", "gcmesh_world_halo_push", "gcmesh_world_halo_status",
     "gcmesh_default_light_rules", "gcmesh_set_light_rules", "gcmesh_world_compute_surface", "gcmesh_world_light",
     "gcmesh_world_light_stats", "gcmesh_world_download",
     "gcmesh_world_upload_rle", "gcmesh_world_rle_refused", "gcmesh_world_encode_rle",
     "gcmesh_world_set_blocks", "gcmesh_world_vertex_counts", "gcmesh_world_generate",
-    "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_mesh_host", "gcmesh_wait", "gcmesh_batch_results",
+    "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_submit_exchange", "gcmesh_batch_set_timing", "gcmesh_mesh_host", "gcmesh_wait", "gcmesh_batch_results",
     "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_fill_device", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
     "gcmesh_batch_launches", "gcmesh_kernel_info", "gcmesh_batch_profile",
 ]
@@ -91,10 +94,13 @@ _lib = None
 
 
 def lib() -> ctypes.CDLL:
-    """Load libgcmesh.so (building it if the sources are newer).  Fails loudly when it cannot be loaded."""
+    """Load libgcmesh.so, rebuilding it first when a source or header is newer (where nvcc exists: the GPU box runs the
+    library that travelled with the snapshot).  Fails loudly when it cannot be loaded."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        import shutil
+
+        if not os.environ.get("GCMESH_LIB") and (not os.path.exists(LIB_PATH) or shutil.which("nvcc")):
             build()
         L = ctypes.CDLL(LIB_PATH)
         vp, ci = ctypes.c_void_p, ctypes.c_int
@@ -113,7 +119,10 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_upload_all.argtypes = [vp, vp, vp, vp, vp]
         L.gcmesh_world_upload_rows.argtypes = [vp, ci, ci, vp, vp, vp, vp]
         L.gcmesh_world_upload_sparse.argtypes = [vp, vp, vp, vp, vp, vp, ci]
+        L.gcmesh_world_set_option.argtypes = [vp, ci, ci]
         L.gcmesh_world_upload_launches.argtypes = [vp]
+        L.gcmesh_world_upload_bytes.argtypes = [vp]
+        L.gcmesh_world_upload_bytes.restype = ctypes.c_uint64
         L.gcmesh_world_device_ptrs.argtypes = [vp] + [ctypes.POINTER(vp)] * 4
         L.gcmesh_world_halo_bytes.argtypes = [vp]
         L.gcmesh_world_halo_bytes.restype = ctypes.c_size_t
@@ -139,6 +148,8 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_batch_create.argtypes = [vp, ci, ctypes.c_uint64, ctypes.POINTER(vp)]
         L.gcmesh_batch_destroy.argtypes = [vp]
         L.gcmesh_submit.argtypes = [vp, vp, vp, ci]
+        L.gcmesh_submit_exchange.argtypes = [vp, vp, vp, ci, ci, ci]
+        L.gcmesh_batch_set_timing.argtypes = [vp, ci]
         L.gcmesh_wait.argtypes = [vp]
         L.gcmesh_mesh_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, ctypes.c_uint64, ci]
         L.gcmesh_batch_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_uint64)]
@@ -251,6 +262,14 @@ class World:
 
     def upload_launches(self) -> int:
         return int(lib().gcmesh_world_upload_launches(self.h))
+
+    def set_option(self, option: int, value: int = 1) -> "World":
+        _check(lib().gcmesh_world_set_option(self.h, int(option), int(value)), "gcmesh_world_set_option")
+        return self
+
+    def upload_bytes(self) -> int:
+        """Host -> device bytes the last sparse upload / mesh_host call moved."""
+        return int(lib().gcmesh_world_upload_bytes(self.h))
 
     def upload_rows(self, host, cz0: int, cz1: int) -> "World":
         _check(lib().gcmesh_world_upload_rows(self.h, cz0, cz1, _ptr(host.blocks), _ptr(host.sun), _ptr(host.light), _ptr(host.surface)),
@@ -410,6 +429,18 @@ class Batch:
     def submit(self, world: World, coords) -> "Batch":
         self._coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)
         _check(lib().gcmesh_submit(world.h, self.h, _ptr(self._coords), len(self._coords)), "gcmesh_submit")
+        return self
+
+    def submit_exchange(self, world: World, coords, send_row_down: int, send_row_up: int) -> "Batch":
+        """Slab halo exchange + mesh build in one kernel (gcmesh_submit_exchange)."""
+        self._coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)
+        _check(lib().gcmesh_submit_exchange(world.h, self.h, _ptr(self._coords), len(self._coords), int(send_row_down), int(send_row_up)),
+               "gcmesh_submit_exchange")
+        return self
+
+    def set_timing(self, on: bool) -> "Batch":
+        """Record (default) or leave out the two timing events around the kernel (:meth:`elapsed_ms` needs them)."""
+        _check(lib().gcmesh_batch_set_timing(self.h, 1 if on else 0), "gcmesh_batch_set_timing")
         return self
 
     def mesh_host(self, world: World, host, coords, vertices, indices, nonzero_hint=None, threads: int = 0) -> "Batch":

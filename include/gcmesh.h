@@ -68,6 +68,7 @@ typedef struct GcChunkCoord { int32_t cx, cy, cz; } GcChunkCoord;
 /* Per-chunk result flags. */
 #define GC_CHUNK_OVERFLOW 1u   /* more than GC_MAX_QUADS quads: the reference asserts (WorldRender.cpp:558); nothing is emitted */
 #define GC_CHUNK_NO_SPACE 2u   /* the batch arena was too small for this chunk; nothing is emitted */
+#define GC_CHUNK_HALO_MISSING 4u /* gcmesh_submit_exchange: the neighbour's boundary plane never arrived; nothing is emitted */
 
 /*
  * Per-chunk result: the counters of the reference's MeshData / MeshIndexData (Code/Mesh.h:31-52) plus where the
@@ -138,8 +139,17 @@ int gcmesh_world_upload_rows(GcWorld* world, int cz0, int cz1, const uint16_t* b
  * cudaHostRegister), else by one cudaMemcpyAsync each; arrays that were non-zero on the device and are zero now are cleared. */
 int gcmesh_world_upload_sparse(GcWorld* world, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light,
                                const uint8_t* surface, const uint8_t* nonzero_hint, int threads);
+/* Options of a window.  GC_WORLD_SURFACE_BOUNDS_BLOCKS (default 0): the caller vouches that the `surface` maps handed to
+ * gcmesh_world_upload_sparse / gcmesh_mesh_host are ComputeSurface of the block ids handed with them (Lighting.cpp:5-26 —
+ * what ChunkGroup::surface holds for every pre-processed column; a stale entry is only ever too high).  The host scan then
+ * takes a brick lying wholly at or above its column's highest entry for AIR without reading it (layer y = 255, which
+ * ComputeSurface does not look at, is still read). */
+enum { GC_WORLD_SURFACE_BOUNDS_BLOCKS = 1 };
+int gcmesh_world_set_option(GcWorld* world, int option, int value);
 /* Kernels launched by the last gcmesh_world_upload_sparse call. */
 int gcmesh_world_upload_launches(const GcWorld* world);
+/* Host -> device bytes the last gcmesh_world_upload_sparse / gcmesh_mesh_host call moved (brick arrays, work lists, surface maps, coordinates). */
+unsigned long long gcmesh_world_upload_bytes(const GcWorld* world);
 /* Raw device pointers of the four arenas, for device-resident producers (and for NCCL halo exchange). */
 int gcmesh_world_device_ptrs(GcWorld* world, void** blocks, void** sunlight, void** block_light, void** surface);
 /* Slab halo (multi-GPU): the z-boundary plane of one row of columns — for every column cx and chunk cy the
@@ -161,9 +171,14 @@ int gcmesh_world_unpack_halo(GcWorld* world, int cz, int z, const void* device_b
  *                                   z = 31 plane of row send_row_up to the rank above, wait for the neighbours' planes.
  *                                   Work enqueued afterwards (gcmesh_submit) sees the new halo.  Every rank of a chain
  *                                   calls it the same number of times.
+ *                                   A neighbour that does not enter the exchange within the wait bound is left alone (nothing
+ *                                   is stored into its window, no arrival is published to it) and the failure is recorded in
+ *                                   both ranks' flag blocks; gcmesh_submit / gcmesh_wait do not look there — poll
+ *                                   gcmesh_world_halo_status, or use gcmesh_submit_exchange, whose gcmesh_wait reports it.
  *   gcmesh_world_halo_status        synchronises; timed_out != 0: a neighbour did not show up within 10 s
  *                                   (GCMESH_HALO_WAIT_MS, read at the first exchange of the process) — an error, not a hang;
- *                                   the value is (exchange serial << 8) | (1 + flag word waited for) of the first such wait */
+ *                                   the value is (exchange serial << 8) | (1 + flag word waited for) of the first such wait,
+ *                                   here or as reported by a neighbour that waited for this rank */
 #define GC_HALO_HANDLE_BYTES 320
 int gcmesh_world_halo_export(GcWorld* world, void* handles);
 int gcmesh_world_halo_connect_ipc(GcWorld* world, int side, const void* handles, int peer_row);
@@ -269,6 +284,15 @@ int gcmesh_batch_destroy(GcBatch* batch);
  * WorldRender.cpp:235).  Asynchronous; inputs must not change until gcmesh_wait (the reference's gating rule,
  * WorldRender.cpp:265-277). `coords` is copied. */
 int gcmesh_submit(GcWorld* world, GcBatch* batch, const GcChunkCoord* coords, int n);
+/* Slab halo exchange + mesh build as ONE kernel (multi-GPU; replaces gcmesh_world_halo_push followed by gcmesh_submit):
+ * the kernel's first work items store this rank's boundary planes — the z = 0 plane of row send_row_down to the rank below,
+ * the z = 31 plane of row send_row_up to the rank above — straight into the neighbours' halo rows over NVLink peer memory
+ * while the other CTAs already mesh; the chunks of rows send_row_down / send_row_up, the only ones that read a neighbour's
+ * plane, are claimed last and wait for that plane's "arrived" flag.  Nothing separates the exchange from the meshing: no
+ * second launch, no flag round trip ahead of the first chunk.  Neighbours are connected as for gcmesh_world_halo_push;
+ * every rank of a chain calls it the same number of times (n >= 1).  A plane that does not arrive within the wait bound
+ * (GCMESH_HALO_WAIT_MS) flags the chunks that needed it GC_CHUNK_HALO_MISSING and makes gcmesh_wait fail. */
+int gcmesh_submit_exchange(GcWorld* world, GcBatch* batch, const GcChunkCoord* coords, int n, int send_row_down, int send_row_up);
 int gcmesh_wait(GcBatch* batch);
 /* After gcmesh_wait: per-chunk descriptors (host memory owned by the batch, n entries, submit order). */
 int gcmesh_batch_results(GcBatch* batch, const GcChunkOut** out, int* n, uint64_t* total_quads);
@@ -301,8 +325,11 @@ int gcmesh_batch_fill_device(GcBatch* batch, const GcDeviceMesh* targets, int n)
 int gcmesh_mesh_host(GcWorld* world, GcBatch* batch, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light,
                      const uint8_t* surface, const uint8_t* nonzero_hint, const GcChunkCoord* coords, int n,
                      void* host_vertices, void* host_indices, uint64_t host_capacity_quads, int threads);
-/* Milliseconds the last submission's kernels took on the device (CUDA events on the context stream). */
+/* Milliseconds the last submission's kernels took on the device (CUDA events on the context stream).  The two timing events
+ * around the kernel are recorded by default; gcmesh_batch_set_timing(batch, 0) leaves them out (back-to-back submissions
+ * then have nothing but the launch between their kernels) and gcmesh_batch_elapsed_ms fails with GC_ERR_STATE. */
 int gcmesh_batch_elapsed_ms(GcBatch* batch, float* ms);
+int gcmesh_batch_set_timing(GcBatch* batch, int on);
 /* Number of kernel launches the last submission made. */
 int gcmesh_batch_launches(GcBatch* batch);
 

@@ -94,6 +94,9 @@ def oracle_lib() -> ctypes.CDLL:
         L.gcor_chunk_overflowed.argtypes = [ctypes.POINTER(_OrWorld)] + [ctypes.c_int] * 7
         L.gcor_bench_build.argtypes = [ctypes.POINTER(_OrWorld), ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
         L.gcor_bench_build.restype = ctypes.c_double
+        L.gcor_check_batch.argtypes = [ctypes.POINTER(_OrWorld), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+        L.gcor_check_batch.restype = ctypes.c_int64
         L.gcor_fnv1a64.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
         L.gcor_fnv1a64.restype = ctypes.c_uint64
         L.gcor_default_block_table.argtypes = [ctypes.POINTER(BlockInfo), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
@@ -135,6 +138,9 @@ def ref_lib() -> ctypes.CDLL:
         L.gcref_pending_updates.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.gcref_bench_build.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
         L.gcref_bench_build.restype = ctypes.c_double
+        L.gcref_check_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+        L.gcref_check_batch.restype = ctypes.c_int64
         _rlib = L
     return _rlib
 
@@ -201,6 +207,19 @@ def default_block_table():
     return arr, n.value, kz.value
 
 
+def _check_batch(call, coords, desc, vertices, indices, threads):
+    coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)
+    desc = np.ascontiguousarray(desc)
+    assert desc.dtype.itemsize == 64 and len(desc) == len(coords)
+    vertices, indices = np.ascontiguousarray(vertices), np.ascontiguousarray(indices)
+    arena_quads = min(vertices.nbytes // 48, indices.nbytes // 12)
+    result = np.zeros(len(coords), np.uint8)
+    q = ctypes.c_int64(0)
+    bad = call(coords.ctypes.data, len(coords), desc.ctypes.data, vertices.ctypes.data, indices.ctypes.data, arena_quads,
+               int(threads) if threads and threads > 0 else (os.cpu_count() or 1), result.ctypes.data, ctypes.byref(q))
+    return int(bad), result, int(q.value)
+
+
 class OracleWorld:
     """The restated oracle over a HostWorld's arrays (borrowed, not copied)."""
 
@@ -227,6 +246,11 @@ class OracleWorld:
 
     def chunk_overflowed(self, cx, cy, cz, x, y, z, total_vertices) -> bool:
         return bool(oracle_lib().gcor_chunk_overflowed(ctypes.byref(self._w), cx, cy, cz, x, y, z, total_vertices))
+
+    def check_batch(self, coords, desc, vertices, indices, threads: int = 0):
+        """Exhaustive byte comparison of a mesher batch (64-byte GcChunkOut descriptors + the downloaded vertex / index
+        arenas) with this oracle's build of every chunk -> (mismatching chunks, per-chunk result bytes, quads compared)."""
+        return _check_batch(lambda *a: oracle_lib().gcor_check_batch(ctypes.byref(self._w), *a), coords, desc, vertices, indices, threads)
 
     def bench(self, coords: np.ndarray, threads: int):
         coords = np.ascontiguousarray(coords, np.int32)
@@ -345,6 +369,10 @@ class RefWorld:
         out = np.zeros(self.size * self.size * 4, np.uint8)
         self.L.gcref_pending_updates(self.h, out.ctypes.data, int(clear))
         return out.reshape(self.size, self.size, 4)
+
+    def check_batch(self, coords, desc, vertices, indices, threads: int = 0):
+        """As OracleWorld.check_batch, against the reference's own BuildChunkAsync (chunks with flags != 0 count as mismatches)."""
+        return _check_batch(lambda *a: self.L.gcref_check_batch(self.h, *a), coords, desc, vertices, indices, threads)
 
     def bench(self, coords: np.ndarray, threads: int):
         coords = np.ascontiguousarray(coords, np.int32)

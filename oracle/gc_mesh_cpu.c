@@ -3,7 +3,10 @@
  * Written from the behaviour of the reference (file:line cited per function), not from its text:
  * the world is a dense window of bricks and every neighbour lookup goes through one probe function.
  */
+#define _GNU_SOURCE
 #include "gc_oracle.h"
+
+#include <sched.h>
 
 #include <pthread.h>
 #include <stdatomic.h>
@@ -277,11 +280,31 @@ typedef struct OrJob
     int n;
     atomic_int* next;
     int64_t quads;
+    int index;
 } OrJob;
+
+/* worker t runs on the t-th CPU this process may use (round robin): a timed run does not depend on where the scheduler
+ * happens to put, or move, its threads */
+static void or_pin_self(int t)
+{
+    cpu_set_t all, one;
+    if (sched_getaffinity(0, sizeof(all), &all) != 0) return;
+    const int n = CPU_COUNT(&all);
+    if (n <= 0) return;
+    int want = t % n;
+    for (int c = 0; c < CPU_SETSIZE; c++)
+        if (CPU_ISSET(c, &all) && want-- == 0)
+        {
+            CPU_ZERO(&one); CPU_SET(c, &one);
+            pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+            return;
+        }
+}
 
 static void* or_worker(void* p)
 {
     OrJob* job = (OrJob*)p;
+    or_pin_self(job->index);
     GcOrMesh* m = (GcOrMesh*)malloc(sizeof(GcOrMesh));
     for (;;)
     {
@@ -303,7 +326,7 @@ double gcor_bench_build(const GcOrWorld* w, const int32_t* coords, int n, int th
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < threads; t++)
     {
-        jobs[t].w = w; jobs[t].coords = coords; jobs[t].n = n; jobs[t].next = &next; jobs[t].quads = 0;
+        jobs[t].w = w; jobs[t].coords = coords; jobs[t].n = n; jobs[t].next = &next; jobs[t].quads = 0; jobs[t].index = t;
         pthread_create(&th[t], NULL, or_worker, &jobs[t]);
     }
     int64_t quads = 0;
@@ -320,4 +343,90 @@ uint64_t gcor_fnv1a64(const void* data, uint64_t n, uint64_t h)
     if (h == 0) h = 14695981039346656037ull;
     for (uint64_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
     return h;
+}
+
+/* ---- exhaustive parity check of a mesher batch against this oracle (multi-threaded) ----
+ * desc: one 64-byte GcChunkOut per chunk (include/gcmesh.h: quad_base, vert_count, index_count[5], index_offset[5],
+ * quads, flags), vertices / indices: the batch arenas as gcmesh_batch_download returns them.  Every chunk is rebuilt with
+ * gcor_build_chunk (BuildChunkAsync, WorldRender.cpp:6-27) and compared byte for byte.
+ * result[i]: 0 identical; bit 0 counts differ, bit 1 vertex bytes, bit 2 index bytes, bit 3 flags / segment outside the arena. */
+typedef struct OrChunkOut
+{
+    uint32_t quad_base, vert_count, index_count[GCOR_MESH_TYPES], index_offset[GCOR_MESH_TYPES], quads, flags, reserved[2];
+} OrChunkOut;
+
+typedef struct OrCheckJob
+{
+    const GcOrWorld* w;
+    const int32_t* coords;
+    int n;
+    const OrChunkOut* desc;
+    const uint8_t* vertices;
+    const uint16_t* indices;
+    uint64_t arena_quads;
+    uint8_t* result;
+    atomic_int* next;
+    int64_t bad, quads;
+} OrCheckJob;
+
+static void* or_check_worker(void* p)
+{
+    OrCheckJob* job = (OrCheckJob*)p;
+    GcOrMesh* m = (GcOrMesh*)malloc(sizeof(GcOrMesh));
+    for (;;)
+    {
+        int i = atomic_fetch_add(job->next, 1);
+        if (i >= job->n) break;
+        const OrChunkOut* d = job->desc + i;
+        const int total = gcor_build_chunk(job->w, job->coords[3 * i], job->coords[3 * i + 1], job->coords[3 * i + 2], m);
+        uint8_t r = 0;
+        if (m->overflow)
+        {
+            /* over the reference's cap (an assert there, WorldRender.cpp:558): the mesher must flag it and emit nothing */
+            if (!(d->flags & 1u) || d->vert_count != 0 || d->quads != (uint32_t)(total / 4)) r |= 8;
+        }
+        else
+        {
+            if (d->flags != 0) r |= 8;
+            if (d->vert_count != (uint32_t)m->vert_count || d->quads != (uint32_t)(m->vert_count / 4)) r |= 1;
+            for (int t = 0; t < GCOR_MESH_TYPES; t++)
+                if (d->index_count[t] != (uint32_t)m->index_count[t]) r |= 1;
+            if (!r && m->vert_count)
+            {
+                if ((uint64_t)d->quad_base + d->quads > job->arena_quads) r |= 8;
+                else
+                {
+                    if (memcmp(job->vertices + (size_t)d->quad_base * 48, m->vertices, (size_t)m->vert_count * 12)) r |= 2;
+                    for (int t = 0; t < GCOR_MESH_TYPES; t++)
+                        if (m->index_count[t] &&
+                            memcmp(job->indices + (size_t)d->quad_base * 6 + d->index_offset[t], m->indices[t], (size_t)m->index_count[t] * 2)) r |= 4;
+                }
+            }
+            job->quads += m->vert_count / 4;
+        }
+        if (job->result) job->result[i] = r;
+        if (r) job->bad++;
+    }
+    free(m);
+    return NULL;
+}
+
+int64_t gcor_check_batch(const GcOrWorld* w, const int32_t* coords, int n, const void* desc, const void* vertices, const void* indices,
+                         uint64_t arena_quads, int threads, uint8_t* result, int64_t* quads_checked)
+{
+    if (threads < 1) threads = 1;
+    atomic_int next = 0;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
+    OrCheckJob* jobs = (OrCheckJob*)malloc(sizeof(OrCheckJob) * (size_t)threads);
+    for (int t = 0; t < threads; t++)
+    {
+        OrCheckJob j = { w, coords, n, (const OrChunkOut*)desc, (const uint8_t*)vertices, (const uint16_t*)indices, arena_quads, result, &next, 0, 0 };
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, or_check_worker, &jobs[t]);
+    }
+    int64_t bad = 0, quads = 0;
+    for (int t = 0; t < threads; t++) { pthread_join(th[t], NULL); bad += jobs[t].bad; quads += jobs[t].quads; }
+    free(th); free(jobs);
+    if (quads_checked) *quads_checked = quads;
+    return bad;
 }

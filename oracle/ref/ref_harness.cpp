@@ -90,6 +90,8 @@ static void DeleteDirectory(char*) {}
 
 #include <chrono>
 #include <thread>
+#include <pthread.h>
+#include <sched.h>
 
 // ---------------------------------------------------------------------------------------
 // C ABI of the gold oracle.
@@ -399,6 +401,22 @@ double gcref_bench_build(GcRefWorld* w, const int32_t* coords, int n, int thread
     {
         pool.emplace_back([&, t]()
         {
+            // worker t runs on the t-th CPU this process may use (round robin): a timed run does not depend on where the
+            // scheduler happens to put, or move, its threads
+            {
+                cpu_set_t all, one;
+                if (sched_getaffinity(0, sizeof(all), &all) == 0 && CPU_COUNT(&all) > 0)
+                {
+                    int want = t % CPU_COUNT(&all);
+                    for (int c = 0; c < CPU_SETSIZE; c++)
+                        if (CPU_ISSET(c, &all) && want-- == 0)
+                        {
+                            CPU_ZERO(&one); CPU_SET(c, &one);
+                            pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+                            break;
+                        }
+                }
+            }
             MeshData* md = mds[t];
             int64_t local = 0;
             for (;;)
@@ -422,6 +440,68 @@ double gcref_bench_build(GcRefWorld* w, const int32_t* coords, int n, int thread
     for (int t = 0; t < threads; t++) delete mds[t];
     if (quadsOut) *quadsOut = quads.load();
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Exhaustive parity check of a mesher batch against the reference's own BuildChunkAsync (multi-threaded): desc = one 64-byte
+// GcChunkOut per chunk (include/gcmesh.h), vertices / indices = the batch arenas.  result[i]: 0 identical; bit 0 counts,
+// bit 1 vertex bytes, bit 2 index bytes, bit 3 flags / segment outside the arena.  Chunks over the reference's cap (an
+// assert in the reference, WorldRender.cpp:558) cannot be built by it: the caller must not pass them (flags != 0 is reported).
+struct RefChunkOut { uint32_t quad_base, vert_count, index_count[MESH_TYPE_COUNT], index_offset[MESH_TYPE_COUNT], quads, flags, reserved[2]; };
+int64_t gcref_check_batch(GcRefWorld* w, const int32_t* coords, int n, const void* descv, const void* verticesv, const void* indicesv,
+                          uint64_t arenaQuads, int threads, uint8_t* result, int64_t* quadsChecked)
+{
+    const RefChunkOut* desc = (const RefChunkOut*)descv;
+    const uint8_t* vertices = (const uint8_t*)verticesv;
+    const uint16_t* indices = (const uint16_t*)indicesv;
+    if (threads < 1) threads = 1;
+    std::atomic<int> next(0);
+    std::atomic<int64_t> bad(0), quads(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+    {
+        pool.emplace_back([&]()
+        {
+            MeshData* md = new MeshData();
+            for (;;)
+            {
+                int i = next.fetch_add(1);
+                if (i >= n) break;
+                const RefChunkOut& d = desc[i];
+                uint8_t r = 0;
+                if (d.flags != 0) r |= 8;
+                else
+                {
+                    Chunk* chunk = RefGroup(w, coords[i * 3 + 0], coords[i * 3 + 2])->chunks + coords[i * 3 + 1];
+                    md->vertCount = 0;
+                    chunk->meshData = md;
+                    BuildChunkAsync(w->state, w->world, chunk);
+                    if (d.vert_count != (uint32_t)md->vertCount || d.quads * 4 != (uint32_t)md->vertCount) r |= 1;
+                    for (int m = 0; m < MESH_TYPE_COUNT; m++)
+                        if (d.index_count[m] != (uint32_t)(md->indices[m] ? md->indices[m]->count : 0)) r |= 1;
+                    if (!r && md->vertCount)
+                    {
+                        if ((uint64_t)d.quad_base + d.quads > arenaQuads) r |= 8;
+                        else
+                        {
+                            if (memcmp(vertices + (size_t)d.quad_base * 48, md->vertices, (size_t)md->vertCount * sizeof(VertexInfo))) r |= 2;
+                            for (int m = 0; m < MESH_TYPE_COUNT; m++)
+                                if (md->indices[m] && md->indices[m]->count &&
+                                    memcmp(indices + (size_t)d.quad_base * 6 + d.index_offset[m], md->indices[m]->data, (size_t)md->indices[m]->count * 2)) r |= 4;
+                        }
+                    }
+                    quads += md->vertCount / 4;
+                    RefResetMeshData(md);
+                    chunk->meshData = nullptr;
+                }
+                if (result) result[i] = r;
+                if (r) bad++;
+            }
+            delete md;
+        });
+    }
+    for (auto& th : pool) th.join();
+    if (quadsChecked) *quadsChecked = quads.load();
+    return bad.load();
 }
 
 }  // extern "C"

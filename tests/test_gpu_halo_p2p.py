@@ -44,7 +44,9 @@ def owned_coords(w, first_owned, last_owned):
     return np.asarray([(cx, cy, cz) for cz in range(first_owned, last_owned + 1) for cx in range(1, w.size_x - 1) for cy in range(4)], np.int32)
 
 
-def test_three_slabs_one_gpu_local_peers():
+@pytest.mark.parametrize("fused", [False, True])
+def test_three_slabs_one_gpu_local_peers(fused):
+    """fused = False: gcmesh_world_halo_push (exchange kernel) + gcmesh_submit; True: gcmesh_submit_exchange (one kernel)."""
     from gamecraft_b200 import mesher, slab
 
     n = 3
@@ -68,8 +70,11 @@ def test_three_slabs_one_gpu_local_peers():
         c["ctx"].synchronize()
     for k in range(3):                                                           # exchange -> mesh, three times over
         for c in ranks:
-            c["world"].halo_push(c["fo"], c["lo"])
-            c["batch"].submit(c["world"], c["coords"])
+            if fused:
+                c["batch"].submit_exchange(c["world"], c["coords"], c["fo"], c["lo"])
+            else:
+                c["world"].halo_push(c["fo"], c["lo"])
+                c["batch"].submit(c["world"], c["coords"])
     g, oracle = global_oracle(n)
     for c in ranks:
         meshes = c["batch"].wait().meshes()
@@ -102,10 +107,30 @@ def missing_neighbour():
     ctx_a, ctx_b = mesher.Context(0), mesher.Context(0)
     a = mesher.World(ctx_a, w.size_x, w.size_z).upload(w)
     b = mesher.World(ctx_b, w.size_x, w.size_z).upload(w)
+    try:
+        a.halo_connect_local(1, mesher.World(ctx_a, w.size_x, w.size_z), fo - 1)   # a neighbour on the same context / stream could never answer
+        raise AssertionError("expected GcMeshError")
+    except mesher.GcMeshError:
+        pass
     a.halo_connect_local(1, b, fo - 1)
     a.halo_push(fo, lo)                                                         # b never calls halo_push
     timed_out, serial = a.halo_status()
     assert timed_out and serial == 1
+    assert b.halo_status()[0] == timed_out                                      # ... and the neighbour's flag block says so too
+    # the fused form: the boundary planes never arrive -> the chunks that needed them are flagged, gcmesh_wait fails
+    coords = owned_coords(w, fo, lo)
+    batch = mesher.Batch(ctx_a, len(coords), len(coords) * 4096)
+    batch.submit_exchange(a, coords, fo, lo)
+    try:
+        batch.wait()
+        raise AssertionError("expected GcMeshError")
+    except mesher.GcMeshError as e:
+        assert "never arrived" in str(e)
+    desc, _ = batch.results()
+    top = coords[:, 2] == lo
+    assert (desc["flags"][top] == 4).all() and (desc["vert_count"][top] == 0).all()        # GC_CHUNK_HALO_MISSING
+    assert (desc["flags"][~top] == 0).all()
+    batch.close()
     try:
         b.halo_push(fo, lo)                                                     # no neighbour connected
         raise AssertionError("expected GcMeshError")
@@ -115,7 +140,7 @@ def missing_neighbour():
     print("timed out as expected: 0x%x" % timed_out)
 
 
-def _ipc_worker(rank, world_size, port, out_dir):
+def _ipc_worker(rank, world_size, port, out_dir, fused):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import json
@@ -142,8 +167,11 @@ def _ipc_worker(rank, world_size, port, out_dir):
     coords = owned_coords(w, fo, lo)
     batch = mesher.Batch(ctx, len(coords), len(coords) * 4096)
     for k in range(3):
-        world.halo_push(fo, lo)
-        batch.submit(world, coords)
+        if fused:
+            batch.submit_exchange(world, coords, fo, lo)
+        else:
+            world.halo_push(fo, lo)
+            batch.submit(world, coords)
     meshes = batch.wait().meshes()
     timed_out, serial = world.halo_status()
     sigs = {"timed_out": bool(timed_out), "serial": serial}
@@ -157,7 +185,8 @@ def _ipc_worker(rank, world_size, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_one_process_per_gpu_ipc_peers(tmp_path):
+@pytest.mark.parametrize("fused", [False, True])
+def test_one_process_per_gpu_ipc_peers(tmp_path, fused):
     import json
 
     import torch
@@ -169,7 +198,7 @@ def test_one_process_per_gpu_ipc_peers(tmp_path):
     if n < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_ipc_worker, args=(n, port, str(tmp_path)), nprocs=n, join=True)
+    mp.spawn(_ipc_worker, args=(n, port, str(tmp_path), fused), nprocs=n, join=True)
     g, oracle = global_oracle(n)
     seen = 0
     for r in range(n):

@@ -207,7 +207,8 @@ def test_gpu_halo_pack_unpack_kernels_match_host_layout(ctx):
 
 
 def test_gpu_full_size_properties(ctx):
-    """BASELINE config 2 at full size (4096 forest chunks): size-independent properties + a sampled byte comparison."""
+    """BASELINE config 2 at full size (4096 forest chunks): size-independent properties + EVERY chunk byte-compared with the
+    oracle (and with the reference's own mesher where oracle/_ref travelled)."""
     from gamecraft_b200 import mesher
 
     w = util.HostWorld(36, 36, origin=(-18, -18)).build("forest", 1337)
@@ -227,7 +228,7 @@ def test_gpu_full_size_properties(ctx):
     assert desc["quad_base"][nz][0] == 0 and np.array_equal(desc["quad_base"][nz][1:], ends[:-1]) and ends[-1] == q
     # every chunk: the five index streams reference each quad exactly once with SetIndices' pattern (Mesh.cpp:41-47)
     pat = np.array([2, 1, 0, 3, 2, 0], np.int64)
-    for d in desc[::7]:
+    for d in desc:
         nq = int(d["quads"])
         if nq == 0:
             continue
@@ -235,21 +236,44 @@ def test_gpu_full_size_properties(ctx):
         o = seg[:, 2]
         assert np.array_equal(seg, o[:, None] + pat[None, :]) and np.array_equal(np.sort(o), np.arange(nq) * 4)
         assert int(d["index_count"].sum()) == nq * 6 and int(d["vert_count"]) == nq * 4
-    # determinism: a second submission gives identical bytes per chunk
+    # every chunk, every byte, against the oracle
+    bad, result, quads = ob.OracleWorld(w).check_batch(coords, desc, verts, idx)
+    assert bad == 0 and quads == q, "chunks differing from the oracle: %s" % coords[np.nonzero(result)[0][:8]].tolist()
+    if ob.have_ref():
+        r = ob.RefWorld(w)
+        bad, result, quads = r.check_batch(coords, desc, verts, idx)
+        r.close()
+        assert bad == 0 and quads == q, "chunks differing from the reference's own mesher: %s" % coords[np.nonzero(result)[0][:8]].tolist()
+    # determinism: a second submission (history-based work order, segments elsewhere in the arena) gives identical bytes
     batch.submit(world, coords).wait()
     desc2, _ = batch.results()
     verts2, idx2 = batch.download()
-    for i in range(0, 4096, 97):
-        a, b = desc[i], desc2[i]
-        assert a["quads"] == b["quads"]
-        n = int(a["quads"])
-        assert np.array_equal(verts[int(a["quad_base"]) * 4: int(a["quad_base"]) * 4 + n * 4], verts2[int(b["quad_base"]) * 4: int(b["quad_base"]) * 4 + n * 4])
-    # sampled byte comparison with the oracle
-    o = ob.OracleWorld(w)
-    meshes = batch.meshes()
-    rng = np.random.default_rng(0)
-    for i in rng.choice(4096, 96, replace=False):
-        util.assert_same_mesh(meshes[i], o.build_chunk(*coords[i]), str(coords[i]))
+    assert ob.OracleWorld(w).check_batch(coords, desc2.copy(), verts2, idx2)[0] == 0
+    batch.close(); world.close()
+
+
+@pytest.mark.parametrize("kind,cols,seed,radius,min_quads", [("islands", 32, 4242, 512, 1), ("checker", 16, 99, None, 9216), ("noise", 16, 77, None, 5000)])
+def test_gpu_full_size_other_workloads_every_chunk(ctx, kind, cols, seed, radius, min_quads):
+    """The other bench workloads at bench size (BASELINE configs 3 and 4: islands4096, checker1024, noise1024): every chunk
+    byte-compared with the oracle."""
+    from gamecraft_b200 import mesher
+    from gamecraft_b200.worldgen import INT_MAX
+
+    size = cols + 4
+    w = util.HostWorld(size, size, origin=(-(size // 2), -(size // 2))).build(kind, seed, radius=radius or INT_MAX)
+    coords = w.interior_chunks(2)
+    world = mesher.World(ctx, size, size).upload(w)
+    batch = mesher.Batch(ctx, len(coords), len(coords) * mesher.MAX_QUADS)
+    for _ in range(2):                                   # first submission: static work order; second: by quad history
+        batch.submit(world, coords).wait()
+        desc, q = batch.results()
+        verts, idx = batch.download()
+        assert not desc["flags"].any()
+        bad, result, quads = ob.OracleWorld(w).check_batch(coords, desc.copy(), verts, idx)
+        assert bad == 0 and quads == q, "%s: chunks differing from the oracle: %s" % (kind, coords[np.nonzero(result)[0][:8]].tolist())
+        assert desc["quads"].max() >= min_quads
+    if kind == "islands":
+        assert (desc["index_count"][:, 3] > 0).any()     # the FLUID stream is exercised (water top faces)
     batch.close(); world.close()
 
 
@@ -332,6 +356,46 @@ def test_gpu_mesh_host_pipeline(ctx):
     # the ordinary submit path still works on the same batch / world afterwards
     for m, x in zip(batch.submit(world, coords).wait().meshes(), want):
         util.assert_same_mesh(m, x)
+    batch.close(); world.close()
+
+
+def test_gpu_surface_bounds_blocks_option(ctx):
+    """GC_WORLD_SURFACE_BOUNDS_BLOCKS: the host scan takes bricks at or above their column's highest surface entry for AIR
+    without reading them — except layer y = 255, which ComputeSurface (Lighting.cpp:5-17) never looks at.  Meshes equal the
+    oracle's, fewer bytes are scanned, and a block at y = 255 above an otherwise empty sky is still found."""
+    import torch
+
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(6, 7, origin=(-3, -3)).generate("mixed", 29, radius=110, falloff=60)
+    for wx, wz, b in ((70, 75, 3), (71, 75, 14), (100, 130, 22)):            # stone, a lantern and glass on the world's top layer
+        w.set_block(wx, 255, wz, b)
+    util.light_world(w)
+    assert int(w.surface[w.column(2, 2)][(75 & 31) * 32 + (70 & 31)]) < 255  # the surface map does not see them
+    coords = w.interior_chunks(1)
+    o = ob.OracleWorld(w)
+    want = [o.build_chunk(*c) for c in coords]
+    total = sum(m.quads for m in want)
+    pins = [torch.from_numpy(a).pin_memory() for a in (w.blocks, w.sun, w.light, w.surface)]
+
+    class P:
+        size_x, size_z = 6, 7
+        blocks, sun, light, surface = [t.numpy() for t in pins]
+
+    world = mesher.World(ctx, 6, 7).set_option(mesher.WORLD_SURFACE_BOUNDS_BLOCKS, 1)
+    batch = mesher.Batch(ctx, len(coords), total + 10)
+    hv = torch.zeros((total * 4, 12), dtype=torch.uint8).pin_memory().numpy()
+    hi = torch.zeros(total * 6, dtype=torch.uint16).pin_memory().numpy()
+    for _ in range(2):
+        batch.mesh_host(world, P, coords, hv, hi)
+        desc, q = batch.results()
+        assert q == total
+        assert o.check_batch(coords, desc.copy(), hv, hi)[0] == 0
+    world.upload_sparse(P)
+    for m, x, c in zip(batch.submit(world, coords).wait().meshes(), want, coords):
+        util.assert_same_mesh(m, x, str(c))
+    with pytest.raises(mesher.GcMeshError):
+        world.set_option(99, 1)
     batch.close(); world.close()
 
 
