@@ -55,6 +55,7 @@ struct HaloFused
     uint32_t* flags;            // this world's flag block
     uint32_t serial;
     unsigned long long wait_ns;
+    int32_t debug;              // GCMESH_HALO_DEBUG (development): 1 no copies, 2 no arrival waits, 4 no ready handshake
 };
 
 #if defined(__CUDACC__)

@@ -118,6 +118,8 @@ struct GcWorld
     int launches;             // kernels launched by the last upload call
     unsigned long long upload_bytes;   // host -> device bytes the last sparse upload / gcmesh_mesh_host call moved
     bool surface_bounds_blocks;        // GC_WORLD_SURFACE_BOUNDS_BLOCKS
+    int copy_run;                      // GC_WORLD_COPY_RUN (0: default)
+    int16_t* col_smax;                 // host, per column: highest surface entry (-1: not computed in this scan)
     // light fill scratch (grown on demand)
     uint32_t* d_light_counters;   // 8 x u32
     uint32_t* h_light_counters;   // pinned
@@ -413,7 +415,8 @@ int gcmesh_world_create(GcContext* ctx, int size_x, int size_z, GcWorld** out)
     w->slot_dirty = (uint8_t*)calloc(w->n_slots, 1);
     w->scan_flags = (uint8_t*)calloc(w->n_slots, 1);
     w->block_flags = (uint8_t*)calloc(w->n_slots, 1);
-    if (!w->slot_dirty || !w->scan_flags || !w->block_flags) { gcmesh_world_destroy(w); return fail(GC_ERR_ARG, "out of host memory"); }
+    w->col_smax = (int16_t*)malloc(sizeof(int16_t) * w->n_cols);
+    if (!w->slot_dirty || !w->scan_flags || !w->block_flags || !w->col_smax) { gcmesh_world_destroy(w); return fail(GC_ERR_ARG, "out of host memory"); }
     w->light_zero = true;
     int st = GC_OK;
     if (st == GC_OK) st = encode_map(ctx, &w->maps.blocks_slab, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w->d_blocks, w->n_slots);
@@ -447,7 +450,7 @@ int gcmesh_world_destroy(GcWorld* w)
     if (w->edit_graph) cudaGraphExecDestroy(w->edit_graph);
     if (w->h_edit_coords) cudaFreeHost(w->h_edit_coords);
     if (w->h_edit_count) cudaFreeHost(w->h_edit_count);
-    free(w->slot_dirty); free(w->scan_flags); free(w->block_flags);
+    free(w->slot_dirty); free(w->scan_flags); free(w->block_flags); free(w->col_smax);
     delete w;
     return GC_OK;
 }
@@ -557,14 +560,45 @@ static bool all_zero(const void* p, size_t bytes)
 // A sunlight brick that lies wholly at or above its column's surface is never read: every cell there reads 15 whatever
 // is stored (GetSunlight, Lighting.cpp:69-79; light_pair_of in mesh_core.cuh).  With the surface map at hand such bricks
 // are classified "nothing to transfer" without being scanned — in a terrain world that is most of the sky.
-static inline bool sun_brick_never_read(const uint8_t* surface, size_t slot)
+// highest entry of a column's surface map, computed once per scan by whoever asks first (col_smax: -1 = not yet)
+static inline int column_smax(GcWorld* w, const uint8_t* surface, size_t col)
+{
+    int v = w->col_smax[col];
+    if (v >= 0) return v;
+    const uint8_t* s = surface + col * GC_CHUNK_SIZE_2;
+    v = 0;
+    for (int i = 0; i < GC_CHUNK_SIZE_2; i++) v = s[i] > v ? s[i] : v;
+    w->col_smax[col] = (int16_t)v;
+    return v;
+}
+
+static inline bool sun_brick_never_read(GcWorld* w, const uint8_t* surface, size_t slot)
 {
     if (!surface) return false;
-    const uint8_t* s = surface + (slot >> 2) * GC_CHUNK_SIZE_2;
-    const unsigned y0 = (unsigned)(slot & 3) * GC_CHUNK_SIZE_V;
-    for (int i = 0; i < GC_CHUNK_SIZE_2; i++)
-        if (s[i] > y0) return false;
-    return true;
+    return (int)(slot & 3) * GC_CHUNK_SIZE_V >= column_smax(w, surface, slot >> 2);
+}
+
+// With GC_WORLD_SURFACE_BOUNDS_BLOCKS (every block of a column lies below its surface entry, layer y = 255 aside): a quad
+// reads light within one voxel of its block, so at or below the highest surface entry of the block's column; an all-AIR
+// brick that starts above the highest entry of the 3 x 3 columns around it is out of every quad's reach — neither of its
+// light arrays is scanned or transferred.  (Bricks of the top row are left to the neighbourhood rule: a block on layer 255,
+// which the surface map does not see, lights cells of that row.)
+static inline bool light_out_of_reach(GcWorld* w, const uint8_t* surface, size_t slot)
+{
+    if (!w->surface_bounds_blocks || !surface || w->block_flags[slot]) return false;
+    const int cy = (int)(slot & 3);
+    if (cy >= GC_WORLD_CHUNK_HEIGHT - 1) return false;
+    const int col = (int)(slot >> 2), cx = col % w->size_x, cz = col / w->size_x;
+    int top = 0;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dx = -1; dx <= 1; dx++)
+        {
+            const int nx = cx + dx, nz = cz + dz;
+            if (nx < 0 || nx >= w->size_x || nz < 0 || nz >= w->size_z) continue;
+            const int v = column_smax(w, surface, (size_t)nz * w->size_x + nx);
+            top = v > top ? v : top;
+        }
+    return cy * GC_CHUNK_SIZE_V > top;
 }
 
 // The scan of a window runs in two stages per brick.  Stage A classifies the block ids.  Stage B classifies the two light
@@ -580,7 +614,7 @@ static inline bool sun_brick_never_read(const uint8_t* surface, size_t slot)
 static inline void scan_blocks(GcWorld* w, size_t slot, const uint16_t* blocks, const uint8_t* surface)
 {
     const uint16_t* b = blocks + slot * GC_CHUNK_SIZE_3;
-    if (w->surface_bounds_blocks && sun_brick_never_read(surface, slot))
+    if (w->surface_bounds_blocks && sun_brick_never_read(w, surface, slot))
     {
         uint8_t any = 0;
         if ((slot & 3) == GC_WORLD_CHUNK_HEIGHT - 1)
@@ -611,9 +645,9 @@ static inline void scan_lights(GcWorld* w, size_t slot, const uint8_t* sunlight,
 {
     uint8_t f = w->block_flags[slot];
     static const bool skip_rule = []() { const char* e = getenv("GCMESH_SCAN_LIGHT_SKIP"); return !(e && e[0] == '0'); }();
-    if (!skip_rule || !brick_neighbourhood_is_air(w, slot))
+    if (!skip_rule || !(brick_neighbourhood_is_air(w, slot) || light_out_of_reach(w, surface, slot)))
     {
-        if (!sun_brick_never_read(surface, slot) && !all_zero(sunlight + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 2;
+        if (!sun_brick_never_read(w, surface, slot) && !all_zero(sunlight + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 2;
         if (!all_zero(block_light + slot * GC_CHUNK_SIZE_3, GC_CHUNK_SIZE_3)) f |= 4;
     }
     w->scan_flags[slot] = f;
@@ -635,6 +669,7 @@ struct ScanPlan
         : w(w_), blocks(b), sunlight(s), block_light(l), surface(sf), slots_per_row((size_t)w_->size_x * GC_WORLD_CHUNK_HEIGHT), rows(w_->size_z),
           a_remaining((size_t)w_->size_z), next(0)
     {
+        memset(w->col_smax, 0xFF, sizeof(int16_t) * w->n_cols);
         for (auto& r : a_remaining) r.store((int)slots_per_row);
     }
 
@@ -689,28 +724,57 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
                         bool mapped, cudaStream_t s)
 {
     const size_t s_begin = (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, s_end = (size_t)cz1 * w->size_x * GC_WORLD_CHUNK_HEIGHT;
+    const size_t c_begin = s_begin / GC_WORLD_CHUNK_HEIGHT, c_end = s_end / GC_WORLD_CHUNK_HEIGHT;
     uint32_t* items = w->h_items + s_begin * 3;   // this row range's own part of the pinned work list
     w->light_zero = false;
     int n_items = 0;
+    // Non-zero arrays.  A terrain world's non-zero bricks lie at the same height in column after column, and a column's four
+    // bricks are consecutive slots: the same array of brick cy of k consecutive columns is a strided block — k rows of one
+    // brick array, four brick arrays apart — that ONE 2-D copy moves with the copy engine at full link speed in large
+    // requests.  (Measured: the GPU pull kernel reads pinned host memory at 51 GB/s alone but 31 GB/s while the meshes of the
+    // previous strip travel the other way — its many small read requests share the upstream direction with that data — where
+    // copy-engine traffic keeps 47 GB/s each way; one copy per array gets 20 GB/s.)  Short runs go to the pull kernel.
+    static const int env_run = []() { const char* e = getenv("GCMESH_COPY_RUN"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+    const int min_run = w->copy_run > 0 ? w->copy_run : env_run;
+    for (int a = 0; a < 3; a++)
+    {
+        const size_t bytes = a == 0 ? (size_t)GC_CHUNK_SIZE_3 * 2 : (size_t)GC_CHUNK_SIZE_3;
+        const uint8_t* src0 = a == 0 ? (const uint8_t*)blocks : (a == 1 ? sunlight : block_light);
+        uint8_t* dst0 = a == 0 ? (uint8_t*)w->d_blocks : (a == 1 ? w->d_sun : w->d_light);
+        for (int cy = 0; cy < GC_WORLD_CHUNK_HEIGHT; cy++)
+        {
+            size_t col = c_begin;
+            while (col < c_end)
+            {
+                if (!(w->scan_flags[col * GC_WORLD_CHUNK_HEIGHT + cy] & (1 << a))) { col++; continue; }
+                size_t run = 1;
+                while (col + run < c_end && (w->scan_flags[(col + run) * GC_WORLD_CHUNK_HEIGHT + cy] & (1 << a))) run++;
+                w->upload_bytes += bytes * run;
+                const size_t first = col * GC_WORLD_CHUNK_HEIGHT + cy;
+                if ((int)run >= min_run || !mapped)
+                {
+                    const cudaError_t e = run == 1 ? cudaMemcpyAsync(dst0 + first * bytes, src0 + first * bytes, bytes, cudaMemcpyHostToDevice, s)
+                                                   : cudaMemcpy2DAsync(dst0 + first * bytes, bytes * GC_WORLD_CHUNK_HEIGHT, src0 + first * bytes, bytes * GC_WORLD_CHUNK_HEIGHT,
+                                                                       bytes, run, cudaMemcpyHostToDevice, s);
+                    if (e != cudaSuccess) return -1;
+                }
+                else
+                    for (size_t k = 0; k < run; k++) items[n_items++] = (uint32_t)((first + k * GC_WORLD_CHUNK_HEIGHT) * 4 + a);
+                col += run;
+            }
+        }
+    }
+    // arrays that held data on the device and are zero now
     for (size_t slot = s_begin; slot < s_end; slot++)
     {
-        const uint8_t f = w->scan_flags[slot], dirty = w->slot_dirty[slot];
-        for (int a = 0; a < 3; a++)
-        {
-            const size_t bytes = a == 0 ? (size_t)GC_CHUNK_SIZE_3 * 2 : (size_t)GC_CHUNK_SIZE_3;
-            uint8_t* dst = a == 0 ? (uint8_t*)w->d_blocks + slot * bytes : (a == 1 ? w->d_sun : w->d_light) + slot * bytes;
-            if (f & (1 << a))
+        const uint8_t f = w->scan_flags[slot], stale = w->slot_dirty[slot] & ~f;
+        for (int a = 0; a < 3 && stale; a++)
+            if (stale & (1 << a))
             {
-                w->upload_bytes += bytes;
-                if (mapped) items[n_items++] = (uint32_t)(slot * 4 + a);
-                else
-                {
-                    const uint8_t* src = a == 0 ? (const uint8_t*)blocks + slot * bytes : (a == 1 ? sunlight : block_light) + slot * bytes;
-                    if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
-                }
+                const size_t bytes = a == 0 ? (size_t)GC_CHUNK_SIZE_3 * 2 : (size_t)GC_CHUNK_SIZE_3;
+                uint8_t* dst = a == 0 ? (uint8_t*)w->d_blocks + slot * bytes : (a == 1 ? w->d_sun : w->d_light) + slot * bytes;
+                if (cudaMemsetAsync(dst, 0, bytes, s) != cudaSuccess) return -1;
             }
-            else if (dirty & (1 << a)) { if (cudaMemsetAsync(dst, 0, bytes, s) != cudaSuccess) return -1; }
-        }
         w->slot_dirty[slot] = f;
     }
     if (n_items)
@@ -772,6 +836,7 @@ int gcmesh_world_set_option(GcWorld* w, int option, int value)
 {
     if (!w) return fail(GC_ERR_ARG, "world is null");
     if (option == GC_WORLD_SURFACE_BOUNDS_BLOCKS) { w->surface_bounds_blocks = value != 0; return GC_OK; }
+    if (option == GC_WORLD_COPY_RUN) { if (value < 0) return fail(GC_ERR_ARG, "run length must not be negative"); w->copy_run = value; return GC_OK; }
     return fail(GC_ERR_ARG, "unknown world option");
 }
 
@@ -1500,6 +1565,8 @@ static int submit_impl(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n
         halo.peer[0] = w->halo_peer[0]; halo.peer[1] = w->halo_peer[1];
         halo.flags = w->d_halo_flags;
         halo.wait_ns = halo_wait_ns();
+        static const int debug_env = getenv("GCMESH_HALO_DEBUG") ? atoi(getenv("GCMESH_HALO_DEBUG")) : 0;
+        halo.debug = debug_env;
     }
     // the pinned coordinate staging buffer is reused: wait until the previous submission has consumed it (its kernel
     // may still be queued or running, so back-to-back submissions keep the GPU busy)

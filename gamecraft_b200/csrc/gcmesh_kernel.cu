@@ -186,13 +186,14 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
 __device__ void halo_push_task(const HaloFused& h, int task, int* s_flag)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
+    if (h.debug & 8) return;
     const int T = h.tasks_per_dir;
     int d = task / T;
     const int part = task % T;
     if (!h.peer[0].connected) d = 1;                       // one neighbour only: every task is for it
     const HaloPeer& peer = h.peer[d];
     // the neighbour must have entered this exchange: until then its previous kernel may still read its halo rows
-    if (tid == 0) *s_flag = halo_wait_at_least(h.flags, d == 0 ? HF_READY_FROM_DOWN : HF_READY_FROM_UP, h.serial, h.wait_ns, peer.flags) ? 1 : 0;
+    if (tid == 0) *s_flag = ((h.debug & 4) || halo_wait_at_least(h.flags, d == 0 ? HF_READY_FROM_DOWN : HF_READY_FROM_UP, h.serial, h.wait_ns, peer.flags)) ? 1 : 0;
     __syncthreads();
     const bool ready = *s_flag != 0;
     __syncthreads();
@@ -200,8 +201,9 @@ __device__ void halo_push_task(const HaloFused& h, int task, int* s_flag)
     const int z = d == 0 ? 0 : 31;
     const int src_row = h.send_row[d];
     const int planes = h.size_x * 4;
-    const int p0 = (int)((long long)planes * part / T), p1 = (int)((long long)planes * (part + 1) / T);
+    const int p0 = planes * part / T, p1 = planes * (part + 1) / T;      // (planes * T stays far below 2^31: size_x <= 16 384 columns)
     const int per_plane = 8192 / 16;                       // uint4 per plane: 256 blocks, 128 sunlight, 128 blockLight
+    if (!(h.debug & 1))
     for (int i = p0 * per_plane + tid; i < p1 * per_plane; i += nt)
     {
         const int plane = i / per_plane, q = i % per_plane;
@@ -213,6 +215,7 @@ __device__ void halo_push_task(const HaloFused& h, int task, int* s_flag)
         else reinterpret_cast<uint4*>(peer.light + dst)[q - 384] = reinterpret_cast<const uint4*>(h.light + src)[q - 384];
     }
     const int c0 = (p0 + 3) >> 2, c1 = (p1 + 3) >> 2;      // columns whose first plane lies in this share
+    if (!(h.debug & 1))
     for (int i = c0 * 8 + tid; i < c1 * 8; i += nt)
     {
         const int cx = i >> 3, q = i & 7;
@@ -314,7 +317,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
 
     // fused exchange: tell both neighbours that this rank has entered exchange `serial` — its previous kernel, the last reader
     // of its halo rows, has finished (stream order), so they may be overwritten
-    if (kHalo && blockIdx.x == 0 && tid < 2 && p.halo.peer[tid].connected)
+    if (kHalo && blockIdx.x == 0 && tid < 2 && p.halo.peer[tid].connected && !(p.halo.debug & 4))
         halo_store_release_sys(p.halo.peer[tid].flags + (tid == 0 ? HF_READY_FROM_UP : HF_READY_FROM_DOWN), p.halo.serial);
     uint32_t halo_seen = 0, halo_failed = 0;   // bit d: the plane from neighbour d is known to have arrived / was given up on (CTA-uniform)
 
@@ -343,6 +346,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             // a chunk of the first / last owned row reads the neighbour's plane: wait (once per CTA and side) until it has arrived
             uint32_t need = ((cz == p.halo.send_row[0] && p.halo.peer[0].connected) ? 1u : 0u) | ((cz == p.halo.send_row[1] && p.halo.peer[1].connected) ? 2u : 0u);
             need &= ~halo_seen;
+            if (p.halo.debug & 2) need = 0;
             if (need)
             {
                 int* s_halo_ok = &s_ctx->halo_ok;
@@ -919,7 +923,8 @@ cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int gri
 {
     cudaError_t e0 = configure_mesh_kernel();
     if (e0 != cudaSuccess) return e0;
-    if (p.halo.enabled) gc_mesh_kernel<false, true><<<grid, NT, kSmemBytes, stream>>>(p, maps);   // (no profiling instantiation of the exchange form)
+    static const bool force_halo = getenv("GCMESH_FORCE_HALO_KERNEL") != nullptr;
+    if (p.halo.enabled || force_halo) gc_mesh_kernel<false, true><<<grid, NT, kSmemBytes, stream>>>(p, maps);   // (no profiling instantiation of the exchange form)
     else if (p.prof) gc_mesh_kernel<true, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
     else gc_mesh_kernel<false, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
     return cudaGetLastError();

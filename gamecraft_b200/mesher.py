@@ -28,6 +28,7 @@ CHUNK_OVERFLOW = 1
 CHUNK_NO_SPACE = 2
 CHUNK_HALO_MISSING = 4
 WORLD_SURFACE_BOUNDS_BLOCKS = 1      # GC_WORLD_SURFACE_BOUNDS_BLOCKS
+WORLD_COPY_RUN = 2                   # GC_WORLD_COPY_RUN
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -143,8 +143,10 @@ int gcmesh_world_upload_sparse(GcWorld* world, const uint16_t* blocks, const uin
  * gcmesh_world_upload_sparse / gcmesh_mesh_host are ComputeSurface of the block ids handed with them (Lighting.cpp:5-26 —
  * what ChunkGroup::surface holds for every pre-processed column; a stale entry is only ever too high).  The host scan then
  * takes a brick lying wholly at or above its column's highest entry for AIR without reading it (layer y = 255, which
- * ComputeSurface does not look at, is still read). */
-enum { GC_WORLD_SURFACE_BOUNDS_BLOCKS = 1 };
+ * ComputeSurface does not look at, is still read).
+ * GC_WORLD_COPY_RUN (default 0 = 4): sparse uploads move the same brick array of at least this many consecutive columns
+ * with one strided copy-engine copy; shorter runs are pulled by a GPU kernel out of pinned host memory (a huge value: always). */
+enum { GC_WORLD_SURFACE_BOUNDS_BLOCKS = 1, GC_WORLD_COPY_RUN = 2 };
 int gcmesh_world_set_option(GcWorld* world, int option, int value);
 /* Kernels launched by the last gcmesh_world_upload_sparse call. */
 int gcmesh_world_upload_launches(const GcWorld* world);

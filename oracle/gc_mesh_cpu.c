@@ -288,7 +288,7 @@ typedef struct OrJob
 static void or_pin_self(int t)
 {
     cpu_set_t all, one;
-    if (sched_getaffinity(0, sizeof(all), &all) != 0) return;
+    if (getenv("GCREF_NO_PIN") || sched_getaffinity(0, sizeof(all), &all) != 0) return;
     const int n = CPU_COUNT(&all);
     if (n <= 0) return;
     int want = t % n;

@@ -405,7 +405,7 @@ double gcref_bench_build(GcRefWorld* w, const int32_t* coords, int n, int thread
             // scheduler happens to put, or move, its threads
             {
                 cpu_set_t all, one;
-                if (sched_getaffinity(0, sizeof(all), &all) == 0 && CPU_COUNT(&all) > 0)
+                if (!getenv("GCREF_NO_PIN") && sched_getaffinity(0, sizeof(all), &all) == 0 && CPU_COUNT(&all) > 0)
                 {
                     int want = t % CPU_COUNT(&all);
                     for (int c = 0; c < CPU_SETSIZE; c++)

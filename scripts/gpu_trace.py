@@ -11,6 +11,8 @@ class P:
     blocks, sun, light, surface = [t.numpy() for t in pin]
 ctx = mesher.Context(0)
 world = mesher.World(ctx, 36, 36)
+if os.environ.get("HINT"):
+    world.set_option(mesher.WORLD_SURFACE_BOUNDS_BLOCKS, 1)
 batch = mesher.Batch(ctx, len(coords), 4_000_000)
 world.upload_sparse(P); ctx.synchronize(); batch.submit(world, coords).wait(); desc, q = batch.results()
 hv = torch.empty((q * 4, 12), dtype=torch.uint8).pin_memory().numpy(); hi = torch.empty(q * 6, dtype=torch.uint16).pin_memory().numpy()

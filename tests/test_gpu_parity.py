@@ -303,9 +303,13 @@ def test_gpu_sparse_upload_equals_dense(ctx):
         size_x, size_z = 5, 5
         blocks, sun, light, surface = [t.numpy() for t in pins]
 
-    world2 = mesher.World(ctx, 5, 5).upload_sparse(P)                      # pinned arrays: GPU pull kernel
+    world2 = mesher.World(ctx, 5, 5).set_option(mesher.WORLD_COPY_RUN, 1 << 20).upload_sparse(P)   # pinned arrays, every array through the GPU pull kernel
     assert world2.upload_launches() == 1
     check(world2)
+    world4 = mesher.World(ctx, 5, 5).set_option(mesher.WORLD_COPY_RUN, 2).upload_sparse(P)         # runs of two or more columns as strided copies, the rest pulled
+    assert 0 < world4.upload_bytes() <= world2.upload_bytes()               # same arrays, a shorter (or no) pull list
+    check(world4)
+    world4.close()
     hint = (P.blocks.any(axis=1) * 1 + P.sun.any(axis=1) * 2 + P.light.any(axis=1) * 4).astype(np.uint8)
     world3 = mesher.World(ctx, 5, 5).upload_sparse(P, nonzero_hint=hint)   # caller's hint instead of the scan
     check(world3)
@@ -397,6 +401,33 @@ def test_gpu_surface_bounds_blocks_option(ctx):
     with pytest.raises(mesher.GcMeshError):
         world.set_option(99, 1)
     batch.close(); world.close()
+
+    # light of an all-AIR brick that starts above the highest surface entry of the 3 x 3 columns around it is out of every
+    # quad's reach (the top row of bricks aside): with the option such arrays are neither scanned nor moved — junk there
+    # must not change a byte (forest terrain: everything from y = 64 up)
+    f = util.HostWorld(6, 6).build("forest", 31)
+    fcoords = f.interior_chunks(1)
+    fo = ob.OracleWorld(f)
+    fwant = [fo.build_chunk(*c) for c in fcoords]
+    smax = f.surface.reshape(6, 6, -1).max(axis=2).astype(int)                              # [cz][cx]
+    far = 0
+    for cz in range(6):
+        for cx in range(6):
+            top = smax[max(cz - 1, 0):cz + 2, max(cx - 1, 0):cx + 2].max()
+            for cy in range(3):
+                sl = f.slot(cx, cy, cz)
+                if cy * 64 > top and not f.blocks[sl].any():
+                    f.sun[sl] = 5; f.light[sl] = 9
+                    far += 1
+    assert far >= 36
+    fworld = mesher.World(ctx, 6, 6).set_option(mesher.WORLD_SURFACE_BOUNDS_BLOCKS, 1).upload_sparse(f)
+    moved = fworld.upload_bytes()
+    for m, x, c in zip(mesher.rebuild_chunks(fworld, fcoords), fwant, fcoords):
+        util.assert_same_mesh(m, x, str(c))
+    fworld.close()
+    fworld = mesher.World(ctx, 6, 6).upload_sparse(f)                                       # without the option the junk is moved
+    assert fworld.upload_bytes() >= moved + 36 * 65536                                       # (blockLight of the 36 bricks of row cy = 1)
+    fworld.close()
 
 
 def test_gpu_work_order_does_not_change_results(ctx):
