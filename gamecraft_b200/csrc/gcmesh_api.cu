@@ -94,7 +94,8 @@ struct GcContext
     LightRules* d_light_rules;
     int use_tma;
     // gcmesh_mesh_host pipeline
-    cudaStream_t upload_stream, download_stream;
+    cudaStream_t upload_stream, upload_stream2, download_stream;   // (upload_stream2: the light arrays of a strip travel beside its block ids)
+    cudaEvent_t ev_up2;
     cudaEvent_t ev_fork, ev_join, ev_uploaded[64], ev_meshed[64];
     unsigned long long* h_strip_cursor;   // pinned [64]
 };
@@ -317,6 +318,8 @@ int gcmesh_create(int device, void* stream, GcContext** out)
 
     e = cudaMalloc(&ctx->d_tables, sizeof(DeviceTables));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->upload_stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_up2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->download_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
@@ -346,7 +349,8 @@ int gcmesh_destroy(GcContext* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_tables); cudaFree(ctx->d_light_rules);
-    cudaStreamDestroy(ctx->upload_stream); cudaStreamDestroy(ctx->download_stream);
+    cudaStreamDestroy(ctx->upload_stream); cudaStreamDestroy(ctx->upload_stream2); cudaStreamDestroy(ctx->download_stream);
+    cudaEventDestroy(ctx->ev_up2);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (int i = 0; i < 64; i++) { cudaEventDestroy(ctx->ev_uploaded[i]); cudaEventDestroy(ctx->ev_meshed[i]); }
     cudaFreeHost(ctx->h_strip_cursor);
@@ -383,6 +387,7 @@ int gcmesh_synchronize(GcContext* ctx)
     GC_CUDA(cudaSetDevice(ctx->device));
     GC_CUDA(cudaStreamSynchronize(ctx->stream));
     GC_CUDA(cudaStreamSynchronize(ctx->upload_stream));
+    GC_CUDA(cudaStreamSynchronize(ctx->upload_stream2));
     GC_CUDA(cudaStreamSynchronize(ctx->download_stream));
     return GC_OK;
 }
@@ -721,8 +726,11 @@ static int scan_threads(int threads)
 // Enqueue on `s` the upload of rows [cz0, cz1) according to w->scan_flags: non-zero arrays are pulled by the GPU (or copied
 // one by one when the host arrays are not pinned), arrays that turned zero are cleared.  Returns kernels launched (< 0: error).
 static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, const uint8_t* sunlight, const uint8_t* block_light,
-                        bool mapped, cudaStream_t s)
+                        bool mapped, cudaStream_t s, cudaStream_t s_light = nullptr)
 {
+    // s_light: a second stream for the strided copies of the two light arrays — a strided copy pays per row, two of them
+    // side by side (two copy engines) keep the link busy.  The caller orders s_light before and after this call.
+    if (!s_light) s_light = s;
     const size_t s_begin = (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, s_end = (size_t)cz1 * w->size_x * GC_WORLD_CHUNK_HEIGHT;
     const size_t c_begin = s_begin / GC_WORLD_CHUNK_HEIGHT, c_end = s_end / GC_WORLD_CHUNK_HEIGHT;
     uint32_t* items = w->h_items + s_begin * 3;   // this row range's own part of the pinned work list
@@ -753,9 +761,10 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
                 const size_t first = col * GC_WORLD_CHUNK_HEIGHT + cy;
                 if ((int)run >= min_run || !mapped)
                 {
-                    const cudaError_t e = run == 1 ? cudaMemcpyAsync(dst0 + first * bytes, src0 + first * bytes, bytes, cudaMemcpyHostToDevice, s)
+                    cudaStream_t sc = a == 0 ? s : s_light;
+                    const cudaError_t e = run == 1 ? cudaMemcpyAsync(dst0 + first * bytes, src0 + first * bytes, bytes, cudaMemcpyHostToDevice, sc)
                                                    : cudaMemcpy2DAsync(dst0 + first * bytes, bytes * GC_WORLD_CHUNK_HEIGHT, src0 + first * bytes, bytes * GC_WORLD_CHUNK_HEIGHT,
-                                                                       bytes, run, cudaMemcpyHostToDevice, s);
+                                                                       bytes, run, cudaMemcpyHostToDevice, sc);
                     if (e != cudaSuccess) return -1;
                 }
                 else
@@ -1683,13 +1692,14 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         for (int i = 0; i < n; i++) { const int pos = sub[key(i)]++; perm[pos] = i; b->h_coords[pos] = coords[i]; }
     }
 
-    cudaStream_t sm = ctx->stream, su = ctx->upload_stream, sd = ctx->download_stream;
+    cudaStream_t sm = ctx->stream, su = ctx->upload_stream, su2 = ctx->upload_stream2, sd = ctx->download_stream;
     const bool mapped = host_arrays_mapped(blocks, sunlight, block_light);
     b->n = n; b->launches = 0; w->launches = 0;
     w->upload_bytes = w->n_cols * GC_CHUNK_SIZE_2 + sizeof(GcChunkCoord) * (size_t)n;
     b->order_n = 0;                                           // d_coords is about to hold the strip-sorted list
     GC_CUDA(cudaEventRecord(ctx->ev_fork, sm));
     GC_CUDA(cudaStreamWaitEvent(su, ctx->ev_fork, 0));        // the upload overwrites what earlier work on the context stream read
+    GC_CUDA(cudaStreamWaitEvent(su2, ctx->ev_fork, 0));
     GC_CUDA(cudaStreamWaitEvent(sd, ctx->ev_fork, 0));
     GC_CUDA(cudaMemcpyAsync(b->d_coords, b->h_coords, sizeof(GcChunkCoord) * (size_t)n, cudaMemcpyHostToDevice, su));
     GC_CUDA(cudaMemcpyAsync(w->d_surface, surface, w->n_cols * GC_CHUNK_SIZE_2, cudaMemcpyHostToDevice, su));
@@ -1727,6 +1737,9 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         return GC_OK;
     };
 
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_scan_done[64] = { 0 };                           // (trace) when the scan threads finished each strip
     // the zero-scan runs on background threads over the whole window, slots in ascending order; the pipeline below
     // consumes it strip by strip (remaining[k] = slots of strip k still to classify)
     const size_t slots_per_row = (size_t)w->size_x * GC_WORLD_CHUNK_HEIGHT;
@@ -1746,24 +1759,28 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         if (threads <= 0 && nt > 1) nt--;
         auto work = [&, slots_per_row, kStripRows]()
         {
-            plan.work([&](size_t slot) { remaining[(slot / slots_per_row) / kStripRows].fetch_sub(1, std::memory_order_release); });
+            plan.work([&](size_t slot)
+            {
+                const size_t k = (slot / slots_per_row) / kStripRows;
+                if (remaining[k].fetch_sub(1, std::memory_order_release) == 1) t_scan_done[k] = now_ms();
+            });
         };
         for (int t = 0; t < nt; t++) pool.emplace_back(work);
     }
     struct Joiner { std::vector<std::thread>& p; ~Joiner() { for (auto& t : p) if (t.joinable()) t.join(); } } joiner{ pool };
 
     const bool trace = getenv("GCMESH_TRACE") != nullptr;
-    const auto t_begin = std::chrono::steady_clock::now();
-    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     double t_scanned[64], t_enqueued[64];
     for (int k = 0; k < n_strips; k++)
     {
         const int cz0 = k * kStripRows, cz1 = cz0 + kStripRows < w->size_z ? cz0 + kStripRows : w->size_z;
         if (!nonzero_hint) while (remaining[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
         t_scanned[k] = now_ms();
-        const int launched = enqueue_rows(w, cz0, cz1, blocks, sunlight, block_light, mapped, su);
+        const int launched = enqueue_rows(w, cz0, cz1, blocks, sunlight, block_light, mapped, su, su2);
         if (launched < 0) return fail(GC_ERR_CUDA, "sparse upload", cudaGetErrorString(cudaGetLastError()));
         w->launches += launched;
+        GC_CUDA(cudaEventRecord(ctx->ev_up2, su2));
+        GC_CUDA(cudaStreamWaitEvent(su, ctx->ev_up2, 0));
         GC_CUDA(cudaEventRecord(ctx->ev_uploaded[k], su));
         t_enqueued[k] = now_ms();
         if (k >= 1) { const int st = mesh_strip(k - 1); if (st != GC_OK) return st; }
@@ -1788,7 +1805,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         {
             float up = 0, me = 0;
             cudaEventElapsedTime(&up, b->ev_start, ctx->ev_uploaded[k]); cudaEventElapsedTime(&me, b->ev_start, ctx->ev_meshed[k]);
-            fprintf(stderr, "  strip %2d: scanned %.2f  enqueued %.2f | uploaded %.2f  meshed %.2f (device, since start)\n", k, t_scanned[k], t_enqueued[k], up, me);
+            fprintf(stderr, "  strip %2d: scan done %.2f  seen %.2f  enqueued %.2f | uploaded %.2f  meshed %.2f (device, since start)\n", k, t_scan_done[k], t_scanned[k], t_enqueued[k], up, me);
         }
         float dn = 0; cudaEventElapsedTime(&dn, b->ev_start, b->ev_stop);
         fprintf(stderr, "  last kernel done %.2f\n", dn);
