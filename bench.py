@@ -73,6 +73,7 @@ def parse_args():
     ap.add_argument("--no-surface-hint", action="store_true", help="e2e: scan every block brick (GC_WORLD_SURFACE_BOUNDS_BLOCKS off)")
     ap.add_argument("--no-weak-leg", action="store_true", help="N > 1 default run: skip the weak-scaling (forest4096 per rank) second leg")
     ap.add_argument("--no-preprocess", action="store_true", help="skip the surface + light-fill leg (SURVEY 8(f1))")
+    ap.add_argument("--no-stress", action="store_true", help="skip the uncapped 196 608-quads-per-chunk leg (BASELINE config 4, stress variant)")
     return ap.parse_args()
 
 
@@ -475,6 +476,58 @@ def edit_path_leg(ctx, world, host, args):
                     "gcmesh_wait + gcmesh_batch_download"}
 
 
+def stress_leg(ctx, args):
+    """BASELINE config 4, the stress variant: full 3-D checkerboard chunks — 196 608 quads each, twenty
+    times the reference's cap — through an uncapped batch (GC_BATCH_UNCAPPED: 32-bit indices).  No parity claim against the
+    reference (it asserts at its cap); checked against the oracle's traversal with the cap lifted on a sample of chunks."""
+    import torch
+    from gamecraft_b200 import mesher
+    from gamecraft_b200.worldgen import HostWorld
+
+    cols = 8                                                     # 8 x 8 meshed columns x 4 = 256 chunks, 50.3 M quads, 3.6 GB of output
+    host = HostWorld(cols + 2, cols + 2).build("stress", 1)
+    coords = host.interior_chunks(1)
+    n = len(coords)
+    world = mesher.World(ctx, host.size_x, host.size_z).upload(host)
+    batch = mesher.Batch(ctx, n, n * 196608, uncapped=True)
+    for _ in range(3):
+        batch.submit(world, coords)
+    batch.wait()
+    k = max(1, min(args.steps, 10))
+    ms = []
+    for _ in range(k):
+        batch.submit(world, coords).wait()
+        ms.append(batch.elapsed_ms())
+    desc, q = batch.results()
+    kms = float(np.mean(ms))
+    out_bytes = q * (48 + 24)
+    alg = n * ALG_BYTES_PER_CHUNK + out_bytes
+    peak, peak_src = hbm_peak()
+    checked, bad = 0, 0
+    if not args.no_parity:
+        from oracle import binding as ob
+
+        o = ob.OracleWorld(host)
+        verts, idx = batch.download()
+        for i in range(0, n, max(n // 8, 1)):
+            d = desc[i]
+            want = o.build_chunk_uncapped(*coords[i])
+            qb, nq = int(d["quad_base"]), int(d["quads"])
+            ok = nq == want.quads and np.array_equal(verts[qb * 4: qb * 4 + nq * 4], want.vertices)
+            for t in range(5):
+                ok = ok and np.array_equal(idx[qb * 6 + int(d["index_offset"][t]): qb * 6 + int(d["index_offset"][t]) + int(d["index_count"][t])], want.indices[t])
+            checked += 1; bad += 0 if ok else 1
+        del verts, idx
+    flags = int((desc["flags"] != 0).sum())
+    batch.close(); world.close()
+    return {"workload": "stress196608", "chunks": n, "quads_per_chunk": q / n, "kernel_ms": kms, "chunks_per_s": n / (kms * 1e-3), "quads_per_s": q / (kms * 1e-3),
+            "output_gbs": out_bytes / (kms * 1e-3) / 1e9, "index_bits": 32, "chunks_flagged": flags,
+            "roofline": {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (kms * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": alg, "note": "262 424 B in + 72 B per quad out (48 B of vertices, six uint32 indices)", "traffic": None},
+            "checked_against_uncapped_oracle": {"chunks": checked, "mismatches": bad},
+            "note": "no reference behaviour (the reference asserts at 10 000 quads per chunk, WorldRender.cpp:558): reported separately, no parity claim"}
+
+
 def cpu_reference_run(host, coords, seconds: float, threads: int | None = None):
     """Times the reference CPU mesher on the host cores: oracle/_ref (the reference compiled verbatim) when that
     library travelled with the repo, else the plain-C port.  Returns the cpu_baseline object."""
@@ -570,13 +623,24 @@ def scribble_margin_rows(world, host, rows, seed):
     world.ctx.synchronize()
 
 
+_T0 = time.time()
+
+
+def log(rank, msg):
+    """Progress on stderr (GCBENCH_VERBOSE=1): which stage a rank is in, seconds since the process started."""
+    if os.environ.get("GCBENCH_VERBOSE"):
+        print("[bench %6.1fs rank %d] %s" % (time.time() - _T0, rank, msg), file=sys.stderr, flush=True)
+
+
 def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs):
     """One workload: device-resident timing, parity of every chunk against the oracle, kernel-only timing, and (full_legs) the
     end-to-end and §8(f) legs.  Returns the JSON line (rank 0) or None."""
     from gamecraft_b200 import mesher
 
+    log(rank, "building the %s window" % workload)
     host, coords, gen_s = make_world(workload, rank, world_size)
     n = len(coords)
+    log(rank, "window %dx%d columns, %d chunks (%.1f s)" % (host.size_x, host.size_z, n, gen_s))
 
     # an explicit (non-default) stream: the library launches on it, torch's events and NCCL ops are ordered on it
     stream = torch.cuda.Stream()
@@ -598,6 +662,7 @@ def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs
 
     world.upload(Pinned)
     ctx.synchronize()
+    log(rank, "window on the device")
 
     def barrier():
         if world_size > 1:
@@ -669,6 +734,7 @@ def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs
         b.submit(world, coords)
         return launches + 1
 
+    log(rank, "exchange: %s" % exchange_kind)
     # size the arenas from a first pass (with its exchange: every rank steps the same number of times)
     probe = mesher.Batch(ctx, n, n * mesher.MAX_QUADS // 8 + 1)
     step(probe); probe.wait()
@@ -695,6 +761,7 @@ def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs
             cold_ms.append(cold.elapsed_ms())
             cold.close()
 
+    log(rank, "%d quads; timing" % total_quads)
     batch = mesher.Batch(ctx, n, total_quads + 1)
     batch.set_timing(False)                              # nothing but the launch between back-to-back kernels
 
@@ -718,6 +785,7 @@ def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs
     total_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
 
+    log(rank, "timed region done: %.3f ms per step on this rank" % (total_ms / args.steps))
     # ---- parity: every chunk of the last timed submission, byte for byte, against the oracle of this rank's (correct) window ----
     parity = None
     desc, tq = batch.results()
@@ -749,6 +817,7 @@ def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs
             parity["boundary_row_mismatches"] = a[4]
             parity["halo_rows_scribbled_before_first_exchange"] = True
 
+    log(rank, "parity: %s" % (parity and {k: parity[k] for k in ("chunks", "mismatches")}))
     # mean duration of the mesh kernel alone (the library's own events bracket exactly the launch)
     batch.set_timing(True)
     kernel_ms = []
@@ -775,6 +844,7 @@ def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs
     # streams back.  "e2e_dense" is the same with a plain full upload (every array of every chunk, cudaMemcpyAsync).
     e2e = None
     e2e_dense = None
+    log(rank, "device-resident legs done")
     if want_e2e:
         h_verts = torch.empty((total_quads * 4 + 4, 12), dtype=torch.uint8).pin_memory().numpy()
         h_idx = torch.empty(total_quads * 6 + 6, dtype=torch.uint16).pin_memory().numpy()
@@ -844,7 +914,9 @@ def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs
             e2e_dense["staged_sparse"] = e2e_staged
 
     # ---- column pre-processing on the device: surface map + light flood fill from the block ids ----
-    preprocess = load_path = stream_path = edit_path = None
+    preprocess = load_path = stream_path = edit_path = stress = None
+    if full_legs and not args.no_stress and world_size == 1:
+        stress = stress_leg(ctx, args)
     if full_legs and not args.no_preprocess and world_size == 1:
         preprocess = preprocess_leg(ctx, host, Pinned, args)
         load_path = load_path_leg(ctx, world, batch, host, coords, total_quads, args)
@@ -891,10 +963,11 @@ def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs
                 line["e2e_dense"] = e2e_dense
         if full_legs and not args.no_cpu_baseline and world_size == 1:
             line["cpu_baseline"] = cpu_reference_run(host, coords, args.cpu_seconds)
-        for k, v in (("preprocess", preprocess), ("load_path", load_path), ("stream_path", stream_path), ("edit_path", edit_path)):
+        for k, v in (("stress", stress), ("preprocess", preprocess), ("load_path", load_path), ("stream_path", stream_path), ("edit_path", edit_path)):
             if v:
                 line[k] = v
 
+    log(rank, "legs done")
     halo_timed_out = world.halo_status()[0] if exchange_kind in ("p2p", "fused") else False
     if world_size > 1:
         dist.barrier()                                    # nobody unmaps a window a neighbour may still write to

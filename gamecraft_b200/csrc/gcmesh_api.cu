@@ -179,6 +179,8 @@ struct GcBatch
     bool timing;                    // record ev_start / ev_stop around the kernel (gcmesh_batch_set_timing)
     bool timed;                     // ... and the last submission did
     int order_rows[2];              // gcmesh_submit_exchange: the boundary rows the order was built for (-1: plain submission)
+    bool uncapped;                  // GC_BATCH_UNCAPPED: no per-chunk quad cap, 32-bit indices
+    size_t index_quad_bytes;        // 12 (six uint16) or 24 (six uint32) bytes of indices per quad
     // work order: chunks are claimed heaviest first so that the kernel's tail is made of cheap ones
     int32_t* d_order;
     int32_t* h_order;               // pinned
@@ -1446,8 +1448,14 @@ int gcmesh_world_encode_rle(GcWorld* w, const GcChunkCoord* coords, int n, uint1
 // ---------------------------------------------------------------------------------------------------------
 int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBatch** out)
 {
+    return gcmesh_batch_create_ex(ctx, max_chunks, max_quads, 0, out);
+}
+
+int gcmesh_batch_create_ex(GcContext* ctx, int max_chunks, uint64_t max_quads, uint32_t flags, GcBatch** out)
+{
     if (!ctx || !out) return fail(GC_ERR_ARG, "null argument");
     *out = nullptr;
+    if (flags & ~(uint32_t)GC_BATCH_UNCAPPED) return fail(GC_ERR_ARG, "unknown batch flag");
     if (max_chunks < 1) return fail(GC_ERR_ARG, "max_chunks must be positive");
     if (max_quads < 1) max_quads = 1;
     if (max_quads > 0xFFFFFFFFull) return fail(GC_ERR_ARG, "max_quads must fit 32 bits (GcChunkOut::quad_base)");
@@ -1455,10 +1463,12 @@ int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBa
     GcBatch* b = new (std::nothrow) GcBatch();
     if (!b) return fail(GC_ERR_ARG, "out of host memory");
     b->ctx = ctx; b->max_chunks = max_chunks; b->max_quads = max_quads;
+    b->uncapped = (flags & GC_BATCH_UNCAPPED) != 0;
+    b->index_quad_bytes = b->uncapped ? 24 : 12;
     cudaError_t e = cudaMalloc(&b->d_coords, sizeof(GcChunkCoord) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_out, sizeof(GcChunkOut) * (size_t)max_chunks);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_vertices, (size_t)max_quads * 48);
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_indices, (size_t)max_quads * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_indices, (size_t)max_quads * b->index_quad_bytes);
     // one 32-byte control block {quad cursor | work counter, error flag | CTAs done, pad | quads of the last launch}: cleared
     // here once — the last CTA of every launch leaves it ready for the next one — and read back once per submission
     if (e == cudaSuccess) e = cudaMalloc(&b->d_cursor, 32);
@@ -1533,6 +1543,7 @@ static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cu
     p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma; p.prof = b->d_prof;
     p.done_counter = reinterpret_cast<uint32_t*>(b->d_cursor + 2); p.total_out = b->d_cursor + 3; p.keep_cursor = keep_cursor ? 1 : 0;
     p.vert_table = w->d_vert_table;
+    p.wide = b->uncapped ? 1 : 0;
     p.n_push = 0;
     memset(&p.halo, 0, sizeof(p.halo));
     if (halo && halo->enabled)
@@ -1561,6 +1572,7 @@ static int submit_impl(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n
     memset(&halo, 0, sizeof(halo));
     if (rows)
     {
+        if (b->uncapped) return fail(GC_ERR_ARG, "an uncapped batch cannot carry the halo exchange");
         if (!w->halo_peer[0].connected && !w->halo_peer[1].connected) return fail(GC_ERR_ARG, "no neighbour connected");
         if ((w->halo_peer[0].connected && (rows[0] < 1 || rows[0] >= w->size_z - 1)) || (w->halo_peer[1].connected && (rows[1] < 1 || rows[1] >= w->size_z - 1)))
             return fail(GC_ERR_ARG, "send row outside the meshable rows of the window");
@@ -1583,7 +1595,8 @@ static int submit_impl(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n
     // Work order (longest first): a chunk with thousands of quads costs several times an air chunk, and the chunks claimed
     // last decide when the kernel ends.  With the quad counts of a finished submission of the same list the order is by
     // those; otherwise lower chunks first (terrain sits at the bottom of the world, the sky above it is air).  With a fused
-    // exchange the chunks of the boundary rows come after all others (by then the neighbours' planes have long arrived).
+    // exchange the heavy chunks of the boundary rows come after the heavy chunks of all other rows — by then the neighbours'
+    // planes have long arrived — and the light (air) chunks of all rows still make up the tail.
     const int r0 = rows && w->halo_peer[0].connected ? rows[0] : -1, r1 = rows && w->halo_peer[1].connected ? rows[1] : -1;
     const bool same_list = n == b->order_n && n > 0 && r0 == b->order_rows[0] && r1 == b->order_rows[1] &&
                            memcmp(coords, b->order_coords, sizeof(GcChunkCoord) * (size_t)n) == 0;
@@ -1592,16 +1605,22 @@ static int submit_impl(GcWorld* w, GcBatch* b, const GcChunkCoord* coords, int n
     {
         constexpr int kBuckets = 24;
         const bool history = same_list && b->state == 2;
-        int start[2 * kBuckets + 1] = { 0 };
+        int start[3 * kBuckets + 1] = { 0 };
         auto bucket = [&](int i) -> int
         {
-            const int interior = (coords[i].cz == r0 || coords[i].cz == r1) ? 0 : kBuckets;
-            if (!history) return interior + kBuckets - 1 - (coords[i].cy < 4 ? coords[i].cy : 3);       // cy 0 first
-            const uint32_t q = b->h_out[i].quads;
-            return interior + (q == 0 ? 0 : 1 + (q >= 11264 ? 22 : (int)(q >> 9)));                    // 512-quad classes, heaviest last
+            const bool boundary = coords[i].cz == r0 || coords[i].cz == r1;
+            int weight; bool heavy;
+            if (!history) { const int cy = coords[i].cy < 4 ? coords[i].cy : 3; weight = kBuckets - 1 - cy; heavy = cy < 2; }   // cy 0 first
+            else
+            {
+                const uint32_t q = b->h_out[i].quads;
+                weight = q == 0 ? 0 : 1 + (q >= 11264 ? 22 : (int)(q >> 9));                                             // 512-quad classes
+                heavy = q != 0;
+            }
+            return (heavy ? (boundary ? 1 : 2) : 0) * kBuckets + weight;
         };
         for (int i = 0; i < n; i++) start[bucket(i) + 1]++;
-        for (int k = 0; k < 2 * kBuckets; k++) start[k + 1] += start[k];
+        for (int k = 0; k < 3 * kBuckets; k++) start[k + 1] += start[k];
         for (int i = 0; i < n; i++) b->h_order[n - 1 - start[bucket(i)]++] = i;             // descending bucket
         memcpy(b->order_coords, coords, sizeof(GcChunkCoord) * (size_t)n);
         b->order_n = n; b->order_from_history = history; b->order_rows[0] = r0; b->order_rows[1] = r1;
@@ -1722,7 +1741,8 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         if (end > copied)
         {
             if (host_vertices) GC_CUDA(cudaMemcpyAsync((uint8_t*)host_vertices + copied * 48, b->d_vertices + copied * 48, (size_t)(end - copied) * 48, cudaMemcpyDeviceToHost, sd));
-            if (host_indices) GC_CUDA(cudaMemcpyAsync((uint8_t*)host_indices + copied * 12, (uint8_t*)b->d_indices + copied * 12, (size_t)(end - copied) * 12, cudaMemcpyDeviceToHost, sd));
+            if (host_indices) GC_CUDA(cudaMemcpyAsync((uint8_t*)host_indices + copied * b->index_quad_bytes, (uint8_t*)b->d_indices + copied * b->index_quad_bytes,
+                                                      (size_t)(end - copied) * b->index_quad_bytes, cudaMemcpyDeviceToHost, sd));
             copied = end;
         }
         return GC_OK;
@@ -1848,7 +1868,7 @@ int gcmesh_batch_download(GcBatch* b, void* vertices, void* indices)
     const uint64_t q = b->h_cursor[3] < b->max_quads ? b->h_cursor[3] : b->max_quads;
     if (q == 0) return GC_OK;
     if (vertices) GC_CUDA(cudaMemcpyAsync(vertices, b->d_vertices, (size_t)q * 48, cudaMemcpyDeviceToHost, b->ctx->stream));
-    if (indices) GC_CUDA(cudaMemcpyAsync(indices, b->d_indices, (size_t)q * 12, cudaMemcpyDeviceToHost, b->ctx->stream));
+    if (indices) GC_CUDA(cudaMemcpyAsync(indices, b->d_indices, (size_t)q * b->index_quad_bytes, cudaMemcpyDeviceToHost, b->ctx->stream));
     GC_CUDA(cudaStreamSynchronize(b->ctx->stream));
     return GC_OK;
 }
@@ -1858,6 +1878,7 @@ int gcmesh_batch_fill_meshdata(GcBatch* b, int i, GcMeshData* out)
     if (!b || !out) return fail(GC_ERR_ARG, "null argument");
     if (b->state != 2) return fail(GC_ERR_STATE, "call gcmesh_wait first");
     if (i < 0 || i >= b->n) return fail(GC_ERR_ARG, "chunk index outside the batch");
+    if (b->uncapped) return fail(GC_ERR_STATE, "GcMeshData is the reference's capped, 16-bit MeshData: not available from an uncapped batch");
     GC_CUDA(cudaSetDevice(b->ctx->device));
     const GcChunkOut& c = b->h_out[i];
     out->vert_count = (int32_t)c.vert_count;
@@ -1897,8 +1918,9 @@ int gcmesh_batch_fill_device(GcBatch* b, const GcDeviceMesh* targets, int n)
         for (int t = 0; t < GC_MESH_TYPE_COUNT; t++)
             if (targets[i].indices[t] && c.index_count[t])
             {
-                j.src[1 + t] = b->d_indices + (size_t)c.quad_base * 6 + c.index_offset[t]; j.dst[1 + t] = targets[i].indices[t];
-                j.bytes[1 + t] = c.index_count[t] * 2;
+                const size_t ib = b->index_quad_bytes / 6;   // bytes per index
+                j.src[1 + t] = (uint8_t*)b->d_indices + ((size_t)c.quad_base * 6 + c.index_offset[t]) * ib; j.dst[1 + t] = targets[i].indices[t];
+                j.bytes[1 + t] = (uint32_t)(c.index_count[t] * ib);
             }
     }
     cudaStream_t s = b->ctx->stream;

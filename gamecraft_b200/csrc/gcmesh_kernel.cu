@@ -70,7 +70,8 @@ constexpr int kOffFaces = kOffLayerTypBaseB + 256;                        // Fac
 constexpr int kOffBars = kOffFaces + 6 * 48;                              // full[8]
 constexpr int kOffCtx = kOffBars + kStages * 8;
 constexpr int kOffNext = kOffCtx + 128;                                    // NextChunk[2]
-constexpr int kSmemBytes = kOffNext + 32;
+constexpr int kOffTyp32 = kOffNext + 32;                                   // u32[4][64]: uncapped mode, first quad of mesh types 1..4 per layer
+constexpr int kSmemBytes = kOffTyp32 + 4 * 64 * 4;
 static_assert(kOffPlanes % 128 == 0 && kOffBv % 16 == 0 && kOffSurf % 16 == 0 && kOffList % 16 == 0 && kOffTList % 2 == 0, "align");
 static_assert(kOffLut % 8 == 0 && kOffMat % 8 == 0 && kOffBars % 8 == 0 && kOffLayerCnt % 4 == 0 && kOffCtx % 4 == 0 && kOffFaces % 16 == 0, "align");
 static_assert(2 * (kSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM");
@@ -91,6 +92,7 @@ struct ChunkCtx
     uint8_t slab_cls[kSlabs + 2];   // per z-slab: 0xFF = its plane rows are written; else the class byte of the one non-emitting block
                                     // (air, as a rule) that fills it — such rows are only written if the chunk turns out to need them
     int32_t halo_ok;      // fused exchange: result of a wait for a neighbour, broadcast to the CTA
+    uint32_t batch_base[kMeshTypes];   // uncapped mode: first quad of each mesh type in the current P3 batch (the list holds ranks relative to it)
 };
 static_assert(sizeof(ChunkCtx) <= 128, "ChunkCtx outgrew its slot");
 
@@ -243,7 +245,8 @@ __device__ void halo_push_task(const HaloFused& h, int task, int* s_flag)
     } while (0)
 
 // =====================================================================================================
-template <bool kProf, bool kHalo>
+// kWide: the uncapped ("stress") form — no 10 000-quad cap, 32-bit indices (not a reference behaviour)
+template <bool kProf, bool kHalo, bool kWide>
 __global__ void __launch_bounds__(NT, 2)
 gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
 {
@@ -271,6 +274,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     FacePlan* s_faces = reinterpret_cast<FacePlan*>(smem + kOffFaces);
     uint64_t* s_bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     ChunkCtx* s_ctx = reinterpret_cast<ChunkCtx*>(smem + kOffCtx);
+    uint32_t* s_typ32 = reinterpret_cast<uint32_t*>(smem + kOffTyp32);
 
     // ---- one-time setup ----
     for (int i = tid; i < 256; i += NT)
@@ -659,7 +663,21 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
             s_layer_base[2 * lane + 1] = ce + c0;
             if (lane == 31) s_layer_base[64] = total;
             uint32_t ta_tot = 0, tb_tot = 0;
-            if (total <= (uint32_t)kMaxQuads)   // 16-bit fields cannot overflow below the cap
+            uint32_t wide_tot[4] = { 0, 0, 0, 0 };
+            if (kWide)
+            {
+                // a layer holds at most 4224 quads (16-bit fields are enough per layer), a chunk up to 196 608: 32-bit scans
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                {
+                    const uint32_t v0 = ((t < 2 ? a0 : b0) >> (16 * (t & 1))) & 0xFFFFu, v1 = ((t < 2 ? a1 : b1) >> (16 * (t & 1))) & 0xFFFFu;
+                    const uint32_t vi = warp_incl_scan(v0 + v1, lane);
+                    wide_tot[t] = __shfl_sync(0xffffffffu, vi, 31);
+                    s_typ32[t * 64 + 2 * lane] = vi - (v0 + v1);
+                    s_typ32[t * 64 + 2 * lane + 1] = vi - v1;
+                }
+            }
+            else if (total <= (uint32_t)kMaxQuads)   // 16-bit fields cannot overflow below the cap
             {
                 const uint32_t ai = warp_incl_scan(a0 + a1, lane), bi = warp_incl_scan(b0 + b1, lane);
                 ta_tot = __shfl_sync(0xffffffffu, ai, 31);
@@ -674,11 +692,12 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 o.quad_base = 0; o.vert_count = 0; o.quads = total; o.flags = 0; o.reserved[0] = 0; o.reserved[1] = 0;
                 for (int t = 0; t < kMeshTypes; t++) { o.index_count[t] = 0; o.index_offset[t] = 0; }
                 int emit = 0;
-                if (total > (uint32_t)kMaxQuads) o.flags = GC_CHUNK_OVERFLOW;
+                if (!kWide && total > (uint32_t)kMaxQuads) o.flags = GC_CHUNK_OVERFLOW;
                 else
                 {
                     uint32_t tq[kMeshTypes];
                     tq[1] = ta_tot & 0xFFFFu; tq[2] = ta_tot >> 16; tq[3] = tb_tot & 0xFFFFu; tq[4] = tb_tot >> 16;
+                    if (kWide) { tq[1] = wide_tot[0]; tq[2] = wide_tot[1]; tq[3] = wide_tot[2]; tq[4] = wide_tot[3]; }
                     tq[0] = total - tq[1] - tq[2] - tq[3] - tq[4];
                     unsigned long long base = total ? atomicAdd(p.quad_cursor, (unsigned long long)total) : 0ull;
                     if (base + total > p.max_quads) o.flags = GC_CHUNK_NO_SPACE;
@@ -741,6 +760,24 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                     while (s_layer_base[l1 + 1] - first <= (uint32_t)kListCap) l1++;
                 }
                 const uint32_t count = s_layer_base[l1] - first;
+                if (kWide && count)
+                {
+                    // the list's 16-bit per-type ranks are relative to the batch (a batch holds at most kListCap quads)
+                    if (tid < kTY && tid >= l0 && tid < l1)
+                    {
+                        const uint32_t r1 = s_typ32[0 * 64 + tid] - s_typ32[0 * 64 + l0], r2 = s_typ32[1 * 64 + tid] - s_typ32[1 * 64 + l0];
+                        const uint32_t r3 = s_typ32[2 * 64 + tid] - s_typ32[2 * 64 + l0], r4 = s_typ32[3 * 64 + tid] - s_typ32[3 * 64 + l0];
+                        s_layer_typbase_a[tid] = r1 | (r2 << 16);
+                        s_layer_typbase_b[tid] = r3 | (r4 << 16);
+                    }
+                    if (tid == 0)
+                    {
+                        const uint32_t b1 = s_typ32[0 * 64 + l0], b2 = s_typ32[1 * 64 + l0], b3 = s_typ32[2 * 64 + l0], b4 = s_typ32[3 * 64 + l0];
+                        s_ctx->batch_base[0] = first - b1 - b2 - b3 - b4;
+                        s_ctx->batch_base[1] = b1; s_ctx->batch_base[2] = b2; s_ctx->batch_base[3] = b3; s_ctx->batch_base[4] = b4;
+                    }
+                    __syncthreads();
+                }
                 if (count)
                 {
                     // ---- 3a: rows -> ordered quad list + per-type ranks ----
@@ -762,7 +799,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                             uint32_t trank[kMeshTypes];
                             const uint32_t rank0 = s_layer_base[layer] + ce;
                             trank[1] = ae & 0xFFFFu; trank[2] = ae >> 16; trank[3] = be & 0xFFFFu; trank[4] = be >> 16;
-                            trank[0] = rank0 - trank[1] - trank[2] - trank[3] - trank[4];
+                            trank[0] = (kWide ? rank0 - first : rank0) - trank[1] - trank[2] - trank[3] - trank[4];
                             p3a_row(rf, layer, lane, rank0 - first, trank, s_list, s_tlist);
                         }
                     }
@@ -785,10 +822,21 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                             id_next = __ldg(chunk_blocks + ((en >> 3) & 31) + 32 * (((en >> 13) & 63) + 64 * ((en >> 8) & 31)));
                         }
                         const uint32_t rank = first + i;
-                        uint32_t iw[3];
-                        quad_index_words(rank, iw);
-                        uint32_t* ip = idx_words + (size_t)(s_ctx->type_off[(e >> 19) & 7] + s_tlist[i]) * 3;
-                        ip[0] = iw[0]; ip[1] = iw[1]; ip[2] = iw[2];
+                        if (kWide)
+                        {
+                            // SetIndices' pattern with 32-bit indices: o + 2, o + 1, o, o + 3, o + 2, o
+                            const uint32_t t = (e >> 19) & 7, o = rank * 4u;
+                            uint2* ip = reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(p.index_arena) + (size_t)quad_base * 6) +
+                                        (size_t)(s_ctx->type_off[t] + s_ctx->batch_base[t] + s_tlist[i]) * 3;
+                            ip[0] = make_uint2(o + 2u, o + 1u); ip[1] = make_uint2(o, o + 3u); ip[2] = make_uint2(o + 2u, o);
+                        }
+                        else
+                        {
+                            uint32_t iw[3];
+                            quad_index_words(rank, iw);
+                            uint32_t* ip = idx_words + (size_t)(s_ctx->type_off[(e >> 19) & 7] + s_tlist[i]) * 3;
+                            ip[0] = iw[0]; ip[1] = iw[1]; ip[2] = iw[2];
+                        }
                         uint32_t v[12];
                         p3b_quad(e, s_faces[e & 7], lg, s_planes + 4 * kHaloRows, s_hx, s_mat[id], v);
                         uint4* dst = vtx + (size_t)rank * 3;
@@ -898,8 +946,9 @@ static cudaError_t configure_mesh_kernel()
     static bool configured = false;
     if (configured) return cudaSuccess;
     cudaError_t e = cudaSuccess;
-    const void* kernels[3] = { (const void*)gc_mesh_kernel<false, false>, (const void*)gc_mesh_kernel<true, false>, (const void*)gc_mesh_kernel<false, true> };
-    for (int k = 0; k < 3 && e == cudaSuccess; k++)
+    const void* kernels[4] = { (const void*)gc_mesh_kernel<false, false, false>, (const void*)gc_mesh_kernel<true, false, false>,
+                               (const void*)gc_mesh_kernel<false, true, false>, (const void*)gc_mesh_kernel<false, false, true> };
+    for (int k = 0; k < 4 && e == cudaSuccess; k++)
     {
         e = cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         // the whole unified L1 / shared array as shared memory: two ~112 KB CTAs per SM
@@ -913,9 +962,9 @@ int mesh_ctas_per_sm()
 {
     if (configure_mesh_kernel() != cudaSuccess) return 0;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gc_mesh_kernel<false, false>, NT, kSmemBytes) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gc_mesh_kernel<false, false, false>, NT, kSmemBytes) != cudaSuccess) return 0;
     int nh = 0;   // (the exchange instantiation must fit as many: its waiting CTAs rely on the grid being resident)
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nh, gc_mesh_kernel<false, true>, NT, kSmemBytes) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nh, gc_mesh_kernel<false, true, false>, NT, kSmemBytes) != cudaSuccess) return 0;
     return n < nh ? n : nh;
 }
 
@@ -924,16 +973,17 @@ cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int gri
     cudaError_t e0 = configure_mesh_kernel();
     if (e0 != cudaSuccess) return e0;
     static const bool force_halo = getenv("GCMESH_FORCE_HALO_KERNEL") != nullptr;
-    if (p.halo.enabled || force_halo) gc_mesh_kernel<false, true><<<grid, NT, kSmemBytes, stream>>>(p, maps);   // (no profiling instantiation of the exchange form)
-    else if (p.prof) gc_mesh_kernel<true, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
-    else gc_mesh_kernel<false, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
+    if (p.wide) gc_mesh_kernel<false, false, true><<<grid, NT, kSmemBytes, stream>>>(p, maps);                        // (uncapped form: no exchange, no profiling)
+    else if (p.halo.enabled || force_halo) gc_mesh_kernel<false, true, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);   // (no profiling instantiation of the exchange form)
+    else if (p.prof) gc_mesh_kernel<true, false, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
+    else gc_mesh_kernel<false, false, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
     return cudaGetLastError();
 }
 
 cudaError_t mesh_kernel_attributes(int* regs, int* static_smem, int* max_dyn_smem)
 {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, gc_mesh_kernel<false, false>);
+    cudaError_t e = cudaFuncGetAttributes(&a, gc_mesh_kernel<false, false, false>);
     if (e != cudaSuccess) return e;
     if (regs) *regs = a.numRegs;
     if (static_smem) *static_smem = (int)a.sharedSizeBytes;

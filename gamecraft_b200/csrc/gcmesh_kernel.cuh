@@ -48,6 +48,7 @@ struct MeshParams
     // planes into the neighbours' windows, item n_push + k is chunk order[k]
     int32_t n_push;
     HaloFused halo;
+    int32_t wide;                      // uncapped batch (GC_BATCH_UNCAPPED): no quad cap per chunk, 32-bit indices (24 bytes per quad in the index arena)
 };
 
 // The block-id arena viewed as (256, 8, z = 32, slot): one box (256, 8, 1, 1) is one whole z-slab of a brick

@@ -29,6 +29,7 @@ CHUNK_NO_SPACE = 2
 CHUNK_HALO_MISSING = 4
 WORLD_SURFACE_BOUNDS_BLOCKS = 1      # GC_WORLD_SURFACE_BOUNDS_BLOCKS
 WORLD_COPY_RUN = 2                   # GC_WORLD_COPY_RUN
+BATCH_UNCAPPED = 1                   # GC_BATCH_UNCAPPED
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -86,7 +87,7 @@ EXPORTS = [
     "gcmesh_world_light_stats", "gcmesh_world_download",
     "gcmesh_world_upload_rle", "gcmesh_world_rle_refused", "gcmesh_world_encode_rle",
     "gcmesh_world_set_blocks", "gcmesh_world_vertex_counts", "gcmesh_world_generate",
-    "gcmesh_batch_create", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_submit_exchange", "gcmesh_batch_set_timing", "gcmesh_mesh_host", "gcmesh_wait", "gcmesh_batch_results",
+    "gcmesh_batch_create", "gcmesh_batch_create_ex", "gcmesh_batch_destroy", "gcmesh_submit", "gcmesh_submit_exchange", "gcmesh_batch_set_timing", "gcmesh_mesh_host", "gcmesh_wait", "gcmesh_batch_results",
     "gcmesh_batch_download", "gcmesh_batch_fill_meshdata", "gcmesh_batch_fill_device", "gcmesh_batch_device_ptrs", "gcmesh_batch_elapsed_ms",
     "gcmesh_batch_launches", "gcmesh_kernel_info", "gcmesh_batch_profile",
 ]
@@ -147,6 +148,7 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_vertex_counts.argtypes = [vp, vp]
         L.gcmesh_world_generate.argtypes = [vp, ci, ctypes.c_uint32, ci, ci, ci, ci]
         L.gcmesh_batch_create.argtypes = [vp, ci, ctypes.c_uint64, ctypes.POINTER(vp)]
+        L.gcmesh_batch_create_ex.argtypes = [vp, ci, ctypes.c_uint64, ctypes.c_uint32, ctypes.POINTER(vp)]
         L.gcmesh_batch_destroy.argtypes = [vp]
         L.gcmesh_submit.argtypes = [vp, vp, vp, ci]
         L.gcmesh_submit_exchange.argtypes = [vp, vp, vp, ci, ci, ci]
@@ -420,10 +422,12 @@ class ChunkMesh:
 class Batch:
     """Output arenas + descriptors of one batched submission (the reference's ``vector<Chunk*>`` job)."""
 
-    def __init__(self, ctx: Context, max_chunks: int, max_quads: int):
-        self.ctx, self.max_chunks, self.max_quads = ctx, int(max_chunks), int(max_quads)
+    def __init__(self, ctx: Context, max_chunks: int, max_quads: int, uncapped: bool = False):
+        """``uncapped``: GC_BATCH_UNCAPPED — no 10 000-quad cap per chunk, uint32 indices (the "stress" form; not a reference behaviour)."""
+        self.ctx, self.max_chunks, self.max_quads, self.uncapped = ctx, int(max_chunks), int(max_quads), bool(uncapped)
+        self.index_dtype = np.uint32 if uncapped else np.uint16
         self.h = ctypes.c_void_p()
-        _check(lib().gcmesh_batch_create(ctx.h, self.max_chunks, self.max_quads, ctypes.byref(self.h)), "gcmesh_batch_create")
+        _check(lib().gcmesh_batch_create_ex(ctx.h, self.max_chunks, self.max_quads, BATCH_UNCAPPED if uncapped else 0, ctypes.byref(self.h)), "gcmesh_batch_create_ex")
         ctx._children.add(self)
         self._coords = None
 
@@ -473,7 +477,7 @@ class Batch:
         if vertices is None:
             vertices = np.empty((q * 4, 12), np.uint8)
         if indices is None:
-            indices = np.empty(q * 6, np.uint16)
+            indices = np.empty(q * 6, self.index_dtype)
         _check(lib().gcmesh_batch_download(self.h, _ptr(vertices), _ptr(indices)), "gcmesh_batch_download")
         return vertices, indices
 

@@ -281,6 +281,13 @@ int gcmesh_world_vertex_counts(GcWorld* world, int32_t* counts);
 /* ---- batches: one GPU submission = the reference's vector<Chunk*> job (WorldRender.cpp:29-37) ---- */
 /* Arenas for up to max_chunks chunks and max_quads quads in total (48 B of vertices + 12 B of indices per quad). */
 int gcmesh_batch_create(GcContext* ctx, int max_chunks, uint64_t max_quads, GcBatch** out);
+/* The same with flags.  GC_BATCH_UNCAPPED: the "stress" form of SURVEY 8(d) config 4 — NOT a reference behaviour (the reference
+ * asserts at 40 000 vertices, WorldRender.cpp:558): chunks of any quad count are meshed (a full 3-D checkerboard has
+ * 196 608), never flagged GC_CHUNK_OVERFLOW, and every index is a uint32 (SetIndices' pattern o + 2, o + 1, o, o + 3, o + 2, o
+ * without the uint16 wrap): the index arena holds 24 bytes per quad, index_count / index_offset count uint32 elements.
+ * Vertex bytes are what the capped form writes.  gcmesh_batch_fill_meshdata and gcmesh_submit_exchange refuse such a batch. */
+#define GC_BATCH_UNCAPPED 1u
+int gcmesh_batch_create_ex(GcContext* ctx, int max_chunks, uint64_t max_quads, uint32_t flags, GcBatch** out);
 int gcmesh_batch_destroy(GcBatch* batch);
 /* Mesh `n` chunks of `world`.  Chunks on the window edge are rejected (the reference never meshes them,
  * WorldRender.cpp:235).  Asynchronous; inputs must not change until gcmesh_wait (the reference's gating rule,

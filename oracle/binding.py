@@ -97,6 +97,8 @@ def oracle_lib() -> ctypes.CDLL:
         L.gcor_check_batch.argtypes = [ctypes.POINTER(_OrWorld), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
         L.gcor_check_batch.restype = ctypes.c_int64
+        L.gcor_build_chunk_uncapped.argtypes = [ctypes.POINTER(_OrWorld)] + [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        L.gcor_build_chunk_uncapped.restype = ctypes.c_int64
         L.gcor_fnv1a64.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
         L.gcor_fnv1a64.restype = ctypes.c_uint64
         L.gcor_default_block_table.argtypes = [ctypes.POINTER(BlockInfo), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
@@ -243,6 +245,16 @@ class OracleWorld:
         verts = np.frombuffer(m.vertices, np.uint8, n * 12).reshape(n, 12).copy()
         idx = [np.frombuffer(m.indices[t], np.uint16, m.index_count[t]).copy() for t in range(MESH_TYPES)]
         return Mesh(verts, idx, m.overflow, [int(a) for a in m.index_allocated])
+
+    def build_chunk_uncapped(self, cx, cy, cz, max_quads: int = 196608) -> Mesh:
+        """The traversal with the reference's cap lifted and 32-bit indices (the "stress" variant; not a reference behaviour)."""
+        verts = np.zeros(max_quads * 48, np.uint8)
+        idx = [np.zeros(max_quads * 6, np.uint32) for _ in range(MESH_TYPES)]
+        ptrs = (ctypes.c_void_p * MESH_TYPES)(*[a.ctypes.data for a in idx])
+        counts = np.zeros(MESH_TYPES, np.int64)
+        q = oracle_lib().gcor_build_chunk_uncapped(ctypes.byref(self._w), int(cx), int(cy), int(cz), verts.ctypes.data, ptrs, max_quads, counts.ctypes.data)
+        assert q >= 0
+        return Mesh(verts[: q * 48].reshape(q * 4, 12).copy(), [idx[t][: counts[t]].copy() for t in range(MESH_TYPES)])
 
     def chunk_overflowed(self, cx, cy, cz, x, y, z, total_vertices) -> bool:
         return bool(oracle_lib().gcor_chunk_overflowed(ctypes.byref(self._w), cx, cy, cz, x, y, z, total_vertices))

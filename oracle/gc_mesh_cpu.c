@@ -205,6 +205,21 @@ static void or_push_indices(GcOrMesh* m, int type)
     m->index_count[type] = n + 6;
 }
 
+/* The four vertices of one drawn face (WorldRender.cpp:475-553): 48 bytes at `o`. */
+static void or_face_vertices(const GcOrWorld* w, int cx, int cy, int cz, const GcOrBlockInfo* info, int f, int x, int y, int z, uint8_t* o)
+{
+    const OrFace* face = &OR_FACES[f];
+    for (int v = 0; v < 4; v++, o += 12)
+    {
+        const int* c = face->c[v];
+        OrColor col = or_vertex_light(w, cx, cy, cz, face->axis, x, y, z, 2 * c[0] - 1, 2 * c[1] - 1, 2 * c[2] - 1);
+        o[0] = (uint8_t)(x + c[0]); o[1] = (uint8_t)(y + c[1]); o[2] = (uint8_t)(z + c[2]);   /* VertexInfo, Mesh.h:37-44 */
+        o[3] = OR_UV[v][0]; o[4] = OR_UV[v][1]; o[5] = info->textures[f];
+        o[6] = o[7] = o[8] = (uint8_t)col.l; o[9] = (uint8_t)col.s;
+        o[10] = info->alpha; o[11] = 0;
+    }
+}
+
 /* BuildBlock (WorldRender.cpp:445-560). */
 static int or_build_block(const GcOrWorld* w, int cx, int cy, int cz, GcOrMesh* m, int x, int y, int z, int block)
 {
@@ -222,19 +237,44 @@ static int or_build_block(const GcOrWorld* w, int cx, int cy, int cz, GcOrMesh* 
         if (m->vert_count + 4 > GCOR_MAX_VERTICES) { m->overflow = 1; continue; }
 
         or_push_indices(m, info->mesh_type);
-        for (int v = 0; v < 4; v++)
-        {
-            const int* c = face->c[v];
-            OrColor col = or_vertex_light(w, cx, cy, cz, face->axis, x, y, z, 2 * c[0] - 1, 2 * c[1] - 1, 2 * c[2] - 1);
-            uint8_t* o = m->vertices + (size_t)(m->vert_count + v) * 12; /* VertexInfo, Mesh.h:37-44 */
-            o[0] = (uint8_t)(x + c[0]); o[1] = (uint8_t)(y + c[1]); o[2] = (uint8_t)(z + c[2]);
-            o[3] = OR_UV[v][0]; o[4] = OR_UV[v][1]; o[5] = info->textures[f];
-            o[6] = o[7] = o[8] = (uint8_t)col.l; o[9] = (uint8_t)col.s;
-            o[10] = info->alpha; o[11] = 0;
-        }
+        or_face_vertices(w, cx, cy, cz, info, f, x, y, z, m->vertices + (size_t)m->vert_count * 12);
         m->vert_count += 4;
     }
     return added;
+}
+
+/* The same traversal with the reference's fixed-size MeshData lifted (the "stress" variant: no
+ * 40 000-vertex cap, 32-bit indices — SetIndices' pattern o+2, o+1, o, o+3, o+2, o without the uint16 wrap).  The caller
+ * provides the buffers: vertices (max_quads * 48 bytes) and one uint32 index array of max_quads * 6 elements per mesh type.
+ * Returns the quad count, or -1 when a buffer is too small.  Not a reference behaviour: the reference asserts at the cap. */
+int64_t gcor_build_chunk_uncapped(const GcOrWorld* w, int cx, int cy, int cz, uint8_t* vertices, uint32_t* const* indices, int64_t max_quads,
+                                  int64_t* index_count)
+{
+    const uint16_t* blocks = w->blocks + (((int64_t)cz * w->size_x + cx) * GCOR_WORLD_CHUNKS_Y + cy) * GCOR_CHUNK_VOXELS;
+    int64_t quads = 0;
+    for (int t = 0; t < GCOR_MESH_TYPES; t++) index_count[t] = 0;
+    for (int y = 0; y < GCOR_CHUNK_V; y++)
+        for (int z = 0; z < GCOR_CHUNK_H; z++)
+            for (int x = 0; x < GCOR_CHUNK_H; x++)
+            {
+                const int block = blocks[x + 32 * (y + 64 * z)];
+                if (block == 0 || w->table[block].invisible) continue;
+                const GcOrBlockInfo* info = &w->table[block];
+                for (int f = 0; f < 6; f++)
+                {
+                    const OrFace* face = &OR_FACES[f];
+                    int adj = or_block(w, or_probe(w, cx, cy, cz, x + face->nx, y + face->ny, z + face->nz));
+                    if (!(info->cull < w->table[adj].cull && adj != block)) continue;
+                    if (quads >= max_quads) return -1;
+                    const uint32_t o = (uint32_t)(quads * 4);
+                    uint32_t* d = indices[info->mesh_type] + index_count[info->mesh_type];
+                    d[0] = o + 2; d[1] = o + 1; d[2] = o; d[3] = o + 3; d[4] = o + 2; d[5] = o;
+                    index_count[info->mesh_type] += 6;
+                    or_face_vertices(w, cx, cy, cz, info, f, x, y, z, vertices + (size_t)quads * 48);
+                    quads++;
+                }
+            }
+    return quads;
 }
 
 /* BuildChunkAsync (WorldRender.cpp:6-27): y outer, z middle, x inner; AIR and invisible blocks skipped. */

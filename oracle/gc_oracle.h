@@ -74,6 +74,9 @@ void gcor_world_init(GcOrWorld* w, int size_x, int size_z, const uint16_t* block
                      const uint8_t* light, const uint8_t* surface);
 /* BuildChunkAsync (WorldRender.cpp:6-27).  Returns totalVertices. */
 int gcor_build_chunk(const GcOrWorld* w, int cx, int cy, int cz, GcOrMesh* out);
+/* BuildChunkAsync with the fixed-size MeshData lifted (the "stress" variant, no reference behaviour: no cap, 32-bit indices). */
+int64_t gcor_build_chunk_uncapped(const GcOrWorld* w, int cx, int cy, int cz, uint8_t* vertices, uint32_t* const* indices, int64_t max_quads,
+                                  int64_t* index_count);
 /* ChunkOverflowed (WorldRender.cpp:412-439). */
 int gcor_chunk_overflowed(const GcOrWorld* w, int cx, int cy, int cz, int x, int y, int z, int total_vertices);
 /* One-chunk-per-job pool (Async.cpp:5-35 restated as an atomic counter). Returns seconds. */

@@ -99,6 +99,59 @@ def test_gpu_cap_edges_and_overflow_flag(ctx):
     assert (desc["flags"] == mesher.CHUNK_OVERFLOW).all() and (desc["quads"] == 196608).all() and q == 0
 
 
+def test_gpu_uncapped_batch_meshes_what_the_cap_refuses(ctx):
+    """GC_BATCH_UNCAPPED (the stress variant — no reference behaviour, no parity claim against the reference,
+    which asserts at its cap): a full 3-D checkerboard chunk — 196 608 quads — is meshed with 32-bit indices; checked against the
+    oracle's traversal with the cap lifted, and structurally (every quad indexed once with SetIndices' pattern, Mesh.cpp:41-47)."""
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(3, 3).build("stress", 1)
+    coords = w.interior_chunks(1)
+    world = mesher.World(ctx, 3, 3).upload(w)
+    batch = mesher.Batch(ctx, len(coords), len(coords) * 196608, uncapped=True)
+    o = ob.OracleWorld(w)
+    pat = np.array([2, 1, 0, 3, 2, 0], np.int64)
+    for _ in range(2):
+        batch.submit(world, coords).wait()
+        desc, q = batch.results()
+        assert q == 4 * 196608 and not desc["flags"].any() and (desc["quads"] == 196608).all() and (desc["vert_count"] == 786432).all()
+        for c, m in zip(coords, batch.meshes()):
+            want = o.build_chunk_uncapped(*c)
+            assert m.indices[0].dtype == np.uint32
+            util.assert_same_mesh(m, want, "uncapped %s" % (c,))
+            seg = m.indices[0].astype(np.int64).reshape(-1, 6)
+            assert np.array_equal(seg, seg[:, 2:3] + pat[None, :]) and np.array_equal(seg[:, 2], np.arange(196608) * 4)
+    md = ctypes.create_string_buffer(480000 + 5 * 120000 + 24)                 # GcMeshData is the reference's capped, 16-bit MeshData
+    assert mesher.lib().gcmesh_batch_fill_meshdata(batch.h, 0, md) == -4          # GC_ERR_STATE
+    batch.close(); world.close()
+    # below the cap an uncapped batch writes the capped form's bytes, with the indices widened; every stream is exercised
+    w = util.HostWorld(5, 5, origin=(-2, -2)).build("mixed", 11, radius=100, falloff=60)
+    coords = w.interior_chunks(1)
+    world = mesher.World(ctx, 5, 5).upload(w)
+    batch = mesher.Batch(ctx, len(coords), len(coords) * 12000, uncapped=True)
+    o = ob.OracleWorld(w)
+    streams = np.zeros(5, np.int64)
+    for c, m in zip(coords, batch.submit(world, coords).wait().meshes()):
+        want = o.build_chunk_uncapped(*c)
+        util.assert_same_mesh(m, want, "uncapped %s" % (c,))
+        streams += [len(i) for i in m.indices]
+    assert (streams > 0).all()
+    # a world of many batches per chunk and several mesh types: noise at several times the cap
+    w = util.HostWorld(3, 3)
+    rng = np.random.default_rng(4)
+    w.blocks[:] = rng.choice(np.array([0, 0, 0, 3, 8, 13, 22, 17, 10], np.uint16), w.blocks.shape)
+    util.light_world(w)
+    coords = w.interior_chunks(1)
+    world2 = mesher.World(ctx, 3, 3).upload(w)
+    batch2 = mesher.Batch(ctx, len(coords), len(coords) * 196608, uncapped=True)
+    o = ob.OracleWorld(w)
+    for c, m in zip(coords, batch2.submit(world2, coords).wait().meshes()):
+        want = o.build_chunk_uncapped(*c)
+        assert want.quads > 30000
+        util.assert_same_mesh(m, want, "uncapped noise %s" % (c,))
+    batch.close(); world.close(); batch2.close(); world2.close()
+
+
 def test_gpu_arena_too_small_is_flagged_not_overrun(ctx):
     from gamecraft_b200 import mesher
 
