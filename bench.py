@@ -49,8 +49,11 @@ WORKLOADS = {
     # BASELINE config 5: one 128 x 128-column forest (65 536 chunks) split into z-slabs over the ranks (strong scaling);
     # rows per rank = 128 / N (the entry holds the total)
     "forest65536": ("forest", 128, 128, 1337, None),
+    # BASELINE config 3 for several GPUs: one fixed-size island (radius 2048 blocks = 64 columns, fall-off over the last 64 blocks)
+    # filling a 128 x 128-column window, every chunk re-meshed, split into z-slabs over the ranks (strong scaling)
+    "islands65536": ("islands", 128, 128, 4242, 2048),
 }
-STRONG = {"forest65536"}
+STRONG = {"forest65536", "islands65536"}
 
 
 def rows_per_rank(workload: str, world_size: int) -> int:
