@@ -117,12 +117,18 @@ __global__ void __launch_bounds__(32) gc_edit_apply_kernel(EditArgs a)
     {
         slot = (size_t)col * 4 + (y >> 6);
         index = slot * kVox + (x & 31) + 32 * ((y & 63) + 64 * (z & 31));
-        if (a.vert_table[slot] < 0) status = GC_EDIT_NOT_BUILT;                            // World.cpp:562-565
-        else if (a.blocks_rw[index] == e.block) status = GC_EDIT_UNCHANGED;                // World.cpp:570
+        // lane 0 alone reads the old block (it is about to overwrite it) and the warp takes its verdict: every lane leaves
+        // this block with the same status whatever the order of its load and lane 0's store
+        if (lane == 0)
+        {
+            if (a.vert_table[slot] < 0) status = GC_EDIT_NOT_BUILT;                        // World.cpp:562-565
+            else if (a.blocks_rw[index] == e.block) status = GC_EDIT_UNCHANGED;            // World.cpp:570
+            else a.blocks_rw[index] = e.block;
+        }
     }
+    status = __shfl_sync(0xffffffffu, status, 0);
     if (status == GC_EDIT_APPLIED)
     {
-        if (lane == 0) a.blocks_rw[index] = e.block;
         __syncwarp();
         if (e.block != 0)
         {

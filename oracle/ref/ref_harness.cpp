@@ -321,6 +321,42 @@ int gcref_rle_save_group(GcRefWorld* w, int cx, int cz, uint16_t* out, int cap, 
     return total;
 }
 
+// A window whose column (0, 0) is world column (ox, oz): the groups' world positions as World::CreateChunkGroup would have
+// set them.  Only the region functions below look at group->pos (the mesher walks World::groups by window index).
+void gcref_world_set_origin(GcRefWorld* w, int ox, int oz)
+{
+    for (int cz = 0; cz < w->size; cz++)
+        for (int cx = 0; cx < w->size; cx++) RefGroup(w, cx, cz)->pos = ivec3(cx + ox, 0, cz + oz);
+}
+
+// What LoadRegionFile (WorldIO.cpp:15-80) does with one record read from a region file: word 0 (`position`) picks the
+// list of the region — here the region of column (cx, cz) — that receives [position][items][items words].
+// Returns the position, or -1 for a position outside the region.
+int gcref_rle_store_record(GcRefWorld* w, int cx, int cz, const uint16_t* rec, int words)
+{
+    World* world = w->world;
+    ChunkGroup* group = RefGroup(w, cx, cz);
+    Region* region = GetOrLoadRegion(world, ChunkToRegionP(group->pos));
+    if (words < 2) return -1;
+    const uint16_t position = rec[0], items = rec[1];
+    if (position >= REGION_SIZE_3) return -1;
+    List<uint16_t>* chunk = region->chunks + position;
+    chunk->Clear();
+    chunk->Reserve(words);
+    chunk->Add(position);
+    chunk->Add(items);
+    for (int i = 2; i < words; i++) chunk->Add(rec[i]);
+    region->hasData = true;
+    return position;
+}
+
+// Empties every list of the region of column (cx, cz).
+void gcref_rle_clear_region(GcRefWorld* w, int cx, int cz)
+{
+    Region* region = GetOrLoadRegion(w->world, ChunkToRegionP(RefGroup(w, cx, cz)->pos));
+    for (int i = 0; i < REGION_SIZE_3; i++) region->chunks[i].Clear();
+}
+
 // LoadGroupFromDisk (WorldIO.cpp:167-221): the records currently stored for column (cx, cz) decoded into its chunks'
 // block arrays (which the caller may have cleared in between).  Returns 1 when all four chunks had data.
 int gcref_rle_load_group(GcRefWorld* w, int cx, int cz)
