@@ -104,6 +104,7 @@ struct GcWorld
 {
     GcContext* ctx;
     int size_x, size_z;
+    int origin_cx, origin_cz;   // world-space column of window column (0, 0): gcmesh_world_set_origin / gcmesh_world_generate (region records)
     size_t n_cols, n_slots;
     uint16_t* d_blocks;
     uint8_t* d_sun;
@@ -851,6 +852,13 @@ int gcmesh_world_set_option(GcWorld* w, int option, int value)
     return fail(GC_ERR_ARG, "unknown world option");
 }
 
+int gcmesh_world_set_origin(GcWorld* w, int origin_cx, int origin_cz)
+{
+    if (!w) return fail(GC_ERR_ARG, "world is null");
+    w->origin_cx = origin_cx; w->origin_cz = origin_cz;
+    return GC_OK;
+}
+
 int gcmesh_world_upload_launches(const GcWorld* w) { return w ? w->launches : 0; }
 unsigned long long gcmesh_world_upload_bytes(const GcWorld* w) { return w ? w->upload_bytes : 0; }
 
@@ -1059,6 +1067,7 @@ int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, in
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    w->origin_cx = origin_cx; w->origin_cz = origin_cz;
     if (!w->d_gen_height)
     {
         GC_CUDA(cudaMalloc(&w->d_gen_height, sizeof(int16_t) * w->n_cols * GC_CHUNK_SIZE_2));
@@ -1421,7 +1430,10 @@ int gcmesh_world_encode_rle(GcWorld* w, const GcChunkCoord* coords, int n, uint1
             const GcChunkCoord c = coords[g0 + i];
             if (!column_ok(w, c.cx, c.cz) || c.cy < 0 || c.cy >= GC_WORLD_CHUNK_HEIGHT) return fail(GC_ERR_ARG, "chunk outside the window");
             h_slots[i] = (uint32_t)(((size_t)c.cz * w->size_x + c.cx) * GC_WORLD_CHUNK_HEIGHT + c.cy);
-            h_offsets[i] = (uint16_t)((c.cx & 7) + 8 * (c.cy + GC_WORLD_CHUNK_HEIGHT * (c.cz & 7)));   // RegionIndex of (pos & REGION_MASK), WorldIO.cpp:5-8,259
+            // RegionIndex of (ChunkP & REGION_MASK) (WorldIO.cpp:5-8,259-260): the chunk's WORLD position — LoadRegionFile files the
+            // record under this word (WorldIO.cpp:48-62)
+            const int wx = w->origin_cx + c.cx, wz = w->origin_cz + c.cz;
+            h_offsets[i] = (uint16_t)((wx & 7) + 8 * (c.cy + GC_WORLD_CHUNK_HEIGHT * (wz & 7)));
         }
         GC_CUDA(cudaMemcpyAsync(w->d_rle_slots, h_slots, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         GC_CUDA(cudaMemcpyAsync(w->d_rle_offsets, h_offsets, m * sizeof(uint16_t), cudaMemcpyHostToDevice, s));

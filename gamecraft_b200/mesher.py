@@ -80,7 +80,7 @@ EXPORTS = [
     "gcmesh_version", "gcmesh_last_error", "gcmesh_create", "gcmesh_destroy", "gcmesh_set_stream",
     "gcmesh_set_block_table", "gcmesh_default_block_table", "gcmesh_synchronize",
     "gcmesh_world_create", "gcmesh_world_destroy", "gcmesh_world_upload_chunk", "gcmesh_world_upload_surface",
-    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_set_option", "gcmesh_world_upload_launches", "gcmesh_world_upload_bytes", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
+    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_set_option", "gcmesh_world_set_origin", "gcmesh_world_upload_launches", "gcmesh_world_upload_bytes", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
     "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
     "gcmesh_world_halo_export", "gcmesh_world_halo_connect_ipc", "gcmesh_world_halo_connect_local", "gcmesh_world_halo_push", "gcmesh_world_halo_status",
     "gcmesh_default_light_rules", "gcmesh_set_light_rules", "gcmesh_world_compute_surface", "gcmesh_world_light",
@@ -122,6 +122,7 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_upload_rows.argtypes = [vp, ci, ci, vp, vp, vp, vp]
         L.gcmesh_world_upload_sparse.argtypes = [vp, vp, vp, vp, vp, vp, ci]
         L.gcmesh_world_set_option.argtypes = [vp, ci, ci]
+        L.gcmesh_world_set_origin.argtypes = [vp, ci, ci]
         L.gcmesh_world_upload_launches.argtypes = [vp]
         L.gcmesh_world_upload_bytes.argtypes = [vp]
         L.gcmesh_world_upload_bytes.restype = ctypes.c_uint64
@@ -268,6 +269,11 @@ class World:
 
     def set_option(self, option: int, value: int = 1) -> "World":
         _check(lib().gcmesh_world_set_option(self.h, int(option), int(value)), "gcmesh_world_set_option")
+        return self
+
+    def set_origin(self, origin_cx: int, origin_cz: int) -> "World":
+        """World-space column of window column (0, 0) (ChunkGroup::pos): region records carry it in their first word."""
+        _check(lib().gcmesh_world_set_origin(self.h, int(origin_cx), int(origin_cz)), "gcmesh_world_set_origin")
         return self
 
     def upload_bytes(self) -> int:

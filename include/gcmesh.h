@@ -148,6 +148,8 @@ int gcmesh_world_upload_sparse(GcWorld* world, const uint16_t* blocks, const uin
  * with one strided copy-engine copy; shorter runs are pulled by a GPU kernel out of pinned host memory (a huge value: always). */
 enum { GC_WORLD_SURFACE_BOUNDS_BLOCKS = 1, GC_WORLD_COPY_RUN = 2 };
 int gcmesh_world_set_option(GcWorld* world, int option, int value);
+/* World-space column (ChunkGroup::pos, World.h) of window column (0, 0).  Only region records depend on it (gcmesh_world_encode_rle). */
+int gcmesh_world_set_origin(GcWorld* world, int origin_cx, int origin_cz);
 /* Kernels launched by the last gcmesh_world_upload_sparse call. */
 int gcmesh_world_upload_launches(const GcWorld* world);
 /* Host -> device bytes the last gcmesh_world_upload_sparse / gcmesh_mesh_host call moved (brick arrays, work lists, surface maps, coordinates). */
@@ -224,7 +226,9 @@ typedef struct GcRleChunk
 int gcmesh_world_upload_rle(GcWorld* world, const GcRleChunk* chunks, int n, const uint16_t* data, size_t data_words);
 int gcmesh_world_rle_refused(GcWorld* world, int* refused);
 /* SaveGroup's encode (WorldIO.cpp:272-303) of `n` bricks of the device world: records are appended to `records` (host,
- * `capacity_words` uint16), out[i] says where chunk i's record lies; offset = RegionIndex(pos & REGION_MASK).  Synchronous. */
+ * `capacity_words` uint16), out[i] says where chunk i's record lies.  Word 0 of a record is RegionIndex(ChunkP & REGION_MASK)
+ * of the chunk's WORLD position (WorldIO.cpp:259-260; LoadRegionFile files the record under it, :48-62): window position +
+ * the window's origin as set by gcmesh_world_set_origin or the last gcmesh_world_generate (default (0, 0)).  Synchronous. */
 int gcmesh_world_encode_rle(GcWorld* world, const GcChunkCoord* coords, int n, uint16_t* records, size_t capacity_words, GcRleChunk* out);
 
 /* ---- terrain generation on the device: columns are born in HBM ----

@@ -124,6 +124,9 @@ def ref_lib() -> ctypes.CDLL:
         L.gcref_block_light_emitted.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.gcref_rle_save_group.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.gcref_rle_load_group.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.gcref_world_set_origin.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.gcref_rle_store_record.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.gcref_rle_clear_region.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.gcref_set_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.gcref_get_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
         L.gcref_set_surface.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
@@ -346,6 +349,18 @@ class RefWorld:
         for n in sizes:
             recs.append(out[p:p + n].copy()); p += int(n)
         return recs
+
+    def set_origin(self, ox, oz):
+        """group->pos = window position + (ox, oz) for every column (only the region functions read it)."""
+        self.L.gcref_world_set_origin(self.h, ox, oz)
+
+    def rle_store_record(self, cx, cz, record) -> int:
+        """LoadRegionFile's filing of one record read from a region file: word 0 picks the region's list."""
+        rec = np.ascontiguousarray(record, np.uint16)
+        return int(self.L.gcref_rle_store_record(self.h, cx, cz, rec.ctypes.data, len(rec)))
+
+    def rle_clear_region(self, cx, cz):
+        self.L.gcref_rle_clear_region(self.h, cx, cz)
 
     def rle_load_group(self, cx, cz) -> bool:
         """LoadGroupFromDisk on one column (decodes what rle_save_group stored into the column's chunks)."""

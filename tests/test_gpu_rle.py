@@ -26,7 +26,8 @@ def host_records(w, coords):
     """the oracle's records of the listed chunks, concatenated, with the locating array"""
     from gamecraft_b200 import mesher
 
-    recs = [ob.rle_encode_chunk(w.blocks[w.slot(*c)], region_index(*c)) for c in coords.tolist()]
+    ox, oz = w.origin
+    recs = [ob.rle_encode_chunk(w.blocks[w.slot(*c)], region_index(c[0] + ox, c[1], c[2] + oz)) for c in coords.tolist()]
     loc = np.zeros(len(recs), mesher.RLE_CHUNK_DTYPE)
     p = 0
     for i, (c, r) in enumerate(zip(coords.tolist(), recs)):
@@ -46,7 +47,7 @@ def test_decode_and_encode_equal_oracle(ctx, kind, size, seed):
     w = util.HostWorld(size, size, origin=(-(size // 2), -(size // 2)) if kw else (0, 0)).generate(kind, seed, **kw)
     coords = all_chunks(w)
     loc, data, recs = host_records(w, coords)
-    world = mesher.World(ctx, size, size)
+    world = mesher.World(ctx, size, size).set_origin(*w.origin)
     junk = util.HostWorld(size, size); junk.blocks[:] = 0x1234
     world.upload(junk)                                              # the decode has to overwrite every voxel
     world.upload_rle(loc, data)
@@ -59,6 +60,37 @@ def test_decode_and_encode_equal_oracle(ctx, kind, size, seed):
     assert np.array_equal(loc2["words"], loc["words"]) and np.array_equal(loc2["first_word"], loc["first_word"])
     assert np.array_equal(data2, data)
     world.close()
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref/libgcref.so not built (no reference tree)")
+def test_records_of_a_window_off_the_region_grid_load_in_the_reference(ctx):
+    """A window whose origin is no multiple of 8 columns (a slab window, a player far from the origin): the device's records
+    carry RegionIndex of the chunks' WORLD positions, so the reference's own loader — LoadRegionFile's filing by word 0
+    (WorldIO.cpp:48-62), then LoadGroupFromDisk (:167-221) — restores every column from them."""
+    from gamecraft_b200 import mesher
+
+    ox, oz = -3, 13
+    w = util.HostWorld(3, 3, origin=(ox, oz)).generate("mixed", 8, radius=600, falloff=500)
+    world = mesher.World(ctx, 3, 3).upload(w).set_origin(ox, oz)
+    coords = all_chunks(w)
+    loc, data = world.encode_rle(coords)
+    for c, l in zip(coords.tolist(), loc):
+        assert data[l["first_word"]] == region_index(c[0] + ox, c[1], c[2] + oz)
+    ref = ob.RefWorld(util.HostWorld(3, 3))            # an empty reference window at the same world position
+    ref.set_origin(ox, oz)
+    for cz in range(3):
+        for cx in range(3):
+            ref.rle_clear_region(cx, cz)
+    for c, l in zip(coords.tolist(), loc):
+        rec = data[l["first_word"]:l["first_word"] + l["words"]]
+        assert ref.rle_store_record(c[0], c[2], rec) == rec[0]
+    for cz in range(3):
+        for cx in range(3):
+            assert ref.rle_load_group(cx, cz)
+    got = util.HostWorld(3, 3)
+    ref.download(got)
+    assert np.array_equal(got.blocks, w.blocks)
+    ref.close(); world.close()
 
 
 def test_extreme_records(ctx):

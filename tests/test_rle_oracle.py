@@ -46,6 +46,30 @@ def test_decode_equals_reference():
     r.close()
 
 
+@needs_ref
+def test_offset_word_is_the_region_index_of_the_world_position():
+    """SaveGroup files a chunk under RegionIndex(ChunkP & REGION_MASK) of its WORLD position (WorldIO.cpp:259-260): with a
+    window origin that is no multiple of 8 the word differs from the window-local one, and LoadRegionFile's filing by that
+    word (WorldIO.cpp:48-62) + LoadGroupFromDisk only finds records that carry the world-position word."""
+    ox, oz = -3, 13
+    w = util.HostWorld(3, 3, origin=(ox, oz)).generate("noise", 6)
+    r = ob.RefWorld(w)
+    r.set_origin(ox, oz)
+    for cz in range(3):
+        for cx in range(3):
+            recs = r.rle_save_group(cx, cz)
+            for cy in range(4):
+                assert recs[cy][0] == region_index(cx + ox, cy, cz + oz) != region_index(cx, cy, cz)
+                assert np.array_equal(ob.rle_encode_chunk(w.blocks[w.slot(cx, cy, cz)], region_index(cx + ox, cy, cz + oz)), recs[cy])
+    # records with the window-local word land in other lists: the loader does not find the column
+    recs = [ob.rle_encode_chunk(w.blocks[w.slot(1, cy, 1)], region_index(1, cy, 1)) for cy in range(4)]
+    r.rle_clear_region(1, 1)
+    for rec in recs:
+        assert r.rle_store_record(1, 1, rec) == rec[0]
+    assert not r.rle_load_group(1, 1)
+    r.close()
+
+
 def test_known_answers_and_round_trips():
     uniform = np.full(65536, 3, np.uint16)
     rec = ob.rle_encode_chunk(uniform, 77)
