@@ -29,7 +29,49 @@ __global__ void __launch_bounds__(256) gc_fill_device_kernel(const FillJob* __re
     for (int k = 0; k < 1 + GC_MESH_TYPE_COUNT; k++)
         if (j.bytes[k]) copy_bytes(j.dst[k], j.src[k], j.bytes[k]);
 }
+
+// ids >= n_types in the block arena: how many, and the first one's voxel index (the reference asserts block < BLOCK_COUNT
+// when a block is stored, World.cpp:294; the mesh kernel reads such ids through an 8-bit table index)
+__global__ void __launch_bounds__(256) gc_validate_blocks_kernel(const uint4* __restrict__ blocks, size_t n_vec, uint32_t n_types, unsigned long long* out)
+{
+    unsigned long long bad = 0, first = ~0ull;
+    const uint32_t lim2 = n_types | (n_types << 16);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const uint4 v = blocks[i];
+        // per 16-bit half: id >= n_types
+        const uint32_t m = __vcmpgeu2(v.x, lim2) | __vcmpgeu2(v.y, lim2) | __vcmpgeu2(v.z, lim2) | __vcmpgeu2(v.w, lim2);
+        if (m)
+        {
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+            for (int k = 0; k < 8; k++)
+                if (((w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu) >= n_types)
+                {
+                    bad++;
+                    const unsigned long long at = (unsigned long long)i * 8 + k;
+                    if (at < first) first = at;
+                }
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        bad += __shfl_xor_sync(0xffffffffu, bad, d);
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, first, d);
+        first = o < first ? o : first;
+    }
+    if ((threadIdx.x & 31) == 0 && bad)
+    {
+        atomicAdd(out, bad);
+        atomicMin(out + 1, first);
+    }
+}
 }  // namespace
+
+cudaError_t launch_validate_blocks(const uint16_t* blocks, size_t n_voxels, int n_types, unsigned long long* d_out, int num_sms, cudaStream_t s)
+{
+    gc_validate_blocks_kernel<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const uint4*>(blocks), n_voxels / 8, (uint32_t)n_types, d_out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_fill_device(const FillJob* jobs, int n, cudaStream_t s)
 {

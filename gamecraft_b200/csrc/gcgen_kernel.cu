@@ -2,9 +2,10 @@
 //
 // Three kernels per window:
 //   heights  one thread per (column, z, x): island test, biome / flat / mountain noise, terrain height; column maximum
-//   layers   one thread per (column, z, x) walking up to the column maximum: stone pockets (3-D fBm), grass, dirt, water
-//   trees    one thread per column: the column's own PRNG stream places trunks and leaf boxes in order (later trees
-//            overwrite earlier ones, as in the host producer)
+//   layers   one thread per (column, z, x) walking up to the column maximum: stone pockets (3-D fBm), then the biome's
+//            layering (grass / dirt / water; snow / ice; sand; obsidian / lava)
+//   trees    one thread per column: the column's own PRNG stream places trunks and leaf boxes (forest, islands) or cacti
+//            (desert) in order (later ones overwrite earlier ones, as in the host producer)
 // Every float operation is an explicitly rounded single operation (__fmul_rn / __fadd_rn / ...), never a fused
 // multiply-add, in the order the host producer evaluates it (compiled with -ffp-contract=off), so both give the same
 // heights; powf is taken through double precision.
@@ -14,7 +15,11 @@ namespace gc
 {
 namespace
 {
-enum { B_AIR = 0, B_GRASS = 1, B_DIRT = 2, B_STONE = 3, B_METAL_CRATE = 7, B_WATER = 8, B_WOOD = 9, B_LEAVES = 10 };   // Code/Block.h:11-38
+enum { B_AIR = 0, B_GRASS = 1, B_DIRT = 2, B_STONE = 3, B_SAND = 5, B_METAL_CRATE = 7, B_WATER = 8, B_WOOD = 9, B_LEAVES = 10,
+       B_SNOW = 12, B_ICE = 13, B_CACTUS = 16, B_OBSIDIAN = 19, B_LAVA = 21 };   // Code/Block.h:11-38
+enum { T_FOREST = 0, T_ISLANDS = 1, T_SNOW = 2, T_DESERT = 3, T_VOLCANIC = 4 };   // GenArgs::biome
+__device__ __forceinline__ int sea_level(int biome) { return biome == T_FOREST || biome == T_DESERT ? 10 : (biome == T_VOLCANIC ? 12 : 20); }
+constexpr int kIceBit = 0x4000;   // height scratch: "the sea surface freezes over this cell" (snow)
 
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
@@ -182,6 +187,17 @@ __device__ float billow2(uint32_t seed, float x, float y, int octaves)
     return mul(sum, fractal_bounding(octaves));
 }
 
+__device__ float fbm2(uint32_t seed, float x, float y, int octaves)
+{
+    float sum = simplex2(seed, x, y), amp = 1.0f;
+    for (int i = 1; i < octaves; i++)
+    {
+        x = mul(x, 2.0f); y = mul(y, 2.0f); amp = mul(amp, 0.5f);
+        sum = add(sum, mul(simplex2(seed + (uint32_t)i, x, y), amp));
+    }
+    return mul(sum, fractal_bounding(octaves));
+}
+
 __device__ float fbm3(uint32_t seed, float x, float y, float z, int octaves)
 {
     float sum = simplex3(seed, x, y, z), amp = 1.0f;
@@ -209,10 +225,9 @@ __global__ void __launch_bounds__(256) gc_gen_height_kernel(GenArgs a)
     if (i >= n) return;
     const int col = i >> 10, z = (i >> 5) & 31, x = i & 31;
     const int cx = col % a.size_x, cz = col / a.size_x;
-    const int sea = a.islands ? 20 : 10;
-    const float mscale = a.islands ? 60.0f : 30.0f, mbase = a.islands ? 20.0f : 10.0f;
+    const int sea = sea_level(a.biome);
     const int wx = (a.origin_cx + cx) * 32 + x, wz = (a.origin_cz + cz) * 32 + z;
-    int h = 0, m = sea;
+    int h = 0, m = sea, ice = 0;
     // IsWithinIsland (Generation.cpp:66-81)
     const int v = (int)sqrt((double)wx * wx + (double)wz * wz);
     if (v < a.radius)
@@ -220,21 +235,49 @@ __global__ void __launch_bounds__(256) gc_gen_height_kernel(GenArgs a)
         float p = 1.0f;
         if (v > a.falloff) p = sub(1.0f, __fdiv_rn((float)(v - a.falloff), (float)(a.radius - a.falloff)));
         const float bx = (float)wx, bz = (float)wz;
-        const float biome = simplex2(a.seed + 101u, mul(bx, 0.01f), mul(bz, 0.01f));
-        float flat = mul(add(billow2(a.seed + 202u, mul(mul(bx, 0.025f), 0.5f), mul(mul(bz, 0.025f), 0.5f), 4), 1.0f), 0.5f);
-        flat = add(mul(mul(flat, 0.2f), 30.0f), 10.0f);
-        float mount = mul(add(ridged2(a.seed + 303u, mul(mul(bx, 0.015f), 0.5f), mul(mul(bz, 0.015f), 0.5f), 4), 1.0f), 0.5f);
-        if (mount < 0.0f) mount = 0.0f;
-        mount = add(mul((float)pow((double)mount, 3.5), mscale), mbase);
         float terrain;
-        if (biome < 0.0f) terrain = flat;
-        else if (biome > 0.6f) terrain = mount;
-        else terrain = add(flat, mul(scurve3(__fdiv_rn(biome, 0.6f)), sub(mount, flat)));
+        if (a.biome == T_DESERT)
+        {
+            // one billow field of three octaves (Generation.cpp:566-569, :585-586)
+            const float base = mul(add(billow2(a.seed + 202u, mul(mul(bx, 0.05f), 0.25f), mul(mul(bz, 0.05f), 0.25f), 3), 1.0f), 0.5f);
+            terrain = add(mul(mul(base, 0.2f), 30.0f), 20.0f);
+        }
+        else if (a.biome == T_SNOW)
+        {
+            // sea floor and land blended over the biome band -0.4 .. 0, whose upper part freezes the sea (Generation.cpp:431-479)
+            const float biome = fbm2(a.seed + 101u, mul(bx, 0.005f), mul(bz, 0.005f), 3);
+            float floor_ = mul(add(billow2(a.seed + 202u, mul(mul(bx, 0.025f), 0.5f), mul(mul(bz, 0.025f), 0.5f), 4), 1.0f), 0.5f);
+            floor_ = add(mul(mul(floor_, 0.2f), 20.0f), 5.0f);
+            float land = mul(add(ridged2(a.seed + 303u, mul(mul(bx, 0.015f), 0.5f), mul(mul(bz, 0.015f), 0.5f), 4), 1.0f), 0.5f);
+            land = add(mul(mul(land, 0.2f), 10.0f), 20.0f);
+            const float lower = -0.4f, upper = 0.0f;
+            if (biome < lower) terrain = floor_;
+            else if (biome > upper) terrain = land;
+            else
+            {
+                if (biome >= -0.25f && biome <= 0.0f) ice = kIceBit;
+                terrain = add(floor_, mul(scurve3(__fdiv_rn(sub(biome, lower), sub(upper, lower))), sub(land, floor_)));
+            }
+        }
+        else
+        {
+            const float mscale = a.biome == T_FOREST ? 30.0f : 60.0f, mbase = a.biome == T_FOREST ? 10.0f : 20.0f;
+            const float bfreq = a.biome == T_VOLCANIC ? 0.005f : 0.01f;
+            const float biome = simplex2(a.seed + 101u, mul(bx, bfreq), mul(bz, bfreq));
+            float flat = mul(add(billow2(a.seed + 202u, mul(mul(bx, 0.025f), 0.5f), mul(mul(bz, 0.025f), 0.5f), 4), 1.0f), 0.5f);
+            flat = add(mul(mul(flat, 0.2f), 30.0f), 10.0f);
+            float mount = mul(add(ridged2(a.seed + 303u, mul(mul(bx, 0.015f), 0.5f), mul(mul(bz, 0.015f), 0.5f), 4), 1.0f), 0.5f);
+            if (mount < 0.0f) mount = 0.0f;
+            mount = add(mul((float)pow((double)mount, 3.5), mscale), mbase);
+            if (biome < 0.0f) terrain = flat;
+            else if (biome > 0.6f) terrain = mount;
+            else terrain = add(flat, mul(scurve3(__fdiv_rn(biome, 0.6f)), sub(mount, flat)));
+        }
         h = (int)mul(terrain, p);
         if (h > GC_WORLD_BLOCK_HEIGHT - 12) h = GC_WORLD_BLOCK_HEIGHT - 12;
         if (h > m) m = h;
     }
-    a.height[i] = (int16_t)h;
+    a.height[i] = (int16_t)(h | ice);
     // ComputeSurface's entry for this cell (Lighting.cpp:5-17) before trees: the layering fills 0..h and water up to sea level
     a.surface[i] = (uint8_t)(max(h, sea) + 1);
     // column maximum of m: warp first, one atomic per warp (a warp is one z-row of one column)
@@ -250,8 +293,10 @@ __global__ void __launch_bounds__(256) gc_gen_layers_kernel(GenArgs a)
     const int col = blockIdx.x >> 2;
     const int z = (blockIdx.x & 3) * 8 + (threadIdx.x >> 5), x = threadIdx.x & 31;
     const int cx = col % a.size_x, cz = col / a.size_x;
-    const int sea = a.islands ? 20 : 10;
-    const int h = a.height[col * 1024 + z * 32 + x];
+    const int sea = sea_level(a.biome);
+    const int hraw = a.height[col * 1024 + z * 32 + x];
+    const int h = hraw & (kIceBit - 1);
+    const bool ice = (hraw & kIceBit) != 0;
     const int top = a.max_y[col];
     const int wx = (a.origin_cx + cx) * 32 + x, wz = (a.origin_cz + cz) * 32 + z;
     const float fx = mul(mul((float)wx, 0.015f), 0.2f), fz = mul(mul((float)wz, 0.015f), 0.2f);
@@ -259,12 +304,23 @@ __global__ void __launch_bounds__(256) gc_gen_layers_kernel(GenArgs a)
     {
         int b = B_AIR;
         bool stone = false;
-        if (wy <= h - 4)
+        if (a.biome != T_DESERT && wy <= h - 4)
         {
             const float comp = mul(add(fbm3(a.seed + 404u, fx, mul(mul((float)wy, 0.015f), 0.2f), fz, 2), 1.0f), 0.5f);
             stone = comp <= 0.2f;
         }
         if (stone) b = B_STONE;
+        else if (a.biome == T_SNOW)
+        {
+            // (Generation.cpp:525-539) the sea-level layer is tested before "below the surface": a column taller than the sea
+            // holds water (or ice) at y = 20 inside its dirt
+            if (wy == h) b = B_SNOW;
+            else if (wy > h && wy < sea) b = B_WATER;
+            else if (wy == sea) b = ice ? B_ICE : B_WATER;
+            else if (wy < h) b = B_DIRT;
+        }
+        else if (a.biome == T_DESERT) b = wy <= h ? B_SAND : (wy <= sea ? B_WATER : B_AIR);          // (:610-613)
+        else if (a.biome == T_VOLCANIC) b = wy <= h ? B_OBSIDIAN : (wy <= sea ? B_LAVA : B_AIR);     // (:750-753)
         else if (wy == h) b = B_GRASS;
         else if (wy > h && wy <= sea) b = B_WATER;
         else if (wy < h) b = B_DIRT;
@@ -299,9 +355,25 @@ __global__ void gc_gen_trees_kernel(GenArgs a)
     if (col >= a.size_x * a.size_z) return;
     const int cx = col % a.size_x, cz = col / a.size_x;
     const int wcx = a.origin_cx + cx, wcz = a.origin_cz + cz;
-    const int sea = a.islands ? 20 : 10;
+    const int sea = sea_level(a.biome);
     Rng r = { ((uint64_t)hash3(a.seed, wcx, wcz, 77) << 32) | hash3(a.seed, wcz, wcx, 78) };
-    const int trees = a.islands ? rng_range(r, 1, 3) : rng_range(r, 3, 6);
+    if (a.biome == T_DESERT)
+    {
+        // zero to two cacti anywhere in the column, two to four blocks on top of the surface entry — under water too (Generation.cpp:630-641)
+        const int cacti = rng_range(r, 0, 2);
+        for (int i = 0; i < cacti; i++)
+        {
+            const int rx = rng_range(r, 0, 31);
+            const int rz = rng_range(r, 0, 31);
+            const int ch = rng_range(r, 2, 4);
+            const int s = a.height[col * 1024 + rz * 32 + rx];
+            for (int j = 1; j <= ch; j++) set_block(a, col, rx, s + j, rz, B_CACTUS);
+            raise_surface(a, col, rx, rz, rx, rz, s + ch);
+        }
+        return;
+    }
+    if (a.biome != T_FOREST && a.biome != T_ISLANDS) return;   // snow and volcanic columns carry no decoration
+    const int trees = a.biome == T_ISLANDS ? rng_range(r, 1, 3) : rng_range(r, 3, 6);
     for (int i = 0; i < trees; i++)
     {
         const int rx = rng_range(r, 3, 32 - 4);
@@ -324,6 +396,19 @@ __global__ void gc_gen_trees_kernel(GenArgs a)
         raise_surface(a, col, rx - 1, rz + 2, rx + 1, rz + 2, sy + 2);
         raise_surface(a, col, rx - 1, rz - 2, rx + 1, rz - 2, sy + 2);
     }
+}
+
+// GenerateDungeon (Dungeon.cpp:17-31): in the column's lowest chunk a stone floor and four stone walls eleven blocks high along
+// the column's border.  One thread per (column, z, x).
+__global__ void __launch_bounds__(256) gc_gen_dungeon_kernel(GenArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.size_x * a.size_z * 1024) return;
+    const int col = i >> 10, z = (i >> 5) & 31, x = i & 31;
+    const bool wall = x == 0 || x == 31 || z == 0 || z == 31;
+    const int top = wall ? 10 : 0;
+    for (int y = 0; y <= top; y++) set_block(a, col, x, y, z, B_STONE);
+    a.surface[i] = (uint8_t)(top + 1);
 }
 
 // ---- the reference's three generators that use no noise: reproduced exactly (pinned against the reference's own code) ----
@@ -401,6 +486,13 @@ cudaError_t launch_generate_terrain(const GenArgs& a, cudaStream_t s)
     gc_gen_height_kernel<<<(n_cols * 1024 + 255) / 256, 256, 0, s>>>(a);
     gc_gen_layers_kernel<<<n_cols * 4, 256, 0, s>>>(a);
     gc_gen_trees_kernel<<<(n_cols + 63) / 64, 64, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_generate_dungeon(const GenArgs& a, cudaStream_t s)
+{
+    const int n = a.size_x * a.size_z * 1024;
+    gc_gen_dungeon_kernel<<<(n + 255) / 256, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

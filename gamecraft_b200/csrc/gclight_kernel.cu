@@ -9,6 +9,8 @@
 //   blockLight  seeds = emitters of the pre-processed columns up to maxY (Lighting.cpp:231-281); candidates = the
 //               non-opaque cells of the bricks within one brick of a seed (light travels < 15 voxels)
 // A value falls by at least one per hop, so 14 sweeps reach the fixpoint whatever the order of the updates.
+// The whole-window fill (gcmesh_world_light) keeps its candidates as bit maps (one word per x-row of a brick) and its active set
+// per brick: nothing is sized on the host, so the call enqueues a fixed sequence of launches and never synchronises.
 // Canonical form of the reference's column-order dependent block-light seeding: see oracle/gc_light_cpu.c.
 #include "gclight_kernel.cuh"
 
@@ -78,9 +80,15 @@ __global__ void __launch_bounds__(256) gc_surface_max_kernel(LightWorld w, const
     reinterpret_cast<uint32_t*>(w.surface + (size_t)col * 1024)[q] = best;
 }
 
-// ---- scan of every column cell up to maxY: appends the sunlight candidates, seeds the emitters ----
-// Entries beyond `cap` are counted but not written (the caller grows the list and scans again).
-__global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32_t* sun_list, uint32_t cap, uint8_t* brick_flags, uint32_t* counters)
+// ---- scan of every column cell up to maxY: candidate bit maps, emitters seeded ----
+// A warp owns one z-row of one column (lane = x) and walks up its cells, so a ballot is one word of a bit map: word
+// (slot * 2048 + z * 64 + y) = voxel index >> 5.
+//   sun_bits   bit x = the cell is a sunlight candidate (non-opaque, below its column's surface)
+//   opq_bits   bit x = the cell is opaque (rows the walk never reaches are air: the maps are cleared beforehand)
+//   sun_flag   per brick: it holds a sunlight candidate (the first sweep's active set, and the bricks worth visiting at all)
+//   seed_flag  per brick: it holds a seeded emitter (the first block-light sweep's active set)
+__global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32_t* __restrict__ sun_bits, uint32_t* __restrict__ opq_bits,
+                                                            uint8_t* sun_flag, uint8_t* seed_flag, uint32_t* counters)
 {
     const int lane = threadIdx.x & 31;
     const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
@@ -101,10 +109,11 @@ __global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32
         my = max(max(max(my, sf), max(sb, sl)), sr);
         if (my > GC_WORLD_BLOCK_HEIGHT - 1) my = GC_WORLD_BLOCK_HEIGHT - 1;
     }
-    // candidates lie below the own surface; seeds reach up to maxY
+    // candidates and opaque cells lie below the own surface; seeds reach up to maxY
     int top_w = inner ? my : s - 1;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) top_w = max(top_w, __shfl_xor_sync(0xffffffffu, top_w, d));
+    uint32_t n_cand = 0, n_seed = 0;
     for (int y0 = 0; y0 <= top_w; y0 += 8)
     {
         uint32_t id[8];
@@ -118,73 +127,39 @@ __global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32
         for (int k = 0; k < 8; k++)
         {
             const int y = y0 + k;
+            if (y >= GC_WORLD_BLOCK_HEIGHT) break;                // (warp-uniform)
             const size_t slot = (size_t)col * 4 + (y >> 6);
             const uint32_t v = (uint32_t)(slot * kVox + x + 32 * ((y & 63) + 64 * z));
-            const bool cand = y < s && w.rules->step[id[k]] != 255;
-            const uint32_t m = __ballot_sync(0xffffffffu, cand);
-            if (m)
+            const bool opaque = w.rules->step[id[k]] == 255;
+            const bool cand = y < s && !opaque;
+            const uint32_t mo = __ballot_sync(0xffffffffu, opaque), mc = __ballot_sync(0xffffffffu, cand);
+            if (lane == 0)
             {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&counters[LC_SUN_CAND], (uint32_t)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                if (cand && pos < cap) sun_list[pos] = v;
+                if (mo) opq_bits[v >> 5] = mo;
+                if (mc) { sun_bits[v >> 5] = mc; sun_flag[slot] = 1; n_cand += (uint32_t)__popc(mc); }
             }
             const uint32_t e = w.rules->emitted[id[k]];
             if (inner && y <= my && e > 1)   // CheckForBlockLight (Lighting.cpp:231-245); the arrays were cleared, so this is a max
             {
                 w.light[v] = (uint8_t)e;
-                brick_flags[slot] = 1;
-                atomicAdd(&counters[LC_SEEDS], 1u);
+                seed_flag[slot] = 1;
+                n_seed++;
             }
         }
     }
-}
-
-__global__ void gc_active_bricks_kernel(LightWorld w, const uint8_t* brick_flags, uint32_t* active_list, uint32_t* counters)
-{
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_slots = w.size_x * w.size_z * 4;
-    if (slot >= n_slots) return;
-    const int col = slot >> 2, cy = slot & 3, cx = col % w.size_x, cz = col / w.size_x;
-    bool on = false;
-    for (int dz = -1; dz <= 1; dz++)
-        for (int dx = -1; dx <= 1; dx++)
-            for (int dy = -1; dy <= 1; dy++)
-            {
-                const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
-                if (nx < 0 || nx >= w.size_x || nz < 0 || nz >= w.size_z || ny < 0 || ny > 3) continue;
-                on |= brick_flags[((size_t)nz * w.size_x + nx) * 4 + ny] != 0;
-            }
-    if (on) active_list[atomicAdd(&counters[LC_ACTIVE_BRICKS], 1u)] = (uint32_t)slot;
-}
-
-__global__ void __launch_bounds__(256) gc_light_candidates_kernel(LightWorld w, const uint32_t* active_list, uint32_t* light_list, uint32_t cap, uint32_t* counters)
-{
-    const uint32_t slot = active_list[blockIdx.x];
-    const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < kVox; i += blockDim.x)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_seed += __shfl_xor_sync(0xffffffffu, n_seed, d);
+    if (lane == 0)
     {
-        const uint32_t v = slot * (uint32_t)kVox + (uint32_t)i;
-        const bool cand = w.rules->step[w.blocks[v] & 255u] != 255;
-        const uint32_t m = __ballot_sync(0xffffffffu, cand);
-        if (m)
-        {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&counters[LC_LIGHT_CAND], (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-            if (cand && pos < cap) light_list[pos] = v;
-        }
+        if (n_cand) atomicAdd(&counters[LC_SUN_CAND], n_cand);
+        if (n_seed) atomicAdd(&counters[LC_SEEDS], n_seed);
     }
 }
 
-// `changed` points at this sweep's flag word; the previous sweep's is at changed[-1] (sweep 0: a word preset to 1).  A sweep
-// that changed nothing has reached the fixpoint, so every later sweep returns at once.
+// One candidate cell: the maximum over the six neighbours' offers, stored in place when it beats the cell's value.
 template <bool kSun>
-__device__ __forceinline__ void relax_cell(const LightWorld& w, const uint32_t* __restrict__ list, uint32_t i, uint32_t* changed)
+__device__ __forceinline__ bool relax_voxel(const LightWorld& w, uint32_t v)
 {
-    const uint32_t v = list[i];
     uint8_t* arr = kSun ? w.sun : w.light;
     const int cur = arr[v];
     const uint32_t slot = v >> 16, in = v & 65535u;
@@ -220,17 +195,64 @@ __device__ __forceinline__ void relax_cell(const LightWorld& w, const uint32_t* 
     if (best > cur && best > 1)
     {
         arr[v] = (uint8_t)best;
-        *changed = 1;
+        return true;
     }
+    return false;
+}
+template <bool kSun>
+__device__ __forceinline__ void relax_cell(const LightWorld& w, const uint32_t* __restrict__ list, uint32_t i, uint32_t* changed)
+{
+    if (relax_voxel<kSun>(w, list[i])) *changed = 1;
 }
 
-template <bool kSun>
-__global__ void __launch_bounds__(256) gc_relax_kernel(LightWorld w, const uint32_t* __restrict__ list, uint32_t n, uint32_t* changed)
+// ---- one sweep of the whole-window fill: a CTA per (fill, brick) ----
+// A brick is visited when it, or one of its six face neighbours (light moves by face steps), changed in the previous sweep —
+// the first sweep's "previous" flags are the bricks that hold a sunlight candidate / a seeded emitter.  A sweep in which nothing
+// changed leaves no flag behind and every later launch finds all its CTAs idle.  Inside a brick a warp takes 32 bit-map words
+// at a time (one coalesced load) and visits the rows that have candidates with lane = x, so the six neighbour loads of a
+// row are consecutive bytes.
+__global__ void __launch_bounds__(256) gc_relax_bricks_kernel(LightWorld w, const uint32_t* __restrict__ sun_bits, const uint32_t* __restrict__ opq_bits,
+                                                              const uint8_t* __restrict__ sun_flag, const uint8_t* __restrict__ prev_sun, uint8_t* now_sun,
+                                                              const uint8_t* __restrict__ prev_light, uint8_t* now_light, uint32_t* counters)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (changed[-1] == 0) return;
-    relax_cell<kSun>(w, list, i, changed);
+    const int n_slots = w.size_x * w.size_z * 4;
+    const bool sun = (int)blockIdx.x < n_slots;
+    const int slot = sun ? blockIdx.x : blockIdx.x - n_slots;
+    if (sun && !sun_flag[slot]) return;                           // no candidate in this brick: nothing can change here
+    const uint8_t* prev = sun ? prev_sun : prev_light;
+    {
+        const int col = slot >> 2, cy = slot & 3, cx = col % w.size_x, cz = col / w.size_x;
+        bool on = prev[slot] != 0;
+        if (cy > 0) on |= prev[slot - 1] != 0;
+        if (cy < 3) on |= prev[slot + 1] != 0;
+        if (cx > 0) on |= prev[slot - 4] != 0;
+        if (cx < w.size_x - 1) on |= prev[slot + 4] != 0;
+        if (cz > 0) on |= prev[slot - 4 * w.size_x] != 0;
+        if (cz < w.size_z - 1) on |= prev[slot + 4 * w.size_x] != 0;
+        if (!on) return;                                          // (CTA-uniform)
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t* bits = (sun ? sun_bits : opq_bits) + (size_t)slot * 2048;
+    bool any = false;
+    for (int r0 = warp * 32; r0 < 2048; r0 += 8 * 32)
+    {
+        uint32_t word = bits[r0 + lane];
+        if (!sun) word = ~word;                                   // block light: every non-opaque cell
+        uint32_t rows = __ballot_sync(0xffffffffu, word != 0);
+        while (rows)
+        {
+            const int r = __ffs((int)rows) - 1;
+            rows &= rows - 1;
+            const uint32_t m = __shfl_sync(0xffffffffu, word, r);
+            if ((m >> lane) & 1u)
+            {
+                const uint32_t v = (uint32_t)slot * (uint32_t)kVox + (uint32_t)(r0 + r) * 32u + (uint32_t)lane;
+                if (sun ? relax_voxel<true>(w, v) : relax_voxel<false>(w, v)) any = true;
+            }
+        }
+    }
+    if (__syncthreads_or(any ? 1 : 0) && threadIdx.x == 0) (sun ? now_sun : now_light)[slot] = 1;
+    if (threadIdx.x == 0) atomicAdd(&counters[sun ? LC_SUN_BRICK_SWEEPS : LC_LIGHT_BRICK_SWEEPS], 1u);
 }
 
 // One sweep of both fills in one launch, list lengths read from device memory (the edit path: launch-latency bound, and
@@ -264,32 +286,17 @@ cudaError_t launch_surface(const LightWorld& w, uint8_t* brick_top, cudaStream_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_list, uint32_t cap, uint8_t* brick_flags, uint32_t* counters, cudaStream_t s)
+cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_bits, uint32_t* opq_bits, uint8_t* sun_flag, uint8_t* seed_flag, uint32_t* counters, cudaStream_t s)
 {
-    gc_light_scan_kernel<<<rows_grid(w), 256, 0, s>>>(w, sun_list, cap, brick_flags, counters);
+    gc_light_scan_kernel<<<rows_grid(w), 256, 0, s>>>(w, sun_bits, opq_bits, sun_flag, seed_flag, counters);
     return cudaGetLastError();
 }
 
-cudaError_t launch_active_bricks(const LightWorld& w, const uint8_t* brick_flags, uint32_t* active_list, uint32_t* counters, cudaStream_t s)
+cudaError_t launch_relax_bricks(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, const uint8_t* sun_flag,
+                                const uint8_t* prev_sun, uint8_t* now_sun, const uint8_t* prev_light, uint8_t* now_light, uint32_t* counters, cudaStream_t s)
 {
     const int n_slots = w.size_x * w.size_z * 4;
-    gc_active_bricks_kernel<<<(n_slots + 127) / 128, 128, 0, s>>>(w, brick_flags, active_list, counters);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_light_candidates(const LightWorld& w, const uint32_t* active_list, int n_active, uint32_t* light_list, uint32_t cap, uint32_t* counters, cudaStream_t s)
-{
-    if (n_active <= 0) return cudaSuccess;
-    gc_light_candidates_kernel<<<n_active, 256, 0, s>>>(w, active_list, light_list, cap, counters);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_relax(const LightWorld& w, bool sun, const uint32_t* list, uint32_t n, uint32_t* changed, cudaStream_t s)
-{
-    if (n == 0) return cudaSuccess;
-    const unsigned grid = (n + 255u) / 256u;
-    if (sun) gc_relax_kernel<true><<<grid, 256, 0, s>>>(w, list, n, changed);
-    else gc_relax_kernel<false><<<grid, 256, 0, s>>>(w, list, n, changed);
+    gc_relax_bricks_kernel<<<2 * n_slots, 256, 0, s>>>(w, sun_bits, opq_bits, sun_flag, prev_sun, now_sun, prev_light, now_light, counters);
     return cudaGetLastError();
 }
 

@@ -91,6 +91,7 @@ struct GcContext
     int mesh_ctas;            // persistent mesh CTAs that fit the device at once (SMs x resident CTAs per SM)
     EncodeTiledFn encode;
     DeviceTables* d_tables;
+    int n_block_types;        // size of the block table in use (gcmesh_set_block_table)
     LightRules* d_light_rules;
     int use_tma;
     // gcmesh_mesh_host pipeline
@@ -125,15 +126,16 @@ struct GcWorld
     // light fill scratch (grown on demand)
     uint32_t* d_light_counters;   // 8 x u32
     uint32_t* h_light_counters;   // pinned
-    uint8_t* d_brick_flags;
+    uint8_t* d_brick_flags;       // per brick and sweep: changed (2 x (kLightSweeps + 1) arrays)
+    uint32_t* d_light_bits;       // candidate bit maps: sunlight candidates, then opaque cells (2048 words per brick each)
     uint8_t* d_brick_top;         // compute_surface scratch: per brick, the highest block of every column cell
-    uint32_t* d_active_list;
-    uint32_t* d_sun_list; size_t sun_list_cap;
-    uint32_t* d_light_list; size_t light_list_cap;
-    int light_launches; uint32_t light_stats[4];
+    int light_launches;
     // both light arenas are known to hold zeros (fresh window, gcmesh_world_generate): gcmesh_world_light need not clear them.
     // Every writer of the arenas resets it; handing out the raw pointers or connecting a halo peer disables it for good.
     bool light_zero, light_untracked;
+    // the last writer of the light arenas was a sparse upload: arrays no mesh can depend on were skipped (and cleared), so the
+    // arenas do not hold the whole light fixpoint that gcmesh_world_set_blocks builds on.  gcmesh_world_light and full uploads clear it.
+    bool light_partial;
     // terrain generation scratch (gcmesh_world_generate)
     int16_t* d_gen_height; int32_t* d_gen_max_y;
     // peer-memory halo exchange (gcmesh_world_halo_*)
@@ -255,6 +257,7 @@ static int upload_tables(GcContext* ctx, const GcBlockInfo* table, int n, int ki
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     delete h;
     if (e != cudaSuccess) return fail(GC_ERR_CUDA, "upload block table", cudaGetErrorString(e));
+    ctx->n_block_types = n;
     return GC_OK;
 }
 
@@ -446,7 +449,7 @@ int gcmesh_world_destroy(GcWorld* w)
     if (w->h_rle_bad) cudaFreeHost(w->h_rle_bad);
     if (w->h_rle_words) cudaFreeHost(w->h_rle_words);
     cudaFree(w->d_brick_top);
-    cudaFree(w->d_light_counters); cudaFree(w->d_brick_flags); cudaFree(w->d_active_list); cudaFree(w->d_sun_list); cudaFree(w->d_light_list);
+    cudaFree(w->d_light_counters); cudaFree(w->d_brick_flags); cudaFree(w->d_light_bits);
     if (w->h_light_counters) cudaFreeHost(w->h_light_counters);
     for (int d = 0; d < 2; d++)
         for (int k = 0; k < 5; k++)
@@ -498,6 +501,7 @@ int gcmesh_world_upload_rows(GcWorld* w, int cz0, int cz1, const uint16_t* block
     memset(w->slot_dirty + (size_t)cz0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, 7, (size_t)(cz1 - cz0) * w->size_x * GC_WORLD_CHUNK_HEIGHT);
     if (blocks) GC_CUDA(cudaMemcpyAsync(w->d_blocks + s0, blocks + s0, ns * 2, cudaMemcpyHostToDevice, w->ctx->stream));
     if (sunlight || block_light) w->light_zero = false;
+    if (sunlight && block_light && cz0 == 0 && cz1 == w->size_z) w->light_partial = false;   // every light array of the window is replaced
     if (sunlight) GC_CUDA(cudaMemcpyAsync(w->d_sun + s0, sunlight + s0, ns, cudaMemcpyHostToDevice, w->ctx->stream));
     if (block_light) GC_CUDA(cudaMemcpyAsync(w->d_light + s0, block_light + s0, ns, cudaMemcpyHostToDevice, w->ctx->stream));
     if (surface)
@@ -738,6 +742,7 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
     const size_t c_begin = s_begin / GC_WORLD_CHUNK_HEIGHT, c_end = s_end / GC_WORLD_CHUNK_HEIGHT;
     uint32_t* items = w->h_items + s_begin * 3;   // this row range's own part of the pinned work list
     w->light_zero = false;
+    w->light_partial = true;
     int n_items = 0;
     // Non-zero arrays.  A terrain world's non-zero bricks lie at the same height in column after column, and a column's four
     // bricks are consecutive slots: the same array of brick cy of k consecutive columns is a strided block — k rows of one
@@ -859,6 +864,35 @@ int gcmesh_world_set_origin(GcWorld* w, int origin_cx, int origin_cz)
     return GC_OK;
 }
 
+int gcmesh_world_validate_blocks(GcWorld* w, unsigned long long* n_invalid, GcChunkCoord* first_chunk, int* first_voxel)
+{
+    if (!w || !n_invalid) return fail(GC_ERR_ARG, "null argument");
+    GcContext* ctx = w->ctx;
+    GC_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long* d_out = nullptr;
+    GC_CUDA(cudaMalloc(&d_out, 2 * sizeof(unsigned long long)));
+    unsigned long long h[2] = { 0ull, ~0ull };
+    cudaError_t e = cudaMemcpyAsync(d_out, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_validate_blocks(w->d_blocks, w->n_slots * GC_CHUNK_SIZE_3, ctx->n_block_types, d_out, ctx->num_sms, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "validate blocks", cudaGetErrorString(e));
+    *n_invalid = h[0];
+    if (h[0])
+    {
+        const size_t slot = (size_t)(h[1] / GC_CHUNK_SIZE_3);
+        if (first_chunk)
+        {
+            first_chunk->cy = (int)(slot % GC_WORLD_CHUNK_HEIGHT);
+            first_chunk->cx = (int)((slot / GC_WORLD_CHUNK_HEIGHT) % w->size_x);
+            first_chunk->cz = (int)((slot / GC_WORLD_CHUNK_HEIGHT) / w->size_x);
+        }
+        if (first_voxel) *first_voxel = (int)(h[1] % GC_CHUNK_SIZE_3);
+    }
+    return GC_OK;
+}
+
 int gcmesh_world_upload_launches(const GcWorld* w) { return w ? w->launches : 0; }
 unsigned long long gcmesh_world_upload_bytes(const GcWorld* w) { return w ? w->upload_bytes : 0; }
 
@@ -937,16 +971,6 @@ int gcmesh_world_compute_surface(GcWorld* w)
     return GC_OK;
 }
 
-static int grow_list(uint32_t** list, size_t* cap, size_t need)
-{
-    if (need <= *cap) return GC_OK;
-    cudaFree(*list); *list = nullptr; *cap = 0;
-    const size_t n = need + need / 8 + 1024;
-    if (cudaMalloc(list, n * sizeof(uint32_t)) != cudaSuccess) return fail(GC_ERR_CUDA, "cudaMalloc", "light candidate list");
-    *cap = n;
-    return GC_OK;
-}
-
 int gcmesh_world_light(GcWorld* w)
 {
     if (!w) return fail(GC_ERR_ARG, "world is null");
@@ -955,23 +979,24 @@ int gcmesh_world_light(GcWorld* w)
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    // Nothing below depends on a count the device produces: candidates are bit maps of fixed size (a word per x-row of a
+    // brick), the active set is a byte per brick and sweep — the call enqueues a fixed sequence and returns.
+    const size_t bits_bytes = w->n_slots * 2048 * sizeof(uint32_t);
+    const size_t flag_stride = (w->n_slots + 255) & ~(size_t)255;
+    const size_t flags_bytes = 2 * (size_t)(kLightSweeps + 1) * flag_stride;        // sunlight, then blockLight: sweep k reads [k], writes [k + 1]
     if (!w->d_light_counters)
     {
         GC_CUDA(cudaMalloc(&w->d_light_counters, kLightCounterWords * sizeof(uint32_t)));
         GC_CUDA(cudaMallocHost(&w->h_light_counters, kLightCounterWords * sizeof(uint32_t)));
-        GC_CUDA(cudaMalloc(&w->d_brick_flags, w->n_slots));
-        GC_CUDA(cudaMalloc(&w->d_active_list, w->n_slots * sizeof(uint32_t)));
+        GC_CUDA(cudaMalloc(&w->d_light_bits, 2 * bits_bytes));
+        GC_CUDA(cudaMalloc(&w->d_brick_flags, flags_bytes));
     }
     const LightWorld lw = light_world(w);
     uint32_t* c = w->d_light_counters;
-    uint32_t* hc = w->h_light_counters;
-    w->light_launches = 0;
-    auto read_counters = [&]() -> int
-    {
-        GC_CUDA(cudaMemcpyAsync(hc, c, LC_FLAGS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        GC_CUDA(cudaStreamSynchronize(s));
-        return GC_OK;
-    };
+    uint32_t* sun_bits = w->d_light_bits;
+    uint32_t* opq_bits = w->d_light_bits + w->n_slots * 2048;
+    uint8_t* sun_flags = w->d_brick_flags;
+    uint8_t* light_flags = w->d_brick_flags + (size_t)(kLightSweeps + 1) * flag_stride;
     // freshly generated chunks hold no light (World.cpp:632): the fill starts from zero (arenas known to be zero are not cleared again)
     if (!(w->light_zero && !w->light_untracked))
     {
@@ -979,60 +1004,42 @@ int gcmesh_world_light(GcWorld* w)
         GC_CUDA(cudaMemsetAsync(w->d_light, 0, w->n_slots * GC_CHUNK_SIZE_3, s));
     }
     w->light_zero = false;
+    w->light_partial = false;   // from here on the arenas hold the whole fill
     GC_CUDA(cudaMemsetAsync(c, 0, kLightCounterWords * sizeof(uint32_t), s));
-    // 1. one pass over the column cells up to maxY: sunlight candidates into the list, emitters seeded.  The list keeps
-    // its capacity between calls; when it turns out too small the pass is repeated once with the exact size.
-    if (!w->d_sun_list && grow_list(&w->d_sun_list, &w->sun_list_cap, w->n_slots * 1024) != GC_OK) return GC_ERR_CUDA;
-    uint32_t n_sun = 0, n_seeds = 0, n_active = 0, n_light = 0;
-    for (int attempt = 0; attempt < 2; attempt++)
-    {
-        GC_CUDA(cudaMemsetAsync(c, 0, LC_FLAGS * sizeof(uint32_t), s));
-        GC_CUDA(cudaMemsetAsync(w->d_brick_flags, 0, w->n_slots, s));
-        GC_CUDA(launch_light_scan(lw, w->d_sun_list, (uint32_t)w->sun_list_cap, w->d_brick_flags, c, s)); w->light_launches++;
-        // 2. bricks in reach of a seed
-        GC_CUDA(launch_active_bricks(lw, w->d_brick_flags, w->d_active_list, c, s)); w->light_launches++;
-        if (read_counters() != GC_OK) return GC_ERR_CUDA;
-        n_sun = hc[LC_SUN_CAND]; n_seeds = hc[LC_SEEDS]; n_active = hc[LC_ACTIVE_BRICKS];
-        if (n_sun <= w->sun_list_cap) break;
-        if (grow_list(&w->d_sun_list, &w->sun_list_cap, n_sun) != GC_OK) return GC_ERR_CUDA;
-    }
-    //    ... and their non-opaque cells (same capacity policy)
-    if (n_active)
-    {
-        if (!w->d_light_list && grow_list(&w->d_light_list, &w->light_list_cap, (size_t)n_active * 8192) != GC_OK) return GC_ERR_CUDA;
-        for (int attempt = 0; attempt < 2; attempt++)
-        {
-            GC_CUDA(cudaMemsetAsync(c + LC_LIGHT_CAND, 0, sizeof(uint32_t), s));
-            GC_CUDA(launch_light_candidates(lw, w->d_active_list, (int)n_active, w->d_light_list, (uint32_t)w->light_list_cap, c, s)); w->light_launches++;
-            if (read_counters() != GC_OK) return GC_ERR_CUDA;
-            n_light = hc[LC_LIGHT_CAND];
-            if (n_light <= w->light_list_cap) break;
-            if (grow_list(&w->d_light_list, &w->light_list_cap, n_light) != GC_OK) return GC_ERR_CUDA;
-        }
-    }
-    // 3. relaxation: a value falls by at least one per hop and nothing at or below MIN_LIGHT is stored, so 14 in-place
-    // sweeps reach the fixpoint (the sweeps are enqueued back to back; no host round trip in between)
-    // (a sweep that changes nothing ends the relaxation: later sweeps see its flag and return at once)
-    {
-        const uint32_t one = 1;
-        GC_CUDA(cudaMemcpyAsync(c + LC_FLAGS, &one, sizeof(one), cudaMemcpyHostToDevice, s));
-        GC_CUDA(cudaMemcpyAsync(c + LC_FLAGS + kLightSweeps + 1, &one, sizeof(one), cudaMemcpyHostToDevice, s));
-    }
+    GC_CUDA(cudaMemsetAsync(w->d_light_bits, 0, 2 * bits_bytes, s));
+    GC_CUDA(cudaMemsetAsync(w->d_brick_flags, 0, flags_bytes, s));
+    w->light_launches = 0;
+    // 1. one pass over the column cells up to maxY: candidate bit maps, emitters seeded, the first sweep's active bricks
+    GC_CUDA(launch_light_scan(lw, sun_bits, opq_bits, sun_flags, light_flags, c, s)); w->light_launches++;
+    // 2. relaxation: a value falls by at least one per hop and nothing at or below MIN_LIGHT is stored, so 14 in-place sweeps
+    // reach the fixpoint; a sweep visits the bricks that changed in the one before (or whose face neighbours did), so the
+    // launches after the fixpoint find nothing to do
     for (int sweep = 0; sweep < kLightSweeps; sweep++)
     {
-        GC_CUDA(launch_relax(lw, true, w->d_sun_list, n_sun, c + LC_FLAGS + 1 + sweep, s)); if (n_sun) w->light_launches++;
-        GC_CUDA(launch_relax(lw, false, w->d_light_list, n_light, c + LC_FLAGS + kLightSweeps + 2 + sweep, s)); if (n_light) w->light_launches++;
+        GC_CUDA(launch_relax_bricks(lw, sun_bits, opq_bits, sun_flags, sun_flags + (size_t)sweep * flag_stride, sun_flags + (size_t)(sweep + 1) * flag_stride,
+                                    light_flags + (size_t)sweep * flag_stride, light_flags + (size_t)(sweep + 1) * flag_stride, c, s));
+        w->light_launches++;
     }
-    w->light_stats[0] = n_sun; w->light_stats[1] = n_light; w->light_stats[2] = n_active; w->light_stats[3] = n_seeds;
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
     memset(w->slot_dirty, 7, w->n_slots);
     return GC_OK;
 }
 
-int gcmesh_world_light_stats(const GcWorld* w, uint32_t* stats4, int* launches)
+int gcmesh_world_light_stats(GcWorld* w, uint32_t* stats4, int* launches)
 {
     if (!w) return fail(GC_ERR_ARG, "world is null");
-    if (stats4) memcpy(stats4, w->light_stats, sizeof(w->light_stats));
+    if (stats4)
+    {
+        memset(stats4, 0, 4 * sizeof(uint32_t));
+        if (w->d_light_counters)
+        {
+            GC_CUDA(cudaSetDevice(w->ctx->device));
+            GC_CUDA(cudaMemcpyAsync(w->h_light_counters, w->d_light_counters, LC_FLAGS * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->ctx->stream));
+            GC_CUDA(cudaStreamSynchronize(w->ctx->stream));
+            stats4[0] = w->h_light_counters[LC_SUN_CAND]; stats4[1] = w->h_light_counters[LC_LIGHT_BRICK_SWEEPS];
+            stats4[2] = w->h_light_counters[LC_SUN_BRICK_SWEEPS]; stats4[3] = w->h_light_counters[LC_SEEDS];
+        }
+    }
     if (launches) *launches = w->light_launches;
     return GC_OK;
 }
@@ -1055,8 +1062,8 @@ int gcmesh_world_download(GcWorld* w, uint16_t* blocks, uint8_t* sunlight, uint8
 int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, int origin_cz, int radius, int falloff)
 {
     if (!w) return fail(GC_ERR_ARG, "world is null");
-    if (kind < GC_GEN_FLAT || kind > GC_GEN_VOID) return fail(GC_ERR_ARG, "unknown generator");
-    if (kind != GC_GEN_VOID && (radius <= 0 || falloff < 0 || falloff >= radius)) return fail(GC_ERR_ARG, "need 0 <= falloff < radius");
+    if (kind < GC_GEN_FLAT || kind > GC_GEN_DUNGEON) return fail(GC_ERR_ARG, "unknown generator");
+    if (kind != GC_GEN_VOID && kind != GC_GEN_DUNGEON && (radius <= 0 || falloff < 0 || falloff >= radius)) return fail(GC_ERR_ARG, "need 0 <= falloff < radius");
     // Square() in IsWithinIsland is integer arithmetic (Generation.cpp:68): keep world coordinates where it cannot overflow
     {
         const long long lim = 32000;
@@ -1082,8 +1089,10 @@ int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, in
     GenArgs a;
     a.blocks = w->d_blocks; a.surface = w->d_surface; a.height = w->d_gen_height; a.max_y = w->d_gen_max_y;
     a.size_x = w->size_x; a.size_z = w->size_z; a.origin_cx = origin_cx; a.origin_cz = origin_cz;
-    a.seed = seed; a.islands = kind == GC_GEN_ISLANDS; a.radius = radius; a.falloff = falloff;
+    a.seed = seed; a.radius = radius; a.falloff = falloff;
+    a.biome = kind == GC_GEN_ISLANDS ? 1 : (kind == GC_GEN_SNOW ? 2 : (kind == GC_GEN_DESERT ? 3 : (kind == GC_GEN_VOLCANIC ? 4 : 0)));
     if (kind == GC_GEN_FLAT) GC_CUDA(launch_generate_flat(a, s));
+    else if (kind == GC_GEN_DUNGEON) GC_CUDA(launch_generate_dungeon(a, s));
     else if (kind == GC_GEN_GRID || kind == GC_GEN_VOID)
     {
         if (surface_scratch(w) != GC_OK) return GC_ERR_CUDA;
@@ -1094,6 +1103,7 @@ int gcmesh_world_generate(GcWorld* w, int kind, uint32_t seed, int origin_cx, in
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
     memset(w->slot_dirty, 7, w->n_slots);
     w->light_zero = true;
+    w->light_partial = false;
     return GC_OK;
 }
 
@@ -1245,6 +1255,10 @@ int gcmesh_world_set_blocks(GcWorld* w, const GcBlockEdit* edits, int n, int32_t
             return fail(GC_ERR_ARG, "edit outside the pre-processed (non-edge) columns of the window");
     }
     if (n == 0) return GC_OK;
+    // the relight reads the cells around its box as the fixpoint they are supposed to hold: a sparse upload left light arrays
+    // out (those no mesh depends on), so the window's light is not that fixpoint
+    if (w->light_partial)
+        return fail(GC_ERR_STATE, "the window's light arrays come from a sparse upload (gcmesh_world_upload_sparse / gcmesh_mesh_host): run gcmesh_world_light or a full upload before editing");
     w->light_zero = false;
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));

@@ -36,8 +36,15 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 SOURCES = ["gcmesh_kernel.cu", "gclight_kernel.cu", "gcrle_kernel.cu", "gcedit_kernel.cu", "gchalo_kernel.cu", "gcgen_kernel.cu", "gcfill_kernel.cu", "gcmesh_api.cu"]
 
 
+GEN_KINDS = {"flat": 0, "forest": 1, "islands": 2, "grid": 3, "void": 4, "snow": 5, "desert": 6, "volcanic": 7, "dungeon": 8}   # GC_GEN_*
+
+
 class GcMeshError(RuntimeError):
-    pass
+    """A C-ABI call failed; ``status`` is its negative GcStatus."""
+
+    def __init__(self, message: str, status: int = 0):
+        super().__init__(message)
+        self.status = status
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -80,7 +87,7 @@ EXPORTS = [
     "gcmesh_version", "gcmesh_last_error", "gcmesh_create", "gcmesh_destroy", "gcmesh_set_stream",
     "gcmesh_set_block_table", "gcmesh_default_block_table", "gcmesh_synchronize",
     "gcmesh_world_create", "gcmesh_world_destroy", "gcmesh_world_upload_chunk", "gcmesh_world_upload_surface",
-    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_set_option", "gcmesh_world_set_origin", "gcmesh_world_upload_launches", "gcmesh_world_upload_bytes", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
+    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_set_option", "gcmesh_world_set_origin", "gcmesh_world_validate_blocks", "gcmesh_world_upload_launches", "gcmesh_world_upload_bytes", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
     "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
     "gcmesh_world_halo_export", "gcmesh_world_halo_connect_ipc", "gcmesh_world_halo_connect_local", "gcmesh_world_halo_push", "gcmesh_world_halo_status",
     "gcmesh_default_light_rules", "gcmesh_set_light_rules", "gcmesh_world_compute_surface", "gcmesh_world_light",
@@ -123,6 +130,7 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_upload_sparse.argtypes = [vp, vp, vp, vp, vp, vp, ci]
         L.gcmesh_world_set_option.argtypes = [vp, ci, ci]
         L.gcmesh_world_set_origin.argtypes = [vp, ci, ci]
+        L.gcmesh_world_validate_blocks.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), vp, ctypes.POINTER(ci)]
         L.gcmesh_world_upload_launches.argtypes = [vp]
         L.gcmesh_world_upload_bytes.argtypes = [vp]
         L.gcmesh_world_upload_bytes.restype = ctypes.c_uint64
@@ -171,7 +179,7 @@ def lib() -> ctypes.CDLL:
 
 def _check(status: int, what: str) -> None:
     if status != 0:
-        raise GcMeshError("%s failed (%d): %s" % (what, status, lib().gcmesh_last_error().decode()))
+        raise GcMeshError("%s failed (%d): %s" % (what, status, lib().gcmesh_last_error().decode()), status)
 
 
 def _ptr(a) -> ctypes.c_void_p:
@@ -276,6 +284,15 @@ class World:
         _check(lib().gcmesh_world_set_origin(self.h, int(origin_cx), int(origin_cz)), "gcmesh_world_set_origin")
         return self
 
+    def validate_blocks(self):
+        """(number of block ids >= the block table's size, (cx, cy, cz) of the first one's chunk, its voxel index) — the
+        reference's ``assert(block < BLOCK_COUNT)`` (Code/World.cpp:294) as a scan of the device window."""
+        n = ctypes.c_uint64(0)
+        c = np.zeros(3, np.int32)
+        v = ctypes.c_int(-1)
+        _check(lib().gcmesh_world_validate_blocks(self.h, ctypes.byref(n), _ptr(c), ctypes.byref(v)), "gcmesh_world_validate_blocks")
+        return int(n.value), (tuple(int(x) for x in c) if n.value else None), (int(v.value) if n.value else None)
+
     def upload_bytes(self) -> int:
         """Host -> device bytes the last sparse upload / mesh_host call moved."""
         return int(lib().gcmesh_world_upload_bytes(self.h))
@@ -312,7 +329,7 @@ class World:
     def light_stats(self):
         st, n = np.zeros(4, np.uint32), ctypes.c_int(0)
         _check(lib().gcmesh_world_light_stats(self.h, _ptr(st), ctypes.byref(n)), "gcmesh_world_light_stats")
-        return {"sun_candidates": int(st[0]), "light_candidates": int(st[1]), "active_bricks": int(st[2]), "seeds": int(st[3]), "launches": n.value}
+        return {"sun_candidates": int(st[0]), "light_brick_sweeps": int(st[1]), "sun_brick_sweeps": int(st[2]), "seeds": int(st[3]), "launches": n.value}
 
     # -- region records (the reference's saved-chunk format, Code/WorldIO.cpp:167-307) --
     def upload_rle(self, chunks: np.ndarray, data: np.ndarray) -> "World":
@@ -339,8 +356,9 @@ class World:
         return out, data[:used]
 
     def generate(self, kind, seed: int = 1337, origin=(0, 0), radius: int = 2**31 - 1, falloff: int | None = None) -> "World":
-        """Terrain of every column of the window, generated on the device ("flat", "forest", "islands", "grid" or "void")."""
-        k = {"flat": 0, "forest": 1, "islands": 2, "grid": 3, "void": 4}[kind] if isinstance(kind, str) else int(kind)
+        """Terrain of every column of the window, generated on the device: the reference's nine biomes ("flat", "forest",
+        "islands", "grid", "void", "snow", "desert", "volcanic", "dungeon"; Code/Environment.cpp:83-143)."""
+        k = GEN_KINDS[kind] if isinstance(kind, str) else int(kind)
         if falloff is None:
             falloff = radius - 64                                                   # World.cpp:911
         _check(lib().gcmesh_world_generate(self.h, k, seed & 0xFFFFFFFF, int(origin[0]), int(origin[1]), int(radius), int(falloff)),

@@ -1,7 +1,7 @@
 """Deterministic synthetic-world producer (ctypes binding of ``libgcworld.so``, see ``gcworld.c``).
 
 Input producer only: it restates the reference's terrain / surface / light-fill *rules*
-(Code/Generation.cpp:83-369,772-836; Code/Lighting.cpp:5-26,109-281) with its own seeded noise, because
+(Code/Generation.cpp:83-836, Code/Dungeon.cpp:17-31; Code/Lighting.cpp:5-26,109-281) with its own seeded noise, because
 the reference's FastNoiseSIMD + ``rand()`` worlds are not reproducible.  The mesher never links it.
 """
 from __future__ import annotations
@@ -18,9 +18,10 @@ _LIB_PATH = os.path.join(_HERE, "libgcworld.so")
 CHUNK_VOXELS = 65536
 CHUNKS_PER_COLUMN = 4
 
-FLAT, FOREST, ISLANDS, CHECKER, NOISE, STRESS, MIXED, EMPTY = range(8)
+FLAT, FOREST, ISLANDS, CHECKER, NOISE, STRESS, MIXED, EMPTY, SNOW, DESERT, VOLCANIC, DUNGEON = range(12)
 KINDS = {"flat": FLAT, "forest": FOREST, "islands": ISLANDS, "checker": CHECKER, "noise": NOISE,
-         "stress": STRESS, "mixed": MIXED, "empty": EMPTY}
+         "stress": STRESS, "mixed": MIXED, "empty": EMPTY, "snow": SNOW, "desert": DESERT, "volcanic": VOLCANIC,
+         "dungeon": DUNGEON}
 INT_MAX = 2**31 - 1
 
 

@@ -5,7 +5,8 @@
  * uint8 blockLight) plus a 32x32 uint8 surface map.  The reference builds them with FastNoiseSIMD +
  * MSVC rand(), neither of which is reproducible here (not vendored / thread-timing dependent), so this
  * file restates the reference's *rules* with its own seeded simplex noise and PRNG:
- *   terrain layering   Code/Generation.cpp:83-226 (forest), :228-369 (islands), :772-836 (flat)
+ *   terrain layering   Code/Generation.cpp:83-226 (forest), :228-369 (islands), :412-556 (snow), :558-645 (desert),
+ *                      :647-770 (volcanic), :772-836 (flat); Code/Dungeon.cpp:17-31 (dungeon)
  *   trees              Code/Generation.cpp:50-64, :204-215
  *   island fall-off    Code/Generation.cpp:66-81
  *   surface map        Code/Lighting.cpp:5-26
@@ -50,7 +51,8 @@ typedef struct GcwWorld
     uint8_t* surface;
 } GcwWorld;
 
-enum { GCW_FLAT = 0, GCW_FOREST = 1, GCW_ISLANDS = 2, GCW_CHECKER = 3, GCW_NOISE = 4, GCW_STRESS = 5, GCW_MIXED = 6, GCW_EMPTY = 7 };
+enum { GCW_FLAT = 0, GCW_FOREST = 1, GCW_ISLANDS = 2, GCW_CHECKER = 3, GCW_NOISE = 4, GCW_STRESS = 5, GCW_MIXED = 6, GCW_EMPTY = 7,
+       GCW_SNOW = 8, GCW_DESERT = 9, GCW_VOLCANIC = 10, GCW_DUNGEON = 11 };
 
 
 /* ------------------------------------------------------------------------------------------ */
@@ -213,6 +215,18 @@ static float billow2(uint32_t seed, float x, float y, int octaves)
     return sum * fractal_bounding(octaves);
 }
 
+/* fBm, 2-D */
+static float fbm2(uint32_t seed, float x, float y, int octaves)
+{
+    float sum = simplex2(seed, x, y), amp = 1.0f;
+    for (int i = 1; i < octaves; i++)
+    {
+        x *= 2.0f; y *= 2.0f; amp *= 0.5f;
+        sum += simplex2(seed + (uint32_t)i, x, y) * amp;
+    }
+    return sum * fractal_bounding(octaves);
+}
+
 /* fBm, 3-D */
 static float fbm3(uint32_t seed, float x, float y, float z, int octaves)
 {
@@ -272,14 +286,20 @@ static int within_island(int wx, int wz, int radius, int falloff, float* p)
 
 static inline float scurve3(float a) { return a * a * (3.0f - 2.0f * a); }
 
-/* Forest / islands layering rules (Generation.cpp:83-226 / :228-369) for one column. */
-static void gen_terrain_column(GcwWorld* w, int cx, int cz, uint32_t seed, int islands, int radius, int falloff)
+/* The five noise terrains (Generation.cpp:83-226 forest, :228-369 islands, :412-556 snow, :558-645 desert, :647-770 volcanic)
+ * for one column: a height field blended from two fractal fields by a biome field (desert: one field), the island fall-off,
+ * stone pockets where a 3-D fBm drops to 0.2 or below from four layers under the surface (not in the desert), the biome's
+ * layering, then its decorations (trees / cacti) from the column's own PRNG stream. */
+enum { T_FOREST = 0, T_ISLANDS = 1, T_SNOW = 2, T_DESERT = 3, T_VOLCANIC = 4 };
+static void gen_terrain_column(GcwWorld* w, int cx, int cz, uint32_t seed, int biome_kind, int radius, int falloff)
 {
-    const int sea = islands ? 20 : 10;
-    const float mscale = islands ? 60.0f : 30.0f, mbase = islands ? 20.0f : 10.0f;
+    static const int SEA[5] = { 10, 20, 20, 10, 12 };
+    const int sea = SEA[biome_kind];
     int wcx = w->origin_cx + cx, wcz = w->origin_cz + cz;
     int height[CH * CH];
+    uint8_t ice[CH * CH];
     int max_y = 0;
+    memset(ice, 0, sizeof(ice));
 
     for (int z = 0; z < CH; z++)
     {
@@ -291,16 +311,45 @@ static void gen_terrain_column(GcwWorld* w, int cx, int cz, uint32_t seed, int i
             if (within_island(wx, wz, radius, falloff, &p))
             {
                 float bx = (float)wx, bz = (float)wz;
-                float biome = simplex2(seed + 101u, bx * 0.01f, bz * 0.01f);
-                float flat = (billow2(seed + 202u, bx * 0.025f * 0.5f, bz * 0.025f * 0.5f, 4) + 1.0f) * 0.5f;
-                flat = flat * 0.2f * 30.0f + 10.0f;
-                float mount = (ridged2(seed + 303u, bx * 0.015f * 0.5f, bz * 0.015f * 0.5f, 4) + 1.0f) * 0.5f;
-                if (mount < 0.0f) mount = 0.0f;
-                mount = powf(mount, 3.5f) * mscale + mbase;
                 float terrain;
-                if (biome < 0.0f) terrain = flat;
-                else if (biome > 0.6f) terrain = mount;
-                else terrain = flat + scurve3(biome / 0.6f) * (mount - flat);
+                if (biome_kind == T_DESERT)
+                {
+                    /* one billow field, frequency 0.05 sampled at scale 0.25, the library's default three octaves (:566-569,:585-586) */
+                    float base = (billow2(seed + 202u, bx * 0.05f * 0.25f, bz * 0.05f * 0.25f, 3) + 1.0f) * 0.5f;
+                    terrain = base * 0.2f * 30.0f + 20.0f;
+                }
+                else if (biome_kind == T_SNOW)
+                {
+                    /* biome: 3-octave fBm at 0.005; sea floor from the billow field, land from the ridged one, blended over
+                     * -0.4 .. 0; the upper part of the blend band freezes the sea surface (:431-479) */
+                    float biome = fbm2(seed + 101u, bx * 0.005f, bz * 0.005f, 3);
+                    float floor_ = (billow2(seed + 202u, bx * 0.025f * 0.5f, bz * 0.025f * 0.5f, 4) + 1.0f) * 0.5f;
+                    floor_ = floor_ * 0.2f * 20.0f + 5.0f;
+                    float land = (ridged2(seed + 303u, bx * 0.015f * 0.5f, bz * 0.015f * 0.5f, 4) + 1.0f) * 0.5f;
+                    land = land * 0.2f * 10.0f + 20.0f;
+                    const float lower = -0.4f, upper = 0.0f;
+                    if (biome < lower) terrain = floor_;
+                    else if (biome > upper) terrain = land;
+                    else
+                    {
+                        if (biome >= -0.25f && biome <= 0.0f) ice[z * CH + x] = 1;
+                        terrain = floor_ + scurve3((biome - lower) / (upper - lower)) * (land - floor_);
+                    }
+                }
+                else
+                {
+                    const float mscale = biome_kind == T_FOREST ? 30.0f : 60.0f, mbase = biome_kind == T_FOREST ? 10.0f : 20.0f;
+                    const float bfreq = biome_kind == T_VOLCANIC ? 0.005f : 0.01f;   /* (:103-104 forest, :248-249 islands, :667-668 volcanic) */
+                    float biome = simplex2(seed + 101u, bx * bfreq, bz * bfreq);
+                    float flat = (billow2(seed + 202u, bx * 0.025f * 0.5f, bz * 0.025f * 0.5f, 4) + 1.0f) * 0.5f;
+                    flat = flat * 0.2f * 30.0f + 10.0f;
+                    float mount = (ridged2(seed + 303u, bx * 0.015f * 0.5f, bz * 0.015f * 0.5f, 4) + 1.0f) * 0.5f;
+                    if (mount < 0.0f) mount = 0.0f;
+                    mount = powf(mount, 3.5f) * mscale + mbase;
+                    if (biome < 0.0f) terrain = flat;
+                    else if (biome > 0.6f) terrain = mount;
+                    else terrain = flat + scurve3(biome / 0.6f) * (mount - flat);
+                }
                 h = (int)(terrain * p);
                 if (h > WH - 12) h = WH - 12;
                 if (h > m) m = h;
@@ -320,12 +369,31 @@ static void gen_terrain_column(GcwWorld* w, int cx, int cz, uint32_t seed, int i
             {
                 int b = B_AIR;
                 int stone = 0;
-                if (wy <= h - 4)
+                if (biome_kind != T_DESERT && wy <= h - 4)
                 {
                     float comp = (fbm3(seed + 404u, (float)wx * 0.015f * 0.2f, (float)wy * 0.015f * 0.2f, (float)wz * 0.015f * 0.2f, 2) + 1.0f) * 0.5f;
                     stone = comp <= 0.2f;
                 }
                 if (stone) b = B_STONE;
+                else if (biome_kind == T_SNOW)
+                {
+                    /* (:525-539) the sea-level layer is tested before "below the surface": a column taller than the sea holds
+                     * water (or ice) at y = 20 inside its dirt, as the reference's branch order has it */
+                    if (wy == h) b = B_SNOW;
+                    else if (wy > h && wy < sea) b = B_WATER;
+                    else if (wy == sea) b = ice[z * CH + x] ? B_ICE : B_WATER;
+                    else if (wy < h) b = B_DIRT;
+                }
+                else if (biome_kind == T_DESERT)
+                {
+                    if (wy <= h) b = B_SAND;                      /* (:610-613) */
+                    else if (wy <= sea) b = B_WATER;
+                }
+                else if (biome_kind == T_VOLCANIC)
+                {
+                    if (wy <= h) b = B_OBSIDIAN;                  /* (:750-753) */
+                    else if (wy <= sea) b = B_LAVA;
+                }
                 else if (wy == h) b = B_GRASS;
                 else if (wy > h && wy <= sea) b = B_WATER;
                 else if (wy < h) b = B_DIRT;
@@ -335,13 +403,39 @@ static void gen_terrain_column(GcwWorld* w, int cx, int cz, uint32_t seed, int i
     }
 
     Rng r = { ((uint64_t)hash3(seed, wcx, wcz, 77) << 32) | hash3(seed, wcz, wcx, 78) };
-    int trees = islands ? rng_range(&r, 1, 3) : rng_range(&r, 3, 6);
-    for (int i = 0; i < trees; i++)
+    if (biome_kind == T_FOREST || biome_kind == T_ISLANDS)
     {
-        int rx = rng_range(&r, 3, CH - 4), rz = rng_range(&r, 3, CH - 4);
-        int s = height[rz * CH + rx];
-        if (s > sea) tree(w, cx, cz, &r, rx, s + 1, rz);
+        int trees = biome_kind == T_ISLANDS ? rng_range(&r, 1, 3) : rng_range(&r, 3, 6);
+        for (int i = 0; i < trees; i++)
+        {
+            int rx = rng_range(&r, 3, CH - 4), rz = rng_range(&r, 3, CH - 4);
+            int s = height[rz * CH + rx];
+            if (s > sea) tree(w, cx, cz, &r, rx, s + 1, rz);
+        }
     }
+    else if (biome_kind == T_DESERT)
+    {
+        /* zero to two cacti anywhere in the column, two to four blocks on top of the surface entry — under water too (:630-641) */
+        int cacti = rng_range(&r, 0, 2);
+        for (int i = 0; i < cacti; i++)
+        {
+            int rx = rng_range(&r, 0, CH - 1), rz = rng_range(&r, 0, CH - 1);
+            int ch = rng_range(&r, 2, 4);
+            for (int j = 1; j <= ch; j++) set_block(w, cx, cz, rx, height[rz * CH + rx] + j, rz, B_CACTUS);
+        }
+    }
+}
+
+/* GenerateDungeon (Dungeon.cpp:17-31): in the column's lowest chunk a stone floor and four stone walls eleven blocks high
+ * along the column's border; no noise, no randomness. */
+static void gen_dungeon_column(GcwWorld* w, int cx, int cz)
+{
+    const int wall = 10, lim = CH - 1;
+    box(w, cx, cz, 0, 0, 0, lim, 0, lim, B_STONE);
+    box(w, cx, cz, 0, 0, 0, lim, wall, 0, B_STONE);
+    box(w, cx, cz, 0, 0, 0, 0, wall, lim, B_STONE);
+    box(w, cx, cz, 0, 0, lim, lim, wall, lim, B_STONE);
+    box(w, cx, cz, lim, 0, 0, lim, wall, lim, B_STONE);
 }
 
 /* GenerateFlatTerrain (Generation.cpp:772-836): sea level 12; inside the island grass at (int)(12 * p) over dirt, water up
@@ -446,8 +540,12 @@ static void gen_column(void* p, int c, int worker)
     switch (g->kind)
     {
         case GCW_FLAT: gen_flat_column(w, cx, cz, g->radius, g->falloff); break;
-        case GCW_FOREST: gen_terrain_column(w, cx, cz, g->seed, 0, g->radius, g->falloff); break;
-        case GCW_ISLANDS: gen_terrain_column(w, cx, cz, g->seed, 1, g->radius, g->falloff); break;
+        case GCW_FOREST: gen_terrain_column(w, cx, cz, g->seed, T_FOREST, g->radius, g->falloff); break;
+        case GCW_ISLANDS: gen_terrain_column(w, cx, cz, g->seed, T_ISLANDS, g->radius, g->falloff); break;
+        case GCW_SNOW: gen_terrain_column(w, cx, cz, g->seed, T_SNOW, g->radius, g->falloff); break;
+        case GCW_DESERT: gen_terrain_column(w, cx, cz, g->seed, T_DESERT, g->radius, g->falloff); break;
+        case GCW_VOLCANIC: gen_terrain_column(w, cx, cz, g->seed, T_VOLCANIC, g->radius, g->falloff); break;
+        case GCW_DUNGEON: gen_dungeon_column(w, cx, cz); break;
         case GCW_CHECKER: gen_checker_column(w, cx, cz, g->seed); break;
         case GCW_NOISE: gen_noise_column(w, cx, cz, g->seed); break;
         case GCW_STRESS: gen_stress_column(w, cx, cz); break;

@@ -150,6 +150,11 @@ enum { GC_WORLD_SURFACE_BOUNDS_BLOCKS = 1, GC_WORLD_COPY_RUN = 2 };
 int gcmesh_world_set_option(GcWorld* world, int option, int value);
 /* World-space column (ChunkGroup::pos, World.h) of window column (0, 0).  Only region records depend on it (gcmesh_world_encode_rle). */
 int gcmesh_world_set_origin(GcWorld* world, int origin_cx, int origin_cz);
+/* The reference asserts block < BLOCK_COUNT wherever a block is stored (World.cpp:294).  The mesh kernel indexes its class
+ * table with the low byte of an id; ids from the table size up to 255 read as AIR, larger ones alias.  This scans the
+ * device window's block ids once (HBM-bound) and reports how many are >= the size of the block table in use and, if any,
+ * the chunk and voxel index (BlockIndex order) of the first.  Synchronous on the context stream. */
+int gcmesh_world_validate_blocks(GcWorld* world, unsigned long long* n_invalid, GcChunkCoord* first_chunk, int* first_voxel);
 /* Kernels launched by the last gcmesh_world_upload_sparse call. */
 int gcmesh_world_upload_launches(const GcWorld* world);
 /* Host -> device bytes the last gcmesh_world_upload_sparse / gcmesh_mesh_host call moved (brick arrays, work lists, surface maps, coordinates). */
@@ -202,11 +207,13 @@ int gcmesh_default_light_rules(uint8_t* step256, uint8_t* emitted256);
 int gcmesh_set_light_rules(GcContext* ctx, const uint8_t* step256, const uint8_t* emitted256);
 /* surface[column][z*32 + x] = highest non-AIR y in 0..254, plus one (0 for an empty column cell).  Asynchronous. */
 int gcmesh_world_compute_surface(GcWorld* world);
-/* Clears the sunlight / blockLight arenas and fills them from the block ids and the surface map.  Enqueued on the
- * context stream; the call itself synchronises twice to size its work lists. */
+/* Clears the sunlight / blockLight arenas and fills them from the block ids and the surface map.  Asynchronous: a fixed
+ * sequence of launches on the context stream (candidates are bit maps, the active set a byte per brick and sweep — nothing is
+ * sized from a device count), no synchronisation. */
 int gcmesh_world_light(GcWorld* world);
-/* Of the last gcmesh_world_light: {sunlight candidates, blockLight candidates, active bricks, seeded emitters}, kernels launched. */
-int gcmesh_world_light_stats(const GcWorld* world, uint32_t* stats4, int* launches);
+/* Of the last gcmesh_world_light: {sunlight candidate cells, (brick, sweep) visits of the blockLight relaxation, of the sunlight
+ * relaxation, seeded emitters}, kernels launched.  Synchronises the context stream to read them. */
+int gcmesh_world_light_stats(GcWorld* world, uint32_t* stats4, int* launches);
 /* Device -> host copy of the window's arrays (NULL skips one); synchronous. */
 int gcmesh_world_download(GcWorld* world, uint16_t* blocks, uint8_t* sunlight, uint8_t* block_light, uint8_t* surface);
 
@@ -232,21 +239,27 @@ int gcmesh_world_rle_refused(GcWorld* world, int* refused);
 int gcmesh_world_encode_rle(GcWorld* world, const GcChunkCoord* coords, int n, uint16_t* records, size_t capacity_words, GcRleChunk* out);
 
 /* ---- terrain generation on the device: columns are born in HBM ----
- * Five of the reference's generators (GenerateFlatTerrain Code/Generation.cpp:772-836, GenerateGridTerrain :371-410,
- * GenerateVoidTerrain :838-852 — no noise involved: identical to the reference's own output; GenerateForestTerrain :83-226,
- * GenerateIslandsTerrain :228-369 with CreateTree :50-64, IsWithinIsland :66-81) fill the block ids of every column
+ * The reference's nine generators (Environment.cpp:83-143) — GenerateFlatTerrain Code/Generation.cpp:772-836,
+ * GenerateGridTerrain :371-410, GenerateVoidTerrain :838-852, GenerateDungeon Code/Dungeon.cpp:17-31: no noise involved,
+ * identical to the reference's own output; GenerateForestTerrain :83-226, GenerateIslandsTerrain :228-369,
+ * GenerateSnowTerrain :412-556, GenerateDesertTerrain :558-645, GenerateVolcanicTerrain :647-770 with CreateTree :50-64,
+ * IsWithinIsland :66-81 — fill the block ids of every column
  * of the window and its surface map (as ComputeSurface would, Lighting.cpp:5-26); sunlight and blockLight are cleared
  * (follow with gcmesh_world_light) and every chunk counts as never built (gcmesh_world_set_blocks refuses it until it is meshed).  origin = world-space column of window column (0, 0); radius / falloff = WorldProperties::radius
- * and World::falloffRadius in blocks (an unbounded world: INT_MAX and INT_MAX - 64).  For forest and islands the layering,
- * tree and fall-off rules are the reference's; its noise (FastNoiseSIMD, not vendored) and its thread-timing dependent rand() are replaced by a seeded
+ * and World::falloffRadius in blocks (an unbounded world: INT_MAX and INT_MAX - 64).  For the five noise terrains the layering,
+ * tree / cactus and fall-off rules are the reference's; its noise (FastNoiseSIMD, not vendored) and its thread-timing dependent rand() are replaced by a seeded
  * simplex noise and a per-column PRNG — the same ones as the host input producer gamecraft_b200/worldgen, whose worlds
  * this call reproduces block for block.  Asynchronous on the context stream. */
-enum { GC_GEN_FLAT = 0, GC_GEN_FOREST = 1, GC_GEN_ISLANDS = 2, GC_GEN_GRID = 3, GC_GEN_VOID = 4 };
+enum { GC_GEN_FLAT = 0, GC_GEN_FOREST = 1, GC_GEN_ISLANDS = 2, GC_GEN_GRID = 3, GC_GEN_VOID = 4,
+       GC_GEN_SNOW = 5, GC_GEN_DESERT = 6, GC_GEN_VOLCANIC = 7, GC_GEN_DUNGEON = 8 };
 int gcmesh_world_generate(GcWorld* world, int kind, uint32_t seed, int origin_cx, int origin_cz, int radius, int falloff);
 
 /* ---- block edits on a device-resident window: the interactive caller of the mesher ----
  * SetBlock(world, lwX, lwY, lwZ, block) (Code/World.cpp:548-582) for a window whose block ids, surface map and light
- * arrays are on the device (gcmesh_world_compute_surface + gcmesh_world_light, or uploads):
+ * arrays are on the device (gcmesh_world_compute_surface + gcmesh_world_light, or FULL uploads of both light arrays: after a
+ * sparse upload — gcmesh_world_upload_sparse, gcmesh_mesh_host — the light arrays no mesh depends on were left out, the
+ * window does not hold the light fixpoint the relight builds on, and the call fails with GC_ERR_STATE until
+ * gcmesh_world_light or gcmesh_world_upload_all with both light arrays has run):
  *   - the reference's decisions: y outside the world is ignored; a chunk that was never meshed refuses the edit
  *     (chunk->state < CHUNK_NEEDS_FILL; here: no gcmesh_submit has covered it); an unchanged block does nothing;
  *     ChunkOverflowed (WorldRender.cpp:412-439) — the new block's own drawable faces on top of the chunk's vertex count

@@ -320,8 +320,8 @@ class RefWorld:
         self.L.gcref_generate_flat(self.h)
 
     def generate(self, kind):
-        """The reference's own noise-free generators over every column: "flat", "grid" or "void"."""
-        assert self.L.gcref_generate(self.h, {"flat": 0, "grid": 3, "void": 4}[kind]) == 0
+        """The reference's own noise-free generators over every column: "flat", "grid", "void" or "dungeon"."""
+        assert self.L.gcref_generate(self.h, {"flat": 0, "grid": 3, "void": 4, "dungeon": 8}[kind]) == 0
 
     def compute_surface(self):
         self.L.gcref_compute_surface_all(self.h)

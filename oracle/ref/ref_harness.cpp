@@ -87,6 +87,7 @@ static void DeleteDirectory(char*) {}
 #include "Lighting.cpp"
 #include "WorldRender.cpp"
 #include "Generation.cpp"
+#include "Dungeon.cpp"
 
 #include <chrono>
 #include <thread>
@@ -254,7 +255,8 @@ void gcref_generate_flat(GcRefWorld* w)
 }
 
 // The reference's generators that need no FastNoiseSIMD, on every column of the window (group->pos = window position):
-// 0 GenerateFlatTerrain (Generation.cpp:772-836), 3 GenerateGridTerrain (:371-410), 4 GenerateVoidTerrain (:838-852).
+// 0 GenerateFlatTerrain (Generation.cpp:772-836), 3 GenerateGridTerrain (:371-410), 4 GenerateVoidTerrain (:838-852),
+// 8 GenerateDungeon (Dungeon.cpp:17-31).
 int gcref_generate(GcRefWorld* w, int kind)
 {
     for (int i = 0; i < w->world->totalGroups; i++)
@@ -263,6 +265,7 @@ int gcref_generate(GcRefWorld* w, int kind)
         if (kind == 0) GenerateFlatTerrain(w->world, g);
         else if (kind == 3) GenerateGridTerrain(w->world, g);
         else if (kind == 4) GenerateVoidTerrain(w->world, g);
+        else if (kind == 8) GenerateDungeon(w->world, g);
         else return -1;
     }
     return 0;

@@ -1,6 +1,8 @@
 """The generators of the reference that need no noise library (GenerateFlatTerrain, GenerateGridTerrain, GenerateVoidTerrain,
-Code/Generation.cpp:772-836, :371-410, :838-852) run from the reference's own sources (oracle/_ref): the host input
-producer's flat rule is pinned against them here, the device generators in tests/test_gpu_generate.py."""
+Code/Generation.cpp:772-836, :371-410, :838-852; GenerateDungeon, Code/Dungeon.cpp:17-31) run from the reference's own
+sources (oracle/_ref): the host input producer's flat and dungeon rules are pinned against them here, the device generators
+in tests/test_gpu_generate.py.  The noise terrains' layering rules (snow, desert, volcanic) are checked for the properties the
+reference's code implies."""
 import numpy as np
 import pytest
 
@@ -42,3 +44,73 @@ def test_reference_grid_and_void_shapes():
         assert chunk[17, 0, 16] == 7 and chunk[16, 62, 16] == 7 and chunk[16, 63, 16] == 0
     void = reference_blocks("void", 3, 50, 0)
     assert int((void != 0).sum()) == 1024 and (void[0].reshape(32, 64, 32)[:, 40, :] == 1).all()
+
+
+@needs_ref
+def test_host_dungeon_rule_equals_reference():
+    """GenerateDungeon: a stone floor and eleven-high walls along the border of every column's lowest chunk."""
+    size = 4
+    want = reference_blocks("dungeon", size, 50, 0)
+    got = util.HostWorld(size, size).generate("dungeon", 1)
+    assert np.array_equal(got.blocks, want)
+    chunk = want[(1 * size + 2) * 4].reshape(32, 64, 32)             # [z][y][x]
+    assert (chunk[:, 0, :] == 3).all() and (chunk[0, :11, :] == 3).all() and (chunk[:, :11, 31] == 3).all()
+    assert not chunk[1:31, 1:, 1:31].any() and not chunk[:, 11:, :].any()
+    assert not want.reshape(size * size, 4, 65536)[:, 1:].any()      # only the lowest chunk of a column is touched
+
+
+def column_profile(w, cx, cz):
+    """(32, 256, 32) [z][y][x] block ids of one column."""
+    return np.concatenate([w.blocks[w.slot(cx, cy, cz)].reshape(32, 64, 32) for cy in range(4)], axis=1)
+
+
+def test_snow_rules():
+    """GenerateSnowTerrain (Generation.cpp:412-556): snow on top, dirt below, water under sea level 20, the sea-level layer is
+    water or ice wherever the surface is not exactly there — also inside taller ground — and stone only four layers down."""
+    w = util.HostWorld(6, 6, origin=(-3, -3)).generate("snow", 11)
+    ids = set(np.unique(w.blocks).tolist())
+    assert ids <= {0, 2, 3, 8, 12, 13} and {2, 8, 12} <= ids
+    saw_ice = saw_buried = False
+    for cz in range(6):
+        for cx in range(6):
+            col = column_profile(w, cx, cz)
+            top = (col != 0).cumsum(axis=1).argmax(axis=1)             # highest non-air y per (z, x)
+            snow_y = (col == 12).argmax(axis=1)
+            assert ((col == 12).sum(axis=1) == 1).all()                # one snow block per cell: the surface
+            h = snow_y
+            level = col[:, 20, :]
+            assert np.isin(level[h != 20], (8, 13)).all()              # y = 20 is water or ice unless it is the surface itself
+            saw_buried |= bool((h > 20).any())
+            saw_ice |= bool((level == 13).any())
+            assert (top == np.maximum(h, 20)).all()
+            below = np.arange(256).reshape(1, 256, 1) < h.reshape(32, 1, 32)
+            assert np.isin(col[below & (np.arange(256).reshape(1, 256, 1) != 20)], (2, 3)).all()
+    assert saw_ice and saw_buried
+
+
+def test_desert_rules():
+    """GenerateDesertTerrain (Generation.cpp:558-645): sand up to the surface, water up to sea level 10, no stone, at most two
+    cacti per column of two to four blocks standing on the surface entry."""
+    w = util.HostWorld(6, 6, origin=(2, -5)).generate("desert", 5)
+    assert set(np.unique(w.blocks).tolist()) <= {0, 5, 8, 16} and 16 in np.unique(w.blocks)
+    for cz in range(6):
+        for cx in range(6):
+            col = column_profile(w, cx, cz)
+            cactus = (col == 16)
+            stems = cactus.any(axis=1)
+            assert stems.sum() <= 2
+            for z, x in zip(*np.nonzero(stems)):
+                ys = np.nonzero(cactus[z, :, x])[0]
+                assert 2 <= len(ys) <= 4 and (np.diff(ys) == 1).all()
+                assert col[z, ys[0] - 1, x] in (5, 8, 16) and (col[z, :ys[0], x] != 0).all()
+
+
+def test_volcanic_rules():
+    """GenerateVolcanicTerrain (Generation.cpp:647-770): obsidian with stone pockets, lava up to sea level 12, nothing else."""
+    w = util.HostWorld(6, 6, origin=(-1, 7)).generate("volcanic", 9)
+    ids = set(np.unique(w.blocks).tolist())
+    assert ids <= {0, 3, 19, 21} and {19, 21} <= ids
+    col = column_profile(w, 2, 2)
+    solid = col != 0
+    assert (solid[:, :13, :]).all()                                    # everything up to the lava level is filled
+    assert not (col[:, 13:, :] == 21).any()

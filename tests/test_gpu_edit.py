@@ -265,3 +265,75 @@ def test_refusals(ctx):
     with pytest.raises(mesher.GcMeshError):
         world.set_blocks([(48, 64, 48, STONE)], rebuild_capacity=1)           # y = 64: two chunks of the column see it
     world.close()
+
+
+def test_edit_after_a_sparse_upload_is_refused_until_the_light_is_whole(ctx):
+    """A sparse upload leaves out (and clears) light arrays no mesh depends on, so the window does not hold the fixpoint the
+    relight builds on: the edit is refused with GC_ERR_STATE; gcmesh_world_light, or a full upload of both light arrays,
+    makes the window editable again and the result equals the from-scratch fill."""
+    from gamecraft_b200 import mesher
+
+    host = util.HostWorld(4, 4).build("forest", 5)
+    world = mesher.World(ctx, 4, 4).upload_sparse(host)
+    mesher.rebuild_chunks(world, host.interior_chunks())
+    with pytest.raises(mesher.GcMeshError) as e:
+        world.set_blocks([(50, 200, 50, STONE)])
+    assert e.value.status == -4 and "sparse" in str(e.value)                  # GC_ERR_STATE
+    world.upload(host)                                                        # every light array replaced
+    status, _ = world.set_blocks([(50, 200, 50, STONE)])
+    assert status.tolist() == [APPLIED]
+    world.upload_sparse(host)
+    with pytest.raises(mesher.GcMeshError):
+        world.set_blocks([(50, 200, 50, 0)])
+    world.compute_surface().light()                                           # the device's own fill
+    status, _ = world.set_blocks([(50, 200, 50, LANTERN)])
+    assert status.tolist() == [APPLIED]
+    got = snapshot(world, host)
+    host.set_block(50, 200, 50, LANTERN)
+    assert np.array_equal(got.blocks, host.blocks)
+    surface = ob.compute_surface(host)
+    sun, light = ob.light_fill(host, surface)
+    dl = util.HostWorld(4, 4); world.download(dl, blocks=False, light=True)
+    assert np.array_equal(dl.sun, sun) and np.array_equal(dl.light, light)
+    world.close()
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref/libgcref.so not built (no reference tree)")
+@pytest.mark.parametrize("kind,seed,kw,exact", [("forest", 2, {}, True), ("islands", 8, dict(radius=90, falloff=50), False)])
+def test_device_edits_against_the_reference_s_own_setblock(ctx, kind, seed, kw, exact):
+    """The documented f3 divergence, bounded on the GPU path itself: the same edits through gcmesh_world_set_blocks and
+    through the reference's SetBlock -> RecomputeLight compiled verbatim.  Blocks and surface always agree; on forest terrain
+    sunlight (as GetSunlight reads it) and block light are identical; after islands edits (under water, surface rises over
+    caves) the reference's removal queues may stop short: its sunlight is never above the device's, differs in fewer than
+    100 cells of the window and by one level, block light is identical."""
+    from gamecraft_b200 import mesher
+    from test_edit_oracle import start
+
+    size = 5
+    z, r = start(kind, seed, size, **kw)
+    world = mesher.World(ctx, size, size).upload(z)                            # the reference's own state: blocks, surface, light
+    mesher.rebuild_chunks(world, z.interior_chunks())
+    rng = np.random.default_rng(seed)
+    applied = 0
+    for e in range(40):
+        edit = random_edit(rng, z, size)
+        changed = r.set_block(*edit)
+        status, _ = world.set_blocks([edit])
+        assert (status[0] == APPLIED) == changed
+        applied += int(changed)
+        r.download(z)
+    assert applied >= 20
+    d = util.HostWorld(size, size)
+    world.download(d, blocks=True)
+    assert np.array_equal(d.blocks, z.blocks)
+    assert np.array_equal(d.surface, z.surface)
+    ed, ez = effective_sun(d), effective_sun(z)
+    assert np.array_equal(d.light, z.light)
+    if exact:
+        assert np.array_equal(ed, ez)
+    else:
+        assert not (ez > ed).any()
+        short = ez < ed
+        assert int(short.sum()) < 100
+        assert int((ed.astype(np.int16) - ez)[short].max(initial=0)) <= 1
+    r.close(); world.close()

@@ -27,6 +27,13 @@ CASES = [
     ("islands", 5, 8, (9, 9), dict(radius=512, falloff=448)),
     ("flat", 4, 1, (0, 0), {}),
     ("flat", 5, 1, (-2, -3), dict(radius=70, falloff=30)),
+    ("snow", 6, 11, (-3, -3), {}),                                          # ice over the blend band, water inside taller ground
+    ("snow", 5, 3, (-2, -3), dict(radius=80, falloff=30)),
+    ("desert", 6, 5, (2, -5), {}),                                          # cacti, also on the sea floor
+    ("desert", 5, 6, (-3, -2), dict(radius=75, falloff=20)),
+    ("volcanic", 6, 9, (-1, 7), {}),
+    ("volcanic", 5, 10, (-2, -2), dict(radius=70, falloff=25)),
+    ("dungeon", 4, 1, (0, 0), {}),
 ]
 
 
@@ -46,7 +53,7 @@ def test_generated_blocks_equal_host_producer(ctx, kind, size, seed, origin, kw)
     assert diff == 0, "%d of %d block ids differ" % (diff, host.blocks.size)
     assert not got.sun.any() and not got.light.any()
     assert np.array_equal(got.surface, ob.compute_surface(host)), "the generator's surface map is not ComputeSurface's"
-    if kind != "flat":
+    if kind in ("forest", "islands"):
         assert len(np.unique(host.blocks)) >= 5                                    # air, grass, dirt, stone, water and / or trees
 
 
@@ -55,9 +62,9 @@ needs_ref = pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref/libgcref.s
 
 @needs_ref
 @pytest.mark.parametrize("kind,radius,falloff", [("flat", 2**31 - 1, 2**31 - 1 - 64), ("flat", 100, 36), ("flat", 33, 1),
-                                                 ("grid", 2**31 - 1, 0), ("grid", 90, 0), ("void", 50, 0)])
+                                                 ("grid", 2**31 - 1, 0), ("grid", 90, 0), ("void", 50, 0), ("dungeon", 50, 0)])
 def test_noise_free_generators_equal_the_reference_itself(ctx, kind, radius, falloff):
-    """GenerateFlatTerrain / GenerateGridTerrain / GenerateVoidTerrain run from the reference's own sources (oracle/_ref)."""
+    """GenerateFlatTerrain / GenerateGridTerrain / GenerateVoidTerrain / GenerateDungeon run from the reference's own sources (oracle/_ref)."""
     from gamecraft_b200 import mesher
     from test_generate_oracle import reference_blocks
 
@@ -112,6 +119,31 @@ def test_device_only_pipeline_meshes_like_the_oracle(ctx):
     world.close()
 
 
+@pytest.mark.parametrize("kind,seed", [("snow", 4), ("desert", 12), ("volcanic", 2), ("dungeon", 1)])
+def test_device_only_pipeline_on_the_other_biomes(ctx, kind, seed):
+    """generate -> light -> mesh entirely on the device for the biomes with other block kinds (ice and snow, cactus, lava's
+    light, the dungeon's enclosed rooms), against the oracle's fill and meshes of the host producer's blocks."""
+    from gamecraft_b200 import mesher
+
+    size, origin = 5, (-2, -2)
+    world = mesher.World(ctx, size, size)
+    world.generate(kind, seed, origin=origin).light()
+    host = util.HostWorld(size, size, origin=origin).generate(kind, seed)
+    host.surface[:] = ob.compute_surface(host)
+    host.sun[:], host.light[:] = ob.light_fill(host, host.surface)
+    got = util.HostWorld(size, size); world.download(got, blocks=True)
+    assert np.array_equal(got.blocks, host.blocks) and np.array_equal(got.surface, host.surface)
+    assert np.array_equal(got.sun, host.sun) and np.array_equal(got.light, host.light)
+    coords = host.interior_chunks()
+    orc = ob.OracleWorld(host)
+    quads = 0
+    for c, m in zip(coords.tolist(), mesher.rebuild_chunks(world, coords)):
+        util.assert_same_mesh(m, orc.build_chunk(*c), "chunk %r" % (c,))
+        quads += m.vert_count // 4
+    assert quads > 5000
+    world.close()
+
+
 def test_light_after_generate_skips_the_clear_only_while_the_arenas_are_known_zero(ctx):
     """gcmesh_world_generate leaves both light arenas zero, so the fill that follows does not clear them again; any writer in
     between (a second fill, an upload) brings the clear back."""
@@ -140,7 +172,7 @@ def test_bad_arguments(ctx):
 
     world = mesher.World(ctx, 3, 3)
     with pytest.raises(mesher.GcMeshError):
-        world.generate(5, 1)
+        world.generate(9, 1)
     with pytest.raises(mesher.GcMeshError):
         world.generate("flat", 1, origin=(2000, 0))                                # Square() of the reference would overflow
     with pytest.raises(mesher.GcMeshError):

@@ -643,3 +643,25 @@ def test_gpu_fill_device_buffers(ctx):
     with pytest.raises(mesher.GcMeshError):
         batch.fill_device([(len(coords), 0, [0] * 5)])
     batch.close(); world.close()
+
+
+def test_gpu_validate_blocks(ctx):
+    """The reference asserts block < BLOCK_COUNT where a block is stored (World.cpp:294): the device scan counts the ids of a
+    window that lie outside the block table and names the first."""
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(3, 3).generate("mixed", 4)
+    world = mesher.World(ctx, 3, 3).upload(w)
+    assert world.validate_blocks() == (0, None, None)
+    n_types = len(mesher.default_block_table()[0])                           # 24
+    bad = [((2, 1, 0), 77, n_types), ((1, 3, 2), 65535, 300), ((1, 3, 2), 4, 0xFF00)]
+    for (cx, cy, cz), v, value in bad:
+        w.blocks[w.slot(cx, cy, cz)][v] = value
+    world.upload(w)
+    n, chunk, voxel = world.validate_blocks()
+    assert n == 3 and chunk == (2, 1, 0) and voxel == 77                     # slot order: (cz * size_x + cx) * 4 + cy
+    w.blocks[w.slot(2, 1, 0)][77] = n_types - 1
+    world.upload(w)
+    n, chunk, voxel = world.validate_blocks()
+    assert n == 2 and chunk == (1, 3, 2) and voxel == 4
+    world.close()
