@@ -74,6 +74,7 @@ def parse_args():
     ap.add_argument("--exchange", choices=["fused", "p2p", "nccl"], default="fused", help="N > 1: how slab neighbours trade boundary planes")
     ap.add_argument("--no-parity", action="store_true", help="skip the byte comparison of every chunk of the timed output with the oracle")
     ap.add_argument("--no-surface-hint", action="store_true", help="e2e: scan every block brick (GC_WORLD_SURFACE_BOUNDS_BLOCKS off)")
+    ap.add_argument("--no-surface-bounded", action="store_true", help="skip the GC_WORLD_SURFACE_BOUNDS_MESH leg")
     ap.add_argument("--no-weak-leg", action="store_true", help="N > 1 default run: skip the weak-scaling (forest4096 per rank) second leg")
     ap.add_argument("--no-preprocess", action="store_true", help="skip the surface + light-fill leg (SURVEY 8(f1))")
     ap.add_argument("--no-stress", action="store_true", help="skip the uncapped 196 608-quads-per-chunk leg (BASELINE config 4, stress variant)")
@@ -829,6 +830,43 @@ def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs
         kernel_ms.append(batch.elapsed_ms())
     batch.set_timing(False)
 
+    # ---- the same submission with GC_WORLD_SURFACE_BOUNDS_MESH: the window's surface maps are ComputeSurface of its block ids (they
+    # are: the producer computed them, as PreprocessGroup does before any chunk is meshed, WorldRender.cpp:240-262), so the kernel
+    # takes bricks at or above their column's highest surface entry for AIR from the 1 KB map instead of reading 128 KB of ids.
+    # Reported beside the headline, which stays the mesher as a function of the block ids alone. ----
+    bounded = None
+    if not args.no_surface_bounded:
+        world.set_option(mesher.WORLD_SURFACE_BOUNDS_MESH, 1)
+        for _ in range(3):
+            step(batch)
+        batch.wait()
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(args.steps):
+            step(batch)
+        b1.record()
+        batch.wait()
+        barrier()
+        bt = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device="cuda")
+        bbad = None
+        if not args.no_parity:
+            from oracle import binding as ob
+
+            bdesc, _ = batch.results()
+            verts, idx = batch.download()
+            bbad = ob.OracleWorld(host).check_batch(coords, bdesc.copy(), verts, idx, threads=max((os.cpu_count() or 1) // world_size, 1))[0]
+            del verts, idx
+        bb = torch.tensor([float(bbad or 0)], dtype=torch.float64, device="cuda")
+        if world_size > 1:
+            dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bb, op=dist.ReduceOp.SUM)
+        world.set_option(mesher.WORLD_SURFACE_BOUNDS_MESH, 0)
+        bounded = {"ms_per_step": float(bt.item()) / args.steps, "steps": args.steps,
+                   "parity_mismatches": None if bbad is None else int(bb.item()),
+                   "option": "GC_WORLD_SURFACE_BOUNDS_MESH: bricks at or above their column's highest surface entry are AIR by ComputeSurface's "
+                             "definition (Lighting.cpp:5-17); the kernel answers them from the surface map and does not read their block ids"}
+
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     km = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
     cq = torch.tensor([float(n), float(total_quads)], dtype=torch.float64, device="cuda")
@@ -954,6 +992,10 @@ def measure(args, workload, torch, dist, world_size, rank, local_rank, full_legs
             "gpu_launches": launches, "clocks": clocks, "kernel_info": ctx.kernel_info(), "worldgen_s": gen_s,
             "between_kernels_us": 1e3 * (ms_per_step - kms),
         }
+        if bounded:
+            bounded["value"] = all_chunks / (bounded["ms_per_step"] * 1e-3)
+            bounded["unit"] = "chunks/s"
+            line["surface_bounded"] = bounded
         if cold_ms:
             line["cold_order"] = {"kernel_ms": float(np.median(cold_ms)), "chunks_per_s": n / (float(np.median(cold_ms)) * 1e-3),
                                   "note": "first submission of the list on a fresh batch: no quad history, work order = lower chunks first"}

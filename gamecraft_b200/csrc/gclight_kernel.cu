@@ -12,6 +12,8 @@
 // The whole-window fill (gcmesh_world_light) keeps its candidates as bit maps (one word per x-row of a brick) and its active set
 // per brick: nothing is sized on the host, so the call enqueues a fixed sequence of launches and never synchronises.
 // Canonical form of the reference's column-order dependent block-light seeding: see oracle/gc_light_cpu.c.
+#include <cooperative_groups.h>
+
 #include "gclight_kernel.cuh"
 
 namespace gc
@@ -147,6 +149,13 @@ __global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32
             }
         }
     }
+    if (top_w < GC_WORLD_BLOCK_HEIGHT - 1)
+    {
+        // the world's top layer lies outside ComputeSurface's walk (Lighting.cpp:9): a block there is above every surface entry
+        const uint32_t v = (uint32_t)(((size_t)col * 4 + 3) * kVox + x + 32 * (63 + 64 * z));
+        const uint32_t mo = __ballot_sync(0xffffffffu, w.rules->step[w.blocks[v] & 255u] == 255);
+        if (lane == 0 && mo) opq_bits[v >> 5] = mo;
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_seed += __shfl_xor_sync(0xffffffffu, n_seed, d);
     if (lane == 0)
@@ -160,8 +169,9 @@ __global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32
 template <bool kSun>
 __device__ __forceinline__ bool relax_voxel(const LightWorld& w, uint32_t v)
 {
+    // (values are read through L2: in the persistent fill kernel another SM may have raised them since this SM last looked)
     uint8_t* arr = kSun ? w.sun : w.light;
-    const int cur = arr[v];
+    const int cur = __ldcg(arr + v);
     const uint32_t slot = v >> 16, in = v & 65535u;
     const int x = in & 31, y = (in >> 5) & 63, z = in >> 11;
     const int col = slot >> 2, cy = slot & 3, cx = col % w.size_x, cz = col / w.size_x;
@@ -189,7 +199,7 @@ __device__ __forceinline__ bool relax_voxel(const LightWorld& w, uint32_t v)
             if (ncx < 1 || ncx >= w.size_x - 1 || ncz < 1 || ncz >= w.size_z - 1) continue;
             val = 15;
         }
-        else val = arr[nv];                                       // (a stored 0 reads as MIN_LIGHT = 1: offers nothing either way)
+        else val = __ldcg(arr + nv);                              // (a stored 0 reads as MIN_LIGHT = 1: offers nothing either way)
         best = max(best, val - st);
     }
     if (best > cur && best > 1)
@@ -205,54 +215,74 @@ __device__ __forceinline__ void relax_cell(const LightWorld& w, const uint32_t* 
     if (relax_voxel<kSun>(w, list[i])) *changed = 1;
 }
 
-// ---- one sweep of the whole-window fill: a CTA per (fill, brick) ----
-// A brick is visited when it, or one of its six face neighbours (light moves by face steps), changed in the previous sweep —
-// the first sweep's "previous" flags are the bricks that hold a sunlight candidate / a seeded emitter.  A sweep in which nothing
-// changed leaves no flag behind and every later launch finds all its CTAs idle.  Inside a brick a warp takes 32 bit-map words
-// at a time (one coalesced load) and visits the rows that have candidates with lane = x, so the six neighbour loads of a
-// row are consecutive bytes.
-__global__ void __launch_bounds__(256) gc_relax_bricks_kernel(LightWorld w, const uint32_t* __restrict__ sun_bits, const uint32_t* __restrict__ opq_bits,
-                                                              const uint8_t* __restrict__ sun_flag, const uint8_t* __restrict__ prev_sun, uint8_t* now_sun,
-                                                              const uint8_t* __restrict__ prev_light, uint8_t* now_light, uint32_t* counters)
+// ---- the whole-window relaxation: one persistent kernel, all sweeps ----
+// Per sweep: (A) every (fill, brick) pair is tested — a brick is visited when it, or one of its six face neighbours (light moves
+// by face steps), changed in the previous sweep; the first sweep's "previous" flags are the bricks that hold a sunlight
+// candidate / a seeded emitter — and the visits are appended to a list; grid barrier; (B) CTAs take visits off the list: a warp
+// reads 32 bit-map words at a time (one coalesced load) and walks the rows that have candidates with lane = x, so the six
+// neighbour loads of a row are consecutive bytes; bricks that changed are flagged for the next sweep; grid barrier.  A sweep
+// whose list is empty has reached the fixpoint and ends the kernel.  Launched cooperatively (every CTA resident).
+__global__ void __launch_bounds__(256) gc_relax_all_kernel(LightWorld w, const uint32_t* __restrict__ sun_bits, const uint32_t* __restrict__ opq_bits,
+                                                           uint8_t* sun_flags, uint8_t* light_flags, size_t flag_stride, uint32_t* lists, uint32_t* counters)
 {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int n_slots = w.size_x * w.size_z * 4;
-    const bool sun = (int)blockIdx.x < n_slots;
-    const int slot = sun ? blockIdx.x : blockIdx.x - n_slots;
-    if (sun && !sun_flag[slot]) return;                           // no candidate in this brick: nothing can change here
-    const uint8_t* prev = sun ? prev_sun : prev_light;
-    {
-        const int col = slot >> 2, cy = slot & 3, cx = col % w.size_x, cz = col / w.size_x;
-        bool on = prev[slot] != 0;
-        if (cy > 0) on |= prev[slot - 1] != 0;
-        if (cy < 3) on |= prev[slot + 1] != 0;
-        if (cx > 0) on |= prev[slot - 4] != 0;
-        if (cx < w.size_x - 1) on |= prev[slot + 4] != 0;
-        if (cz > 0) on |= prev[slot - 4 * w.size_x] != 0;
-        if (cz < w.size_z - 1) on |= prev[slot + 4 * w.size_x] != 0;
-        if (!on) return;                                          // (CTA-uniform)
-    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t* bits = (sun ? sun_bits : opq_bits) + (size_t)slot * 2048;
-    bool any = false;
-    for (int r0 = warp * 32; r0 < 2048; r0 += 8 * 32)
+    for (int sweep = 0; sweep < kLightSweeps; sweep++)
     {
-        uint32_t word = bits[r0 + lane];
-        if (!sun) word = ~word;                                   // block light: every non-opaque cell
-        uint32_t rows = __ballot_sync(0xffffffffu, word != 0);
-        while (rows)
+        const size_t prev_off = (size_t)sweep * flag_stride, now_off = prev_off + flag_stride;
+        uint32_t* list = lists + (size_t)(sweep & 1) * 2 * n_slots;
+        uint32_t* count = counters + LC_VISITS + sweep;
+        // (A) this sweep's visits
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_slots; i += gridDim.x * blockDim.x)
         {
-            const int r = __ffs((int)rows) - 1;
-            rows &= rows - 1;
-            const uint32_t m = __shfl_sync(0xffffffffu, word, r);
-            if ((m >> lane) & 1u)
-            {
-                const uint32_t v = (uint32_t)slot * (uint32_t)kVox + (uint32_t)(r0 + r) * 32u + (uint32_t)lane;
-                if (sun ? relax_voxel<true>(w, v) : relax_voxel<false>(w, v)) any = true;
-            }
+            const int sun = i < n_slots ? 1 : 0;
+            const int slot = sun ? i : i - n_slots;
+            if (sun && !__ldcg(sun_flags + slot)) continue;       // no candidate in this brick: nothing can change here
+            const uint8_t* pv = (sun ? sun_flags : light_flags) + prev_off;
+            const int col = slot >> 2, cy = slot & 3, cx = col % w.size_x, cz = col / w.size_x;
+            bool on = __ldcg(pv + slot) != 0;
+            if (cy > 0) on |= __ldcg(pv + slot - 1) != 0;
+            if (cy < 3) on |= __ldcg(pv + slot + 1) != 0;
+            if (cx > 0) on |= __ldcg(pv + slot - 4) != 0;
+            if (cx < w.size_x - 1) on |= __ldcg(pv + slot + 4) != 0;
+            if (cz > 0) on |= __ldcg(pv + slot - 4 * w.size_x) != 0;
+            if (cz < w.size_z - 1) on |= __ldcg(pv + slot + 4 * w.size_x) != 0;
+            if (on) list[atomicAdd(count, 1u)] = (uint32_t)i;
         }
+        grid.sync();
+        const uint32_t n = __ldcg(count);
+        if (n == 0) break;                                        // (the same for every thread of the grid)
+        // (B) the visits
+        for (uint32_t j = blockIdx.x; j < n; j += gridDim.x)
+        {
+            const int i = (int)__ldcg(list + j);
+            const bool sun = i < n_slots;
+            const int slot = sun ? i : i - n_slots;
+            const uint32_t* bits = (sun ? sun_bits : opq_bits) + (size_t)slot * 2048;
+            bool any = false;
+            for (int r0 = warp * 32; r0 < 2048; r0 += 8 * 32)
+            {
+                uint32_t word = bits[r0 + lane];
+                if (!sun) word = ~word;                           // block light: every non-opaque cell
+                uint32_t rows = __ballot_sync(0xffffffffu, word != 0);
+                while (rows)
+                {
+                    const int r = __ffs((int)rows) - 1;
+                    rows &= rows - 1;
+                    const uint32_t m = __shfl_sync(0xffffffffu, word, r);
+                    if ((m >> lane) & 1u)
+                    {
+                        const uint32_t v = (uint32_t)slot * (uint32_t)kVox + (uint32_t)(r0 + r) * 32u + (uint32_t)lane;
+                        if (sun ? relax_voxel<true>(w, v) : relax_voxel<false>(w, v)) any = true;
+                    }
+                }
+            }
+            if (__syncthreads_or(any ? 1 : 0) && threadIdx.x == 0) (sun ? sun_flags : light_flags)[now_off + slot] = 1;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[LC_SWEEPS] = (uint32_t)(sweep + 1);
+        grid.sync();
     }
-    if (__syncthreads_or(any ? 1 : 0) && threadIdx.x == 0) (sun ? now_sun : now_light)[slot] = 1;
-    if (threadIdx.x == 0) atomicAdd(&counters[sun ? LC_SUN_BRICK_SWEEPS : LC_LIGHT_BRICK_SWEEPS], 1u);
 }
 
 // One sweep of both fills in one launch, list lengths read from device memory (the edit path: launch-latency bound, and
@@ -292,12 +322,22 @@ cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_bits, uint32_t*
     return cudaGetLastError();
 }
 
-cudaError_t launch_relax_bricks(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, const uint8_t* sun_flag,
-                                const uint8_t* prev_sun, uint8_t* now_sun, const uint8_t* prev_light, uint8_t* now_light, uint32_t* counters, cudaStream_t s)
+cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, uint8_t* sun_flags, uint8_t* light_flags,
+                             size_t flag_stride, uint32_t* lists, uint32_t* counters, int num_sms, cudaStream_t s)
 {
-    const int n_slots = w.size_x * w.size_z * 4;
-    gc_relax_bricks_kernel<<<2 * n_slots, 256, 0, s>>>(w, sun_bits, opq_bits, sun_flag, prev_sun, now_sun, prev_light, now_light, counters);
-    return cudaGetLastError();
+    // every CTA has to be resident (grid barriers): the occupancy query bounds the grid, the cooperative launch enforces it.
+    // Four CTAs per SM are plenty (a visit is a whole brick) and keep the barriers cheap.
+    static int per_sm = 0;
+    if (!per_sm)
+    {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc_relax_all_kernel, 256, 0);
+        if (e != cudaSuccess) return e;
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    }
+    LightWorld lw = w;
+    void* args[] = { &lw, &sun_bits, &opq_bits, &sun_flags, &light_flags, &flag_stride, &lists, &counters };
+    return cudaLaunchCooperativeKernel((const void*)gc_relax_all_kernel, dim3(num_sms * per_sm), dim3(256), args, 0, s);
 }
 
 cudaError_t launch_relax_pair(const LightWorld& w, const uint32_t* sun_list, const uint32_t* light_list, uint32_t cap, const uint32_t* n_sun,

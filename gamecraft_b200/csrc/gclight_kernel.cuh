@@ -28,19 +28,20 @@ struct LightWorld
 
 // statistics of a fill (device memory, kLightCounterWords x u32, cleared by the caller); from LC_FLAGS on: the edit path's
 // "something changed" words of its list sweeps, one preset word + one per sweep for sunlight, then the same for blockLight
-enum { LC_SUN_CAND = 0, LC_LIGHT_BRICK_SWEEPS = 1, LC_SUN_BRICK_SWEEPS = 2, LC_SEEDS = 4, LC_FLAGS = 8 };
 constexpr int kLightSweeps = 14;
-constexpr int kLightCounterWords = LC_FLAGS + 2 * (kLightSweeps + 1);
+enum { LC_SUN_CAND = 0, LC_SWEEPS = 1, LC_SEEDS = 4, LC_FLAGS = 8, LC_VISITS = LC_FLAGS + 2 * (kLightSweeps + 1) };   // LC_VISITS: brick visits per sweep
+constexpr int kLightCounterWords = LC_VISITS + kLightSweeps;
 
 // brick_top: scratch, 1024 bytes per brick of the window
 cudaError_t launch_surface(const LightWorld& w, uint8_t* brick_top, cudaStream_t s);
 // pass over every column cell up to its maxY: the candidate bit maps (one word per x-row of a brick, 2048 words per brick;
 // cleared by the caller), per brick "holds a sunlight candidate" / "holds a seeded emitter", emitters seeded
 cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_bits, uint32_t* opq_bits, uint8_t* sun_flag, uint8_t* seed_flag, uint32_t* counters, cudaStream_t s);
-// one in-place sweep of both fills over the bricks that, or whose face neighbours, changed in the previous sweep (prev_*);
-// bricks that change are flagged in now_* (cleared by the caller)
-cudaError_t launch_relax_bricks(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, const uint8_t* sun_flag,
-                                const uint8_t* prev_sun, uint8_t* now_sun, const uint8_t* prev_light, uint8_t* now_light, uint32_t* counters, cudaStream_t s);
+// the relaxation of both fills, all sweeps in one cooperative launch: sweep k visits the bricks that, or whose face neighbours,
+// changed in sweep k - 1 (flag arrays [k] -> [k + 1], `flag_stride` bytes apart, cleared by the caller except [0] from the scan);
+// lists: 2 x (2 x bricks) words of scratch; ends at the first sweep that has nothing to visit
+cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, uint8_t* sun_flags, uint8_t* light_flags,
+                             size_t flag_stride, uint32_t* lists, uint32_t* counters, int num_sms, cudaStream_t s);
 // the edit path's sweep over its two candidate lists (gcedit_kernel.cu): both fills in one launch; the lists' lengths are read
 // from device memory, `cap` is their capacity; changed_*: this sweep's flag word, the previous sweep's at changed_*[-1]
 cudaError_t launch_relax_pair(const LightWorld& w, const uint32_t* sun_list, const uint32_t* light_list, uint32_t cap, const uint32_t* n_sun,

@@ -121,6 +121,7 @@ struct GcWorld
     int launches;             // kernels launched by the last upload call
     unsigned long long upload_bytes;   // host -> device bytes the last sparse upload / gcmesh_mesh_host call moved
     bool surface_bounds_blocks;        // GC_WORLD_SURFACE_BOUNDS_BLOCKS
+    bool surface_bounds_mesh;          // GC_WORLD_SURFACE_BOUNDS_MESH
     int copy_run;                      // GC_WORLD_COPY_RUN (0: default)
     int16_t* col_smax;                 // host, per column: highest surface entry (-1: not computed in this scan)
     // light fill scratch (grown on demand)
@@ -853,6 +854,7 @@ int gcmesh_world_set_option(GcWorld* w, int option, int value)
 {
     if (!w) return fail(GC_ERR_ARG, "world is null");
     if (option == GC_WORLD_SURFACE_BOUNDS_BLOCKS) { w->surface_bounds_blocks = value != 0; return GC_OK; }
+    if (option == GC_WORLD_SURFACE_BOUNDS_MESH) { w->surface_bounds_mesh = value != 0; return GC_OK; }
     if (option == GC_WORLD_COPY_RUN) { if (value < 0) return fail(GC_ERR_ARG, "run length must not be negative"); w->copy_run = value; return GC_OK; }
     return fail(GC_ERR_ARG, "unknown world option");
 }
@@ -988,7 +990,7 @@ int gcmesh_world_light(GcWorld* w)
     {
         GC_CUDA(cudaMalloc(&w->d_light_counters, kLightCounterWords * sizeof(uint32_t)));
         GC_CUDA(cudaMallocHost(&w->h_light_counters, kLightCounterWords * sizeof(uint32_t)));
-        GC_CUDA(cudaMalloc(&w->d_light_bits, 2 * bits_bytes));
+        GC_CUDA(cudaMalloc(&w->d_light_bits, 2 * bits_bytes + 4 * w->n_slots * sizeof(uint32_t)));   // + the two visit lists
         GC_CUDA(cudaMalloc(&w->d_brick_flags, flags_bytes));
     }
     const LightWorld lw = light_world(w);
@@ -1012,14 +1014,10 @@ int gcmesh_world_light(GcWorld* w)
     // 1. one pass over the column cells up to maxY: candidate bit maps, emitters seeded, the first sweep's active bricks
     GC_CUDA(launch_light_scan(lw, sun_bits, opq_bits, sun_flags, light_flags, c, s)); w->light_launches++;
     // 2. relaxation: a value falls by at least one per hop and nothing at or below MIN_LIGHT is stored, so 14 in-place sweeps
-    // reach the fixpoint; a sweep visits the bricks that changed in the one before (or whose face neighbours did), so the
-    // launches after the fixpoint find nothing to do
-    for (int sweep = 0; sweep < kLightSweeps; sweep++)
-    {
-        GC_CUDA(launch_relax_bricks(lw, sun_bits, opq_bits, sun_flags, sun_flags + (size_t)sweep * flag_stride, sun_flags + (size_t)(sweep + 1) * flag_stride,
-                                    light_flags + (size_t)sweep * flag_stride, light_flags + (size_t)(sweep + 1) * flag_stride, c, s));
-        w->light_launches++;
-    }
+    // reach the fixpoint; one persistent kernel runs them with grid barriers in between, visits per sweep only the bricks
+    // that changed in the sweep before (or whose face neighbours did), and ends with the first sweep that finds none
+    GC_CUDA(launch_relax_all(lw, sun_bits, opq_bits, sun_flags, light_flags, flag_stride, w->d_light_bits + 2 * w->n_slots * 2048, c, ctx->num_sms, s));
+    w->light_launches++;
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
     memset(w->slot_dirty, 7, w->n_slots);
     return GC_OK;
@@ -1034,10 +1032,12 @@ int gcmesh_world_light_stats(GcWorld* w, uint32_t* stats4, int* launches)
         if (w->d_light_counters)
         {
             GC_CUDA(cudaSetDevice(w->ctx->device));
-            GC_CUDA(cudaMemcpyAsync(w->h_light_counters, w->d_light_counters, LC_FLAGS * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->ctx->stream));
+            GC_CUDA(cudaMemcpyAsync(w->h_light_counters, w->d_light_counters, kLightCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->ctx->stream));
             GC_CUDA(cudaStreamSynchronize(w->ctx->stream));
-            stats4[0] = w->h_light_counters[LC_SUN_CAND]; stats4[1] = w->h_light_counters[LC_LIGHT_BRICK_SWEEPS];
-            stats4[2] = w->h_light_counters[LC_SUN_BRICK_SWEEPS]; stats4[3] = w->h_light_counters[LC_SEEDS];
+            uint32_t visits = 0;
+            for (int k = 0; k < kLightSweeps; k++) visits += w->h_light_counters[LC_VISITS + k];
+            stats4[0] = w->h_light_counters[LC_SUN_CAND]; stats4[1] = visits;
+            stats4[2] = w->h_light_counters[LC_SWEEPS]; stats4[3] = w->h_light_counters[LC_SEEDS];
         }
     }
     if (launches) *launches = w->light_launches;
@@ -1570,6 +1570,7 @@ static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cu
     p.done_counter = reinterpret_cast<uint32_t*>(b->d_cursor + 2); p.total_out = b->d_cursor + 3; p.keep_cursor = keep_cursor ? 1 : 0;
     p.vert_table = w->d_vert_table;
     p.wide = b->uncapped ? 1 : 0;
+    p.trust_surface = w->surface_bounds_mesh ? 1 : 0;
     p.n_push = 0;
     memset(&p.halo, 0, sizeof(p.halo));
     if (halo && halo->enabled)

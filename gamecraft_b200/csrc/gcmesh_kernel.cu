@@ -301,22 +301,58 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     uint32_t warp_seq = 0;  // slabs this warp has staged so far (mbarrier parity source)
     long long prof_t = clock64();
 
-    // Claim the next chunk, a chunk ahead of the rest of the CTA (one warp, into buffer `b`).
+    // Claim the next chunk, a chunk ahead of the rest of the CTA (the fetch warp, into buffer `b`).
+    // With p.trust_surface (the window's surface maps are ComputeSurface of its block ids, Lighting.cpp:5-26) a brick that lies
+    // wholly at or above its column's highest surface entry is AIR by definition: its empty result is written right here and
+    // the warp claims again, so such a chunk costs one 1 KB surface read instead of 128 KB of block ids and never reaches the
+    // CTA's phases.  (Layer y = 255 is outside ComputeSurface's walk, Lighting.cpp:9: the top brick's last layer is looked at.)
     auto fetch_chunk = [&](int b)
     {
-        if (lane == 0)
+        int c = -1, fx = 0, fy = 0, fz = 0;
+        for (;;)
         {
-            int c = atomicAdd(p.work_counter, 1), fx = 0, fy = 0, fz = 0;
-            if (kHalo && c < p.n_push) { fx = c; c = kPushItem; }          // a halo push task (fused exchange): its number travels in cx
-            else
+            if (lane == 0)
             {
-                if (kHalo) c -= p.n_push;
-                if (c >= p.n_chunks) c = -1;
-                else if (p.order) c = p.order[c];
-                if (c >= 0) { const GcChunkCoord cc = p.coords[c]; fx = cc.cx; fy = cc.cy; fz = cc.cz; }
+                c = atomicAdd(p.work_counter, 1); fx = 0; fy = 0; fz = 0;
+                if (kHalo && c < p.n_push) { fx = c; c = kPushItem; }          // a halo push task (fused exchange): its number travels in cx
+                else
+                {
+                    if (kHalo) c -= p.n_push;
+                    if (c >= p.n_chunks) c = -1;
+                    else if (p.order) c = p.order[c];
+                    if (c >= 0) { const GcChunkCoord cc = p.coords[c]; fx = cc.cx; fy = cc.cy; fz = cc.cz; }
+                }
             }
-            s_next[b].chunk = c; s_next[b].cx = fx; s_next[b].cy = fy; s_next[b].cz = fz;
+            if (!p.trust_surface) break;
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c < 0) break;
+            fx = __shfl_sync(0xffffffffu, fx, 0); fy = __shfl_sync(0xffffffffu, fy, 0); fz = __shfl_sync(0xffffffffu, fz, 0);
+            const size_t col = (size_t)fz * p.size_x + fx;
+            const uint4* sp = reinterpret_cast<const uint4*>(p.surface + col * 1024) + lane * 2;
+            const uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+            uint32_t m = __vmaxu4(__vmaxu4(__vmaxu4(s0.x, s0.y), __vmaxu4(s0.z, s0.w)), __vmaxu4(__vmaxu4(s1.x, s1.y), __vmaxu4(s1.z, s1.w)));
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) m = __vmaxu4(m, __shfl_xor_sync(0xffffffffu, m, d));
+            const int top = (int)max(max(m & 255u, (m >> 8) & 255u), max((m >> 16) & 255u, m >> 24));   // highest block of the column + 1
+            bool air = fy * kTY >= top;
+            if (air && fy == GC_WORLD_CHUNK_HEIGHT - 1)
+            {
+                const uint4* bp = reinterpret_cast<const uint4*>(p.blocks + (col * 4 + fy) * GC_CHUNK_SIZE_3 + 32 * (63 + 64 * lane));   // row z = lane of layer y = 255
+                const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
+                const uint32_t any = b0.x | b0.y | b0.z | b0.w | b1.x | b1.y | b1.z | b1.w | b2.x | b2.y | b2.z | b2.w | b3.x | b3.y | b3.z | b3.w;
+                air = !__any_sync(0xffffffffu, any != 0u);
+            }
+            if (!air) break;
+            if (lane == 0)
+            {
+                GcChunkOut o;
+                o.quad_base = 0; o.vert_count = 0; o.quads = 0; o.flags = 0; o.reserved[0] = 0; o.reserved[1] = 0;
+                for (int t = 0; t < kMeshTypes; t++) { o.index_count[t] = 0; o.index_offset[t] = 0; }
+                p.out[c] = o;
+                if (p.vert_table) p.vert_table[(col * 4 + fy)] = 0;
+            }
         }
+        if (lane == 0) { s_next[b].chunk = c; s_next[b].cx = fx; s_next[b].cy = fy; s_next[b].cz = fz; }
     };
 
     // fused exchange: tell both neighbours that this rank has entered exchange `serial` — its previous kernel, the last reader
@@ -525,9 +561,9 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         }
         else if (warp == kFetchWarp)
         {
-            // ---- the next chunk's claim, then the two z-halo slabs (tz = -1, 32): contiguous 4 KB of the bricks in front / behind,
-            // two rows per lane straight from global memory ----
-            fetch_chunk(buf ^ 1);
+            // ---- the two z-halo slabs (tz = -1, 32): contiguous 4 KB of the bricks in front / behind, two rows per lane straight
+            // from global memory; then the next chunk's claim (which may pass over several bricks that are known to be air) ----
+            if (!p.trust_surface) fetch_chunk(buf ^ 1);
 #pragma unroll 1
             for (int side = 0; side < 2; side++)
             {
@@ -542,6 +578,7 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 }
                 convert_rows(qa, qb, row_uniformity(qa), row_uniformity(qb), rot_selector(0), side ? kSlabs - 1 : 0);
             }
+            if (p.trust_surface) fetch_chunk(buf ^ 1);
         }
         __syncthreads();
         GC_PROF_MARK(1);

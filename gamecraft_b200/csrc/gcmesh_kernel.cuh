@@ -48,6 +48,7 @@ struct MeshParams
     // planes into the neighbours' windows, item n_push + k is chunk order[k]
     int32_t n_push;
     HaloFused halo;
+    int32_t trust_surface;             // GC_WORLD_SURFACE_BOUNDS_MESH: bricks at or above their column's highest surface entry are AIR, not read
     int32_t wide;                      // uncapped batch (GC_BATCH_UNCAPPED): no quad cap per chunk, 32-bit indices (24 bytes per quad in the index arena)
 };
 

@@ -29,6 +29,7 @@ CHUNK_NO_SPACE = 2
 CHUNK_HALO_MISSING = 4
 WORLD_SURFACE_BOUNDS_BLOCKS = 1      # GC_WORLD_SURFACE_BOUNDS_BLOCKS
 WORLD_COPY_RUN = 2                   # GC_WORLD_COPY_RUN
+WORLD_SURFACE_BOUNDS_MESH = 3        # GC_WORLD_SURFACE_BOUNDS_MESH
 BATCH_UNCAPPED = 1                   # GC_BATCH_UNCAPPED
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -329,7 +330,7 @@ class World:
     def light_stats(self):
         st, n = np.zeros(4, np.uint32), ctypes.c_int(0)
         _check(lib().gcmesh_world_light_stats(self.h, _ptr(st), ctypes.byref(n)), "gcmesh_world_light_stats")
-        return {"sun_candidates": int(st[0]), "light_brick_sweeps": int(st[1]), "sun_brick_sweeps": int(st[2]), "seeds": int(st[3]), "launches": n.value}
+        return {"sun_candidates": int(st[0]), "brick_visits": int(st[1]), "sweeps": int(st[2]), "seeds": int(st[3]), "launches": n.value}
 
     # -- region records (the reference's saved-chunk format, Code/WorldIO.cpp:167-307) --
     def upload_rle(self, chunks: np.ndarray, data: np.ndarray) -> "World":

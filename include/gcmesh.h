@@ -144,9 +144,15 @@ int gcmesh_world_upload_sparse(GcWorld* world, const uint16_t* blocks, const uin
  * what ChunkGroup::surface holds for every pre-processed column; a stale entry is only ever too high).  The host scan then
  * takes a brick lying wholly at or above its column's highest entry for AIR without reading it (layer y = 255, which
  * ComputeSurface does not look at, is still read).
+ * GC_WORLD_SURFACE_BOUNDS_MESH (default 0): the same promise for the window on the device — its surface map is ComputeSurface of
+ * its block ids, as it is after gcmesh_world_compute_surface, gcmesh_world_generate, gcmesh_world_set_blocks, or uploads of a
+ * pre-processed window (in the reference a chunk is only ever meshed after PreprocessGroup, WorldRender.cpp:240-262).  The mesh
+ * kernel then takes a brick lying wholly at or above its column's highest surface entry for AIR — an empty mesh — from the
+ * 1 KB surface map, without reading the brick's 128 KB of block ids (the top brick's layer y = 255 is still looked at).
+ * With the option off (default) the mesher is a function of the block ids alone, whatever the surface map says.
  * GC_WORLD_COPY_RUN (default 0 = 4): sparse uploads move the same brick array of at least this many consecutive columns
  * with one strided copy-engine copy; shorter runs are pulled by a GPU kernel out of pinned host memory (a huge value: always). */
-enum { GC_WORLD_SURFACE_BOUNDS_BLOCKS = 1, GC_WORLD_COPY_RUN = 2 };
+enum { GC_WORLD_SURFACE_BOUNDS_BLOCKS = 1, GC_WORLD_COPY_RUN = 2, GC_WORLD_SURFACE_BOUNDS_MESH = 3 };
 int gcmesh_world_set_option(GcWorld* world, int option, int value);
 /* World-space column (ChunkGroup::pos, World.h) of window column (0, 0).  Only region records depend on it (gcmesh_world_encode_rle). */
 int gcmesh_world_set_origin(GcWorld* world, int origin_cx, int origin_cz);
@@ -208,11 +214,11 @@ int gcmesh_set_light_rules(GcContext* ctx, const uint8_t* step256, const uint8_t
 /* surface[column][z*32 + x] = highest non-AIR y in 0..254, plus one (0 for an empty column cell).  Asynchronous. */
 int gcmesh_world_compute_surface(GcWorld* world);
 /* Clears the sunlight / blockLight arenas and fills them from the block ids and the surface map.  Asynchronous: a fixed
- * sequence of launches on the context stream (candidates are bit maps, the active set a byte per brick and sweep — nothing is
- * sized from a device count), no synchronisation. */
+ * sequence on the context stream — clears, one scan kernel, one persistent relaxation kernel (cooperative launch; candidates are
+ * bit maps, the active set a byte per brick and sweep: nothing is sized from a device count) — and no synchronisation. */
 int gcmesh_world_light(GcWorld* world);
-/* Of the last gcmesh_world_light: {sunlight candidate cells, (brick, sweep) visits of the blockLight relaxation, of the sunlight
- * relaxation, seeded emitters}, kernels launched.  Synchronises the context stream to read them. */
+/* Of the last gcmesh_world_light: {sunlight candidate cells, brick visits of the relaxation (both fills, all sweeps), sweeps
+ * that found something to visit, seeded emitters}, kernels launched.  Synchronises the context stream to read them. */
 int gcmesh_world_light_stats(GcWorld* world, uint32_t* stats4, int* launches);
 /* Device -> host copy of the window's arrays (NULL skips one); synchronous. */
 int gcmesh_world_download(GcWorld* world, uint16_t* blocks, uint8_t* sunlight, uint8_t* block_light, uint8_t* surface);

@@ -665,3 +665,41 @@ def test_gpu_validate_blocks(ctx):
     n, chunk, voxel = world.validate_blocks()
     assert n == 2 and chunk == (1, 3, 2) and voxel == 4
     world.close()
+
+
+def test_gpu_surface_bounds_mesh_option(ctx):
+    """GC_WORLD_SURFACE_BOUNDS_MESH: with the surface map being ComputeSurface of the block ids, the kernel answers bricks at or above
+    their column's highest entry from the map — same bytes as without the option, on terrain, on a world with blocks on layer
+    y = 255 (outside ComputeSurface's walk: the top brick is still looked at), with and without a work order from an earlier
+    submission.  With a surface map that lies, the option changes the result (that is its contract); without it, it does not."""
+    from gamecraft_b200 import mesher
+
+    for kind, seed, kw in (("forest", 3, {}), ("mixed", 29, dict(radius=110, falloff=60)), ("islands", 8, dict(radius=90, falloff=50))):
+        w = util.HostWorld(6, 6, origin=(-3, -3)).generate(kind, seed, **kw)
+        for wx, wz, b in ((70, 75, 3), (71, 75, 14), (100, 130, 22)):        # stone, a lantern and glass on the world's top layer
+            w.set_block(wx, 255, wz, b)
+        util.light_world(w)
+        coords = w.interior_chunks(1)
+        o = ob.OracleWorld(w)
+        want = [o.build_chunk(*c) for c in coords]
+        air = sum(1 for m in want if m.vert_count == 0)
+        assert air >= len(want) // 3
+        world = mesher.World(ctx, 6, 6).upload(w).set_option(mesher.WORLD_SURFACE_BOUNDS_MESH, 1)
+        batch = mesher.Batch(ctx, len(coords), sum(m.quads for m in want) + 10)
+        for _ in range(3):                                                   # the second and third submission carry a work order
+            for m, x, c in zip(batch.submit(world, coords).wait().meshes(), want, coords):
+                util.assert_same_mesh(m, x, "%s %s" % (kind, c))
+        assert (world.vertex_counts()[1:-1, 1:-1].reshape(-1) == [m.vert_count for m in want]).all()
+        batch.close(); world.close()
+
+    # a surface map that claims empty columns: bricks are skipped on its word (option on), or meshed regardless (option off)
+    w = util.HostWorld(3, 3).build("forest", 5)
+    lie = util.HostWorld(3, 3)
+    lie.blocks[:] = w.blocks; lie.sun[:] = w.sun; lie.light[:] = w.light; lie.surface[:] = 0
+    truth = ob.OracleWorld(lie).build_chunk(1, 0, 1)
+    assert truth.vert_count > 0
+    world = mesher.World(ctx, 3, 3).upload(lie)
+    util.assert_same_mesh(mesher.rebuild_chunks(world, [(1, 0, 1)])[0], truth)
+    world.set_option(mesher.WORLD_SURFACE_BOUNDS_MESH, 1)
+    assert mesher.rebuild_chunks(world, [(1, 0, 1)])[0].vert_count == 0
+    world.close()
