@@ -87,10 +87,11 @@ __global__ void __launch_bounds__(256) gc_surface_max_kernel(LightWorld w, const
 // (slot * 2048 + z * 64 + y) = voxel index >> 5.
 //   sun_bits   bit x = the cell is a sunlight candidate (non-opaque, below its column's surface)
 //   opq_bits   bit x = the cell is opaque (rows the walk never reaches are air: the maps are cleared beforehand)
-//   sun_flag   per brick: it holds a sunlight candidate (the first sweep's active set, and the bricks worth visiting at all)
+//   sun_flag   per brick: it holds a sunlight candidate (the first sweep's active set)
+//   sun_unit   per unit (four z-slices of a brick = 256 rows = 8192 cells): it holds a sunlight candidate (worth visiting at all)
 //   seed_flag  per brick: it holds a seeded emitter (the first block-light sweep's active set)
 __global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32_t* __restrict__ sun_bits, uint32_t* __restrict__ opq_bits,
-                                                            uint8_t* sun_flag, uint8_t* seed_flag, uint32_t* counters)
+                                                            uint8_t* sun_flag, uint8_t* sun_unit, uint8_t* seed_flag, uint32_t* counters)
 {
     const int lane = threadIdx.x & 31;
     const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32
             if (lane == 0)
             {
                 if (mo) opq_bits[v >> 5] = mo;
-                if (mc) { sun_bits[v >> 5] = mc; sun_flag[slot] = 1; n_cand += (uint32_t)__popc(mc); }
+                if (mc) { sun_bits[v >> 5] = mc; sun_flag[slot] = 1; sun_unit[slot * 8 + (z >> 2)] = 1; n_cand += (uint32_t)__popc(mc); }
             }
             const uint32_t e = w.rules->emitted[id[k]];
             if (inner && y <= my && e > 1)   // CheckForBlockLight (Lighting.cpp:231-245); the arrays were cleared, so this is a max
@@ -216,29 +217,37 @@ __device__ __forceinline__ void relax_cell(const LightWorld& w, const uint32_t* 
 }
 
 // ---- the whole-window relaxation: one persistent kernel, all sweeps ----
-// Per sweep: (A) every (fill, brick) pair is tested — a brick is visited when it, or one of its six face neighbours (light moves
-// by face steps), changed in the previous sweep; the first sweep's "previous" flags are the bricks that hold a sunlight
-// candidate / a seeded emitter — and the visits are appended to a list; grid barrier; (B) CTAs take visits off the list: a warp
-// reads 32 bit-map words at a time (one coalesced load) and walks the rows that have candidates with lane = x, so the six
-// neighbour loads of a row are consecutive bytes; bricks that changed are flagged for the next sweep; grid barrier.  A sweep
-// whose list is empty has reached the fixpoint and ends the kernel.  Launched cooperatively (every CTA resident).
+// Work unit: four z-slices of a brick (256 rows, 8192 cells).  Per sweep: (A) every (fill, unit) pair is tested — a brick is
+// visited when it, or one of its six face neighbours (light moves by face steps), changed in the previous sweep; the first
+// sweep's "previous" flags are the bricks that hold a sunlight candidate / a seeded emitter; sunlight units without a candidate
+// are never visited — and the visits are appended to a list; grid barrier; (B) a CTA takes a visit off the list, turns the
+// unit's 256 bit-map words into a list of cells in shared memory (popcount scan), and relaxes them one cell per thread:
+// consecutive threads hold consecutive candidates, which are neighbours in x, so their loads share sectors; bricks that changed
+// are flagged for the next sweep; grid barrier.  A sweep whose list is empty has reached the fixpoint and ends the kernel.
+// Launched cooperatively (every CTA resident).
+constexpr int kUnitRows = 256, kUnitsPerBrick = 2048 / kUnitRows;
 __global__ void __launch_bounds__(256) gc_relax_all_kernel(LightWorld w, const uint32_t* __restrict__ sun_bits, const uint32_t* __restrict__ opq_bits,
-                                                           uint8_t* sun_flags, uint8_t* light_flags, size_t flag_stride, uint32_t* lists, uint32_t* counters)
+                                                           const uint8_t* __restrict__ sun_unit, uint8_t* sun_flags, uint8_t* light_flags, size_t flag_stride,
+                                                           uint32_t* lists, uint32_t* counters)
 {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ uint16_t s_cells[kUnitRows * 32];
+    __shared__ uint32_t s_warp_total[8];
     const int n_slots = w.size_x * w.size_z * 4;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_units = n_slots * kUnitsPerBrick;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int sweep = 0; sweep < kLightSweeps; sweep++)
     {
         const size_t prev_off = (size_t)sweep * flag_stride, now_off = prev_off + flag_stride;
-        uint32_t* list = lists + (size_t)(sweep & 1) * 2 * n_slots;
+        uint32_t* list = lists + (size_t)(sweep & 1) * 2 * n_units;
         uint32_t* count = counters + LC_VISITS + sweep;
         // (A) this sweep's visits
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_slots; i += gridDim.x * blockDim.x)
+        for (int i = blockIdx.x * blockDim.x + tid; i < 2 * n_units; i += gridDim.x * blockDim.x)
         {
-            const int sun = i < n_slots ? 1 : 0;
-            const int slot = sun ? i : i - n_slots;
-            if (sun && !__ldcg(sun_flags + slot)) continue;       // no candidate in this brick: nothing can change here
+            const int sun = i < n_units ? 1 : 0;
+            const int unit = sun ? i : i - n_units;
+            const int slot = unit / kUnitsPerBrick;
+            if (sun && !sun_unit[unit]) continue;                 // no candidate in this unit: nothing can change here
             const uint8_t* pv = (sun ? sun_flags : light_flags) + prev_off;
             const int col = slot >> 2, cy = slot & 3, cx = col % w.size_x, cz = col / w.size_x;
             bool on = __ldcg(pv + slot) != 0;
@@ -254,33 +263,61 @@ __global__ void __launch_bounds__(256) gc_relax_all_kernel(LightWorld w, const u
         const uint32_t n = __ldcg(count);
         if (n == 0) break;                                        // (the same for every thread of the grid)
         // (B) the visits
+        uint32_t word = 0;
+        int item = 0;
+        if (blockIdx.x < n)
+        {
+            item = (int)__ldcg(list + blockIdx.x);
+            word = ((item < n_units ? sun_bits : opq_bits))[(size_t)(item < n_units ? item : item - n_units) * kUnitRows + tid];
+        }
         for (uint32_t j = blockIdx.x; j < n; j += gridDim.x)
         {
-            const int i = (int)__ldcg(list + j);
-            const bool sun = i < n_slots;
-            const int slot = sun ? i : i - n_slots;
-            const uint32_t* bits = (sun ? sun_bits : opq_bits) + (size_t)slot * 2048;
-            bool any = false;
-            for (int r0 = warp * 32; r0 < 2048; r0 += 8 * 32)
+            const bool sun = item < n_units;
+            const int unit = sun ? item : item - n_units;
+            const int slot = unit / kUnitsPerBrick;
+            uint32_t m = sun ? word : ~word;                      // block light: every non-opaque cell
+            // the next visit's bit-map word travels while this one is worked on
+            if (j + gridDim.x < n)
             {
-                uint32_t word = bits[r0 + lane];
-                if (!sun) word = ~word;                           // block light: every non-opaque cell
-                uint32_t rows = __ballot_sync(0xffffffffu, word != 0);
-                while (rows)
-                {
-                    const int r = __ffs((int)rows) - 1;
-                    rows &= rows - 1;
-                    const uint32_t m = __shfl_sync(0xffffffffu, word, r);
-                    if ((m >> lane) & 1u)
-                    {
-                        const uint32_t v = (uint32_t)slot * (uint32_t)kVox + (uint32_t)(r0 + r) * 32u + (uint32_t)lane;
-                        if (sun ? relax_voxel<true>(w, v) : relax_voxel<false>(w, v)) any = true;
-                    }
-                }
+                item = (int)__ldcg(list + j + gridDim.x);
+                word = ((item < n_units ? sun_bits : opq_bits))[(size_t)(item < n_units ? item : item - n_units) * kUnitRows + tid];
             }
-            if (__syncthreads_or(any ? 1 : 0) && threadIdx.x == 0) (sun ? sun_flags : light_flags)[now_off + slot] = 1;
+            // cells of the unit -> shared list: thread = row, exclusive scan of the rows' candidate counts
+            const uint32_t cnt = (uint32_t)__popc(m);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) s_warp_total[warp] = incl;
+            __syncthreads();
+            uint32_t base = incl - cnt, total = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+            {
+                const uint32_t t = s_warp_total[k];
+                if (k < warp) base += t;
+                total += t;
+            }
+            while (m)
+            {
+                const uint32_t bit = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1;
+                s_cells[base++] = (uint16_t)((tid << 5) | bit);
+            }
+            __syncthreads();
+            bool any = false;
+            const uint32_t v0 = (uint32_t)unit * (uint32_t)(kUnitRows * 32);
+            for (uint32_t k = tid; k < total; k += 256)
+            {
+                const uint32_t v = v0 + s_cells[k];
+                if (sun ? relax_voxel<true>(w, v) : relax_voxel<false>(w, v)) any = true;
+            }
+            if (__syncthreads_or(any ? 1 : 0) && tid == 0) (sun ? sun_flags : light_flags)[now_off + slot] = 1;
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) counters[LC_SWEEPS] = (uint32_t)(sweep + 1);
+        if (blockIdx.x == 0 && tid == 0) counters[LC_SWEEPS] = (uint32_t)(sweep + 1);
         grid.sync();
     }
 }
@@ -316,27 +353,27 @@ cudaError_t launch_surface(const LightWorld& w, uint8_t* brick_top, cudaStream_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_bits, uint32_t* opq_bits, uint8_t* sun_flag, uint8_t* seed_flag, uint32_t* counters, cudaStream_t s)
+cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_bits, uint32_t* opq_bits, uint8_t* sun_flag, uint8_t* sun_unit, uint8_t* seed_flag, uint32_t* counters, cudaStream_t s)
 {
-    gc_light_scan_kernel<<<rows_grid(w), 256, 0, s>>>(w, sun_bits, opq_bits, sun_flag, seed_flag, counters);
+    gc_light_scan_kernel<<<rows_grid(w), 256, 0, s>>>(w, sun_bits, opq_bits, sun_flag, sun_unit, seed_flag, counters);
     return cudaGetLastError();
 }
 
-cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, uint8_t* sun_flags, uint8_t* light_flags,
+cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, const uint8_t* sun_unit, uint8_t* sun_flags, uint8_t* light_flags,
                              size_t flag_stride, uint32_t* lists, uint32_t* counters, int num_sms, cudaStream_t s)
 {
     // every CTA has to be resident (grid barriers): the occupancy query bounds the grid, the cooperative launch enforces it.
-    // Four CTAs per SM are plenty (a visit is a whole brick) and keep the barriers cheap.
+    // (a barrier costs more the more CTAs take part: six per SM keep ~1500 cells per SM in flight)
     static int per_sm = 0;
     if (!per_sm)
     {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc_relax_all_kernel, 256, 0);
         if (e != cudaSuccess) return e;
-        if (per_sm > 4) per_sm = 4;
+        if (per_sm > 6) per_sm = 6;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     LightWorld lw = w;
-    void* args[] = { &lw, &sun_bits, &opq_bits, &sun_flags, &light_flags, &flag_stride, &lists, &counters };
+    void* args[] = { &lw, &sun_bits, &opq_bits, &sun_unit, &sun_flags, &light_flags, &flag_stride, &lists, &counters };
     return cudaLaunchCooperativeKernel((const void*)gc_relax_all_kernel, dim3(num_sms * per_sm), dim3(256), args, 0, s);
 }
 

@@ -985,12 +985,13 @@ int gcmesh_world_light(GcWorld* w)
     // brick), the active set is a byte per brick and sweep — the call enqueues a fixed sequence and returns.
     const size_t bits_bytes = w->n_slots * 2048 * sizeof(uint32_t);
     const size_t flag_stride = (w->n_slots + 255) & ~(size_t)255;
-    const size_t flags_bytes = 2 * (size_t)(kLightSweeps + 1) * flag_stride;        // sunlight, then blockLight: sweep k reads [k], writes [k + 1]
+    const size_t unit_stride = (w->n_slots * 8 + 255) & ~(size_t)255;               // per unit (256 rows; 8 per brick): holds a sunlight candidate
+    const size_t flags_bytes = 2 * (size_t)(kLightSweeps + 1) * flag_stride + unit_stride;   // sunlight, then blockLight: sweep k reads [k], writes [k + 1]; then the unit bytes
     if (!w->d_light_counters)
     {
         GC_CUDA(cudaMalloc(&w->d_light_counters, kLightCounterWords * sizeof(uint32_t)));
         GC_CUDA(cudaMallocHost(&w->h_light_counters, kLightCounterWords * sizeof(uint32_t)));
-        GC_CUDA(cudaMalloc(&w->d_light_bits, 2 * bits_bytes + 4 * w->n_slots * sizeof(uint32_t)));   // + the two visit lists
+        GC_CUDA(cudaMalloc(&w->d_light_bits, 2 * bits_bytes + 32 * w->n_slots * sizeof(uint32_t)));   // + the two visit lists (2 fills x 8 units per brick each)
         GC_CUDA(cudaMalloc(&w->d_brick_flags, flags_bytes));
     }
     const LightWorld lw = light_world(w);
@@ -999,6 +1000,7 @@ int gcmesh_world_light(GcWorld* w)
     uint32_t* opq_bits = w->d_light_bits + w->n_slots * 2048;
     uint8_t* sun_flags = w->d_brick_flags;
     uint8_t* light_flags = w->d_brick_flags + (size_t)(kLightSweeps + 1) * flag_stride;
+    uint8_t* sun_unit = w->d_brick_flags + 2 * (size_t)(kLightSweeps + 1) * flag_stride;
     // freshly generated chunks hold no light (World.cpp:632): the fill starts from zero (arenas known to be zero are not cleared again)
     if (!(w->light_zero && !w->light_untracked))
     {
@@ -1012,11 +1014,12 @@ int gcmesh_world_light(GcWorld* w)
     GC_CUDA(cudaMemsetAsync(w->d_brick_flags, 0, flags_bytes, s));
     w->light_launches = 0;
     // 1. one pass over the column cells up to maxY: candidate bit maps, emitters seeded, the first sweep's active bricks
-    GC_CUDA(launch_light_scan(lw, sun_bits, opq_bits, sun_flags, light_flags, c, s)); w->light_launches++;
+    GC_CUDA(launch_light_scan(lw, sun_bits, opq_bits, sun_flags, sun_unit, light_flags, c, s)); w->light_launches++;
     // 2. relaxation: a value falls by at least one per hop and nothing at or below MIN_LIGHT is stored, so 14 in-place sweeps
     // reach the fixpoint; one persistent kernel runs them with grid barriers in between, visits per sweep only the bricks
-    // that changed in the sweep before (or whose face neighbours did), and ends with the first sweep that finds none
-    GC_CUDA(launch_relax_all(lw, sun_bits, opq_bits, sun_flags, light_flags, flag_stride, w->d_light_bits + 2 * w->n_slots * 2048, c, ctx->num_sms, s));
+    // that changed in the sweep before (or whose face neighbours did) — in units of 256 rows whose candidates a CTA spreads over
+    // its threads one cell each — and ends with the first sweep that finds none
+    GC_CUDA(launch_relax_all(lw, sun_bits, opq_bits, sun_unit, sun_flags, light_flags, flag_stride, w->d_light_bits + 2 * w->n_slots * 2048, c, ctx->num_sms, s));
     w->light_launches++;
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
     memset(w->slot_dirty, 7, w->n_slots);

@@ -683,7 +683,7 @@ def test_gpu_surface_bounds_mesh_option(ctx):
         o = ob.OracleWorld(w)
         want = [o.build_chunk(*c) for c in coords]
         air = sum(1 for m in want if m.vert_count == 0)
-        assert air >= len(want) // 3
+        assert air >= len(want) // 3 or kind == "mixed"                        # (the mixed world reaches the top of every column)
         world = mesher.World(ctx, 6, 6).upload(w).set_option(mesher.WORLD_SURFACE_BOUNDS_MESH, 1)
         batch = mesher.Batch(ctx, len(coords), sum(m.quads for m in want) + 10)
         for _ in range(3):                                                   # the second and third submission carry a work order
