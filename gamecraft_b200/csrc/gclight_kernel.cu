@@ -226,13 +226,17 @@ __device__ __forceinline__ void relax_cell(const LightWorld& w, const uint32_t* 
 // are flagged for the next sweep; grid barrier.  A sweep whose list is empty has reached the fixpoint and ends the kernel.
 // Launched cooperatively (every CTA resident).
 constexpr int kUnitRows = 256, kUnitsPerBrick = 2048 / kUnitRows;
+// "did row r of brick `slot` change in the previous sweep?" — one bit per row, 64 words per brick
+__device__ __forceinline__ uint32_t row_bit(const uint32_t* rows, int slot, int r) { return (__ldcg(rows + (size_t)slot * 64 + (r >> 5)) >> (r & 31)) & 1u; }
+
 __global__ void __launch_bounds__(256) gc_relax_all_kernel(LightWorld w, const uint32_t* __restrict__ sun_bits, const uint32_t* __restrict__ opq_bits,
                                                            const uint8_t* __restrict__ sun_unit, uint8_t* sun_flags, uint8_t* light_flags, size_t flag_stride,
-                                                           uint32_t* lists, uint32_t* counters)
+                                                           uint32_t* lists, uint32_t* row_maps, uint32_t* counters)
 {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     __shared__ uint16_t s_cells[kUnitRows * 32];
     __shared__ uint32_t s_warp_total[8];
+    __shared__ uint32_t s_row_changed[kUnitRows / 32];
     const int n_slots = w.size_x * w.size_z * 4;
     const int n_units = n_slots * kUnitsPerBrick;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -241,6 +245,13 @@ __global__ void __launch_bounds__(256) gc_relax_all_kernel(LightWorld w, const u
         const size_t prev_off = (size_t)sweep * flag_stride, now_off = prev_off + flag_stride;
         uint32_t* list = lists + (size_t)(sweep & 1) * 2 * n_units;
         uint32_t* count = counters + LC_VISITS + sweep;
+        // rows that changed, one bit each, per fill (sunlight first): three maps in rotation — this sweep reads the previous
+        // sweep's, writes its own, and clears the one the next sweep will write
+        const size_t map_words = (size_t)2 * n_slots * 64;
+        const uint32_t* prev_rows = row_maps + (size_t)(sweep % 3) * map_words;
+        uint32_t* now_rows = row_maps + (size_t)((sweep + 1) % 3) * map_words;
+        uint32_t* next_rows = row_maps + (size_t)((sweep + 2) % 3) * map_words;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < map_words; i += (size_t)gridDim.x * blockDim.x) next_rows[i] = 0;
         // (A) this sweep's visits
         for (int i = blockIdx.x * blockDim.x + tid; i < 2 * n_units; i += gridDim.x * blockDim.x)
         {
@@ -276,6 +287,23 @@ __global__ void __launch_bounds__(256) gc_relax_all_kernel(LightWorld w, const u
             const int unit = sun ? item : item - n_units;
             const int slot = unit / kUnitsPerBrick;
             uint32_t m = sun ? word : ~word;                      // block light: every non-opaque cell
+            if (sweep > 0 && m)
+            {
+                // a cell can only change when a neighbour's value has: this row, the rows above / below / in front / behind it,
+                // or the same row of the bricks to the left / right changed in the previous sweep — else the row is left alone
+                const uint32_t* pr = prev_rows + (sun ? (size_t)0 : (size_t)n_slots * 64);
+                const int col = slot >> 2, cy = slot & 3, cx = col % w.size_x, cz = col / w.size_x;
+                const int r = (unit % kUnitsPerBrick) * kUnitRows + tid, y = r & 63, z = r >> 6;
+                uint32_t on = row_bit(pr, slot, r);
+                if (y > 0) on |= row_bit(pr, slot, r - 1); else if (cy > 0) on |= row_bit(pr, slot - 1, r + 63);
+                if (y < 63) on |= row_bit(pr, slot, r + 1); else if (cy < 3) on |= row_bit(pr, slot + 1, r - 63);
+                if (z > 0) on |= row_bit(pr, slot, r - 64); else if (cz > 0) on |= row_bit(pr, slot - 4 * w.size_x, r + 31 * 64);
+                if (z < 31) on |= row_bit(pr, slot, r + 64); else if (cz < w.size_z - 1) on |= row_bit(pr, slot + 4 * w.size_x, r - 31 * 64);
+                if (cx > 0) on |= row_bit(pr, slot - 4, r);
+                if (cx < w.size_x - 1) on |= row_bit(pr, slot + 4, r);
+                if (!on) m = 0;
+            }
+            if (tid < kUnitRows / 32) s_row_changed[tid] = 0;
             // the next visit's bit-map word travels while this one is worked on
             if (j + gridDim.x < n)
             {
@@ -312,10 +340,19 @@ __global__ void __launch_bounds__(256) gc_relax_all_kernel(LightWorld w, const u
             const uint32_t v0 = (uint32_t)unit * (uint32_t)(kUnitRows * 32);
             for (uint32_t k = tid; k < total; k += 256)
             {
-                const uint32_t v = v0 + s_cells[k];
-                if (sun ? relax_voxel<true>(w, v) : relax_voxel<false>(w, v)) any = true;
+                const uint32_t c = s_cells[k];
+                if (sun ? relax_voxel<true>(w, v0 + c) : relax_voxel<false>(w, v0 + c))
+                {
+                    any = true;
+                    atomicOr(&s_row_changed[c >> 10], 1u << ((c >> 5) & 31));
+                }
             }
-            if (__syncthreads_or(any ? 1 : 0) && tid == 0) (sun ? sun_flags : light_flags)[now_off + slot] = 1;
+            if (__syncthreads_or(any ? 1 : 0))
+            {
+                if (tid == 0) (sun ? sun_flags : light_flags)[now_off + slot] = 1;
+                if (tid < kUnitRows / 32 && s_row_changed[tid])
+                    now_rows[(sun ? (size_t)0 : (size_t)n_slots * 64) + (size_t)slot * 64 + (unit % kUnitsPerBrick) * (kUnitRows / 32) + tid] = s_row_changed[tid];
+            }
         }
         if (blockIdx.x == 0 && tid == 0) counters[LC_SWEEPS] = (uint32_t)(sweep + 1);
         grid.sync();
@@ -360,7 +397,7 @@ cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_bits, uint32_t*
 }
 
 cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, const uint8_t* sun_unit, uint8_t* sun_flags, uint8_t* light_flags,
-                             size_t flag_stride, uint32_t* lists, uint32_t* counters, int num_sms, cudaStream_t s)
+                             size_t flag_stride, uint32_t* lists, uint32_t* row_maps, uint32_t* counters, int num_sms, cudaStream_t s)
 {
     // every CTA has to be resident (grid barriers): the occupancy query bounds the grid, the cooperative launch enforces it.
     // (a barrier costs more the more CTAs take part: six per SM keep ~1500 cells per SM in flight)
@@ -373,7 +410,7 @@ cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, cons
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     LightWorld lw = w;
-    void* args[] = { &lw, &sun_bits, &opq_bits, &sun_unit, &sun_flags, &light_flags, &flag_stride, &lists, &counters };
+    void* args[] = { &lw, &sun_bits, &opq_bits, &sun_unit, &sun_flags, &light_flags, &flag_stride, &lists, &row_maps, &counters };
     return cudaLaunchCooperativeKernel((const void*)gc_relax_all_kernel, dim3(num_sms * per_sm), dim3(256), args, 0, s);
 }
 

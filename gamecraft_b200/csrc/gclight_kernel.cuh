@@ -40,9 +40,11 @@ cudaError_t launch_surface(const LightWorld& w, uint8_t* brick_top, cudaStream_t
 cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_bits, uint32_t* opq_bits, uint8_t* sun_flag, uint8_t* sun_unit, uint8_t* seed_flag, uint32_t* counters, cudaStream_t s);
 // the relaxation of both fills, all sweeps in one cooperative launch: sweep k visits the bricks that, or whose face neighbours,
 // changed in sweep k - 1 (flag arrays [k] -> [k + 1], `flag_stride` bytes apart, cleared by the caller except [0] from the scan);
-// lists: 2 x (2 x 8 x bricks) words of scratch (visits are units of 256 rows); ends at the first sweep that has nothing to visit
+// lists: 2 x (2 x 8 x bricks) words of scratch (visits are units of 256 rows); row_maps: 3 x (2 x 64 x bricks) words — per sweep
+// and fill one bit per row "changed" (map 1 cleared by the caller, the kernel clears the others as it goes); ends at the first
+// sweep that has nothing to visit
 cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, const uint8_t* sun_unit, uint8_t* sun_flags, uint8_t* light_flags,
-                             size_t flag_stride, uint32_t* lists, uint32_t* counters, int num_sms, cudaStream_t s);
+                             size_t flag_stride, uint32_t* lists, uint32_t* row_maps, uint32_t* counters, int num_sms, cudaStream_t s);
 // the edit path's sweep over its two candidate lists (gcedit_kernel.cu): both fills in one launch; the lists' lengths are read
 // from device memory, `cap` is their capacity; changed_*: this sweep's flag word, the previous sweep's at changed_*[-1]
 cudaError_t launch_relax_pair(const LightWorld& w, const uint32_t* sun_list, const uint32_t* light_list, uint32_t cap, const uint32_t* n_sun,

@@ -991,7 +991,8 @@ int gcmesh_world_light(GcWorld* w)
     {
         GC_CUDA(cudaMalloc(&w->d_light_counters, kLightCounterWords * sizeof(uint32_t)));
         GC_CUDA(cudaMallocHost(&w->h_light_counters, kLightCounterWords * sizeof(uint32_t)));
-        GC_CUDA(cudaMalloc(&w->d_light_bits, 2 * bits_bytes + 32 * w->n_slots * sizeof(uint32_t)));   // + the two visit lists (2 fills x 8 units per brick each)
+        // + the two visit lists (2 fills x 8 units per brick each) + three "row changed" maps (2 fills x 64 words per brick each)
+        GC_CUDA(cudaMalloc(&w->d_light_bits, 2 * bits_bytes + (32 + 3 * 128) * w->n_slots * sizeof(uint32_t)));
         GC_CUDA(cudaMalloc(&w->d_brick_flags, flags_bytes));
     }
     const LightWorld lw = light_world(w);
@@ -1015,11 +1016,14 @@ int gcmesh_world_light(GcWorld* w)
     w->light_launches = 0;
     // 1. one pass over the column cells up to maxY: candidate bit maps, emitters seeded, the first sweep's active bricks
     GC_CUDA(launch_light_scan(lw, sun_bits, opq_bits, sun_flags, sun_unit, light_flags, c, s)); w->light_launches++;
+    uint32_t* visit_lists = w->d_light_bits + 2 * w->n_slots * 2048;
+    uint32_t* row_maps = visit_lists + 32 * w->n_slots;
+    GC_CUDA(cudaMemsetAsync(row_maps + 128 * w->n_slots, 0, 128 * w->n_slots * sizeof(uint32_t), s));   // the map the first sweep writes (the kernel clears the others)
     // 2. relaxation: a value falls by at least one per hop and nothing at or below MIN_LIGHT is stored, so 14 in-place sweeps
     // reach the fixpoint; one persistent kernel runs them with grid barriers in between, visits per sweep only the bricks
     // that changed in the sweep before (or whose face neighbours did) — in units of 256 rows whose candidates a CTA spreads over
     // its threads one cell each — and ends with the first sweep that finds none
-    GC_CUDA(launch_relax_all(lw, sun_bits, opq_bits, sun_unit, sun_flags, light_flags, flag_stride, w->d_light_bits + 2 * w->n_slots * 2048, c, ctx->num_sms, s));
+    GC_CUDA(launch_relax_all(lw, sun_bits, opq_bits, sun_unit, sun_flags, light_flags, flag_stride, visit_lists, row_maps, c, ctx->num_sms, s));
     w->light_launches++;
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
     memset(w->slot_dirty, 7, w->n_slots);
