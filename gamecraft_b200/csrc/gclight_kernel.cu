@@ -13,6 +13,7 @@
 // per brick: nothing is sized on the host, so the call enqueues a fixed sequence of launches and never synchronises.
 // Canonical form of the reference's column-order dependent block-light seeding: see oracle/gc_light_cpu.c.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "gclight_kernel.cuh"
 
@@ -229,7 +230,7 @@ constexpr int kUnitRows = 256, kUnitsPerBrick = 2048 / kUnitRows;
 // "did row r of brick `slot` change in the previous sweep?" — one bit per row, 64 words per brick
 __device__ __forceinline__ uint32_t row_bit(const uint32_t* rows, int slot, int r) { return (__ldcg(rows + (size_t)slot * 64 + (r >> 5)) >> (r & 31)) & 1u; }
 
-__global__ void __launch_bounds__(256) gc_relax_all_kernel(LightWorld w, const uint32_t* __restrict__ sun_bits, const uint32_t* __restrict__ opq_bits,
+__global__ void __launch_bounds__(256, 8) gc_relax_all_kernel(LightWorld w, const uint32_t* __restrict__ sun_bits, const uint32_t* __restrict__ opq_bits,
                                                            const uint8_t* __restrict__ sun_unit, uint8_t* sun_flags, uint8_t* light_flags, size_t flag_stride,
                                                            uint32_t* lists, uint32_t* row_maps, uint32_t* counters)
 {
@@ -406,7 +407,8 @@ cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, cons
     {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc_relax_all_kernel, 256, 0);
         if (e != cudaSuccess) return e;
-        if (per_sm > 6) per_sm = 6;
+        if (per_sm > 8) per_sm = 8;
+        if (const char* env = getenv("GCMESH_LIGHT_CTAS_PER_SM")) { const int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     LightWorld lw = w;
