@@ -128,6 +128,7 @@ struct GcWorld
     uint32_t* d_light_counters;   // 8 x u32
     uint32_t* h_light_counters;   // pinned
     uint8_t* d_brick_flags;       // per brick and sweep: changed (2 x (kLightSweeps + 1) arrays)
+    uint8_t* d_group_sun; uint8_t* d_group_light; size_t group_light_slots;   // gcmesh_mesh_host without light arrays: the light of one group of rows
     uint32_t* d_light_bits;       // candidate bit maps: sunlight candidates, then opaque cells (2048 words per brick each)
     uint8_t* d_brick_top;         // compute_surface scratch: per brick, the highest block of every column cell
     int light_launches;
@@ -450,7 +451,7 @@ int gcmesh_world_destroy(GcWorld* w)
     if (w->h_rle_bad) cudaFreeHost(w->h_rle_bad);
     if (w->h_rle_words) cudaFreeHost(w->h_rle_words);
     cudaFree(w->d_brick_top);
-    cudaFree(w->d_light_counters); cudaFree(w->d_brick_flags); cudaFree(w->d_light_bits);
+    cudaFree(w->d_light_counters); cudaFree(w->d_brick_flags); cudaFree(w->d_light_bits); cudaFree(w->d_group_sun); cudaFree(w->d_group_light);
     if (w->h_light_counters) cudaFreeHost(w->h_light_counters);
     for (int d = 0; d < 2; d++)
         for (int k = 0; k < 5; k++)
@@ -657,6 +658,7 @@ static inline bool brick_neighbourhood_is_air(const GcWorld* w, size_t slot)
 static inline void scan_lights(GcWorld* w, size_t slot, const uint8_t* sunlight, const uint8_t* block_light, const uint8_t* surface)
 {
     uint8_t f = w->block_flags[slot];
+    if (!sunlight) { w->scan_flags[slot] = f; return; }          // (no light arrays handed in: the light is filled on the device)
     static const bool skip_rule = []() { const char* e = getenv("GCMESH_SCAN_LIGHT_SKIP"); return !(e && e[0] == '0'); }();
     if (!skip_rule || !(brick_neighbourhood_is_air(w, slot) || light_out_of_reach(w, surface, slot)))
     {
@@ -757,6 +759,7 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
     {
         const size_t bytes = a == 0 ? (size_t)GC_CHUNK_SIZE_3 * 2 : (size_t)GC_CHUNK_SIZE_3;
         const uint8_t* src0 = a == 0 ? (const uint8_t*)blocks : (a == 1 ? sunlight : block_light);
+        if (!src0) continue;
         uint8_t* dst0 = a == 0 ? (uint8_t*)w->d_blocks : (a == 1 ? w->d_sun : w->d_light);
         for (int cy = 0; cy < GC_WORLD_CHUNK_HEIGHT; cy++)
         {
@@ -785,7 +788,8 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
     // arrays that held data on the device and are zero now
     for (size_t slot = s_begin; slot < s_end; slot++)
     {
-        const uint8_t f = w->scan_flags[slot], stale = w->slot_dirty[slot] & ~f;
+        const uint8_t keep = sunlight ? 0 : 6;                    // (no light arrays handed in: the device's light arrays are left alone)
+        const uint8_t f = w->scan_flags[slot] | (w->slot_dirty[slot] & keep), stale = w->slot_dirty[slot] & ~f;
         for (int a = 0; a < 3 && stale; a++)
             if (stale & (1 << a))
             {
@@ -829,8 +833,8 @@ static bool host_arrays_mapped(const void* blocks, const void* sunlight, const v
 {
     cudaPointerAttributes attr;
     const bool mapped = cudaPointerGetAttributes(&attr, blocks) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr
-                        && cudaPointerGetAttributes(&attr, sunlight) == cudaSuccess && attr.type == cudaMemoryTypeHost
-                        && cudaPointerGetAttributes(&attr, block_light) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+                        && (!sunlight || (cudaPointerGetAttributes(&attr, sunlight) == cudaSuccess && attr.type == cudaMemoryTypeHost))
+                        && (!block_light || (cudaPointerGetAttributes(&attr, block_light) == cudaSuccess && attr.type == cudaMemoryTypeHost));
     cudaGetLastError();
     return mapped;
 }
@@ -973,6 +977,54 @@ int gcmesh_world_compute_surface(GcWorld* w)
     return GC_OK;
 }
 
+// Scratch of the light fill (sized for the whole window once; a fill over a range of rows uses the front of it).
+static int light_scratch(GcWorld* w)
+{
+    if (w->d_light_counters) return GC_OK;
+    const size_t bits_bytes = w->n_slots * 2048 * sizeof(uint32_t);
+    const size_t flag_stride = (w->n_slots + 255) & ~(size_t)255;
+    const size_t unit_stride = (w->n_slots * 8 + 255) & ~(size_t)255;
+    GC_CUDA(cudaMalloc(&w->d_light_counters, kLightCounterWords * sizeof(uint32_t)));
+    GC_CUDA(cudaMallocHost(&w->h_light_counters, kLightCounterWords * sizeof(uint32_t)));
+    // two bit maps + the two visit lists (2 fills x 8 units per brick each) + three "row changed" maps (2 fills x 64 words per brick each)
+    GC_CUDA(cudaMalloc(&w->d_light_bits, 2 * bits_bytes + (32 + 3 * 128) * w->n_slots * sizeof(uint32_t)));
+    GC_CUDA(cudaMalloc(&w->d_brick_flags, 2 * (size_t)(kLightSweeps + 1) * flag_stride + unit_stride));
+    return GC_OK;
+}
+
+// Enqueue the fill of `lw` — the window, or a range of its rows seen as a window of its own (rows are contiguous ranges of
+// slots) — on `s`.  lw.sun / lw.light must hold zeros.  Nothing below depends on a count the device produces: candidates
+// are bit maps of fixed size (a word per x-row of a brick), the active set is a byte per brick and sweep — a fixed sequence.
+static int enqueue_light_fill(GcWorld* w, const LightWorld& lw, cudaStream_t s)
+{
+    if (light_scratch(w) != GC_OK) return GC_ERR_CUDA;
+    const size_t n_slots = (size_t)lw.size_x * lw.size_z * GC_WORLD_CHUNK_HEIGHT;
+    const size_t bits_bytes = n_slots * 2048 * sizeof(uint32_t);
+    const size_t flag_stride = (n_slots + 255) & ~(size_t)255;
+    const size_t unit_stride = (n_slots * 8 + 255) & ~(size_t)255;               // per unit (256 rows; 8 per brick): holds a sunlight candidate
+    const size_t flags_bytes = 2 * (size_t)(kLightSweeps + 1) * flag_stride + unit_stride;   // sunlight, then blockLight: sweep k reads [k], writes [k + 1]; then the unit bytes
+    uint32_t* c = w->d_light_counters;
+    uint32_t* sun_bits = w->d_light_bits;
+    uint32_t* opq_bits = w->d_light_bits + n_slots * 2048;
+    uint8_t* sun_flags = w->d_brick_flags;
+    uint8_t* light_flags = w->d_brick_flags + (size_t)(kLightSweeps + 1) * flag_stride;
+    uint8_t* sun_unit = w->d_brick_flags + 2 * (size_t)(kLightSweeps + 1) * flag_stride;
+    GC_CUDA(cudaMemsetAsync(c, 0, kLightCounterWords * sizeof(uint32_t), s));
+    GC_CUDA(cudaMemsetAsync(w->d_light_bits, 0, 2 * bits_bytes, s));
+    GC_CUDA(cudaMemsetAsync(w->d_brick_flags, 0, flags_bytes, s));
+    // 1. one pass over the column cells up to maxY: candidate bit maps, emitters seeded, the first sweep's active bricks
+    GC_CUDA(launch_light_scan(lw, sun_bits, opq_bits, sun_flags, sun_unit, light_flags, c, s));
+    uint32_t* visit_lists = w->d_light_bits + 2 * n_slots * 2048;
+    uint32_t* row_maps = visit_lists + 32 * n_slots;
+    GC_CUDA(cudaMemsetAsync(row_maps + 128 * n_slots, 0, 128 * n_slots * sizeof(uint32_t), s));   // the map the first sweep writes (the kernel clears the others)
+    // 2. relaxation: a value falls by at least one per hop and nothing at or below MIN_LIGHT is stored, so 14 in-place sweeps
+    // reach the fixpoint; one persistent kernel runs them with grid barriers in between, visits per sweep only the bricks
+    // that changed in the sweep before (or whose face neighbours did) — in units of 256 rows whose candidates a CTA spreads over
+    // its threads one cell each — and ends with the first sweep that finds none
+    GC_CUDA(launch_relax_all(lw, sun_bits, opq_bits, sun_unit, sun_flags, light_flags, flag_stride, visit_lists, row_maps, c, w->ctx->num_sms, s));
+    return GC_OK;
+}
+
 int gcmesh_world_light(GcWorld* w)
 {
     if (!w) return fail(GC_ERR_ARG, "world is null");
@@ -981,27 +1033,6 @@ int gcmesh_world_light(GcWorld* w)
     GcContext* ctx = w->ctx;
     GC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    // Nothing below depends on a count the device produces: candidates are bit maps of fixed size (a word per x-row of a
-    // brick), the active set is a byte per brick and sweep — the call enqueues a fixed sequence and returns.
-    const size_t bits_bytes = w->n_slots * 2048 * sizeof(uint32_t);
-    const size_t flag_stride = (w->n_slots + 255) & ~(size_t)255;
-    const size_t unit_stride = (w->n_slots * 8 + 255) & ~(size_t)255;               // per unit (256 rows; 8 per brick): holds a sunlight candidate
-    const size_t flags_bytes = 2 * (size_t)(kLightSweeps + 1) * flag_stride + unit_stride;   // sunlight, then blockLight: sweep k reads [k], writes [k + 1]; then the unit bytes
-    if (!w->d_light_counters)
-    {
-        GC_CUDA(cudaMalloc(&w->d_light_counters, kLightCounterWords * sizeof(uint32_t)));
-        GC_CUDA(cudaMallocHost(&w->h_light_counters, kLightCounterWords * sizeof(uint32_t)));
-        // + the two visit lists (2 fills x 8 units per brick each) + three "row changed" maps (2 fills x 64 words per brick each)
-        GC_CUDA(cudaMalloc(&w->d_light_bits, 2 * bits_bytes + (32 + 3 * 128) * w->n_slots * sizeof(uint32_t)));
-        GC_CUDA(cudaMalloc(&w->d_brick_flags, flags_bytes));
-    }
-    const LightWorld lw = light_world(w);
-    uint32_t* c = w->d_light_counters;
-    uint32_t* sun_bits = w->d_light_bits;
-    uint32_t* opq_bits = w->d_light_bits + w->n_slots * 2048;
-    uint8_t* sun_flags = w->d_brick_flags;
-    uint8_t* light_flags = w->d_brick_flags + (size_t)(kLightSweeps + 1) * flag_stride;
-    uint8_t* sun_unit = w->d_brick_flags + 2 * (size_t)(kLightSweeps + 1) * flag_stride;
     // freshly generated chunks hold no light (World.cpp:632): the fill starts from zero (arenas known to be zero are not cleared again)
     if (!(w->light_zero && !w->light_untracked))
     {
@@ -1010,21 +1041,8 @@ int gcmesh_world_light(GcWorld* w)
     }
     w->light_zero = false;
     w->light_partial = false;   // from here on the arenas hold the whole fill
-    GC_CUDA(cudaMemsetAsync(c, 0, kLightCounterWords * sizeof(uint32_t), s));
-    GC_CUDA(cudaMemsetAsync(w->d_light_bits, 0, 2 * bits_bytes, s));
-    GC_CUDA(cudaMemsetAsync(w->d_brick_flags, 0, flags_bytes, s));
-    w->light_launches = 0;
-    // 1. one pass over the column cells up to maxY: candidate bit maps, emitters seeded, the first sweep's active bricks
-    GC_CUDA(launch_light_scan(lw, sun_bits, opq_bits, sun_flags, sun_unit, light_flags, c, s)); w->light_launches++;
-    uint32_t* visit_lists = w->d_light_bits + 2 * w->n_slots * 2048;
-    uint32_t* row_maps = visit_lists + 32 * w->n_slots;
-    GC_CUDA(cudaMemsetAsync(row_maps + 128 * w->n_slots, 0, 128 * w->n_slots * sizeof(uint32_t), s));   // the map the first sweep writes (the kernel clears the others)
-    // 2. relaxation: a value falls by at least one per hop and nothing at or below MIN_LIGHT is stored, so 14 in-place sweeps
-    // reach the fixpoint; one persistent kernel runs them with grid barriers in between, visits per sweep only the bricks
-    // that changed in the sweep before (or whose face neighbours did) — in units of 256 rows whose candidates a CTA spreads over
-    // its threads one cell each — and ends with the first sweep that finds none
-    GC_CUDA(launch_relax_all(lw, sun_bits, opq_bits, sun_unit, sun_flags, light_flags, flag_stride, visit_lists, row_maps, c, ctx->num_sms, s));
-    w->light_launches++;
+    if (enqueue_light_fill(w, light_world(w), s) != GC_OK) return GC_ERR_CUDA;
+    w->light_launches = 2;
     // the sparse-upload bookkeeping no longer knows what the device arrays hold
     memset(w->slot_dirty, 7, w->n_slots);
     return GC_OK;
@@ -1563,12 +1581,12 @@ static int validate_coords(const GcWorld* w, const GcChunkCoord* coords, int n)
 // a launch resets the work counter and (unless keep_cursor) the quad cursor, and leaves the cursor's value in word 3 of the
 // control block: no memset between launches.
 static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cudaStream_t s, bool keep_cursor = false, const int32_t* order = nullptr,
-                                const HaloFused* halo = nullptr)
+                                const HaloFused* halo = nullptr, const uint8_t* sun = nullptr, const uint8_t* light = nullptr)
 {
     GcContext* ctx = w->ctx;
     if (count <= 0) return cudaSuccess;
     MeshParams p;
-    p.blocks = w->d_blocks; p.sun = w->d_sun; p.light = w->d_light; p.surface = w->d_surface;
+    p.blocks = w->d_blocks; p.sun = sun ? sun : w->d_sun; p.light = light ? light : w->d_light; p.surface = w->d_surface;
     p.size_x = w->size_x; p.size_z = w->size_z;
     p.coords = b->d_coords + first; p.order = order; p.n_chunks = count; p.out = b->d_out + first;
     p.vertex_arena = b->d_vertices; p.index_arena = b->d_indices; p.max_quads = b->max_quads;
@@ -1719,7 +1737,12 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
                      const uint8_t* surface, const uint8_t* nonzero_hint, const GcChunkCoord* coords, int n,
                      void* host_vertices, void* host_indices, uint64_t host_capacity_quads, int threads)
 {
-    if (!w || !b || !blocks || !sunlight || !block_light || !surface || (!coords && n > 0)) return fail(GC_ERR_ARG, "null argument");
+    if (!w || !b || !blocks || !surface || (!coords && n > 0)) return fail(GC_ERR_ARG, "null argument");
+    if ((sunlight == nullptr) != (block_light == nullptr)) return fail(GC_ERR_ARG, "hand in both light arrays or neither");
+    // neither light array: the light is filled on the device from the block ids and the surface map (what PreprocessGroup
+    // computes, WorldRender.cpp:240-262), group of rows by group of rows, and only block ids cross the link
+    const bool device_light = sunlight == nullptr;
+    if (device_light && (size_t)w->size_x * GC_WORLD_CHUNK_HEIGHT * 16 > 65535) return fail(GC_ERR_CAPACITY, "window too wide for the light fill (32-bit voxel addresses)");
     if (w->ctx != b->ctx) return fail(GC_ERR_ARG, "world and batch belong to different contexts");
     if (n < 0 || n > b->max_chunks) return fail(GC_ERR_CAPACITY, "batch created for fewer chunks");
     if (validate_coords(w, coords, n) != GC_OK) return GC_ERR_ARG;
@@ -1791,6 +1814,59 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         return GC_OK;
     };
 
+    // ---- device light: groups of strips ----
+    // A group's light is filled into a scratch pair of arenas over the rows [z0 - 2, z1 + 2) around its rows [z0, z1) seen as a
+    // window of their own: its edge rows only receive, the rows next to them are seeded like every inner column — light reaches
+    // less than a column (15 voxels), so the cells the group's chunks read (one voxel into rows z0 - 1 and z1) hold exactly
+    // what the fill of the whole window gives them.  The group's chunks are then meshed against the scratch arenas (base pointers
+    // shifted so that window slots address them).  Fill and meshing follow each other on the context stream, so one scratch
+    // pair serves every group; uploads of the next group and read-backs of the previous one run beside them.
+    static const int group_rows_env = getenv("GCMESH_LIGHT_GROUP_ROWS") ? atoi(getenv("GCMESH_LIGHT_GROUP_ROWS")) : 0;
+    const int group_strips = device_light ? std::max(1, (group_rows_env > 0 ? group_rows_env : 6) / kStripRows) : 0;
+    const int n_groups = device_light ? (n_strips + group_strips - 1) / group_strips : 0;
+    if (device_light)
+    {
+        const size_t need = (size_t)(group_strips * kStripRows + 4) * w->size_x * GC_WORLD_CHUNK_HEIGHT;
+        if (need > 65535) return fail(GC_ERR_CAPACITY, "light group too large for the light fill (32-bit voxel addresses): lower GCMESH_LIGHT_GROUP_ROWS");
+        if (w->group_light_slots < need)
+        {
+            cudaFree(w->d_group_sun); cudaFree(w->d_group_light); w->d_group_sun = w->d_group_light = nullptr; w->group_light_slots = 0;
+            GC_CUDA(cudaMalloc(&w->d_group_sun, need * GC_CHUNK_SIZE_3));
+            GC_CUDA(cudaMalloc(&w->d_group_light, need * GC_CHUNK_SIZE_3));
+            w->group_light_slots = need;
+        }
+        if (light_scratch(w) != GC_OK) return GC_ERR_CUDA;
+    }
+    auto light_and_mesh_group = [&](int g) -> int                // the strips of group g and the one after it are uploaded (or queued)
+    {
+        const int s0 = g * group_strips, s1 = std::min(s0 + group_strips, n_strips);
+        const int z0 = s0 * kStripRows, z1 = std::min(s1 * kStripRows, w->size_z);
+        const int r0 = std::max(z0 - 2, 0), r1 = std::min(z1 + 2, w->size_z);
+        const int up = std::min((r1 - 1) / kStripRows, n_strips - 1);
+        GC_CUDA(cudaStreamWaitEvent(sm, ctx->ev_uploaded[up], 0));
+        bool any = false;
+        for (int j = s0; j < s1; j++) any = any || first[j + 1] > first[j];
+        const size_t slot0 = (size_t)r0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, n_sub = (size_t)(r1 - r0) * w->size_x * GC_WORLD_CHUNK_HEIGHT;
+        if (any)
+        {
+            GC_CUDA(cudaMemsetAsync(w->d_group_sun, 0, n_sub * GC_CHUNK_SIZE_3, sm));
+            GC_CUDA(cudaMemsetAsync(w->d_group_light, 0, n_sub * GC_CHUNK_SIZE_3, sm));
+            LightWorld lw = light_world(w);
+            lw.blocks = w->d_blocks + slot0 * GC_CHUNK_SIZE_3; lw.surface = w->d_surface + (slot0 / GC_WORLD_CHUNK_HEIGHT) * GC_CHUNK_SIZE_2;
+            lw.sun = w->d_group_sun; lw.light = w->d_group_light; lw.size_z = r1 - r0;
+            if (enqueue_light_fill(w, lw, sm) != GC_OK) return GC_ERR_CUDA;
+            b->launches += 2;
+        }
+        for (int j = s0; j < s1; j++)
+        {
+            GC_CUDA(launch_range(w, b, first[j], first[j + 1] - first[j], sm, j != last_nonempty, nullptr, nullptr,
+                                 w->d_group_sun - slot0 * GC_CHUNK_SIZE_3, w->d_group_light - slot0 * GC_CHUNK_SIZE_3));
+            GC_CUDA(cudaMemcpyAsync(&cursors[j], b->d_cursor + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm));
+            GC_CUDA(cudaEventRecord(ctx->ev_meshed[j], sm));
+        }
+        return GC_OK;
+    };
+
     const auto t_begin = std::chrono::steady_clock::now();
     auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     double t_scan_done[64] = { 0 };                           // (trace) when the scan threads finished each strip
@@ -1825,6 +1901,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
 
     const bool trace = getenv("GCMESH_TRACE") != nullptr;
     double t_scanned[64], t_enqueued[64];
+    int next_group = 0, next_read = 0;
     for (int k = 0; k < n_strips; k++)
     {
         const int cz0 = k * kStripRows, cz1 = cz0 + kStripRows < w->size_z ? cz0 + kStripRows : w->size_z;
@@ -1837,15 +1914,36 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         GC_CUDA(cudaStreamWaitEvent(su, ctx->ev_up2, 0));
         GC_CUDA(cudaEventRecord(ctx->ev_uploaded[k], su));
         t_enqueued[k] = now_ms();
+        if (device_light)
+        {
+            // a group goes to the device once the strip behind its last row is queued; the group before it is read back then
+            while (next_group < n_groups)
+            {
+                const int s1 = std::min((next_group + 1) * group_strips, n_strips);
+                const int need = std::min((std::min(s1 * kStripRows, w->size_z) + 1) / kStripRows, n_strips - 1);
+                if (need > k) break;
+                { const int st = light_and_mesh_group(next_group); if (st != GC_OK) return st; }
+                next_group++;
+                while (next_read < (next_group - 1) * group_strips) { const int st = read_back(next_read++); if (st != GC_OK) return st; }
+            }
+            continue;
+        }
         if (k >= 1) { const int st = mesh_strip(k - 1); if (st != GC_OK) return st; }
         if (k >= 2) { const int st = read_back(k - 2); if (st != GC_OK) return st; }
     }
-    { const int st = mesh_strip(n_strips - 1); if (st != GC_OK) return st; }
+    if (device_light)
+        while (next_group < n_groups) { const int st = light_and_mesh_group(next_group++); if (st != GC_OK) return st; }
+    else { const int st = mesh_strip(n_strips - 1); if (st != GC_OK) return st; }
     GC_CUDA(cudaEventRecord(b->ev_stop, sm));
     GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, sm));
     GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, 32, cudaMemcpyDeviceToHost, sm));
-    if (n_strips >= 2) { const int st = read_back(n_strips - 2); if (st != GC_OK) return st; }
-    { const int st = read_back(n_strips - 1); if (st != GC_OK) return st; }
+    if (device_light)
+        while (next_read < n_strips) { const int st = read_back(next_read++); if (st != GC_OK) return st; }
+    else
+    {
+        if (n_strips >= 2) { const int st = read_back(n_strips - 2); if (st != GC_OK) return st; }
+        { const int st = read_back(n_strips - 1); if (st != GC_OK) return st; }
+    }
     GC_CUDA(cudaEventRecord(ctx->ev_join, sd));
     GC_CUDA(cudaStreamWaitEvent(sm, ctx->ev_join, 0));
     GC_CUDA(cudaEventRecord(b->ev_done, sm));

@@ -703,3 +703,52 @@ def test_gpu_surface_bounds_mesh_option(ctx):
     world.set_option(mesher.WORLD_SURFACE_BOUNDS_MESH, 1)
     assert mesher.rebuild_chunks(world, [(1, 0, 1)])[0].vert_count == 0
     world.close()
+
+
+@pytest.mark.parametrize("kind,size,seed,kw", [("forest", 9, 3, {}), ("mixed", 8, 29, dict(radius=140, falloff=80)), ("islands", 11, 8, dict(radius=150, falloff=90)),
+                                               ("volcanic", 7, 2, {})])
+def test_gpu_mesh_host_without_light_arrays(ctx, kind, size, seed, kw):
+    """gcmesh_mesh_host with sunlight == block_light == NULL: only block ids cross the link, the light is filled on the device
+    group of rows by group of rows (each group a window of its own with a two-row margin), and the meshes equal the oracle's
+    meshes of the window lit by the oracle's fill of the WHOLE window — whatever the group boundaries cut through (tree shadows,
+    water, emitters next to a boundary).  Called twice: the second call finds the scratch arenas used."""
+    import torch
+
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(size, size, origin=(-(size // 2), -(size // 2))).generate(kind, seed, **kw)
+    if kind == "forest":
+        for wz in (127, 128, 191, 192):                                       # lanterns either side of a group boundary (rows 5 | 6) and of its margin (3 | 4)
+            w.set_block(100, 60, wz, 14)
+            w.set_block(140, 58, wz, 17)
+    w.surface[:] = ob.compute_surface(w)
+    w.sun[:], w.light[:] = ob.light_fill(w, w.surface)
+    coords = w.interior_chunks(1)
+    o = ob.OracleWorld(w)
+    pins = [torch.from_numpy(a).pin_memory() for a in (w.blocks, w.surface)]
+
+    class P:
+        size_x, size_z = size, size
+        blocks, surface = [t.numpy() for t in pins]
+        sun = None
+        light = None
+
+    world = mesher.World(ctx, size, size)
+    batch = mesher.Batch(ctx, len(coords), len(coords) * 3000)
+    hv = torch.zeros((len(coords) * 3000 * 4, 12), dtype=torch.uint8).pin_memory().numpy()
+    hi = torch.zeros(len(coords) * 3000 * 6, dtype=torch.uint16).pin_memory().numpy()
+    for rep in range(2):
+        if rep == 1:
+            world.set_option(mesher.WORLD_SURFACE_BOUNDS_BLOCKS, 1).set_option(mesher.WORLD_SURFACE_BOUNDS_MESH, 1)
+        batch.mesh_host(world, P, coords, hv, hi)
+        desc, q = batch.results()
+        bad, result, checked = o.check_batch(coords, desc.copy(), hv, hi)
+        assert bad == 0, "%d of %d chunks differ (call %d)" % (bad, len(coords), rep)
+        assert checked == q and q > 20000
+        assert world.upload_bytes() < w.blocks.nbytes                           # block ids only, and not the air
+    with pytest.raises(mesher.GcMeshError):
+        world.set_blocks([(40, 70, 40, 3)])                                     # the window's own light arenas do not hold the fill
+    P.sun = w.sun
+    with pytest.raises(mesher.GcMeshError):
+        batch.mesh_host(world, P, coords, hv, hi)                               # one light array without the other
+    batch.close(); world.close()
