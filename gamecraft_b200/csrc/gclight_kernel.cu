@@ -230,17 +230,32 @@ constexpr int kUnitRows = 256, kUnitsPerBrick = 2048 / kUnitRows;
 // "did row r of brick `slot` change in the previous sweep?" — one bit per row, 64 words per brick
 __device__ __forceinline__ uint32_t row_bit(const uint32_t* rows, int slot, int r) { return (__ldcg(rows + (size_t)slot * 64 + (r >> 5)) >> (r & 31)) & 1u; }
 
-__global__ void __launch_bounds__(256, 8) gc_relax_all_kernel(LightWorld w, const uint32_t* __restrict__ sun_bits, const uint32_t* __restrict__ opq_bits,
-                                                           const uint8_t* __restrict__ sun_unit, uint8_t* sun_flags, uint8_t* light_flags, size_t flag_stride,
-                                                           uint32_t* lists, uint32_t* row_maps, uint32_t* counters)
+constexpr int kRelaxTeams = 4;                                   // teams of 256 threads per CTA: few, fat CTAs keep the grid barriers cheap
+constexpr int kRelaxSmem = kRelaxTeams * (kUnitRows * 32 * 2 + 64);
+// (barrier numbers as literals: with a number in a register ptxas reserves all sixteen hardware barriers for the CTA, and a second
+// CTA no longer fits the SM)
+__device__ __forceinline__ void team_sync(int team)
+{
+    if (team == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else if (team == 1) asm volatile("bar.sync 2, 256;" ::: "memory");
+    else if (team == 2) asm volatile("bar.sync 3, 256;" ::: "memory");
+    else asm volatile("bar.sync 4, 256;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(256 * kRelaxTeams, 2) gc_relax_all_kernel(LightWorld w, const uint32_t* __restrict__ sun_bits, const uint32_t* __restrict__ opq_bits,
+                                                                         const uint8_t* __restrict__ sun_unit, uint8_t* sun_flags, uint8_t* light_flags, size_t flag_stride,
+                                                                         uint32_t* lists, uint32_t* row_maps, uint32_t* counters)
 {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    __shared__ uint16_t s_cells[kUnitRows * 32];
-    __shared__ uint32_t s_warp_total[8];
-    __shared__ uint32_t s_row_changed[kUnitRows / 32];
+    extern __shared__ __align__(16) uint8_t relax_smem[];
+    const int team = threadIdx.x >> 8, tid = threadIdx.x & 255, lane = tid & 31, warp = tid >> 5;
+    uint16_t* s_cells = reinterpret_cast<uint16_t*>(relax_smem) + team * (kUnitRows * 32);
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(relax_smem + kRelaxTeams * kUnitRows * 32 * 2) + team * 16;
+    uint32_t* s_warp_total = s_misc;                              // [8]
+    uint32_t* s_row_changed = s_misc + 8;                         // [kUnitRows / 32 = 8] — word 0 .. 7; "any" is their OR
     const int n_slots = w.size_x * w.size_z * 4;
     const int n_units = n_slots * kUnitsPerBrick;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t vcta = blockIdx.x * kRelaxTeams + team, n_vcta = gridDim.x * kRelaxTeams;   // a team works like a CTA of its own
     for (int sweep = 0; sweep < kLightSweeps; sweep++)
     {
         const size_t prev_off = (size_t)sweep * flag_stride, now_off = prev_off + flag_stride;
@@ -252,9 +267,9 @@ __global__ void __launch_bounds__(256, 8) gc_relax_all_kernel(LightWorld w, cons
         const uint32_t* prev_rows = row_maps + (size_t)(sweep % 3) * map_words;
         uint32_t* now_rows = row_maps + (size_t)((sweep + 1) % 3) * map_words;
         uint32_t* next_rows = row_maps + (size_t)((sweep + 2) % 3) * map_words;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < map_words; i += (size_t)gridDim.x * blockDim.x) next_rows[i] = 0;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < map_words; i += (size_t)gridDim.x * blockDim.x) next_rows[i] = 0;
         // (A) this sweep's visits
-        for (int i = blockIdx.x * blockDim.x + tid; i < 2 * n_units; i += gridDim.x * blockDim.x)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_units; i += gridDim.x * blockDim.x)
         {
             const int sun = i < n_units ? 1 : 0;
             const int unit = sun ? i : i - n_units;
@@ -277,12 +292,12 @@ __global__ void __launch_bounds__(256, 8) gc_relax_all_kernel(LightWorld w, cons
         // (B) the visits
         uint32_t word = 0;
         int item = 0;
-        if (blockIdx.x < n)
+        if (vcta < n)
         {
-            item = (int)__ldcg(list + blockIdx.x);
+            item = (int)__ldcg(list + vcta);
             word = ((item < n_units ? sun_bits : opq_bits))[(size_t)(item < n_units ? item : item - n_units) * kUnitRows + tid];
         }
-        for (uint32_t j = blockIdx.x; j < n; j += gridDim.x)
+        for (uint32_t j = vcta; j < n; j += n_vcta)
         {
             const bool sun = item < n_units;
             const int unit = sun ? item : item - n_units;
@@ -306,9 +321,9 @@ __global__ void __launch_bounds__(256, 8) gc_relax_all_kernel(LightWorld w, cons
             }
             if (tid < kUnitRows / 32) s_row_changed[tid] = 0;
             // the next visit's bit-map word travels while this one is worked on
-            if (j + gridDim.x < n)
+            if (j + n_vcta < n)
             {
-                item = (int)__ldcg(list + j + gridDim.x);
+                item = (int)__ldcg(list + j + n_vcta);
                 word = ((item < n_units ? sun_bits : opq_bits))[(size_t)(item < n_units ? item : item - n_units) * kUnitRows + tid];
             }
             // cells of the unit -> shared list: thread = row, exclusive scan of the rows' candidate counts
@@ -321,7 +336,7 @@ __global__ void __launch_bounds__(256, 8) gc_relax_all_kernel(LightWorld w, cons
                 if (lane >= d) incl += o;
             }
             if (lane == 31) s_warp_total[warp] = incl;
-            __syncthreads();
+            team_sync(team);
             uint32_t base = incl - cnt, total = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++)
@@ -336,26 +351,23 @@ __global__ void __launch_bounds__(256, 8) gc_relax_all_kernel(LightWorld w, cons
                 m &= m - 1;
                 s_cells[base++] = (uint16_t)((tid << 5) | bit);
             }
-            __syncthreads();
-            bool any = false;
+            team_sync(team);
             const uint32_t v0 = (uint32_t)unit * (uint32_t)(kUnitRows * 32);
             for (uint32_t k = tid; k < total; k += 256)
             {
                 const uint32_t c = s_cells[k];
                 if (sun ? relax_voxel<true>(w, v0 + c) : relax_voxel<false>(w, v0 + c))
-                {
-                    any = true;
                     atomicOr(&s_row_changed[c >> 10], 1u << ((c >> 5) & 31));
-                }
             }
-            if (__syncthreads_or(any ? 1 : 0))
+            team_sync(team);
+            if (tid < kUnitRows / 32 && s_row_changed[tid])
             {
-                if (tid == 0) (sun ? sun_flags : light_flags)[now_off + slot] = 1;
-                if (tid < kUnitRows / 32 && s_row_changed[tid])
-                    now_rows[(sun ? (size_t)0 : (size_t)n_slots * 64) + (size_t)slot * 64 + (unit % kUnitsPerBrick) * (kUnitRows / 32) + tid] = s_row_changed[tid];
+                (sun ? sun_flags : light_flags)[now_off + slot] = 1;
+                now_rows[(sun ? (size_t)0 : (size_t)n_slots * 64) + (size_t)slot * 64 + (unit % kUnitsPerBrick) * (kUnitRows / 32) + tid] = s_row_changed[tid];
             }
+            team_sync(team);                                      // (the row words are cleared again at the top)
         }
-        if (blockIdx.x == 0 && tid == 0) counters[LC_SWEEPS] = (uint32_t)(sweep + 1);
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[LC_SWEEPS] = (uint32_t)(sweep + 1);
         grid.sync();
     }
 }
@@ -401,19 +413,21 @@ cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, cons
                              size_t flag_stride, uint32_t* lists, uint32_t* row_maps, uint32_t* counters, int num_sms, cudaStream_t s)
 {
     // every CTA has to be resident (grid barriers): the occupancy query bounds the grid, the cooperative launch enforces it.
-    // (a barrier costs more the more CTAs take part: six per SM keep ~1500 cells per SM in flight)
+    // (a barrier costs more the more CTAs take part: two CTAs of four 256-thread teams per SM — 2048 threads — instead of eight CTAs)
     static int per_sm = 0;
     if (!per_sm)
     {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc_relax_all_kernel, 256, 0);
+        cudaError_t e = cudaFuncSetAttribute(gc_relax_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRelaxSmem);
         if (e != cudaSuccess) return e;
-        if (per_sm > 8) per_sm = 8;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc_relax_all_kernel, 256 * kRelaxTeams, kRelaxSmem);
+        if (e != cudaSuccess) return e;
+        if (per_sm > 2) per_sm = 2;
         if (const char* env = getenv("GCMESH_LIGHT_CTAS_PER_SM")) { const int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     LightWorld lw = w;
     void* args[] = { &lw, &sun_bits, &opq_bits, &sun_unit, &sun_flags, &light_flags, &flag_stride, &lists, &row_maps, &counters };
-    return cudaLaunchCooperativeKernel((const void*)gc_relax_all_kernel, dim3(num_sms * per_sm), dim3(256), args, 0, s);
+    return cudaLaunchCooperativeKernel((const void*)gc_relax_all_kernel, dim3(num_sms * per_sm), dim3(256 * kRelaxTeams), args, kRelaxSmem, s);
 }
 
 cudaError_t launch_relax_pair(const LightWorld& w, const uint32_t* sun_list, const uint32_t* light_list, uint32_t cap, const uint32_t* n_sun,

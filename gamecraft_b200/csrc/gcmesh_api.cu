@@ -746,7 +746,7 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
     uint32_t* items = w->h_items + s_begin * 3;   // this row range's own part of the pinned work list
     w->light_zero = false;
     w->light_partial = true;
-    int n_items = 0;
+    int n_items = 0, n_copies = 0;
     // Non-zero arrays.  A terrain world's non-zero bricks lie at the same height in column after column, and a column's four
     // bricks are consecutive slots: the same array of brick cy of k consecutive columns is a strided block — k rows of one
     // brick array, four brick arrays apart — that ONE 2-D copy moves with the copy engine at full link speed in large
@@ -773,7 +773,8 @@ static int enqueue_rows(GcWorld* w, int cz0, int cz1, const uint16_t* blocks, co
                 const size_t first = col * GC_WORLD_CHUNK_HEIGHT + cy;
                 if ((int)run >= min_run || !mapped)
                 {
-                    cudaStream_t sc = a == 0 ? s : s_light;
+                    // (no light arrays handed in: the block-id runs take turns on the two streams — two copy engines side by side)
+                    cudaStream_t sc = a == 0 ? ((!sunlight && (n_copies++ & 1)) ? s_light : s) : s_light;
                     const cudaError_t e = run == 1 ? cudaMemcpyAsync(dst0 + first * bytes, src0 + first * bytes, bytes, cudaMemcpyHostToDevice, sc)
                                                    : cudaMemcpy2DAsync(dst0 + first * bytes, bytes * GC_WORLD_CHUNK_HEIGHT, src0 + first * bytes, bytes * GC_WORLD_CHUNK_HEIGHT,
                                                                        bytes, run, cudaMemcpyHostToDevice, sc);
@@ -1581,7 +1582,7 @@ static int validate_coords(const GcWorld* w, const GcChunkCoord* coords, int n)
 // a launch resets the work counter and (unless keep_cursor) the quad cursor, and leaves the cursor's value in word 3 of the
 // control block: no memset between launches.
 static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cudaStream_t s, bool keep_cursor = false, const int32_t* order = nullptr,
-                                const HaloFused* halo = nullptr, const uint8_t* sun = nullptr, const uint8_t* light = nullptr)
+                                const HaloFused* halo = nullptr, const uint8_t* sun = nullptr, const uint8_t* light = nullptr, unsigned long long* total_host = nullptr)
 {
     GcContext* ctx = w->ctx;
     if (count <= 0) return cudaSuccess;
@@ -1593,6 +1594,7 @@ static cudaError_t launch_range(GcWorld* w, GcBatch* b, int first, int count, cu
     p.quad_cursor = b->d_cursor; p.work_counter = b->d_counters; p.tables = ctx->d_tables;
     p.error_flag = b->d_counters + 1; p.use_tma = ctx->use_tma; p.prof = b->d_prof;
     p.done_counter = reinterpret_cast<uint32_t*>(b->d_cursor + 2); p.total_out = b->d_cursor + 3; p.keep_cursor = keep_cursor ? 1 : 0;
+    p.total_out_host = total_host;
     p.vert_table = w->d_vert_table;
     p.wide = b->uncapped ? 1 : 0;
     p.trust_surface = w->surface_bounds_mesh ? 1 : 0;
@@ -1788,11 +1790,14 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     for (int j = 0; j < n_strips; j++)
         if (first[j + 1] > first[j]) last_nonempty = j;
 
-    unsigned long long* cursors = ctx->h_strip_cursor;        // pinned: arena cursor after each strip's kernel
+    unsigned long long* cursors = ctx->h_strip_cursor;        // pinned: arena cursor after each strip's kernel, stored by the kernel itself
+    unsigned long long* cursors_dev = nullptr;
+    GC_CUDA(cudaHostGetDevicePointer((void**)&cursors_dev, cursors, 0));
     uint64_t copied = 0;
     auto read_back = [&](int j) -> int                        // strip j has been meshed: copy its arena range to the host buffers
     {
         GC_CUDA(cudaEventSynchronize(ctx->ev_meshed[j]));
+        if (first[j + 1] == first[j]) return GC_OK;           // (a strip without chunks — the window's edge rows — launched nothing)
         uint64_t end = cursors[j] < b->max_quads ? cursors[j] : b->max_quads;
         if (end > host_capacity_quads) end = host_capacity_quads;
         if (end > copied)
@@ -1808,8 +1813,8 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     {
         const int up = j + 1 < n_strips ? j + 1 : n_strips - 1;
         GC_CUDA(cudaStreamWaitEvent(sm, ctx->ev_uploaded[up], 0));
-        GC_CUDA(launch_range(w, b, first[j], first[j + 1] - first[j], sm, j != last_nonempty));
-        GC_CUDA(cudaMemcpyAsync(&cursors[j], b->d_cursor + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm));
+        if (first[j + 1] > first[j])
+            GC_CUDA(launch_range(w, b, first[j], first[j + 1] - first[j], sm, j != last_nonempty, nullptr, nullptr, nullptr, nullptr, cursors_dev + j));
         GC_CUDA(cudaEventRecord(ctx->ev_meshed[j], sm));
         return GC_OK;
     };
@@ -1823,7 +1828,23 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     // pair serves every group; uploads of the next group and read-backs of the previous one run beside them.
     static const int group_rows_env = getenv("GCMESH_LIGHT_GROUP_ROWS") ? atoi(getenv("GCMESH_LIGHT_GROUP_ROWS")) : 0;
     const int group_strips = device_light ? std::max(1, (group_rows_env > 0 ? group_rows_env : 6) / kStripRows) : 0;
-    const int n_groups = device_light ? (n_strips + group_strips - 1) / group_strips : 0;
+    // the first groups are short — one strip, then two — so that the first meshes start their way back early; the read-back
+    // is the longest leg of the call
+    std::vector<int> gfirst;                                     // group g = strips [gfirst[g], gfirst[g + 1])
+    if (device_light)
+        for (int s0 = 0, len = 1; s0 < n_strips; s0 += len)
+        {
+            gfirst.push_back(s0);
+            // ... and so are the last ones (two strips, then one): what follows the last upload — fill, meshing, read-back of the
+            // last group — is not overlapped by anything
+            const int left = n_strips - (s0 + len);
+            len = std::min(len + 1, group_strips);
+            if (left <= 3) len = left == 3 ? 2 : 1;
+            else if (left - len < 3 && left - len > 0) len = left - 3;
+            if (len < 1) len = 1;
+        }
+    const int n_groups = (int)gfirst.size();
+    gfirst.push_back(n_strips);
     if (device_light)
     {
         const size_t need = (size_t)(group_strips * kStripRows + 4) * w->size_x * GC_WORLD_CHUNK_HEIGHT;
@@ -1839,7 +1860,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     }
     auto light_and_mesh_group = [&](int g) -> int                // the strips of group g and the one after it are uploaded (or queued)
     {
-        const int s0 = g * group_strips, s1 = std::min(s0 + group_strips, n_strips);
+        const int s0 = gfirst[g], s1 = gfirst[g + 1];
         const int z0 = s0 * kStripRows, z1 = std::min(s1 * kStripRows, w->size_z);
         const int r0 = std::max(z0 - 2, 0), r1 = std::min(z1 + 2, w->size_z);
         const int up = std::min((r1 - 1) / kStripRows, n_strips - 1);
@@ -1859,9 +1880,9 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         }
         for (int j = s0; j < s1; j++)
         {
-            GC_CUDA(launch_range(w, b, first[j], first[j + 1] - first[j], sm, j != last_nonempty, nullptr, nullptr,
-                                 w->d_group_sun - slot0 * GC_CHUNK_SIZE_3, w->d_group_light - slot0 * GC_CHUNK_SIZE_3));
-            GC_CUDA(cudaMemcpyAsync(&cursors[j], b->d_cursor + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm));
+            if (first[j + 1] > first[j])
+                GC_CUDA(launch_range(w, b, first[j], first[j + 1] - first[j], sm, j != last_nonempty, nullptr, nullptr,
+                                     w->d_group_sun - slot0 * GC_CHUNK_SIZE_3, w->d_group_light - slot0 * GC_CHUNK_SIZE_3, cursors_dev + j));
             GC_CUDA(cudaEventRecord(ctx->ev_meshed[j], sm));
         }
         return GC_OK;
@@ -1919,17 +1940,20 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
             // a group goes to the device once the strip behind its last row is queued; the group before it is read back then
             while (next_group < n_groups)
             {
-                const int s1 = std::min((next_group + 1) * group_strips, n_strips);
+                const int s1 = gfirst[next_group + 1];
                 const int need = std::min((std::min(s1 * kStripRows, w->size_z) + 1) / kStripRows, n_strips - 1);
                 if (need > k) break;
                 { const int st = light_and_mesh_group(next_group); if (st != GC_OK) return st; }
                 next_group++;
-                while (next_read < (next_group - 1) * group_strips) { const int st = read_back(next_read++); if (st != GC_OK) return st; }
             }
+            // strips that are meshed by now start their way back; this thread does not wait for any (it has uploads to queue)
+            while (next_read < gfirst[next_group] && cudaEventQuery(ctx->ev_meshed[next_read]) == cudaSuccess) { const int st = read_back(next_read++); if (st != GC_OK) return st; }
             continue;
         }
         if (k >= 1) { const int st = mesh_strip(k - 1); if (st != GC_OK) return st; }
-        if (k >= 2) { const int st = read_back(k - 2); if (st != GC_OK) return st; }
+        // strips that are meshed by now start their way back; this thread does not wait for any of them here — it has uploads to
+        // queue (waiting for strip k - 2 at this point ran upload, meshing and read-back in lock step)
+        while (next_read < k && cudaEventQuery(ctx->ev_meshed[next_read]) == cudaSuccess) { const int st = read_back(next_read++); if (st != GC_OK) return st; }
     }
     if (device_light)
         while (next_group < n_groups) { const int st = light_and_mesh_group(next_group++); if (st != GC_OK) return st; }
@@ -1937,13 +1961,7 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     GC_CUDA(cudaEventRecord(b->ev_stop, sm));
     GC_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(GcChunkOut) * (size_t)n, cudaMemcpyDeviceToHost, sm));
     GC_CUDA(cudaMemcpyAsync(b->h_cursor, b->d_cursor, 32, cudaMemcpyDeviceToHost, sm));
-    if (device_light)
-        while (next_read < n_strips) { const int st = read_back(next_read++); if (st != GC_OK) return st; }
-    else
-    {
-        if (n_strips >= 2) { const int st = read_back(n_strips - 2); if (st != GC_OK) return st; }
-        { const int st = read_back(n_strips - 1); if (st != GC_OK) return st; }
-    }
+    while (next_read < n_strips) { const int st = read_back(next_read++); if (st != GC_OK) return st; }
     GC_CUDA(cudaEventRecord(ctx->ev_join, sd));
     GC_CUDA(cudaStreamWaitEvent(sm, ctx->ev_join, 0));
     GC_CUDA(cudaEventRecord(b->ev_done, sm));

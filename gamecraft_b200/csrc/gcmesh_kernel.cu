@@ -897,7 +897,13 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
         __threadfence();
         if (atomicInc(p.done_counter, gridDim.x - 1) == gridDim.x - 1)
         {
-            *p.total_out = p.keep_cursor ? atomicAdd(p.quad_cursor, 0ull) : atomicExch(p.quad_cursor, 0ull);
+            const unsigned long long total = p.keep_cursor ? atomicAdd(p.quad_cursor, 0ull) : atomicExch(p.quad_cursor, 0ull);
+            *p.total_out = total;
+            if (p.total_out_host)   // (mapped host memory: the host reads it once the launch's event has fired — no copy engine involved)
+            {
+                *p.total_out_host = total;
+                __threadfence_system();
+            }
             atomicExch(p.work_counter, 0);
         }
     }

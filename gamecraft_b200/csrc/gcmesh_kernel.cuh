@@ -39,6 +39,7 @@ struct MeshParams
     int32_t* work_counter;             // dynamic chunk scheduler
     uint32_t* done_counter;            // CTAs that have left the work loop; the last one resets the scheduler for the next launch
     unsigned long long* total_out;     // ... and leaves the quad cursor's final value here
+    unsigned long long* total_out_host; // optional: and in mapped host memory (gcmesh_mesh_host: a copy on the stream would queue behind the read-backs)
     int32_t keep_cursor;               // 1: the cursor keeps running into the next launch (strips of one gcmesh_mesh_host call)
     const DeviceTables* tables;
     int32_t* error_flag;               // set by the mbarrier watchdog

@@ -9,12 +9,14 @@ pin = [torch.from_numpy(a).pin_memory() for a in (host.blocks, host.sun, host.li
 class P:
     size_x, size_z = 36, 36
     blocks, sun, light, surface = [t.numpy() for t in pin]
+if os.environ.get("NOLIGHT"):          # gcmesh_mesh_host(blocks, NULL, NULL, surface): the light is filled on the device
+    P.sun = None; P.light = None
 ctx = mesher.Context(0)
 world = mesher.World(ctx, 36, 36)
 if os.environ.get("HINT"):
-    world.set_option(mesher.WORLD_SURFACE_BOUNDS_BLOCKS, 1)
+    world.set_option(mesher.WORLD_SURFACE_BOUNDS_BLOCKS, 1).set_option(mesher.WORLD_SURFACE_BOUNDS_MESH, 1)
 batch = mesher.Batch(ctx, len(coords), 4_000_000)
-world.upload_sparse(P); ctx.synchronize(); batch.submit(world, coords).wait(); desc, q = batch.results()
+world.upload(host); ctx.synchronize(); batch.submit(world, coords).wait(); desc, q = batch.results()
 hv = torch.empty((q * 4, 12), dtype=torch.uint8).pin_memory().numpy(); hi = torch.empty(q * 6, dtype=torch.uint16).pin_memory().numpy()
 th = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 hint = None
