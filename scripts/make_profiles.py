@@ -28,8 +28,12 @@ r = rows[2]
 mul = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}
 def val(k): i = hdr.index(k); return float(r[i]) * mul.get(units[i], 1)
 traffic = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
-json.dump({"forest4096": traffic, "_source": "profiles/%s_final_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum of gc_mesh_kernel, one launch "
-           "(ncu --set full --clock-control none)" % tag}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+tj = os.path.join(P, "traffic.json")
+td = json.load(open(tj)) if os.path.exists(tj) else {}
+td["forest4096"] = traffic
+td["_source"] = ("profiles/%s_final_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum of gc_mesh_kernel, one launch "
+                 "(ncu --set full --clock-control none)" % tag)
+json.dump(td, open(tj, "w"), indent=1)
 for src, dst in (("launches_final.csv", "_final_launches.csv"), ("phase_forest.txt", "_phase_cycles_forest4096.txt"), ("phase_checker.txt", "_phase_cycles_checker4096.txt"),
                  ("BENCH_local.json", "_bench_forest4096.json"), ("BENCH_ref_local.json", "_bench_reference_arm.json"), ("bench_islands4096.json", "_bench_islands4096.json"),
                  ("bench_checker1024.json", "_bench_checker1024.json"), ("bench_noise1024.json", "_bench_noise1024.json"), ("pytest_gpu.txt", "_pytest_gpu.txt")):
