@@ -65,7 +65,25 @@ __global__ void __launch_bounds__(256) gc_validate_blocks_kernel(const uint4* __
         atomicMin(out + 1, first);
     }
 }
+
+// zero fill as a kernel: cudaMemsetAsync may be served by a copy engine, where it queues behind the transfers that keep the
+// engines busy during gcmesh_mesh_host
+__global__ void __launch_bounds__(256) gc_zero_kernel(uint4* __restrict__ p, size_t n_vec)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
 }  // namespace
+
+cudaError_t launch_zero(void* p, size_t bytes, int num_sms, cudaStream_t s)
+{
+    if (bytes == 0) return cudaSuccess;
+    if ((((uintptr_t)p | bytes) & 15u) != 0) return cudaMemsetAsync(p, 0, bytes, s);
+    const size_t n_vec = bytes / 16;
+    size_t grid = (n_vec + 255) / 256;
+    if (grid > (size_t)num_sms * 8) grid = (size_t)num_sms * 8;
+    gc_zero_kernel<<<(unsigned)grid, 256, 0, s>>>(reinterpret_cast<uint4*>(p), n_vec);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_validate_blocks(const uint16_t* blocks, size_t n_voxels, int n_types, unsigned long long* d_out, int num_sms, cudaStream_t s)
 {

@@ -20,6 +20,8 @@ struct FillJob
 };
 // one CTA per job
 cudaError_t launch_fill_device(const FillJob* jobs, int n, cudaStream_t s);
+// zero fill by a kernel (16-byte stores; falls back to cudaMemsetAsync for unaligned ranges)
+cudaError_t launch_zero(void* p, size_t bytes, int num_sms, cudaStream_t s);
 // block ids >= n_types: d_out[0] += their number, d_out[1] = min(d_out[1], voxel index of the first); the caller presets {0, ~0}
 cudaError_t launch_validate_blocks(const uint16_t* blocks, size_t n_voxels, int n_types, unsigned long long* d_out, int num_sms, cudaStream_t s);
 }  // namespace gc

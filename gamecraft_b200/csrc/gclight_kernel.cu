@@ -410,7 +410,7 @@ cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_bits, uint32_t*
 }
 
 cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, const uint8_t* sun_unit, uint8_t* sun_flags, uint8_t* light_flags,
-                             size_t flag_stride, uint32_t* lists, uint32_t* row_maps, uint32_t* counters, int num_sms, cudaStream_t s)
+                             size_t flag_stride, uint32_t* lists, uint32_t* row_maps, uint32_t* counters, int num_sms, int ctas_per_sm, cudaStream_t s)
 {
     // every CTA has to be resident (grid barriers): the occupancy query bounds the grid, the cooperative launch enforces it.
     // (a barrier costs more the more CTAs take part: two CTAs of four 256-thread teams per SM — 2048 threads — instead of eight CTAs)
@@ -427,7 +427,10 @@ cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, cons
     }
     LightWorld lw = w;
     void* args[] = { &lw, &sun_bits, &opq_bits, &sun_unit, &sun_flags, &light_flags, &flag_stride, &lists, &row_maps, &counters };
-    return cudaLaunchCooperativeKernel((const void*)gc_relax_all_kernel, dim3(num_sms * per_sm), dim3(256 * kRelaxTeams), args, kRelaxSmem, s);
+    // (a cooperative grid starts only when all of it fits: with every thread slot of every SM asked for, it waits for whatever
+    // else is running — the PCIe pull kernels of gcmesh_mesh_host, say; half of that leaves them room)
+    const int use = ctas_per_sm >= 1 && ctas_per_sm < per_sm ? ctas_per_sm : per_sm;
+    return cudaLaunchCooperativeKernel((const void*)gc_relax_all_kernel, dim3(num_sms * use), dim3(256 * kRelaxTeams), args, kRelaxSmem, s);
 }
 
 cudaError_t launch_relax_pair(const LightWorld& w, const uint32_t* sun_list, const uint32_t* light_list, uint32_t cap, const uint32_t* n_sun,

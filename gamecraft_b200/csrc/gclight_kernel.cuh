@@ -44,7 +44,7 @@ cudaError_t launch_light_scan(const LightWorld& w, uint32_t* sun_bits, uint32_t*
 // and fill one bit per row "changed" (map 1 cleared by the caller, the kernel clears the others as it goes); ends at the first
 // sweep that has nothing to visit
 cudaError_t launch_relax_all(const LightWorld& w, const uint32_t* sun_bits, const uint32_t* opq_bits, const uint8_t* sun_unit, uint8_t* sun_flags, uint8_t* light_flags,
-                             size_t flag_stride, uint32_t* lists, uint32_t* row_maps, uint32_t* counters, int num_sms, cudaStream_t s);
+                             size_t flag_stride, uint32_t* lists, uint32_t* row_maps, uint32_t* counters, int num_sms, int ctas_per_sm, cudaStream_t s);
 // the edit path's sweep over its two candidate lists (gcedit_kernel.cu): both fills in one launch; the lists' lengths are read
 // from device memory, `cap` is their capacity; changed_*: this sweep's flag word, the previous sweep's at changed_*[-1]
 cudaError_t launch_relax_pair(const LightWorld& w, const uint32_t* sun_list, const uint32_t* light_list, uint32_t cap, const uint32_t* n_sun,

@@ -996,7 +996,7 @@ static int light_scratch(GcWorld* w)
 // Enqueue the fill of `lw` — the window, or a range of its rows seen as a window of its own (rows are contiguous ranges of
 // slots) — on `s`.  lw.sun / lw.light must hold zeros.  Nothing below depends on a count the device produces: candidates
 // are bit maps of fixed size (a word per x-row of a brick), the active set is a byte per brick and sweep — a fixed sequence.
-static int enqueue_light_fill(GcWorld* w, const LightWorld& lw, cudaStream_t s)
+static int enqueue_light_fill(GcWorld* w, const LightWorld& lw, cudaStream_t s, int ctas_per_sm = 0)
 {
     if (light_scratch(w) != GC_OK) return GC_ERR_CUDA;
     const size_t n_slots = (size_t)lw.size_x * lw.size_z * GC_WORLD_CHUNK_HEIGHT;
@@ -1010,19 +1010,20 @@ static int enqueue_light_fill(GcWorld* w, const LightWorld& lw, cudaStream_t s)
     uint8_t* sun_flags = w->d_brick_flags;
     uint8_t* light_flags = w->d_brick_flags + (size_t)(kLightSweeps + 1) * flag_stride;
     uint8_t* sun_unit = w->d_brick_flags + 2 * (size_t)(kLightSweeps + 1) * flag_stride;
-    GC_CUDA(cudaMemsetAsync(c, 0, kLightCounterWords * sizeof(uint32_t), s));
-    GC_CUDA(cudaMemsetAsync(w->d_light_bits, 0, 2 * bits_bytes, s));
-    GC_CUDA(cudaMemsetAsync(w->d_brick_flags, 0, flags_bytes, s));
+    const int sms = w->ctx->num_sms;
+    GC_CUDA(launch_zero(c, kLightCounterWords * sizeof(uint32_t), sms, s));
+    GC_CUDA(launch_zero(w->d_light_bits, 2 * bits_bytes, sms, s));
+    GC_CUDA(launch_zero(w->d_brick_flags, flags_bytes, sms, s));
     // 1. one pass over the column cells up to maxY: candidate bit maps, emitters seeded, the first sweep's active bricks
     GC_CUDA(launch_light_scan(lw, sun_bits, opq_bits, sun_flags, sun_unit, light_flags, c, s));
     uint32_t* visit_lists = w->d_light_bits + 2 * n_slots * 2048;
     uint32_t* row_maps = visit_lists + 32 * n_slots;
-    GC_CUDA(cudaMemsetAsync(row_maps + 128 * n_slots, 0, 128 * n_slots * sizeof(uint32_t), s));   // the map the first sweep writes (the kernel clears the others)
+    GC_CUDA(launch_zero(row_maps + 128 * n_slots, 128 * n_slots * sizeof(uint32_t), sms, s));   // the map the first sweep writes (the kernel clears the others)
     // 2. relaxation: a value falls by at least one per hop and nothing at or below MIN_LIGHT is stored, so 14 in-place sweeps
     // reach the fixpoint; one persistent kernel runs them with grid barriers in between, visits per sweep only the bricks
     // that changed in the sweep before (or whose face neighbours did) — in units of 256 rows whose candidates a CTA spreads over
     // its threads one cell each — and ends with the first sweep that finds none
-    GC_CUDA(launch_relax_all(lw, sun_bits, opq_bits, sun_unit, sun_flags, light_flags, flag_stride, visit_lists, row_maps, c, w->ctx->num_sms, s));
+    GC_CUDA(launch_relax_all(lw, sun_bits, opq_bits, sun_unit, sun_flags, light_flags, flag_stride, visit_lists, row_maps, c, w->ctx->num_sms, ctas_per_sm, s));
     return GC_OK;
 }
 
@@ -1794,10 +1795,12 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     unsigned long long* cursors_dev = nullptr;
     GC_CUDA(cudaHostGetDevicePointer((void**)&cursors_dev, cursors, 0));
     uint64_t copied = 0;
+    std::vector<char> no_cursor((size_t)n_strips, 0);
+    for (int j = 0; j < n_strips; j++) no_cursor[j] = first[j + 1] == first[j];
     auto read_back = [&](int j) -> int                        // strip j has been meshed: copy its arena range to the host buffers
     {
         GC_CUDA(cudaEventSynchronize(ctx->ev_meshed[j]));
-        if (first[j + 1] == first[j]) return GC_OK;           // (a strip without chunks — the window's edge rows — launched nothing)
+        if (no_cursor[j]) return GC_OK;                       // (a strip without chunks — the window's edge rows — launched nothing; a strip meshed by its group's one launch has no cursor of its own)
         uint64_t end = cursors[j] < b->max_quads ? cursors[j] : b->max_quads;
         if (end > host_capacity_quads) end = host_capacity_quads;
         if (end > copied)
@@ -1832,12 +1835,13 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
     // is the longest leg of the call
     std::vector<int> gfirst;                                     // group g = strips [gfirst[g], gfirst[g + 1])
     if (device_light)
-        for (int s0 = 0, len = 1; s0 < n_strips; s0 += len)
+        for (int s0 = 0, len = 1; s0 < n_strips;)
         {
             gfirst.push_back(s0);
+            s0 += len;
             // ... and so are the last ones (two strips, then one): what follows the last upload — fill, meshing, read-back of the
             // last group — is not overlapped by anything
-            const int left = n_strips - (s0 + len);
+            const int left = n_strips - s0;
             len = std::min(len + 1, group_strips);
             if (left <= 3) len = left == 3 ? 2 : 1;
             else if (left - len < 3 && left - len > 0) len = left - 3;
@@ -1870,19 +1874,22 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         const size_t slot0 = (size_t)r0 * w->size_x * GC_WORLD_CHUNK_HEIGHT, n_sub = (size_t)(r1 - r0) * w->size_x * GC_WORLD_CHUNK_HEIGHT;
         if (any)
         {
-            GC_CUDA(cudaMemsetAsync(w->d_group_sun, 0, n_sub * GC_CHUNK_SIZE_3, sm));
-            GC_CUDA(cudaMemsetAsync(w->d_group_light, 0, n_sub * GC_CHUNK_SIZE_3, sm));
+            GC_CUDA(launch_zero(w->d_group_sun, n_sub * GC_CHUNK_SIZE_3, ctx->num_sms, sm));
+            GC_CUDA(launch_zero(w->d_group_light, n_sub * GC_CHUNK_SIZE_3, ctx->num_sms, sm));
             LightWorld lw = light_world(w);
             lw.blocks = w->d_blocks + slot0 * GC_CHUNK_SIZE_3; lw.surface = w->d_surface + (slot0 / GC_WORLD_CHUNK_HEIGHT) * GC_CHUNK_SIZE_2;
             lw.sun = w->d_group_sun; lw.light = w->d_group_light; lw.size_z = r1 - r0;
-            if (enqueue_light_fill(w, lw, sm) != GC_OK) return GC_ERR_CUDA;
+            if (enqueue_light_fill(w, lw, sm, 1) != GC_OK) return GC_ERR_CUDA;   // (one CTA per SM: uploads' pull kernels run beside it)
             b->launches += 2;
         }
+        // one launch for the group's chunks (a strip of 288 chunks leaves each of the 296 persistent CTAs one chunk: as long as a
+        // launch of three strips); its cursor is filed under the group's last strip
+        if (any)
+            GC_CUDA(launch_range(w, b, first[s0], first[s1] - first[s0], sm, !(last_nonempty >= s0 && last_nonempty < s1), nullptr, nullptr,
+                                 w->d_group_sun - slot0 * GC_CHUNK_SIZE_3, w->d_group_light - slot0 * GC_CHUNK_SIZE_3, cursors_dev + (s1 - 1)));
         for (int j = s0; j < s1; j++)
         {
-            if (first[j + 1] > first[j])
-                GC_CUDA(launch_range(w, b, first[j], first[j + 1] - first[j], sm, j != last_nonempty, nullptr, nullptr,
-                                     w->d_group_sun - slot0 * GC_CHUNK_SIZE_3, w->d_group_light - slot0 * GC_CHUNK_SIZE_3, cursors_dev + j));
+            no_cursor[j] = j != s1 - 1 || !any;
             GC_CUDA(cudaEventRecord(ctx->ev_meshed[j], sm));
         }
         return GC_OK;
