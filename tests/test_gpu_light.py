@@ -119,3 +119,29 @@ def test_non_square_window(ctx):
     for (cx, cy, cz), m in zip(coords, batch.meshes()):
         util.assert_same_mesh(m, o.build_chunk(cx, cy, cz), "%s" % ((cx, cy, cz),))
     batch.close(); world.close()
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref/libgcref.so not built (no reference tree)")
+@pytest.mark.parametrize("kind,seed,kw", [("forest", 4, {}), ("islands", 9, dict(radius=90, falloff=50)), ("mixed", 3, dict(radius=90, falloff=50))])
+def test_device_fill_against_the_reference_s_own_fill(ctx, kind, seed, kw):
+    """The documented f1 divergence, bounded on the GPU path itself: the device fill next to ComputeSurface + SetLightNodes of the
+    reference compiled verbatim (columns in z-major order).  Surface and sunlight are identical on every world; block light is
+    identical where all emitters shine alike (forest, islands: none) and, where weak and strong emitters mix, never below the
+    reference's — the reference re-assigns a seeded emitter's own value below light it had already received (Lighting.cpp:240),
+    the fixpoint keeps the brighter value."""
+    size = 5
+    w = util.HostWorld(size, size, origin=(-(size // 2), -(size // 2)) if kw else (0, 0)).generate(kind, seed, **kw)
+    got, _ = device_fill(ctx, w)
+    z = util.HostWorld(size, size)
+    z.blocks[:] = w.blocks
+    r = ob.RefWorld(z)
+    r.compute_surface(); r.compute_light()
+    r.download(z)
+    r.close()
+    assert np.array_equal(got.surface, z.surface)
+    assert np.array_equal(got.sun, z.sun), "sunlight: %d cells differ from the reference" % int((got.sun != z.sun).sum())
+    if kind == "mixed":
+        assert not (got.light < z.light).any()
+        assert int((got.light != z.light).sum()) < got.light.size // 1000
+    else:
+        assert np.array_equal(got.light, z.light)
