@@ -75,6 +75,7 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the byte comparison of every chunk of the timed output with the oracle")
     ap.add_argument("--no-surface-hint", action="store_true", help="e2e: scan every block brick (GC_WORLD_SURFACE_BOUNDS_BLOCKS off)")
     ap.add_argument("--no-surface-bounded", action="store_true", help="skip the GC_WORLD_SURFACE_BOUNDS_MESH leg")
+    ap.add_argument("--no-config5-leg", action="store_true", help="N = 1 default run: skip the forest65536 (BASELINE config 5) single-GPU leg")
     ap.add_argument("--no-weak-leg", action="store_true", help="N > 1 default run: skip the weak-scaling (forest4096 per rank) second leg")
     ap.add_argument("--no-preprocess", action="store_true", help="skip the surface + light-fill leg (SURVEY 8(f1))")
     ap.add_argument("--no-stress", action="store_true", help="skip the uncapped 196 608-quads-per-chunk leg (BASELINE config 4, stress variant)")
@@ -1090,6 +1091,11 @@ def main():
         weak = measure(args, "forest4096", torch, dist, world_size, rank, local_rank, full_legs=False)
         if rank == 0:
             line["weak_scaling_leg"] = {k: weak[k] for k in ("value", "unit", "ms_per_step", "scaling", "config", "quads_per_s", "parity", "roofline", "gpu_launches", "between_kernels_us")}
+    if world_size == 1 and not args.workload and not args.no_config5_leg:
+        # the N = 1 point of the strong-scaling curve the N > 1 runs report: BASELINE config 5 on one GPU (17 GB resident)
+        c5 = measure(args, "forest65536", torch, dist, world_size, rank, local_rank, full_legs=False)
+        line["config5_single_gpu_leg"] = {k: c5[k] for k in ("value", "unit", "ms_per_step", "scaling", "config", "quads_per_s", "parity", "roofline", "gpu_launches",
+                                                               "between_kernels_us", "surface_bounded") if k in c5}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world_size > 1:
