@@ -750,6 +750,20 @@ def test_gpu_mesh_host_without_light_arrays(ctx, kind, size, seed, kw):
             assert world.upload_bytes() < w.blocks.nbytes // 2                  # and not the air above the terrain
     with pytest.raises(mesher.GcMeshError):
         world.set_blocks([(40, 70, 40, 3)])                                     # the window's own light arenas do not hold the fill
+    if kind == "forest":
+        # pageable host arrays (plain numpy) and a caller's hint instead of the scan: the same meshes
+        class Q:
+            size_x, size_z = size, size
+            blocks, surface = w.blocks, w.surface
+            sun = None
+            light = None
+
+        hint = (w.blocks.any(axis=1) * 1).astype(np.uint8)
+        pv, pi = np.zeros_like(hv), np.zeros_like(hi)
+        for nz in (None, hint):
+            batch.mesh_host(world, Q, coords, pv, pi, nonzero_hint=nz)
+            desc, q = batch.results()
+            assert o.check_batch(coords, desc.copy(), pv, pi)[0] == 0
     P.sun = w.sun
     with pytest.raises(mesher.GcMeshError):
         batch.mesh_host(world, P, coords, hv, hi)                               # one light array without the other
