@@ -92,6 +92,7 @@ struct ChunkCtx
     uint8_t slab_cls[kSlabs + 2];   // per z-slab: 0xFF = its plane rows are written; else the class byte of the one non-emitting block
                                     // (air, as a rule) that fills it — such rows are only written if the chunk turns out to need them
     int32_t halo_ok;      // fused exchange: result of a wait for a neighbour, broadcast to the CTA
+    uint32_t halo_seen, halo_failed;   // fused exchange, bit d: the plane from neighbour d is known to have arrived / was given up on
     uint32_t batch_base[kMeshTypes];   // uncapped mode: first quad of each mesh type in the current P3 batch (the list holds ranks relative to it)
 };
 static_assert(sizeof(ChunkCtx) <= 128, "ChunkCtx outgrew its slot");
@@ -359,40 +360,48 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     // of its halo rows, has finished (stream order), so they may be overwritten
     if (kHalo && blockIdx.x == 0 && tid < 2 && p.halo.peer[tid].connected && !(p.halo.debug & 4))
         halo_store_release_sys(p.halo.peer[tid].flags + (tid == 0 ? HF_READY_FROM_UP : HF_READY_FROM_DOWN), p.halo.serial);
-    uint32_t halo_seen = 0, halo_failed = 0;   // bit d: the plane from neighbour d is known to have arrived / was given up on (CTA-uniform)
+    if (kHalo && tid == 0) { s_ctx->halo_seen = 0; s_ctx->halo_failed = 0; }   // (kept in shared memory: two registers less in the chunk loop)
 
     int buf = 0;
     if (warp == kFetchWarp) fetch_chunk(0);
     if (tid == 0) { s_ctx->any_emit = 0; s_ctx->any_bv = 0; }
     if (tid < 2 * kBvWords) s_bvm[tid] = 0;
 
+    if (kHalo)
+    {
+        // ---- halo push tasks: a share of this rank's boundary planes goes into a neighbour's halo row over peer memory ----
+        // They are the first items of the work counter, so a CTA's claims run through them before its first chunk: they are
+        // worked off here, ahead of the chunk loop (whose registers they then do not compete for).
+        for (;;)
+        {
+            __syncthreads();
+            if (s_next[0].chunk != kPushItem) break;
+            const int task = s_next[0].cx;
+            __syncthreads();                                      // (everyone has read the item: the fetch warp may claim the next one)
+            if (warp == kFetchWarp) fetch_chunk(0);
+            halo_push_task(p.halo, task, &s_ctx->halo_ok);
+        }
+    }
     for (;; buf ^= 1)
     {
         // ================= P0: the chunk prefetched during the previous chunk's P1 =================
         __syncthreads();
         const int chunk = s_next[buf].chunk;
         if (chunk == -1) break;
-        if (kHalo && chunk == kPushItem)
-        {
-            // ---- a halo push task: a share of this rank's boundary planes goes into a neighbour's halo row over peer memory ----
-            if (warp == kFetchWarp) fetch_chunk(buf ^ 1);
-            halo_push_task(p.halo, s_next[buf].cx, &s_ctx->halo_ok);
-            continue;
-        }
         const int cx = s_next[buf].cx, cy = s_next[buf].cy, cz = s_next[buf].cz;
         const int lwy = cy * kTY;
         if (kHalo)
         {
             // a chunk of the first / last owned row reads the neighbour's plane: wait (once per CTA and side) until it has arrived
             uint32_t need = ((cz == p.halo.send_row[0] && p.halo.peer[0].connected) ? 1u : 0u) | ((cz == p.halo.send_row[1] && p.halo.peer[1].connected) ? 2u : 0u);
-            need &= ~halo_seen;
+            need &= ~s_ctx->halo_seen;                      // (tid 0 updates it only behind the barrier below: every thread has read it by then)
             if (p.halo.debug & 2) need = 0;
             if (need)
             {
                 int* s_halo_ok = &s_ctx->halo_ok;
                 if (tid == 0)
                 {
-                    bool ok = (need & halo_failed) == 0;   // (a plane this CTA already gave up on is not waited for again)
+                    bool ok = (need & s_ctx->halo_failed) == 0;   // (a plane this CTA already gave up on is not waited for again)
                     if (ok && (need & 1u)) ok = halo_wait_at_least(p.halo.flags, HF_ARRIVED_FROM_DOWN, p.halo.serial, p.halo.wait_ns) && ok;
                     if (ok && (need & 2u)) ok = halo_wait_at_least(p.halo.flags, HF_ARRIVED_FROM_UP, p.halo.serial, p.halo.wait_ns);
                     // the planes were written by another GPU (generic proxy); this CTA reads them through TMA as well
@@ -401,11 +410,11 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                 }
                 __syncthreads();
                 const bool ok = *s_halo_ok != 0;
+                if (tid == 0) { if (ok) s_ctx->halo_seen |= need; else s_ctx->halo_failed |= need; }
                 __syncthreads();
                 if (!ok)
                 {
                     // the neighbour never delivered: the chunk is flagged, nothing is emitted
-                    halo_failed |= need;
                     if (warp == kFetchWarp) fetch_chunk(buf ^ 1);
                     if (tid == 0)
                     {
@@ -417,7 +426,6 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
                     }
                     continue;
                 }
-                halo_seen |= need;
             }
         }
 
