@@ -277,7 +277,10 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     ChunkCtx* s_ctx = reinterpret_cast<ChunkCtx*>(smem + kOffCtx);
     uint32_t* s_typ32 = reinterpret_cast<uint32_t*>(smem + kOffTyp32);
 
-    // ---- one-time setup ----
+    // Programmatic dependent launch: the next launch on the stream may start its CTAs as soon as SM slots come free (this grid is
+    // wholly resident from the start, so nothing of it waits for a slot) ...
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // ---- one-time setup (block tables never change while a launch is in flight: gcmesh_set_block_table synchronises) ----
     for (int i = tid; i < 256; i += NT)
     {
         s_lut[i] = p.tables->lut[i];
@@ -298,6 +301,9 @@ gc_mesh_kernel(const MeshParams p, const __grid_constant__ MeshTensorMaps maps)
     const int kill_cls = p.tables->cls8[p.tables->kill_zone & 255];
     const int air_cls = p.tables->cls8[0];
     __syncthreads();
+    // ... and the set-up above ran beside the previous launch's tail: from here on that launch is complete and its writes — the
+    // control block its last CTA reset, meshes, whatever earlier work on the stream left in the window — are visible
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     uint32_t warp_seq = 0;  // slabs this warp has staged so far (mbarrier parity source)
     long long prof_t = clock64();
@@ -1024,11 +1030,19 @@ cudaError_t launch_mesh(const MeshParams& p, const MeshTensorMaps& maps, int gri
     cudaError_t e0 = configure_mesh_kernel();
     if (e0 != cudaSuccess) return e0;
     static const bool force_halo = getenv("GCMESH_FORCE_HALO_KERNEL") != nullptr;
-    if (p.wide) gc_mesh_kernel<false, false, true><<<grid, NT, kSmemBytes, stream>>>(p, maps);                        // (uncapped form: no exchange, no profiling)
-    else if (p.halo.enabled || force_halo) gc_mesh_kernel<false, true, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);   // (no profiling instantiation of the exchange form)
-    else if (p.prof) gc_mesh_kernel<true, false, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
-    else gc_mesh_kernel<false, false, false><<<grid, NT, kSmemBytes, stream>>>(p, maps);
-    return cudaGetLastError();
+    // launched with programmatic stream serialisation: back-to-back submissions overlap a launch's set-up with its predecessor's
+    // tail (GCMESH_NO_PDL=1: plain stream order)
+    static const bool no_pdl = getenv("GCMESH_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    if (p.wide) return cudaLaunchKernelEx(&cfg, gc_mesh_kernel<false, false, true>, p, maps);                        // (uncapped form: no exchange, no profiling)
+    if (p.halo.enabled || force_halo) return cudaLaunchKernelEx(&cfg, gc_mesh_kernel<false, true, false>, p, maps);   // (no profiling instantiation of the exchange form)
+    if (p.prof) return cudaLaunchKernelEx(&cfg, gc_mesh_kernel<true, false, false>, p, maps);
+    return cudaLaunchKernelEx(&cfg, gc_mesh_kernel<false, false, false>, p, maps);
 }
 
 cudaError_t mesh_kernel_attributes(int* regs, int* static_smem, int* max_dyn_smem)
