@@ -2007,6 +2007,20 @@ int gcmesh_wait(GcBatch* b)
     return GC_OK;
 }
 
+int gcmesh_query(GcBatch* b, int* done)
+{
+    if (!b || !done) return fail(GC_ERR_ARG, "null argument");
+    *done = 0;
+    if (b->state == 0) return fail(GC_ERR_STATE, "nothing submitted");
+    if (b->state == 2) { *done = 1; return GC_OK; }
+    GC_CUDA(cudaSetDevice(b->ctx->device));
+    const cudaError_t e = cudaEventQuery(b->ev_done);
+    if (e == cudaErrorNotReady) { cudaGetLastError(); return GC_OK; }
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "cudaEventQuery", cudaGetErrorString(e));
+    *done = 1;
+    return gcmesh_wait(b);          // (finished: the same bookkeeping and error checks as a wait that does not block)
+}
+
 int gcmesh_batch_results(GcBatch* b, const GcChunkOut** out, int* n, uint64_t* total_quads)
 {
     if (!b) return fail(GC_ERR_ARG, "batch is null");

@@ -88,7 +88,7 @@ EXPORTS = [
     "gcmesh_version", "gcmesh_last_error", "gcmesh_create", "gcmesh_destroy", "gcmesh_set_stream",
     "gcmesh_set_block_table", "gcmesh_default_block_table", "gcmesh_synchronize",
     "gcmesh_world_create", "gcmesh_world_destroy", "gcmesh_world_upload_chunk", "gcmesh_world_upload_surface",
-    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_set_option", "gcmesh_world_set_origin", "gcmesh_world_validate_blocks", "gcmesh_world_upload_launches", "gcmesh_world_upload_bytes", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
+    "gcmesh_world_upload_all", "gcmesh_world_upload_rows", "gcmesh_world_upload_sparse", "gcmesh_world_set_option", "gcmesh_world_set_origin", "gcmesh_world_validate_blocks", "gcmesh_query", "gcmesh_world_upload_launches", "gcmesh_world_upload_bytes", "gcmesh_world_device_ptrs", "gcmesh_world_halo_bytes",
     "gcmesh_world_pack_halo", "gcmesh_world_unpack_halo",
     "gcmesh_world_halo_export", "gcmesh_world_halo_connect_ipc", "gcmesh_world_halo_connect_local", "gcmesh_world_halo_push", "gcmesh_world_halo_status",
     "gcmesh_default_light_rules", "gcmesh_set_light_rules", "gcmesh_world_compute_surface", "gcmesh_world_light",
@@ -131,6 +131,7 @@ def lib() -> ctypes.CDLL:
         L.gcmesh_world_upload_sparse.argtypes = [vp, vp, vp, vp, vp, vp, ci]
         L.gcmesh_world_set_option.argtypes = [vp, ci, ci]
         L.gcmesh_world_set_origin.argtypes = [vp, ci, ci]
+        L.gcmesh_query.argtypes = [vp, ctypes.POINTER(ci)]
         L.gcmesh_world_validate_blocks.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), vp, ctypes.POINTER(ci)]
         L.gcmesh_world_upload_launches.argtypes = [vp]
         L.gcmesh_world_upload_bytes.argtypes = [vp]
@@ -486,6 +487,12 @@ class Batch:
     def wait(self) -> "Batch":
         _check(lib().gcmesh_wait(self.h), "gcmesh_wait")
         return self
+
+    def done(self) -> bool:
+        """gcmesh_query: has the last submission finished?  (Does not block.)"""
+        d = ctypes.c_int(0)
+        _check(lib().gcmesh_query(self.h, ctypes.byref(d)), "gcmesh_query")
+        return bool(d.value)
 
     def results(self):
         """(descriptors as a structured numpy array view, total_quads)."""

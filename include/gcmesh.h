@@ -326,6 +326,9 @@ int gcmesh_submit(GcWorld* world, GcBatch* batch, const GcChunkCoord* coords, in
  * (GCMESH_HALO_WAIT_MS) flags the chunks that needed it GC_CHUNK_HALO_MISSING and makes gcmesh_wait fail. */
 int gcmesh_submit_exchange(GcWorld* world, GcBatch* batch, const GcChunkCoord* coords, int n, int send_row_down, int send_row_up);
 int gcmesh_wait(GcBatch* batch);
+/* The same without blocking: *done = 1 once the submission has finished (results may then be read as after gcmesh_wait), else 0.
+ * What the reference's main thread does when it polls its job callbacks once per frame (Async.cpp:48-60). */
+int gcmesh_query(GcBatch* batch, int* done);
 /* After gcmesh_wait: per-chunk descriptors (host memory owned by the batch, n entries, submit order). */
 int gcmesh_batch_results(GcBatch* batch, const GcChunkOut** out, int* n, uint64_t* total_quads);
 /* After gcmesh_wait: copy the used arena prefix to host memory (total_quads*48 and total_quads*12 bytes). */

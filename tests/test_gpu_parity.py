@@ -768,3 +768,27 @@ def test_gpu_mesh_host_without_light_arrays(ctx, kind, size, seed, kw):
     with pytest.raises(mesher.GcMeshError):
         batch.mesh_host(world, P, coords, hv, hi)                               # one light array without the other
     batch.close(); world.close()
+
+
+def test_gpu_query_polls_a_submission(ctx):
+    """gcmesh_query: the non-blocking form of gcmesh_wait — refuses a batch nothing was submitted to, turns true once the
+    submission has finished, and the results are then readable without a wait."""
+    import time
+
+    from gamecraft_b200 import mesher
+
+    w = util.HostWorld(6, 6).build("forest", 9)
+    world = mesher.World(ctx, 6, 6).upload(w)
+    coords = w.interior_chunks(1)
+    batch = mesher.Batch(ctx, len(coords), len(coords) * 3000)
+    with pytest.raises(mesher.GcMeshError):
+        batch.done()
+    batch.submit(world, coords)
+    t0 = time.time()
+    while not batch.done():
+        assert time.time() - t0 < 10
+    desc, q = batch.results()                                                  # no gcmesh_wait in between
+    o = ob.OracleWorld(w)
+    assert q == sum(o.build_chunk(*c).quads for c in coords)
+    assert batch.done()
+    batch.close(); world.close()
