@@ -1915,6 +1915,9 @@ int gcmesh_mesh_host(GcWorld* w, GcBatch* b, const uint16_t* blocks, const uint8
         // one core stays with this thread, which feeds the three streams as strips become ready
         int nt = scan_threads(threads);
         if (threads <= 0 && nt > 1) nt--;
+        // no light arrays and block bricks bounded by the surface maps: the scan reads a few kilobytes per column, and starting
+        // fifteen threads (this thread does, one after the other) would take longer than the scan itself
+        if (device_light && w->surface_bounds_blocks && nt > 4) nt = 4;
         auto work = [&, slots_per_row, kStripRows]()
         {
             plan.work([&](size_t slot)
