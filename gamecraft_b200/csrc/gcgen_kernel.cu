@@ -298,15 +298,20 @@ __global__ void __launch_bounds__(256) gc_gen_layers_kernel(GenArgs a)
     const int h = hraw & (kIceBit - 1);
     const bool ice = (hraw & kIceBit) != 0;
     const int top = a.max_y[col];
-    const int wx = (a.origin_cx + cx) * 32 + x, wz = (a.origin_cz + cz) * 32 + z;
-    const float fx = mul(mul((float)wx, 0.015f), 0.2f), fz = mul(mul((float)wz, 0.015f), 0.2f);
+    const int wz = (a.origin_cz + cz) * 32 + z;
+    const float fz = mul(mul((float)wz, 0.015f), 0.2f);
     for (int wy = 0; wy <= top; wy++)
     {
         int b = B_AIR;
         bool stone = false;
         if (a.biome != T_DESERT && wy <= h - 4)
         {
-            const float comp = mul(add(fbm3(a.seed + 404u, fx, mul(mul((float)wy, 0.015f), 0.2f), fz, 2), 1.0f), 0.5f);
+            // what the reference's code does, not what it means: its 3-D noise set has maxY + 1 layers per x and is read with a
+            // stride of maxY (Generation.cpp:16-18 against :157-161), so cell (x, wY) gets the sample of (x', y') with
+            // x' * (maxY + 1) + y' = x * maxY + wY
+            const int q = x * top + wy, sx = q / (top + 1), sy = q % (top + 1);
+            const float fx = mul(mul((float)((a.origin_cx + cx) * 32 + sx), 0.015f), 0.2f);
+            const float comp = mul(add(fbm3(a.seed + 404u, fx, mul(mul((float)sy, 0.015f), 0.2f), fz, 2), 1.0f), 0.5f);
             stone = comp <= 0.2f;
         }
         if (stone) b = B_STONE;

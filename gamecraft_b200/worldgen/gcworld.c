@@ -239,6 +239,26 @@ static float fbm3(uint32_t seed, float x, float y, float z, int octaves)
     return sum * fractal_bounding(octaves);
 }
 
+/* The per-column random stream of the tree / cactus placement, for the same test infrastructure: a column's start state and the
+ * next draw (rng_range(lo, hi) = lo + draw % (hi + 1 - lo), RandRange's formula). */
+uint64_t gcw_column_rng(uint32_t seed, int32_t wcx, int32_t wcz) { return ((uint64_t)hash3(seed, wcx, wcz, 77) << 32) | hash3(seed, wcz, wcx, 78); }
+uint32_t gcw_rng_next(uint64_t* state) { Rng r = { *state }; const uint32_t v = rng_next(&r); *state = r.s; return v; }
+
+/* The noise fields by number, for test infrastructure that runs the reference's own generator code over them
+ * (oracle/ref: its FastNoiseSIMD stand-in calls back into this): 0 simplex (x, y), 1 billow (x, y), 2 ridged (x, y),
+ * 3 fBm (x, y), 4 fBm (x, y, z). */
+float gcw_noise(uint32_t seed, int fn, int octaves, float x, float y, float z)
+{
+    switch (fn)
+    {
+        case 0: return simplex2(seed, x, y);
+        case 1: return billow2(seed, x, y, octaves);
+        case 2: return ridged2(seed, x, y, octaves);
+        case 3: return fbm2(seed, x, y, octaves);
+        default: return fbm3(seed, x, y, z, octaves);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* column helpers                                                                               */
 /* ------------------------------------------------------------------------------------------ */
@@ -364,14 +384,19 @@ static void gen_terrain_column(GcwWorld* w, int cx, int cz, uint32_t seed, int b
         for (int x = 0; x < CH; x++)
         {
             int h = height[z * CH + x];
-            int wx = wcx * CH + x, wz = wcz * CH + z;
+            int wz = wcz * CH + z;
             for (int wy = 0; wy <= max_y; wy++)
             {
                 int b = B_AIR;
                 int stone = 0;
                 if (biome_kind != T_DESERT && wy <= h - 4)
                 {
-                    float comp = (fbm3(seed + 404u, (float)wx * 0.015f * 0.2f, (float)wy * 0.015f * 0.2f, (float)wz * 0.015f * 0.2f, 2) + 1.0f) * 0.5f;
+                    /* What the reference's code does, not what it means: the 3-D noise set has maxY + 1 layers per x
+                     * (GetNoise3D(noise, x, z, maxY + 1), Generation.cpp:157-161) and is read with a stride of maxY
+                     * (GetNoiseValue3D(comp, x, wY, z, maxY), :16-18, :179), so cell (x, wY) gets the sample of
+                     * (x', y') with x' * (maxY + 1) + y' = x * maxY + wY. */
+                    const int q = x * max_y + wy, sx = q / (max_y + 1), sy = q % (max_y + 1);
+                    float comp = (fbm3(seed + 404u, (float)(wcx * CH + sx) * 0.015f * 0.2f, (float)sy * 0.015f * 0.2f, (float)wz * 0.015f * 0.2f, 2) + 1.0f) * 0.5f;
                     stone = comp <= 0.2f;
                 }
                 if (stone) b = B_STONE;

@@ -252,10 +252,11 @@ int gcmesh_world_encode_rle(GcWorld* world, const GcChunkCoord* coords, int n, u
  * IsWithinIsland :66-81 — fill the block ids of every column
  * of the window and its surface map (as ComputeSurface would, Lighting.cpp:5-26); sunlight and blockLight are cleared
  * (follow with gcmesh_world_light) and every chunk counts as never built (gcmesh_world_set_blocks refuses it until it is meshed).  origin = world-space column of window column (0, 0); radius / falloff = WorldProperties::radius
- * and World::falloffRadius in blocks (an unbounded world: INT_MAX and INT_MAX - 64).  For the five noise terrains the layering,
- * tree / cactus and fall-off rules are the reference's; its noise (FastNoiseSIMD, not vendored) and its thread-timing dependent rand() are replaced by a seeded
- * simplex noise and a per-column PRNG — the same ones as the host input producer gamecraft_b200/worldgen, whose worlds
- * this call reproduces block for block.  Asynchronous on the context stream. */
+ * and World::falloffRadius in blocks (an unbounded world: INT_MAX and INT_MAX - 64).  For the five noise terrains everything the reference's
+ * code does is reproduced (its own Generation.cpp, run over this project's noise, gives the same blocks — tested); its noise
+ * library (FastNoiseSIMD, not vendored) and its thread-timing dependent rand() are replaced by a seeded simplex noise and a
+ * per-column PRNG — the same ones as the host input producer gamecraft_b200/worldgen, whose worlds this call reproduces block
+ * for block.  Asynchronous on the context stream. */
 enum { GC_GEN_FLAT = 0, GC_GEN_FOREST = 1, GC_GEN_ISLANDS = 2, GC_GEN_GRID = 3, GC_GEN_VOID = 4,
        GC_GEN_SNOW = 5, GC_GEN_DESERT = 6, GC_GEN_VOLCANIC = 7, GC_GEN_DUNGEON = 8 };
 int gcmesh_world_generate(GcWorld* world, int kind, uint32_t seed, int origin_cx, int origin_cz, int radius, int falloff);

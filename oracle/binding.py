@@ -125,6 +125,9 @@ def ref_lib() -> ctypes.CDLL:
         L.gcref_rle_save_group.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.gcref_rle_load_group.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.gcref_world_set_origin.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.gcref_set_noise.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.gcref_set_seed.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.gcref_generate_noise_terrain.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.gcref_rle_store_record.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.gcref_rle_clear_region.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.gcref_set_chunk.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
@@ -322,6 +325,23 @@ class RefWorld:
     def generate(self, kind):
         """The reference's own noise-free generators over every column: "flat", "grid", "void" or "dungeon"."""
         assert self.L.gcref_generate(self.h, {"flat": 0, "grid": 3, "void": 4, "dungeon": 8}[kind]) == 0
+
+    def generate_noise_terrain(self, kind, seed, own_random=True):
+        """The reference's own GenerateForest / Islands / Snow / Desert / VolcanicTerrain over this project's noise fields
+        (gamecraft_b200/worldgen's gcw_noise plugged into the FastNoiseSIMD stand-in).  Trees and cacti come from rand(): the
+        producer's per-column stream with ``own_random``, else the C library's."""
+        from gamecraft_b200 import worldgen
+
+        wl = worldgen.lib()
+        fn = ctypes.cast(wl.gcw_noise, ctypes.c_void_p)
+        crng, nxt = (ctypes.cast(wl.gcw_column_rng, ctypes.c_void_p), ctypes.cast(wl.gcw_rng_next, ctypes.c_void_p)) if own_random else (None, None)
+        self.L.gcref_set_noise(fn, crng, nxt)
+        try:
+            self.L.gcref_set_seed(self.h, int(seed))
+            rc = self.L.gcref_generate_noise_terrain(self.h, {"forest": 1, "islands": 2, "snow": 5, "desert": 6, "volcanic": 7}[kind])
+            assert rc == 0, rc
+        finally:
+            self.L.gcref_set_noise(None, None, None)
 
     def compute_surface(self):
         self.L.gcref_compute_surface_all(self.h)

@@ -30,6 +30,15 @@ struct ObjectPool
 };
 
 #include "Containers.h"
+// The reference draws tree and cactus positions with rand() (Random.h:32-35, RandRange = min + rand() % n).  Tests may plug a
+// stream in (gcref_set_noise): rand() then returns draw % 1248 — 1248 = lcm of every n the generators use (3, 4, 26, 32), so
+// rand() % n equals draw % n and the reference's own placement code reproduces the host producer's per-column stream.  Without a
+// stream it is the C library's rand().
+static int (*const g_libc_rand)(void) = rand;
+static uint32_t (*g_rng_next)(uint64_t*) = nullptr;
+static uint64_t g_rng_state = 0;
+static int gcref_rand() { return g_rng_next ? (int)(g_rng_next(&g_rng_state) % 1248u) : g_libc_rand(); }
+#define rand gcref_rand
 #include "Random.h"
 
 struct UI { int unused; };
@@ -266,6 +275,52 @@ int gcref_generate(GcRefWorld* w, int kind)
         else if (kind == 3) GenerateGridTerrain(w->world, g);
         else if (kind == 4) GenerateVoidTerrain(w->world, g);
         else if (kind == 8) GenerateDungeon(w->world, g);
+        else return -1;
+    }
+    return 0;
+}
+
+// ---- the noise terrains over a plugged-in noise field ----
+// `fn`: float (*)(uint32_t seed, int field, int octaves, float x, float y, float z) — gamecraft_b200/worldgen's gcw_noise.  The
+// generators set one seed for all their fields; the host producer keeps its fields apart by an offset on the seed (biome + 101,
+// billow + 202, ridged + 303, 3-D fBm + 404), which is put back here from what the generator asked for.
+typedef float (*GcwNoiseFn)(uint32_t, int, int, float, float, float);
+static GcwNoiseFn g_gcw_noise = nullptr;
+static float NoiseBridge(int seed, int type, int ftype, int octaves, int dims, float x, float y, float z)
+{
+    const bool fractal = type == (int)FastNoiseSIMD::SimplexFractal;
+    if (dims == 3) return g_gcw_noise((uint32_t)seed + 404u, 4, octaves, x, y, z);
+    if (!fractal) return g_gcw_noise((uint32_t)seed + 101u, 0, 1, x, z, 0.0f);                         // plain simplex: the biome field
+    if (ftype == (int)FastNoiseSIMD::Billow) return g_gcw_noise((uint32_t)seed + 202u, 1, octaves, x, z, 0.0f);
+    if (ftype == (int)FastNoiseSIMD::RigidMulti) return g_gcw_noise((uint32_t)seed + 303u, 2, octaves, x, z, 0.0f);
+    return g_gcw_noise((uint32_t)seed + 101u, 3, octaves, x, z, 0.0f);                                  // 2-D fBm: the snow biome field
+}
+typedef uint64_t (*GcwColumnRngFn)(uint32_t, int32_t, int32_t);
+static GcwColumnRngFn g_column_rng = nullptr;
+void gcref_set_noise(void* fn, void* column_rng, void* rng_next)
+{
+    g_gcw_noise = (GcwNoiseFn)fn;
+    FastNoiseSIMD::hook() = fn ? NoiseBridge : nullptr;
+    g_column_rng = (GcwColumnRngFn)column_rng;
+    g_rng_next = (uint32_t (*)(uint64_t*))rng_next;
+}
+void gcref_set_seed(GcRefWorld* w, int seed) { w->world->properties.seed = seed; }
+
+// The reference's five noise terrains (Generation.cpp:83-226, :228-369, :412-556, :558-645, :647-770) on every column, over the
+// plugged-in noise: 1 forest, 2 islands, 5 snow, 6 desert, 7 volcanic (the numbering of GC_GEN_*).  Trees and cacti come from
+// rand() as in the reference — the plugged-in per-column stream when there is one (see gcref_rand above).
+int gcref_generate_noise_terrain(GcRefWorld* w, int kind)
+{
+    if (!g_gcw_noise) return -2;
+    for (int i = 0; i < w->world->totalGroups; i++)
+    {
+        ChunkGroup* g = w->world->groups[i];
+        if (g_column_rng) g_rng_state = g_column_rng((uint32_t)w->world->properties.seed, g->pos.x, g->pos.z);   // the column's own stream
+        if (kind == 1) GenerateForestTerrain(w->world, g);
+        else if (kind == 2) GenerateIslandsTerrain(w->world, g);
+        else if (kind == 5) GenerateSnowTerrain(w->world, g);
+        else if (kind == 6) GenerateDesertTerrain(w->world, g);
+        else if (kind == 7) GenerateVolcanicTerrain(w->world, g);
         else return -1;
     }
     return 0;

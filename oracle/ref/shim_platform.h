@@ -134,6 +134,12 @@ public:
     void SetFractalGain(float) {}
     void SetFractalLacunarity(float) {}
 
+    // Tests may plug a noise field in (gcref_set_noise): the reference's own generator code then runs over it.  The hook gets
+    // what the generator configured (seed, noise type, fractal type, octaves), whether the set is a 2-D one (one layer) and the
+    // sample position in FastNoiseSIMD's convention: (start + index) * frequency * scale per axis.
+    typedef float (*Hook)(int seed, int type, int ftype, int octaves, int dims, float x, float y, float z);
+    static Hook& hook() { static Hook h = nullptr; return h; }
+
     float* GetNoiseSet(int xs, int ys, int zs, int sx, int sy, int sz, float scale = 1.0f)
     {
         float* set = (float*)malloc(sizeof(float) * (size_t)sx * sy * sz);
@@ -141,7 +147,10 @@ public:
         for (int x = 0; x < sx; x++)
             for (int y = 0; y < sy; y++)
                 for (int z = 0; z < sz; z++)
-                    set[i++] = Smooth((xs + x) * freq * scale, (ys + y) * freq * scale, (zs + z) * freq * scale);
+                {
+                    const float px = (xs + x) * freq * scale, py = (ys + y) * freq * scale, pz = (zs + z) * freq * scale;
+                    set[i++] = hook() ? hook()(seed, (int)type, (int)ftype, octaves, sy == 1 ? 2 : 3, px, py, pz) : Smooth(px, py, pz);
+                }
         return set;
     }
     static void FreeNoiseSet(float* s) { free(s); }

@@ -114,3 +114,42 @@ def test_volcanic_rules():
     solid = col != 0
     assert (solid[:, :13, :]).all()                                    # everything up to the lava level is filled
     assert not (col[:, 13:, :] == 21).any()
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,seed,origin,radius,falloff", [
+    ("forest", 1337, (-2, -3), 2**31 - 1, None), ("forest", 7, (-2, -2), 75, 30), ("islands", 4242, (-3, -2), 90, 40),
+    ("islands", 8, (3, -4), 2**31 - 1, None), ("snow", 11, (-2, -2), 2**31 - 1, None), ("snow", 3, (-3, -2), 85, 30),
+    ("desert", 5, (-2, -2), 2**31 - 1, None), ("desert", 6, (-3, -2), 75, 20), ("volcanic", 9, (-2, -3), 80, 25),
+    ("volcanic", 2, (-2, -2), 2**31 - 1, None)])
+def test_reference_generator_code_over_this_project_s_noise(kind, seed, origin, radius, falloff):
+    """The five noise terrains, pinned to the reference's own CODE: GenerateForest / Islands / Snow / Desert / VolcanicTerrain run
+    from the reference's sources (oracle/_ref) over this project's noise fields and random stream — gcw_noise plugged into the
+    FastNoiseSIMD stand-in, the producer's per-column stream plugged in under rand() (RandRange = min + rand() % n, Random.h:32-35)
+    — with the same seed, world position and island, and EVERY block equals the host producer's: heights, the biome blend, the
+    island fall-off, sea levels, grass / dirt / snow / sand / obsidian, water / ice / lava, the snow biome's sea-level layer
+    inside taller ground, stone pockets (including the reference's reading of its 3-D noise set with a stride of maxY where the
+    set has maxY + 1 layers, Generation.cpp:16-18 against :157-161), trees and cacti with the reference's draw order.  What stays
+    unpinned is what cannot be pinned here: the values FastNoiseSIMD and MSVC's rand() would have produced."""
+    size = 5
+    fo = (radius - 64) if falloff is None else falloff
+    host = util.HostWorld(size, size, origin=origin).generate(kind, seed, radius=radius, falloff=fo)
+    r = ob.RefWorld(size=size, seed=seed, radius=radius, falloff=fo)
+    r.set_origin(*origin)
+    r.generate_noise_terrain(kind, seed)
+    got = util.HostWorld(size, size)
+    r.download(got)
+    r.close()
+    diff = got.blocks != host.blocks
+    assert not diff.any(), "%d cells differ from the reference's own %s generator" % (int(diff.sum()), kind)
+    assert int((host.blocks != 0).sum()) > 100000                              # the comparison is not vacuous
+    ids = set(np.unique(host.blocks).tolist())
+    assert {"forest": {1, 2, 9, 10}, "islands": {1, 2, 8}, "snow": {2, 8, 12}, "desert": {5, 16}, "volcanic": {19, 21}}[kind] <= ids
+    # with the C library's rand() instead of the producer's stream only the decorations differ
+    r = ob.RefWorld(size=size, seed=seed, radius=radius, falloff=fo)
+    r.set_origin(*origin)
+    r.generate_noise_terrain(kind, seed, own_random=False)
+    r.download(got)
+    r.close()
+    deco = np.isin(got.blocks, (9, 10, 16)) | np.isin(host.blocks, (9, 10, 16))
+    assert not ((got.blocks != host.blocks) & ~deco).any()
