@@ -565,7 +565,11 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    workload = args.workload or "forest4096"
+    # this arm's configuration at --gpus N: forest4096 at N = 1, forest65536 (BASELINE config 5) at N > 1.  The CPU is given a
+    # bounded sample of it: for forest65536 the 32 x 32 meshed columns at the centre of the same world (same generator, seed and
+    # world-space noise: forest4096's window is that cut) — a full 65 536-chunk step would take the host most of a second
+    named = args.workload or ("forest4096" if args.gpus <= 1 else "forest65536")
+    workload = "forest4096" if named == "forest65536" else ("islands4096" if named == "islands65536" else named)
     host, coords, gen_s = make_world(workload, 0, 1)
     threads = os.cpu_count() or 1
     from oracle import binding as ob
@@ -583,18 +587,31 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "chunks_meshed_per_s", "value": value, "unit": "chunks/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * med, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(workload, 1, host, coords),
+        "scaling": "strong" if named in STRONG else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": reference_arm_config(named, workload, args.gpus, host, coords),
         "quads_per_s": q / args.steps / med,
         "step_ms": {"median": 1e3 * med, "best": 1e3 * best, "worst": 1e3 * worst, "mean": 1e3 * mean,
                     "note": "value = chunks / median step; each step spawns its workers (one per host thread, pinned to the process's CPUs in turn)"},
         "best_step_chunks_per_s": n / best, "mean_chunks_per_s": n / mean,
         "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": kind,
-                         "sample": "every step = the full %d-chunk list on %d host threads" % (n, threads)},
+                         "sample": ("every step = the full %d-chunk list on %d host threads" % (n, threads)) if named == workload else
+                                   ("every step = %d chunks of %s (the 32 x 32 meshed columns at the centre of its world) on %d host threads" % (n, named, threads))},
         "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def reference_arm_config(named, sampled, n_gpus, host, coords):
+    """`config` of the reference arm: this arm's configuration at the same --gpus (so the two lines name one workload), with the
+    CPU's bounded sample spelled out when it is a cut of it."""
+    if named == sampled:
+        return workload_config(sampled, 1, host, coords)
+    kind, mx, mz, seed, radius = WORKLOADS[named]
+    rows = rows_per_rank(named, max(n_gpus, 1))
+    return {"workload": named, "world": kind, "seed": seed, "chunks_per_gpu": mx * rows * 4, "window_columns_per_gpu": [mx + 4, rows + 4],
+            "chunk_voxels": "32x64x32", "parallelism": "z-slab per GPU (the GPU arm); the CPU arm runs on the host's cores",
+            "cpu_sample": {"workload": sampled, "chunks": int(len(coords)), "window_columns": [host.size_x, host.size_z]}}
 
 
 def workload_config(workload, n_gpus, host, coords, exchange=None):
