@@ -396,10 +396,24 @@ def stream_path_leg(ctx, batch, host, coords, total_quads, workload, gen_s):
     got = HostWorld(host.size_x, host.size_z)
     lw.download(got, blocks=True, sun=False, light=False, surface=True)
     same = bool(np.array_equal(got.blocks, host.blocks)) and bool(np.array_equal(got.surface, host.surface))
+    # every biome of the reference (Environment.cpp:83-143) on the same window: generate (block ids + surface map), ms per window
+    biomes = {}
+    try:
+        for b in ("forest", "islands", "snow", "desert", "volcanic", "flat", "grid", "void", "dungeon"):
+            rb = 2048 if b == "islands" else (INT_MAX if b != "grid" else 512)
+            lw.generate(b, seed, origin=host.origin, radius=rb)
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                lw.generate(b, seed, origin=host.origin, radius=rb)
+            ctx.synchronize()
+            biomes[b] = 1e3 * (time.perf_counter() - t0) / 3
+    except Exception as err:                                  # (a leg of the line, never the line itself)
+        biomes["error"] = str(err)
     lw.close()
     n_cols = host.size_x * host.size_z
     return {"metric": "chunks_meshed_per_s", "value": len(coords) / sec, "unit": "chunks/s", "ms_per_step": 1e3 * sec, "steps": k,
-            "generate_ms": 1e3 * gen_sec, "columns_generated_per_s": n_cols / gen_sec,
+            "generate_ms": 1e3 * gen_sec, "columns_generated_per_s": n_cols / gen_sec, "generate_ms_per_biome": biomes,
             "host_producer": {"seconds": gen_s, "columns_per_s": n_cols / gen_s if gen_s else None, "cores": os.cpu_count(),
                               "what": "gamecraft_b200/worldgen on the host cores: generate + surface + light of the same window (the run's own input preparation)"},
             "blocks_identical_to_host_producer": same, "same_quads_as_host_prepared_world": bool(int(q) == int(total_quads)),
