@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(32) gc_edit_apply_kernel(EditArgs a)
     {
         __syncwarp();
         // ComputeSurfaceAt (Lighting.cpp:5-17): highest non-AIR y in 0..254, plus one; the warp looks at all 255 cells at once
+        // (replay mode: the replay computes it itself — RecomputeSunlight compares the old entry with the new one)
         int top = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++)
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(32) gc_edit_apply_kernel(EditArgs a)
         for (int d = 16; d > 0; d >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, d));
         if (lane == 0)
         {
-            a.w.surface[(size_t)col * 1024 + (z & 31) * 32 + (x & 31)] = (uint8_t)top;
+            if (!a.replay) a.w.surface[(size_t)col * 1024 + (z & 31) * 32 + (x & 31)] = (uint8_t)top;
             flag_around(a.w, a.dirty, x, y, z);                                             // FlagChunkForUpdate (World.cpp:507-546)
         }
     }
@@ -231,6 +232,19 @@ __global__ void __launch_bounds__(256) gc_edit_diff_kernel(EditArgs a)
 
 __global__ void gc_edit_next_kernel(EditArgs a) { a.state[EP_CURSOR] += 1; }
 
+// RecomputeLight as the reference runs it, on one thread: the queues are sequential by definition (relight_core.cuh)
+__global__ void __launch_bounds__(32) gc_edit_replay_kernel(EditArgs a)
+{
+    if (threadIdx.x != 0 || a.state[ES_SKIP]) return;
+    const GcBlockEdit e = a.edits[a.state[EP_CURSOR]];
+    RelightWorld w;
+    w.blocks = a.blocks_rw; w.sun = a.w.sun; w.light = a.w.light; w.surface = a.w.surface;
+    w.step = a.w.rules->step; w.emitted = a.w.rules->emitted; w.vert_table = a.vert_table; w.dirty = a.dirty;
+    w.size_x = a.w.size_x; w.size_z = a.w.size_z;
+    RelightQueue qa = { a.queue_a, 0, 0, 0 }, qb = { a.queue_b, 0, 0, 0 };
+    rl_recompute_light(w, e.wx, e.wy, e.wz, qa, qb);
+}
+
 __global__ void __launch_bounds__(256) gc_edit_list_kernel(LightWorld w, uint8_t* dirty, GcChunkCoord* out, uint32_t* n_out)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,6 +273,16 @@ cudaError_t launch_edit(const EditArgs& a, cudaStream_t s)
         if (e != cudaSuccess) return e;
     }
     gc_edit_diff_kernel<<<grid, 256, 0, s>>>(a);
+    gc_edit_next_kernel<<<1, 1, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_edit_replay(const EditArgs& a, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(a.state, 0, kEditStateWords * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    gc_edit_apply_kernel<<<1, 32, 0, s>>>(a);
+    gc_edit_replay_kernel<<<1, 32, 0, s>>>(a);
     gc_edit_next_kernel<<<1, 1, 0, s>>>(a);
     return cudaGetLastError();
 }

@@ -10,6 +10,7 @@
 #include "../../include/gcmesh.h"
 #include "gclight_kernel.cuh"
 #include "gcmesh_kernel.cuh"
+#include "relight_core.cuh"
 
 namespace gc
 {
@@ -39,12 +40,19 @@ struct EditArgs
     uint8_t* save;                // 2 x kEditBoxCells: effective sunlight, blockLight before the edit
     uint32_t* sun_list;           // kEditBoxCells each
     uint32_t* light_list;
+    // GC_WORLD_EDIT_REPLAY: the reference's own queues replayed node for node (relight_core.cuh) instead of the box refill
+    int32_t replay;
+    uint64_t* queue_a;            // kRelightQueueNodes entries each
+    uint64_t* queue_b;
 };
 
 // The kernels of one edit — the one state[EP_CURSOR] points at, which the last kernel advances — enqueued back to back
 // on `s`.  Nothing in the argument list depends on the edit, so the sequence can be captured once into a CUDA graph and
 // replayed per edit.
 cudaError_t launch_edit(const EditArgs& a, cudaStream_t s);
+// The same edit with RecomputeLight (Lighting.cpp:283-449) replayed as the reference runs it: apply (decisions, store, overflow,
+// the 27 flags — the surface entry is left to the replay, which needs the old one) -> one thread walking the queues -> cursor step.
+cudaError_t launch_edit_replay(const EditArgs& a, cudaStream_t s);
 // dirty bricks of the pre-processed (non-edge) columns -> coords (unordered), count in *n_out; clears the flags
 cudaError_t launch_edit_list(const LightWorld& w, uint8_t* dirty, GcChunkCoord* out, uint32_t* n_out, cudaStream_t s);
 }  // namespace gc

@@ -122,6 +122,8 @@ struct GcWorld
     unsigned long long upload_bytes;   // host -> device bytes the last sparse upload / gcmesh_mesh_host call moved
     bool surface_bounds_blocks;        // GC_WORLD_SURFACE_BOUNDS_BLOCKS
     bool surface_bounds_mesh;          // GC_WORLD_SURFACE_BOUNDS_MESH
+    bool edit_replay;                  // GC_WORLD_EDIT_REPLAY
+    uint64_t* d_edit_queues;           // two queues of kRelightQueueNodes positions (replay mode)
     int copy_run;                      // GC_WORLD_COPY_RUN (0: default)
     int16_t* col_smax;                 // host, per column: highest surface entry (-1: not computed in this scan)
     // light fill scratch (grown on demand)
@@ -458,7 +460,7 @@ int gcmesh_world_destroy(GcWorld* w)
             if (w->halo_ipc[d][k]) cudaIpcCloseMemHandle(w->halo_ipc[d][k]);
     cudaFree(w->d_halo_flags);
     cudaFree(w->d_gen_height); cudaFree(w->d_gen_max_y);
-    cudaFree(w->d_vert_table); cudaFree(w->d_edit_dirty); cudaFree(w->d_edit_state); cudaFree(w->d_edit_save);
+    cudaFree(w->d_vert_table); cudaFree(w->d_edit_dirty); cudaFree(w->d_edit_state); cudaFree(w->d_edit_save); cudaFree(w->d_edit_queues);
     cudaFree(w->d_edit_sun_list); cudaFree(w->d_edit_light_list); cudaFree(w->d_edits); cudaFree(w->d_edit_status); cudaFree(w->d_edit_coords);
     if (w->edit_graph) cudaGraphExecDestroy(w->edit_graph);
     if (w->h_edit_coords) cudaFreeHost(w->h_edit_coords);
@@ -860,6 +862,7 @@ int gcmesh_world_set_option(GcWorld* w, int option, int value)
     if (!w) return fail(GC_ERR_ARG, "world is null");
     if (option == GC_WORLD_SURFACE_BOUNDS_BLOCKS) { w->surface_bounds_blocks = value != 0; return GC_OK; }
     if (option == GC_WORLD_SURFACE_BOUNDS_MESH) { w->surface_bounds_mesh = value != 0; return GC_OK; }
+    if (option == GC_WORLD_EDIT_REPLAY) { w->edit_replay = value != 0; return GC_OK; }
     if (option == GC_WORLD_COPY_RUN) { if (value < 0) return fail(GC_ERR_ARG, "run length must not be negative"); w->copy_run = value; return GC_OK; }
     return fail(GC_ERR_ARG, "unknown world option");
 }
@@ -1309,10 +1312,16 @@ int gcmesh_world_set_blocks(GcWorld* w, const GcBlockEdit* edits, int n, int32_t
     a.w = light_world(w); a.blocks_rw = w->d_blocks; a.tables = ctx->d_tables; a.vert_table = w->d_vert_table;
     a.edits = w->d_edits; a.status = w->d_edit_status; a.dirty = w->d_edit_dirty; a.state = w->d_edit_state;
     a.save = w->d_edit_save; a.sun_list = w->d_edit_sun_list; a.light_list = w->d_edit_light_list;
+    a.replay = w->edit_replay ? 1 : 0; a.queue_a = nullptr; a.queue_b = nullptr;
+    if (w->edit_replay)
+    {
+        if (!w->d_edit_queues) GC_CUDA(cudaMalloc(&w->d_edit_queues, 2 * sizeof(uint64_t) * (size_t)kRelightQueueNodes));
+        a.queue_a = w->d_edit_queues; a.queue_b = w->d_edit_queues + kRelightQueueNodes;
+    }
     // One edit is 19 tiny launches whose arguments never change (the kernels find the edit through a device-side cursor):
     // captured once per world into a CUDA graph and replayed per edit.  GCMESH_EDIT_GRAPH=0, a stream that cannot be
     // captured (the legacy default stream) or a failed capture fall back to plain launches of the same sequence.
-    if (!w->edit_graph_tried)
+    if (!w->edit_graph_tried && !w->edit_replay)
     {
         w->edit_graph_tried = true;
         const char* env = getenv("GCMESH_EDIT_GRAPH");
@@ -1336,7 +1345,8 @@ int gcmesh_world_set_blocks(GcWorld* w, const GcBlockEdit* edits, int n, int32_t
         GC_CUDA(cudaMemsetAsync(w->d_edit_state + EP_CURSOR, 0, sizeof(uint32_t), s));
         for (int i = 0; i < count; i++)
         {
-            if (w->edit_graph) GC_CUDA(cudaGraphLaunch(w->edit_graph, s));
+            if (w->edit_replay) GC_CUDA(launch_edit_replay(a, s));
+            else if (w->edit_graph) GC_CUDA(cudaGraphLaunch(w->edit_graph, s));
             else GC_CUDA(launch_edit(a, s));
         }
         if (status) GC_CUDA(cudaMemcpyAsync(status + first, w->d_edit_status, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, s));

@@ -30,6 +30,7 @@ CHUNK_HALO_MISSING = 4
 WORLD_SURFACE_BOUNDS_BLOCKS = 1      # GC_WORLD_SURFACE_BOUNDS_BLOCKS
 WORLD_COPY_RUN = 2                   # GC_WORLD_COPY_RUN
 WORLD_SURFACE_BOUNDS_MESH = 3        # GC_WORLD_SURFACE_BOUNDS_MESH
+WORLD_EDIT_REPLAY = 4                # GC_WORLD_EDIT_REPLAY
 BATCH_UNCAPPED = 1                   # GC_BATCH_UNCAPPED
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

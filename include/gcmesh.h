@@ -150,9 +150,14 @@ int gcmesh_world_upload_sparse(GcWorld* world, const uint16_t* blocks, const uin
  * kernel then takes a brick lying wholly at or above its column's highest surface entry for AIR — an empty mesh — from the
  * 1 KB surface map, without reading the brick's 128 KB of block ids (the top brick's layer y = 255 is still looked at).
  * With the option off (default) the mesher is a function of the block ids alone, whatever the surface map says.
+ * GC_WORLD_EDIT_REPLAY (default 0): gcmesh_world_set_blocks relights by replaying the reference's own RecomputeLight
+ * (Lighting.cpp:283-449) node for node — the same FIFO queues, neighbour order and comparisons, on one device thread — instead
+ * of refilling the box around the edit: block ids, the surface map (including the entry the reference leaves stale when a column
+ * empties), both light arrays and the set of chunks flagged for rebuild come out byte for byte as the reference's SetBlock leaves
+ * them (also where its removal queues stop short of a from-scratch fill).  Slower per edit than the default; see below.
  * GC_WORLD_COPY_RUN (default 0 = 4): sparse uploads move the same brick array of at least this many consecutive columns
  * with one strided copy-engine copy; shorter runs are pulled by a GPU kernel out of pinned host memory (a huge value: always). */
-enum { GC_WORLD_SURFACE_BOUNDS_BLOCKS = 1, GC_WORLD_COPY_RUN = 2, GC_WORLD_SURFACE_BOUNDS_MESH = 3 };
+enum { GC_WORLD_SURFACE_BOUNDS_BLOCKS = 1, GC_WORLD_COPY_RUN = 2, GC_WORLD_SURFACE_BOUNDS_MESH = 3, GC_WORLD_EDIT_REPLAY = 4 };
 int gcmesh_world_set_option(GcWorld* world, int option, int value);
 /* World-space column (ChunkGroup::pos, World.h) of window column (0, 0).  Only region records depend on it (gcmesh_world_encode_rle). */
 int gcmesh_world_set_origin(GcWorld* world, int origin_cx, int origin_cz);
@@ -279,6 +284,8 @@ int gcmesh_world_generate(GcWorld* world, int kind, uint32_t seed, int origin_cx
  *   - FlagChunkForUpdate (World.cpp:507-546): the chunks around the edited cell, plus every chunk that has a cell whose
  *     block, blockLight or effective sunlight changed inside its one-voxel halo.  Chunks outside the list mesh to the
  *     bytes they meshed to before.
+ * With GC_WORLD_EDIT_REPLAY the last two items are the reference's to the letter instead: its incremental queues, and
+ * every built chunk a queue touched flagged (a superset of the chunks whose mesh changes).
  * Edits are applied in order; the caller's player-overlap test (World.cpp:552) stays with the caller. */
 typedef struct GcBlockEdit
 {

@@ -176,3 +176,16 @@ extern "C" int gcemu_build_chunk(int size_x, int size_z, const uint16_t* blocks,
     }
     return 0;
 }
+
+
+// ---- the relight replay (gamecraft_b200/csrc/relight_core.cuh) on the host: the device kernel runs the same functions ----
+#include "../../gamecraft_b200/csrc/relight_core.cuh"
+
+extern "C" void gcemu_recompute_light(int size_x, int size_z, const uint16_t* blocks, uint8_t* sun, uint8_t* light, uint8_t* surface,
+                                      const uint8_t* step, const uint8_t* emitted, const int32_t* vert_table, uint8_t* dirty, int x, int y, int z)
+{
+    gc::RelightWorld w = { blocks, sun, light, surface, step, emitted, vert_table, dirty, size_x, size_z };
+    std::vector<uint64_t> a((size_t)gc::kRelightQueueNodes), b((size_t)gc::kRelightQueueNodes);
+    gc::RelightQueue qa = { a.data(), 0, 0, 0 }, qb = { b.data(), 0, 0, 0 };
+    gc::rl_recompute_light(w, x, y, z, qa, qb);
+}

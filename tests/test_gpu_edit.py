@@ -337,3 +337,47 @@ def test_device_edits_against_the_reference_s_own_setblock(ctx, kind, seed, kw, 
         assert int(short.sum()) < 100
         assert int((ed.astype(np.int16) - ez)[short].max(initial=0)) <= 1
     r.close(); world.close()
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref/libgcref.so not built (no reference tree)")
+@pytest.mark.parametrize("kind,seed,kw", [("forest", 2, {}), ("islands", 8, dict(radius=90, falloff=50)), ("mixed", 3, dict(radius=90, falloff=50))])
+def test_edit_replay_mode_equals_the_reference_to_the_byte(ctx, kind, seed, kw):
+    """GC_WORLD_EDIT_REPLAY: gcmesh_world_set_blocks replays the reference's own RecomputeLight node for node on the device.
+    Against the reference's SetBlock compiled verbatim, edit after edit (single edits and batches): block ids, the surface map,
+    BOTH RAW LIGHT ARRAYS and the set of chunks flagged for rebuild (the reference's pendingUpdate set over the meshed chunks) are
+    identical — on islands too, where the default relight (the from-scratch fill) differs from the reference by design, and with
+    weak and strong emitters mixed.  The flagged chunks then mesh to the oracle's bytes of that state."""
+    from gamecraft_b200 import mesher
+    from test_edit_oracle import start
+
+    size = 5
+    z, r = start(kind, seed, size, **kw)
+    world = mesher.World(ctx, size, size).upload(z).set_option(mesher.WORLD_EDIT_REPLAY, 1)
+    mesher.rebuild_chunks(world, z.interior_chunks())
+    rng = np.random.default_rng(seed)
+    d = util.HostWorld(size, size)
+    applied = 0
+    for step in range(24):
+        edits = [random_edit(rng, z, size) for _ in range(1 if step % 4 else 3)]
+        if step % 6 == 5:
+            edits = [e[:3] + (0,) for e in edits]                              # take blocks (emitters among them) away again
+        changed = [r.set_block(*e) for e in edits]
+        status, rebuild = world.set_blocks(edits)
+        assert [s == APPLIED for s in status.tolist()] == changed
+        applied += sum(changed)
+        r.download(z)
+        pending = r.pending_updates(clear=True)                                # (size_z, size_x, 4)
+        world.download(d, blocks=True)
+        where = "%s step %d %r" % (kind, step, edits)
+        assert np.array_equal(d.blocks, z.blocks), where
+        assert np.array_equal(d.surface, z.surface), where
+        assert np.array_equal(d.sun, z.sun), "%s: %d sunlight bytes differ" % (where, int((d.sun != z.sun).sum()))
+        assert np.array_equal(d.light, z.light), "%s: %d blockLight bytes differ" % (where, int((d.light != z.light).sum()))
+        want = sorted((cx, cy, cz) for cz in range(1, size - 1) for cx in range(1, size - 1) for cy in range(4) if pending[cz, cx, cy])
+        assert sorted(tuple(c) for c in rebuild.tolist()) == want, where
+        if len(rebuild):
+            orc = ob.OracleWorld(z)
+            for c, m in zip(rebuild.tolist(), mesher.rebuild_chunks(world, rebuild)):
+                util.assert_same_mesh(m, orc.build_chunk(*c), "%s chunk %r" % (where, c))
+    assert applied >= 12
+    r.close(); world.close()
