@@ -448,6 +448,22 @@ def edit_path_leg(ctx, world, host, args):
         if i >= 2:                                            # the first calls allocate the scratch
             t_edit.append(t1 - t0); t_total.append(t2 - t0); flagged.append(len(rebuild))
         applied += int(status[0] == mesher.EDIT_APPLIED)
+    # the same edits with GC_WORLD_EDIT_REPLAY: the reference's RecomputeLight replayed node for node on one device thread
+    t_replay, flagged_replay = [], []
+    try:
+        world.set_option(mesher.WORLD_EDIT_REPLAY, 1)
+        for i, (wx, wy, wz, old) in enumerate(spots + spots):
+            block = 0 if i < len(spots) else old
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            status, rebuild = world.set_blocks([(wx, wy, wz, block)])
+            t1 = time.perf_counter()
+            if i >= 2:
+                t_replay.append(t1 - t0); flagged_replay.append(len(rebuild))
+    except mesher.GcMeshError as err:
+        print("edit replay leg: %s" % err, file=sys.stderr)
+    finally:
+        world.set_option(mesher.WORLD_EDIT_REPLAY, 0)
     small.close()
     cpu = None
     if not args.no_cpu_baseline:
@@ -491,6 +507,9 @@ def edit_path_leg(ctx, world, host, args):
             cpu = {"unavailable": str(e)}
     return {"ms_per_edit": 1e3 * float(np.median(t_edit)), "ms_per_edit_and_remesh": 1e3 * float(np.median(t_total)),
             "edits": len(t_edit), "applied": applied, "chunks_flagged_per_edit": float(np.mean(flagged)), "cpu_reference": cpu,
+            "replay_mode": ({"ms_per_edit": 1e3 * float(np.median(t_replay)), "chunks_flagged_per_edit": float(np.mean(flagged_replay)),
+                             "what": "GC_WORLD_EDIT_REPLAY: byte-identical to the reference's RecomputeLight (its queues replayed on one device thread)"}
+                            if t_replay else None),
             "call": "gcmesh_world_set_blocks (one edit: a CUDA graph replay of 19 small kernels) + gcmesh_submit of the flagged chunks + "
                     "gcmesh_wait + gcmesh_batch_download"}
 
