@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(256) gc_surface_max_kernel(LightWorld w, const
     reinterpret_cast<uint32_t*>(w.surface + (size_t)col * 1024)[q] = best;
 }
 
-// ---- scan of every column cell up to maxY: candidate bit maps, emitters seeded ----
-// A warp owns one z-row of one column (lane = x) and walks up its cells, so a ballot is one word of a bit map: word
+// ---- scan of every column cell up to maxY: candidate bit maps, emitters seeded, sunlight started at its straight-down value ----
+// A warp owns one z-row of one column (lane = x) and walks down its cells, so a ballot is one word of a bit map: word
 // (slot * 2048 + z * 64 + y) = voxel index >> 5.
 //   sun_bits   bit x = the cell is a sunlight candidate (non-opaque, below its column's surface)
 //   opq_bits   bit x = the cell is opaque (rows the walk never reaches are air: the maps are cleared beforehand)
@@ -118,29 +118,42 @@ __global__ void __launch_bounds__(256) gc_light_scan_kernel(LightWorld w, uint32
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) top_w = max(top_w, __shfl_xor_sync(0xffffffffu, top_w, d));
     uint32_t n_cand = 0, n_seed = 0;
-    for (int y0 = 0; y0 <= top_w; y0 += 8)
+    // The walk goes DOWN the column and carries what each cell hands to the one below it (its value less its own lightStep,
+    // ScatterSunlight's rule; a sky cell of a pre-processed column reads 15): a candidate starts at the light that reaches it
+    // straight from above.  That is a value some path really delivers — a lower bound of the fixpoint, so the relaxation ends
+    // at the same values — and it is most of the fixpoint (open water, shafts, cave mouths): the sweeps that follow only move
+    // light sideways.  (The cell above the walk's first cell is sky and AIR — every surface entry lies below it — unless the
+    // walk starts at the world's top layer.)
+    const int st_air = w.rules->step[0];
+    int offer = (inner && st_air != 255 && (top_w | 7) < GC_WORLD_BLOCK_HEIGHT - 1) ? 15 - st_air : 0;
+    for (int y0 = top_w & ~7; y0 >= 0; y0 -= 8)
     {
         uint32_t id[8];
 #pragma unroll
         for (int k = 0; k < 8; k++)   // eight loads in flight per lane
-        {
-            const int y = min(y0 + k, GC_WORLD_BLOCK_HEIGHT - 1);
-            id[k] = w.blocks[((size_t)col * 4 + (y >> 6)) * kVox + x + 32 * ((y & 63) + 64 * z)] & 255u;
-        }
+            id[k] = w.blocks[((size_t)col * 4 + ((y0 + k) >> 6)) * kVox + x + 32 * (((y0 + k) & 63) + 64 * z)] & 255u;
 #pragma unroll
-        for (int k = 0; k < 8; k++)
+        for (int k = 7; k >= 0; k--)
         {
-            const int y = y0 + k;
-            if (y >= GC_WORLD_BLOCK_HEIGHT) break;                // (warp-uniform)
+            const int y = y0 + k;                                 // (<= 255: y0 is a multiple of eight below 256)
             const size_t slot = (size_t)col * 4 + (y >> 6);
             const uint32_t v = (uint32_t)(slot * kVox + x + 32 * ((y & 63) + 64 * z));
-            const bool opaque = w.rules->step[id[k]] == 255;
+            const int st = w.rules->step[id[k]];
+            const bool opaque = st == 255;
             const bool cand = y < s && !opaque;
             const uint32_t mo = __ballot_sync(0xffffffffu, opaque), mc = __ballot_sync(0xffffffffu, cand);
             if (lane == 0)
             {
                 if (mo) opq_bits[v >> 5] = mo;
                 if (mc) { sun_bits[v >> 5] = mc; sun_flag[slot] = 1; sun_unit[slot * 8 + (z >> 2)] = 1; n_cand += (uint32_t)__popc(mc); }
+            }
+            if (opaque) offer = 0;                                // neither holds nor passes light
+            else if (y >= s) offer = inner ? 15 - st : 0;         // sky (only the pre-processed columns' sky cells were ever queued)
+            else
+            {
+                const int val = offer > 1 ? offer : 0;            // (nothing at or below MIN_LIGHT is stored)
+                if (val) w.sun[v] = (uint8_t)val;
+                offer = val - st;
             }
             const uint32_t e = w.rules->emitted[id[k]];
             if (inner && y <= my && e > 1)   // CheckForBlockLight (Lighting.cpp:231-245); the arrays were cleared, so this is a max

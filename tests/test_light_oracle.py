@@ -83,3 +83,40 @@ def test_lantern_in_a_cave():
     assert at(light, 50, 20, 48) == 0                                   # stone is opaque: nothing stored
     assert int(sun.max()) == 0                                          # sealed: every stored sunlight value stays 0
     assert int((light > 0).sum()) == 27
+
+
+def _straight_down_start(w, surface):
+    """numpy model of what the device scan (gc_light_scan_kernel) stores before the relaxation: each candidate starts at the
+    light that reaches it straight from above — every cell hands its value less its own lightStep to the cell below it, a sky
+    cell of a pre-processed column reads 15, an opaque cell passes nothing."""
+    step, _ = ob.default_light_rules()
+    step = step.astype(np.int32)
+    nc = w.size_x * w.size_z
+    ids = (w.blocks.reshape(nc, 4, 32, 64, 32) & 255).transpose(0, 1, 3, 2, 4).reshape(nc, 256, 32, 32)
+    top = surface.reshape(nc, 32, 32).astype(np.int32)
+    cx, cz = np.arange(nc) % w.size_x, np.arange(nc) // w.size_x
+    inner = ((cx >= 1) & (cx < w.size_x - 1) & (cz >= 1) & (cz < w.size_z - 1))[:, None, None]
+    offer = np.zeros((nc, 32, 32), np.int32)
+    out = np.zeros((nc, 256, 32, 32), np.uint8)
+    for y in range(255, -1, -1):
+        st = step[ids[:, y]]
+        opaque = st == 255
+        val = np.where(offer > 1, offer, 0)
+        out[:, y] = np.where((y < top) & ~opaque, val, 0)
+        offer = np.where(opaque, 0, np.where(y >= top, np.where(inner, 15 - st, 0), val - st))
+    return out.reshape(nc, 4, 64, 32, 32).transpose(0, 1, 3, 2, 4).reshape(nc * 4, -1)
+
+
+@pytest.mark.parametrize("kind,seed", [("forest", 5), ("islands", 8), ("noise", 4), ("checker", 6), ("mixed", 3)])
+def test_straight_down_start_is_a_lower_bound_of_the_fill(kind, seed):
+    """The device fill starts its sunlight relaxation from the straight-down values instead of zero.  A max-relaxation from any
+    state at or below the fixpoint ends at the fixpoint, so all this needs is: never above the fill's value, anywhere."""
+    kw = dict(radius=90, falloff=50) if kind in ("islands", "mixed") else {}
+    w = util.HostWorld(5, 5, origin=(-2, -2) if kw else (0, 0)).generate(kind, seed, **kw)
+    surface = ob.compute_surface(w)
+    sun, _ = ob.light_fill(w, surface)
+    start = _straight_down_start(w, surface)
+    assert (start <= sun).all()
+    if kind == "islands":   # open water: most of the fill is the straight-down value
+        lit = sun > 0
+        assert ((start == sun) & lit).sum() > 0.8 * lit.sum()
